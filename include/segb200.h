@@ -1,0 +1,244 @@
+/*
+ * segb200.h -- C ABI of libsegb200.so: B200 (sm_100a) kernels for the
+ * segmentalist hot path (score every candidate segment embedding against every
+ * mixture component, then segment with dynamic programming).
+ *
+ * The reference (kamperh/segmentalist) has no FFI: its seams are duck-typed
+ * Python objects plus one Cython module.  Each entry point below names the
+ * reference code it replaces (paths relative to the reference's segmentalist/
+ * directory).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name starts with h_;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on
+ *     it unless stated;
+ *   - return value: 0 ok, <0 bad argument (SEGB_E_*), >0 a cudaError_t;
+ *     segb_last_error() gives the text;
+ *   - no CPU fallback exists: without a CUDA device every call fails.
+ *
+ * Layouts
+ *   X            [n_emb, D] row-major embeddings (components.X), float32 or float64
+ *   banded slot  (pos_off[u] + t - 1) * S + (l - 1)  <->  segment [t-l, t) of
+ *                utterance u, i.e. packed-triangular entry t(t-1)/2 + (t-l) of
+ *                utterances.py:59-65; S = band width (longest stored span)
+ *   bounds       [n_pos] uint8, bounds[pos_off[u] + j] = boundaries[u, j]
+ */
+#ifndef SEGB200_H
+#define SEGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGB_E_ARG        (-1)
+#define SEGB_E_UNSUPPORTED (-2)
+#define SEGB_E_NODEVICE   (-3)
+
+/* per-utterance DP status codes written to `status` */
+#define SEGB_DP_OK          0
+#define SEGB_DP_INFEASIBLE  1  /* back-tracking reached t == 0 (reference: undefined negative index) */
+#define SEGB_DP_EMPTY_SLICE 2  /* n_slices_min trimmed a window to nothing (reference: UB) */
+#define SEGB_DP_NAN         3
+
+#define SEGB_DP_FFBS           0  /* unigram_acoustic_wordseg.py:653-756 forward_backward */
+#define SEGB_DP_VITERBI_GMM    1  /* unigram_acoustic_wordseg.py:759-864 forward_backward_viterbi */
+#define SEGB_DP_VITERBI_KMEANS 2  /* kmeans_acoustic_wordseg.py:449-555 forward_backward_kmeans_viterbi */
+
+const char *segb_last_error(void);
+int segb_version(void);
+/* number of kernel launches issued by this library since load (bench "gpu_launches") */
+int64_t segb_launch_count(void);
+
+/* ------------------------------------------------------------------ corpus */
+
+/* Device view of Utterances (utterances.py:91-105) in banded form. */
+typedef struct {
+    int32_t n_utt;
+    int32_t S;                 /* band width */
+    int32_t N_max;             /* longest utterance (landmarks) */
+    int32_t n_slices_min;
+    int32_t n_slices_max;      /* 0 = unlimited, as in the reference */
+    int64_t n_pos;             /* sum of utterance lengths */
+    const int64_t *pos_off;    /* [n_utt + 1] */
+    const int32_t *seg_id;     /* [n_pos * S] embedding id or -1 (vec_ids) */
+    const double *seg_dur;     /* [n_pos * S] frames, NaN = unusable (durations) */
+    uint8_t *bounds;           /* [n_pos] current boundaries */
+    int32_t *tok_id;           /* [n_pos] embedding id of the token ENDING at this landmark, -1 if none */
+} segb_corpus;
+
+/* ------------------------------------------------------------------ DP (A5-A7) */
+
+/* Batched segmentation DP over n_utt independent utterances (warp per
+ * utterance).  Replaces the three fb_func implementations named above.
+ * scores: banded float64.  uniforms: utterance u reads uniforms[pos_off[u] + i]
+ * for its i-th back-sampled segment, unless u_counter != NULL, in which case
+ * the draws are taken from uniforms[*u_counter ...] and *u_counter is advanced
+ * (sequential Gibbs; n_utt must be 1).  alphas (optional) receives
+ * log_alphas / gammas.  utt_first selects a sub-range of the corpus.          */
+int segb_dp_banded(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const double *scores,
+                   int32_t mode, double log_p_continue, double anneal_temp,
+                   const double *uniforms, int64_t *u_counter,
+                   uint8_t *bounds_out, double *log_prob, double *alphas,
+                   int32_t *n_draws, int32_t *status, void *stream);
+
+/* ------------------------------------------------------------------ fixed-variance FBGMM (A1-A4, A9) */
+
+/* Device view of GaussianComponentsFixedVar (gaussian_components_fixedvar.py:80-120)
+ * plus the FBGMM scalars (fbgmm.py:58-63).  The *T tables are [D, K_max]
+ * (component index fastest) so a warp scoring 32 components reads contiguous
+ * memory; mu_N = mu_N_num / prec_N is cached because log_post_pred (:247)
+ * recomputes that quotient for every item.                                     */
+typedef struct {
+    int32_t D, K_max;
+    int32_t x_is_f64;          /* dtype of X */
+    int64_t n_emb;
+    const void *X;
+    double *mu_N_numT;         /* [D, K_max] mu_N_numerators^T */
+    double *prec_NT;           /* [D, K_max] precision_Ns^T */
+    double *prec_predT;        /* [D, K_max] precision_preds^T */
+    double *mu_NT;             /* [D, K_max] mu_N_numerators / precision_Ns */
+    double *log_prod_prec_pred;/* [K_max] */
+    int32_t *counts;           /* [K_max] */
+    int32_t *assignments;      /* [n_emb] */
+    int32_t *K;                /* [1] active components */
+    int64_t *n_total;          /* [1] sum(counts) */
+    const double *precision;   /* [D] 1/var */
+    const double *mu_0;        /* [D] */
+    const double *precision_0; /* [D] 1/var_0 */
+    double alpha, lms;
+    double sum_log_precision_0;/* sum_d log(precision_0[d]) (_cython_utils.sum_log, :228) */
+} segb_fixedvar;
+
+/* add_item (:153-170) / del_item (:172-188, incl. del_component :190-221) for a
+ * list of items, applied strictly in list order by one thread block.
+ * ks[i] > K is clamped to K as FBGMM does before add_item (fbgmm.py:459-460).
+ * relabel_ids/relabel_n: the set of item ids whose assignment may equal the
+ * moved component (the reference scans all of `assignments`; pass NULL/0 for
+ * that behaviour, or the corpus tok_id table to scan only live tokens).      */
+int segb_fixedvar_add_items(const segb_fixedvar *m, const int32_t *ids, const int32_t *ks, int32_t n,
+                            void *stream);
+int segb_fixedvar_del_items(const segb_fixedvar *m, const int32_t *ids, int32_t n,
+                            const int32_t *relabel_ids, int64_t relabel_n, void *stream);
+
+/* log_post_pred(i) (:242-253) for k < K and log_prior(i) (:224-231) for one item:
+ * out[0..K_max): active slots get the posterior predictive, the rest the prior. */
+int segb_fixedvar_log_pred_row(const segb_fixedvar *m, int32_t id, double *out, void *stream);
+
+/* FBGMM.log_marg_i (fbgmm.py:256-285) for n items, optionally followed by the
+ * duration scaling of get_vec_embed_log_probs (unigram_acoustic_wordseg.py:474-511):
+ *   out[i] = log_marg_i(ids[i]) * durs[i]**time_power_term + wip
+ * with -inf where ids[i] == -1 or durs[i] is NaN.  durs == NULL -> raw log_marg_i. */
+int segb_fixedvar_log_marg(const segb_fixedvar *m, const int32_t *ids, const double *durs, int64_t n,
+                           double time_power_term, double wip, double *out, void *stream);
+
+/* gibbs_sample_inside_loop_i (fbgmm.py:422-463; mode 0) or map_assign_i
+ * (:465-494; mode 1) for a list of items in order; each assignment sees the
+ * statistics left by the previous one.  Draws come from uniforms[*u_counter..]. */
+int segb_fixedvar_assign_items(const segb_fixedvar *m, const int32_t *ids, int32_t n, int32_t mode,
+                               double anneal_temp, const double *uniforms, int64_t *u_counter,
+                               int32_t *ks_out, void *stream);
+
+/* UnigramAcousticWordseg.gibbs_sample_i (unigram_acoustic_wordseg.py:252-360)
+ * for the utterances listed in h_order (HOST array), strictly sequential:
+ * remove the utterance's tokens, score every candidate segment, run the DP
+ * (fb_mode SEGB_DP_FFBS or SEGB_DP_VITERBI_GMM), assign the new tokens.
+ * scratch_scores: [N_max * S] doubles.  log_probs: [n_order] (device) receives
+ * the per-utterance log_prob; status [n_order].  No host synchronisation.     */
+int segb_gibbs_sweep_fixedvar(const segb_fixedvar *m, const segb_corpus *c, const int32_t *h_order,
+                              int32_t n_order, int32_t fb_mode, double time_power_term, double wip,
+                              double anneal_temp, int32_t anneal_gibbs_am,
+                              const double *uniforms, int64_t *u_counter, double *scratch_scores,
+                              double *log_probs, int32_t *status, void *stream);
+
+/* ------------------------------------------------------------------ k-means (A10-A12) */
+
+/* Device view of KMeansComponents (kmeans_components.py:18-91). `means` has X's
+ * dtype; meansT is its [D, K_max] transpose used by the scoring kernels.      */
+typedef struct {
+    int32_t D, K_max;
+    int32_t x_is_f64;
+    int64_t n_emb;
+    const void *X;
+    double *mean_num;          /* [K_max, D] mean_numerators */
+    void *means;               /* [K_max, D] X dtype */
+    void *meansT;              /* [D, K_max] X dtype */
+    const void *random_means;  /* [K_max, D] X dtype */
+    int32_t *counts;           /* [K_max] */
+    int32_t *assignments;      /* [n_emb] */
+    int32_t *K;                /* [1] */
+} segb_kmeans;
+
+/* neg_sqrd_norm(i) (kmeans_components.py:225-226) over all K_max rows, in X's
+ * dtype and NumPy's pairwise summation order (bit-exact).                     */
+int segb_kmeans_neg_sqrd_norm_row(const segb_kmeans *m, int32_t id, void *out, void *stream);
+
+/* max / first argmax of neg_sqrd_norm for n items (:228-232).  ids[i] == -1 ->
+ * best_val = -inf, best_k = -1.  best_val has X's dtype.                      */
+int segb_kmeans_best(const segb_kmeans *m, const int32_t *ids, int64_t n, void *best_val,
+                     int32_t *best_k, void *stream);
+
+/* add_item (:93-111, with the k > K clamp) / del_item (:113-132) /
+ * clean_components (:263-266), list order, one thread block.                  */
+int segb_kmeans_add_items(const segb_kmeans *m, const int32_t *ids, const int32_t *ks, int32_t n,
+                          void *stream);
+int segb_kmeans_del_items(const segb_kmeans *m, const int32_t *ids, int32_t n, void *stream);
+int segb_kmeans_clean(const segb_kmeans *m, const int32_t *relabel_ids, int64_t relabel_n, void *stream);
+/* KMeans.fit M-step (kmeans.py:149-151): del_item(ids[i]); add_item(ids[i], ks[i]) in list order. */
+int segb_kmeans_move_items(const segb_kmeans *m, const int32_t *ids, const int32_t *ks, int32_t n, void *stream);
+
+/* get_vec_embed_neg_len_sqrd_norms (kmeans_acoustic_wordseg.py:334-351) from
+ * per-embedding best values: scores[slot] = (double)best_val[seg_id[slot]] *
+ * seg_dur[slot] + wip, -inf where absent.  Covers landmark positions
+ * [pos_first, pos_first + n_positions) (host-known: pos_off of the utterance range). */
+int segb_kmeans_band_scores(const segb_kmeans *m, const segb_corpus *c, int64_t pos_first, int64_t n_positions,
+                            const void *best_val, double wip, double *scores, void *stream);
+
+/* SegmentalKMeansWordseg.segment_i (kmeans_acoustic_wordseg.py:225-332) for the
+ * utterances in h_order (HOST array), strictly sequential with online mean
+ * updates.  totals [n_order] receives sum_neg_len_sqrd_norm per utterance.    */
+int segb_kmeans_segment_sweep(const segb_kmeans *m, const segb_corpus *c, const int32_t *h_order,
+                              int32_t n_order, double wip, double *scratch_scores,
+                              float *scratch_best, int32_t *scratch_arg,
+                              double *totals, int32_t *status, void *stream);
+
+/* Frozen-state sweep pieces (new batch mode; KMeans.fit semantics kmeans.py:124-171).
+ * segb_kmeans_collect: for utterances [utt_first, +n_utt) turn `bounds` into
+ * tokens (tok_id), set assignments[id] = best_k[id], and accumulate
+ * sum_x[k] += X[id] (float64) and cnt[k] += 1 for the chosen segments.  sum_x /
+ * cnt are the buffers an NCCL allreduce combines across ranks.
+ * segb_kmeans_set_means: mean_num <- sum_x, counts <- cnt,
+ * means[k] = (X dtype)(sum_x[k] / cnt[k]) where cnt[k] > 0 (:110).            */
+int segb_kmeans_collect(const segb_kmeans *m, const segb_corpus *c, int32_t utt_first, int32_t n_utt,
+                        const int32_t *best_k, double *sum_x, int64_t *cnt, void *stream);
+int segb_kmeans_set_means(const segb_kmeans *m, const double *sum_x, const int64_t *cnt, void *stream);
+
+/* ------------------------------------------------------------------ tensor-core scoring (tcgen05 + TMA) */
+
+/* Sizes of the pre-tiled fp16 operand images used by the tcgen05 filter GEMM. */
+int64_t segb_mma_x_tiles_bytes(int64_t n_emb, int32_t D);
+int64_t segb_mma_w_tiles_bytes(int32_t K_max, int32_t D);
+int64_t segb_mma_cand_bytes(int64_t n_emb);
+
+/* Ingest: write the fp16 UMMA-canonical tile image of X (done once; X is
+ * constant across sweeps) and the per-row rounding-error norms used by the
+ * rigorous candidate threshold.                                               */
+int segb_mma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, float *x_err, void *stream);
+/* Per sweep: tile image of the K_max float32 means, with -|mu|^2/2 folded into
+ * padding columns of the inner dimension.                                     */
+int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D, void *w_tiles, float *w_err,
+                        void *stream);
+/* Filter GEMM (tcgen05.mma kind::f16, fp32 accumulate in TMEM, operands staged
+ * by cp.async.bulk): for every embedding the best / second / third 16-component
+ * chunk of x.mu - |mu|^2/2.  cand: opaque per-row records for segb_mma_refine. */
+int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
+                    void *cand, void *stream);
+/* Refine: re-score the candidate chunks exactly (float32, NumPy order, same
+ * code path as segb_kmeans_best) -> bit-exact max / first argmax.  n_fallback
+ * (device, optional) counts rows that needed the full exact scan.             */
+int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_err,
+                    int64_t n_emb, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGB200_H */

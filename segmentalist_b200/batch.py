@@ -1,0 +1,168 @@
+"""
+Frozen-state batch sweep for segmental k-means (new mode).
+
+Given frozen means, every utterance is independent: score all candidate
+segments (max / argmax over K_max components), build the banded duration-
+weighted scores, run the Viterbi DP, read off the chosen segments and their
+components.  The model update is then a pure reduction -- per-component sum of
+embeddings and counts -- which is what shards over GPUs: each rank owns a
+contiguous range of utterances (and their embeddings) plus a replica of the
+means, and one NCCL all-reduce of (sum_x [K_max, D] float64, cnt [K_max] int64)
+per sweep rebuilds identical means everywhere.
+
+Semantics (pinned by oracle.seg_oracle.frozen_kmeans_sweep and
+tests/golden/kmeans_wordseg.npz): phase 1 = the reference's pure functions
+get_vec_embed_neg_len_sqrd_norms -> forward_backward_kmeans_viterbi ->
+get_max_assignments (kmeans_acoustic_wordseg.py:334-351,449-555,
+kmeans_components.py:256-261) per utterance; phase 2 = del_item for every old
+token, add_item for every new one in utterance order, clean_components()
+(kmeans_acoustic_wordseg.py:312-320).
+
+Two scorers produce the per-embedding (max, argmax):
+  "exact" -- SIMT kernel, float32 in NumPy order (segb_kmeans_best);
+  "mma"   -- tcgen05 filter GEMM + exact refine (segb_mma_filter / segb_mma_refine),
+             same bits out, tensor-core speed.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def _dist_on():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class FrozenKMeansSweep(object):
+
+    def __init__(self, components, corpus, wip=0.0, scorer="auto"):
+        self.c, self.corpus, self.wip = components, corpus, float(wip)
+        lib = _lib.lib()
+        c = components
+        if scorer == "auto":
+            scorer = "mma" if (c.X.dtype == np.float32 and c.D <= 240 and c.K_max <= 8192) else "exact"
+        assert scorer in ("exact", "mma")
+        self.scorer = scorer
+        dev = "cuda"
+        self.best_val = torch.empty(c.N, dtype=c._row.dtype, device=dev)
+        self.best_k = torch.empty(c.N, dtype=torch.int32, device=dev)
+        self.scores = torch.empty(corpus.n_pos * corpus.S, dtype=torch.float64, device=dev)
+        self.log_prob = torch.zeros(corpus.n_utt, dtype=torch.float64, device=dev)
+        self.status = torch.zeros(corpus.n_utt, dtype=torch.int32, device=dev)
+        self.sum_x = torch.zeros(c.K_max, c.D, dtype=torch.float64, device=dev)
+        self.cnt = torch.zeros(c.K_max, dtype=torch.int64, device=dev)
+        self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.last_fallback = 0
+        if scorer == "mma":
+            self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
+            self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
+            self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
+            self.x_err = torch.empty(c.N, dtype=torch.float32, device=dev)
+            self.w_err = torch.empty(c.K_max, dtype=torch.float32, device=dev)
+            _lib.check(lib.segb_mma_pack_x(_lib.ptr(c._X), c.N, c.D, _lib.ptr(self.x_tiles), _lib.ptr(self.x_err),
+                                           _lib.stream_ptr()))
+
+    # ---- phases (each is one or two launches; no host sync inside)
+    def score(self):
+        lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
+        m = c.struct()
+        if self.scorer == "exact":
+            _lib.check(lib.segb_kmeans_best(m, None, c.N, _lib.ptr(self.best_val), _lib.ptr(self.best_k), sp))
+        else:
+            _lib.check(lib.segb_mma_pack_means(_lib.ptr(c._means), c.K_max, c.D, _lib.ptr(self.w_tiles),
+                                               _lib.ptr(self.w_err), sp))
+            _lib.check(lib.segb_mma_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
+                                           _lib.ptr(self.cand), sp))
+            self.n_fallback.zero_()
+            _lib.check(lib.segb_mma_refine(m, _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_err), c.N,
+                                           _lib.ptr(self.best_val), _lib.ptr(self.best_k),
+                                           _lib.ptr(self.n_fallback), sp))
+
+    def segment(self):
+        lib, c, cp, sp = _lib.lib(), self.c, self.corpus, _lib.stream_ptr()
+        cs = cp.struct()
+        _lib.check(lib.segb_kmeans_band_scores(c.struct(), cs, 0, cp.n_pos, _lib.ptr(self.best_val), self.wip,
+                                               _lib.ptr(self.scores), sp))
+        _lib.check(lib.segb_dp_banded(cs, 0, cp.n_utt, _lib.ptr(self.scores), _lib.DP_VITERBI_KMEANS, 0.0, 1.0,
+                                      None, None, _lib.ptr(cp.bounds), _lib.ptr(self.log_prob), None, None,
+                                      _lib.ptr(self.status), sp))
+
+    def collect(self, assign_from=None):
+        """Tokens of the current boundaries -> (sum_x, cnt); assignments[id] = k."""
+        lib, c, cp, sp = _lib.lib(), self.c, self.corpus, _lib.stream_ptr()
+        src = self.best_k if assign_from is None else assign_from
+        if assign_from is None:
+            c._assign.fill_(-1)
+        self.sum_x.zero_()
+        self.cnt.zero_()
+        _lib.check(lib.segb_kmeans_collect(c.struct(), cp.struct(), 0, cp.n_utt, _lib.ptr(src), _lib.ptr(self.sum_x),
+                                           _lib.ptr(self.cnt), sp))
+
+    def reduce_and_update(self):
+        """All-reduce the sufficient statistics over ranks (NCCL over NVLink), rebuild means."""
+        lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
+        if _dist_on():
+            dist.all_reduce(self.sum_x, op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.cnt, op=dist.ReduceOp.SUM)
+        _lib.check(lib.segb_kmeans_set_means(c.struct(), _lib.ptr(self.sum_x), _lib.ptr(self.cnt), sp))
+
+    def init_means_from_assignments(self):
+        """Build replicated means from the current (sharded) assignments: used once before
+        the first distributed sweep."""
+        c = self.c
+        self.collect(assign_from=c._assign.clone())
+        self.reduce_and_update()
+        K = int((self.cnt > 0).sum().item())
+        assert bool((self.cnt[:K] > 0).all().item()), "initial assignments must use labels 0..K-1"
+        c._K.fill_(K)
+
+    def sweep(self):
+        """One frozen sweep; returns sum_neg_len_sqrd_norm (summed over all ranks)."""
+        c, cp = self.c, self.corpus
+        K_before = c.K
+        self.score()
+        self.segment()
+        self.collect()
+        # --- host decisions (one sync per sweep)
+        st = self.status.cpu().numpy()
+        assert np.all(st == _lib.DP_OK), "segmentation failed (status %s)" % np.unique(st)
+        total = float(np.cumsum(self.log_prob.cpu().numpy())[-1]) if cp.n_utt else 0.0
+        if self.scorer == "mma":
+            self.last_fallback = int(self.n_fallback.item())
+        if K_before < c.K_max:
+            self._clamp_inactive_winners(K_before)
+        self.reduce_and_update()
+        if _dist_on():
+            t = torch.tensor([total], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            total = float(t.item())
+        if bool((self.cnt[:c.K] == 0).any().item()):
+            c.clean_components()
+        return total
+
+    def _clamp_inactive_winners(self, K_before):
+        """add_item's `k > K -> K` clamp (kmeans_components.py:103-106) for tokens won by an
+        inactive slot.  Sequential by nature; resolved on the host over the (few) affected
+        tokens in utterance order, then the statistics are re-collected."""
+        c, cp = self.c, self.corpus
+        cnt = self.cnt.cpu().numpy()
+        if not np.any(cnt[K_before:] > 0):
+            return
+        assert not _dist_on(), "inactive-slot winners under sharding need a global token order (not implemented)"
+        tok = cp.tok_id.cpu().numpy()
+        ids = tok[tok >= 0]                      # utterance order, left to right
+        ks = self.best_k.cpu().numpy()
+        K = K_before
+        patched = False
+        for e in ids:
+            k = ks[e]
+            if k >= K:
+                if k > K:
+                    ks[e] = K
+                    patched = True
+                K += 1 if ks[e] == K else 0
+        c._K.fill_(int(K))
+        if patched:
+            self.best_k.copy_(torch.from_numpy(ks))
+        self.collect()

@@ -1,0 +1,108 @@
+"""
+Finite Bayesian GMM over device-resident fixed-variance components.
+
+Mirror of the reference's `FBGMM` (segmentalist/fbgmm.py:27-494) for
+covariance_type == "fixed" -- the only covariance on the accelerated path
+(SURVEY.md section 8).  Uniform draws are taken from Python's `random.random()`
+on the host, exactly where the reference takes them, and handed to the kernels,
+so a seeded run consumes the same stream as the reference.
+"""
+import random
+
+import numpy as np
+import torch
+from scipy.special import gammaln
+
+from . import _lib
+from .gaussian_components_fixedvar import GaussianComponentsFixedVar
+
+
+def make_consecutive(assignments):
+    """Relabel so that the used labels are 0..max without gaps (fbgmm.py:124-128)."""
+    for k in range(assignments.max()):
+        while len(np.nonzero(assignments == k)[0]) == 0:
+            assignments[np.where(assignments > k)] -= 1
+        if assignments.max() == k:
+            break
+    return assignments
+
+
+class FBGMM(object):
+
+    def __init__(self, X, prior, alpha, K, assignments="rand", covariance_type="fixed", lms=1.0):
+        self.alpha = alpha
+        self.prior = prior
+        self.covariance_type = covariance_type
+        self.lms = lms
+        self.setup_components(K, assignments, X)
+
+    def setup_components(self, K, assignments="rand", X=None):
+        """fbgmm.py:96-137."""
+        if X is None:
+            assert hasattr(self, "components")
+            X = self.components.X
+        N, D = X.shape
+        if isinstance(assignments, str) and assignments == "rand":
+            assignments = np.random.randint(0, K, N)
+        elif isinstance(assignments, str) and assignments == "each-in-own":
+            assignments = np.arange(N)
+        assignments = make_consecutive(np.asarray(assignments))
+        assert self.covariance_type == "fixed", (
+            "only covariance_type='fixed' is implemented on the B200 path (see DESIGN.md, out of scope)")
+        self.components = GaussianComponentsFixedVar(X, self.prior, assignments, K_max=K,
+                                                     alpha=self.alpha, lms=self.lms)
+
+    # ---- hot path
+    def log_marg_i(self, i):
+        """fbgmm.py:256-285: log p(x_i) marginalised over all K_max slots."""
+        assert i != -1
+        return float(self.log_marg_items(np.asarray([i]))[0])
+
+    def log_marg_items(self, ids, durations=None, time_power_term=1.0, wip=0.0):
+        """Batched log_marg_i (one launch); with `durations` also applies the scaling of
+        get_vec_embed_log_probs (unigram_acoustic_wordseg.py:474-511)."""
+        c = self.components
+        ids_d = _lib.dev(np.asarray(ids, dtype=np.int32))
+        durs_d = None if durations is None else _lib.dev(np.asarray(durations, dtype=np.float64))
+        out = torch.empty(len(ids), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().segb_fixedvar_log_marg(
+            c.struct(), _lib.ptr(ids_d), _lib.ptr(durs_d), len(ids), float(time_power_term), float(wip),
+            _lib.ptr(out), _lib.stream_ptr()))
+        return out.cpu().numpy()
+
+    def _assign(self, ids, mode, anneal_temp, uniforms):
+        c = self.components
+        ids_d = _lib.dev(np.asarray(ids, dtype=np.int32))
+        ks = torch.empty(len(ids), dtype=torch.int32, device="cuda")
+        u_d = None if uniforms is None else _lib.dev(np.asarray(uniforms, dtype=np.float64))
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        _lib.check(_lib.lib().segb_fixedvar_assign_items(
+            c.struct(), _lib.ptr(ids_d), len(ids), mode, float(anneal_temp), _lib.ptr(u_d), _lib.ptr(cnt),
+            _lib.ptr(ks), _lib.stream_ptr()))
+        return ks.cpu().numpy()
+
+    def gibbs_sample_inside_loop_i(self, i, anneal_temp=1):
+        """fbgmm.py:422-463: draw a component for X[i] and add it."""
+        u = random.random()
+        return int(self._assign([i], 0, anneal_temp, [u])[0])
+
+    def map_assign_i(self, i):
+        """fbgmm.py:465-494."""
+        return int(self._assign([i], 1, 1.0, None)[0])
+
+    # ---- diagnostics (host, from mirrored statistics)
+    def log_prob_z(self):
+        """fbgmm.py:208-225."""
+        counts = self.components.counts
+        K_max = self.components.K_max
+        return (gammaln(self.alpha) - gammaln(self.alpha + np.sum(counts))
+                + np.sum(gammaln(counts + float(self.alpha) / K_max) - gammaln(self.alpha / K_max)))
+
+    def log_prob_X_given_z(self):
+        return self.components.log_marg()
+
+    def log_marg(self):
+        return self.log_prob_z() + self.log_prob_X_given_z()
+
+    def get_n_assigned(self):
+        return len(np.where(self.components.assignments != -1)[0])
