@@ -58,8 +58,8 @@ class FrozenKMeansSweep(object):
             self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
             self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
             self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
-            self.x_err = torch.empty(c.N, dtype=torch.float32, device=dev)
-            self.w_err = torch.empty(c.K_max, dtype=torch.float32, device=dev)
+            self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)          # (|dx|, |x|) per row
+            self.w_err = torch.empty(2 * (c.K_max + 128), dtype=torch.float32, device=dev)  # (|dmu|, |mu^|)
             _lib.check(lib.segb_mma_pack_x(_lib.ptr(c._X), c.N, c.D, _lib.ptr(self.x_tiles), _lib.ptr(self.x_err),
                                            _lib.stream_ptr()))
 

@@ -204,8 +204,9 @@ __global__ void __launch_bounds__(128) dp_banded_kernel(DpParams p) {
         }
         int k = idx + 1;
         if (n_min > 1) k += n_min - 1;             // reference adds this even after back-tracking
-        if (k > t || k > S) { status = SEGB_DP_EMPTY_SLICE; break; }
-        total += sc[(int64_t)(t - 1) * S + (k - 1)];
+        if (k > t) { status = SEGB_DP_EMPTY_SLICE; break; }
+        // spans beyond the band carry no embedding: the packed vector holds -inf there
+        total += (k <= S) ? sc[(int64_t)(t - 1) * S + (k - 1)] : neg_inf();
         if (t - k - 1 < 0) break;
         if (lane == 0) bo[t - k - 1] = 1;
         t = t - k;

@@ -1,9 +1,524 @@
-// placeholder: replaced by the tcgen05 filter GEMM (see next commit)
+// Tensor-core scoring for the frozen k-means sweep: filter GEMM + exact refine.
+//
+// Replaces, for ALL embeddings at once, the reference's per-item
+//   max_k / argmax_k  -sum_d (means[k,d] - x[d])^2
+// (KMeansComponents.neg_sqrd_norm / max_ / argmax_neg_sqrd_norm_i,
+//  segmentalist/kmeans_components.py:225-232, called from
+//  kmeans_acoustic_wordseg.py:334-351 and kmeans.py:141-143).
+//
+// Exactness strategy (SURVEY.md 7.3 "filter-and-refine"): the reference decides in
+// float32 with NumPy's summation order, which no tensor-core pass reproduces.
+// So the GEMM only FILTERS: one fp16 tcgen05 pass computes t^[m,k] ~ x.mu_k - |mu_k|^2/2
+// (argmax_k t = argmax_k of the reference score) and keeps, per embedding, the
+// best three 16-component chunks.  A rigorous per-row error bound then decides
+// which chunks can contain the true winner; those (normally 16 components out
+// of K_max) are re-scored by the exact float32 routine the SIMT path uses, so
+// max and first-argmax come out bit-identical to the reference.  Rows whose
+// third-best chunk is still inside the bound fall back to a full exact scan.
+//
+// Memory layout (designed for the copy engine, not for humans): X and the means
+// are stored in HBM as fp16 "tile images": consecutive 128-row tiles, each
+// already in the UMMA canonical K-major no-swizzle shared-memory layout (8x8
+// core matrices of 128 contiguous bytes).  A tile is therefore ONE contiguous
+// cp.async.bulk (TMA bulk copy, SASS UBLKCP) into shared memory, with no tensor
+// map and no swizzle agreement to get wrong.  The inner dimension is padded from
+// D to KP = roundup(D + 3, 16); three padding columns carry a 3-way fp16 split
+// of -|mu_k|^2/2 (x side: 1.0), so the norm rides along in the GEMM for free.
+//
+// Kernel: persistent, one CTA per SM, 384 threads, warp-specialised:
+//   warp 0  TMA producer  (A = 256 embeddings, once per work item; B = 128-component
+//                          tiles streamed through a 4-stage ring, L2-resident)
+//   warp 1  MMA issuer    (tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accumulate in TMEM,
+//                          2 row-halves x double-buffered accumulators = 512 TMEM columns)
+//   warp 2  TMEM allocator
+//   warps 4-11 epilogue   (tcgen05.ld 32x32b: one thread owns one embedding row; running
+//                          top-3 of chunk maxima in registers; nothing but 32 B per
+//                          embedding ever goes back to HBM)
+#include <cuda_fp16.h>
 #include "common.cuh"
-extern "C" int64_t segb_mma_x_tiles_bytes(int64_t n_emb, int32_t D) { return 16; }
-extern "C" int64_t segb_mma_w_tiles_bytes(int32_t K_max, int32_t D) { return 16; }
-extern "C" int64_t segb_mma_cand_bytes(int64_t n_emb) { return 16; }
-extern "C" int segb_mma_pack_x(const float *, int64_t, int32_t, void *, float *, void *) { segb::set_error("mma path not built"); return SEGB_E_UNSUPPORTED; }
-extern "C" int segb_mma_pack_means(const float *, int32_t, int32_t, void *, float *, void *) { segb::set_error("mma path not built"); return SEGB_E_UNSUPPORTED; }
-extern "C" int segb_mma_filter(const void *, const void *, int64_t, int32_t, int32_t, void *, void *) { segb::set_error("mma path not built"); return SEGB_E_UNSUPPORTED; }
-extern "C" int segb_mma_refine(const segb_kmeans *, const void *, const float *, const float *, int64_t, float *, int32_t *, int64_t *, void *) { segb::set_error("mma path not built"); return SEGB_E_UNSUPPORTED; }
+
+namespace segb {
+namespace mma {
+
+constexpr int TILE_ROWS = 128;     // rows per operand tile image
+constexpr int MT_ROWS = 256;       // embeddings per CTA work item (two A tiles)
+constexpr int NT_COLS = 128;       // components per accumulator tile
+constexpr int CHUNK = 16;          // components per candidate chunk
+constexpr int MAX_STAGES = 4;
+constexpr int N_THREADS = 384;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr float PAD_BIAS = -30000.0f;   // -|mu|^2/2 stand-in for padded components: never wins
+
+struct __align__(32) Cand {        // per-embedding filter record
+    float m1, m2, m3;              // best / second / third chunk maximum of t^
+    int32_t i1, i2;                // chunk ids of m1, m2
+    int32_t pad[3];
+};
+
+__host__ __device__ inline int kp_of(int D) { return (D + 3 + 15) / 16 * 16; }
+__host__ __device__ inline int64_t tile_bytes_of(int D) { return (int64_t)TILE_ROWS * kp_of(D) * 2; }
+// byte offset of element (r, c) inside a 128-row tile image
+__host__ __device__ inline int tile_off(int r, int c) {
+    return ((c >> 3) * (TILE_ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (c & 7) * 2;
+}
+
+// ---------------------------------------------------------------- PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (context error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    printf("segb mma: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+// 32 lanes x 64 consecutive fp32 columns -> 64 registers per thread (thread = TMEM lane = row).
+// Load and wait live in ONE asm statement so no use of the outputs can be scheduled before
+// tcgen05.wait::ld.
+__device__ __forceinline__ void tc_ld64_wait(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr) : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// SBO = distance between 8-row core matrices (128 B), LBO = distance between the two
+// 8-element K chunks of one K=16 instruction ((TILE_ROWS/8)*128 B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    const uint64_t lbo = (TILE_ROWS / 8) * 128, sbo = 128;
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: A,B = fp16 K-major, D = fp32, M = 128, N = 128
+__device__ __forceinline__ uint32_t make_idesc() {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NT_COLS >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- filter GEMM
+
+struct FilterParams {
+    const uint8_t *x_tiles, *w_tiles;
+    Cand *cand;
+    int64_t n_emb;
+    int32_t n_mtiles, n_ntiles, n_ksteps, n_stages;
+    uint32_t tile_bytes;
+};
+
+__device__ __forceinline__ void top3_insert(float cm, int cid, float &m1, float &m2, float &m3, int &i1, int &i2) {
+    if (cm > m3) {
+        if (cm > m2) {
+            m3 = m2;
+            if (cm > m1) { m2 = m1; i2 = i1; m1 = cm; i1 = cid; }
+            else { m2 = cm; i2 = cid; }
+        } else m3 = cm;
+    }
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tb = p.tile_bytes;
+    uint8_t *sA = smem;                               // 2 tiles
+    uint8_t *sB = smem + 2 * (size_t)tb;              // n_stages tiles
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.n_stages * tb);
+    // barrier slots: 0 a_full, 1 a_empty, 2..5 b_full, 6..9 b_empty, 10..11 acc_full, 12..13 acc_empty
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+    if (threadIdx.x == 0) {
+        mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(6 + s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(BAR(10 + b), 1); mbar_init(BAR(12 + b), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t a_phase = 0, b_phase = 0;
+            int s = 0;
+            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+                mbar_wait(BAR(1), a_phase ^ 1);
+                mbar_expect_tx(BAR(0), 2 * tb);
+                bulk_g2s(smem_u32(sA), p.x_tiles + (size_t)(2 * mt) * tb, tb, BAR(0));
+                bulk_g2s(smem_u32(sA + tb), p.x_tiles + (size_t)(2 * mt + 1) * tb, tb, BAR(0));
+                a_phase ^= 1;
+                for (int nt = 0; nt < p.n_ntiles; ++nt) {
+                    mbar_wait(BAR(6 + s), b_phase ^ 1);
+                    mbar_expect_tx(BAR(2 + s), tb);
+                    bulk_g2s(smem_u32(sB + (size_t)s * tb), p.w_tiles + (size_t)nt * tb, tb, BAR(2 + s));
+                    if (++s == p.n_stages) { s = 0; b_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc();
+            const uint32_t kstep_bytes = 2 * (TILE_ROWS / 8) * 128;       // two K chunks per K=16 step
+            uint32_t a_phase = 0, b_phase = 0, n_use = 0;
+            int s = 0;
+            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+                mbar_wait(BAR(0), a_phase);
+                a_phase ^= 1;
+                for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
+                    const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
+                    mbar_wait(BAR(2 + s), b_phase);
+                    mbar_wait(BAR(12 + buf), acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + (size_t)s * tb);
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t a_addr = smem_u32(sA + (size_t)h * tb);
+                        const uint32_t d_tmem = tmem_base + (buf * 2 + h) * NT_COLS;
+                        for (int k = 0; k < p.n_ksteps; ++k)
+                            tc_mma_f16(d_tmem, make_desc(a_addr + k * kstep_bytes), make_desc(b_addr + k * kstep_bytes),
+                                       idesc, k > 0 ? 1u : 0u);
+                    }
+                    tc_commit(BAR(6 + s));          // B stage free once these MMAs have read it
+                    tc_commit(BAR(10 + buf));       // accumulators ready for the epilogue
+                    if (++s == p.n_stages) { s = 0; b_phase ^= 1; }
+                }
+                tc_commit(BAR(1));                  // A tiles free
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: running top-3 chunk maxima per embedding =====================
+        const int e = warp - 4, h = e >> 2, q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint32_t n_use = 0;
+        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+            float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+            int i1 = -1, i2 = -1;
+            for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
+                const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
+                mbar_wait(BAR(10 + buf), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_base + (buf * 2 + h) * NT_COLS;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    float v[64];
+                    tc_ld64_wait(taddr + part * 64, v);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float cm = v[c * 16];
+#pragma unroll
+                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                        top3_insert(cm, nt * (NT_COLS / CHUNK) + part * 4 + c, m1, m2, m3, i1, i2);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(12 + buf));
+            }
+            const int64_t row = (int64_t)mt * MT_ROWS + h * TILE_ROWS + q * 32 + lane;
+            if (row < p.n_emb) {
+                Cand c;
+                c.m1 = m1; c.m2 = m2; c.m3 = m3; c.i1 = i1; c.i2 = i2; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+                p.cand[row] = c;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- operand packing
+
+// One warp per row: lane j converts the 8-element chunk j of the padded row to fp16 and
+// writes its 16 bytes into the tile image.  err[2r] = |x - fp16(x)|_2, err[2r+1] = |x|_2.
+__global__ void pack_x_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad, int D, int KP, uint8_t *tiles,
+                              float *err) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows_pad) return;
+    const int64_t tile = row / TILE_ROWS;
+    const int r = (int)(row % TILE_ROWS);
+    uint8_t *base = tiles + tile * ((int64_t)TILE_ROWS * KP * 2);
+    float e2 = 0.f, n2 = 0.f;
+    bool overflow = false;
+    for (int ch = lane; ch < KP / 8; ch += 32) {
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            float x = 0.f;
+            if (row < n_emb) {
+                if (c < D) x = X[row * D + c];
+                else if (c < D + 3) x = 1.0f;          // multiplies the three -|mu|^2/2 pieces
+            }
+            if (fabsf(x) > 60000.f) overflow = true;
+            const __half hx = __float2half_rn(x);
+            hv[j] = hx;
+            if (c < D) { const float dl = x - __half2float(hx); e2 += dl * dl; n2 += x * x; }
+        }
+        *reinterpret_cast<uint4 *>(base + tile_off(r, ch * 8)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
+    overflow = __any_sync(FULL, overflow);
+    if (lane == 0 && row < n_emb) {
+        err[2 * row] = overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f;
+        err[2 * row + 1] = sqrtf(n2) * 1.0001f;
+    }
+}
+
+// Means tile image + per-component (|mu - fp16(mu)|, |fp16(mu)|); padded components get PAD_BIAS.
+__global__ void pack_w_kernel(const float *means, int K_max, int K_pad, int D, int KP, uint8_t *tiles, float *err) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= K_pad) return;
+    const int tile = row / TILE_ROWS, r = row % TILE_ROWS;
+    uint8_t *base = tiles + (int64_t)tile * ((int64_t)TILE_ROWS * KP * 2);
+    // |mu|^2 in float64 over the float32 means
+    double nrm = 0.0;
+    if (row < K_max)
+        for (int d = lane; d < D; d += 32) { const double v = means[(int64_t)row * D + d]; nrm += v * v; }
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(FULL, nrm, o);
+    float bias = (row < K_max) ? (float)(-0.5 * nrm) : PAD_BIAS;
+    bool overflow = !(fabsf(bias) < 60000.f);
+    const __half b0 = __float2half_rn(bias);
+    const float r1 = bias - __half2float(b0);
+    const __half b1 = __float2half_rn(r1);
+    const __half b2 = __float2half_rn(r1 - __half2float(b1));
+    float e2 = 0.f, n2 = 0.f;
+    for (int ch = lane; ch < KP / 8; ch += 32) {
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            __half hx = __float2half_rn(0.f);
+            if (c < D) {
+                const float x = (row < K_max) ? means[(int64_t)row * D + c] : 0.f;
+                if (fabsf(x) > 60000.f) overflow = true;
+                hx = __float2half_rn(x);
+                const float dl = x - __half2float(hx);
+                e2 += dl * dl;
+                n2 += __half2float(hx) * __half2float(hx);
+            } else if (c == D) hx = b0;
+            else if (c == D + 1) hx = b1;
+            else if (c == D + 2) hx = b2;
+            hv[j] = hx;
+        }
+        *reinterpret_cast<uint4 *>(base + tile_off(r, ch * 8)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
+    overflow = __any_sync(FULL, overflow);
+    if (lane == 0) {
+        err[2 * row] = (row < K_max) ? (overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f) : 0.f;
+        err[2 * row + 1] = (row < K_max) ? sqrtf(n2) * 1.0001f : 0.f;
+    }
+}
+
+}  // namespace mma
+}  // namespace segb
+
+// ---------------------------------------------------------------- exact refine (float32, NumPy order)
+
+namespace segb {
+namespace mma {
+
+// Exact float32 score of component k for the row staged in xs (same routine as kmeans.cu).
+__device__ __forceinline__ float exact_neg_dist(const float *meansT, int KM_, int k, const float *xs, int D) {
+    auto f = [&](int d) -> float {
+        const float dl = __fsub_rn(meansT[(size_t)d * KM_ + k], xs[d]);
+        return __fmul_rn(dl, dl);
+    };
+    float s;
+    if (D <= 128) s = pairwise_block<float>(f, 0, D);
+    else if (D <= 256) {
+        int n2 = D / 2; n2 -= n2 % 8;
+        s = __fadd_rn(pairwise_block<float>(f, 0, n2), pairwise_block<float>(f, n2, D - n2));
+    } else s = pairwise_sum<float>(f, D);
+    return -s;
+}
+
+// One warp per embedding.  Lanes 0-15 re-score the 16 components of the best chunk, lanes
+// 16-31 those of the runner-up chunk when it lies within the error bound; rows whose third
+// chunk is also inside the bound are re-scored against every component.
+__global__ void __launch_bounds__(256) refine_kernel(segb_kmeans m, const Cand *cand, const float *x_err,
+                                                     const float *w_err, int64_t n_emb, int K_pad, float *best_val,
+                                                     int32_t *best_k, unsigned long long *n_fallback) {
+    extern __shared__ float rsm[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, n_w = blockDim.x >> 5;
+    float *xs = rsm + (size_t)wib * m.D;
+    float *red = rsm + (size_t)n_w * m.D;     // [2 * n_w]
+    // model-wide maxima of the per-component rounding error and norm
+    float e_mu = 0.f, n_mu = 0.f;
+    for (int k = threadIdx.x; k < m.K_max; k += blockDim.x) { e_mu = fmaxf(e_mu, w_err[2 * k]); n_mu = fmaxf(n_mu, w_err[2 * k + 1]); }
+    for (int o = 16; o > 0; o >>= 1) { e_mu = fmaxf(e_mu, __shfl_xor_sync(FULL, e_mu, o)); n_mu = fmaxf(n_mu, __shfl_xor_sync(FULL, n_mu, o)); }
+    if (lane == 0) { red[wib] = e_mu; red[n_w + wib] = n_mu; }
+    __syncthreads();
+    e_mu = 0.f; n_mu = 0.f;
+    for (int i = 0; i < n_w; ++i) { e_mu = fmaxf(e_mu, red[i]); n_mu = fmaxf(n_mu, red[n_w + i]); }
+    const int KP = kp_of(m.D);
+    const float c_acc = ldexpf((float)KP, -21) + ldexpf(1.f, -19);   // fp32 accumulation + reference rounding slack
+    const float *X = (const float *)m.X;
+    const float *meansT = (const float *)m.meansT;
+
+    for (int64_t row = (int64_t)blockIdx.x * n_w + wib; row < n_emb; row += (int64_t)gridDim.x * n_w) {
+        __syncwarp();
+        for (int d = lane; d < m.D; d += 32) xs[d] = X[row * m.D + d];
+        __syncwarp();
+        const Cand c = cand[row];
+        const float ex = x_err[2 * row], nx = x_err[2 * row + 1];
+        // t = x.mu - |mu|^2/2.  |t^ - t| <= ex*|mu^| + |x|*e_mu              (fp16 rounding of the operands)
+        //                    + c_acc*((|x|+ex)*|mu^| + |mu|^2/2)              (fp32 accumulation, bias split)
+        // plus eta = (D+3)*2^-24 * (|x|+|mu|)^2 / 2: the reference's own float32 rounding of the score.
+        const float eta = 0.5f * ldexpf((float)(m.D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
+        const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
+        const float tau = 2.0f * bound;
+        const bool need2 = (c.i2 >= 0) && !(c.m1 - c.m2 > tau);
+        const bool need_all = !(c.m1 - c.m3 > tau) && (c.m3 > -CUDART_INF_F);   // NaN-safe: falls back
+        float bv = -CUDART_INF_F;
+        int bk = 0x7fffffff;
+        if (need_all || !(tau < CUDART_INF_F)) {
+            for (int k = lane; k < m.K_max; k += 32) {
+                const float v = exact_neg_dist(meansT, m.K_max, k, xs, m.D);
+                if (v > bv || bk == 0x7fffffff) { bv = v; bk = k; }
+            }
+            if (lane == 0 && n_fallback) atomicAdd(n_fallback, 1ull);
+        } else {
+            const int chunk = (lane < 16) ? c.i1 : (need2 ? c.i2 : -1);
+            const int k = chunk * CHUNK + (lane & 15);
+            if (chunk >= 0 && k < m.K_max) { bv = exact_neg_dist(meansT, m.K_max, k, xs, m.D); bk = k; }
+        }
+        // warp argmax, first (lowest k) among equal values -- np.argmax semantics
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, o);
+            const int ok = __shfl_xor_sync(FULL, bk, o);
+            if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+        }
+        if (lane == 0) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
+    }
+}
+
+static inline int64_t rows_pad(int64_t n) { return (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS; }
+static inline int k_pad(int K) { return (K + NT_COLS - 1) / NT_COLS * NT_COLS; }
+
+}  // namespace mma
+}  // namespace segb
+
+using namespace segb;
+using namespace segb::mma;
+
+extern "C" int64_t segb_mma_x_tiles_bytes(int64_t n_emb, int32_t D) { return rows_pad(n_emb) * kp_of(D) * 2; }
+extern "C" int64_t segb_mma_w_tiles_bytes(int32_t K_max, int32_t D) { return (int64_t)k_pad(K_max) * kp_of(D) * 2; }
+extern "C" int64_t segb_mma_cand_bytes(int64_t n_emb) { return n_emb * (int64_t)sizeof(Cand); }
+
+extern "C" int segb_mma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, float *x_err, void *stream) {
+    SEGB_CHECK_ARG(X && x_tiles && x_err && n_emb > 0 && D > 0, "null pointer");
+    const int64_t np_ = rows_pad(n_emb);
+    const int wpb = 8;
+    pack_x_kernel<<<(unsigned)((np_ + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        X, n_emb, np_, D, kp_of(D), (uint8_t *)x_tiles, x_err);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D, void *w_tiles, float *w_err,
+                                   void *stream) {
+    SEGB_CHECK_ARG(means && w_tiles && w_err && K_max > 0 && D > 0, "null pointer");
+    const int kp_rows = k_pad(K_max);
+    const int wpb = 8;
+    pack_w_kernel<<<(kp_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+        means, K_max, kp_rows, D, kp_of(D), (uint8_t *)w_tiles, w_err);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
+                               void *cand, void *stream) {
+    SEGB_CHECK_ARG(x_tiles && w_tiles && cand && n_emb > 0 && K_max > 0, "null pointer");
+    FilterParams p;
+    p.x_tiles = (const uint8_t *)x_tiles; p.w_tiles = (const uint8_t *)w_tiles; p.cand = (Cand *)cand;
+    p.n_emb = n_emb;
+    p.n_mtiles = (int32_t)(rows_pad(n_emb) / MT_ROWS);
+    p.n_ntiles = k_pad(K_max) / NT_COLS;
+    p.n_ksteps = kp_of(D) / 16;
+    p.tile_bytes = (uint32_t)tile_bytes_of(D);
+    const size_t budget = 227 * 1024 - 512;
+    if (2 * (size_t)p.tile_bytes + 2 * (size_t)p.tile_bytes > budget) {
+        set_error("D=%d too large for the tensor-core scorer", D);
+        return SEGB_E_UNSUPPORTED;
+    }
+    int stages = (int)((budget - 2 * (size_t)p.tile_bytes) / p.tile_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p.n_stages = stages;
+    const size_t smem = (size_t)(2 + stages) * p.tile_bytes + 256;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        SEGB_CUDA(cudaGetDevice(&dev));
+        SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    SEGB_CUDA(cudaFuncSetAttribute(kmeans_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;
+    kmeans_filter_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(p);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_err,
+                               int64_t n_emb, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
+    SEGB_CHECK_ARG(m && cand && x_err && w_err && best_val && best_k, "null pointer");
+    SEGB_CHECK_ARG(!m->x_is_f64, "tensor-core scorer needs float32 embeddings");
+    const int wpb = 8;
+    const size_t smem = sizeof(float) * ((size_t)wpb * m->D + 2 * wpb);
+    int64_t blocks = (n_emb + wpb - 1) / wpb;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    refine_kernel<<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+        *m, (const Cand *)cand, x_err, w_err, n_emb, k_pad(m->K_max), best_val, best_k,
+        (unsigned long long *)n_fallback);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
