@@ -232,11 +232,15 @@ int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D, void *w_ti
  * chunk of x.mu - |mu|^2/2.  cand: opaque per-row records for segb_mma_refine. */
 int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
                     void *cand, void *stream);
-/* Refine: re-score the candidate chunks exactly (float32, NumPy order, same
- * code path as segb_kmeans_best) -> bit-exact max / first argmax.  n_fallback
- * (device, optional) counts rows that needed the full exact scan.             */
+/* Refine: group rows by best chunk (counting sort), stage each chunk's 16 float32 means in
+ * shared memory and re-score the candidates exactly (float32, NumPy order, same arithmetic
+ * as segb_kmeans_best) -> bit-exact max / first argmax.  work: segb_mma_refine_work_bytes()
+ * bytes of scratch.  n_fallback (device, required; reset by the call) counts rows that needed
+ * the exhaustive scan (run by a second kernel, one block per such row). */
+int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max);
 int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_err,
-                    int64_t n_emb, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
+                    int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
+                    void *stream);
 
 #ifdef __cplusplus
 }

@@ -965,22 +965,16 @@ class SegmentalKMeansWordseg(object):
 # with the reference's pure functions, then all updates are applied.
 # ---------------------------------------------------------------------------
 
-def frozen_kmeans_sweep(seg, utt_indices=None):
-    """One frozen-means sweep of a SegmentalKMeansWordseg oracle object.
-
-    Phase 1 (pure, per utterance, means frozen): get_vec_embed_neg_len_sqrd_norms
-    (kmeans_acoustic_wordseg.py:334-351) -> forward_backward_kmeans_viterbi
-    (:449-555) -> get_max_assignments (kmeans_components.py:256-261).
-    Phase 2: del_item for every old token, add_item(new token, k) in utterance
-    order left to right (same calls as segment_i :312-319), one
-    clean_components() at the end (:320).
-    Returns (sum of per-utterance objectives, list of per-utterance
-    (embeds, ks))."""
+def frozen_kmeans_phase1(seg, utt_indices=None):
+    """Pure part of the frozen sweep (means untouched): per utterance
+    get_vec_embed_neg_len_sqrd_norms (kmeans_acoustic_wordseg.py:334-351) ->
+    forward_backward_kmeans_viterbi (:449-555) -> get_max_assignments
+    (kmeans_components.py:256-261).  Writes the new boundaries into
+    seg.utterances and returns (per-utterance objectives, old tokens, plan)."""
     utts, comps = seg.utterances, seg.acoustic_model.components
     if utt_indices is None:
         utt_indices = range(utts.D)
-    plan, total = [], 0.0
-    old_tokens = []
+    plan, totals, old_tokens = [], [], []
     for u in utt_indices:
         N = utts.lengths[u]
         n_packed = (N ** 2 + N) // 2
@@ -988,11 +982,25 @@ def frozen_kmeans_sweep(seg, utt_indices=None):
         scores = seg.get_vec_embed_neg_len_sqrd_norms(utts.vec_ids[u, :n_packed],
                                                       utts.durations[u, :n_packed])
         obj, bounds = forward_backward_kmeans_viterbi(scores, N, seg.n_slices_min, seg.n_slices_max, u)
-        total += obj
+        totals.append(obj)
         utts.boundaries[u, :N] = bounds
         embeds = utts.get_segmented_embeds_i(u)
-        ks = comps.get_max_assignments(embeds)
-        plan.append((embeds, ks))
+        plan.append((embeds, comps.get_max_assignments(embeds)))
+    return totals, old_tokens, plan
+
+
+def frozen_kmeans_sweep(seg, utt_indices=None):
+    """One frozen-means sweep of a SegmentalKMeansWordseg oracle object.
+
+    Phase 1: frozen_kmeans_phase1.  Phase 2: del_item for every old token,
+    add_item(new token, k) in utterance order left to right (same calls as
+    segment_i :312-319), one clean_components() at the end (:320).
+    Returns (sum of per-utterance objectives, list of per-utterance (embeds, ks))."""
+    comps = seg.acoustic_model.components
+    totals, old_tokens, plan = frozen_kmeans_phase1(seg, utt_indices)
+    total = 0.0
+    for t in totals:
+        total += t
     for e in old_tokens:
         comps.del_item(e)
     for embeds, ks in plan:

@@ -75,7 +75,9 @@ _PROTOS = {
     "segb_mma_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "segb_mma_pack_means": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "segb_mma_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
-    "segb_mma_refine": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "segb_mma_refine_work_bytes": (c_i64, [c_i64, c_i32]),
+    "segb_mma_refine": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                       c_vp]),
 }
 
 EXPORTS = sorted(_PROTOS)

@@ -41,7 +41,7 @@ class FrozenKMeansSweep(object):
         lib = _lib.lib()
         c = components
         if scorer == "auto":
-            scorer = "mma" if (c.X.dtype == np.float32 and c.D <= 240 and c.K_max <= 8192) else "exact"
+            scorer = "mma" if (c._X.dtype == torch.float32 and c.D <= 157) else "exact"
         assert scorer in ("exact", "mma")
         self.scorer = scorer
         dev = "cuda"
@@ -58,6 +58,7 @@ class FrozenKMeansSweep(object):
             self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
             self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
             self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
+            self.work = torch.empty(lib.segb_mma_refine_work_bytes(c.N, c.K_max), dtype=torch.uint8, device=dev)
             self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)          # (|dx|, |x|) per row
             self.w_err = torch.empty(2 * (c.K_max + 128), dtype=torch.float32, device=dev)  # (|dmu|, |mu^|)
             _lib.check(lib.segb_mma_pack_x(_lib.ptr(c._X), c.N, c.D, _lib.ptr(self.x_tiles), _lib.ptr(self.x_err),
@@ -76,7 +77,7 @@ class FrozenKMeansSweep(object):
                                            _lib.ptr(self.cand), sp))
             self.n_fallback.zero_()
             _lib.check(lib.segb_mma_refine(m, _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_err), c.N,
-                                           _lib.ptr(self.best_val), _lib.ptr(self.best_k),
+                                           _lib.ptr(self.work), _lib.ptr(self.best_val), _lib.ptr(self.best_k),
                                            _lib.ptr(self.n_fallback), sp))
 
     def segment(self):
@@ -117,6 +118,42 @@ class FrozenKMeansSweep(object):
         assert bool((self.cnt[:K] > 0).all().item()), "initial assignments must use labels 0..K-1"
         c._K.fill_(K)
 
+    def profile_phases(self):
+        """Device time of each phase of one sweep (CUDA events on the launching stream); the
+        model is advanced exactly as by sweep().  Diagnostic for bench.py / profiles/."""
+        names, evs = [], [torch.cuda.Event(enable_timing=True)]
+        evs[0].record()
+
+        def mark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            names.append(name)
+            evs.append(e)
+        lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
+        if self.scorer == "mma":
+            _lib.check(lib.segb_mma_pack_means(_lib.ptr(c._means), c.K_max, c.D, _lib.ptr(self.w_tiles),
+                                               _lib.ptr(self.w_err), sp))
+            mark("pack_means")
+            _lib.check(lib.segb_mma_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
+                                           _lib.ptr(self.cand), sp))
+            mark("filter_gemm")
+            self.n_fallback.zero_()
+            _lib.check(lib.segb_mma_refine(c.struct(), _lib.ptr(self.cand), _lib.ptr(self.x_err),
+                                           _lib.ptr(self.w_err), c.N, _lib.ptr(self.work), _lib.ptr(self.best_val),
+                                           _lib.ptr(self.best_k), _lib.ptr(self.n_fallback), sp))
+            mark("refine_exact")
+        else:
+            self.score()
+            mark("score_exact")
+        self.segment()
+        mark("band_scores+viterbi_dp")
+        self.collect()
+        mark("collect_tokens")
+        self.reduce_and_update()
+        mark("allreduce+set_means")
+        torch.cuda.synchronize()
+        return {n: evs[i].elapsed_time(evs[i + 1]) for i, n in enumerate(names)}
+
     def sweep(self):
         """One frozen sweep; returns sum_neg_len_sqrd_norm (summed over all ranks)."""
         c, cp = self.c, self.corpus
@@ -137,32 +174,63 @@ class FrozenKMeansSweep(object):
             t = torch.tensor([total], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             total = float(t.item())
-        if bool((self.cnt[:c.K] == 0).any().item()):
-            c.clean_components()
+        self._clean_components(c.K)
         return total
+
+    def _clean_components(self, K_old):
+        """clean_components() (kmeans_components.py:263-266) without the per-deletion token
+        scan: the swap-with-last sequence is replayed on the host over the K counts (cheap),
+        giving for every surviving slot the component that ends up there; rows are then
+        gathered and tokens relabelled in one pass each."""
+        c = self.c
+        cnt = self.cnt[:K_old].cpu().numpy()
+        empties = np.where(cnt == 0)[0][::-1]
+        if len(empties) == 0:
+            return
+        slot_src = np.arange(K_old)
+        K = K_old
+        for k in empties:                      # del_component(k), :149-166
+            K -= 1
+            if k != K:
+                slot_src[k] = slot_src[K]
+        dst = np.where(slot_src[:K] != np.arange(K))[0]
+        src = slot_src[dst]
+        if len(dst):
+            dst_d, src_d = _lib.dev(dst), _lib.dev(src)
+            c._mean_num[dst_d] = c._mean_num[src_d]
+            c._counts[dst_d] = c._counts[src_d]
+            c._means[dst_d] = c._means[src_d]
+            inv = torch.arange(c.K_max, dtype=torch.int32, device="cuda")
+            inv[src_d] = dst_d.to(torch.int32)
+            tok = self.corpus.tok_id[self.corpus.tok_id >= 0].long()
+            c._assign[tok] = inv[c._assign[tok].long()]
+        c._mean_num[K:K_old] = 0
+        c._counts[K:K_old] = 0
+        c._means[K:K_old] = c._rnd[K:K_old]
+        c._meansT.copy_(c._means.t())
+        c._K.fill_(int(K))
 
     def _clamp_inactive_winners(self, K_before):
         """add_item's `k > K -> K` clamp (kmeans_components.py:103-106) for tokens won by an
         inactive slot.  Sequential by nature; resolved on the host over the (few) affected
         tokens in utterance order, then the statistics are re-collected."""
         c, cp = self.c, self.corpus
-        cnt = self.cnt.cpu().numpy()
-        if not np.any(cnt[K_before:] > 0):
+        if not bool((self.cnt[K_before:] > 0).any().item()):
             return
         assert not _dist_on(), "inactive-slot winners under sharding need a global token order (not implemented)"
-        tok = cp.tok_id.cpu().numpy()
-        ids = tok[tok >= 0]                      # utterance order, left to right
-        ks = self.best_k.cpu().numpy()
+        tok = cp.tok_id[cp.tok_id >= 0].long()            # utterance order, left to right
+        ks_tok = self.best_k[tok]
+        sel = (ks_tok >= K_before).nonzero().flatten()
+        ids = tok[sel].cpu().numpy()
+        ks = ks_tok[sel].cpu().numpy().astype(np.int64)
         K = K_before
-        patched = False
-        for e in ids:
-            k = ks[e]
-            if k >= K:
-                if k > K:
-                    ks[e] = K
-                    patched = True
-                K += 1 if ks[e] == K else 0
+        for i in range(len(ids)):
+            k = ks[i]
+            if k > K:
+                k = K
+            if k == K:
+                K += 1
+            ks[i] = k
         c._K.fill_(int(K))
-        if patched:
-            self.best_k.copy_(torch.from_numpy(ks))
+        self.best_k[_lib.dev(ids)] = _lib.dev(ks.astype(np.int32))
         self.collect()

@@ -382,63 +382,215 @@ __device__ __forceinline__ float exact_neg_dist(const float *meansT, int KM_, in
     return -s;
 }
 
-// One warp per embedding.  Lanes 0-15 re-score the 16 components of the best chunk, lanes
-// 16-31 those of the runner-up chunk when it lies within the error bound; rows whose third
-// chunk is also inside the bound are re-scored against every component.
-__global__ void __launch_bounds__(256) refine_kernel(segb_kmeans m, const Cand *cand, const float *x_err,
-                                                     const float *w_err, int64_t n_emb, int K_pad, float *best_val,
-                                                     int32_t *best_k, unsigned long long *n_fallback) {
-    extern __shared__ float rsm[];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, n_w = blockDim.x >> 5;
-    float *xs = rsm + (size_t)wib * m.D;
-    float *red = rsm + (size_t)n_w * m.D;     // [2 * n_w]
-    // model-wide maxima of the per-component rounding error and norm
-    float e_mu = 0.f, n_mu = 0.f;
-    for (int k = threadIdx.x; k < m.K_max; k += blockDim.x) { e_mu = fmaxf(e_mu, w_err[2 * k]); n_mu = fmaxf(n_mu, w_err[2 * k + 1]); }
-    for (int o = 16; o > 0; o >>= 1) { e_mu = fmaxf(e_mu, __shfl_xor_sync(FULL, e_mu, o)); n_mu = fmaxf(n_mu, __shfl_xor_sync(FULL, n_mu, o)); }
-    if (lane == 0) { red[wib] = e_mu; red[n_w + wib] = n_mu; }
+// ---- binned refine -------------------------------------------------------------------
+// Re-scoring one row needs the 16 float32 means of its best chunk (16 x D x 4 B = 8.3 KB at
+// D = 130).  Fetching those from L2 per row would move ~175 GB per sweep, so rows are first
+// grouped by best chunk (counting sort: histogram -> scan -> scatter); a block then stages ONE
+// chunk's means in shared memory and streams that bin's rows through it, one half-warp per
+// row, lane j <-> candidate j.  Rows whose runner-up chunk lies inside the error bound also
+// visit that chunk (from L2); rows whose third chunk does too are scanned exhaustively.
+
+constexpr int REFINE_THREADS = 256;
+constexpr int ROWS_PER_UNIT = 512;       // rows of one bin handled by one block iteration
+
+struct RefineWork {                      // carved out of the caller's workspace
+    int32_t *perm;                       // [n_emb] rows grouped by best chunk
+    int32_t *bin_cnt, *bin_off, *bin_cur, *unit_off;   // [n_bins + 1] each
+};
+__host__ __device__ inline int n_bins_of(int K_pad) { return K_pad / CHUNK + 1; }   // +1: rows without a chunk
+
+__global__ void refine_hist_kernel(const Cand *cand, int64_t n_emb, int n_bins, int32_t *bin_cnt) {
+    extern __shared__ int32_t sh[];
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    e_mu = 0.f; n_mu = 0.f;
-    for (int i = 0; i < n_w; ++i) { e_mu = fmaxf(e_mu, red[i]); n_mu = fmaxf(n_mu, red[n_w + i]); }
-    const int KP = kp_of(m.D);
-    const float c_acc = ldexpf((float)KP, -21) + ldexpf(1.f, -19);   // fp32 accumulation + reference rounding slack
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_emb; r += (int64_t)gridDim.x * blockDim.x) {
+        int b = cand[r].i1;
+        if (b < 0 || b >= n_bins - 1) b = n_bins - 1;
+        atomicAdd(&sh[b], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) if (sh[i]) atomicAdd(&bin_cnt[i], sh[i]);
+}
+
+__global__ void refine_scan_kernel(int n_bins, const int32_t *bin_cnt, int32_t *bin_off, int32_t *bin_cur,
+                                   int32_t *unit_off) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int32_t o = 0, u = 0;
+        for (int i = 0; i < n_bins; ++i) {
+            bin_off[i] = o; bin_cur[i] = o; unit_off[i] = u;
+            o += bin_cnt[i];
+            u += (bin_cnt[i] + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+        }
+        bin_off[n_bins] = o; unit_off[n_bins] = u;
+    }
+}
+
+__global__ void refine_scatter_kernel(const Cand *cand, int64_t n_emb, int n_bins, int32_t *bin_cur, int32_t *perm) {
+    extern __shared__ int32_t sh[];      // [n_bins] local counts, then [n_bins] claimed bases
+    int32_t *cnt = sh, *base = sh + n_bins;
+    const int64_t per_block = 4096;
+    for (int64_t lo = (int64_t)blockIdx.x * per_block; lo < n_emb; lo += (int64_t)gridDim.x * per_block) {
+        const int64_t hi = lo + per_block < n_emb ? lo + per_block : n_emb;
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) cnt[i] = 0;
+        __syncthreads();
+        for (int64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+            int b = cand[r].i1;
+            if (b < 0 || b >= n_bins - 1) b = n_bins - 1;
+            atomicAdd(&cnt[b], 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) {
+            base[i] = cnt[i] ? atomicAdd(&bin_cur[i], cnt[i]) : 0;
+            cnt[i] = 0;
+        }
+        __syncthreads();
+        for (int64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+            int b = cand[r].i1;
+            if (b < 0 || b >= n_bins - 1) b = n_bins - 1;
+            perm[base[b] + atomicAdd(&cnt[b], 1)] = (int32_t)r;
+        }
+        __syncthreads();
+    }
+}
+
+// exact score of one candidate whose mean is staged as sm[d * CHUNK + j]
+__device__ __forceinline__ float exact_neg_dist_smem(const float *sm, int j, const float *xs, int D) {
+    auto f = [&](int d) -> float {
+        const float dl = __fsub_rn(sm[d * CHUNK + j], xs[d]);
+        return __fmul_rn(dl, dl);
+    };
+    float s;
+    if (D <= 128) s = pairwise_block<float>(f, 0, D);
+    else if (D <= 256) {
+        int n2 = D / 2; n2 -= n2 % 8;
+        s = __fadd_rn(pairwise_block<float>(f, 0, n2), pairwise_block<float>(f, n2, D - n2));
+    } else s = pairwise_sum<float>(f, D);
+    return -s;
+}
+
+__global__ void __launch_bounds__(REFINE_THREADS) refine_binned_kernel(
+    segb_kmeans m, const Cand *cand, const float *x_err, const float *w_err, int64_t n_emb, int n_bins,
+    const int32_t *perm, const int32_t *bin_off, const int32_t *unit_off, float *best_val, int32_t *best_k,
+    unsigned long long *n_fallback, int32_t *fb_list) {
+    extern __shared__ float rsm[];
+    const int D = m.D, KM = m.K_max;
+    const int hw = threadIdx.x >> 4, j = threadIdx.x & 15, n_hw = blockDim.x >> 4;
+    float *sm = rsm;                                 // [D * CHUNK] staged means of the block's chunk
+    float *xs_all = rsm + (size_t)D * CHUNK;         // [n_hw * D] one row per half-warp
+    float *red = xs_all + (size_t)n_hw * D;          // [64]
+    float *xs = xs_all + (size_t)hw * D;
     const float *X = (const float *)m.X;
     const float *meansT = (const float *)m.meansT;
 
-    for (int64_t row = (int64_t)blockIdx.x * n_w + wib; row < n_emb; row += (int64_t)gridDim.x * n_w) {
-        __syncwarp();
-        for (int d = lane; d < m.D; d += 32) xs[d] = X[row * m.D + d];
-        __syncwarp();
-        const Cand c = cand[row];
-        const float ex = x_err[2 * row], nx = x_err[2 * row + 1];
-        // t = x.mu - |mu|^2/2.  |t^ - t| <= ex*|mu^| + |x|*e_mu              (fp16 rounding of the operands)
-        //                    + c_acc*((|x|+ex)*|mu^| + |mu|^2/2)              (fp32 accumulation, bias split)
-        // plus eta = (D+3)*2^-24 * (|x|+|mu|)^2 / 2: the reference's own float32 rounding of the score.
-        const float eta = 0.5f * ldexpf((float)(m.D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
-        const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
-        const float tau = 2.0f * bound;
-        const bool need2 = (c.i2 >= 0) && !(c.m1 - c.m2 > tau);
-        const bool need_all = !(c.m1 - c.m3 > tau) && (c.m3 > -CUDART_INF_F);   // NaN-safe: falls back
+    // model-wide maxima of the per-component rounding error and norm
+    float e_mu = 0.f, n_mu = 0.f;
+    for (int k = threadIdx.x; k < KM; k += blockDim.x) { e_mu = fmaxf(e_mu, w_err[2 * k]); n_mu = fmaxf(n_mu, w_err[2 * k + 1]); }
+    for (int o = 16; o > 0; o >>= 1) { e_mu = fmaxf(e_mu, __shfl_xor_sync(FULL, e_mu, o)); n_mu = fmaxf(n_mu, __shfl_xor_sync(FULL, n_mu, o)); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = e_mu; red[32 + (threadIdx.x >> 5)] = n_mu; }
+    __syncthreads();
+    e_mu = 0.f; n_mu = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { e_mu = fmaxf(e_mu, red[i]); n_mu = fmaxf(n_mu, red[32 + i]); }
+    const float c_acc = ldexpf((float)kp_of(D), -21) + ldexpf(1.f, -19);   // fp32 accumulation slack
+
+    const int total_units = unit_off[n_bins];
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        // which bin owns this unit?  (binary search over unit_off)
+        int lo = 0, hi = n_bins;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (unit_off[mid] <= unit) lo = mid; else hi = mid; }
+        const int bin = lo;
+        const int r0 = bin_off[bin] + (unit - unit_off[bin]) * ROWS_PER_UNIT;
+        const int r1 = min(r0 + ROWS_PER_UNIT, bin_off[bin + 1]);
+        const bool real_bin = bin < n_bins - 1;
+        __syncthreads();
+        if (real_bin)
+            for (int i = threadIdx.x; i < D * CHUNK; i += blockDim.x) {
+                const int d = i / CHUNK, jj = i % CHUNK, k = bin * CHUNK + jj;
+                sm[i] = k < KM ? meansT[(size_t)d * KM + k] : 0.f;
+            }
+        __syncthreads();
+        // both half-warps of a warp iterate together (full-mask shuffles below); the odd one
+        // may be past the end of the bin on the last trip and is then only predicated off
+        for (int rb = r0 + (hw & ~1); rb < r1; rb += n_hw) {
+            const int rr = rb + (hw & 1);
+            const bool active = rr < r1;
+            const int64_t row = perm[active ? rr : r1 - 1];
+            for (int d = j; d < D; d += 16) xs[d] = X[row * D + d];
+            __syncwarp();
+            const Cand c = cand[row];
+            const float ex = x_err[2 * row], nx = x_err[2 * row + 1];
+            // t = x.mu - |mu|^2/2.  |t^ - t| <= ex*|mu^| + |x|*e_mu              (fp16 rounding of the operands)
+            //                    + c_acc*((|x|+ex)*|mu^| + |mu|^2/2)              (fp32 accumulation, bias split)
+            // plus eta = (D+3)*2^-24 * (|x|+|mu|)^2 / 2: the reference's own float32 rounding of the score.
+            const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
+            const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
+            const float tau = 2.0f * bound;
+            const bool need_all = !real_bin || !(tau < CUDART_INF_F) ||
+                                  (!(c.m1 - c.m3 > tau) && (c.m3 > -CUDART_INF_F));
+            const bool need2 = !need_all && (c.i2 >= 0) && !(c.m1 - c.m2 > tau);
+            float bv = -CUDART_INF_F;
+            int bk = 0x7fffffff;
+            if (need_all) {
+                // rare: hand the row to refine_full_kernel (a whole block per row)
+                if (j == 0 && active) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;
+            } else {
+                const int k = bin * CHUNK + j;
+                if (k < KM) { bv = exact_neg_dist_smem(sm, j, xs, D); bk = k; }
+                if (need2) {
+                    const int k2 = c.i2 * CHUNK + j;
+                    if (k2 < KM) {
+                        const float v2 = exact_neg_dist(meansT, KM, k2, xs, D);
+                        if (v2 > bv || (v2 == bv && k2 < bk)) { bv = v2; bk = k2; }
+                    }
+                }
+            }
+            // half-warp argmax, first (lowest k) among equal values -- np.argmax semantics
+            for (int o = 8; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, bv, o);
+                const int ok = __shfl_xor_sync(FULL, bk, o);
+                if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+            }
+            if (j == 0 && active && !need_all) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
+            __syncwarp();
+        }
+    }
+}
+
+// Exhaustive exact scan for the rows the filter could not decide: one block per row.
+__global__ void __launch_bounds__(256) refine_full_kernel(segb_kmeans m, const int32_t *fb_list,
+                                                          const unsigned long long *n_fallback, float *best_val,
+                                                          int32_t *best_k) {
+    extern __shared__ float fsm[];
+    float *xs = fsm;                      // [D]
+    float *rv = fsm + m.D;                // [8] per-warp best value
+    int *rk = (int *)(rv + 8);            // [8] per-warp best index
+    const int D = m.D, KM = m.K_max;
+    const float *X = (const float *)m.X;
+    const float *meansT = (const float *)m.meansT;
+    const long long n = (long long)*n_fallback;
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        const int64_t row = fb_list[i];
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = X[row * D + d];
+        __syncthreads();
         float bv = -CUDART_INF_F;
         int bk = 0x7fffffff;
-        if (need_all || !(tau < CUDART_INF_F)) {
-            for (int k = lane; k < m.K_max; k += 32) {
-                const float v = exact_neg_dist(meansT, m.K_max, k, xs, m.D);
-                if (v > bv || bk == 0x7fffffff) { bv = v; bk = k; }
-            }
-            if (lane == 0 && n_fallback) atomicAdd(n_fallback, 1ull);
-        } else {
-            const int chunk = (lane < 16) ? c.i1 : (need2 ? c.i2 : -1);
-            const int k = chunk * CHUNK + (lane & 15);
-            if (chunk >= 0 && k < m.K_max) { bv = exact_neg_dist(meansT, m.K_max, k, xs, m.D); bk = k; }
+        for (int k = threadIdx.x; k < KM; k += blockDim.x) {
+            const float v = exact_neg_dist(meansT, KM, k, xs, D);
+            if (v > bv || bk == 0x7fffffff) { bv = v; bk = k; }
         }
-        // warp argmax, first (lowest k) among equal values -- np.argmax semantics
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(FULL, bv, o);
             const int ok = __shfl_xor_sync(FULL, bk, o);
             if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
         }
-        if (lane == 0) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
+        if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = bv; rk[threadIdx.x >> 5] = bk; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (rv[w] > bv || (rv[w] == bv && rk[w] < bk)) { bv = rv[w]; bk = rk[w]; }
+            best_val[row] = bv;
+            best_k[row] = (bk == 0x7fffffff) ? -1 : bk;
+        }
     }
 }
 
@@ -508,17 +660,48 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     return 0;
 }
 
+extern "C" int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max) {
+    return (2 * n_emb + 4 * (int64_t)(n_bins_of(k_pad(K_max)) + 1) + 64) * (int64_t)sizeof(int32_t);
+}
+
 extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_err,
-                               int64_t n_emb, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
-    SEGB_CHECK_ARG(m && cand && x_err && w_err && best_val && best_k, "null pointer");
+                               int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
+                               void *stream) {
+    SEGB_CHECK_ARG(m && cand && x_err && w_err && work && best_val && best_k && n_fallback, "null pointer");
     SEGB_CHECK_ARG(!m->x_is_f64, "tensor-core scorer needs float32 embeddings");
-    const int wpb = 8;
-    const size_t smem = sizeof(float) * ((size_t)wpb * m->D + 2 * wpb);
-    int64_t blocks = (n_emb + wpb - 1) / wpb;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    refine_kernel<<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
-        *m, (const Cand *)cand, x_err, w_err, n_emb, k_pad(m->K_max), best_val, best_k,
-        (unsigned long long *)n_fallback);
+    SEGB_CHECK_ARG(n_emb < (1ll << 31), "too many embeddings for one refine call");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_bins = n_bins_of(k_pad(m->K_max));
+    int32_t *w = (int32_t *)work;
+    RefineWork rw;
+    rw.bin_cnt = w; rw.bin_off = w + (n_bins + 1); rw.bin_cur = w + 2 * (n_bins + 1); rw.unit_off = w + 3 * (n_bins + 1);
+    rw.perm = w + 4 * (n_bins + 1) + 16;
+    int32_t *fb_list = rw.perm + n_emb;
+    SEGB_CUDA(cudaMemsetAsync(n_fallback, 0, sizeof(int64_t), st));
+    SEGB_CUDA(cudaMemsetAsync(rw.bin_cnt, 0, sizeof(int32_t) * (n_bins + 1), st));
+    const Cand *cd = (const Cand *)cand;
+    int64_t hb = (n_emb + 256 * 16 - 1) / (256 * 16);
+    if (hb > 148 * 8) hb = 148 * 8;
+    refine_hist_kernel<<<(unsigned)hb, 256, sizeof(int32_t) * n_bins, st>>>(cd, n_emb, n_bins, rw.bin_cnt);
+    SEGB_LAUNCH_CHECK();
+    refine_scan_kernel<<<1, 32, 0, st>>>(n_bins, rw.bin_cnt, rw.bin_off, rw.bin_cur, rw.unit_off);
+    SEGB_LAUNCH_CHECK();
+    int64_t sb = (n_emb + 4095) / 4096;
+    if (sb > 148 * 8) sb = 148 * 8;
+    refine_scatter_kernel<<<(unsigned)sb, 256, 2 * sizeof(int32_t) * n_bins, st>>>(cd, n_emb, n_bins, rw.bin_cur, rw.perm);
+    SEGB_LAUNCH_CHECK();
+    const int n_hw = REFINE_THREADS / 16;
+    const size_t smem = sizeof(float) * ((size_t)m->D * CHUNK + (size_t)n_hw * m->D + 64);
+    if (smem > 48 * 1024)
+        SEGB_CUDA(cudaFuncSetAttribute(refine_binned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (n_emb + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT + n_bins;
+    if (blocks > 148 * 6) blocks = 148 * 6;
+    refine_binned_kernel<<<(unsigned)blocks, REFINE_THREADS, smem, st>>>(
+        *m, cd, x_err, w_err, n_emb, n_bins, rw.perm, rw.bin_off, rw.unit_off, best_val, best_k,
+        (unsigned long long *)n_fallback, fb_list);
+    SEGB_LAUNCH_CHECK();
+    refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(
+        *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
     SEGB_LAUNCH_CHECK();
     return 0;
 }

@@ -24,7 +24,8 @@ class KMeansComponents(object):
         self.K_max = int(K_max)
         assignments = np.asarray(assignments, dtype=np.int64)
         assert (self.N,) == assignments.shape
-        assert set(assignments).difference([-1]) == set(range(assignments.max() + 1))
+        used = np.unique(assignments[assignments >= 0])
+        assert np.array_equal(used, np.arange(assignments.max() + 1))       # labels 0..max, no gaps (:69-70)
         self.setup_random_means()                                           # :75-76
         _lib.lib()
         tdt = torch.float64 if X.dtype == np.float64 else torch.float32
@@ -42,13 +43,37 @@ class KMeansComponents(object):
         order = order[assignments[order] >= 0]
         self._add_many(order, assignments[order])
 
+    @classmethod
+    def from_device(cls, X_dev, K_max, random_means_dev):
+        """Bench-scale constructor: embeddings already resident in HBM (float32 [N, D] CUDA
+        tensor), no items assigned yet.  `X` (host mirror) is not kept."""
+        self = cls.__new__(cls)
+        assert X_dev.is_cuda and X_dev.dtype == torch.float32 and X_dev.is_contiguous()
+        _lib.lib()
+        self.X = None
+        self.N, self.D = int(X_dev.shape[0]), int(X_dev.shape[1])
+        self.K_max = int(K_max)
+        self.random_means = None
+        self._X = X_dev
+        self._x_is_f64 = False
+        self._mean_num = torch.zeros(self.K_max, self.D, dtype=torch.float64, device="cuda")
+        self._rnd = random_means_dev.contiguous()
+        self._means = self._rnd.clone()
+        self._meansT = self._rnd.t().contiguous()
+        self._counts = torch.zeros(self.K_max, dtype=torch.int32, device="cuda")
+        self._assign = torch.full((self.N,), -1, dtype=torch.int32, device="cuda")
+        self._K = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self._row = torch.empty(self.K_max, dtype=torch.float32, device="cuda")
+        self._relabel = None
+        return self
+
     def setup_random_means(self):
         """:90-91 (consumes np.random exactly like the reference)."""
         self.random_means = self.X[np.random.choice(range(self.N), self.K_max, replace=True), :]
 
     def struct(self):
         m = _lib.KMeansM()
-        m.D, m.K_max, m.x_is_f64, m.n_emb = self.D, self.K_max, int(self.X.dtype == np.float64), self.N
+        m.D, m.K_max, m.x_is_f64, m.n_emb = self.D, self.K_max, int(self._X.dtype == torch.float64), self.N
         m.X, m.mean_num = self._X.data_ptr(), self._mean_num.data_ptr()
         m.means, m.meansT, m.random_means = self._means.data_ptr(), self._meansT.data_ptr(), self._rnd.data_ptr()
         m.counts, m.assignments, m.K = self._counts.data_ptr(), self._assign.data_ptr(), self._K.data_ptr()

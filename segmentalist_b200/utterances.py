@@ -194,19 +194,19 @@ class DeviceCorpus(object):
         return c
 
     def refresh_tokens_from_bounds(self):
-        """tok_id[p] = embedding id of the token ending at landmark p (host pass; used at
-        initialisation and after the host edits `boundaries`)."""
+        """tok_id[p] = embedding id of the token ending at landmark p (vectorised host pass;
+        used at initialisation and after the host edits `boundaries`)."""
         b = self.bounds.cpu().numpy().astype(bool)
         seg = self.seg_id.cpu().numpy()
         tok = np.full(self.n_pos, -1, dtype=np.int32)
-        for u in range(self.n_utt):
-            lo, hi = self.pos_off_h[u], self.pos_off_h[u + 1]
-            prev = 0
-            for j in np.where(b[lo:hi])[0]:
-                span = int(j) + 1 - prev
-                if span <= self.S:
-                    tok[lo + j] = seg[lo + j, span - 1]
-                prev = int(j) + 1
+        idx = np.where(b)[0]
+        if len(idx):
+            utt = np.searchsorted(self.pos_off_h, idx, "right") - 1
+            first = np.concatenate([[True], utt[1:] != utt[:-1]])
+            start = np.where(first, self.pos_off_h[utt], np.concatenate([[0], idx[:-1] + 1]))
+            span = idx - start + 1
+            ok = span <= self.S
+            tok[idx[ok]] = seg[idx[ok], span[ok] - 1]
         self.tok_id.copy_(torch.from_numpy(tok))
 
     def boundaries_matrix(self):

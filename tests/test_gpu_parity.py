@@ -379,12 +379,13 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
     val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
     arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
     nfb = torch.zeros(1, dtype=torch.int64, device="cuda")
+    work = torch.empty(lib.segb_mma_refine_work_bytes(n_emb, K_max), dtype=torch.uint8, device="cuda")
     sp = _lib.stream_ptr()
     _lib.check(lib.segb_mma_pack_x(_lib.ptr(comps._X), n_emb, 130, _lib.ptr(x_tiles), _lib.ptr(x_err), sp))
     _lib.check(lib.segb_mma_pack_means(_lib.ptr(comps._means), K_max, 130, _lib.ptr(w_tiles), _lib.ptr(w_err), sp))
     _lib.check(lib.segb_mma_filter(_lib.ptr(x_tiles), _lib.ptr(w_tiles), n_emb, K_max, 130, _lib.ptr(cand), sp))
     _lib.check(lib.segb_mma_refine(comps.struct(), _lib.ptr(cand), _lib.ptr(x_err), _lib.ptr(w_err), n_emb,
-                                   _lib.ptr(val), _lib.ptr(arg), _lib.ptr(nfb), sp))
+                                   _lib.ptr(work), _lib.ptr(val), _lib.ptr(arg), _lib.ptr(nfb), sp))
     torch.cuda.synchronize()
     npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
     npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
