@@ -359,13 +359,11 @@ def run_ours(args):
         sp = _lib.stream_ptr()
         if args.scorer == "mma":
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            _lib.check(lib.segb_mma_filter(_lib.ptr(sweep.x_tiles), _lib.ptr(sweep.w_tiles), M, args.K, D,
-                                           _lib.ptr(sweep.cand), sp))
+            sweep.mma.filter()
             torch.cuda.synchronize()
             e0.record()
             for _ in range(reps):
-                _lib.check(lib.segb_mma_filter(_lib.ptr(sweep.x_tiles), _lib.ptr(sweep.w_tiles), M, args.K, D,
-                                               _lib.ptr(sweep.cand), sp))
+                sweep.mma.filter()
             e1.record()
             torch.cuda.synchronize()
             k_ms = e0.elapsed_time(e1) / reps
@@ -407,8 +405,7 @@ def run_ours(args):
             comps._X.copy_(X_host, non_blocking=True)                       # H2D embeddings
             comps._means.copy_(means_host, non_blocking=True)               # H2D model
             comps._meansT.copy_(comps._means.t())
-            _lib.check(lib.segb_mma_pack_x(_lib.ptr(comps._X), M, D, _lib.ptr(sweep.x_tiles), _lib.ptr(sweep.x_err),
-                                           _lib.stream_ptr()))
+            sweep.mma.pack_x()                                              # fp16 tile image of the fresh upload
             total_host.append(sweep.sweep())                                # sweep (includes result syncs)
             bounds_host.copy_(corpus.bounds, non_blocking=True)             # D2H segmentation
             assign_host.copy_(comps._assign, non_blocking=True)             # D2H assignments
@@ -472,7 +469,7 @@ def run_ours(args):
                        "candidate_segments": int(tot[1].item()), "scorer": args.scorer,
                        "parallelism": "utterance shards x%d + NCCL all-reduce(sum_x, counts)" % world,
                        "l2": "inputs (fp16 tile image %.1f GB per rank) exceed L2; no flush needed"
-                             % (sweep.x_tiles.numel() / 1e9 if args.scorer == "mma" else X.numel() * 4 / 1e9)},
+                             % (sweep.mma.x_tiles.numel() / 1e9 if args.scorer == "mma" else X.numel() * 4 / 1e9)},
             "segment_component_evals_per_s": evals_per_s,
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,

@@ -219,26 +219,29 @@ int64_t segb_mma_x_tiles_bytes(int64_t n_emb, int32_t D);
 int64_t segb_mma_w_tiles_bytes(int32_t K_max, int32_t D);
 int64_t segb_mma_cand_bytes(int64_t n_emb);
 
-/* Ingest: write the fp16 UMMA-canonical tile image of X (done once; X is
- * constant across sweeps) and the per-row rounding-error norms used by the
- * rigorous candidate threshold.                                               */
-int segb_mma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, float *x_err, void *stream);
-/* Per sweep: tile image of the K_max float32 means, with -|mu|^2/2 folded into
- * padding columns of the inner dimension.                                     */
-int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D, void *w_tiles, float *w_err,
+/* Ingest: write the fp16 UMMA-canonical tile image of X (done once; X is constant across
+ * sweeps).  x_err [2 * n_emb]: per row (|x - fp16(x)|, |x|); x_max [2]: their maxima -- the
+ * inputs of the rigorous candidate threshold.                                                */
+int segb_mma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, float *x_err, float *x_max,
+                    void *stream);
+/* Per sweep: tile image of the K_max float32 means, with -|mu|^2/2 folded into padding columns
+ * of the inner dimension.  w_err [2 * (K_max + 128)]: per component (|mu - fp16(mu)|,
+ * |fp16(mu)|); w_max [2]: their maxima.                                                      */
+int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D, void *w_tiles, float *w_err, float *w_max,
                         void *stream);
-/* Filter GEMM (tcgen05.mma kind::f16, fp32 accumulate in TMEM, operands staged
- * by cp.async.bulk): for every embedding the best / second / third 16-component
- * chunk of x.mu - |mu|^2/2.  cand: opaque per-row records for segb_mma_refine. */
+/* Filter GEMM (tcgen05.mma kind::f16, fp32 accumulate in TMEM, operands staged by
+ * cp.async.bulk): for every embedding the best / second / third 16-component chunk of
+ * x.mu - |mu|^2/2 and, for the best two, which members lie within the error bound of the
+ * chunk maximum.  cand: opaque 32-byte per-row records for segb_mma_refine.                  */
 int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
-                    void *cand, void *stream);
-/* Refine: group rows by best chunk (counting sort), stage each chunk's 16 float32 means in
- * shared memory and re-score the candidates exactly (float32, NumPy order, same arithmetic
- * as segb_kmeans_best) -> bit-exact max / first argmax.  work: segb_mma_refine_work_bytes()
- * bytes of scratch.  n_fallback (device, required; reset by the call) counts rows that needed
- * the exhaustive scan (run by a second kernel, one block per such row). */
+                    const float *x_max, const float *w_max, void *cand, void *stream);
+/* Refine: re-score the surviving candidates (normally one per embedding) exactly -- float32,
+ * NumPy pairwise order, same bits as segb_kmeans_best -> bit-exact max / first argmax.
+ * work: segb_mma_refine_work_bytes() bytes of scratch.  n_fallback (device, required; reset by
+ * the call) counts rows whose third-best chunk was still inside the bound: those get an
+ * exhaustive exact scan (second kernel, one block per such row).                             */
 int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max);
-int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_err,
+int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_max,
                     int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
                     void *stream);
 

@@ -72,9 +72,9 @@ _PROTOS = {
     "segb_mma_x_tiles_bytes": (c_i64, [c_i64, c_i32]),
     "segb_mma_w_tiles_bytes": (c_i64, [c_i32, c_i32]),
     "segb_mma_cand_bytes": (c_i64, [c_i64]),
-    "segb_mma_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
-    "segb_mma_pack_means": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
-    "segb_mma_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "segb_mma_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "segb_mma_pack_means": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "segb_mma_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "segb_mma_refine_work_bytes": (c_i64, [c_i64, c_i32]),
     "segb_mma_refine": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                        c_vp]),

@@ -34,6 +34,55 @@ def _dist_on():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+class MmaScorer(object):
+    """Buffers and call sequence of the tensor-core scorer (segb_mma_*): fp16 tile images of
+    the embeddings (packed once) and of the means (packed per sweep), the 32-byte per-row
+    filter records, and the per-row / per-component rounding-error norms behind the rigorous
+    candidate threshold."""
+
+    def __init__(self, components):
+        lib, c, dev = _lib.lib(), components, "cuda"
+        assert c._X.dtype == torch.float32, "tensor-core scorer needs float32 embeddings"
+        self.c = c
+        self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
+        self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
+        self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
+        self.work = torch.empty(lib.segb_mma_refine_work_bytes(c.N, c.K_max), dtype=torch.uint8, device=dev)
+        self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)              # (|dx|, |x|) per row
+        self.w_err = torch.empty(2 * (c.K_max + 128), dtype=torch.float32, device=dev)  # (|dmu|, |mu^|)
+        self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.w_max = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.pack_x()
+
+    def pack_x(self):
+        c = self.c
+        _lib.check(_lib.lib().segb_mma_pack_x(_lib.ptr(c._X), c.N, c.D, _lib.ptr(self.x_tiles), _lib.ptr(self.x_err),
+                                              _lib.ptr(self.x_max), _lib.stream_ptr()))
+
+    def pack_means(self):
+        c = self.c
+        _lib.check(_lib.lib().segb_mma_pack_means(_lib.ptr(c._means), c.K_max, c.D, _lib.ptr(self.w_tiles),
+                                                  _lib.ptr(self.w_err), _lib.ptr(self.w_max), _lib.stream_ptr()))
+
+    def filter(self):
+        c = self.c
+        _lib.check(_lib.lib().segb_mma_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
+                                              _lib.ptr(self.x_max), _lib.ptr(self.w_max), _lib.ptr(self.cand),
+                                              _lib.stream_ptr()))
+
+    def refine(self, best_val, best_k):
+        c = self.c
+        _lib.check(_lib.lib().segb_mma_refine(c.struct(), _lib.ptr(self.cand), _lib.ptr(self.x_err),
+                                              _lib.ptr(self.w_max), c.N, _lib.ptr(self.work), _lib.ptr(best_val),
+                                              _lib.ptr(best_k), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+
+    def score(self, best_val, best_k):
+        self.pack_means()
+        self.filter()
+        self.refine(best_val, best_k)
+
+
 class FrozenKMeansSweep(object):
 
     def __init__(self, components, corpus, wip=0.0, scorer="auto"):
@@ -52,17 +101,8 @@ class FrozenKMeansSweep(object):
         self.status = torch.zeros(corpus.n_utt, dtype=torch.int32, device=dev)
         self.sum_x = torch.zeros(c.K_max, c.D, dtype=torch.float64, device=dev)
         self.cnt = torch.zeros(c.K_max, dtype=torch.int64, device=dev)
-        self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
         self.last_fallback = 0
-        if scorer == "mma":
-            self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
-            self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
-            self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
-            self.work = torch.empty(lib.segb_mma_refine_work_bytes(c.N, c.K_max), dtype=torch.uint8, device=dev)
-            self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)          # (|dx|, |x|) per row
-            self.w_err = torch.empty(2 * (c.K_max + 128), dtype=torch.float32, device=dev)  # (|dmu|, |mu^|)
-            _lib.check(lib.segb_mma_pack_x(_lib.ptr(c._X), c.N, c.D, _lib.ptr(self.x_tiles), _lib.ptr(self.x_err),
-                                           _lib.stream_ptr()))
+        self.mma = MmaScorer(c) if scorer == "mma" else None
 
     # ---- phases (each is one or two launches; no host sync inside)
     def score(self):
@@ -71,14 +111,7 @@ class FrozenKMeansSweep(object):
         if self.scorer == "exact":
             _lib.check(lib.segb_kmeans_best(m, None, c.N, _lib.ptr(self.best_val), _lib.ptr(self.best_k), sp))
         else:
-            _lib.check(lib.segb_mma_pack_means(_lib.ptr(c._means), c.K_max, c.D, _lib.ptr(self.w_tiles),
-                                               _lib.ptr(self.w_err), sp))
-            _lib.check(lib.segb_mma_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
-                                           _lib.ptr(self.cand), sp))
-            self.n_fallback.zero_()
-            _lib.check(lib.segb_mma_refine(m, _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_err), c.N,
-                                           _lib.ptr(self.work), _lib.ptr(self.best_val), _lib.ptr(self.best_k),
-                                           _lib.ptr(self.n_fallback), sp))
+            self.mma.score(self.best_val, self.best_k)
 
     def segment(self):
         lib, c, cp, sp = _lib.lib(), self.c, self.corpus, _lib.stream_ptr()
@@ -129,18 +162,13 @@ class FrozenKMeansSweep(object):
             e.record()
             names.append(name)
             evs.append(e)
-        lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
+        c = self.c
         if self.scorer == "mma":
-            _lib.check(lib.segb_mma_pack_means(_lib.ptr(c._means), c.K_max, c.D, _lib.ptr(self.w_tiles),
-                                               _lib.ptr(self.w_err), sp))
+            self.mma.pack_means()
             mark("pack_means")
-            _lib.check(lib.segb_mma_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
-                                           _lib.ptr(self.cand), sp))
+            self.mma.filter()
             mark("filter_gemm")
-            self.n_fallback.zero_()
-            _lib.check(lib.segb_mma_refine(c.struct(), _lib.ptr(self.cand), _lib.ptr(self.x_err),
-                                           _lib.ptr(self.w_err), c.N, _lib.ptr(self.work), _lib.ptr(self.best_val),
-                                           _lib.ptr(self.best_k), _lib.ptr(self.n_fallback), sp))
+            self.mma.refine(self.best_val, self.best_k)
             mark("refine_exact")
         else:
             self.score()
@@ -166,7 +194,7 @@ class FrozenKMeansSweep(object):
         assert np.all(st == _lib.DP_OK), "segmentation failed (status %s)" % np.unique(st)
         total = float(np.cumsum(self.log_prob.cpu().numpy())[-1]) if cp.n_utt else 0.0
         if self.scorer == "mma":
-            self.last_fallback = int(self.n_fallback.item())
+            self.last_fallback = int(self.mma.n_fallback.item())
         if K_before < c.K_max:
             self._clamp_inactive_winners(K_before)
         self.reduce_and_update()

@@ -220,6 +220,157 @@ __global__ void __launch_bounds__(128) dp_banded_kernel(DpParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Short-span fast path: one THREAD per utterance (band width <= 8, N <= DP_SMALL_N,
+// n_slices_min <= 1).  With S = 6 a warp-per-utterance layout leaves 26 of 32 lanes idle and
+// spends its time in shuffles; here the S candidates of a position live in registers, the
+// next position's scores are requested before the current one is reduced, and the float64
+// alphas sit in a per-thread local array (L1-resident).  Same operation order as the
+// warp kernel / the reference, so results are identical.
+constexpr int DP_SMALL_N = 64;
+constexpr int DP_SMALL_S = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(128) dp_small_kernel(DpParams p) {
+    const int u_local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u_local >= p.n_utt) return;
+    const int u = p.utt_first + u_local;
+    const int64_t off = p.pos_off[u];
+    const int N = (int)(p.pos_off[u + 1] - off);
+    const int S = p.S;
+    const int Wlim = (p.n_max == 0 || p.n_max > S) ? S : p.n_max;
+    const double *sc = p.scores + (p.scores_local ? 0 : off * S);
+    uint8_t *bo = p.bounds + off;
+    if (N <= 0) { p.status[u_local] = SEGB_DP_OK; p.log_prob[u_local] = 0.0; return; }
+
+    double al[DP_SMALL_N];
+    al[0] = 0.0;
+    int status = SEGB_DP_OK;
+    double cur[DP_SMALL_S], nxt[DP_SMALL_S];
+#pragma unroll
+    for (int l = 0; l < DP_SMALL_S; ++l) cur[l] = (l < S) ? sc[l] : neg_inf();      // row of t = 1
+
+    // c[l-1] = score(t, l) + alpha[t-l] for l = 1..W; returns max, flags NaN
+    auto cands = [&](const double *row, int t, int W, double *c, bool &has_nan) {
+        double m = neg_inf();
+        has_nan = false;
+#pragma unroll
+        for (int l = 1; l <= DP_SMALL_S; ++l) {
+            if (l <= W) {
+                const double v = row[l - 1] + al[t - l];
+                c[l - 1] = v;
+                has_nan |= (v != v);
+                m = fmax(m, v);
+            } else c[l - 1] = neg_inf();
+        }
+        return m;
+    };
+    // logsumexp in the reference's element order: descending span
+    auto lse_desc = [&](const double *c, int W, double m) {
+        double s = 0.0;
+#pragma unroll
+        for (int l = DP_SMALL_S; l >= 1; --l) if (l <= W) s += exp(c[l - 1] - m);
+        return log(s) + m;
+    };
+
+    for (int t = 1; t < N; ++t) {
+        // request the next row before reducing this one
+#pragma unroll
+        for (int l = 0; l < DP_SMALL_S; ++l) nxt[l] = (l < S) ? sc[(int64_t)t * S + l] : neg_inf();
+        const int W = min(t, Wlim);
+        double c[DP_SMALL_S];
+        bool has_nan;
+        const double m = cands(cur, t, W, c, has_nan);
+        double a_t;
+        if (has_nan) { status = SEGB_DP_NAN; a_t = neg_inf(); }
+        else if (m == neg_inf()) a_t = neg_inf();
+        else if (MODE == SEGB_DP_FFBS) a_t = lse_desc(c, W, m) + p.log_p_continue;
+        else a_t = m;
+        al[t] = a_t;
+#pragma unroll
+        for (int l = 0; l < DP_SMALL_S; ++l) cur[l] = nxt[l];
+    }
+    if (p.alphas) for (int j = 0; j < N; ++j) p.alphas[off + j] = al[j];
+
+    unsigned long long bmask = 1ull << (N - 1);
+    double total = 0.0;
+    int used = 0;
+    const int64_t ubase = p.u_counter ? *p.u_counter : off;
+    int t = N;
+    for (int guard = 0; guard <= N && status == SEGB_DP_OK; ++guard) {
+        int W = min(t, Wlim);
+        double c[DP_SMALL_S], row[DP_SMALL_S];
+        bool has_nan;
+#pragma unroll
+        for (int l = 0; l < DP_SMALL_S; ++l) row[l] = (l < S) ? sc[(int64_t)(t - 1) * S + l] : neg_inf();
+        double m = cands(row, t, W, c, has_nan);
+        if (has_nan && MODE != SEGB_DP_VITERBI_GMM) { status = SEGB_DP_NAN; break; }
+        if (m == neg_inf()) {
+            while (m == neg_inf()) {
+                t = t - 1;
+                if (t == 0) break;
+                W = min(t, Wlim);
+#pragma unroll
+                for (int l = 0; l < DP_SMALL_S; ++l) row[l] = (l < S) ? sc[(int64_t)(t - 1) * S + l] : neg_inf();
+                m = cands(row, t, W, c, has_nan);
+            }
+            if (t == 0) { status = SEGB_DP_INFEASIBLE; break; }
+            bmask |= 1ull << (t - 1);
+        }
+        int idx = 0;
+        if (MODE == SEGB_DP_VITERBI_KMEANS) {
+            idx = W - 1;
+#pragma unroll
+            for (int l = DP_SMALL_S; l >= 1; --l) if (l <= W && c[l - 1] == m) idx = l - 1;   // first maximum
+        } else {
+            const double lse = lse_desc(c, W, m);
+            double pr[DP_SMALL_S];
+            if (MODE == SEGB_DP_FFBS && p.anneal_temp != 1.0) {
+                const double inv_t = 1. / p.anneal_temp;
+                double q[DP_SMALL_S], mq = neg_inf();
+#pragma unroll
+                for (int l = 1; l <= DP_SMALL_S; ++l) if (l <= W) { q[l - 1] = inv_t * (c[l - 1] - lse); mq = fmax(mq, q[l - 1]); }
+                double s2 = 0.0;
+#pragma unroll
+                for (int l = 1; l <= DP_SMALL_S; ++l) if (l <= W) s2 += exp(q[l - 1] - mq);      // ascending span
+                const double lse2 = log(s2) + mq;
+#pragma unroll
+                for (int l = 1; l <= DP_SMALL_S; ++l) pr[l - 1] = (l <= W) ? exp(q[l - 1] - lse2) : 0.0;
+            } else {
+#pragma unroll
+                for (int l = 1; l <= DP_SMALL_S; ++l) pr[l - 1] = (l <= W) ? exp(c[l - 1] - lse) : 0.0;
+            }
+            if (MODE == SEGB_DP_FFBS) {
+                double uu = p.uniforms[ubase + used];
+                used++;
+                idx = W - 1;
+                bool done = false;
+#pragma unroll
+                for (int l = 1; l <= DP_SMALL_S; ++l)
+                    if (l <= W && !done) { uu = uu - pr[l - 1]; if (uu < 0) { idx = l - 1; done = true; } }
+            } else {
+                double pm = -1.0;
+#pragma unroll
+                for (int l = 1; l <= DP_SMALL_S; ++l) if (l <= W) pm = fmax(pm, pr[l - 1]);
+                idx = 0;
+                bool found = false;
+#pragma unroll
+                for (int l = 1; l <= DP_SMALL_S; ++l) if (l <= W && !found && pr[l - 1] == pm) { idx = l - 1; found = true; }
+            }
+        }
+        const int k = idx + 1;
+        total += row[k - 1];
+        if (t - k - 1 < 0) break;
+        bmask |= 1ull << (t - k - 1);
+        t = t - k;
+    }
+    for (int j = 0; j < N; ++j) bo[j] = (uint8_t)((bmask >> j) & 1ull);
+    p.log_prob[u_local] = (status == SEGB_DP_OK) ? total : CUDART_NAN;
+    p.status[u_local] = status;
+    if (p.n_draws) p.n_draws[u_local] = used;
+    if (p.u_counter) *p.u_counter = ubase + used;
+}
+
 int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const double *scores, int32_t mode,
               double log_p_continue, double anneal_temp, const double *uniforms, int64_t *u_counter,
               uint8_t *bounds_out, double *log_prob, double *alphas, int32_t *n_draws, int32_t *status,
@@ -230,6 +381,14 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
     p.bounds = bounds_out; p.log_prob = log_prob; p.alphas = alphas; p.n_draws = n_draws; p.status = status;
     p.utt_first = utt_first; p.n_utt = n_utt; p.S = c->S; p.n_min = c->n_slices_min; p.n_max = c->n_slices_max;
     p.mode = mode; p.N_cap = c->N_max; p.log_p_continue = log_p_continue; p.anneal_temp = anneal_temp;
+    if (c->S <= DP_SMALL_S && c->N_max <= DP_SMALL_N && c->n_slices_min <= 1) {
+        const int threads = 128, blocks = (n_utt + threads - 1) / threads;
+        if (mode == SEGB_DP_FFBS) dp_small_kernel<SEGB_DP_FFBS><<<blocks, threads, 0, stream>>>(p);
+        else if (mode == SEGB_DP_VITERBI_GMM) dp_small_kernel<SEGB_DP_VITERBI_GMM><<<blocks, threads, 0, stream>>>(p);
+        else dp_small_kernel<SEGB_DP_VITERBI_KMEANS><<<blocks, threads, 0, stream>>>(p);
+        SEGB_LAUNCH_CHECK();
+        return 0;
+    }
     const int warps = 4;
     const size_t smem = (size_t)warps * c->N_max * sizeof(double);
     if (smem > 200 * 1024) { set_error("utterance too long for the DP kernel (N_max=%d)", c->N_max); return SEGB_E_UNSUPPORTED; }

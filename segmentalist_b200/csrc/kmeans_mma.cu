@@ -52,7 +52,8 @@ constexpr float PAD_BIAS = -30000.0f;   // -|mu|^2/2 stand-in for padded compone
 struct __align__(32) Cand {        // per-embedding filter record
     float m1, m2, m3;              // best / second / third chunk maximum of t^
     int32_t i1, i2;                // chunk ids of m1, m2
-    int32_t pad[3];
+    uint32_t masks;                // bits 0-15: members of chunk i1 within tau of its max; 16-31: chunk i2
+    int32_t pad[2];
 };
 
 __host__ __device__ inline int kp_of(int D) { return (D + 3 + 15) / 16 * 16; }
@@ -60,6 +61,19 @@ __host__ __device__ inline int64_t tile_bytes_of(int D) { return (int64_t)TILE_R
 // byte offset of element (r, c) inside a 128-row tile image
 __host__ __device__ inline int tile_off(int r, int c) {
     return ((c >> 3) * (TILE_ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (c & 7) * 2;
+}
+
+// Rigorous bound on |t^ - t| for t = x.mu - |mu|^2/2 as computed by the fp16 filter GEMM:
+//   ex*|mu^| + |x|*e_mu                      fp16 rounding of the two operands (Cauchy-Schwarz)
+//   c_acc*((|x|+ex)*|mu^| + |mu|^2/2)        fp32 accumulation in the tensor core, bias split
+//   eta = (D+3)*2^-24*(|x|+|mu|)^2/2         the reference's own float32 rounding of the score
+// ex = |x - fp16(x)|, nx = |x|, e_mu = max_k |mu_k - fp16(mu_k)|, n_mu = max_k |fp16(mu_k)|.
+// A component whose t^ is more than tau = 2*bound below the best t^ cannot be the reference's argmax.
+__host__ __device__ inline float filter_tau(float ex, float nx, float e_mu, float n_mu, int D) {
+    const float c_acc = ldexpf((float)kp_of(D), -21) + ldexpf(1.f, -19);
+    const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
+    const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
+    return 2.0f * bound;
 }
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -137,14 +151,23 @@ struct FilterParams {
     int64_t n_emb;
     int32_t n_mtiles, n_ntiles, n_ksteps, n_stages;
     uint32_t tile_bytes;
+    const float *x_max, *w_max;    // [2] each: corpus-wide (max ex, max nx), model-wide (max e_mu, max n_mu)
+    int32_t D;
 };
 
-__device__ __forceinline__ void top3_insert(float cm, int cid, float &m1, float &m2, float &m3, int &i1, int &i2) {
+// Insert a chunk maximum into the running top-3; chunks entering the top-2 also record which of
+// their 16 members lie within tau_c of the chunk maximum (the only ones the refine has to score).
+__device__ __forceinline__ void top3_insert(const float *vv, float cm, int cid, float tau_c, float &m1, float &m2,
+                                            float &m3, int &i1, int &i2, uint32_t &k1, uint32_t &k2) {
     if (cm > m3) {
         if (cm > m2) {
+            uint32_t mk = 0;
+            const float thr = cm - tau_c;
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) mk |= (vv[j] >= thr) ? (1u << j) : 0u;
             m3 = m2;
-            if (cm > m1) { m2 = m1; i2 = i1; m1 = cm; i1 = cid; }
-            else { m2 = cm; i2 = cid; }
+            if (cm > m1) { m2 = m1; i2 = i1; k2 = k1; m1 = cm; i1 = cid; k1 = mk; }
+            else { m2 = cm; i2 = cid; k2 = mk; }
         } else m3 = cm;
     }
 }
@@ -232,10 +255,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
         // ===================== epilogue: running top-3 chunk maxima per embedding =====================
         const int e = warp - 4, h = e >> 2, q = warp & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        // one threshold for the whole launch: the loosest per-row tau (refine re-derives the exact per-row one)
+        const float tau_c = filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D);
         uint32_t n_use = 0;
         for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
             float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
             int i1 = -1, i2 = -1;
+            uint32_t k1 = 0, k2 = 0;
             for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                 const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
                 mbar_wait(BAR(10 + buf), acc_phase);
@@ -250,7 +276,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                         float cm = v[c * 16];
 #pragma unroll
                         for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
-                        top3_insert(cm, nt * (NT_COLS / CHUNK) + part * 4 + c, m1, m2, m3, i1, i2);
+                        top3_insert(&v[c * 16], cm, nt * (NT_COLS / CHUNK) + part * 4 + c, tau_c, m1, m2, m3, i1, i2,
+                                    k1, k2);
                     }
                 }
                 tc_fence_before();
@@ -260,7 +287,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
             const int64_t row = (int64_t)mt * MT_ROWS + h * TILE_ROWS + q * 32 + lane;
             if (row < p.n_emb) {
                 Cand c;
-                c.m1 = m1; c.m2 = m2; c.m3 = m3; c.i1 = i1; c.i2 = i2; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+                c.m1 = m1; c.m2 = m2; c.m3 = m3; c.i1 = i1; c.i2 = i2;
+                c.masks = (k1 & 0xffffu) | (k2 << 16); c.pad[0] = c.pad[1] = 0;
                 p.cand[row] = c;
             }
         }
@@ -278,7 +306,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
 // One warp per row: lane j converts the 8-element chunk j of the padded row to fp16 and
 // writes its 16 bytes into the tile image.  err[2r] = |x - fp16(x)|_2, err[2r+1] = |x|_2.
 __global__ void pack_x_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad, int D, int KP, uint8_t *tiles,
-                              float *err) {
+                              float *err, float *x_max) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_rows_pad) return;
@@ -307,8 +335,26 @@ __global__ void pack_x_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad,
     for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
     overflow = __any_sync(FULL, overflow);
     if (lane == 0 && row < n_emb) {
-        err[2 * row] = overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f;
-        err[2 * row + 1] = sqrtf(n2) * 1.0001f;
+        const float ex = overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f, nx = sqrtf(n2) * 1.0001f;
+        err[2 * row] = ex;
+        err[2 * row + 1] = nx;
+        // non-negative floats order like their bit patterns
+        atomicMax(reinterpret_cast<int *>(x_max), __float_as_int(ex));
+        atomicMax(reinterpret_cast<int *>(x_max) + 1, __float_as_int(nx));
+    }
+}
+
+// model-wide maxima of the per-component rounding error and norm -> w_max[0..1]
+__global__ void wmax_kernel(const float *w_err, int K_max, float *w_max) {
+    __shared__ float red[64];
+    float e_mu = 0.f, n_mu = 0.f;
+    for (int k = threadIdx.x; k < K_max; k += blockDim.x) { e_mu = fmaxf(e_mu, w_err[2 * k]); n_mu = fmaxf(n_mu, w_err[2 * k + 1]); }
+    for (int o = 16; o > 0; o >>= 1) { e_mu = fmaxf(e_mu, __shfl_xor_sync(FULL, e_mu, o)); n_mu = fmaxf(n_mu, __shfl_xor_sync(FULL, n_mu, o)); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = e_mu; red[32 + (threadIdx.x >> 5)] = n_mu; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { e_mu = fmaxf(e_mu, red[i]); n_mu = fmaxf(n_mu, red[32 + i]); }
+        w_max[0] = e_mu; w_max[1] = n_mu;
     }
 }
 
@@ -368,7 +414,9 @@ namespace segb {
 namespace mma {
 
 // Exact float32 score of component k for the row staged in xs (same routine as kmeans.cu).
-__device__ __forceinline__ float exact_neg_dist(const float *meansT, int KM_, int k, const float *xs, int D) {
+// Cold path (runner-up chunks, exhaustive scans): kept out of line so it does not inflate the
+// register footprint of the hot loops.
+__device__ __noinline__ float exact_neg_dist(const float *meansT, int KM_, int k, const float *xs, int D) {
     auto f = [&](int d) -> float {
         const float dl = __fsub_rn(meansT[(size_t)d * KM_ + k], xs[d]);
         return __fmul_rn(dl, dl);
@@ -382,176 +430,97 @@ __device__ __forceinline__ float exact_neg_dist(const float *meansT, int KM_, in
     return -s;
 }
 
-// ---- binned refine -------------------------------------------------------------------
-// Re-scoring one row needs the 16 float32 means of its best chunk (16 x D x 4 B = 8.3 KB at
-// D = 130).  Fetching those from L2 per row would move ~175 GB per sweep, so rows are first
-// grouped by best chunk (counting sort: histogram -> scan -> scatter); a block then stages ONE
-// chunk's means in shared memory and streams that bin's rows through it, one half-warp per
-// row, lane j <-> candidate j.  Rows whose runner-up chunk lies inside the error bound also
-// visit that chunk (from L2); rows whose third chunk does too are scanned exhaustively.
+// ---- refine ---------------------------------------------------------------------------
+// The filter leaves, per embedding, the best two chunks and a 16-bit mask of the members of
+// each that lie within tau of the chunk maximum -- normally ONE component.  Those are re-scored
+// in the reference's exact arithmetic by a half-warp per embedding: NumPy's pairwise sum keeps 8
+// running accumulators per block of <= 128 terms, so lane q of an 8-lane group owns accumulator
+// q (terms d = q, q+8, ...), the butterfly (xor 1, 2, 4) reproduces the combination tree
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) bit for bit, and the second 8-lane group handles the second
+// block when D > 128.  Loads are coalesced along d (row-major X and means).
+
+// code: -2 exhaustive scan needed, -1 best chunk suffices, >= 0 also visit that chunk.
+__device__ __forceinline__ int refine_decide(const Cand &c, float tau, int n_chunks) {
+    if (c.i1 < 0 || c.i1 >= n_chunks || !(tau < CUDART_INF_F) ||
+        (!(c.m1 - c.m3 > tau) && (c.m3 > -CUDART_INF_F))) return -2;
+    if ((c.i2 >= 0) && !(c.m1 - c.m2 > tau)) return c.i2;
+    return -1;
+}
 
 constexpr int REFINE_THREADS = 256;
-constexpr int ROWS_PER_UNIT = 512;       // rows of one bin handled by one block iteration
+constexpr int REFINE_MAX_STEPS = 16;     // 128 terms / 8 accumulators
 
-struct RefineWork {                      // carved out of the caller's workspace
-    int32_t *perm;                       // [n_emb] rows grouped by best chunk
-    int32_t *bin_cnt, *bin_off, *bin_cur, *unit_off;   // [n_bins + 1] each
-};
-__host__ __device__ inline int n_bins_of(int K_pad) { return K_pad / CHUNK + 1; }   // +1: rows without a chunk
-
-__global__ void refine_hist_kernel(const Cand *cand, int64_t n_emb, int n_bins, int32_t *bin_cnt) {
-    extern __shared__ int32_t sh[];
-    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_emb; r += (int64_t)gridDim.x * blockDim.x) {
-        int b = cand[r].i1;
-        if (b < 0 || b >= n_bins - 1) b = n_bins - 1;
-        atomicAdd(&sh[b], 1);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) if (sh[i]) atomicAdd(&bin_cnt[i], sh[i]);
-}
-
-__global__ void refine_scan_kernel(int n_bins, const int32_t *bin_cnt, int32_t *bin_off, int32_t *bin_cur,
-                                   int32_t *unit_off) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int32_t o = 0, u = 0;
-        for (int i = 0; i < n_bins; ++i) {
-            bin_off[i] = o; bin_cur[i] = o; unit_off[i] = u;
-            o += bin_cnt[i];
-            u += (bin_cnt[i] + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-        }
-        bin_off[n_bins] = o; unit_off[n_bins] = u;
-    }
-}
-
-__global__ void refine_scatter_kernel(const Cand *cand, int64_t n_emb, int n_bins, int32_t *bin_cur, int32_t *perm) {
-    extern __shared__ int32_t sh[];      // [n_bins] local counts, then [n_bins] claimed bases
-    int32_t *cnt = sh, *base = sh + n_bins;
-    const int64_t per_block = 4096;
-    for (int64_t lo = (int64_t)blockIdx.x * per_block; lo < n_emb; lo += (int64_t)gridDim.x * per_block) {
-        const int64_t hi = lo + per_block < n_emb ? lo + per_block : n_emb;
-        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) cnt[i] = 0;
-        __syncthreads();
-        for (int64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
-            int b = cand[r].i1;
-            if (b < 0 || b >= n_bins - 1) b = n_bins - 1;
-            atomicAdd(&cnt[b], 1);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) {
-            base[i] = cnt[i] ? atomicAdd(&bin_cur[i], cnt[i]) : 0;
-            cnt[i] = 0;
-        }
-        __syncthreads();
-        for (int64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
-            int b = cand[r].i1;
-            if (b < 0 || b >= n_bins - 1) b = n_bins - 1;
-            perm[base[b] + atomicAdd(&cnt[b], 1)] = (int32_t)r;
-        }
-        __syncthreads();
-    }
-}
-
-// exact score of one candidate whose mean is staged as sm[d * CHUNK + j]
-__device__ __forceinline__ float exact_neg_dist_smem(const float *sm, int j, const float *xs, int D) {
-    auto f = [&](int d) -> float {
-        const float dl = __fsub_rn(sm[d * CHUNK + j], xs[d]);
-        return __fmul_rn(dl, dl);
-    };
-    float s;
-    if (D <= 128) s = pairwise_block<float>(f, 0, D);
-    else if (D <= 256) {
-        int n2 = D / 2; n2 -= n2 % 8;
-        s = __fadd_rn(pairwise_block<float>(f, 0, n2), pairwise_block<float>(f, n2, D - n2));
-    } else s = pairwise_sum<float>(f, D);
-    return -s;
-}
-
-__global__ void __launch_bounds__(REFINE_THREADS) refine_binned_kernel(
-    segb_kmeans m, const Cand *cand, const float *x_err, const float *w_err, int64_t n_emb, int n_bins,
-    const int32_t *perm, const int32_t *bin_off, const int32_t *unit_off, float *best_val, int32_t *best_k,
-    unsigned long long *n_fallback, int32_t *fb_list) {
-    extern __shared__ float rsm[];
+__global__ void __launch_bounds__(REFINE_THREADS) refine_rows_kernel(
+    segb_kmeans m, const Cand *cand, const float *x_err, const float *w_max, int64_t n_emb, int n_chunks,
+    float *best_val, int32_t *best_k, unsigned long long *n_fallback, int32_t *fb_list) {
     const int D = m.D, KM = m.K_max;
-    const int hw = threadIdx.x >> 4, j = threadIdx.x & 15, n_hw = blockDim.x >> 4;
-    float *sm = rsm;                                 // [D * CHUNK] staged means of the block's chunk
-    float *xs_all = rsm + (size_t)D * CHUNK;         // [n_hw * D] one row per half-warp
-    float *red = xs_all + (size_t)n_hw * D;          // [64]
-    float *xs = xs_all + (size_t)hw * D;
+    const int lane = threadIdx.x & 31, j = lane & 15, g = j >> 3, q = j & 7;
+    const unsigned hmask = 0xffffu << (lane & 16);
+    const int hbase = lane & 16;
     const float *X = (const float *)m.X;
-    const float *meansT = (const float *)m.meansT;
+    const float *means = (const float *)m.means;
+    const float e_mu = w_max[0], n_mu = w_max[1];
+    // block structure of NumPy's pairwise sum for n = D (n <= 128: one block; else split once)
+    int n2 = 0;
+    if (D > 128) { n2 = D / 2; n2 -= n2 % 8; }
+    const int lo_g = g == 0 ? 0 : n2;                         // first term of this group's block
+    const int n_g = (D > 128) ? (g == 0 ? n2 : D - n2) : (g == 0 ? D : 0);
+    const int n8_g = n_g >= 8 ? n_g - (n_g % 8) : 0;          // terms covered by the 8 accumulators
+    const int steps = n8_g / 8;
+    const bool two_blocks = D > 128;
 
-    // model-wide maxima of the per-component rounding error and norm
-    float e_mu = 0.f, n_mu = 0.f;
-    for (int k = threadIdx.x; k < KM; k += blockDim.x) { e_mu = fmaxf(e_mu, w_err[2 * k]); n_mu = fmaxf(n_mu, w_err[2 * k + 1]); }
-    for (int o = 16; o > 0; o >>= 1) { e_mu = fmaxf(e_mu, __shfl_xor_sync(FULL, e_mu, o)); n_mu = fmaxf(n_mu, __shfl_xor_sync(FULL, n_mu, o)); }
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = e_mu; red[32 + (threadIdx.x >> 5)] = n_mu; }
-    __syncthreads();
-    e_mu = 0.f; n_mu = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { e_mu = fmaxf(e_mu, red[i]); n_mu = fmaxf(n_mu, red[32 + i]); }
-    const float c_acc = ldexpf((float)kp_of(D), -21) + ldexpf(1.f, -19);   // fp32 accumulation slack
-
-    const int total_units = unit_off[n_bins];
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        // which bin owns this unit?  (binary search over unit_off)
-        int lo = 0, hi = n_bins;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (unit_off[mid] <= unit) lo = mid; else hi = mid; }
-        const int bin = lo;
-        const int r0 = bin_off[bin] + (unit - unit_off[bin]) * ROWS_PER_UNIT;
-        const int r1 = min(r0 + ROWS_PER_UNIT, bin_off[bin + 1]);
-        const bool real_bin = bin < n_bins - 1;
-        __syncthreads();
-        if (real_bin)
-            for (int i = threadIdx.x; i < D * CHUNK; i += blockDim.x) {
-                const int d = i / CHUNK, jj = i % CHUNK, k = bin * CHUNK + jj;
-                sm[i] = k < KM ? meansT[(size_t)d * KM + k] : 0.f;
-            }
-        __syncthreads();
-        // both half-warps of a warp iterate together (full-mask shuffles below); the odd one
-        // may be past the end of the bin on the last trip and is then only predicated off
-        for (int rb = r0 + (hw & ~1); rb < r1; rb += n_hw) {
-            const int rr = rb + (hw & 1);
-            const bool active = rr < r1;
-            const int64_t row = perm[active ? rr : r1 - 1];
-            for (int d = j; d < D; d += 16) xs[d] = X[row * D + d];
-            __syncwarp();
-            const Cand c = cand[row];
-            const float ex = x_err[2 * row], nx = x_err[2 * row + 1];
-            // t = x.mu - |mu|^2/2.  |t^ - t| <= ex*|mu^| + |x|*e_mu              (fp16 rounding of the operands)
-            //                    + c_acc*((|x|+ex)*|mu^| + |mu|^2/2)              (fp32 accumulation, bias split)
-            // plus eta = (D+3)*2^-24 * (|x|+|mu|)^2 / 2: the reference's own float32 rounding of the score.
-            const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
-            const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
-            const float tau = 2.0f * bound;
-            const bool need_all = !real_bin || !(tau < CUDART_INF_F) ||
-                                  (!(c.m1 - c.m3 > tau) && (c.m3 > -CUDART_INF_F));
-            const bool need2 = !need_all && (c.i2 >= 0) && !(c.m1 - c.m2 > tau);
-            float bv = -CUDART_INF_F;
-            int bk = 0x7fffffff;
-            if (need_all) {
-                // rare: hand the row to refine_full_kernel (a whole block per row)
-                if (j == 0 && active) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;
-            } else {
-                const int k = bin * CHUNK + j;
-                if (k < KM) { bv = exact_neg_dist_smem(sm, j, xs, D); bk = k; }
-                if (need2) {
-                    const int k2 = c.i2 * CHUNK + j;
-                    if (k2 < KM) {
-                        const float v2 = exact_neg_dist(meansT, KM, k2, xs, D);
-                        if (v2 > bv || (v2 == bv && k2 < bk)) { bv = v2; bk = k2; }
+    const int64_t hw_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int64_t hw_total = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    for (int64_t row = hw_global; row < n_emb; row += hw_total) {
+        const Cand c = cand[row];
+        const float tau = filter_tau(x_err[2 * row], x_err[2 * row + 1], e_mu, n_mu, D);
+        const int code = refine_decide(c, tau, n_chunks);
+        if (code == -2) {
+            if (j == 0) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;      // -> refine_full_kernel
+            continue;
+        }
+        const float *xr = X + row * D;
+        float xv[REFINE_MAX_STEPS];
+#pragma unroll
+        for (int i = 0; i < REFINE_MAX_STEPS; ++i) xv[i] = (i < steps) ? xr[lo_g + i * 8 + q] : 0.f;
+        float bv = -CUDART_INF_F;
+        int bk = 0x7fffffff;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            uint32_t mk = pass == 0 ? (c.masks & 0xffffu) : (code >= 0 ? (c.masks >> 16) : 0u);
+            const int chunk = pass == 0 ? c.i1 : c.i2;
+            while (mk) {
+                const int bit = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const int k = chunk * CHUNK + bit;
+                if (k >= KM) continue;
+                const float *mu = means + (size_t)k * D;
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < REFINE_MAX_STEPS; ++i) {
+                    if (i < steps) {
+                        const float dl = __fsub_rn(mu[lo_g + i * 8 + q], xv[i]);
+                        const float pr = __fmul_rn(dl, dl);
+                        acc = (i == 0) ? pr : __fadd_rn(acc, pr);
                     }
                 }
+                // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) inside each 8-lane group
+                acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 1));
+                acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 2));
+                acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 4));
+                // the remaining n % 8 terms of the block are added one by one (lane q == 0 of the group)
+                if (n8_g == 0) acc = 0.f;
+                for (int d = lo_g + n8_g; d < lo_g + n_g; ++d) {
+                    const float dl = __fsub_rn(mu[d], xr[d]);
+                    acc = __fadd_rn(acc, __fmul_rn(dl, dl));
+                }
+                float tot = __shfl_sync(hmask, acc, hbase);
+                if (two_blocks) tot = __fadd_rn(tot, __shfl_sync(hmask, acc, hbase + 8));
+                const float v = -tot;
+                if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; }
             }
-            // half-warp argmax, first (lowest k) among equal values -- np.argmax semantics
-            for (int o = 8; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(FULL, bv, o);
-                const int ok = __shfl_xor_sync(FULL, bk, o);
-                if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-            }
-            if (j == 0 && active && !need_all) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
-            __syncwarp();
         }
+        if (j == 0) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
     }
 }
 
@@ -607,33 +576,38 @@ extern "C" int64_t segb_mma_x_tiles_bytes(int64_t n_emb, int32_t D) { return row
 extern "C" int64_t segb_mma_w_tiles_bytes(int32_t K_max, int32_t D) { return (int64_t)k_pad(K_max) * kp_of(D) * 2; }
 extern "C" int64_t segb_mma_cand_bytes(int64_t n_emb) { return n_emb * (int64_t)sizeof(Cand); }
 
-extern "C" int segb_mma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, float *x_err, void *stream) {
-    SEGB_CHECK_ARG(X && x_tiles && x_err && n_emb > 0 && D > 0, "null pointer");
+extern "C" int segb_mma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, float *x_err, float *x_max,
+                               void *stream) {
+    SEGB_CHECK_ARG(X && x_tiles && x_err && x_max && n_emb > 0 && D > 0, "null pointer");
     const int64_t np_ = rows_pad(n_emb);
     const int wpb = 8;
+    SEGB_CUDA(cudaMemsetAsync(x_max, 0, 2 * sizeof(float), (cudaStream_t)stream));
     pack_x_kernel<<<(unsigned)((np_ + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        X, n_emb, np_, D, kp_of(D), (uint8_t *)x_tiles, x_err);
+        X, n_emb, np_, D, kp_of(D), (uint8_t *)x_tiles, x_err, x_max);
     SEGB_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D, void *w_tiles, float *w_err,
-                                   void *stream) {
-    SEGB_CHECK_ARG(means && w_tiles && w_err && K_max > 0 && D > 0, "null pointer");
+                                   float *w_max, void *stream) {
+    SEGB_CHECK_ARG(means && w_tiles && w_err && w_max && K_max > 0 && D > 0, "null pointer");
     const int kp_rows = k_pad(K_max);
     const int wpb = 8;
     pack_w_kernel<<<(kp_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
         means, K_max, kp_rows, D, kp_of(D), (uint8_t *)w_tiles, w_err);
     SEGB_LAUNCH_CHECK();
+    wmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w_err, K_max, w_max);
+    SEGB_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
-                               void *cand, void *stream) {
-    SEGB_CHECK_ARG(x_tiles && w_tiles && cand && n_emb > 0 && K_max > 0, "null pointer");
+                               const float *x_max, const float *w_max, void *cand, void *stream) {
+    SEGB_CHECK_ARG(x_tiles && w_tiles && cand && x_max && w_max && n_emb > 0 && K_max > 0, "null pointer");
     FilterParams p;
     p.x_tiles = (const uint8_t *)x_tiles; p.w_tiles = (const uint8_t *)w_tiles; p.cand = (Cand *)cand;
     p.n_emb = n_emb;
+    p.x_max = x_max; p.w_max = w_max; p.D = D;
     p.n_mtiles = (int32_t)(rows_pad(n_emb) / MT_ROWS);
     p.n_ntiles = k_pad(K_max) / NT_COLS;
     p.n_ksteps = kp_of(D) / 16;
@@ -661,43 +635,27 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
 }
 
 extern "C" int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max) {
-    return (2 * n_emb + 4 * (int64_t)(n_bins_of(k_pad(K_max)) + 1) + 64) * (int64_t)sizeof(int32_t);
+    (void)K_max;
+    return (n_emb + 64) * (int64_t)sizeof(int32_t);
 }
 
-extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_err,
+extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_max,
                                int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
                                void *stream) {
-    SEGB_CHECK_ARG(m && cand && x_err && w_err && work && best_val && best_k && n_fallback, "null pointer");
+    SEGB_CHECK_ARG(m && cand && x_err && w_max && work && best_val && best_k && n_fallback, "null pointer");
     SEGB_CHECK_ARG(!m->x_is_f64, "tensor-core scorer needs float32 embeddings");
     SEGB_CHECK_ARG(n_emb < (1ll << 31), "too many embeddings for one refine call");
+    {   // the half-warp scheme covers NumPy's pairwise structure up to one split with blocks <= 128
+        int n2 = m->D / 2; n2 -= n2 % 8;
+        SEGB_CHECK_ARG(m->D <= 128 || (m->D <= 256 && m->D - n2 <= 128), "refine: unsupported D");
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_bins = n_bins_of(k_pad(m->K_max));
-    int32_t *w = (int32_t *)work;
-    RefineWork rw;
-    rw.bin_cnt = w; rw.bin_off = w + (n_bins + 1); rw.bin_cur = w + 2 * (n_bins + 1); rw.unit_off = w + 3 * (n_bins + 1);
-    rw.perm = w + 4 * (n_bins + 1) + 16;
-    int32_t *fb_list = rw.perm + n_emb;
+    int32_t *fb_list = (int32_t *)work;
     SEGB_CUDA(cudaMemsetAsync(n_fallback, 0, sizeof(int64_t), st));
-    SEGB_CUDA(cudaMemsetAsync(rw.bin_cnt, 0, sizeof(int32_t) * (n_bins + 1), st));
-    const Cand *cd = (const Cand *)cand;
-    int64_t hb = (n_emb + 256 * 16 - 1) / (256 * 16);
-    if (hb > 148 * 8) hb = 148 * 8;
-    refine_hist_kernel<<<(unsigned)hb, 256, sizeof(int32_t) * n_bins, st>>>(cd, n_emb, n_bins, rw.bin_cnt);
-    SEGB_LAUNCH_CHECK();
-    refine_scan_kernel<<<1, 32, 0, st>>>(n_bins, rw.bin_cnt, rw.bin_off, rw.bin_cur, rw.unit_off);
-    SEGB_LAUNCH_CHECK();
-    int64_t sb = (n_emb + 4095) / 4096;
-    if (sb > 148 * 8) sb = 148 * 8;
-    refine_scatter_kernel<<<(unsigned)sb, 256, 2 * sizeof(int32_t) * n_bins, st>>>(cd, n_emb, n_bins, rw.bin_cur, rw.perm);
-    SEGB_LAUNCH_CHECK();
-    const int n_hw = REFINE_THREADS / 16;
-    const size_t smem = sizeof(float) * ((size_t)m->D * CHUNK + (size_t)n_hw * m->D + 64);
-    if (smem > 48 * 1024)
-        SEGB_CUDA(cudaFuncSetAttribute(refine_binned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (n_emb + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT + n_bins;
-    if (blocks > 148 * 6) blocks = 148 * 6;
-    refine_binned_kernel<<<(unsigned)blocks, REFINE_THREADS, smem, st>>>(
-        *m, cd, x_err, w_err, n_emb, n_bins, rw.perm, rw.bin_off, rw.unit_off, best_val, best_k,
+    int64_t blocks = (n_emb * 16 + REFINE_THREADS - 1) / REFINE_THREADS;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    refine_rows_kernel<<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+        *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
         (unsigned long long *)n_fallback, fb_list);
     SEGB_LAUNCH_CHECK();
     refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(

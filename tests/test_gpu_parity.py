@@ -370,22 +370,12 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
     np.random.seed(1)
     comps = KMeansComponents(X, assign, K_max)
     val_e, arg_e = comps.best(None)
-    lib = _lib.lib()
-    x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(n_emb, 130), dtype=torch.uint8, device="cuda")
-    w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(K_max, 130), dtype=torch.uint8, device="cuda")
-    cand = torch.empty(lib.segb_mma_cand_bytes(n_emb), dtype=torch.uint8, device="cuda")
-    x_err = torch.empty(2 * n_emb, dtype=torch.float32, device="cuda")
-    w_err = torch.empty(2 * (K_max + 128), dtype=torch.float32, device="cuda")
+    from segmentalist_b200.batch import MmaScorer
+    mma = MmaScorer(comps)
     val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
     arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
-    nfb = torch.zeros(1, dtype=torch.int64, device="cuda")
-    work = torch.empty(lib.segb_mma_refine_work_bytes(n_emb, K_max), dtype=torch.uint8, device="cuda")
-    sp = _lib.stream_ptr()
-    _lib.check(lib.segb_mma_pack_x(_lib.ptr(comps._X), n_emb, 130, _lib.ptr(x_tiles), _lib.ptr(x_err), sp))
-    _lib.check(lib.segb_mma_pack_means(_lib.ptr(comps._means), K_max, 130, _lib.ptr(w_tiles), _lib.ptr(w_err), sp))
-    _lib.check(lib.segb_mma_filter(_lib.ptr(x_tiles), _lib.ptr(w_tiles), n_emb, K_max, 130, _lib.ptr(cand), sp))
-    _lib.check(lib.segb_mma_refine(comps.struct(), _lib.ptr(cand), _lib.ptr(x_err), _lib.ptr(w_err), n_emb,
-                                   _lib.ptr(work), _lib.ptr(val), _lib.ptr(arg), _lib.ptr(nfb), sp))
+    mma.score(val, arg)
+    cand, nfb = mma.cand, mma.n_fallback
     torch.cuda.synchronize()
     npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
     npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
@@ -407,3 +397,38 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
                                   bv.ctypes.data_as(fp), bk.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
     npt.assert_array_equal(bk, arg.cpu().numpy()[ids])
     npt.assert_array_equal(bv, val.cpu().numpy()[ids])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("S", [1, 3, 6, 8])
+def test_dp_small_fastpath_vs_oracle(sb, mode, S):
+    """Thread-per-utterance DP kernel (band <= 8, N <= 64): ragged lengths incl. N = 1, -inf holes
+    that force back-tracking, annealed FFBS."""
+    rng = np.random.RandomState(500 + 11 * mode + S)
+    cases = []
+    for _ in range(3000):
+        N = int(rng.randint(1, 61))
+        vec = -np.inf * np.ones(N * (N + 1) // 2)
+        hole = rng.choice([0.0, 0.05, 0.3])
+        for t in range(1, N + 1):
+            for j in range(max(0, t - S), t):
+                if rng.rand() < hole:
+                    continue
+                vec[t * (t - 1) // 2 + j] = rng.randn() * 6 - 2
+        cases.append(dict(vec=vec, N=N, u=rng.rand(N + 1)))
+    temp = 2.0 if (mode == 0 and S == 3) else 1.0
+    res = _run_dp_batch(cases, S, 0, S, mode, temp)
+    n_ok = n_bad = 0
+    for c, (st, lp, b, al, nd) in zip(cases, res):
+        ost, olp, ob, oal, oused = so.dp_packed_c(c["vec"], c["N"], 0, S, mode, c["u"], temp)
+        assert st == ost, (st, ost, c["N"])
+        if ost != 0:
+            n_bad += 1
+            continue
+        n_ok += 1
+        assert np.array_equal(b, ob)
+        assert nd == oused
+        npt.assert_allclose(lp, olp, rtol=1e-12)
+        fin = np.isfinite(oal)
+        npt.assert_allclose(al[fin], oal[fin], rtol=1e-12, atol=1e-12)
+    assert n_ok > 1500 and n_bad > 0
