@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--scorer", default="mma", choices=["mma", "exact"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gibbs", action="store_true", help="skip the secondary workload (BASELINE configs[1])")
+    ap.add_argument("--gibbs-utts", type=int, default=2000)
+    ap.add_argument("--only-gibbs", action="store_true", help="run only the secondary Gibbs workload")
     return ap.parse_args()
 
 
@@ -267,6 +270,78 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary workload: sequential collapsed Gibbs (BASELINE configs[1]); replicas only, so N = 1
+# ------------------------------------------------------------------------------------------------
+
+def run_gibbs_extra(args):
+    """UnigramAcousticWordseg.gibbs_sample on synthetic D=130, K=1000, 2k utterances, max_span 6,
+    through the reference-facing API; CPU oracle timed on a bounded sample of the same corpus
+    with identical seeds (so the first utterances are also a parity check)."""
+    import random
+
+    import torch
+    from oracle import seg_oracle as so
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf, synth
+    from segmentalist_b200 import unigram_acoustic_wordseg as uaw
+    K, n_utt = 1000, args.gibbs_utts
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K, n_min=N_LO, n_max=N_HI,
+                                                    n_slices_max=S_MAX, noise=NOISE, seed=31)
+    var = 0.002 * np.ones(D)
+    prior = gcf.FixedVarPrior(var, np.zeros(D), var / 0.05)
+    random.seed(3)
+    np.random.seed(3)
+    t0 = time.perf_counter()
+    seg = uaw.UnigramAcousticWordseg(fbgmm.FBGMM, 10., K, prior, mats, vids, durs, lms, p_boundary_init=0.5,
+                                     beta_sent_boundary=-1, n_slices_max=S_MAX)
+    setup_s = time.perf_counter() - t0
+    n_seg = int(sum(m.shape[0] for m in mats.values()))
+    order = list(range(n_utt))
+    seg._sweep(order, 1, False)                       # warm-up sweep
+    torch.cuda.synchronize()
+    reps = 2
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(reps):
+        seg._sweep(order, 1, False)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    dev_s = ev0.elapsed_time(ev1) * 1e-3 / reps
+    out = {"workload": "unigram_fbgmm_fixedvar_gibbs_sweep D=130 K=1000 U=%d max_span=6 (BASELINE configs[1])" % n_utt,
+           "utt_per_s": n_utt / max(wall, dev_s), "ms_per_sweep": max(wall, dev_s) * 1e3,
+           "device_ms_per_sweep": dev_s * 1e3, "candidate_segments": n_seg,
+           "segment_component_evals_per_s": n_seg * K / max(wall, dev_s),
+           "K_active": seg.acoustic_model.components.K, "setup_s": setup_s, "dtype": "f64"}
+    if not args.no_cpu:
+        # CPU oracle: same construction + seeds, a bounded number of gibbs_sample_i calls
+        n_cpu = 24
+        random.seed(3)
+        np.random.seed(3)
+        oprior = so.FixedVarPrior(var, np.zeros(D), var / 0.05)
+        oseg = so.UnigramAcousticWordseg(so.FBGMM, 10., K, oprior, mats, vids, durs, lms, p_boundary_init=0.5,
+                                         beta_sent_boundary=-1, n_slices_max=S_MAX)
+        random.seed(3)
+        np.random.seed(3)
+        gseg = uaw.UnigramAcousticWordseg(fbgmm.FBGMM, 10., K, prior, mats, vids, durs, lms, p_boundary_init=0.5,
+                                          beta_sent_boundary=-1, n_slices_max=S_MAX)
+        st = random.getstate()
+        t0 = time.perf_counter()
+        for u in range(n_cpu):
+            oseg.gibbs_sample_i(u)
+        dt = time.perf_counter() - t0
+        random.setstate(st)
+        gseg._sweep(list(range(n_cpu)), 1, False)
+        same = bool(np.array_equal(gseg.utterances.boundaries[:n_cpu], oseg.utterances.boundaries[:n_cpu]) and
+                    np.array_equal(gseg.acoustic_model.components.assignments,
+                                   oseg.acoustic_model.components.assignments))
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "utt/s", "cores": 1, "kind": "port",
+                               "sample": "%d gibbs_sample_i calls of the same seeded corpus/model" % n_cpu,
+                               "seconds": dt, "identical_samples_on_sample": same}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 
@@ -460,6 +535,12 @@ def run_ours(args):
                                   "oracle port of the reference's pure functions" % (n_s, int((ids >= 0).sum()), args.K),
                         "seconds": dt, "parity_with_gpu_on_sample": parity}
 
+    gibbs = None
+    if rank == 0 and world == 1 and not args.no_gibbs:
+        try:
+            gibbs = run_gibbs_extra(args)
+        except Exception as exc:                      # the headline line must still be printed
+            gibbs = {"error": repr(exc)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
@@ -474,6 +555,7 @@ def run_ours(args):
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "roofline_dp": roofline_dp, "cpu_baseline": cpu_baseline, "phases_ms": phases,
+            "secondary_gibbs_fixedvar": gibbs,
         }
         print(json.dumps(line))
     if world > 1:
@@ -484,6 +566,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.only_gibbs:
+        print(json.dumps({"secondary_gibbs_fixedvar": run_gibbs_extra(args)}))
     else:
         run_ours(args)
 

@@ -28,10 +28,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-
-
-def _dist_on():
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+from .sharding import clamp_plan, compaction_plan, dist_on as _dist_on, reduce_stats
 
 
 class MmaScorer(object):
@@ -136,9 +133,7 @@ class FrozenKMeansSweep(object):
     def reduce_and_update(self):
         """All-reduce the sufficient statistics over ranks (NCCL over NVLink), rebuild means."""
         lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
-        if _dist_on():
-            dist.all_reduce(self.sum_x, op=dist.ReduceOp.SUM)
-            dist.all_reduce(self.cnt, op=dist.ReduceOp.SUM)
+        reduce_stats(self.sum_x, self.cnt)
         _lib.check(lib.segb_kmeans_set_means(c.struct(), _lib.ptr(self.sum_x), _lib.ptr(self.cnt), sp))
 
     def init_means_from_assignments(self):
@@ -212,17 +207,9 @@ class FrozenKMeansSweep(object):
         gathered and tokens relabelled in one pass each."""
         c = self.c
         cnt = self.cnt[:K_old].cpu().numpy()
-        empties = np.where(cnt == 0)[0][::-1]
-        if len(empties) == 0:
+        if not np.any(cnt == 0):
             return
-        slot_src = np.arange(K_old)
-        K = K_old
-        for k in empties:                      # del_component(k), :149-166
-            K -= 1
-            if k != K:
-                slot_src[k] = slot_src[K]
-        dst = np.where(slot_src[:K] != np.arange(K))[0]
-        src = slot_src[dst]
+        K, dst, src = compaction_plan(cnt, K_old)
         if len(dst):
             dst_d, src_d = _lib.dev(dst), _lib.dev(src)
             c._mean_num[dst_d] = c._mean_num[src_d]
@@ -243,22 +230,26 @@ class FrozenKMeansSweep(object):
         inactive slot.  Sequential by nature; resolved on the host over the (few) affected
         tokens in utterance order, then the statistics are re-collected."""
         c, cp = self.c, self.corpus
-        if not bool((self.cnt[K_before:] > 0).any().item()):
+        flag = (self.cnt[K_before:] > 0).any().to(torch.int32).reshape(1)
+        if _dist_on():
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) == 0:
             return
-        assert not _dist_on(), "inactive-slot winners under sharding need a global token order (not implemented)"
         tok = cp.tok_id[cp.tok_id >= 0].long()            # utterance order, left to right
         ks_tok = self.best_k[tok]
         sel = (ks_tok >= K_before).nonzero().flatten()
         ids = tok[sel].cpu().numpy()
         ks = ks_tok[sel].cpu().numpy().astype(np.int64)
-        K = K_before
-        for i in range(len(ids)):
-            k = ks[i]
-            if k > K:
-                k = K
-            if k == K:
-                K += 1
-            ks[i] = k
+        if _dist_on():
+            # ranks hold consecutive utterance ranges: rank order IS the global token order
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, ks.tolist())
+            all_ks, K = clamp_plan([k for part in parts for k in part], K_before)
+            lo = sum(len(part) for part in parts[:dist.get_rank()])
+            ks = all_ks[lo:lo + len(ks)]
+        else:
+            ks, K = clamp_plan(ks, K_before)
         c._K.fill_(int(K))
-        self.best_k[_lib.dev(ids)] = _lib.dev(ks.astype(np.int32))
+        if len(ids):
+            self.best_k[_lib.dev(ids)] = _lib.dev(np.asarray(ks).astype(np.int32))
         self.collect()

@@ -45,7 +45,9 @@ constexpr int MT_ROWS = 256;       // embeddings per CTA work item (two A tiles)
 constexpr int NT_COLS = 128;       // components per accumulator tile
 constexpr int CHUNK = 16;          // components per candidate chunk
 constexpr int MAX_STAGES = 4;
-constexpr int N_THREADS = 384;
+constexpr int EPI_PARTS = 1;         // column halves of an accumulator tile handled by separate warp sets
+constexpr int N_EPI_WARPS = 8 * EPI_PARTS;
+constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float PAD_BIAS = -30000.0f;   // -|mu|^2/2 stand-in for padded components: never wins
 
@@ -155,16 +157,31 @@ struct FilterParams {
     int32_t D;
 };
 
-// Insert a chunk maximum into the running top-3; chunks entering the top-2 also record which of
-// their 16 members lie within tau_c of the chunk maximum (the only ones the refine has to score).
+// Insert a chunk maximum into the running top-3.  A chunk that becomes the new BEST also records
+// which of its 16 members lie within tau_c of the chunk maximum (the only ones the refine has to
+// score); a chunk entering as runner-up keeps all 16 (it is only visited for the rare rows whose
+// runner-up chunk is inside the bound), which keeps this divergent path short.
 __device__ __forceinline__ void top3_insert(const float *vv, float cm, int cid, float tau_c, float &m1, float &m2,
                                             float &m3, int &i1, int &i2, uint32_t &k1, uint32_t &k2) {
     if (cm > m3) {
         if (cm > m2) {
-            uint32_t mk = 0;
-            const float thr = cm - tau_c;
+            m3 = m2;
+            if (cm > m1) {
+                uint32_t mk = 0;
+                const float thr = cm - tau_c;
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) mk |= (vv[j] >= thr) ? (1u << j) : 0u;
+                for (int j = 0; j < CHUNK; ++j) mk |= (vv[j] >= thr) ? (1u << j) : 0u;
+                m2 = m1; i2 = i1; k2 = k1; m1 = cm; i1 = cid; k1 = mk;
+            } else { m2 = cm; i2 = cid; k2 = 0xffffu; }
+        } else m3 = cm;
+    }
+}
+
+// same insertion with the member mask already known (merging two partial top-3 lists)
+__device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float &m1, float &m2, float &m3, int &i1,
+                                           int &i2, uint32_t &k1, uint32_t &k2) {
+    if (cm > m3) {
+        if (cm > m2) {
             m3 = m2;
             if (cm > m1) { m2 = m1; i2 = i1; k2 = k1; m1 = cm; i1 = cid; k1 = mk; }
             else { m2 = cm; i2 = cid; k2 = mk; }
@@ -181,13 +198,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.n_stages * tb);
     // barrier slots: 0 a_full, 1 a_empty, 2..5 b_full, 6..9 b_empty, 10..11 acc_full, 12..13 acc_empty
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    float4 *merge = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [MT_ROWS][2] partial top-3
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     if (threadIdx.x == 0) {
         mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(6 + s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(BAR(10 + b), 1); mbar_init(BAR(12 + b), 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(BAR(10 + b), 1); mbar_init(BAR(12 + b), N_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -253,8 +271,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
         }
     } else if (warp >= 4) {
         // ===================== epilogue: running top-3 chunk maxima per embedding =====================
-        const int e = warp - 4, h = e >> 2, q = warp & 3;
+        // warp -> (TMEM lane quadrant q = warp % 4, row half h, column part)
+        const int e = warp - 4, q = warp & 3, h = (e >> 2) & 1, part = e >> 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        constexpr int COLS = NT_COLS / EPI_PARTS;          // columns of each tile this warp reduces
         // one threshold for the whole launch: the loosest per-row tau (refine re-derives the exact per-row one)
         const float tau_c = filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D);
         uint32_t n_use = 0;
@@ -266,26 +286,42 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
                 mbar_wait(BAR(10 + buf), acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_base + (buf * 2 + h) * NT_COLS;
+                const uint32_t taddr = tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS;
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {
+                for (int sub = 0; sub < COLS / 64; ++sub) {
                     float v[64];
-                    tc_ld64_wait(taddr + part * 64, v);
+                    tc_ld64_wait(taddr + sub * 64, v);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float cm = v[c * 16];
 #pragma unroll
                         for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
-                        top3_insert(&v[c * 16], cm, nt * (NT_COLS / CHUNK) + part * 4 + c, tau_c, m1, m2, m3, i1, i2,
-                                    k1, k2);
+                        top3_insert(&v[c * 16], cm, nt * (NT_COLS / CHUNK) + (part * COLS + sub * 64) / CHUNK + c, tau_c,
+                                    m1, m2, m3, i1, i2, k1, k2);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(12 + buf));
             }
-            const int64_t row = (int64_t)mt * MT_ROWS + h * TILE_ROWS + q * 32 + lane;
-            if (row < p.n_emb) {
+            const int r_local = h * TILE_ROWS + q * 32 + lane;
+            if (EPI_PARTS == 2) {
+                // the two column parts of a row meet through shared memory
+                if (part == 1) {
+                    merge[2 * r_local] = make_float4(m1, m2, m3, __int_as_float(i1));
+                    merge[2 * r_local + 1] = make_float4(__int_as_float(i2), __uint_as_float(k1), __uint_as_float(k2), 0.f);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * N_EPI_WARPS) : "memory");
+                if (part == 0) {
+                    const float4 a = merge[2 * r_local], b = merge[2 * r_local + 1];
+                    top3_merge(a.x, __float_as_int(a.w), __float_as_uint(b.y), m1, m2, m3, i1, i2, k1, k2);
+                    top3_merge(a.y, __float_as_int(b.x), __float_as_uint(b.z), m1, m2, m3, i1, i2, k1, k2);
+                    if (a.z > m3) m3 = a.z;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * N_EPI_WARPS) : "memory");
+            }
+            const int64_t row = (int64_t)mt * MT_ROWS + r_local;
+            if (part == 0 && row < p.n_emb) {
                 Cand c;
                 c.m1 = m1; c.m2 = m2; c.m3 = m3; c.i1 = i1; c.i2 = i2;
                 c.masks = (k1 & 0xffffu) | (k2 << 16); c.pad[0] = c.pad[1] = 0;
@@ -612,7 +648,7 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     p.n_ntiles = k_pad(K_max) / NT_COLS;
     p.n_ksteps = kp_of(D) / 16;
     p.tile_bytes = (uint32_t)tile_bytes_of(D);
-    const size_t budget = 227 * 1024 - 512;
+    const size_t budget = 227 * 1024 - 1024 - 512 - (size_t)MT_ROWS * 32;
     if (2 * (size_t)p.tile_bytes + 2 * (size_t)p.tile_bytes > budget) {
         set_error("D=%d too large for the tensor-core scorer", D);
         return SEGB_E_UNSUPPORTED;
@@ -620,7 +656,7 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     int stages = (int)((budget - 2 * (size_t)p.tile_bytes) / p.tile_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     p.n_stages = stages;
-    const size_t smem = (size_t)(2 + stages) * p.tile_bytes + 256;
+    const size_t smem = (size_t)(2 + stages) * p.tile_bytes + 256 + (size_t)MT_ROWS * 32;
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
