@@ -465,6 +465,38 @@ def run_ours(args):
                        "frac": dp_bytes / (dp_ms * 1e-3) / 1e9 / peak_bw, "traffic": None, "kernel_ms": dp_ms,
                        "algorithmic_bytes_per_launch": dp_bytes}
 
+    # ---- the other scoring kernel: FBGMM log_marg_i as an FP32-accurate tcgen05 GEMM + fused logsumexp
+    roofline_fv = None
+    if rank == 0 and args.scorer == "mma":
+        from segmentalist_b200 import fbgmm as fbgmm_mod
+        from segmentalist_b200.gaussian_components_fixedvar import FixedVarPrior, GaussianComponentsFixedVar
+        n_fv = min(M, 4 * 1024 * 1024)
+        var = 0.002 * np.ones(D)
+        am = fbgmm_mod.FBGMM.__new__(fbgmm_mod.FBGMM)
+        am.alpha, am.lms, am.covariance_type = 10., 1.0, "fixed"
+        am.components = GaussianComponentsFixedVar.from_device(X[:n_fv], FixedVarPrior(var, np.zeros(D), var / 0.05),
+                                                               args.K, alpha=10., lms=1.0)
+        n_tok = 4 * args.K
+        am.components._add_many(np.arange(n_tok), np.arange(n_tok) % args.K)
+        am.log_marg_all(tensor_cores=True)                      # packs X, warms up
+        x_t, w_t, out_t = am._tc
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            _lib.check(lib.segb_fvmma_log_marg(am.components.struct(), _lib.ptr(x_t), _lib.ptr(w_t), n_fv,
+                                               _lib.ptr(out_t), _lib.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        fv_ms = e0.elapsed_time(e1) / 3
+        fl = 2.0 * D * n_fv * args.K
+        roofline_fv = {"kernel": "fv_logmarg_kernel (tcgen05 fp16 hi/lo split x3 passes -> fp32 TMEM, fused online logsumexp)",
+                       "bound": "tensor", "achieved": fl / (fv_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                       "frac": fl / (fv_ms * 1e-3) / 1e12 / peak_tf, "traffic": None, "kernel_ms": fv_ms,
+                       "rows": n_fv, "K": args.K, "algorithmic_flops_per_launch": fl,
+                       "note": "3 tensor passes per algorithmic flop (FP32-accurate split): ceiling ~1/3.3 of peak"}
+        del am
+
     # ---- end to end: host buffers in, host results out, every step
     e2e = None
     if not args.no_e2e:
@@ -554,7 +586,7 @@ def run_ours(args):
             "segment_component_evals_per_s": evals_per_s,
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "roofline_dp": roofline_dp, "cpu_baseline": cpu_baseline, "phases_ms": phases,
+            "roofline_dp": roofline_dp, "roofline_fixedvar_logmarg": roofline_fv, "cpu_baseline": cpu_baseline, "phases_ms": phases,
             "secondary_gibbs_fixedvar": gibbs,
         }
         print(json.dumps(line))

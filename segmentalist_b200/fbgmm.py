@@ -70,6 +70,27 @@ class FBGMM(object):
             _lib.ptr(out), _lib.stream_ptr()))
         return out.cpu().numpy()
 
+    def log_marg_all(self, tensor_cores=True):
+        """log_marg_i of EVERY embedding against the current (frozen) model in one launch.
+        tensor_cores=True: FP32-accurate tcgen05 GEMM with the logsumexp fused into the epilogue
+        (segb_fvmma_log_marg; isotropic variances, float32 embeddings; ~1e-6 relative);
+        False: the exact float64 kernel."""
+        c = self.components
+        if not tensor_cores:
+            return self.log_marg_items(np.arange(c.N))
+        iso = (np.all(c.precision == c.precision[0]) and np.all(c.precision_0 == c.precision_0[0]))
+        assert iso and c._X.dtype == torch.float32, "tensor-core log_marg needs isotropic variances and float32 X"
+        lib = _lib.lib()
+        if getattr(self, "_tc", None) is None:
+            x_tiles = torch.empty(lib.segb_fvmma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device="cuda")
+            w_tiles = torch.empty(lib.segb_fvmma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.segb_fvmma_pack_x(_lib.ptr(c._X), c.N, c.D, _lib.ptr(x_tiles), _lib.stream_ptr()))
+            self._tc = (x_tiles, w_tiles, torch.empty(c.N, dtype=torch.float32, device="cuda"))
+        x_tiles, w_tiles, out = self._tc
+        _lib.check(lib.segb_fvmma_log_marg(c.struct(), _lib.ptr(x_tiles), _lib.ptr(w_tiles), c.N, _lib.ptr(out),
+                                           _lib.stream_ptr()))
+        return out.cpu().numpy().astype(np.float64)
+
     def _assign(self, ids, mode, anneal_temp, uniforms):
         c = self.components
         ids_d = _lib.dev(np.asarray(ids, dtype=np.int32))

@@ -74,10 +74,39 @@ class GaussianComponentsFixedVar(object):
             order = order[assignments[order] >= 0]
             self._add_many(order, assignments[order])
 
+    @classmethod
+    def from_device(cls, X_dev, prior, K_max, alpha=1.0, lms=1.0):
+        """Bench-scale constructor: float32 embeddings already resident in HBM, nothing assigned."""
+        self = cls.__new__(cls)
+        assert X_dev.is_cuda and X_dev.dtype == torch.float32 and X_dev.is_contiguous()
+        _lib.lib()
+        self.X = None
+        self.N, self.D = int(X_dev.shape[0]), int(X_dev.shape[1])
+        self.K_max = int(K_max)
+        self.precision = np.asarray(1. / prior.var, dtype=np.float64) * np.ones(self.D)
+        self.mu_0 = np.asarray(prior.mu_0, dtype=np.float64) * np.ones(self.D)
+        self.precision_0 = np.asarray(1. / prior.var_0, dtype=np.float64) * np.ones(self.D)
+        self._cached_neg_half_D_log_2pi = -0.5 * self.D * math.log(2. * np.pi)
+        self.lm = None
+        dv, z = _lib.dev, lambda *s: torch.zeros(*s, dtype=torch.float64, device="cuda")
+        self._X = X_dev
+        self._mu_N_numT, self._prec_NT = z(self.D, self.K_max), z(self.D, self.K_max)
+        self._prec_predT, self._mu_NT = z(self.D, self.K_max), z(self.D, self.K_max)
+        self._log_prod = z(self.K_max)
+        self._counts = torch.zeros(self.K_max, dtype=torch.int32, device="cuda")
+        self._assign = torch.full((self.N,), -1, dtype=torch.int32, device="cuda")
+        self._K = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self._n_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self._precision, self._mu_0, self._precision_0 = dv(self.precision), dv(self.mu_0), dv(self.precision_0)
+        self._alpha, self._lms = float(alpha), float(lms)
+        self._relabel = None
+        self._scratch_row = z(self.K_max)
+        return self
+
     # ---- C-ABI plumbing
     def struct(self):
         m = _lib.FixedVar()
-        m.D, m.K_max, m.x_is_f64, m.n_emb = self.D, self.K_max, int(self.X.dtype == np.float64), self.N
+        m.D, m.K_max, m.x_is_f64, m.n_emb = self.D, self.K_max, int(self._X.dtype == torch.float64), self.N
         m.X = self._X.data_ptr()
         m.mu_N_numT, m.prec_NT = self._mu_N_numT.data_ptr(), self._prec_NT.data_ptr()
         m.prec_predT, m.mu_NT = self._prec_predT.data_ptr(), self._mu_NT.data_ptr()

@@ -432,3 +432,32 @@ def test_dp_small_fastpath_vs_oracle(sb, mode, S):
         fin = np.isfinite(oal)
         npt.assert_allclose(al[fin], oal[fin], rtol=1e-12, atol=1e-12)
     assert n_ok > 1500 and n_bad > 0
+
+
+@pytest.mark.parametrize("K_max,n_assigned,n_emb", [(64, 300, 700), (1000, 6000, 9000), (40, 0, 300)])
+def test_fixedvar_tensor_core_log_marg(sb, K_max, n_assigned, n_emb):
+    """tcgen05 FP32-accurate GEMM + fused logsumexp vs the exact float64 kernel and the oracle:
+    log-likelihoods within 1e-4 relative (north star); K_act < K_max exercises the empty-slot term."""
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf, synth
+    rng = np.random.RandomState(K_max + 1)
+    D = 130
+    centres = synth.cluster_centres(50, D, rng)
+    X = synth._unit_rows(centres[rng.randint(0, 50, n_emb)] + 0.05 * rng.standard_normal((n_emb, D)).astype(np.float32))
+    assign = -np.ones(n_emb, dtype=np.int64)
+    if n_assigned:
+        k_used = min(K_max - 3, max(1, n_assigned // 4))
+        assign[:n_assigned] = np.arange(n_assigned) % k_used
+    var = 0.002 * np.ones(D)
+    prior = gcf.FixedVarPrior(var, np.zeros(D), var / 0.05)
+    am = fbgmm.FBGMM(X, prior, 10., K_max, assign.copy(), covariance_type="fixed", lms=0.9)
+    exact = am.log_marg_all(tensor_cores=False)
+    tc = am.log_marg_all(tensor_cores=True)
+    rel = np.abs(tc - exact) / np.abs(exact)
+    assert rel.max() < 1e-4, rel.max()
+    assert rel.max() < 2e-5, rel.max()          # what the split actually delivers
+    # oracle on a few items
+    oam = so.FBGMM(X, so.FixedVarPrior(var, np.zeros(D), var / 0.05), 10., K_max, assign.copy(), lms=0.9)
+    for i in range(0, n_emb, max(1, n_emb // 12)):
+        ref = oam.log_marg_i(i)
+        assert abs(tc[i] - ref) <= 1e-4 * abs(ref)
+        assert abs(exact[i] - ref) <= 1e-11 * abs(ref)
