@@ -460,7 +460,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         dp_ms = e0.elapsed_time(e1) / reps
         dp_bytes = 8.0 * n_pos * S_MAX + n_pos + 8.0 * corpus.n_utt + 8.0 * (corpus.n_utt + 1) + 4.0 * corpus.n_utt
-        roofline_dp = {"kernel": "dp_banded_kernel (Viterbi, float64 banded scores)", "bound": "hbm",
+        roofline_dp = {"kernel": "dp_staged_kernel (Viterbi, float64 banded scores, cp.async.bulk staging, thread per utterance)", "bound": "hbm",
                        "achieved": dp_bytes / (dp_ms * 1e-3) / 1e9, "peak": peak_bw, "unit": "GB/s",
                        "frac": dp_bytes / (dp_ms * 1e-3) / 1e9 / peak_bw, "traffic": None, "kernel_ms": dp_ms,
                        "algorithmic_bytes_per_launch": dp_bytes}

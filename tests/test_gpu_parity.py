@@ -400,14 +400,16 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("S", [1, 3, 6, 8])
-def test_dp_small_fastpath_vs_oracle(sb, mode, S):
-    """Thread-per-utterance DP kernel (band <= 8, N <= 64): ragged lengths incl. N = 1, -inf holes
-    that force back-tracking, annealed FFBS."""
-    rng = np.random.RandomState(500 + 11 * mode + S)
+@pytest.mark.parametrize("S,n_hi", [(1, 60), (3, 60), (6, 60), (8, 60), (2, 26), (4, 26), (6, 26), (8, 26), (3, 26)])
+def test_dp_small_fastpath_vs_oracle(sb, mode, S, n_hi):
+    """Thread-per-utterance DP kernels (band <= 8, N <= 64): ragged lengths incl. N = 1, -inf holes
+    that force back-tracking, annealed FFBS.  n_hi = 26 with an even band selects the staged
+    kernel (score blocks brought into shared memory by cp.async.bulk), everything else the
+    global-memory variant; 3001 utterances leave a partial last group."""
+    rng = np.random.RandomState(500 + 11 * mode + S + n_hi)
     cases = []
-    for _ in range(3000):
-        N = int(rng.randint(1, 61))
+    for _ in range(3001):
+        N = int(rng.randint(1, n_hi + 1))
         vec = -np.inf * np.ones(N * (N + 1) // 2)
         hole = rng.choice([0.0, 0.05, 0.3])
         for t in range(1, N + 1):
