@@ -27,6 +27,7 @@ struct DpParams {
     int32_t *n_draws;
     int32_t *status;
     int32_t utt_first, n_utt, S, n_min, n_max, mode, N_cap, scores_local;
+    int32_t group;             // utterances per warp of the staged kernel (<= 32)
     double log_p_continue, anneal_temp;
 };
 
@@ -455,16 +456,23 @@ __global__ void __launch_bounds__(128) dp_small_kernel(DpParams p) {
 // of every position as a back-pointer byte and the backward pass only chases pointers, the
 // other two modes keep their alphas in shared memory and run the general backward pass.
 // Boundaries are assembled in shared memory and written back as one contiguous run of bytes.
-__host__ __device__ inline int dp_staged_slot_granules(int N_cap, int S) {
-    int g = (N_cap * S * 8 + 15) / 16;
-    while ((g & 7) != 1) ++g;
-    return g;
-}
-__host__ __device__ inline size_t dp_staged_smem_bytes(int N_cap, int S, bool alphas_in_smem) {
+// Shared memory of one warp: the group's score rows (tightly packed, one bulk copy), SB rows of
+// slack for the row ring of the skewed forward pass, back-pointer bytes, boundary bytes.
+__host__ __device__ inline size_t dp_staged_smem_bytes(int N_cap, int S, int G, bool alphas_in_smem) {
     return 128 + (alphas_in_smem ? (size_t)32 * N_cap * 8 : 0) + (size_t)32 * (N_cap + 1) /* back-pointers */
-           + (size_t)((32 * N_cap + 4 + 15) / 16) * 16 /* boundary bytes (+ alignment phase) */
-           + (size_t)32 * dp_staged_slot_granules(N_cap, S) * 16
-           + (size_t)(S + 1) * S * 8 /* the row ring of the skewed forward pass reads S rows ahead */;
+           + (size_t)((G * N_cap + 4 + 15) / 16) * 16 /* boundary bytes (+ alignment phase) */
+           + (size_t)G * N_cap * S * 8 + (size_t)(S + 1) * S * 8;
+}
+// Utterances per warp: the choice that keeps most utterances resident per SM (228 KB of shared
+// memory, 1 KB reserved per block), ties to the wider group.
+inline int dp_staged_pick_group(int N_cap, int S, bool alphas_in_smem) {
+    int best = 0, best_res = 0;
+    for (int G = 32; G >= 16; --G) {
+        const size_t b = dp_staged_smem_bytes(N_cap, S, G, alphas_in_smem) + 1024;
+        const int per_sm = (int)min((size_t)32, (size_t)(228 * 1024) / b);
+        if (G * per_sm > best_res) { best_res = G * per_sm; best = G; }
+    }
+    return best;
 }
 
 template <int J, int E, typename F>
@@ -625,30 +633,29 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
     extern __shared__ __align__(128) unsigned char dp_sm[];
     constexpr bool AL_SMEM = (MODE != SEGB_DP_VITERBI_KMEANS);
     const int lane = threadIdx.x;
-    const int N_cap = p.N_cap;
-    const int slot_g = dp_staged_slot_granules(N_cap, SB);
+    const int N_cap = p.N_cap, G = p.group;
     double *al_s = reinterpret_cast<double *>(dp_sm + 128);
     uint8_t *bp_s = dp_sm + 128 + (AL_SMEM ? (size_t)32 * N_cap * 8 : 0);
     uint8_t *bo_s = bp_s + (size_t)32 * (N_cap + 1);
-    unsigned char *sc_s = bo_s + (size_t)((32 * N_cap + 4 + 15) / 16) * 16;
+    const double *sc_s = reinterpret_cast<const double *>(bo_s + (size_t)((G * N_cap + 4 + 15) / 16) * 16);
     const uint32_t bar = mma::smem_u32(dp_sm);
-    const double *sc = reinterpret_cast<const double *>(sc_s + (size_t)lane * slot_g * 16);
     uint8_t *bp = bp_s + lane;
     double *al = al_s + lane;
 
     if (lane == 0) {
-        mma::mbar_init(bar, 32);
+        mma::mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
 
-    // persistent warp: groups of 32 consecutive utterances, grid-strided; the next group's
-    // offsets are requested before this group's copy is awaited and consumed after its compute
-    const int n_groups = (p.n_utt + 31) >> 5;
+    // persistent warp: groups of G consecutive utterances (lane = utterance), grid-strided; the
+    // next group's offsets are requested before this group's copy is awaited and consumed
+    // after its compute.  The group's score rows are contiguous in HBM: ONE bulk copy.
+    const int n_groups = (p.n_utt + G - 1) / G;
     auto group_offsets = [&](int g, int64_t &o0, int64_t &o1, bool &valid) {
-        const int u_local = g * 32 + lane;
-        valid = g < n_groups && u_local < p.n_utt;
+        const int u_local = g * G + lane;
+        valid = g < n_groups && lane < G && u_local < p.n_utt;
         const int u = p.utt_first + (valid ? u_local : 0);
         o0 = p.pos_off[u];
         o1 = p.pos_off[u + 1];
@@ -659,31 +666,33 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
     int N = valid ? (int)(o1 - off) : 0;
     uint32_t parity = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        if (N > 0) {
-            const uint32_t bytes = (uint32_t)N * SB * 8;
-            mma::mbar_expect_tx(bar, bytes);
-            mma::bulk_g2s(mma::smem_u32(sc), p.scores + off * SB, bytes, bar);
-        } else {
-            mma::mbar_arrive(bar);
-        }
-        group_offsets(g + gridDim.x, off_next, o1_next, valid_next);
-        const int u_local = g * 32 + lane;
         const int64_t off0 = __shfl_sync(FULL, off, 0);
-        // boundary bytes are staged with the same 4-byte phase as their destination in HBM
-        uint8_t *bo = p.bounds + off0;
-        const int phase = (int)((uintptr_t)bo & 3);
-        uint8_t *bs0 = bo_s + phase;
         int64_t end = valid ? off + N : 0;
-        // ---------------- forward: t = 1 .. Nf (k-means Viterbi also forms the window of t = N)
-        const int Nf = (MODE == SEGB_DP_VITERBI_KMEANS) ? N : N - 1;
         // uniform trip count: every lane runs to the longest utterance of the group
+        const int Nf = (MODE == SEGB_DP_VITERBI_KMEANS) ? N : N - 1;
         int Nf_w = Nf;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             Nf_w = max(Nf_w, __shfl_xor_sync(FULL, Nf_w, o));
             end = max(end, __shfl_xor_sync(FULL, end, o));
         }
-        const int n_bytes = (int)(end - off0);
+        const int n_bytes = (int)(end - off0);                  // landmarks of the group
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)n_bytes * SB * 8;
+            if (bytes) {
+                mma::mbar_expect_tx(bar, bytes);
+                mma::bulk_g2s(mma::smem_u32(sc_s), p.scores + off0 * SB, bytes, bar);
+            } else {
+                mma::mbar_arrive(bar);
+            }
+        }
+        group_offsets(g + gridDim.x, off_next, o1_next, valid_next);
+        const double *sc = sc_s + (valid ? (off - off0) * SB : 0);
+        const int u_local = g * G + lane;
+        // boundary bytes are staged with the same 4-byte phase as their destination in HBM
+        uint8_t *bo = p.bounds + off0;
+        const int phase = (int)((uintptr_t)bo & 3);
+        uint8_t *bs0 = bo_s + phase;
         for (int wd = lane; wd * 4 < phase + n_bytes; wd += 32) reinterpret_cast<uint32_t *>(bo_s)[wd] = 0u;
         bool bad = false;
         if (AL_SMEM) al[0] = 0.0;
@@ -722,25 +731,32 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
             // ---------------- backward
             uint8_t *bs = bs0 + (off - off0);
             if (MODE == SEGB_DP_VITERBI_KMEANS) {
+                // pointer chase; the chosen score of one hop is added while the next hop's
+                // back-pointer is in flight (same summation order: right to left)
                 bs[N - 1] = 1;
                 int t = N;
+                double pend = 0.0;
+                bool have = false;
                 for (int guard = 0; guard <= N && status == SEGB_DP_OK; ++guard) {
                     int b = bp[t * 32];
+                    if (have) total += pend;
                     if (b == 0xff) {                       // window all -inf: walk left until feasible
                         while (b == 0xff) {
                             t = t - 1;
                             if (t == 0) break;
                             b = bp[t * 32];
                         }
-                        if (t == 0) { status = SEGB_DP_INFEASIBLE; break; }
+                        if (t == 0) { status = SEGB_DP_INFEASIBLE; have = false; break; }
                         bs[t - 1] = 1;
                     }
                     const int k = b + 1;
-                    total += sc[(t - 1) * SB + b];
+                    pend = sc[(t - 1) * SB + b];
+                    have = true;
                     if (t - k - 1 < 0) break;
                     bs[t - k - 1] = 1;
                     t = t - k;
                 }
+                if (have) total += pend;
             } else {
                 SharedRows rows;
                 rows.sc = sc; rows.S = SB;
@@ -786,6 +802,7 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
               cudaStream_t stream, int scores_local = 0) {
     DpParams p;
     p.scores_local = scores_local;
+    p.group = 32;
     p.pos_off = c->pos_off; p.scores = scores; p.uniforms = uniforms; p.u_counter = u_counter;
     p.bounds = bounds_out; p.log_prob = log_prob; p.alphas = alphas; p.n_draws = n_draws; p.status = status;
     p.utt_first = utt_first; p.n_utt = n_utt; p.S = c->S; p.n_min = c->n_slices_min; p.n_max = c->n_slices_max;
@@ -794,10 +811,12 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
         // batched calls: stage the score blocks through shared memory with the copy engine
         const int Wlim = (c->n_slices_max == 0 || c->n_slices_max > c->S) ? c->S : c->n_slices_max;
         const bool al_smem = (mode != SEGB_DP_VITERBI_KMEANS);
-        const size_t st_smem = dp_staged_smem_bytes(c->N_max, c->S, al_smem);
-        if (!scores_local && !u_counter && n_utt >= 32 && (c->S % 2) == 0 && Wlim == c->S &&
+        const int G = dp_staged_pick_group(c->N_max, c->S, al_smem);
+        const size_t st_smem = G ? dp_staged_smem_bytes(c->N_max, c->S, G, al_smem) : 0;
+        if (!scores_local && !u_counter && n_utt >= 32 && (c->S % 2) == 0 && Wlim == c->S && G >= 16 &&
             ((uintptr_t)scores & 15) == 0 && st_smem <= 72 * 1024 && !(alphas && !al_smem)) {
-            const int groups = (n_utt + 31) / 32;
+            p.group = G;
+            const int groups = (n_utt + G - 1) / G;
             auto launch = [&](auto kern) -> int {
                 if (st_smem > 48 * 1024)
                     SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
