@@ -12,19 +12,22 @@
 // so the whole [rows x K] score matrix is ONE GEMM.  p_k ~ 1/var (500 in the recipes) amplifies
 // any error of x.mu, and the target is 1e-4 relative on log_marg (~1e-2 absolute), so single-
 // pass fp16/tf32 is not enough.  FP32-accurate split: x = xh + xl, B_k = p_k mu_k
-// = Bh + Bl (fp16 pairs, 22 bits each) and three tensor-core passes xh.Bh + xh.Bl + xl.Bh
-// accumulate in one fp32 TMEM tile.  A fourth K=16 step adds A_k (3-way fp16 split against
-// 1.0 columns) and -1/2 p_k |x|^2 (split |x|^2 against split p_k) -- norms, count-weighted log
-// prior and constants all ride inside the GEMM; the accumulator IS s_k.  The epilogue runs an
-// online logsumexp over the component tiles (running max + rescaled sum, exp2 on the MUFU
-// pipe) and writes 4 bytes per embedding.  The (K_max - K) empty slots are one virtual
-// component with log(K_max - K) folded into its A.
+// = Bh + Bl (fp16 pairs, 22 bits each) and three tensor-core passes xh.Bh + xl.Bh + xh.Bl
+// accumulate in one fp32 TMEM tile.  Six padding columns of the inner dimension carry A_k
+// (3-way fp16 split against 1.0 columns) and -1/2 p_k |x|^2 (split |x|^2 against split p_k) --
+// norms, count-weighted log prior and constants all ride inside the GEMM; the accumulator IS
+// s_k.  The epilogue runs an online logsumexp over the component tiles (running max +
+// rescaled sum, exp2 on the MUFU pipe) and writes 4 bytes per embedding.  The (K_max - K)
+// empty slots are one virtual component with log(K_max - K) folded into its A.
 //
-// Tile images (mma_common.cuh): X image 128-row tiles with columns [xh | xl | extras], KPX =
-// 2*roundup(D,16) + 16; model image 32-row tiles with columns [Bh | Bl | extras].
-// Kernel: persistent, 384 threads; warp 0 TMA producer (A = 256 embeddings per work item, B =
-// 32-component tiles through a 3-stage ring), warp 1 MMA issuer (M=128, N=32, K=16; 2 halves x
-// 28 steps per tile), warp 2 TMEM, warps 4-11 epilogue (thread = embedding row).
+// Tile images (mma_common.cuh), all 128 rows:
+//   X      columns [xh, extras | xl]          2*dp columns, dp = roundup(D + 6, 16)
+//   model  per 128 components two CHUNKS of dp columns each: H = [Bh, extras], L = [Bl]
+// Kernel: persistent, 384 threads; warp 0 TMA producer (A = 256 embeddings per work item, model
+// chunks through a 2-stage ring: H is consumed by two passes while L loads, and vice versa);
+// warp 1 MMA issuer (tcgen05.mma kind::f16, M=128 N=128 K=16: per 256x128 tile 2 halves x
+// (xh.H, xl.H, xh.L) x dp/16 steps into double-buffered TMEM accumulators); warp 2 TMEM;
+// warps 4-11 epilogue (thread = embedding row).
 #include "mma_common.cuh"
 
 namespace segb {
@@ -32,23 +35,23 @@ namespace fvmma {
 
 using namespace segb::mma;
 
-constexpr int A_ROWS = 128;        // rows per X tile image
+constexpr int T_ROWS = 128;        // rows per tile image (X tiles and model chunks)
 constexpr int MT_ROWS = 256;       // embeddings per CTA work item
-constexpr int B_ROWS = 32;         // components per model tile = MMA N
-constexpr int N_STAGES = 3;
+constexpr int NT_COLS = 128;       // components per accumulator tile = MMA N
+constexpr int N_STAGES = 2;
 constexpr int N_THREADS = 384;
-constexpr uint32_t TMEM_COLS = 128;   // 2 halves x 2 buffers x 32 columns
+constexpr uint32_t TMEM_COLS = 512;   // 2 halves x 2 buffers x 128 columns
 constexpr float DEAD_A = -30000.0f;   // A of padded components: exp2 underflows to exactly 0
+constexpr int N_EXTRA = 6;
 
-__host__ __device__ inline int dpad_of(int D) { return (D + 15) / 16 * 16; }
-__host__ __device__ inline int kpx_of(int D) { return 2 * dpad_of(D) + 16; }
+__host__ __device__ inline int dpad_of(int D) { return (D + N_EXTRA + 15) / 16 * 16; }
 
 struct Params {
     const uint8_t *x_tiles, *w_tiles;
     float *out;
     int64_t n_emb;
-    int32_t n_mtiles, n_ntiles, n_blk_steps;     // n_blk_steps = dpad/16
-    uint32_t a_tile_bytes, b_tile_bytes;
+    int32_t n_mtiles, n_ntiles, n_ksteps;        // n_ksteps = dp/16 per pass
+    uint32_t a_tile_bytes, chunk_bytes;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -56,37 +59,23 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 32 lanes x 32 consecutive fp32 columns, load + wait in one statement
-__device__ __forceinline__ void tc_ld32_wait(uint32_t taddr, float *v) {
-    uint32_t *r = reinterpret_cast<uint32_t *>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
 
 __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ta = p.a_tile_bytes, tbb = p.b_tile_bytes;
+    const uint32_t ta = p.a_tile_bytes, cb = p.chunk_bytes;
     uint8_t *sA = smem;                                   // 2 X tiles
-    uint8_t *sB = smem + 2 * (size_t)ta;                  // N_STAGES model tiles
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)N_STAGES * tbb);
-    // barrier slots: 0 a_full, 1 a_empty, 2..4 b_full, 5..7 b_empty, 8..9 acc_full, 10..11 acc_empty
+    uint8_t *sB = smem + 2 * (size_t)ta;                  // N_STAGES model chunks
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)N_STAGES * cb);
+    // barrier slots: 0 a_full, 1 a_empty, 2..3 b_full, 4..5 b_empty, 6..7 acc_full, 8..9 acc_empty
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     if (threadIdx.x == 0) {
         mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
-        for (int s = 0; s < N_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(5 + s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(BAR(8 + b), 1); mbar_init(BAR(10 + b), 8); }
+        for (int s = 0; s < N_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(4 + s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(BAR(6 + b), 1); mbar_init(BAR(8 + b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -103,7 +92,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
     if (warp == 0) {
         if (lane == 0) {                                  // ===== TMA producer
             uint32_t a_phase = 0, b_phase = 0;
-            int s = 0;
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
                 mbar_wait(BAR(1), a_phase ^ 1);
                 mbar_expect_tx(BAR(0), 2 * ta);
@@ -111,52 +99,58 @@ __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
                 bulk_g2s(smem_u32(sA + ta), p.x_tiles + (size_t)(2 * mt + 1) * ta, ta, BAR(0));
                 a_phase ^= 1;
                 for (int nt = 0; nt < p.n_ntiles; ++nt) {
-                    mbar_wait(BAR(5 + s), b_phase ^ 1);
-                    mbar_expect_tx(BAR(2 + s), tbb);
-                    bulk_g2s(smem_u32(sB + (size_t)s * tbb), p.w_tiles + (size_t)nt * tbb, tbb, BAR(2 + s));
-                    if (++s == N_STAGES) { s = 0; b_phase ^= 1; }
+#pragma unroll
+                    for (int s = 0; s < N_STAGES; ++s) {          // stage 0 = chunk H, stage 1 = chunk L
+                        mbar_wait(BAR(4 + s), b_phase ^ 1);
+                        mbar_expect_tx(BAR(2 + s), cb);
+                        bulk_g2s(smem_u32(sB + (size_t)s * cb), p.w_tiles + ((size_t)nt * 2 + s) * cb, cb, BAR(2 + s));
+                    }
+                    b_phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                  // ===== MMA issuer
-            const uint32_t idesc = make_idesc_mn(A_ROWS, B_ROWS);
-            const uint32_t a_step = 2 * (A_ROWS / 8) * 128, b_step = 2 * (B_ROWS / 8) * 128;   // bytes per K=16 step
-            const int nb = p.n_blk_steps;
+            const uint32_t idesc = make_idesc_mn(T_ROWS, NT_COLS);
+            const uint32_t kstep = 2 * (T_ROWS / 8) * 128;            // bytes per K=16 step (both operands)
+            const int nk = p.n_ksteps;
             uint32_t a_phase = 0, b_phase = 0, n_use = 0;
-            int s = 0;
+            const uint32_t bH = smem_u32(sB), bL = smem_u32(sB + cb);
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
                 mbar_wait(BAR(0), a_phase);
                 a_phase ^= 1;
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                    mbar_wait(BAR(2 + s), b_phase);
-                    mbar_wait(BAR(10 + buf), acc_phase ^ 1);
+                    mbar_wait(BAR(8 + buf), acc_phase ^ 1);
+                    mbar_wait(BAR(2), b_phase);                       // chunk H = [Bh, extras]
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + (size_t)s * tbb);
 #pragma unroll 1
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t a_addr = smem_u32(sA + (size_t)h * ta);
-                        const uint32_t d_tmem = tmem_base + (buf * 2 + h) * B_ROWS;
-                        uint32_t acc = 0;
-                        // three FP32-accurate passes + the constants step
-                        for (int k = 0; k < nb; ++k, acc = 1)         // xh . Bh
-                            tc_mma_f16(d_tmem, make_desc_r(a_addr + k * a_step, A_ROWS),
-                                       make_desc_r(b_addr + k * b_step, B_ROWS), idesc, acc);
-                        for (int k = 0; k < nb; ++k)                  // xh . Bl
-                            tc_mma_f16(d_tmem, make_desc_r(a_addr + k * a_step, A_ROWS),
-                                       make_desc_r(b_addr + (nb + k) * b_step, B_ROWS), idesc, 1u);
-                        for (int k = 0; k < nb; ++k)                  // xl . Bh
-                            tc_mma_f16(d_tmem, make_desc_r(a_addr + (nb + k) * a_step, A_ROWS),
-                                       make_desc_r(b_addr + k * b_step, B_ROWS), idesc, 1u);
-                        tc_mma_f16(d_tmem, make_desc_r(a_addr + 2 * nb * a_step, A_ROWS),     // A_k - p_k|x|^2/2
-                                   make_desc_r(b_addr + 2 * nb * b_step, B_ROWS), idesc, 1u);
+                        const uint32_t d_tmem = tmem_base + (buf * 2 + h) * NT_COLS;
+                        for (int k = 0; k < nk; ++k)                  // xh . Bh (+ constants)
+                            tc_mma_f16(d_tmem, make_desc_r(a_addr + k * kstep, T_ROWS), make_desc_r(bH + k * kstep, T_ROWS),
+                                       idesc, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < nk; ++k)                  // xl . Bh
+                            tc_mma_f16(d_tmem, make_desc_r(a_addr + (nk + k) * kstep, T_ROWS),
+                                       make_desc_r(bH + k * kstep, T_ROWS), idesc, 1u);
                     }
-                    tc_commit(BAR(5 + s));
-                    tc_commit(BAR(8 + buf));
-                    if (++s == N_STAGES) { s = 0; b_phase ^= 1; }
+                    tc_commit(BAR(4));                                // chunk H stage free
+                    mbar_wait(BAR(3), b_phase);                       // chunk L = [Bl]
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t a_addr = smem_u32(sA + (size_t)h * ta);
+                        const uint32_t d_tmem = tmem_base + (buf * 2 + h) * NT_COLS;
+                        for (int k = 0; k < nk; ++k)                  // xh . Bl
+                            tc_mma_f16(d_tmem, make_desc_r(a_addr + k * kstep, T_ROWS), make_desc_r(bL + k * kstep, T_ROWS),
+                                       idesc, 1u);
+                    }
+                    tc_commit(BAR(5));                                // chunk L stage free
+                    tc_commit(BAR(6 + buf));                          // accumulators ready
+                    b_phase ^= 1;
                 }
-                tc_commit(BAR(1));
+                tc_commit(BAR(1));                                    // X tiles free
             }
         }
     } else if (warp >= 4) {
@@ -169,24 +163,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
             float m = -CUDART_INF_F, ssum = 0.f;          // running max (base-2 scaled) and sum
             for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                 const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                mbar_wait(BAR(8 + buf), acc_phase);
+                mbar_wait(BAR(6 + buf), acc_phase);
                 tc_fence_after();
-                float v[32];
-                tc_ld32_wait(tmem_base + lane_base + (buf * 2 + h) * B_ROWS, v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(10 + buf));           // accumulator free: values are in registers
-                float cm = v[0];
+                const uint32_t taddr = tmem_base + lane_base + (buf * 2 + h) * NT_COLS;
 #pragma unroll
-                for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
-                cm *= LOG2E;
-                if (cm > m) { ssum *= ex2(m - cm); m = cm; }          // m = -inf first time: ex2(-inf) = 0
-                float add = 0.f;
+                for (int sub = 0; sub < NT_COLS / 64; ++sub) {
+                    float v[64];
+                    tc_ld64_wait(taddr + sub * 64, v);
+                    if (sub == NT_COLS / 64 - 1) {                    // accumulator free: values are in registers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(8 + buf));
+                    }
+                    float c0 = v[0], c1 = v[1], c2 = v[2], c3 = v[3];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) add += ex2(fmaf(v[j], LOG2E, -m));
-                ssum += add;
+                    for (int j = 4; j < 64; j += 4) {
+                        c0 = fmaxf(c0, v[j]); c1 = fmaxf(c1, v[j + 1]); c2 = fmaxf(c2, v[j + 2]); c3 = fmaxf(c3, v[j + 3]);
+                    }
+                    const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * LOG2E;
+                    if (cm > m) { ssum *= ex2(m - cm); m = cm; }      // m = -inf first time: ex2(-inf) = 0
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 4) {
+                        a0 += ex2(fmaf(v[j], LOG2E, -m));     a1 += ex2(fmaf(v[j + 1], LOG2E, -m));
+                        a2 += ex2(fmaf(v[j + 2], LOG2E, -m)); a3 += ex2(fmaf(v[j + 3], LOG2E, -m));
+                    }
+                    ssum += (a0 + a1) + (a2 + a3);
+                }
             }
-            const int64_t row = (int64_t)mt * MT_ROWS + h * A_ROWS + q * 32 + lane;
+            const int64_t row = (int64_t)mt * MT_ROWS + h * T_ROWS + q * 32 + lane;
             if (row < p.n_emb) p.out[row] = (m + log2f(ssum)) * LN2;
         }
     }
@@ -205,14 +210,14 @@ __device__ __forceinline__ void split2(float v, __half &hi, __half &lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
-// X image: one warp per row.  Columns [xh (dpad) | xl (dpad) | 1,1,1,n2h,n2h,n2l,0...(16)]
+// X image: one warp per row.  Columns [xh (D), 1,1,1,n2h,n2h,n2l, 0.. (dp) | xl (D), 0.. (dp)]
 __global__ void pack_x3_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad, int D, uint8_t *tiles) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_rows_pad) return;
-    const int dp = dpad_of(D), KP = kpx_of(D);
-    uint8_t *base = tiles + (row / A_ROWS) * ((int64_t)A_ROWS * KP * 2);
-    const int r = (int)(row % A_ROWS);
+    const int dp = dpad_of(D), KP = 2 * dp;
+    uint8_t *base = tiles + (row / T_ROWS) * ((int64_t)T_ROWS * KP * 2);
+    const int r = (int)(row % T_ROWS);
     const bool live = row < n_emb;
     double n2 = 0.0;
     if (live) for (int d = lane; d < D; d += 32) { const double v = X[row * D + d]; n2 += v * v; }
@@ -226,15 +231,13 @@ __global__ void pack_x3_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad
             const int c = ch * 8 + j;
             __half out = __float2half_rn(0.f);
             if (live) {
-                if (c < 2 * dp) {
-                    const int d = c < dp ? c : c - dp;
-                    if (d < D) {
-                        __half hi, lo;
-                        split2(X[row * D + d], hi, lo);
-                        out = c < dp ? hi : lo;
-                    }
-                } else {
-                    const int ecol = c - 2 * dp;
+                const int d = c < dp ? c : c - dp;
+                if (d < D) {
+                    __half hi, lo;
+                    split2(X[row * D + d], hi, lo);
+                    out = c < dp ? hi : lo;
+                } else if (c < dp) {
+                    const int ecol = c - D;
                     if (ecol < 3) out = __float2half_rn(1.f);
                     else if (ecol == 3 || ecol == 4) out = n2h;
                     else if (ecol == 5) out = n2l;
@@ -242,21 +245,22 @@ __global__ void pack_x3_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad
             }
             hv[j] = out;
         }
-        *reinterpret_cast<uint4 *>(base + tile_off_r(r, ch * 8, A_ROWS)) = *reinterpret_cast<const uint4 *>(hv);
+        *reinterpret_cast<uint4 *>(base + tile_off_r(r, ch * 8, T_ROWS)) = *reinterpret_cast<const uint4 *>(hv);
     }
 }
 
-// Model image: one warp per (virtual) component.  Columns [Bh | Bl | a0,a1,a2,ph,pl,ph,0...] with
-// B = p_k mu_k, A_k as in the header comment, P = -p_k/2.  Row K (if K < K_max) is the virtual
-// component standing for all empty slots; rows beyond are dead.
+// Model image: one warp per (virtual) component.  Chunk H columns [Bh (D), a0,a1,a2,ph,pl,ph, 0..],
+// chunk L columns [Bl (D), 0..] with B = p_k mu_k, A_k as in the header comment, P = -p_k/2.
+// Row K (if K < K_max) is the virtual component standing for all empty slots; rows beyond are dead.
 __global__ void pack_w3_kernel(segb_fixedvar m, int K_rows_pad, uint8_t *tiles) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= K_rows_pad) return;
-    const int D = m.D, KM = m.K_max, dp = dpad_of(D), KP = kpx_of(D);
+    const int D = m.D, KM = m.K_max, dp = dpad_of(D);
     const int K = *m.K;
-    uint8_t *base = tiles + (int64_t)(row / B_ROWS) * ((int64_t)B_ROWS * KP * 2);
-    const int r = row % B_ROWS;
+    const int64_t chunk_bytes = (int64_t)T_ROWS * dp * 2;
+    uint8_t *base = tiles + (int64_t)(row / NT_COLS) * (2 * chunk_bytes);
+    const int r = row % NT_COLS;
     const bool active = row < K, virt = (row == K && K < KM);
     const double c0 = -0.5 * D * log(2. * 3.14159265358979323846);
     double pk = 0.0, Ak = DEAD_A;
@@ -281,22 +285,22 @@ __global__ void pack_w3_kernel(segb_fixedvar m, int K_rows_pad, uint8_t *tiles) 
     const __half a2 = __float2half_rn(r1 - __half2float(a1));
     __half ph, pl;
     split2((float)(-0.5 * pk), ph, pl);
-    for (int ch = lane; ch < KP / 8; ch += 32) {
+    for (int ch = lane; ch < 2 * dp / 8; ch += 32) {
         __align__(16) __half hv[8];
+        const bool is_l = ch * 8 >= dp;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = ch * 8 + j;
+            const int c = ch * 8 + j - (is_l ? dp : 0);
             __half out = __float2half_rn(0.f);
-            if (c < 2 * dp) {
-                const int d = c < dp ? c : c - dp;
-                if (d < D && (active || virt)) {
-                    const double mu = active ? m.mu_NT[(size_t)d * KM + row] : m.mu_0[d];
+            if (c < D) {
+                if (active || virt) {
+                    const double mu = active ? m.mu_NT[(size_t)c * KM + row] : m.mu_0[c];
                     __half hi, lo;
                     split2((float)(pk * mu), hi, lo);
-                    out = c < dp ? hi : lo;
+                    out = is_l ? lo : hi;
                 }
-            } else {
-                const int ecol = c - 2 * dp;
+            } else if (!is_l) {
+                const int ecol = c - D;
                 if (ecol == 0) out = a0;
                 else if (ecol == 1) out = a1;
                 else if (ecol == 2) out = a2;
@@ -305,12 +309,14 @@ __global__ void pack_w3_kernel(segb_fixedvar m, int K_rows_pad, uint8_t *tiles) 
             }
             hv[j] = out;
         }
-        *reinterpret_cast<uint4 *>(base + tile_off_r(r, ch * 8, B_ROWS)) = *reinterpret_cast<const uint4 *>(hv);
+        const int cc = ch * 8 - (is_l ? dp : 0);
+        *reinterpret_cast<uint4 *>(base + (is_l ? chunk_bytes : 0) + tile_off_r(r, cc, T_ROWS)) =
+            *reinterpret_cast<const uint4 *>(hv);
     }
 }
 
 static inline int64_t rows_pad(int64_t n) { return (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS; }
-static inline int k_rows_pad(int K_max) { return (K_max + 1 + B_ROWS - 1) / B_ROWS * B_ROWS; }   // +1 virtual slot
+static inline int k_rows_pad(int K_max) { return (K_max + 1 + NT_COLS - 1) / NT_COLS * NT_COLS; }   // +1 virtual slot
 
 }  // namespace fvmma
 }  // namespace segb
@@ -318,8 +324,8 @@ static inline int k_rows_pad(int K_max) { return (K_max + 1 + B_ROWS - 1) / B_RO
 using namespace segb;
 using namespace segb::fvmma;
 
-extern "C" int64_t segb_fvmma_x_tiles_bytes(int64_t n_emb, int32_t D) { return rows_pad(n_emb) * kpx_of(D) * 2; }
-extern "C" int64_t segb_fvmma_w_tiles_bytes(int32_t K_max, int32_t D) { return (int64_t)k_rows_pad(K_max) * kpx_of(D) * 2; }
+extern "C" int64_t segb_fvmma_x_tiles_bytes(int64_t n_emb, int32_t D) { return rows_pad(n_emb) * 2 * dpad_of(D) * 2; }
+extern "C" int64_t segb_fvmma_w_tiles_bytes(int32_t K_max, int32_t D) { return (int64_t)k_rows_pad(K_max) * 2 * dpad_of(D) * 2; }
 
 extern "C" int segb_fvmma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, void *stream) {
     SEGB_CHECK_ARG(X && x_tiles && n_emb > 0 && D > 0, "null pointer");
@@ -341,12 +347,12 @@ extern "C" int segb_fvmma_log_marg(const segb_fixedvar *m, const void *x_tiles, 
     Params p;
     p.x_tiles = (const uint8_t *)x_tiles; p.w_tiles = (const uint8_t *)w_tiles; p.out = out; p.n_emb = n_emb;
     p.n_mtiles = (int32_t)(rows_pad(n_emb) / MT_ROWS);
-    p.n_ntiles = krp / B_ROWS;
-    p.n_blk_steps = dpad_of(D) / 16;
-    p.a_tile_bytes = (uint32_t)((int64_t)A_ROWS * kpx_of(D) * 2);
-    p.b_tile_bytes = (uint32_t)((int64_t)B_ROWS * kpx_of(D) * 2);
-    const size_t smem = 2 * (size_t)p.a_tile_bytes + N_STAGES * (size_t)p.b_tile_bytes + 256;
-    if (smem + 1024 > 227 * 1024) {
+    p.n_ntiles = krp / NT_COLS;
+    p.n_ksteps = dpad_of(D) / 16;
+    p.a_tile_bytes = (uint32_t)((int64_t)T_ROWS * 2 * dpad_of(D) * 2);
+    p.chunk_bytes = (uint32_t)((int64_t)T_ROWS * dpad_of(D) * 2);
+    const size_t smem = 2 * (size_t)p.a_tile_bytes + N_STAGES * (size_t)p.chunk_bytes + 256;
+    if (smem > 227 * 1024) {
         set_error("D=%d too large for the tensor-core log_marg kernel", D);
         return SEGB_E_UNSUPPORTED;
     }
