@@ -11,6 +11,7 @@
 // shuffles.  Sums are formed in the reference's element order (ascending start
 // landmark for logsumexp, ascending span for the draw) so that results differ
 // from the CPU only through exp()/log() rounding.  All arithmetic is float64.
+#include <stdlib.h>
 #include <type_traits>
 #include "mma_common.cuh"
 
@@ -731,32 +732,32 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
             // ---------------- backward
             uint8_t *bs = bs0 + (off - off0);
             if (MODE == SEGB_DP_VITERBI_KMEANS) {
-                // pointer chase; the chosen score of one hop is added while the next hop's
-                // back-pointer is in flight (same summation order: right to left)
+                // pointer chase (t strictly decreases, so no trip guard); the chosen score of
+                // one hop is added while the next hop's back-pointer is in flight -- same
+                // summation order as the reference: right to left
                 bs[N - 1] = 1;
                 int t = N;
                 double pend = 0.0;
-                bool have = false;
-                for (int guard = 0; guard <= N && status == SEGB_DP_OK; ++guard) {
-                    int b = bp[t * 32];
-                    if (have) total += pend;
-                    if (b == 0xff) {                       // window all -inf: walk left until feasible
-                        while (b == 0xff) {
-                            t = t - 1;
-                            if (t == 0) break;
-                            b = bp[t * 32];
+                if (status == SEGB_DP_OK) {
+                    while (true) {
+                        int b = bp[t * 32];
+                        total += pend;
+                        if (b == 0xff) {                   // window all -inf: walk left until feasible
+                            while (b == 0xff) {
+                                t = t - 1;
+                                if (t == 0) break;
+                                b = bp[t * 32];
+                            }
+                            if (t == 0) { status = SEGB_DP_INFEASIBLE; pend = 0.0; break; }
+                            bs[t - 1] = 1;
                         }
-                        if (t == 0) { status = SEGB_DP_INFEASIBLE; have = false; break; }
+                        pend = sc[(t - 1) * SB + b];
+                        t = t - b - 1;
+                        if (t <= 0) break;
                         bs[t - 1] = 1;
                     }
-                    const int k = b + 1;
-                    pend = sc[(t - 1) * SB + b];
-                    have = true;
-                    if (t - k - 1 < 0) break;
-                    bs[t - k - 1] = 1;
-                    t = t - k;
+                    total += pend;
                 }
-                if (have) total += pend;
             } else {
                 SharedRows rows;
                 rows.sc = sc; rows.S = SB;
@@ -811,20 +812,31 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
         // batched calls: stage the score blocks through shared memory with the copy engine
         const int Wlim = (c->n_slices_max == 0 || c->n_slices_max > c->S) ? c->S : c->n_slices_max;
         const bool al_smem = (mode != SEGB_DP_VITERBI_KMEANS);
-        const int G = dp_staged_pick_group(c->N_max, c->S, al_smem);
+        int G = dp_staged_pick_group(c->N_max, c->S, al_smem);
+        if (const char *env = getenv("SEGB_DP_GROUP")) {            // tuning aid
+            const int g_env = atoi(env);
+            if (g_env >= 16 && g_env <= 32) G = g_env;
+        }
         const size_t st_smem = G ? dp_staged_smem_bytes(c->N_max, c->S, G, al_smem) : 0;
         if (!scores_local && !u_counter && n_utt >= 32 && (c->S % 2) == 0 && Wlim == c->S && G >= 16 &&
             ((uintptr_t)scores & 15) == 0 && st_smem <= 72 * 1024 && !(alphas && !al_smem)) {
             p.group = G;
             const int groups = (n_utt + G - 1) / G;
             auto launch = [&](auto kern) -> int {
-                if (st_smem > 48 * 1024)
-                    SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
-                int dev = 0, n_sm = 0, per_sm = 0;
-                SEGB_CUDA(cudaGetDevice(&dev));
-                SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-                SEGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, st_smem));
-                const int blocks = min(groups, max(1, per_sm) * n_sm);      // persistent warps
+                // resident warps per device for this (kernel, shared-memory size): queried once
+                static void *cached_kern = nullptr;
+                static size_t cached_smem = 0;
+                static int cached_resident = 0;
+                if (cached_kern != (void *)kern || cached_smem != st_smem) {
+                    if (st_smem > 48 * 1024)
+                        SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
+                    int dev = 0, n_sm = 0, per_sm = 0;
+                    SEGB_CUDA(cudaGetDevice(&dev));
+                    SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+                    SEGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, st_smem));
+                    cached_kern = (void *)kern; cached_smem = st_smem; cached_resident = max(1, per_sm) * n_sm;
+                }
+                const int blocks = min(groups, cached_resident);            // persistent warps
                 kern<<<blocks, 32, st_smem, stream>>>(p);
                 SEGB_LAUNCH_CHECK();
                 return 0;

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--utts", type=int, default=200000)
 ap.add_argument("--mode", type=int, default=2)
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--scores", default="real", choices=["real", "uniform"])
 args = ap.parse_args()
 S = 6
 rng = np.random.RandomState(0)
@@ -24,7 +25,21 @@ lengths = rng.randint(15, 26, size=args.utts).astype(np.int64)
 n_pos = int(lengths.sum())
 corpus = DeviceCorpus(lengths, np.full((n_pos, S), -1, np.int32), np.full((n_pos, S), np.nan),
                       np.zeros(n_pos, np.uint8), 0, S, S)
-scores = -torch.rand(n_pos * S, dtype=torch.float64, device="cuda") * 40.0
+if args.scores == "uniform":
+    scores = -torch.rand(n_pos * S, dtype=torch.float64, device="cuda") * 40.0
+else:
+    # like the k-means sweep: -(distance ~ 0.3) * duration in frames, -inf where the span leaves the utterance
+    gaps = rng.randint(3, 15, size=n_pos).astype(np.float64)
+    B = np.concatenate([[0.0], np.cumsum(gaps)])
+    pos_off = np.concatenate([[0], np.cumsum(lengths)])
+    within = np.arange(n_pos) - np.repeat(pos_off[:-1], lengths)          # t - 1
+    sc = np.full((n_pos, S), -np.inf)
+    for l in range(1, S + 1):
+        ok = within >= l - 1
+        idx = np.nonzero(ok)[0]
+        dur = B[idx + 1] - B[idx + 1 - l]
+        sc[idx, l - 1] = -(0.3 + 0.02 * rng.standard_normal(len(idx))) * dur
+    scores = torch.from_numpy(sc.reshape(-1)).cuda()
 uni = torch.rand(n_pos, dtype=torch.float64, device="cuda")
 lp = torch.zeros(args.utts, dtype=torch.float64, device="cuda")
 st = torch.zeros(args.utts, dtype=torch.int32, device="cuda")
