@@ -96,10 +96,19 @@ class FrozenKMeansSweep(object):
         self.scores = torch.empty(corpus.n_pos * corpus.S, dtype=torch.float64, device=dev)
         self.log_prob = torch.zeros(corpus.n_utt, dtype=torch.float64, device=dev)
         self.status = torch.zeros(corpus.n_utt, dtype=torch.int32, device=dev)
-        self.sum_x = torch.zeros(c.K_max, c.D, dtype=torch.float64, device=dev)
+        # one flat float64 buffer = what a sweep all-reduces: [sum_x (K_max*D) | counts (K_max)]
+        self.red = torch.zeros(c.K_max * c.D + c.K_max, dtype=torch.float64, device=dev)
+        self.sum_x = self.red[:c.K_max * c.D].view(c.K_max, c.D)
+        self.cnt_f = self.red[c.K_max * c.D:]
         self.cnt = torch.zeros(c.K_max, dtype=torch.int64, device=dev)
+        # end-of-sweep scalars read with ONE device->host copy: [bad DP statuses, fallback rows, emptied components]
+        self.flags = torch.zeros(3, dtype=torch.int64, device=dev)
+        self.flags_h = torch.zeros(3, dtype=torch.int64).pin_memory()
+        self.log_prob_h = torch.zeros(corpus.n_utt, dtype=torch.float64).pin_memory()
+        self.side = torch.cuda.Stream()
         self.last_fallback = 0
         self.mma = MmaScorer(c) if scorer == "mma" else None
+        self.K_host = None                     # host copy of the active-component count (no .item() per sweep)
 
     # ---- phases (each is one or two launches; no host sync inside)
     def score(self):
@@ -130,10 +139,26 @@ class FrozenKMeansSweep(object):
         _lib.check(lib.segb_kmeans_collect(c.struct(), cp.struct(), 0, cp.n_utt, _lib.ptr(src), _lib.ptr(self.sum_x),
                                            _lib.ptr(self.cnt), sp))
 
+    def summarize(self):
+        """Start the end-of-sweep summary on a side stream, overlapping the token collection:
+        the per-utterance objectives go to pinned host memory (their sum must be formed in
+        utterance order -- the reference accumulates it one utterance at a time,
+        kmeans_acoustic_wordseg.py:398-406 -- a serial float64 chain that a host core runs
+        faster than one GPU thread: dependent DADDs cost ~24 cycles each on B200) and the DP statuses
+        are counted on the device into self.flags[0]."""
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self.flags[0:1].copy_((self.status != _lib.DP_OK).sum())
+            self.log_prob_h.copy_(self.log_prob, non_blocking=True)
+
     def reduce_and_update(self):
-        """All-reduce the sufficient statistics over ranks (NCCL over NVLink), rebuild means."""
+        """All-reduce the sufficient statistics over ranks (NCCL over NVLink) -- ONE collective
+        over the flat buffer [sum_x | counts] -- and rebuild the means."""
         lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
-        reduce_stats(self.sum_x, self.cnt)
+        if _dist_on():
+            self.cnt_f.copy_(self.cnt)                       # counts ride along as float64 (exact below 2^53)
+            dist.all_reduce(self.red, op=dist.ReduceOp.SUM)
+            self.cnt.copy_(self.cnt_f)
         _lib.check(lib.segb_kmeans_set_means(c.struct(), _lib.ptr(self.sum_x), _lib.ptr(self.cnt), sp))
 
     def init_means_from_assignments(self):
@@ -145,6 +170,7 @@ class FrozenKMeansSweep(object):
         K = int((self.cnt > 0).sum().item())
         assert bool((self.cnt[:K] > 0).all().item()), "initial assignments must use labels 0..K-1"
         c._K.fill_(K)
+        self.K_host = K
 
     def profile_phases(self):
         """Device time of each phase of one sweep (CUDA events on the launching stream); the
@@ -178,26 +204,38 @@ class FrozenKMeansSweep(object):
         return {n: evs[i].elapsed_time(evs[i + 1]) for i, n in enumerate(names)}
 
     def sweep(self):
-        """One frozen sweep; returns sum_neg_len_sqrd_norm (summed over all ranks)."""
+        """One frozen sweep; returns sum_neg_len_sqrd_norm (summed over all ranks).  No host
+        round trip until the end: one all-reduce, one small device->host copy, one sync."""
         c, cp = self.c, self.corpus
-        K_before = c.K
+        if self.K_host is None:
+            self.K_host = c.K
+        K_before = self.K_host
         self.score()
         self.segment()
+        self.summarize()
         self.collect()
-        # --- host decisions (one sync per sweep)
-        st = self.status.cpu().numpy()
-        assert np.all(st == _lib.DP_OK), "segmentation failed (status %s)" % np.unique(st)
-        total = float(np.cumsum(self.log_prob.cpu().numpy())[-1]) if cp.n_utt else 0.0
-        if self.scorer == "mma":
-            self.last_fallback = int(self.mma.n_fallback.item())
         if K_before < c.K_max:
             self._clamp_inactive_winners(K_before)
         self.reduce_and_update()
+        K_now = self.K_host
+        if self.scorer == "mma":
+            self.flags[1:2].copy_(self.mma.n_fallback)
+        self.flags[2:3].copy_((self.cnt[:K_now] == 0).sum())
+        torch.cuda.current_stream().wait_stream(self.side)
+        self.flags_h.copy_(self.flags, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n_bad, n_fb, n_empty = (int(v) for v in self.flags_h.tolist())
+        assert n_bad == 0, "segmentation failed for %d utterances (status %s)" % (
+            n_bad, np.unique(self.status.cpu().numpy()))
+        self.last_fallback = n_fb
+        # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time)
+        total = float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
         if _dist_on():
             t = torch.tensor([total], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             total = float(t.item())
-        self._clean_components(c.K)
+        if n_empty:
+            self._clean_components(K_now)
         return total
 
     def _clean_components(self, K_old):
@@ -224,6 +262,7 @@ class FrozenKMeansSweep(object):
         c._means[K:K_old] = c._rnd[K:K_old]
         c._meansT.copy_(c._means.t())
         c._K.fill_(int(K))
+        self.K_host = int(K)
 
     def _clamp_inactive_winners(self, K_before):
         """add_item's `k > K -> K` clamp (kmeans_components.py:103-106) for tokens won by an
@@ -250,6 +289,7 @@ class FrozenKMeansSweep(object):
         else:
             ks, K = clamp_plan(ks, K_before)
         c._K.fill_(int(K))
+        self.K_host = int(K)
         if len(ids):
             self.best_k[_lib.dev(ids)] = _lib.dev(np.asarray(ks).astype(np.int32))
         self.collect()

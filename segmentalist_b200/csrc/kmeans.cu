@@ -458,3 +458,4 @@ extern "C" int segb_kmeans_set_means(const segb_kmeans *m, const double *sum_x, 
     SEGB_LAUNCH_CHECK();
     return 0;
 }
+

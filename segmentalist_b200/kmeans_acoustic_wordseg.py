@@ -146,6 +146,7 @@ class SegmentalKMeansWordseg(object):
         if self._frozen is None:
             self._frozen = FrozenKMeansSweep(self.acoustic_model.components, self._corpus, wip=self.wip,
                                              scorer=scorer)
+        self._frozen.K_host = None      # sequential sweeps / fit() in between may have changed K
         record = {"sum_neg_len_sqrd_norm": [], "components": [], "n_tokens": [], "sample_time": []}
         for _ in range(n_iter):
             t0 = time.time()
