@@ -511,11 +511,14 @@ def run_ours(args):
         total_host = []
 
         def e2e_step():
-            comps._X.copy_(X_host, non_blocking=True)                       # H2D embeddings
             comps._means.copy_(means_host, non_blocking=True)               # H2D model
             comps._meansT.copy_(comps._means.t())
-            sweep.mma.pack_x()                                              # fp16 tile image of the fresh upload
-            total_host.append(sweep.sweep())                                # sweep (includes result syncs)
+            if args.scorer == "mma":
+                # H2D embeddings in chunks, overlapped with fp16 tile packing + filter + refine
+                total_host.append(sweep.sweep(X_host=X_host))
+            else:
+                comps._X.copy_(X_host, non_blocking=True)
+                total_host.append(sweep.sweep())
             bounds_host.copy_(corpus.bounds, non_blocking=True)             # D2H segmentation
             assign_host.copy_(comps._assign, non_blocking=True)             # D2H assignments
             means_host.copy_(comps._means, non_blocking=True)               # D2H model
@@ -538,7 +541,7 @@ def run_ours(args):
         d2h = bounds_host.numel() + assign_host.numel() * 4 + means_host.numel() * 4 + 8
         e2e = {"value": args.utts / (float(te.item()) * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()),
-               "note": "per rank: pinned-host X + means -> HBM, fp16 tile packing, sweep, boundaries/assignments/means back"}
+               "note": "per rank: pinned-host X (1M-row chunks on a copy stream, overlapped with fp16 tile packing + filter + refine) + means -> HBM, sweep, boundaries/assignments/means back"}
 
     # ---- CPU baseline + parity gate on a bounded sample (rank 0)
     cpu_baseline = None

@@ -79,6 +79,49 @@ class MmaScorer(object):
         self.filter()
         self.refine(best_val, best_k)
 
+    def score_streamed(self, X_host, best_val, best_k, chunk_rows=1 << 20):
+        """Score embeddings that still live in (pinned) HOST memory: the rows are uploaded in
+        chunks on a copy stream while the previous chunk is packed to fp16 tiles, filtered and
+        refined on the compute stream, so the sweep costs max(PCIe, compute) instead of their
+        sum.  Chunks start on 256-row boundaries (whole operand tiles); every kernel is the
+        same C-ABI call as in score(), handed pointers offset to the chunk."""
+        import ctypes
+        lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
+        assert X_host.shape == c._X.shape and X_host.dtype == torch.float32 and X_host.is_pinned()
+        assert chunk_rows % 256 == 0
+        if getattr(self, "copy_stream", None) is None:
+            self.copy_stream = torch.cuda.Stream()
+            self.fb_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        main = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(main)             # earlier kernels may still read X
+        self.pack_means()
+        self.fb_total.zero_()
+        kp2 = lib.segb_mma_x_tiles_bytes(256, c.D) // 256        # bytes of tile image per row
+        rec = lib.segb_mma_cand_bytes(1)
+        m = c.struct()
+        x_base = c._X.data_ptr()
+        vp = ctypes.c_void_p
+        for lo in range(0, c.N, chunk_rows):
+            hi = min(c.N, lo + chunk_rows)
+            n = hi - lo
+            with torch.cuda.stream(self.copy_stream):
+                c._X[lo:hi].copy_(X_host[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            main.wait_event(ev)
+            xt = vp(self.x_tiles.data_ptr() + lo * kp2)
+            xe = vp(self.x_err.data_ptr() + 8 * lo)
+            cd = vp(self.cand.data_ptr() + rec * lo)
+            _lib.check(lib.segb_mma_pack_x(vp(x_base + 4 * c.D * lo), n, c.D, xt, xe, _lib.ptr(self.x_max), sp))
+            _lib.check(lib.segb_mma_filter(xt, _lib.ptr(self.w_tiles), n, c.K_max, c.D, _lib.ptr(self.x_max),
+                                           _lib.ptr(self.w_max), cd, sp))
+            m.X, m.n_emb = x_base + 4 * c.D * lo, n
+            _lib.check(lib.segb_mma_refine(m, cd, xe, _lib.ptr(self.w_max), n, _lib.ptr(self.work),
+                                           vp(best_val.data_ptr() + 4 * lo), vp(best_k.data_ptr() + 4 * lo),
+                                           _lib.ptr(self.n_fallback), sp))
+            self.fb_total += self.n_fallback
+        self.n_fallback.copy_(self.fb_total)
+
 
 class FrozenKMeansSweep(object):
 
@@ -111,10 +154,13 @@ class FrozenKMeansSweep(object):
         self.K_host = None                     # host copy of the active-component count (no .item() per sweep)
 
     # ---- phases (each is one or two launches; no host sync inside)
-    def score(self):
+    def score(self, X_host=None):
         lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
         m = c.struct()
-        if self.scorer == "exact":
+        if X_host is not None:
+            assert self.scorer == "mma", "streaming from host memory uses the tensor-core scorer"
+            self.mma.score_streamed(X_host, self.best_val, self.best_k)
+        elif self.scorer == "exact":
             _lib.check(lib.segb_kmeans_best(m, None, c.N, _lib.ptr(self.best_val), _lib.ptr(self.best_k), sp))
         else:
             self.mma.score(self.best_val, self.best_k)
@@ -203,14 +249,16 @@ class FrozenKMeansSweep(object):
         torch.cuda.synchronize()
         return {n: evs[i].elapsed_time(evs[i + 1]) for i, n in enumerate(names)}
 
-    def sweep(self):
+    def sweep(self, X_host=None):
         """One frozen sweep; returns sum_neg_len_sqrd_norm (summed over all ranks).  No host
-        round trip until the end: one all-reduce, one small device->host copy, one sync."""
+        round trip until the end: one all-reduce, one small device->host copy, one sync.
+        X_host: pinned float32 host copy of the embeddings to (re)upload while scoring
+        (out-of-core / end-to-end use); None = the embeddings are already resident in HBM."""
         c, cp = self.c, self.corpus
         if self.K_host is None:
             self.K_host = c.K
         K_before = self.K_host
-        self.score()
+        self.score(X_host)
         self.segment()
         self.summarize()
         self.collect()

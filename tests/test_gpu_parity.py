@@ -399,6 +399,38 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
     npt.assert_array_equal(bv, val.cpu().numpy()[ids])
 
 
+def test_mma_scorer_streamed_from_host(sb):
+    """Scoring embeddings uploaded chunk by chunk from pinned host memory (copy stream overlapped
+    with packing + filter + refine) gives the same bits as scoring the resident matrix; the
+    device copy of X is scrambled first so that only the streamed upload can make it pass."""
+    from segmentalist_b200 import synth
+    from segmentalist_b200.batch import MmaScorer
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    rng = np.random.RandomState(77)
+    n_emb, K_max = 3000, 300
+    centres = synth.cluster_centres(60, 130, rng)
+    X = synth._unit_rows(centres[rng.randint(0, 60, n_emb)] + 0.05 * rng.standard_normal((n_emb, 130)).astype(np.float32))
+    assign = -np.ones(n_emb, dtype=np.int64)
+    assign[:1500] = np.arange(1500) % K_max
+    np.random.seed(1)
+    comps = KMeansComponents(X, assign, K_max)
+    mma = MmaScorer(comps)
+    val0 = torch.empty(n_emb, dtype=torch.float32, device="cuda")
+    arg0 = torch.empty(n_emb, dtype=torch.int32, device="cuda")
+    mma.score(val0, arg0)
+    fb0 = int(mma.n_fallback.item())
+    X_host = torch.from_numpy(np.ascontiguousarray(X)).pin_memory()
+    comps._X.fill_(0.25)
+    val1 = torch.full((n_emb,), -1.0, dtype=torch.float32, device="cuda")
+    arg1 = torch.full((n_emb,), -7, dtype=torch.int32, device="cuda")
+    mma.score_streamed(X_host, val1, arg1, chunk_rows=1024)
+    torch.cuda.synchronize()
+    npt.assert_array_equal(arg1.cpu().numpy(), arg0.cpu().numpy())
+    npt.assert_array_equal(val1.cpu().numpy(), val0.cpu().numpy())
+    npt.assert_array_equal(comps._X.cpu().numpy(), X)
+    assert int(mma.n_fallback.item()) == fb0
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("S,n_hi", [(1, 60), (3, 60), (6, 60), (8, 60), (2, 26), (4, 26), (6, 26), (8, 26), (3, 26)])
 def test_dp_small_fastpath_vs_oracle(sb, mode, S, n_hi):
