@@ -150,6 +150,18 @@ int segb_gibbs_sweep_fixedvar(const segb_fixedvar *m, const segb_corpus *c, cons
                               const double *uniforms, int64_t *u_counter, double *scratch_scores,
                               double *log_probs, int32_t *status, void *stream);
 
+/* The same sweep as ONE cooperative kernel launch: CTA b owns a contiguous range of components
+ * in shared memory, steps are separated by grid barriers, the small replicated state (counts, K,
+ * draws consumed) advances identically on every CTA (csrc/fixedvar_gibbs.cu).  d_order is a DEVICE
+ * array; work: segb_gibbs_work_bytes() bytes of device scratch.  Returns SEGB_E_UNSUPPORTED when
+ * the model does not fit the per-CTA shared memory (use segb_gibbs_sweep_fixedvar then).      */
+int64_t segb_gibbs_work_bytes(int32_t K_max, int32_t N_max, int32_t S);
+int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb_corpus *c, const int32_t *d_order,
+                                   int32_t n_order, int32_t fb_mode, double time_power_term, double wip,
+                                   double anneal_temp, int32_t anneal_gibbs_am,
+                                   const double *uniforms, int64_t *u_counter, void *work,
+                                   double *log_probs, int32_t *status, void *stream);
+
 /* ------------------------------------------------------------------ k-means (A10-A12) */
 
 /* Device view of KMeansComponents (kmeans_components.py:18-91). `means` has X's

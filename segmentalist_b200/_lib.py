@@ -19,6 +19,7 @@ c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, cty
 
 DP_FFBS, DP_VITERBI_GMM, DP_VITERBI_KMEANS = 0, 1, 2
 DP_OK, DP_INFEASIBLE, DP_EMPTY_SLICE, DP_NAN = 0, 1, 2, 3
+E_UNSUPPORTED = -2
 
 
 class Corpus(ctypes.Structure):
@@ -56,6 +57,10 @@ _PROTOS = {
     "segb_gibbs_sweep_fixedvar": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(Corpus), c_vp, c_i32,
                                                  c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp]),
+    "segb_gibbs_work_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "segb_gibbs_sweep_fixedvar_coop": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(Corpus), c_vp, c_i32,
+                                                      c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                                      c_vp, c_vp]),
     "segb_kmeans_neg_sqrd_norm_row": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_i32, c_vp, c_vp]),
     "segb_kmeans_best": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_i64, c_vp, c_vp, c_vp]),
     "segb_kmeans_add_items": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_i32, c_vp]),

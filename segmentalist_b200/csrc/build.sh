@@ -6,9 +6,13 @@ OUT="$HERE/../libsegb200.so"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr --extended-lambda -Xcompiler -fPIC ${SEGB_NVCC_EXTRA}"
 OBJS=""
-for f in api dp fixedvar kmeans kmeans_mma fixedvar_mma; do
+for f in api dp fixedvar fixedvar_gibbs kmeans kmeans_mma fixedvar_mma; do
   if [ -f "$HERE/$f.cu" ]; then
-    if [ ! -f "$HERE/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/$f.o" ] || [ "$HERE/common.cuh" -nt "$HERE/$f.o" ] || [ "$HERE/mma_common.cuh" -nt "$HERE/$f.o" ] || [ "$HERE/../../include/segb200.h" -nt "$HERE/$f.o" ]; then
+    stale=0
+    for dep in "$HERE/$f.cu" "$HERE"/*.cuh "$HERE/../../include/segb200.h"; do
+      if [ ! -f "$HERE/$f.o" ] || [ "$dep" -nt "$HERE/$f.o" ]; then stale=1; fi
+    done
+    if [ $stale = 1 ]; then
       $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/$f.o" &
     fi
     OBJS="$OBJS $HERE/$f.o"

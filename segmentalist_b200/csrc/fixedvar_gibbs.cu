@@ -1,0 +1,504 @@
+// Persistent cooperative Gibbs sweep for the fixed-variance FBGMM segmenter.
+//
+// Replaces UnigramAcousticWordseg.gibbs_sample_i (unigram_acoustic_wordseg.py:252-360) called
+// for a whole list of utterances, i.e. per utterance, strictly in order:
+//   remove its tokens (:270-273 -> GaussianComponentsFixedVar.del_item / del_component,
+//   gaussian_components_fixedvar.py:172-221), score every candidate segment
+//   (get_vec_embed_log_probs :474-511 -> FBGMM.log_marg_i fbgmm.py:256-285), run the DP
+//   (forward_backward :653-756 or forward_backward_viterbi :759-864), assign the new tokens left
+//   to right (gibbs_sample_inside_loop_i / map_assign_i fbgmm.py:422-494 -> add_item :153-170).
+//
+// Collapsed Gibbs is sequential -- every assignment sees the statistics left by the previous
+// one -- so the sweep is latency-bound, and the version that launches four kernels per
+// utterance (fixedvar.cu) spends its time pulling the [D, K_max] tables through ONE SM for every
+// token.  Here ONE cooperative launch runs the whole sweep: CTA b owns components
+// [b*per, (b+1)*per) and keeps their statistics in shared memory; every step is a short local
+// computation followed by a grid barrier:
+//   remove   owner-local updates; the small replicated state (counts, K, n_total) is advanced
+//            identically by every CTA, so no communication unless a component dies (then the
+//            last component's statistics move between owners through the global tables)
+//   score    every CTA scores all candidate segments against its own components -> partial
+//            (max, sum-exp) per segment -> barrier -> CTA s % G combines segment s -> barrier
+//   DP       every CTA runs the same warp-level DP on the same scores (no broadcast needed)
+//   assign   per token: owners publish the log-probabilities of their slots -> barrier -> every
+//            CTA reads all K_max values and takes the same decision (fv_decide); the owner of
+//            the chosen slot updates its statistics
+// Global tables (the host-visible model) are written through on every update; everything another
+// CTA may have written during the launch is read with ld.global.cg (L1 is not coherent across SMs).
+// All arithmetic is float64; predictive sums use NumPy's pairwise order with separately rounded operations.
+#include "dp_warp.cuh"
+#include "fixedvar_common.cuh"
+
+namespace segb {
+
+constexpr int GB_THREADS = 256;
+
+struct GibbsParams {
+    segb_fixedvar m;
+    segb_corpus c;
+    const int32_t *order;          // device
+    int32_t n_order, fb_mode, assign_mode, per, M_cap, xb;   // xb = candidate rows staged per batch
+    double tpt, wip, anneal_temp, assign_temp;
+    const double *uniforms;
+    int64_t *u_counter;
+    double *log_probs;
+    int32_t *status;
+    // work area (global)
+    unsigned *bar;                 // [2] arrival count, generation
+    double *part_m, *part_t;       // [G][M_cap] partial (max, sum-exp) of every candidate per CTA
+    double *seg_prior;             // [M_cap] log_prior of every candidate
+    double *scores;                // [M_cap] banded scores of the current utterance
+    double *v;                     // [2][K_max] slot log-probabilities of the current token (double-buffered)
+};
+
+// Sense-reversing grid barrier (all CTAs are co-resident: cooperative launch).  A protocol bug
+// traps instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned tag = 0, unsigned h = 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        volatile unsigned *vgen = bar + 1;
+        volatile unsigned *trace = bar + 16;                 // [n_blocks] last barrier tag of every CTA (diagnostics)
+        trace[blockIdx.x] = tag;
+        volatile unsigned *trace2 = bar + 16 + 160;
+        trace2[blockIdx.x] = h;
+        const unsigned gen = *vgen;
+        if (atomicAdd(bar, 1u) == n_blocks - 1) {
+            *bar = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            unsigned spins = 0;
+            while (*vgen == gen) {
+                if (++spins > (1u << 23)) {
+                    printf("segb gibbs: grid barrier timed out: block %d at tag %x; tags of blocks 0..7: %x %x %x %x %x %x %x %x; state %x %x %x %x %x %x %x %x\n",
+                           blockIdx.x, tag, trace[0], trace[1], trace[2], trace[3], trace[4], trace[5], trace[6], trace[7],
+                           trace2[0], trace2[1], trace2[2], trace2[3], trace2[4], trace2[5], trace2[6], trace2[7]);
+                    __trap();
+                }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct GibbsSmem {
+    double *mu, *pp, *num, *pN;    // [per][D] statistics of the owned components
+    double *lpp;                   // [per] log_prod_precision_pred
+    double *pl;                    // [per] log(alpha/K_max + count)  (refreshed when counts change)
+    double *xs;                    // [xb][D] staged embeddings
+    double *vt;                    // [xb][per] scores of the staged batch against the owned components
+    double *red;                   // [40]
+    double *sk;                    // [K_max]  (ScoreSmem view: xs | red | sk is NOT contiguous here)
+    double *sc;                    // [M_cap] scores of the utterance
+    double *al;                    // [N_cap + 1]
+    double *tmp;                   // [D]
+    int32_t *counts;               // [K_max] replicated
+    int32_t *tok;                  // [N_cap] ids of the tokens being removed
+    int32_t *tk;                   // [N_cap] their components (snapshot taken before anything is modified)
+    uint8_t *bo;                   // [N_cap]
+};
+
+__host__ __device__ inline size_t gibbs_smem_bytes(int D, int K_max, int per, int xb, int M_cap, int N_cap) {
+    size_t d = (size_t)4 * per * D + 2 * per + (size_t)xb * D + (size_t)xb * per + 40 + K_max + M_cap + (N_cap + 1) + D;
+    return d * 8 + (size_t)K_max * 4 + (size_t)N_cap * 8 + ((N_cap + 15) / 16) * 16 + 64;
+}
+
+// predictive quadratic form sum_d ((mu_d - x_d)^2 * pp_d) in NumPy's pairwise order (:247-252)
+__device__ __forceinline__ double quad_form(const double *mu, const double *pp, const double *x, int D) {
+    return pairwise_sum<double>([&](int d) {
+        const double dl = __dsub_rn(mu[d], x[d]);
+        return __dmul_rn(__dmul_rn(dl, dl), pp[d]);
+    }, D);
+}
+
+__global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const segb_fixedvar &m = p.m;
+    const segb_corpus &c = p.c;
+    const int D = m.D, KM = m.K_max, per = p.per, xb = p.xb, S = c.S;
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_lo = min(b * per, KM), k_hi = min(k_lo + per, KM), n_own = k_hi - k_lo;
+
+    GibbsSmem s;
+    {
+        double *q = reinterpret_cast<double *>(gsm);
+        s.mu = q; q += (size_t)per * D;
+        s.pp = q; q += (size_t)per * D;
+        s.num = q; q += (size_t)per * D;
+        s.pN = q; q += (size_t)per * D;
+        s.lpp = q; q += per;
+        s.pl = q; q += per;
+        s.xs = q; q += (size_t)xb * D;
+        s.vt = q; q += (size_t)xb * per;
+        s.red = q; q += 40;
+        s.sk = q; q += KM;
+        s.sc = q; q += p.M_cap;
+        s.al = q; q += c.N_max + 1;
+        s.tmp = q; q += D;
+        s.counts = reinterpret_cast<int32_t *>(q);
+        s.tok = s.counts + KM;
+        s.tk = s.tok + c.N_max;
+        s.bo = reinterpret_cast<uint8_t *>(s.tk + c.N_max);
+    }
+    ScoreSmem ds(s.xs, D);          // only .red / .sk are used by fv_decide
+    ds.red = s.red; ds.sk = s.sk;
+
+    // ---- load the owned statistics and the replicated state
+    for (int i = tid; i < n_own * D; i += GB_THREADS) {
+        const int kl = i / D, d = i % D;
+        const size_t o = (size_t)d * KM + (k_lo + kl);
+        s.mu[kl * D + d] = m.mu_NT[o]; s.pp[kl * D + d] = m.prec_predT[o];
+        s.num[kl * D + d] = m.mu_N_numT[o]; s.pN[kl * D + d] = m.prec_NT[o];
+    }
+    for (int kl = tid; kl < n_own; kl += GB_THREADS) s.lpp[kl] = m.log_prod_prec_pred[k_lo + kl];
+    for (int k = tid; k < KM; k += GB_THREADS) s.counts[k] = m.counts[k];
+    int K = *m.K;
+    long long n_total = *m.n_total;
+    long long u_pos = p.u_counter ? *p.u_counter : 0;
+    const double c0 = fv_norm_const(D);
+    const double log_empty = log(m.alpha / KM + 0.);
+    unsigned tok_parity = 0;
+    __syncthreads();
+
+    // refresh precision_pred, mu_N, log_prod_precision_pred of owned slot kl and write the
+    // component through to the global tables (:317-325)
+    auto refresh_and_publish = [&](int kl) {
+        const int k = k_lo + kl;
+        for (int d = tid; d < D; d += GB_THREADS) {
+            const double pNv = s.pN[kl * D + d], pr = m.precision[d];
+            const double ppv = __ddiv_rn(__dmul_rn(pNv, pr), __dadd_rn(pNv, pr));
+            const double muv = __ddiv_rn(s.num[kl * D + d], pNv);
+            s.pp[kl * D + d] = ppv;
+            s.mu[kl * D + d] = muv;
+            s.tmp[d] = log(ppv);
+            const size_t o = (size_t)d * KM + k;
+            m.mu_N_numT[o] = s.num[kl * D + d]; m.prec_NT[o] = pNv; m.prec_predT[o] = ppv; m.mu_NT[o] = muv;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double l = pairwise_sum<double>([&](int i) { return s.tmp[i]; }, D);
+            s.lpp[kl] = l;
+            m.log_prod_prec_pred[k] = l;
+            m.counts[k] = s.counts[k];
+        }
+        __syncthreads();
+    };
+    auto zero_slot = [&](int kl) {
+        const int k = k_lo + kl;
+        for (int d = tid; d < D; d += GB_THREADS) {
+            s.mu[kl * D + d] = 0.; s.pp[kl * D + d] = 0.; s.num[kl * D + d] = 0.; s.pN[kl * D + d] = 0.;
+            const size_t o = (size_t)d * KM + k;
+            m.mu_N_numT[o] = 0.; m.prec_NT[o] = 0.; m.prec_predT[o] = 0.; m.mu_NT[o] = 0.;
+        }
+        if (tid == 0) { s.lpp[kl] = 0.; m.log_prod_prec_pred[k] = 0.; m.counts[k] = 0; }
+        __syncthreads();
+    };
+
+    for (int it = 0; it < p.n_order; ++it) {
+        const int u = p.order[it];
+        const int64_t off = c.pos_off[u];
+        const int N = (int)(c.pos_off[u + 1] - off);
+        const int n_slots = N * S;
+
+        // the same utterance twice in a row: its new tokens must be visible before they are read
+        if (it > 0 && p.order[it - 1] == u) grid_barrier(p.bar, G, (it << 8) | 1);
+
+        // ================= remove the utterance's current tokens (:270-273)
+        // snapshot of (token, component) before anything is modified: every CTA must see the same list
+        for (int j = tid; j < N; j += GB_THREADS) {
+            const int id = __ldcg(c.tok_id + off + j);
+            s.tok[j] = id;
+            s.tk[j] = (id >= 0) ? __ldcg(m.assignments + id) : -1;
+        }
+        __syncthreads();
+        for (int j = 0; j < N; ++j) {
+            const int id = s.tok[j];
+            const int k = s.tk[j];
+            if (id < 0 || k < 0) continue;
+            __syncthreads();
+            const int cnt = s.counts[k] - 1;
+            __syncthreads();
+            if (tid == 0) s.counts[k] = cnt;
+            n_total -= 1;
+            const bool own = (k >= k_lo && k < k_hi);
+            if (cnt > 0) {
+                if (own) {
+                    const int kl = k - k_lo;
+                    for (int d = tid; d < D; d += GB_THREADS) {
+                        const double pr = m.precision[d];
+                        s.num[kl * D + d] = __dsub_rn(s.num[kl * D + d], __dmul_rn(pr, fv_x(m, id, d)));
+                        s.pN[kl * D + d] = __dsub_rn(s.pN[kl * D + d], pr);
+                    }
+                    __syncthreads();
+                    refresh_and_publish(kl);
+                }
+            } else {
+                // del_component (:190-221): the last component moves into slot k
+                const int last = K - 1;
+                grid_barrier(p.bar, G, (it << 8) | 0x10 | (j << 16));   // every owner's write-through is visible
+                if (k != last) {
+                    if (own) {
+                        const int kl = k - k_lo;
+                        for (int d = tid; d < D; d += GB_THREADS) {
+                            const size_t a = (size_t)d * KM + k, o = (size_t)d * KM + last;
+                            const double nu = __ldcg(m.mu_N_numT + o), pNv = __ldcg(m.prec_NT + o), ppv = __ldcg(m.prec_predT + o),
+                                         muv = __ldcg(m.mu_NT + o);
+                            s.num[kl * D + d] = nu; s.pN[kl * D + d] = pNv; s.pp[kl * D + d] = ppv; s.mu[kl * D + d] = muv;
+                            m.mu_N_numT[a] = nu; m.prec_NT[a] = pNv; m.prec_predT[a] = ppv; m.mu_NT[a] = muv;
+                            m.mu_N_numT[o] = 0.; m.prec_NT[o] = 0.; m.prec_predT[o] = 0.; m.mu_NT[o] = 0.;
+                        }
+                        if (tid == 0) {
+                            const double l = __ldcg(m.log_prod_prec_pred + last);
+                            s.lpp[kl] = l;
+                            m.log_prod_prec_pred[k] = l; m.log_prod_prec_pred[last] = 0.;
+                            m.counts[k] = s.counts[last]; m.counts[last] = 0;
+                        }
+                    }
+                    if (last >= k_lo && last < k_hi) {           // the old home forgets it (global zeroed by the new owner)
+                        const int kl = last - k_lo;
+                        for (int d = tid; d < D; d += GB_THREADS) {
+                            s.mu[kl * D + d] = 0.; s.pp[kl * D + d] = 0.; s.num[kl * D + d] = 0.; s.pN[kl * D + d] = 0.;
+                        }
+                        if (tid == 0) s.lpp[kl] = 0.;
+                    }
+                    // relabel the moved component's members: live tokens of the corpus, split over the grid
+                    for (int64_t i = (int64_t)b * GB_THREADS + tid; i < c.n_pos; i += (int64_t)G * GB_THREADS) {
+                        const int t_id = __ldcg(c.tok_id + i);
+                        if (t_id >= 0 && __ldcg(m.assignments + t_id) == last) m.assignments[t_id] = k;
+                    }
+                    for (int jj = j + 1 + tid; jj < N; jj += GB_THREADS) if (s.tk[jj] == last) s.tk[jj] = k;
+                    __syncthreads();
+                    if (tid == 0) { s.counts[k] = s.counts[last]; s.counts[last] = 0; }
+                } else if (own) {
+                    zero_slot(k - k_lo);
+                }
+                K = last;
+                grid_barrier(p.bar, G, (it << 8) | 0x20 | (j << 16));   // relabelled assignments are visible
+            }
+            __syncthreads();
+        }
+
+        // ================= score every candidate segment (:474-511, fbgmm.py:256-285)
+        const double log_norm = log((double)n_total + m.alpha);
+        for (int kl = tid; kl < n_own; kl += GB_THREADS)
+            s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_lo + kl]);
+        __syncthreads();
+        const int n_act = max(0, min(K, k_hi) - k_lo);           // owned ACTIVE components
+        for (int s0 = 0; s0 < n_slots; s0 += xb) {
+            const int nb = min(xb, n_slots - s0);
+            for (int i = tid; i < nb * D; i += GB_THREADS) {
+                const int bb = i / D, d = i % D;
+                const int id = c.seg_id[off * S + s0 + bb];
+                s.xs[bb * D + d] = (id >= 0) ? fv_x(m, id, d) : 0.0;
+            }
+            __syncthreads();
+            for (int i = tid; i < nb * n_act; i += GB_THREADS) {
+                const int bb = i / n_act, kl = i % n_act;
+                const double acc = quad_form(s.mu + kl * D, s.pp + kl * D, s.xs + bb * D, D);
+                s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm) + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
+            }
+            __syncthreads();
+            for (int bb = tid; bb < nb; bb += GB_THREADS) {
+                double mx = neg_inf(), t = 0.0;
+                for (int kl = 0; kl < n_act; ++kl) mx = fmax(mx, s.vt[bb * per + kl]);
+                for (int kl = 0; kl < n_act; ++kl) t += exp(s.vt[bb * per + kl] - mx);
+                p.part_m[(size_t)b * p.M_cap + s0 + bb] = mx;
+                p.part_t[(size_t)b * p.M_cap + s0 + bb] = t;
+            }
+            // log_prior of the candidates this CTA will combine (slot % G == b), one warp each
+            for (int bb = warp; bb < nb; bb += GB_THREADS / 32) {
+                if ((s0 + bb) % G != b) continue;
+                double sq = 0.0;
+                for (int d = lane; d < D; d += 32) {
+                    const double dl = s.xs[bb * D + d] - m.mu_0[d];
+                    sq += dl * dl * m.precision_0[d];
+                }
+                sq = warp_sum(sq);
+                if (lane == 0) p.seg_prior[s0 + bb] = c0 + 0.5 * m.sum_log_precision_0 - 0.5 * sq;
+            }
+            __syncthreads();
+        }
+        grid_barrier(p.bar, G, (it << 8) | 0x30);
+        // every CTA has taken its snapshot: the removed tokens can now be marked unassigned
+        // (not earlier: a slower CTA would read an already cleared token list)
+        if (b == G - 1) for (int j = tid; j < N; j += GB_THREADS) if (s.tok[j] >= 0 && s.tk[j] >= 0) m.assignments[s.tok[j]] = -1;
+        if (b == 0) for (int j = tid; j < N; j += GB_THREADS) c.tok_id[off + j] = -1;
+        // combine: CTA (slot % G) owns the slot; warp 0, lanes over CTAs
+        for (int slot = b; slot < n_slots; slot += G) {
+            if (warp == 0) {
+                const int id = c.seg_id[off * S + slot];
+                const double du = c.seg_dur[off * S + slot];
+                double out = neg_inf();
+                if (id >= 0 && du == du) {                       // uniform over the warp
+                    const int n_empty = KM - K;
+                    const double e = m.lms * (log_empty - log_norm) + __ldcg(p.seg_prior + slot);
+                    double gm = (n_empty > 0) ? e : neg_inf();
+                    for (int bb = lane; bb < G; bb += 32) gm = fmax(gm, __ldcg(p.part_m + (size_t)bb * p.M_cap + slot));
+                    gm = warp_max(gm);
+                    double t = 0.0;
+                    for (int bb = lane; bb < G; bb += 32) {
+                        const double pm = __ldcg(p.part_m + (size_t)bb * p.M_cap + slot);
+                        if (pm > neg_inf()) t += __ldcg(p.part_t + (size_t)bb * p.M_cap + slot) * exp(pm - gm);
+                    }
+                    t = warp_sum(t);
+                    if (n_empty > 0) t += n_empty * exp(e - gm);
+                    double val = log(t) + gm;
+                    val *= (p.tpt == 1.0) ? du : pow(du, p.tpt);
+                    out = val + p.wip;
+                }
+                if (lane == 0) p.scores[slot] = out;
+            }
+        }
+        grid_barrier(p.bar, G, (it << 8) | 0x40);
+
+        // ================= DP: every CTA runs it on the same scores (:653-864)
+        for (int i = tid; i < n_slots; i += GB_THREADS) s.sc[i] = __ldcg(p.scores + i);
+        __syncthreads();
+        double total = 0.0;
+        int dp_status = SEGB_DP_OK, used = 0;
+        if (warp == 0 && N > 0) {
+            DpParams dp;
+            dp.S = S; dp.n_min = c.n_slices_min; dp.n_max = c.n_slices_max; dp.mode = p.fb_mode;
+            dp.log_p_continue = 0.0; dp.anneal_temp = p.anneal_temp; dp.uniforms = p.uniforms;
+            dp_warp_body(dp, s.sc, s.bo, N, s.al, nullptr, u_pos, total, dp_status, used);
+            if (lane == 0) { s.red[36] = total; s.red[37] = (double)dp_status; s.red[38] = (double)used; }
+        }
+        __syncthreads();
+        if (N > 0) { total = s.red[36]; dp_status = (int)s.red[37]; used = (int)s.red[38]; }
+        u_pos += used;
+        if (b == 0) {
+            if (tid == 0) {
+                p.log_probs[it] = (dp_status == SEGB_DP_OK) ? total : CUDART_NAN;
+                p.status[it] = dp_status;
+            }
+            for (int j = tid; j < N; j += GB_THREADS) c.bounds[off + j] = s.bo[j];
+        }
+        __syncthreads();
+        if (dp_status != SEGB_DP_OK) continue;                   // uniform over the grid
+
+        // ================= assign the new tokens left to right (:339-349)
+        int j_prev = 0;
+        for (int j = 0; j < N; ++j) {
+            if (!s.bo[j]) continue;
+            const int t = j + 1, l = t - j_prev;
+            j_prev = j + 1;
+            const int slot = (t - 1) * S + (l - 1);
+            const int id = (l <= S) ? c.seg_id[off * S + slot] : -1;
+            if (b == 0 && tid == 0) c.tok_id[off + j] = id;
+            if (id < 0) continue;                                 // back-tracking leftovers are skipped (:340-342)
+            double *vbuf = p.v + (size_t)tok_parity * KM;
+            tok_parity ^= 1;
+            __syncthreads();
+            for (int d = tid; d < D; d += GB_THREADS) s.xs[d] = fv_x(m, id, d);
+            __syncthreads();
+            const int na = max(0, min(K, k_hi) - k_lo);
+            for (int kl = tid; kl < n_own; kl += GB_THREADS) {
+                double val;
+                if (kl < na) {
+                    const double acc = quad_form(s.mu + kl * D, s.pp + kl * D, s.xs, D);
+                    const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
+                    val = prior + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
+                } else {
+                    val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + __ldcg(p.seg_prior + slot);
+                }
+                vbuf[k_lo + kl] = val;
+            }
+            grid_barrier(p.bar, G, (it << 8) | 0x50 | (j << 16), (unsigned)(K | ((unsigned)n_total << 8) | ((unsigned)u_pos << 20)));
+            double mx = neg_inf();
+            for (int k = tid; k < KM; k += GB_THREADS) {
+                const double val = __ldcg(vbuf + k);
+                s.sk[k] = val;
+                mx = fmax(mx, val);
+            }
+            const double uu = (p.assign_mode == 0) ? p.uniforms[u_pos] : 0.0;
+            if (p.assign_mode == 0) u_pos += 1;
+            int k_sel = fv_decide(ds, K, KM, p.assign_mode, p.assign_temp, uu, mx);
+            // add_item (:153-170)
+            const bool fresh = (k_sel == K);
+            __syncthreads();
+            if (tid == 0) s.counts[k_sel] += 1;
+            if (fresh) K += 1;
+            n_total += 1;
+            if (k_sel >= k_lo && k_sel < k_hi) {
+                const int kl = k_sel - k_lo;
+                for (int d = tid; d < D; d += GB_THREADS) {
+                    double nu = s.num[kl * D + d], pNv = s.pN[kl * D + d];
+                    if (fresh) { nu = __dmul_rn(m.precision_0[d], m.mu_0[d]); pNv = m.precision_0[d]; }
+                    s.num[kl * D + d] = __dadd_rn(nu, __dmul_rn(m.precision[d], s.xs[d]));
+                    s.pN[kl * D + d] = __dadd_rn(pNv, m.precision[d]);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    m.assignments[id] = k_sel;
+                    s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_sel]);
+                }
+                refresh_and_publish(kl);
+            }
+            __syncthreads();
+        }
+    }
+    if (b == 0 && tid == 0) {
+        *m.K = K;
+        *m.n_total = n_total;
+        if (p.u_counter) *p.u_counter = u_pos;
+    }
+}
+
+static inline int gibbs_grid(int K_max, int n_sm) { return K_max < n_sm ? K_max : n_sm; }
+
+}  // namespace segb
+
+using namespace segb;
+
+extern "C" int64_t segb_gibbs_work_bytes(int32_t K_max, int32_t N_max, int32_t S) {
+    const int64_t M_cap = (int64_t)N_max * S, G = 160;
+    return 2048 + 8 * (2 * G * M_cap + 2 * M_cap + 2 * (int64_t)K_max) + 256;
+}
+
+extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb_corpus *c, const int32_t *d_order,
+                                              int32_t n_order, int32_t fb_mode, double time_power_term, double wip,
+                                              double anneal_temp, int32_t anneal_gibbs_am, const double *uniforms,
+                                              int64_t *u_counter, void *work, double *log_probs, int32_t *status,
+                                              void *stream) {
+    SEGB_CHECK_ARG(m && c && d_order && work && log_probs && status, "null pointer");
+    SEGB_CHECK_ARG(fb_mode == SEGB_DP_FFBS || fb_mode == SEGB_DP_VITERBI_GMM, "fb_mode");
+    SEGB_CHECK_ARG(fb_mode == SEGB_DP_VITERBI_GMM || (uniforms && u_counter), "FFBS needs uniforms");
+    SEGB_CHECK_ARG(c->tok_id && c->bounds, "corpus needs bounds and tok_id");
+    if (n_order == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    static int n_sm = 0, coop = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        SEGB_CUDA(cudaGetDevice(&dev));
+        SEGB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (!coop || n_sm > 160) { set_error("cooperative launch unavailable"); return SEGB_E_UNSUPPORTED; }
+    GibbsParams p;
+    p.m = *m; p.c = *c; p.order = d_order; p.n_order = n_order; p.fb_mode = fb_mode;
+    p.assign_mode = (fb_mode == SEGB_DP_FFBS) ? 0 : 1;
+    p.tpt = time_power_term; p.wip = wip; p.anneal_temp = anneal_temp;
+    p.assign_temp = anneal_gibbs_am ? anneal_temp : 1.0;
+    p.uniforms = uniforms; p.u_counter = u_counter; p.log_probs = log_probs; p.status = status;
+    const int G = gibbs_grid(m->K_max, n_sm);
+    p.per = (m->K_max + G - 1) / G;
+    p.M_cap = c->N_max * c->S;
+    p.xb = (p.per > 12) ? 8 : 16;
+    const size_t smem = gibbs_smem_bytes(m->D, m->K_max, p.per, p.xb, p.M_cap, c->N_max);
+    if (smem > 227 * 1024) { set_error("model too large for the persistent Gibbs sweep (%zu bytes of shared memory)", smem); return SEGB_E_UNSUPPORTED; }
+    unsigned char *w = (unsigned char *)work;
+    p.bar = (unsigned *)w; w += 2048;                 // count, generation, pad, per-CTA trace tags
+    p.part_m = (double *)w; w += 8 * (size_t)G * p.M_cap;
+    p.part_t = (double *)w; w += 8 * (size_t)G * p.M_cap;
+    p.seg_prior = (double *)w; w += 8 * (size_t)p.M_cap;
+    p.scores = (double *)w; w += 8 * (size_t)p.M_cap;
+    p.v = (double *)w;
+    SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
+    SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {&p};
+    SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel, dim3(G), dim3(GB_THREADS), args, smem, st));
+    count_launch();
+    return 0;
+}

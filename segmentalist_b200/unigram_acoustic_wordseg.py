@@ -15,6 +15,7 @@ reference.
 """
 import logging
 import math
+import os
 import random
 import time
 
@@ -159,11 +160,27 @@ class UnigramAcousticWordseg(object):
         log_probs = torch.zeros(n, dtype=torch.float64, device="cuda")
         status = torch.zeros(n, dtype=torch.int32, device="cuda")
         assert self.calc_p_continue() == 1.0
-        _lib.check(_lib.lib().segb_gibbs_sweep_fixedvar(
-            am.components.struct(), corpus.struct(), order_h.ctypes.data, n,
-            _lib.DP_FFBS if ffbs else _lib.DP_VITERBI_GMM, float(self.time_power_term), float(self.wip),
-            float(anneal_temp), int(bool(anneal_gibbs_am)), _lib.ptr(feed.dev), _lib.ptr(feed.counter),
-            _lib.ptr(self._scratch), _lib.ptr(log_probs), _lib.ptr(status), _lib.stream_ptr()))
+        lib, comps = _lib.lib(), am.components
+        mode = _lib.DP_FFBS if ffbs else _lib.DP_VITERBI_GMM
+        rc = _lib.E_UNSUPPORTED
+        if os.environ.get("SEGB_GIBBS", "coop") != "steps":
+            # one cooperative launch for the whole sweep (components sharded over the SMs)
+            if getattr(self, "_gibbs_work", None) is None:
+                self._gibbs_work = torch.empty(lib.segb_gibbs_work_bytes(comps.K_max, corpus.N_max, corpus.S),
+                                               dtype=torch.uint8, device="cuda")
+            rc = lib.segb_gibbs_sweep_fixedvar_coop(
+                comps.struct(), corpus.struct(), _lib.ptr(_lib.dev(order_h)), n, mode, float(self.time_power_term),
+                float(self.wip), float(anneal_temp), int(bool(anneal_gibbs_am)), _lib.ptr(feed.dev),
+                _lib.ptr(feed.counter), _lib.ptr(self._gibbs_work), _lib.ptr(log_probs), _lib.ptr(status),
+                _lib.stream_ptr())
+        if rc == _lib.E_UNSUPPORTED:
+            # model too large for per-CTA shared memory: four launches per utterance
+            rc = lib.segb_gibbs_sweep_fixedvar(
+                comps.struct(), corpus.struct(), order_h.ctypes.data, n, mode, float(self.time_power_term),
+                float(self.wip), float(anneal_temp), int(bool(anneal_gibbs_am)), _lib.ptr(feed.dev),
+                _lib.ptr(feed.counter), _lib.ptr(self._scratch), _lib.ptr(log_probs), _lib.ptr(status),
+                _lib.stream_ptr())
+        _lib.check(rc)
         st = status.cpu().numpy()
         feed.finish()
         self.utterances.boundaries[:, :] = corpus.boundaries_matrix()
