@@ -150,4 +150,41 @@ __device__ T pairwise_sum(F f, int n) {
     return ret;
 }
 
+// The same pairwise sum (n <= 256 terms) computed by 16 consecutive lanes: NumPy's block sum
+// keeps 8 running accumulators per block of <= 128 terms, so lane q of an 8-lane group owns
+// accumulator q, the xor-butterfly (1, 2, 4) reproduces ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) on the
+// group's first lane, which then adds the n % 8 leftovers one by one; the second 8-lane group
+// takes the second block when n > 128.  Bit-identical to pairwise_sum<T>(f, n).  `hmask` = the
+// 16 participating lanes of the warp, `j` = lane index within them; result on all 16 lanes.
+template <typename T, typename F>
+__device__ __forceinline__ T pairwise_sum_lanes16(F f, int n, unsigned hmask, int j) {
+    const int g = j >> 3, q = j & 7;
+    const int hbase = (threadIdx.x & 31) & 16;
+    int n2 = 0;
+    if (n > 128) { n2 = n / 2; n2 -= n2 % 8; }
+    const int lo = g == 0 ? 0 : n2;
+    const int ng = (n > 128) ? (g == 0 ? n2 : n - n2) : (g == 0 ? n : 0);
+    T res = T(0);
+    if (ng >= 8) {
+        const int n8 = ng - (ng % 8);
+        T acc = f(lo + q);
+        for (int i = 8; i < n8; i += 8) acc = add_rn<T>(acc, f(lo + i + q));
+        acc = add_rn<T>(acc, __shfl_xor_sync(hmask, acc, 1));
+        acc = add_rn<T>(acc, __shfl_xor_sync(hmask, acc, 2));
+        acc = add_rn<T>(acc, __shfl_xor_sync(hmask, acc, 4));
+        res = acc;
+        for (int i = n8; i < ng; ++i) res = add_rn<T>(res, f(lo + i));
+    } else {
+        // keep the shuffles convergent for the whole half-warp
+        T acc = T(0);
+        acc = add_rn<T>(acc, __shfl_xor_sync(hmask, acc, 1));
+        acc = add_rn<T>(acc, __shfl_xor_sync(hmask, acc, 2));
+        acc = add_rn<T>(acc, __shfl_xor_sync(hmask, acc, 4));
+        for (int i = 0; i < ng; ++i) res = add_rn<T>(res, f(lo + i));
+    }
+    T tot = __shfl_sync(hmask, res, hbase);
+    if (n > 128) tot = add_rn<T>(tot, __shfl_sync(hmask, res, hbase + 8));
+    return tot;
+}
+
 }  // namespace segb

@@ -177,11 +177,14 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             m.mu_N_numT[o] = s.num[kl * D + d]; m.prec_NT[o] = pNv; m.prec_predT[o] = ppv; m.mu_NT[o] = muv;
         }
         __syncthreads();
-        if (tid == 0) {
-            const double l = pairwise_sum<double>([&](int i) { return s.tmp[i]; }, D);
-            s.lpp[kl] = l;
-            m.log_prod_prec_pred[k] = l;
-            m.counts[k] = s.counts[k];
+        if (tid < 16) {
+            const double l = (D <= 256) ? pairwise_sum_lanes16<double>([&](int i) { return s.tmp[i]; }, D, 0xffffu, tid)
+                                        : pairwise_sum<double>([&](int i) { return s.tmp[i]; }, D);
+            if (tid == 0) {
+                s.lpp[kl] = l;
+                m.log_prod_prec_pred[k] = l;
+                m.counts[k] = s.counts[k];
+            }
         }
         __syncthreads();
     };
@@ -394,16 +397,27 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             for (int d = tid; d < D; d += GB_THREADS) s.xs[d] = fv_x(m, id, d);
             __syncthreads();
             const int na = max(0, min(K, k_hi) - k_lo);
-            for (int kl = tid; kl < n_own; kl += GB_THREADS) {
-                double val;
-                if (kl < na) {
-                    const double acc = quad_form(s.mu + kl * D, s.pp + kl * D, s.xs, D);
-                    const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
-                    val = prior + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
-                } else {
-                    val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + __ldcg(p.seg_prior + slot);
+            {
+                // one half-warp per owned slot (the predictive sum is 130 dependent-latency terms)
+                const int hw = tid >> 4, jl = tid & 15;
+                const unsigned hmask = 0xffffu << (lane & 16);
+                for (int kl = hw; kl < n_own; kl += GB_THREADS / 16) {
+                    double val;
+                    if (kl < na) {
+                        const double *mu = s.mu + kl * D, *pp = s.pp + kl * D;
+                        auto term = [&](int d) {
+                            const double dl = __dsub_rn(mu[d], s.xs[d]);
+                            return __dmul_rn(__dmul_rn(dl, dl), pp[d]);
+                        };
+                        const double acc = (D <= 256) ? pairwise_sum_lanes16<double>(term, D, hmask, jl)
+                                                      : pairwise_sum<double>(term, D);
+                        const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
+                        val = prior + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
+                    } else {
+                        val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + __ldcg(p.seg_prior + slot);
+                    }
+                    if (jl == 0) vbuf[k_lo + kl] = val;
                 }
-                vbuf[k_lo + kl] = val;
             }
             grid_barrier(p.bar, G, (it << 8) | 0x50 | (j << 16), (unsigned)(K | ((unsigned)n_total << 8) | ((unsigned)u_pos << 20)));
             double mx = neg_inf();
@@ -485,7 +499,7 @@ extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb
     const int G = gibbs_grid(m->K_max, n_sm);
     p.per = (m->K_max + G - 1) / G;
     p.M_cap = c->N_max * c->S;
-    p.xb = (p.per > 12) ? 8 : 16;
+    p.xb = (p.per > 12) ? 8 : 32;
     const size_t smem = gibbs_smem_bytes(m->D, m->K_max, p.per, p.xb, p.M_cap, c->N_max);
     if (smem > 227 * 1024) { set_error("model too large for the persistent Gibbs sweep (%zu bytes of shared memory)", smem); return SEGB_E_UNSUPPORTED; }
     unsigned char *w = (unsigned char *)work;
