@@ -313,6 +313,16 @@ def run_gibbs_extra(args):
            "device_ms_per_sweep": dev_s * 1e3, "candidate_segments": n_seg,
            "segment_component_evals_per_s": n_seg * K / max(wall, dev_s),
            "K_active": seg.acoustic_model.components.K, "setup_s": setup_s, "dtype": "f64"}
+    # whole-model resampling between sweeps (FBGMM.gibbs_sample, consider_unassigned=False): one
+    # cooperative launch over all assigned tokens
+    n_tok = seg.acoustic_model.get_n_assigned()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    seg.acoustic_model.gibbs_sample(1, consider_unassigned=False)
+    torch.cuda.synchronize()
+    am_s = time.perf_counter() - t0
+    out["am_gibbs_sample"] = {"tokens": int(n_tok), "ms": am_s * 1e3, "tokens_per_s": n_tok / am_s,
+                              "note": "includes the host-side record (log_marg) of the reference API"}
     if not args.no_cpu:
         # CPU oracle: same construction + seeds, a bounded number of gibbs_sample_i calls
         n_cpu = 24

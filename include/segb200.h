@@ -162,6 +162,16 @@ int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb_corpus *c,
                                    const double *uniforms, int64_t *u_counter, void *work,
                                    double *log_probs, int32_t *status, void *stream);
 
+/* FBGMM.gibbs_sample inner loop (fbgmm.py:357-400) over the items listed in d_items (DEVICE
+ * array, in order): cache the item's component, del_item, draw a component from
+ * lms*log(alpha/K_max + n_k) + log_post_pred / log_prior (one uniform per item, from
+ * uniforms[*u_counter ...]), then add_item -- or restore the cached statistics when the item
+ * returns to its component and no component died.  Same cooperative kernel and `work` buffer
+ * (segb_gibbs_work_bytes(K_max, 1, 1) bytes suffice) as segb_gibbs_sweep_fixedvar_coop.        */
+int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t *d_items, int32_t n_items,
+                                double anneal_temp, const double *uniforms, int64_t *u_counter,
+                                void *work, void *stream);
+
 /* ------------------------------------------------------------------ k-means (A10-A12) */
 
 /* Device view of KMeansComponents (kmeans_components.py:18-91). `means` has X's

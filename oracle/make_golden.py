@@ -381,7 +381,71 @@ def golden_kmeans_wordseg(ref_km):
     np.savez_compressed(os.path.join(OUT, "kmeans_wordseg.npz"), **d)
 
 
+def golden_fbgmm_gibbs(ref_fbgmm, ref_fv, ref_uni):
+    """FBGMM.gibbs_sample (fbgmm.py:288-420) on fixed-variance components -- the in-between
+    acoustic-model resampling of UnigramAcousticWordseg.gibbs_sample(am_n_iter > 0)
+    (unigram_acoustic_wordseg.py:440-443) -- with the uniform stream recorded; and one segmenter
+    run that interleaves it with the segmentation sweeps."""
+    from segmentalist_b200 import synth
+    D = 16
+    for tag, n_iter, consider_unassigned, kw in (
+            ("plain", 3, False, {}),
+            ("all_anneal", 2, True, {"anneal_schedule": "linear", "anneal_start_temp_inv": 0.4})):
+        rng = np.random.RandomState(11)
+        centres = synth.cluster_centres(6, D, rng)
+        n = 220
+        X = synth._unit_rows(centres[rng.randint(0, 6, n)] + 0.1 * rng.standard_normal((n, D)).astype(np.float32))
+        assign = rng.randint(0, 9, n)
+        assign[rng.rand(n) < 0.3] = -1                                  # unassigned candidate segments
+        random.seed(4)
+        np.random.seed(4)
+        prior = ref_fv.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+        am = ref_fbgmm.FBGMM(X, prior, 5., 12, assign.copy(), covariance_type="fixed", lms=0.8)
+        d = {"X": X, "init_assignments": am.components.assignments.copy(), "K_max": np.array(12),
+             "alpha": np.array(5.), "lms": np.array(0.8), "consider_unassigned": np.array(consider_unassigned)}
+        with Tap() as tap:
+            rec = am.gibbs_sample(n_iter, consider_unassigned=consider_unassigned, **kw)
+        c = am.components
+        d["uniforms"] = np.array(tap.uniforms)
+        d["anneal_temp"] = np.array(rec["anneal_temp"], dtype=np.float64)
+        for key in ("log_marg", "log_prob_z", "log_prob_X_given_z", "components"):
+            d["rec_" + key] = np.array(rec[key], dtype=np.float64)
+        d["assignments"] = c.assignments.copy()
+        d["counts"] = c.counts.copy()
+        d["K"] = np.array(c.K)
+        d["mu_N_numerators"] = c.mu_N_numerators.copy()
+        d["precision_Ns"] = c.precision_Ns.copy()
+        d["log_prod_precision_preds"] = c.log_prod_precision_preds.copy()
+        np.savez_compressed(os.path.join(OUT, "fbgmm_gibbs_%s.npz" % tag), **d)
+        print("fbgmm_gibbs", tag, "log_marg", rec["log_marg"], "K", c.K, "uniforms", len(tap.uniforms))
+    # segmenter with in-between acoustic-model resampling
+    mats, vids, durs, lms = synth.make_corpus_dicts(12, D=D, K_true=5, n_min=3, n_max=8, n_slices_max=4, noise=0.08, seed=33)
+    random.seed(6)
+    np.random.seed(6)
+    prior = ref_fv.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+    seg = ref_uni.UnigramAcousticWordseg(
+        ref_fbgmm.FBGMM, 10., 9, prior, mats, vids, durs, lms, p_boundary_init=0.5,
+        beta_sent_boundary=-1, n_slices_max=4, lms=1.0, wip=0.0, fb_type="standard")
+    ref_uni.i_debug_monitor = -1
+    d = pack_dicts("in_", mats, vids, durs, lms)
+    with Tap() as tap:
+        rec = seg.gibbs_sample(2, am_n_iter=2)
+    c = seg.acoustic_model.components
+    d["uniforms"] = np.array(tap.uniforms)
+    d["orders"] = np.array(tap.orders)
+    for key in ("log_marg", "log_marg*length", "log_prob_z", "log_prob_X_given_z", "components", "n_tokens"):
+        d["rec_" + key] = np.array(rec[key], dtype=np.float64)
+    d["boundaries"] = seg.utterances.boundaries.copy()
+    d["assignments"] = c.assignments.copy()
+    d["counts"] = c.counts.copy()
+    d["K"] = np.array(c.K)
+    np.savez_compressed(os.path.join(OUT, "unigram_am_iter.npz"), **d)
+    print("unigram_am_iter log_marg", rec["log_marg"], "K", c.K, "uniforms", len(tap.uniforms))
+
+
 def main():
+    only = set(sys.argv[1:])                 # e.g. `make_golden.py fbgmm_gibbs` regenerates one family
+    run = lambda name: (not only) or (name in only)
     os.makedirs(OUT, exist_ok=True)
     tmp = build_shimmed_reference()
     try:
@@ -397,11 +461,18 @@ def main():
                              "segmentalist/tests/test_gaussian_components_fixedvar.py",
                              "segmentalist/tests/test_kmeans_components.py"], cwd=tmp)
         assert r == 0, "shimmed reference fails its own tests"
-        golden_dp(ref_uni, ref_km)
-        golden_fixedvar(ref_fv, ref_fbgmm)
-        golden_kmeans_scoring(ref_kc, ref_kmeans)
-        golden_unigram(ref_uni, ref_fbgmm, ref_fv)
-        golden_kmeans_wordseg(ref_km)
+        if run("dp"):
+            golden_dp(ref_uni, ref_km)
+        if run("fixedvar"):
+            golden_fixedvar(ref_fv, ref_fbgmm)
+        if run("kmeans_scoring"):
+            golden_kmeans_scoring(ref_kc, ref_kmeans)
+        if run("unigram"):
+            golden_unigram(ref_uni, ref_fbgmm, ref_fv)
+        if run("kmeans_wordseg"):
+            golden_kmeans_wordseg(ref_km)
+        if run("fbgmm_gibbs"):
+            golden_fbgmm_gibbs(ref_fbgmm, ref_fv, ref_uni)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -61,6 +61,8 @@ _PROTOS = {
     "segb_gibbs_sweep_fixedvar_coop": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(Corpus), c_vp, c_i32,
                                                       c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                       c_vp, c_vp]),
+    "segb_fbgmm_gibbs_items_coop": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_i32, c_f64, c_vp, c_vp, c_vp,
+                                                   c_vp]),
     "segb_kmeans_neg_sqrd_norm_row": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_i32, c_vp, c_vp]),
     "segb_kmeans_best": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_i64, c_vp, c_vp, c_vp]),
     "segb_kmeans_add_items": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_i32, c_vp]),

@@ -26,6 +26,7 @@
 // Global tables (the host-visible model) are written through on every update; everything another
 // CTA may have written during the launch is read with ld.global.cg (L1 is not coherent across SMs).
 // All arithmetic is float64; predictive sums use NumPy's pairwise order with separately rounded operations.
+#include <string.h>
 #include "dp_warp.cuh"
 #include "fixedvar_common.cuh"
 
@@ -38,6 +39,7 @@ struct GibbsParams {
     segb_corpus c;
     const int32_t *order;          // device
     int32_t n_order, fb_mode, assign_mode, per, M_cap, xb;   // xb = candidate rows staged per batch
+    int32_t item_mode;             // 1: `order` lists ITEMS (FBGMM.gibbs_sample), 0: utterances
     double tpt, wip, anneal_temp, assign_temp;
     const double *uniforms;
     int64_t *u_counter;
@@ -94,6 +96,7 @@ struct GibbsSmem {
     double *sc;                    // [M_cap] scores of the utterance
     double *al;                    // [N_cap + 1]
     double *tmp;                   // [D]
+    double *bk;                    // [3 D + 1] cached statistics of one component (whole-model sweeps)
     int32_t *counts;               // [K_max] replicated
     int32_t *tok;                  // [N_cap] ids of the tokens being removed
     int32_t *tk;                   // [N_cap] their components (snapshot taken before anything is modified)
@@ -101,7 +104,7 @@ struct GibbsSmem {
 };
 
 __host__ __device__ inline size_t gibbs_smem_bytes(int D, int K_max, int per, int xb, int M_cap, int N_cap) {
-    size_t d = (size_t)4 * per * D + 2 * per + (size_t)xb * D + (size_t)xb * per + 40 + K_max + M_cap + (N_cap + 1) + D;
+    size_t d = (size_t)4 * per * D + 2 * per + (size_t)xb * D + (size_t)xb * per + 40 + K_max + M_cap + (N_cap + 1) + D + (3 * D + 1);
     return d * 8 + (size_t)K_max * 4 + (size_t)N_cap * 8 + ((N_cap + 15) / 16) * 16 + 64;
 }
 
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         s.sc = q; q += p.M_cap;
         s.al = q; q += c.N_max + 1;
         s.tmp = q; q += D;
+        s.bk = q; q += 3 * D + 1;
         s.counts = reinterpret_cast<int32_t *>(q);
         s.tok = s.counts + KM;
         s.tk = s.tok + c.N_max;
@@ -199,6 +203,197 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         __syncthreads();
     };
 
+    // del_item (:172-188) of item `id`, currently in component k.  The replicated state (counts, K,
+    // n_total) advances on every CTA; only the owner touches statistics.  Entries j_next.. of the
+    // pending removal list s.tk[0..n_list) are relabelled if a component moves.
+    auto remove_one = [&](int id, int k, unsigned tag, int j_next, int n_list, bool scan_all) {
+        __syncthreads();
+        const int cnt = s.counts[k] - 1;
+        __syncthreads();
+        if (tid == 0) s.counts[k] = cnt;
+        n_total -= 1;
+        const bool own = (k >= k_lo && k < k_hi);
+        if (cnt > 0) {
+            if (own) {
+                const int kl = k - k_lo;
+                for (int d = tid; d < D; d += GB_THREADS) {
+                    const double pr = m.precision[d];
+                    s.num[kl * D + d] = __dsub_rn(s.num[kl * D + d], __dmul_rn(pr, fv_x(m, id, d)));
+                    s.pN[kl * D + d] = __dsub_rn(s.pN[kl * D + d], pr);
+                }
+                __syncthreads();
+                refresh_and_publish(kl);
+            }
+        } else {
+            // del_component (:190-221): the last component moves into slot k
+            const int last = K - 1;
+            grid_barrier(p.bar, G, tag | 0x10);   // every owner's write-through is visible
+            if (k != last) {
+                if (own) {
+                    const int kl = k - k_lo;
+                    for (int d = tid; d < D; d += GB_THREADS) {
+                        const size_t a = (size_t)d * KM + k, o = (size_t)d * KM + last;
+                        const double nu = __ldcg(m.mu_N_numT + o), pNv = __ldcg(m.prec_NT + o), ppv = __ldcg(m.prec_predT + o),
+                                     muv = __ldcg(m.mu_NT + o);
+                        s.num[kl * D + d] = nu; s.pN[kl * D + d] = pNv; s.pp[kl * D + d] = ppv; s.mu[kl * D + d] = muv;
+                        m.mu_N_numT[a] = nu; m.prec_NT[a] = pNv; m.prec_predT[a] = ppv; m.mu_NT[a] = muv;
+                        m.mu_N_numT[o] = 0.; m.prec_NT[o] = 0.; m.prec_predT[o] = 0.; m.mu_NT[o] = 0.;
+                    }
+                    if (tid == 0) {
+                        const double l = __ldcg(m.log_prod_prec_pred + last);
+                        s.lpp[kl] = l;
+                        m.log_prod_prec_pred[k] = l; m.log_prod_prec_pred[last] = 0.;
+                        m.counts[k] = s.counts[last]; m.counts[last] = 0;
+                    }
+                }
+                if (last >= k_lo && last < k_hi) {           // the old home forgets it (global zeroed by the new owner)
+                    const int kl = last - k_lo;
+                    for (int d = tid; d < D; d += GB_THREADS) {
+                        s.mu[kl * D + d] = 0.; s.pp[kl * D + d] = 0.; s.num[kl * D + d] = 0.; s.pN[kl * D + d] = 0.;
+                    }
+                    if (tid == 0) s.lpp[kl] = 0.;
+                }
+                // relabel the moved component's members, split over the grid: the live tokens of the
+                // corpus (segmenter sweeps) or every item (whole-model sweeps, as the reference does, :202)
+                if (scan_all) {
+                    for (int64_t i = (int64_t)b * GB_THREADS + tid; i < m.n_emb; i += (int64_t)G * GB_THREADS)
+                        if (__ldcg(m.assignments + i) == last) m.assignments[i] = k;
+                } else {
+                    for (int64_t i = (int64_t)b * GB_THREADS + tid; i < c.n_pos; i += (int64_t)G * GB_THREADS) {
+                        const int t_id = __ldcg(c.tok_id + i);
+                        if (t_id >= 0 && __ldcg(m.assignments + t_id) == last) m.assignments[t_id] = k;
+                    }
+                }
+                for (int jj = j_next + tid; jj < n_list; jj += GB_THREADS) if (s.tk[jj] == last) s.tk[jj] = k;
+                __syncthreads();
+                if (tid == 0) { s.counts[k] = s.counts[last]; s.counts[last] = 0; }
+            } else if (own) {
+                zero_slot(k - k_lo);
+            }
+            K = last;
+            grid_barrier(p.bar, G, tag | 0x20);   // relabelled assignments are visible
+        }
+        __syncthreads();
+    };
+
+    // One assignment step (gibbs_sample_inside_loop_i / map_assign_i, fbgmm.py:422-494) for item `id`
+    // whose embedding is staged in s.xs[0..D): owners publish their slots' log-probabilities, grid
+    // barrier, every CTA takes the same decision, the owner of the chosen slot updates.
+    // x_prior = log_prior(x); k_restore = slot whose cached statistics (s.bk) are put back when it is
+    // chosen again, or -1.
+    auto assign_one = [&](int id, double x_prior, unsigned tag, int k_restore) -> int {
+    double *vbuf = p.v + (size_t)tok_parity * KM;
+    tok_parity ^= 1;
+    const int na = max(0, min(K, k_hi) - k_lo);
+    {
+        // one half-warp per owned slot (the predictive sum is 130 dependent-latency terms)
+        const int hw = tid >> 4, jl = tid & 15;
+        const unsigned hmask = 0xffffu << (lane & 16);
+        for (int kl = hw; kl < n_own; kl += GB_THREADS / 16) {
+            double val;
+            if (kl < na) {
+                const double *mu = s.mu + kl * D, *pp = s.pp + kl * D;
+                auto term = [&](int d) {
+                    const double dl = __dsub_rn(mu[d], s.xs[d]);
+                    return __dmul_rn(__dmul_rn(dl, dl), pp[d]);
+                };
+                const double acc = (D <= 256) ? pairwise_sum_lanes16<double>(term, D, hmask, jl)
+                                              : pairwise_sum<double>(term, D);
+                const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
+                val = prior + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
+            } else {
+                val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + x_prior;
+            }
+            if (jl == 0) vbuf[k_lo + kl] = val;
+        }
+    }
+    grid_barrier(p.bar, G, tag | 0x50, (unsigned)(K | ((unsigned)n_total << 8) | ((unsigned)u_pos << 20)));
+    double mx = neg_inf();
+    for (int k = tid; k < KM; k += GB_THREADS) {
+        const double val = __ldcg(vbuf + k);
+        s.sk[k] = val;
+        mx = fmax(mx, val);
+    }
+    const double uu = (p.assign_mode == 0) ? p.uniforms[u_pos] : 0.0;
+    if (p.assign_mode == 0) u_pos += 1;
+    int k_sel = fv_decide(ds, K, KM, p.assign_mode, p.assign_temp, uu, mx);
+    // add_item (:153-170) -- or, in whole-model sweeps, put the cached statistics back when the
+    // item returns to its old component and no component died in between (fbgmm.py:397-400)
+    const bool fresh = (k_sel == K);
+    const bool restore = (k_sel == k_restore);
+    __syncthreads();
+    if (tid == 0) s.counts[k_sel] += 1;
+    if (fresh) K += 1;
+    n_total += 1;
+    if (k_sel >= k_lo && k_sel < k_hi) {
+        const int kl = k_sel - k_lo;
+        for (int d = tid; d < D; d += GB_THREADS) {
+            if (restore) { s.num[kl * D + d] = s.bk[d]; s.pN[kl * D + d] = s.bk[D + d]; continue; }
+            double nu = s.num[kl * D + d], pNv = s.pN[kl * D + d];
+            if (fresh) { nu = __dmul_rn(m.precision_0[d], m.mu_0[d]); pNv = m.precision_0[d]; }
+            s.num[kl * D + d] = __dadd_rn(nu, __dmul_rn(m.precision[d], s.xs[d]));
+            s.pN[kl * D + d] = __dadd_rn(pNv, m.precision[d]);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            m.assignments[id] = k_sel;
+            s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_sel]);
+        }
+        refresh_and_publish(kl);
+        if (restore) {       // cached precision_pred / log_prod_precision_pred go back bit for bit
+            for (int d = tid; d < D; d += GB_THREADS) {
+                s.pp[kl * D + d] = s.bk[2 * D + d];
+                m.prec_predT[(size_t)d * KM + k_sel] = s.bk[2 * D + d];
+            }
+            if (tid == 0) { s.lpp[kl] = s.bk[3 * D]; m.log_prod_prec_pred[k_sel] = s.bk[3 * D]; }
+        }
+    }
+    __syncthreads();
+    return k_sel;
+    };
+
+    // ================= whole-model sweep: FBGMM.gibbs_sample over a list of items (fbgmm.py:357-400)
+    if (p.item_mode) {
+        for (int it = 0; it < p.n_order; ++it) {
+            const int id = p.order[it];
+            const int k_old = __ldcg(m.assignments + id);            // uniform over the grid
+            const int K_old = K;
+            __syncthreads();
+            if (k_old >= 0) {
+                if (k_old >= k_lo && k_old < k_hi) {                    // cache_component_stats (:128-141)
+                    const int kl = k_old - k_lo;
+                    for (int d = tid; d < D; d += GB_THREADS) {
+                        s.bk[d] = s.num[kl * D + d]; s.bk[D + d] = s.pN[kl * D + d]; s.bk[2 * D + d] = s.pp[kl * D + d];
+                    }
+                    if (tid == 0) s.bk[3 * D] = s.lpp[kl];
+                }
+                __syncthreads();
+                remove_one(id, k_old, (unsigned)it << 8, 0, 0, true);
+            }
+            for (int d = tid; d < D; d += GB_THREADS) s.xs[d] = fv_x(m, id, d);
+            __syncthreads();
+            if (warp == 0) {                                            // log_prior(x) (:224-231), same bits on every CTA
+                double sq = 0.0;
+                for (int d = lane; d < D; d += 32) {
+                    const double dl = s.xs[d] - m.mu_0[d];
+                    sq += dl * dl * m.precision_0[d];
+                }
+                sq = warp_sum(sq);
+                if (lane == 0) s.red[39] = c0 + 0.5 * m.sum_log_precision_0 - 0.5 * sq;
+            }
+            for (int kl = tid; kl < n_own; kl += GB_THREADS) s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_lo + kl]);
+            __syncthreads();
+            const double x_prior = s.red[39];
+            assign_one(id, x_prior, (unsigned)it << 8, (k_old >= 0 && K == K_old) ? k_old : -1);
+        }
+        if (b == 0 && tid == 0) {
+            *m.K = K;
+            *m.n_total = n_total;
+            if (p.u_counter) *p.u_counter = u_pos;
+        }
+        return;
+    }
+
     for (int it = 0; it < p.n_order; ++it) {
         const int u = p.order[it];
         const int64_t off = c.pos_off[u];
@@ -220,67 +415,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             const int id = s.tok[j];
             const int k = s.tk[j];
             if (id < 0 || k < 0) continue;
-            __syncthreads();
-            const int cnt = s.counts[k] - 1;
-            __syncthreads();
-            if (tid == 0) s.counts[k] = cnt;
-            n_total -= 1;
-            const bool own = (k >= k_lo && k < k_hi);
-            if (cnt > 0) {
-                if (own) {
-                    const int kl = k - k_lo;
-                    for (int d = tid; d < D; d += GB_THREADS) {
-                        const double pr = m.precision[d];
-                        s.num[kl * D + d] = __dsub_rn(s.num[kl * D + d], __dmul_rn(pr, fv_x(m, id, d)));
-                        s.pN[kl * D + d] = __dsub_rn(s.pN[kl * D + d], pr);
-                    }
-                    __syncthreads();
-                    refresh_and_publish(kl);
-                }
-            } else {
-                // del_component (:190-221): the last component moves into slot k
-                const int last = K - 1;
-                grid_barrier(p.bar, G, (it << 8) | 0x10 | (j << 16));   // every owner's write-through is visible
-                if (k != last) {
-                    if (own) {
-                        const int kl = k - k_lo;
-                        for (int d = tid; d < D; d += GB_THREADS) {
-                            const size_t a = (size_t)d * KM + k, o = (size_t)d * KM + last;
-                            const double nu = __ldcg(m.mu_N_numT + o), pNv = __ldcg(m.prec_NT + o), ppv = __ldcg(m.prec_predT + o),
-                                         muv = __ldcg(m.mu_NT + o);
-                            s.num[kl * D + d] = nu; s.pN[kl * D + d] = pNv; s.pp[kl * D + d] = ppv; s.mu[kl * D + d] = muv;
-                            m.mu_N_numT[a] = nu; m.prec_NT[a] = pNv; m.prec_predT[a] = ppv; m.mu_NT[a] = muv;
-                            m.mu_N_numT[o] = 0.; m.prec_NT[o] = 0.; m.prec_predT[o] = 0.; m.mu_NT[o] = 0.;
-                        }
-                        if (tid == 0) {
-                            const double l = __ldcg(m.log_prod_prec_pred + last);
-                            s.lpp[kl] = l;
-                            m.log_prod_prec_pred[k] = l; m.log_prod_prec_pred[last] = 0.;
-                            m.counts[k] = s.counts[last]; m.counts[last] = 0;
-                        }
-                    }
-                    if (last >= k_lo && last < k_hi) {           // the old home forgets it (global zeroed by the new owner)
-                        const int kl = last - k_lo;
-                        for (int d = tid; d < D; d += GB_THREADS) {
-                            s.mu[kl * D + d] = 0.; s.pp[kl * D + d] = 0.; s.num[kl * D + d] = 0.; s.pN[kl * D + d] = 0.;
-                        }
-                        if (tid == 0) s.lpp[kl] = 0.;
-                    }
-                    // relabel the moved component's members: live tokens of the corpus, split over the grid
-                    for (int64_t i = (int64_t)b * GB_THREADS + tid; i < c.n_pos; i += (int64_t)G * GB_THREADS) {
-                        const int t_id = __ldcg(c.tok_id + i);
-                        if (t_id >= 0 && __ldcg(m.assignments + t_id) == last) m.assignments[t_id] = k;
-                    }
-                    for (int jj = j + 1 + tid; jj < N; jj += GB_THREADS) if (s.tk[jj] == last) s.tk[jj] = k;
-                    __syncthreads();
-                    if (tid == 0) { s.counts[k] = s.counts[last]; s.counts[last] = 0; }
-                } else if (own) {
-                    zero_slot(k - k_lo);
-                }
-                K = last;
-                grid_barrier(p.bar, G, (it << 8) | 0x20 | (j << 16));   // relabelled assignments are visible
-            }
-            __syncthreads();
+            remove_one(id, k, (it << 8) | (j << 16), j + 1, N, false);
         }
 
         // ================= score every candidate segment (:474-511, fbgmm.py:256-285)
@@ -391,66 +526,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             const int id = (l <= S) ? c.seg_id[off * S + slot] : -1;
             if (b == 0 && tid == 0) c.tok_id[off + j] = id;
             if (id < 0) continue;                                 // back-tracking leftovers are skipped (:340-342)
-            double *vbuf = p.v + (size_t)tok_parity * KM;
-            tok_parity ^= 1;
             __syncthreads();
             for (int d = tid; d < D; d += GB_THREADS) s.xs[d] = fv_x(m, id, d);
             __syncthreads();
-            const int na = max(0, min(K, k_hi) - k_lo);
-            {
-                // one half-warp per owned slot (the predictive sum is 130 dependent-latency terms)
-                const int hw = tid >> 4, jl = tid & 15;
-                const unsigned hmask = 0xffffu << (lane & 16);
-                for (int kl = hw; kl < n_own; kl += GB_THREADS / 16) {
-                    double val;
-                    if (kl < na) {
-                        const double *mu = s.mu + kl * D, *pp = s.pp + kl * D;
-                        auto term = [&](int d) {
-                            const double dl = __dsub_rn(mu[d], s.xs[d]);
-                            return __dmul_rn(__dmul_rn(dl, dl), pp[d]);
-                        };
-                        const double acc = (D <= 256) ? pairwise_sum_lanes16<double>(term, D, hmask, jl)
-                                                      : pairwise_sum<double>(term, D);
-                        const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
-                        val = prior + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
-                    } else {
-                        val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + __ldcg(p.seg_prior + slot);
-                    }
-                    if (jl == 0) vbuf[k_lo + kl] = val;
-                }
-            }
-            grid_barrier(p.bar, G, (it << 8) | 0x50 | (j << 16), (unsigned)(K | ((unsigned)n_total << 8) | ((unsigned)u_pos << 20)));
-            double mx = neg_inf();
-            for (int k = tid; k < KM; k += GB_THREADS) {
-                const double val = __ldcg(vbuf + k);
-                s.sk[k] = val;
-                mx = fmax(mx, val);
-            }
-            const double uu = (p.assign_mode == 0) ? p.uniforms[u_pos] : 0.0;
-            if (p.assign_mode == 0) u_pos += 1;
-            int k_sel = fv_decide(ds, K, KM, p.assign_mode, p.assign_temp, uu, mx);
-            // add_item (:153-170)
-            const bool fresh = (k_sel == K);
-            __syncthreads();
-            if (tid == 0) s.counts[k_sel] += 1;
-            if (fresh) K += 1;
-            n_total += 1;
-            if (k_sel >= k_lo && k_sel < k_hi) {
-                const int kl = k_sel - k_lo;
-                for (int d = tid; d < D; d += GB_THREADS) {
-                    double nu = s.num[kl * D + d], pNv = s.pN[kl * D + d];
-                    if (fresh) { nu = __dmul_rn(m.precision_0[d], m.mu_0[d]); pNv = m.precision_0[d]; }
-                    s.num[kl * D + d] = __dadd_rn(nu, __dmul_rn(m.precision[d], s.xs[d]));
-                    s.pN[kl * D + d] = __dadd_rn(pNv, m.precision[d]);
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    m.assignments[id] = k_sel;
-                    s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_sel]);
-                }
-                refresh_and_publish(kl);
-            }
-            __syncthreads();
+            assign_one(id, __ldcg(p.seg_prior + slot), (it << 8) | (j << 16), -1);
         }
     }
     if (b == 0 && tid == 0) {
@@ -493,6 +572,7 @@ extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb
     GibbsParams p;
     p.m = *m; p.c = *c; p.order = d_order; p.n_order = n_order; p.fb_mode = fb_mode;
     p.assign_mode = (fb_mode == SEGB_DP_FFBS) ? 0 : 1;
+    p.item_mode = 0;
     p.tpt = time_power_term; p.wip = wip; p.anneal_temp = anneal_temp;
     p.assign_temp = anneal_gibbs_am ? anneal_temp : 1.0;
     p.uniforms = uniforms; p.u_counter = u_counter; p.log_probs = log_probs; p.status = status;
@@ -508,6 +588,43 @@ extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb
     p.part_t = (double *)w; w += 8 * (size_t)G * p.M_cap;
     p.seg_prior = (double *)w; w += 8 * (size_t)p.M_cap;
     p.scores = (double *)w; w += 8 * (size_t)p.M_cap;
+    p.v = (double *)w;
+    SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
+    SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {&p};
+    SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel, dim3(G), dim3(GB_THREADS), args, smem, st));
+    count_launch();
+    return 0;
+}
+
+extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t *d_items, int32_t n_items,
+                                           double anneal_temp, const double *uniforms, int64_t *u_counter,
+                                           void *work, void *stream) {
+    SEGB_CHECK_ARG(m && d_items && uniforms && u_counter && work, "null pointer");
+    if (n_items == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, coop = 0, n_sm = 0;
+    SEGB_CUDA(cudaGetDevice(&dev));
+    SEGB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (!coop || n_sm > 160) { set_error("cooperative launch unavailable"); return SEGB_E_UNSUPPORTED; }
+    GibbsParams p;
+    memset(&p, 0, sizeof(p));
+    p.m = *m;
+    p.c.N_max = 1; p.c.S = 1;                        // no corpus: only the shared-memory carve-up reads these
+    p.order = d_items; p.n_order = n_items; p.item_mode = 1;
+    p.fb_mode = SEGB_DP_FFBS; p.assign_mode = 0;
+    p.tpt = 1.0; p.wip = 0.0; p.anneal_temp = anneal_temp; p.assign_temp = anneal_temp;
+    p.uniforms = uniforms; p.u_counter = u_counter;
+    const int G = gibbs_grid(m->K_max, n_sm);
+    p.per = (m->K_max + G - 1) / G;
+    p.M_cap = 1;
+    p.xb = 1;
+    const size_t smem = gibbs_smem_bytes(m->D, m->K_max, p.per, p.xb, p.M_cap, 1);
+    if (smem > 227 * 1024) { set_error("model too large for the persistent Gibbs sweep (%zu bytes of shared memory)", smem); return SEGB_E_UNSUPPORTED; }
+    unsigned char *w = (unsigned char *)work;
+    p.bar = (unsigned *)w; w += 2048;
+    p.part_m = p.part_t = p.seg_prior = p.scores = nullptr;
     p.v = (double *)w;
     SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
     SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -91,6 +91,41 @@ class FBGMM(object):
                                            _lib.stream_ptr()))
         return out.cpu().numpy().astype(np.float64)
 
+    def gibbs_sample(self, n_iter, consider_unassigned=True, anneal_schedule=None, anneal_start_temp_inv=0.1,
+                     anneal_end_temp_inv=1, n_anneal_steps=-1):
+        """fbgmm.py:288-420: `n_iter` sweeps of collapsed Gibbs sampling over the data items, each
+        sweep one cooperative launch (segb_fbgmm_gibbs_items_coop); `random.random()` is consumed
+        exactly as the reference consumes it (one draw per considered item, in item order)."""
+        import time
+        from .unigram_acoustic_wordseg import UniformFeed, _anneal_iter
+        c, lib = self.components, _lib.lib()
+        record_dict = {k: [] for k in ("sample_time", "log_marg", "log_prob_z", "log_prob_X_given_z",
+                                       "anneal_temp", "components")}
+        get_anneal_temp = _anneal_iter(n_iter, anneal_schedule, anneal_start_temp_inv, anneal_end_temp_inv,
+                                       n_anneal_steps)
+        work = torch.empty(lib.segb_gibbs_work_bytes(c.K_max, 1, 1), dtype=torch.uint8, device="cuda")
+        start_time = time.time()
+        for _ in range(n_iter):
+            anneal_temp = next(get_anneal_temp, anneal_end_temp_inv)
+            assign = c._assign
+            items = (torch.arange(c.N, device="cuda", dtype=torch.int32) if consider_unassigned
+                     else (assign != -1).nonzero().flatten().to(torch.int32))
+            n = int(items.numel())
+            feed = UniformFeed(n)
+            _lib.check(lib.segb_fbgmm_gibbs_items_coop(c.struct(), _lib.ptr(items), n, float(anneal_temp),
+                                                       _lib.ptr(feed.dev), _lib.ptr(feed.counter), _lib.ptr(work),
+                                                       _lib.stream_ptr()))
+            used = feed.finish()
+            assert used == n
+            record_dict["sample_time"].append(time.time() - start_time)
+            start_time = time.time()
+            record_dict["log_marg"].append(self.log_marg())
+            record_dict["log_prob_z"].append(self.log_prob_z())
+            record_dict["log_prob_X_given_z"].append(self.log_prob_X_given_z())
+            record_dict["anneal_temp"].append(anneal_temp)
+            record_dict["components"].append(c.K)
+        return record_dict
+
     def _assign(self, ids, mode, anneal_temp, uniforms):
         c = self.components
         ids_d = _lib.dev(np.asarray(ids, dtype=np.int32))

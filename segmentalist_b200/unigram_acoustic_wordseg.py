@@ -197,13 +197,14 @@ class UnigramAcousticWordseg(object):
     def gibbs_sample(self, n_iter, am_n_iter=0, anneal_schedule=None, anneal_start_temp_inv=0.1,
                      anneal_end_temp_inv=1, n_anneal_steps=-1, anneal_gibbs_am=False):
         """Blocked Gibbs sampling over all utterances (:362-472)."""
-        assert am_n_iter == 0, "in-between FBGMM.gibbs_sample is not on the device path yet (SURVEY 8f)"
         get_anneal_temp = _anneal_iter(n_iter, anneal_schedule, anneal_start_temp_inv, anneal_end_temp_inv,
                                        n_anneal_steps)
         record_dict = {k: [] for k in ("sample_time", "log_marg", "log_marg*length", "log_prob_z",
                                        "log_prob_X_given_z", "anneal_temp", "components", "n_tokens")}
         for i_iter in range(n_iter):
             start_time = time.time()
+            if am_n_iter > 0:                                                   # :440-443
+                self.acoustic_model.gibbs_sample(am_n_iter, consider_unassigned=False)
             anneal_temp = next(get_anneal_temp, anneal_end_temp_inv)
             utt_order = list(range(self.utterances.D))
             random.shuffle(utt_order)

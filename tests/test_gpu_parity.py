@@ -308,6 +308,61 @@ def test_unigram_gibbs_golden(sb, tag, fb_type):
     assert np.array_equal(np.isneginf(got), np.isneginf(z["u0_scores"]))
 
 
+@pytest.mark.parametrize("tag", ["plain", "all_anneal"])
+def test_fbgmm_gibbs_sample_golden(sb, tag):
+    """FBGMM.gibbs_sample on the device (one cooperative launch per sweep) == the reference under the
+    same random stream: assignments / counts / K identical, statistics and record to 1e-10."""
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf
+    z = G.load("fbgmm_gibbs_%s.npz" % tag)
+    D = z["X"].shape[1]
+    random.seed(4)
+    np.random.seed(4)
+    prior = gcf.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+    am = fbgmm.FBGMM(z["X"], prior, float(z["alpha"]), int(z["K_max"]), z["init_assignments"].copy(),
+                     covariance_type="fixed", lms=float(z["lms"]))
+    kw = {} if tag == "plain" else {"anneal_schedule": "linear", "anneal_start_temp_inv": 0.4}
+    st = random.getstate()
+    rec = am.gibbs_sample(len(z["rec_log_marg"]), consider_unassigned=bool(z["consider_unassigned"]), **kw)
+    c = am.components
+    npt.assert_array_equal(c.assignments, z["assignments"])
+    npt.assert_array_equal(c.counts, z["counts"])
+    assert c.K == int(z["K"])
+    npt.assert_allclose(rec["log_marg"], z["rec_log_marg"], rtol=1e-10)
+    npt.assert_allclose(rec["anneal_temp"], z["anneal_temp"], rtol=1e-15)
+    npt.assert_allclose(c.mu_N_numerators, z["mu_N_numerators"], rtol=1e-12, atol=1e-10)
+    npt.assert_allclose(c.log_prod_precision_preds, z["log_prod_precision_preds"], rtol=1e-12)
+    # the host generator advanced by exactly the number of draws the reference made
+    random.setstate(st)
+    for _ in range(len(z["uniforms"])):
+        random.random()
+    expect = random.random()
+    random.setstate(st)
+    npt.assert_array_equal(np.array([random.random() for _ in range(len(z["uniforms"]))]), z["uniforms"])
+    assert random.random() == expect
+
+
+def test_unigram_with_am_resampling_golden(sb):
+    """gibbs_sample(2, am_n_iter=2): segmentation sweeps interleaved with whole-model resampling."""
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf, unigram_acoustic_wordseg as uaw
+    z = G.load("unigram_am_iter.npz")
+    mats, vids, durs, lms = G.unpack_dicts(z)
+    random.seed(6)
+    np.random.seed(6)
+    D = 16
+    prior = gcf.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+    seg = uaw.UnigramAcousticWordseg(
+        fbgmm.FBGMM, 10., 9, prior, mats, vids, durs, lms, p_boundary_init=0.5, beta_sent_boundary=-1,
+        n_slices_max=4, lms=1.0, wip=0.0, fb_type="standard")
+    rec = seg.gibbs_sample(2, am_n_iter=2)
+    c = seg.acoustic_model.components
+    npt.assert_array_equal(seg.utterances.boundaries, z["boundaries"])
+    npt.assert_array_equal(c.assignments, z["assignments"])
+    npt.assert_array_equal(c.counts, z["counts"])
+    assert c.K == int(z["K"])
+    npt.assert_allclose(rec["log_marg"], z["rec_log_marg"], rtol=1e-10)
+    npt.assert_allclose(rec["log_marg*length"], z["rec_log_marg*length"], rtol=1e-10)
+
+
 @pytest.mark.parametrize("init", ["spread", "rand"])
 def test_kmeans_wordseg_golden(sb, init):
     """BASELINE config 1: sequential segment() and the frozen sweep vs the reference."""

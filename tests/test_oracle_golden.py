@@ -248,6 +248,52 @@ def test_golden_unigram_gibbs(tag, fb_type):
     npt.assert_allclose(c.mu_N_numerators, z["mu_N_numerators"], rtol=1e-13, atol=1e-12)
 
 
+@pytest.mark.parametrize("tag", ["plain", "all_anneal"])
+def test_golden_fbgmm_gibbs(tag):
+    """FBGMM.gibbs_sample (fbgmm.py:288-420, fixed variance) as run by the reference: the oracle port
+    reproduces assignments, counts, statistics and the record under the recorded uniform stream."""
+    z = G.load("fbgmm_gibbs_%s.npz" % tag)
+    D = z["X"].shape[1]
+    prior = so.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+    src = so.UniformSource(z["uniforms"])
+    am = so.FBGMM(z["X"], prior, float(z["alpha"]), int(z["K_max"]), z["init_assignments"].copy(),
+                  lms=float(z["lms"]), uniform=src)
+    log_margs = []
+    for temp in z["anneal_temp"]:
+        am.gibbs_sample(1, consider_unassigned=bool(z["consider_unassigned"]), anneal_temp=float(temp))
+        log_margs.append(am.log_marg())
+    c = am.components
+    assert src.pos == len(z["uniforms"])
+    npt.assert_array_equal(c.assignments, z["assignments"])
+    npt.assert_array_equal(c.counts, z["counts"])
+    assert c.K == int(z["K"])
+    npt.assert_allclose(log_margs, z["rec_log_marg"], rtol=1e-12)
+    npt.assert_allclose(c.mu_N_numerators, z["mu_N_numerators"], rtol=1e-13, atol=1e-12)
+    npt.assert_allclose(c.log_prod_precision_preds, z["log_prod_precision_preds"], rtol=1e-13)
+
+
+def test_golden_unigram_with_am_resampling():
+    """UnigramAcousticWordseg.gibbs_sample(2, am_n_iter=2): segmentation sweeps interleaved with
+    whole-model FBGMM.gibbs_sample (unigram_acoustic_wordseg.py:440-443)."""
+    z = G.load("unigram_am_iter.npz")
+    mats, vids, durs, lms = G.unpack_dicts(z)
+    random.seed(6)
+    np.random.seed(6)
+    D = 16
+    prior = so.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+    src = so.UniformSource(z["uniforms"])
+    seg = so.UnigramAcousticWordseg(
+        so.FBGMM, 10., 9, prior, mats, vids, durs, lms, p_boundary_init=0.5, beta_sent_boundary=-1,
+        n_slices_max=4, lms=1.0, wip=0.0, fb_type="standard", uniform=src)
+    rec = seg.gibbs_sample(2, am_n_iter=2, utt_orders=z["orders"])
+    c = seg.acoustic_model.components
+    assert src.pos == len(z["uniforms"])
+    npt.assert_array_equal(seg.utterances.boundaries, z["boundaries"])
+    npt.assert_array_equal(c.assignments, z["assignments"])
+    npt.assert_array_equal(c.counts, z["counts"])
+    npt.assert_allclose(rec["log_marg"], z["rec_log_marg"], rtol=1e-12)
+
+
 @pytest.mark.parametrize("init", ["spread", "rand"])
 def test_golden_kmeans_wordseg(init):
     z = G.load("kmeans_wordseg.npz")
