@@ -28,7 +28,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .sharding import clamp_plan, compaction_plan, dist_on as _dist_on, reduce_stats
+from .sharding import clamp_plan, compaction_plan, dist_on as _dist_on, reduce_packed
 
 
 class MmaScorer(object):
@@ -201,10 +201,7 @@ class FrozenKMeansSweep(object):
         """All-reduce the sufficient statistics over ranks (NCCL over NVLink) -- ONE collective
         over the flat buffer [sum_x | counts] -- and rebuild the means."""
         lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
-        if _dist_on():
-            self.cnt_f.copy_(self.cnt)                       # counts ride along as float64 (exact below 2^53)
-            dist.all_reduce(self.red, op=dist.ReduceOp.SUM)
-            self.cnt.copy_(self.cnt_f)
+        reduce_packed(self.red, self.cnt_f, self.cnt)        # counts ride along as float64 (exact below 2^53)
         _lib.check(lib.segb_kmeans_set_means(c.struct(), _lib.ptr(self.sum_x), _lib.ptr(self.cnt), sp))
 
     def init_means_from_assignments(self):
@@ -285,6 +282,38 @@ class FrozenKMeansSweep(object):
         if n_empty:
             self._clean_components(K_now)
         return total
+
+    def fit(self, n_iter):
+        """Frozen hard-assignment E-step + M-step over the CURRENT tokens -- KMeans.fit(n_iter,
+        consider_unassigned=False) (kmeans.py:97-173) in sharded form: every rank re-assigns its own
+        tokens against the same means (tensor-core scorer), one all-reduce of (sum_x, counts)
+        rebuilds identical means everywhere, clean_components is replayed identically.  Stops when
+        no token changed component on any rank.  Returns the reference's record keys."""
+        c, cp = self.c, self.corpus
+        if self.K_host is None:
+            self.K_host = c.K
+        record = {"components": [], "n_mean_updates": []}
+        tok = cp.tok_id[cp.tok_id >= 0].long()
+        for _ in range(n_iter):
+            K_before = self.K_host
+            self.score()
+            changed = (self.best_k[tok] != c._assign[tok]).sum().to(torch.int64).reshape(1)
+            self.collect()                                  # tokens of the unchanged boundaries, k = argmax
+            if K_before < c.K_max:
+                self._clamp_inactive_winners(K_before)
+            self.reduce_and_update()
+            if _dist_on():
+                dist.all_reduce(changed, op=dist.ReduceOp.SUM)
+            K_now = self.K_host
+            self.flags[2:3].copy_((self.cnt[:K_now] == 0).sum())
+            n_changed, n_empty = int(changed.item()), int(self.flags[2].item())
+            if n_empty:
+                self._clean_components(K_now)
+            record["components"].append(self.K_host)
+            record["n_mean_updates"].append(n_changed)
+            if n_changed == 0:
+                break
+        return record
 
     def _clean_components(self, K_old):
         """clean_components() (kmeans_components.py:263-266) without the per-deletion token

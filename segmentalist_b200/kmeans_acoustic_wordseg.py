@@ -139,10 +139,12 @@ class SegmentalKMeansWordseg(object):
         return record_dict
 
     # ---- frozen-state batch mode (new)
-    def segment_frozen(self, n_iter, scorer="auto"):
+    def segment_frozen(self, n_iter, n_iter_inbetween_kmeans=0, scorer="auto"):
         """Frozen-means sweeps: score + Viterbi for every utterance against the same
         means, then rebuild the means from the new tokens (KMeans.fit semantics,
-        kmeans.py:124-171, applied to segmentation).  Returns a record dict."""
+        kmeans.py:124-171, applied to segmentation); n_iter_inbetween_kmeans > 0 runs that many
+        frozen hard-assignment steps over the current tokens after every sweep
+        (kmeans_acoustic_wordseg.py:414-417), sharded like the sweep.  Returns a record dict."""
         if self._frozen is None:
             self._frozen = FrozenKMeansSweep(self.acoustic_model.components, self._corpus, wip=self.wip,
                                              scorer=scorer)
@@ -156,6 +158,8 @@ class SegmentalKMeansWordseg(object):
             record["components"].append(self.acoustic_model.components.K)
             record["n_tokens"].append(self.acoustic_model.get_n_assigned())
             record["sample_time"].append(time.time() - t0)
+            if n_iter_inbetween_kmeans > 0:
+                record.setdefault("kmeans_fit", []).append(self._frozen.fit(n_iter_inbetween_kmeans))
         return record
 
     def get_unsup_transcript_i(self, i):

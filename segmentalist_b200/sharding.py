@@ -38,6 +38,17 @@ def reduce_stats(sum_x, cnt, extra=None):
     return sum_x, cnt, extra
 
 
+def reduce_packed(red, cnt_f, cnt):
+    """The sweep's ONE collective: `red` is a flat float64 buffer [sum_x | counts]; the int64
+    counts are copied into its tail `cnt_f` (exact below 2^53), the whole buffer is all-reduced
+    (SUM) and the counts copied back.  No-op without an initialised process group."""
+    if dist_on():
+        cnt_f.copy_(cnt)
+        dist.all_reduce(red, op=dist.ReduceOp.SUM)
+        cnt.copy_(cnt_f)
+    return red, cnt
+
+
 def compaction_plan(cnt, K):
     """Replay clean_components' swap-with-last deletions (kmeans_components.py:149-166,263-266)
     on the counts of the K active slots.  Returns (K_new, dst, src): after the deletions slot

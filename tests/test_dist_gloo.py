@@ -61,7 +61,12 @@ def _worker(rank, world, port, init, out):
             sum_x[k] += torch.from_numpy(comps.X[e].astype(np.float64))
             cnt[k] += 1
         obj = torch.tensor([float(np.sum(totals))], dtype=torch.float64)
-        sharding.reduce_stats(sum_x, cnt, obj)
+        # the product's collective: one flat float64 buffer [sum_x | counts] (batch.py)
+        red = torch.zeros(K_max * D + K_max, dtype=torch.float64)
+        red[:K_max * D] = sum_x.reshape(-1)
+        sum_x = red[:K_max * D].view(K_max, D)
+        sharding.reduce_packed(red, red[K_max * D:], cnt)
+        sharding.reduce_stats(torch.zeros(1, 1, dtype=torch.float64), torch.zeros(1, dtype=torch.int64), obj)
         means = sharding.means_from_stats(sum_x.numpy(), cnt.numpy(), comps.means)
         K_new, dst, src = sharding.compaction_plan(cnt.numpy(), K)
         counts = cnt.numpy().copy()

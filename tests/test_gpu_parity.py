@@ -454,6 +454,32 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
     npt.assert_array_equal(bv, val.cpu().numpy()[ids])
 
 
+def test_frozen_fit_equals_reference_kmeans_fit(sb):
+    """FrozenKMeansSweep.fit (sharded hard-assignment E-step + all-reduce M-step) == the reference's
+    KMeans.fit(n, consider_unassigned=False) (kmeans.py:97-173) applied to the segmenter's tokens."""
+    from segmentalist_b200 import kmeans_acoustic_wordseg as kaw, synth
+    mats, vids, durs, lms = synth.make_corpus_dicts(30, D=130, K_true=10, n_min=5, n_max=12, n_slices_max=5, seed=8)
+
+    def seeded():
+        random.seed(3)
+        np.random.seed(3)
+    seeded()
+    seg = kaw.KMeansAcousticWordseg(14, mats, vids, durs, lms, n_slices_max=5, init_am_assignments="spread")
+    seeded()
+    ora = so.SegmentalKMeansWordseg(14, mats, vids, durs, lms, n_slices_max=5, init_am_assignments="spread")
+    seg.segment_frozen(1, scorer="mma")
+    so.frozen_kmeans_sweep(ora)
+    npt.assert_array_equal(seg.acoustic_model.components.assignments, ora.acoustic_model.components.assignments)
+    rec = seg._frozen.fit(4)
+    orec = ora.acoustic_model.fit(4, consider_unassigned=False)
+    c, oc = seg.acoustic_model.components, ora.acoustic_model.components
+    assert rec["n_mean_updates"] == orec["n_mean_updates"]
+    assert rec["components"] == orec["components"]
+    npt.assert_array_equal(c.assignments, oc.assignments)
+    npt.assert_array_equal(c.counts, oc.counts)
+    npt.assert_array_equal(c.means, oc.means)
+
+
 def test_mma_scorer_streamed_from_host(sb):
     """Scoring embeddings uploaded chunk by chunk from pinned host memory (copy stream overlapped
     with packing + filter + refine) gives the same bits as scoring the resident matrix; the
