@@ -344,29 +344,39 @@ class FrozenKMeansSweep(object):
     def _clamp_inactive_winners(self, K_before):
         """add_item's `k > K -> K` clamp (kmeans_components.py:103-106) for tokens won by an
         inactive slot.  Sequential by nature; resolved on the host over the (few) affected
-        tokens in utterance order, then the statistics are re-collected."""
+        tokens in utterance order, then the statistics of exactly those tokens are moved (sums of
+        float32 embeddings are exact in float64, so subtracting and re-adding a row leaves the
+        same bits as collecting again)."""
         c, cp = self.c, self.corpus
         flag = (self.cnt[K_before:] > 0).any().to(torch.int32).reshape(1)
         if _dist_on():
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         if int(flag.item()) == 0:
             return
-        tok = cp.tok_id[cp.tok_id >= 0].long()            # utterance order, left to right
-        ks_tok = self.best_k[tok]
-        sel = (ks_tok >= K_before).nonzero().flatten()
-        ids = tok[sel].cpu().numpy()
-        ks = ks_tok[sel].cpu().numpy().astype(np.int64)
+        tid = cp.tok_id
+        k_at = torch.where(tid >= 0, c._assign[tid.clamp(min=0).long()], torch.full_like(tid, -1))
+        pos = (k_at >= K_before).nonzero().flatten()            # landmark order == token order
+        ids_d = tid[pos].long()
+        ks_old_d = k_at[pos].long()
+        ks = ks_old_d.cpu().numpy().astype(np.int64)
         if _dist_on():
             # ranks hold consecutive utterance ranges: rank order IS the global token order
             parts = [None] * dist.get_world_size()
             dist.all_gather_object(parts, ks.tolist())
             all_ks, K = clamp_plan([k for part in parts for k in part], K_before)
             lo = sum(len(part) for part in parts[:dist.get_rank()])
-            ks = all_ks[lo:lo + len(ks)]
+            ks_new = np.asarray(all_ks[lo:lo + len(ks)], dtype=np.int64)
         else:
-            ks, K = clamp_plan(ks, K_before)
+            ks_new, K = clamp_plan(ks, K_before)
         c._K.fill_(int(K))
         self.K_host = int(K)
-        if len(ids):
-            self.best_k[_lib.dev(ids)] = _lib.dev(np.asarray(ks).astype(np.int32))
-        self.collect()
+        if len(ks):
+            ks_new_d = _lib.dev(np.asarray(ks_new, dtype=np.int64))
+            rows = c._X[ids_d].to(torch.float64)
+            self.sum_x.index_add_(0, ks_old_d, -rows)
+            self.sum_x.index_add_(0, ks_new_d, rows)
+            ones = torch.ones_like(ks_old_d)
+            self.cnt.index_add_(0, ks_old_d, -ones)
+            self.cnt.index_add_(0, ks_new_d, ones)
+            c._assign[ids_d] = ks_new_d.to(torch.int32)
+            self.best_k[ids_d] = ks_new_d.to(torch.int32)
