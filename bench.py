@@ -36,6 +36,11 @@ D, K_MAX, S_MAX = 130, 5000, 6
 N_LO, N_HI = 15, 25
 TOTAL_UTTS = 200000
 NOISE = 0.05
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the three reported kernels,
+# from ONE `ncu --set full --clock-control none` capture of this command at the default configuration on
+# one GPU (profiles/r1_ncu_summary_v3.md).  Reported only when the run uses that configuration.
+NCU_TRAFFIC_BYTES = {"filter": 6.056337e9 + 0.669730e9, "dp": 0.193679e9 + 0.008181e9,
+                     "fv_logmarg_per_row": (607.070976e6 + 4.2e6) / 1048576}
 METRIC = "utterances/sec per sweep"
 WORKLOAD = "kmeans_viterbi_frozen_sweep D=130 K=5000 U=200k max_span=6 (BASELINE configs[2])"
 
@@ -456,7 +461,10 @@ def run_ours(args):
             ach = flops / (k_ms * 1e-3) / 1e12
             roofline = {"kernel": "kmeans_filter_kernel (tcgen05 fp16 -> fp32 TMEM, fused top-3 epilogue)",
                         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                        "frac": ach / peak_tf,
+                        "traffic": NCU_TRAFFIC_BYTES["filter"] if (world == 1 and args.utts == TOTAL_UTTS and args.K == K_MAX) else None,
+                        "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_ncu_summary_v3.md)",
+                        "peak_source": peak_src,
                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops}
         cs = corpus.struct()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -473,7 +481,9 @@ def run_ours(args):
         dp_bytes = 8.0 * n_pos * S_MAX + n_pos + 8.0 * corpus.n_utt + 8.0 * (corpus.n_utt + 1) + 4.0 * corpus.n_utt
         roofline_dp = {"kernel": "dp_staged_kernel (Viterbi, float64 banded scores, cp.async.bulk staging, thread per utterance)", "bound": "hbm",
                        "achieved": dp_bytes / (dp_ms * 1e-3) / 1e9, "peak": peak_bw, "unit": "GB/s",
-                       "frac": dp_bytes / (dp_ms * 1e-3) / 1e9 / peak_bw, "traffic": None, "kernel_ms": dp_ms,
+                       "frac": dp_bytes / (dp_ms * 1e-3) / 1e9 / peak_bw,
+                       "traffic": NCU_TRAFFIC_BYTES["dp"] if (world == 1 and args.utts == TOTAL_UTTS) else None,
+                       "kernel_ms": dp_ms,
                        "algorithmic_bytes_per_launch": dp_bytes}
 
     # ---- the other scoring kernel: FBGMM log_marg_i as an FP32-accurate tcgen05 GEMM + fused logsumexp
@@ -503,7 +513,9 @@ def run_ours(args):
         fl = 2.0 * D * n_fv * args.K
         roofline_fv = {"kernel": "fv_logmarg_kernel (tcgen05 fp16 hi/lo split x3 passes -> fp32 TMEM, fused online logsumexp)",
                        "bound": "tensor", "achieved": fl / (fv_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                       "frac": fl / (fv_ms * 1e-3) / 1e12 / peak_tf, "traffic": None, "kernel_ms": fv_ms,
+                       "frac": fl / (fv_ms * 1e-3) / 1e12 / peak_tf,
+                       "traffic": NCU_TRAFFIC_BYTES["fv_logmarg_per_row"] * n_fv if args.K == K_MAX else None,
+                       "kernel_ms": fv_ms,
                        "rows": n_fv, "K": args.K, "algorithmic_flops_per_launch": fl,
                        "executed_tflops": fl / (fv_ms * 1e-3) / 1e12 * (3 * 16 * ((D + 6 + 15) // 16)) / D,
                        "note": "FP32-accurate split = 3 tensor passes over the padded inner dimension (3*144/130 = 3.3 executed flops per algorithmic flop): algorithmic ceiling ~0.30 of peak; executed_tflops is what the tensor pipe actually did"}
