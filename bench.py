@@ -407,10 +407,13 @@ def run_ours(args):
     evals_per_sweep_local = float(M) * args.K
 
     # ---- warm-up + timed region (device time, max over ranks)
+    # nvidia-smi clock / throttle sampling: started before the warm-up sweeps and stopped after the
+    # kernel-alone timings below, so that short timed regions (25 ms at 8 GPUs) still get samples;
+    # every sampled interval is under load
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         sweep.sweep()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.segb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -421,7 +424,6 @@ def run_ours(args):
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
     launches = lib.segb_launch_count() - launches0
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     tot = torch.tensor([evals_per_sweep_local, float(M), float(fallback)], device=dev, dtype=torch.float64)
@@ -520,6 +522,10 @@ def run_ours(args):
                        "executed_tflops": fl / (fv_ms * 1e-3) / 1e12 * (3 * 16 * ((D + 6 + 15) // 16)) / D,
                        "note": "FP32-accurate split = 3 tensor passes over the padded inner dimension (3*144/130 = 3.3 executed flops per algorithmic flop): algorithmic ceiling ~0.30 of peak; executed_tflops is what the tensor pipe actually did"}
         del am
+
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed sweeps + kernel-alone timings (all under load)"
 
     # ---- end to end: host buffers in, host results out, every step
     e2e = None
