@@ -443,6 +443,90 @@ def golden_fbgmm_gibbs(ref_fbgmm, ref_fv, ref_uni):
     print("unigram_am_iter log_marg", rec["log_marg"], "K", c.K, "uniforms", len(tap.uniforms))
 
 
+def golden_diag(ref_diag, ref_niw, ref_fbgmm, ref_uni):
+    """Diagonal-covariance components (gaussian_components_diag.py): statistics after add/del incl.
+    a component deletion, predictive scores, whole-model Gibbs and a segmenter run (BASELINE config 5
+    family), all produced by the reference."""
+    from segmentalist_b200 import synth
+    D = 12
+    rng = np.random.RandomState(5)
+    m_0 = 0.2 * rng.rand(D) - 0.1
+    prior_args = dict(m_0=m_0, k_0=0.05, v_0=D + 3, S_0=0.02 * rng.rand(D) + 0.01)
+    centres = synth.cluster_centres(5, D, rng)
+    n = 90
+    X = synth._unit_rows(centres[rng.randint(0, 5, n)] + 0.1 * rng.standard_normal((n, D)).astype(np.float32))
+    assign = rng.randint(0, 6, n)
+    assign[rng.rand(n) < 0.25] = -1
+    assign[assign == 5] = -1
+    assign[:2] = 5                                     # a two-item component that will be deleted
+    d = {"X": X, "m_0": m_0, "k_0": np.array(prior_args["k_0"]), "v_0": np.array(prior_args["v_0"]),
+         "S_0": prior_args["S_0"], "init_assignments": assign.copy()}
+    c = ref_diag.GaussianComponentsDiag(X, ref_niw.NIW(**prior_args), assign.copy(), K_max=9)
+    probe = np.where(assign == -1)[0][:6]
+    d["probe"] = probe
+    d["post_pred0"] = np.array([c.log_post_pred(int(i)) for i in probe])
+    d["prior0"] = np.array([c.log_prior(int(i)) for i in probe])
+    d["log_marg0"] = np.array(c.log_marg())
+    c.del_item(0)
+    c.del_item(1)                                      # deletes component 5 (the last one)
+    c.del_item(int(np.where(assign == 0)[0][0]))
+    c.add_item(int(probe[0]), c.K)                     # new component
+    c.add_item(int(probe[1]), 2)
+    d["assignments1"] = c.assignments.copy()
+    d["counts1"] = c.counts.copy()
+    d["K1"] = np.array(c.K)
+    d["m_N_numerators1"] = c.m_N_numerators.copy()
+    d["S_N_partials1"] = c.S_N_partials.copy()
+    d["log_prod_vars1"] = c.log_prod_vars.copy()
+    d["inv_vars1"] = c.inv_vars.copy()
+    d["post_pred1"] = np.array([c.log_post_pred(int(i)) for i in probe[2:]])
+    d["log_marg1"] = np.array(c.log_marg())
+    # whole-model Gibbs
+    random.seed(8)
+    np.random.seed(8)
+    am = ref_fbgmm.FBGMM(X, ref_niw.NIW(**prior_args), 3., 9, assign.copy(), covariance_type="diag", lms=0.9)
+    d["gs_init_assignments"] = am.components.assignments.copy()
+    with Tap() as tap:
+        rec = am.gibbs_sample(2, consider_unassigned=False)
+    cc = am.components
+    d["gs_uniforms"] = np.array(tap.uniforms)
+    d["gs_assignments"] = cc.assignments.copy()
+    d["gs_counts"] = cc.counts.copy()
+    d["gs_K"] = np.array(cc.K)
+    d["gs_log_marg"] = np.array(rec["log_marg"], dtype=np.float64)
+    d["gs_m_N_numerators"] = cc.m_N_numerators.copy()
+    d["gs_log_marg_i"] = np.array([am.log_marg_i(int(i)) for i in probe])
+    np.savez_compressed(os.path.join(OUT, "diag_components.npz"), **d)
+    print("diag components K", int(d["K1"]), "gibbs log_marg", rec["log_marg"], "uniforms", len(tap.uniforms))
+    # segmenter with diagonal covariance
+    mats, vids, durs, lms = synth.make_corpus_dicts(10, D=D, K_true=4, n_min=3, n_max=8, n_slices_max=4, noise=0.1, seed=41)
+    random.seed(9)
+    np.random.seed(9)
+    seg = ref_uni.UnigramAcousticWordseg(
+        ref_fbgmm.FBGMM, 5., 8, ref_niw.NIW(**prior_args), mats, vids, durs, lms, p_boundary_init=0.5,
+        beta_sent_boundary=-1, n_slices_max=4, lms=1.0, wip=0.0, fb_type="standard", covariance_type="diag")
+    ref_uni.i_debug_monitor = -1
+    e = pack_dicts("in_", mats, vids, durs, lms)
+    for k_, v_ in (("m_0", m_0), ("k_0", np.array(prior_args["k_0"])), ("v_0", np.array(prior_args["v_0"])),
+                   ("S_0", prior_args["S_0"])):
+        e[k_] = v_
+    e["init_boundaries"] = seg.utterances.boundaries.copy()
+    e["init_assignments"] = seg.acoustic_model.components.assignments.copy()
+    with Tap() as tap:
+        rec = seg.gibbs_sample(3)
+    cc = seg.acoustic_model.components
+    e["uniforms"] = np.array(tap.uniforms)
+    e["orders"] = np.array(tap.orders)
+    for key in ("log_marg", "log_marg*length", "log_prob_z", "log_prob_X_given_z", "components", "n_tokens"):
+        e["rec_" + key] = np.array(rec[key], dtype=np.float64)
+    e["boundaries"] = seg.utterances.boundaries.copy()
+    e["assignments"] = cc.assignments.copy()
+    e["counts"] = cc.counts.copy()
+    e["K"] = np.array(cc.K)
+    np.savez_compressed(os.path.join(OUT, "unigram_diag.npz"), **e)
+    print("unigram_diag log_marg", rec["log_marg"], "K", cc.K, "uniforms", len(tap.uniforms))
+
+
 def main():
     only = set(sys.argv[1:])                 # e.g. `make_golden.py fbgmm_gibbs` regenerates one family
     run = lambda name: (not only) or (name in only)
@@ -473,6 +557,9 @@ def main():
             golden_kmeans_wordseg(ref_km)
         if run("fbgmm_gibbs"):
             golden_fbgmm_gibbs(ref_fbgmm, ref_fv, ref_uni)
+        if run("diag"):
+            golden_diag(importlib.import_module("segmentalist.gaussian_components_diag"),
+                        importlib.import_module("segmentalist.niw"), ref_fbgmm, ref_uni)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -266,6 +266,170 @@ class FixedVarComponents(object):
 
 
 # ---------------------------------------------------------------------------
+# Diagonal-covariance Gaussian components   (gaussian_components_diag.py, niw.py)
+# ---------------------------------------------------------------------------
+
+class NIW(object):
+    """niw.py:7-15 (v_0 is an integer >= D: it indexes the cached gammaln table)."""
+
+    def __init__(self, m_0, k_0, v_0, S_0):
+        self.m_0, self.k_0, self.S_0 = m_0, k_0, S_0
+        assert v_0 >= len(m_0), "v_0 must be larger or equal to dimension of data"
+        self.v_0 = v_0
+
+
+class DiagComponents(object):
+    """Normal-inverse-chi-squared components with a product-of-Student's-t predictive.
+
+    Restates GaussianComponentsDiag (gaussian_components_diag.py:82-345)."""
+
+    def __init__(self, X, prior, assignments=None, K_max=None):
+        self.X, self.prior = X, prior
+        self.N, self.D = X.shape
+        if K_max is None:                                            # :90-91
+            K_max = self.N
+        self.K_max = K_max
+        assert len(prior.S_0.shape) == 1, "For diagonal covariance, S_0 needs to be vector."
+        self.m_N_numerators = np.zeros((K_max, self.D))              # :97-101
+        self.S_N_partials = np.zeros((K_max, self.D))
+        self.log_prod_vars = np.zeros(K_max)
+        self.inv_vars = np.zeros((K_max, self.D))
+        self.counts = np.zeros(K_max, dtype=np.int64)
+        # :119-131 caches
+        self._sq_m_0 = np.square(prior.m_0)
+        self._sq = np.square(X)
+        n = np.concatenate([[1], np.arange(1, prior.v_0 + self.N + 2)])
+        self._log_v = np.log(n)
+        self._gammaln_by_2 = gammaln(n / 2.)
+        self._log_pi = math.log(np.pi)
+        self.K = 0
+        if assignments is None:
+            self.assignments = -1 * np.ones(self.N, dtype=np.int64)
+        else:
+            assignments = np.asarray(assignments, dtype=np.int64)
+            assert (self.N,) == assignments.shape
+            assert set(assignments).difference([-1]) == set(range(assignments.max() + 1))
+            self.assignments = assignments
+            for k in range(self.assignments.max() + 1):
+                for i in np.where(self.assignments == k)[0]:
+                    self.add_item(i, k)
+
+    def _refresh(self, k):
+        """:332-345."""
+        k_N = self.prior.k_0 + self.counts[k]
+        v_N = self.prior.v_0 + self.counts[k]
+        m_N = self.m_N_numerators[k] / k_N
+        var = (k_N + 1.) / (k_N * v_N) * (self.S_N_partials[k] - k_N * np.square(m_N))
+        self.log_prod_vars[k] = np.log(var).sum()
+        self.inv_vars[k, :] = 1. / var
+
+    def add_item(self, i, k):
+        """:162-177."""
+        if k == self.K:
+            self.K += 1
+            self.m_N_numerators[k, :] = self.prior.k_0 * self.prior.m_0
+            self.S_N_partials[k, :] = self.prior.S_0 + self.prior.k_0 * self._sq_m_0
+        self.m_N_numerators[k, :] += self.X[i]
+        self.S_N_partials[k, :] += self._sq[i]
+        self.counts[k] += 1
+        self._refresh(k)
+        self.assignments[i] = k
+
+    def del_item(self, i):
+        """:179-194."""
+        k = self.assignments[i]
+        if k != -1:
+            self.counts[k] -= 1
+            self.assignments[i] = -1
+            if self.counts[k] == 0:
+                self.del_component(k)
+            else:
+                self.m_N_numerators[k, :] -= self.X[i]
+                self.S_N_partials[k, :] -= self._sq[i]
+                self._refresh(k)
+
+    def del_component(self, k):
+        """:196-214."""
+        self.K -= 1
+        last = self.K
+        if k != last:
+            self.m_N_numerators[k] = self.m_N_numerators[last]
+            self.S_N_partials[k, :] = self.S_N_partials[last, :]
+            self.log_prod_vars[k] = self.log_prod_vars[last]
+            self.inv_vars[k, :] = self.inv_vars[last, :]
+            self.counts[k] = self.counts[last]
+            self.assignments[np.where(self.assignments == last)] = k
+        self.m_N_numerators[last].fill(0.)
+        self.S_N_partials[last, :].fill(0.)
+        self.log_prod_vars[last] = 0.
+        self.inv_vars[last, :].fill(0.)
+        self.counts[last] = 0
+
+    def _log_prod_students_t(self, i, mu, log_prod_var, inv_var, v):
+        """:347-360."""
+        delta = self.X[i, :] - mu
+        return (self.D * (self._gammaln_by_2[v + 1] - self._gammaln_by_2[v]
+                          - 0.5 * self._log_v[v] - 0.5 * self._log_pi)
+                - 0.5 * log_prod_var
+                - (v + 1.) / 2. * (np.log(1. + 1. / v * np.square(delta) * inv_var)).sum())
+
+    def log_prior(self, i):
+        """:216-223."""
+        pr = self.prior
+        var = (pr.k_0 + 1.) / (pr.k_0 * pr.v_0) * pr.S_0
+        return self._log_prod_students_t(i, pr.m_0, np.log(var).sum(), 1. / var, pr.v_0)
+
+    def log_post_pred_k(self, i, k):
+        """:225-234."""
+        k_N = self.prior.k_0 + self.counts[k]
+        v_N = self.prior.v_0 + self.counts[k]
+        return self._log_prod_students_t(i, self.m_N_numerators[k] / k_N, self.log_prod_vars[k],
+                                         self.inv_vars[k], v_N)
+
+    def log_post_pred(self, i):
+        """:237-259 (vectorised; the row sum is einsum("ij->i") there)."""
+        K = self.K
+        k_Ns = self.prior.k_0 + self.counts[:K]
+        v_Ns = self.prior.v_0 + self.counts[:K]
+        m_Ns = self.m_N_numerators[:K] / k_Ns[:, np.newaxis]
+        studentt_gammas = self._gammaln_by_2[v_Ns + 1] - self._gammaln_by_2[v_Ns]
+        deltas = m_Ns - self.X[i]
+        return (self.D * (studentt_gammas - 0.5 * self._log_v[v_Ns] - 0.5 * self._log_pi)
+                - 0.5 * self.log_prod_vars[:K]
+                - (v_Ns + 1) / 2. * np.einsum("ij->i", np.log(
+                    1 + np.square(deltas) * self.inv_vars[:K] * (1. / v_Ns[:, np.newaxis]))))
+
+    def log_marg_k(self, k):
+        """:270-288."""
+        pr = self.prior
+        k_N = pr.k_0 + self.counts[k]
+        v_N = pr.v_0 + self.counts[k]
+        m_N = self.m_N_numerators[k] / k_N
+        S_N = self.S_N_partials[k] - k_N * np.square(m_N)
+        return (- self.counts[k] * self.D / 2. * self._log_pi
+                + self.D / 2. * math.log(pr.k_0) - self.D / 2. * math.log(k_N)
+                + pr.v_0 / 2. * np.log(pr.S_0).sum()
+                - v_N / 2. * np.log(S_N).sum()
+                + self.D * (self._gammaln_by_2[v_N] - self._gammaln_by_2[pr.v_0]))
+
+    def log_marg(self):
+        """:290-301."""
+        total = 0.
+        for k in range(self.K):
+            total += self.log_marg_k(k)
+        return total
+
+    def get_assignments(self, list_of_i):
+        return self.assignments[np.asarray(list_of_i)]
+
+
+def students_t(x, mu, var, v):
+    """gaussian_components_diag.py:371-380 (test helper of the reference)."""
+    c = gammaln((v + 1) / 2.) - gammaln(v / 2.) - 0.5 * (math.log(v) + math.log(np.pi) + math.log(var))
+    return c - (v + 1) / 2. * math.log(1 + 1. / v * (x - mu) ** 2 / var)
+
+
+# ---------------------------------------------------------------------------
 # K-means components   (kmeans_components.py)
 # ---------------------------------------------------------------------------
 
@@ -386,7 +550,7 @@ class FBGMM(object):
 
     def __init__(self, X, prior, alpha, K, assignments="rand", covariance_type="fixed",
                  lms=1.0, uniform=None):
-        assert covariance_type == "fixed", "oracle covers the fixed-variance path only"
+        assert covariance_type in ("fixed", "diag"), "oracle covers the fixed-variance and diagonal paths"
         self.alpha, self.prior, self.covariance_type, self.lms = alpha, prior, covariance_type, lms
         self.uniform = uniform if uniform is not None else UniformSource()
         N = X.shape[0]
@@ -395,7 +559,10 @@ class FBGMM(object):
         elif isinstance(assignments, str) and assignments == "each-in-own":
             assignments = np.arange(N)
         assignments = _consecutive(assignments)
-        self.components = FixedVarComponents(X, prior, assignments, K_max=K)
+        if covariance_type == "diag":                                       # fbgmm.py:130-137
+            self.components = DiagComponents(X, prior, assignments, K_max=K)
+        else:
+            self.components = FixedVarComponents(X, prior, assignments, K_max=K)
 
     def _log_prior_z(self, with_norm):
         c = self.components
@@ -462,9 +629,14 @@ class FBGMM(object):
                 if not consider_unassigned and k_old == -1:
                     continue
                 K_old = c.K
-                stats_old = (c.mu_N_numerators[k_old].copy(), c.precision_Ns[k_old].copy(),
-                             c.log_prod_precision_preds[k_old], c.precision_preds[k_old].copy(),
-                             c.counts[k_old])
+                diag = self.covariance_type == "diag"
+                if diag:        # gaussian_components_diag.py:137-150
+                    stats_old = (c.m_N_numerators[k_old].copy(), c.S_N_partials[k_old].copy(),
+                                 c.log_prod_vars[k_old], c.inv_vars[k_old].copy(), c.counts[k_old])
+                else:
+                    stats_old = (c.mu_N_numerators[k_old].copy(), c.precision_Ns[k_old].copy(),
+                                 c.log_prod_precision_preds[k_old], c.precision_preds[k_old].copy(),
+                                 c.counts[k_old])
                 c.del_item(i)
                 log_prob_z = self._assign_scores(i, True)
                 if anneal_temp != 1:
@@ -477,9 +649,13 @@ class FBGMM(object):
                 if k > c.K:
                     k = c.K
                 if k == k_old and c.K == K_old:
-                    (c.mu_N_numerators[k_old, :], c.precision_Ns[k_old, :],
-                     c.log_prod_precision_preds[k_old], c.precision_preds[k_old, :],
-                     c.counts[k_old]) = stats_old
+                    if diag:
+                        (c.m_N_numerators[k_old, :], c.S_N_partials[k_old, :], c.log_prod_vars[k_old],
+                         c.inv_vars[k_old, :], c.counts[k_old]) = stats_old
+                    else:
+                        (c.mu_N_numerators[k_old, :], c.precision_Ns[k_old, :],
+                         c.log_prod_precision_preds[k_old], c.precision_preds[k_old, :],
+                         c.counts[k_old]) = stats_old
                     c.assignments[i] = k_old
                 else:
                     c.add_item(i, k)

@@ -294,6 +294,99 @@ def test_golden_unigram_with_am_resampling():
     npt.assert_allclose(rec["log_marg"], z["rec_log_marg"], rtol=1e-12)
 
 
+def _diag_prior(z):
+    return so.NIW(m_0=z["m_0"], k_0=float(z["k_0"]), v_0=int(z["v_0"]), S_0=z["S_0"])
+
+
+def test_ref_kat_diag_students_t():
+    """The reference's own analytic checks for the diagonal components
+    (tests/test_gaussian_components_diag.py:17-86,229-256): prior and posterior predictive equal
+    the product of univariate Student's t densities; vectorised == per-component loop."""
+    np.random.seed(1)
+    D = 10
+    m_0 = 5 * np.random.rand(D) - 2
+    k_0 = np.random.randint(15)
+    v_0 = D + np.random.randint(5)
+    S_0 = 2 * np.random.rand(D) + 3
+    prior = so.NIW(m_0=m_0, k_0=k_0, v_0=v_0, S_0=S_0)
+    x = 3 * np.random.rand(D) + 4
+    gmm = so.DiagComponents(np.array([x]), prior)
+    expected = np.sum([so.students_t(x[i], m_0[i], S_0[i] * (k_0 + 1) / (k_0 * v_0), v_0) for i in range(D)])
+    npt.assert_almost_equal(gmm.log_prior(0), expected)
+    N = 12
+    X = 5 * np.random.rand(N, D) - 1
+    gmm = so.DiagComponents(X, prior)
+    for i in range(N):
+        gmm.add_item(i, 0)
+    k_N, v_N = k_0 + N, v_0 + N
+    m_N = (k_0 * m_0 + N * X.mean(axis=0)) / k_N
+    S_N = S_0 + np.square(X).sum(axis=0) + k_0 * np.square(m_0) - k_N * np.square(m_N)
+    expected = np.sum([so.students_t(X[0, i], m_N[i], S_N[i] * (k_N + 1) / (k_N * v_N), v_N) for i in range(D)])
+    npt.assert_almost_equal(gmm.log_post_pred_k(0, 0), expected)
+    gmm2 = so.DiagComponents(X, prior, np.arange(N) % 3, K_max=5)
+    npt.assert_almost_equal(gmm2.log_post_pred(4), [gmm2.log_post_pred_k(4, k) for k in range(gmm2.K)])
+
+
+def test_golden_diag_components():
+    """DiagComponents == the reference's GaussianComponentsDiag: predictive scores, statistics after
+    add/del incl. a component deletion, whole-model Gibbs under the recorded uniforms."""
+    z = G.load("diag_components.npz")
+    c = so.DiagComponents(z["X"], _diag_prior(z), z["init_assignments"].copy(), K_max=9)
+    probe = z["probe"]
+    npt.assert_array_equal(np.array([c.log_post_pred(int(i)) for i in probe]), z["post_pred0"])
+    npt.assert_array_equal(np.array([c.log_prior(int(i)) for i in probe]), z["prior0"])
+    assert c.log_marg() == float(z["log_marg0"])
+    assign = z["init_assignments"]
+    c.del_item(0)
+    c.del_item(1)
+    c.del_item(int(np.where(assign == 0)[0][0]))
+    c.add_item(int(probe[0]), c.K)
+    c.add_item(int(probe[1]), 2)
+    npt.assert_array_equal(c.assignments, z["assignments1"])
+    npt.assert_array_equal(c.counts, z["counts1"])
+    assert c.K == int(z["K1"])
+    npt.assert_array_equal(c.m_N_numerators, z["m_N_numerators1"])
+    npt.assert_array_equal(c.S_N_partials, z["S_N_partials1"])
+    npt.assert_array_equal(c.log_prod_vars, z["log_prod_vars1"])
+    npt.assert_array_equal(c.inv_vars, z["inv_vars1"])
+    npt.assert_array_equal(np.array([c.log_post_pred(int(i)) for i in probe[2:]]), z["post_pred1"])
+    src = so.UniformSource(z["gs_uniforms"])
+    am = so.FBGMM(z["X"], _diag_prior(z), 3., 9, z["init_assignments"].copy(), covariance_type="diag", lms=0.9,
+                  uniform=src)
+    npt.assert_array_equal(am.components.assignments, z["gs_init_assignments"])
+    lm = []
+    for _ in range(2):
+        am.gibbs_sample(1, consider_unassigned=False)
+        lm.append(am.log_marg())
+    assert src.pos == len(z["gs_uniforms"])
+    npt.assert_array_equal(am.components.assignments, z["gs_assignments"])
+    npt.assert_array_equal(am.components.counts, z["gs_counts"])
+    npt.assert_allclose(lm, z["gs_log_marg"], rtol=1e-12)
+    npt.assert_allclose([am.log_marg_i(int(i)) for i in probe], z["gs_log_marg_i"], rtol=1e-13)
+
+
+def test_golden_unigram_diag():
+    """UnigramAcousticWordseg with covariance_type='diag' (BASELINE config 5 family)."""
+    z = G.load("unigram_diag.npz")
+    mats, vids, durs, lms = G.unpack_dicts(z)
+    random.seed(9)
+    np.random.seed(9)
+    src = so.UniformSource(z["uniforms"])
+    seg = so.UnigramAcousticWordseg(
+        so.FBGMM, 5., 8, _diag_prior(z), mats, vids, durs, lms, p_boundary_init=0.5, beta_sent_boundary=-1,
+        n_slices_max=4, lms=1.0, wip=0.0, fb_type="standard", covariance_type="diag", uniform=src)
+    npt.assert_array_equal(seg.utterances.boundaries, z["init_boundaries"])
+    npt.assert_array_equal(seg.acoustic_model.components.assignments, z["init_assignments"])
+    rec = seg.gibbs_sample(3, utt_orders=z["orders"])
+    c = seg.acoustic_model.components
+    assert src.pos == len(z["uniforms"])
+    npt.assert_array_equal(seg.utterances.boundaries, z["boundaries"])
+    npt.assert_array_equal(c.assignments, z["assignments"])
+    npt.assert_array_equal(c.counts, z["counts"])
+    npt.assert_allclose(rec["log_marg"], z["rec_log_marg"], rtol=1e-12)
+    npt.assert_allclose(rec["log_marg*length"], z["rec_log_marg*length"], rtol=1e-12)
+
+
 @pytest.mark.parametrize("init", ["spread", "rand"])
 def test_golden_kmeans_wordseg(init):
     z = G.load("kmeans_wordseg.npz")
