@@ -107,7 +107,19 @@ typedef struct {
     const double *precision_0; /* [D] 1/var_0 */
     double alpha, lms;
     double sum_log_precision_0;/* sum_d log(precision_0[d]) (_cython_utils.sum_log, :228) */
+    /* Component model.  0: fixed variance (fields as named).  1: diagonal covariance with a
+     * normal-inverse-chi-squared prior (gaussian_components_diag.py:82-345, niw.py) -- the same
+     * kernels, with the tables reinterpreted:
+     *   mu_N_numT -> m_N_numerators^T        prec_NT -> S_N_partials^T
+     *   prec_predT -> inv_vars^T             mu_NT   -> m_N = m_N_numerators / (k_0 + n_k)
+     *   log_prod_prec_pred -> log_prod_vars  mu_0 -> m_0   precision_0 -> S_0   precision: unused
+     * and the predictive a product of Student's t densities (:237-259, :347-360).            */
+    int32_t model;
+    int32_t v_0;               /* model 1: prior degrees of freedom (integer, niw.py:12-14) */
+    double k_0;                /* model 1: prior pseudo-count */
 } segb_fixedvar;
+#define SEGB_MODEL_FIXEDVAR 0
+#define SEGB_MODEL_DIAG     1
 
 /* add_item (:153-170) / del_item (:172-188, incl. del_component :190-221) for a
  * list of items, applied strictly in list order by one thread block.

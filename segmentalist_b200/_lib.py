@@ -33,7 +33,8 @@ class FixedVar(ctypes.Structure):
                 ("mu_N_numT", c_vp), ("prec_NT", c_vp), ("prec_predT", c_vp), ("mu_NT", c_vp),
                 ("log_prod_prec_pred", c_vp), ("counts", c_vp), ("assignments", c_vp), ("K", c_vp),
                 ("n_total", c_vp), ("precision", c_vp), ("mu_0", c_vp), ("precision_0", c_vp),
-                ("alpha", c_f64), ("lms", c_f64), ("sum_log_precision_0", c_f64)]
+                ("alpha", c_f64), ("lms", c_f64), ("sum_log_precision_0", c_f64),
+                ("model", c_i32), ("v_0", c_i32), ("k_0", c_f64)]
 
 
 class KMeansM(ctypes.Structure):

@@ -27,16 +27,30 @@ int launch_dp_local(const segb_corpus *c, int32_t utt, const double *local_score
 // Block-cooperative; `tmp` is shared scratch of >= D doubles.
 __device__ void fv_refresh(const segb_fixedvar &m, int k, double *tmp) {
     const int D = m.D, KM = m.K_max;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        const double pN = m.prec_NT[(size_t)d * KM + k];
-        const double pr = m.precision[d];
-        const double pp = __ddiv_rn(__dmul_rn(pN, pr), __dadd_rn(pN, pr));
-        m.prec_predT[(size_t)d * KM + k] = pp;
-        m.mu_NT[(size_t)d * KM + k] = __ddiv_rn(m.mu_N_numT[(size_t)d * KM + k], pN);
-        tmp[d] = log(pp);
+    if (m.model == SEGB_MODEL_DIAG) {
+        // _update_log_prod_vars_and_inv_vars (gaussian_components_diag.py:332-345)
+        const double k_N = m.k_0 + (double)m.counts[k], v_N = (double)(m.v_0 + m.counts[k]);
+        const double f = __ddiv_rn(k_N + 1., __dmul_rn(k_N, v_N));
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const size_t o = (size_t)d * KM + k;
+            const double mN = __ddiv_rn(m.mu_N_numT[o], k_N);
+            const double var = __dmul_rn(f, __dsub_rn(m.prec_NT[o], __dmul_rn(k_N, __dmul_rn(mN, mN))));
+            m.mu_NT[o] = mN;
+            m.prec_predT[o] = __ddiv_rn(1., var);
+            tmp[d] = log(var);
+        }
+    } else {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const double pN = m.prec_NT[(size_t)d * KM + k];
+            const double pr = m.precision[d];
+            const double pp = __ddiv_rn(__dmul_rn(pN, pr), __dadd_rn(pN, pr));
+            m.prec_predT[(size_t)d * KM + k] = pp;
+            m.mu_NT[(size_t)d * KM + k] = __ddiv_rn(m.mu_N_numT[(size_t)d * KM + k], pN);
+            tmp[d] = log(pp);
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0)   // np.log(pp).sum(): NumPy pairwise order
+    if (threadIdx.x == 0)   // np.log(.).sum(): NumPy pairwise order
         m.log_prod_prec_pred[k] = pairwise_sum<double>([&](int i) { return tmp[i]; }, D);
     __syncthreads();
 }
@@ -49,9 +63,18 @@ __device__ void fv_add_item(const segb_fixedvar &m, int id, int k, double *tmp) 
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         const size_t o = (size_t)d * KM + k;
         double num = m.mu_N_numT[o], pN = m.prec_NT[o];
-        if (fresh) { num = __dmul_rn(m.precision_0[d], m.mu_0[d]); pN = m.precision_0[d]; }
-        m.mu_N_numT[o] = __dadd_rn(num, __dmul_rn(m.precision[d], fv_x(m, id, d)));
-        m.prec_NT[o] = __dadd_rn(pN, m.precision[d]);
+        if (m.model == SEGB_MODEL_DIAG) {               // gaussian_components_diag.py:162-177
+            if (fresh) {
+                num = __dmul_rn(m.k_0, m.mu_0[d]);
+                pN = __dadd_rn(m.precision_0[d], __dmul_rn(m.k_0, __dmul_rn(m.mu_0[d], m.mu_0[d])));
+            }
+            m.mu_N_numT[o] = __dadd_rn(num, fv_x(m, id, d));
+            m.prec_NT[o] = __dadd_rn(pN, fv_xsq(m, id, d));
+        } else {
+            if (fresh) { num = __dmul_rn(m.precision_0[d], m.mu_0[d]); pN = m.precision_0[d]; }
+            m.mu_N_numT[o] = __dadd_rn(num, __dmul_rn(m.precision[d], fv_x(m, id, d)));
+            m.prec_NT[o] = __dadd_rn(pN, m.precision[d]);
+        }
     }
     if (threadIdx.x == 0) {
         if (fresh) *m.K = K + 1;
@@ -116,8 +139,13 @@ __device__ void fv_del_item(const segb_fixedvar &m, int id, double *tmp, const i
         const int D = m.D, KM = m.K_max;
         for (int d = threadIdx.x; d < D; d += blockDim.x) {
             const size_t o = (size_t)d * KM + k;
-            m.mu_N_numT[o] = __dsub_rn(m.mu_N_numT[o], __dmul_rn(m.precision[d], fv_x(m, id, d)));
-            m.prec_NT[o] = __dsub_rn(m.prec_NT[o], m.precision[d]);
+            if (m.model == SEGB_MODEL_DIAG) {           // gaussian_components_diag.py:190-193
+                m.mu_N_numT[o] = __dsub_rn(m.mu_N_numT[o], fv_x(m, id, d));
+                m.prec_NT[o] = __dsub_rn(m.prec_NT[o], fv_xsq(m, id, d));
+            } else {
+                m.mu_N_numT[o] = __dsub_rn(m.mu_N_numT[o], __dmul_rn(m.precision[d], fv_x(m, id, d)));
+                m.prec_NT[o] = __dsub_rn(m.prec_NT[o], m.precision[d]);
+            }
         }
         __syncthreads();
         fv_refresh(m, k, tmp);
@@ -130,6 +158,22 @@ __device__ void fv_del_item(const segb_fixedvar &m, int id, double *tmp, const i
 // is a model constant supplied by the host (formed in the reference's sequential order);
 // the quadratic form is reduced across the block.
 __device__ double fv_log_prior_x(const segb_fixedvar &m, const double *xs, double *red) {
+    if (m.model == SEGB_MODEL_DIAG) {
+        // gaussian_components_diag.py:216-223 via _log_prod_students_t (:347-360)
+        const double f = (m.k_0 + 1.) / (m.k_0 * m.v_0), iv = 1. / m.v_0;
+        double acc = 0.0, lpv = 0.0;
+        for (int d = threadIdx.x; d < m.D; d += blockDim.x) {
+            const double var = f * m.precision_0[d];
+            const double dl = xs[d] - m.mu_0[d];
+            lpv += log(var);
+            acc += log(1. + iv * (dl * dl) * (1. / var));
+        }
+        acc = block_sum(acc, red);
+        lpv = block_sum(lpv, red);
+        double cst, hv, iv2;
+        diag_consts(m, 0, cst, hv, iv2);
+        return cst - 0.5 * lpv - hv * acc;
+    }
     double sq = 0.0;
     for (int d = threadIdx.x; d < m.D; d += blockDim.x) {
         const double dl = xs[d] - m.mu_0[d];
@@ -146,6 +190,17 @@ __device__ void fv_post_pred_all(const segb_fixedvar &m, const double *xs, doubl
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         double acc = 0.0;
         const double *mu = m.mu_NT + k, *pp = m.prec_predT + k;
+        if (m.model == SEGB_MODEL_DIAG) {               // gaussian_components_diag.py:237-259
+            double cst, hv, iv;
+            diag_consts(m, m.counts[k], cst, hv, iv);
+#pragma unroll 2
+            for (int d = 0; d < D; ++d) {
+                const double dl = mu[(size_t)d * KM] - xs[d];
+                acc += log(1. + (dl * dl) * pp[(size_t)d * KM] * iv);
+            }
+            sk[k] = cst - 0.5 * m.log_prod_prec_pred[k] - hv * acc;
+            continue;
+        }
 #pragma unroll 4
         for (int d = 0; d < D; ++d) {
             const double dl = mu[(size_t)d * KM] - xs[d];

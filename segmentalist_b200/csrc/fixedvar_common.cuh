@@ -12,6 +12,23 @@ __device__ __forceinline__ double fv_x(const segb_fixedvar &m, int64_t id, int d
 // -0.5*D*log(2*pi) exactly as the reference forms it (:123): one product of three factors
 __device__ __forceinline__ double fv_norm_const(int D) { return -0.5 * D * log(2. * 3.14159265358979323846); }
 
+// x*x exactly as the reference caches it for the diagonal model: np.square(X) keeps X's dtype
+// (gaussian_components_diag.py:122-123), so float32 embeddings are squared in float32.
+__device__ __forceinline__ double fv_xsq(const segb_fixedvar &m, int64_t id, int d) {
+    if (m.x_is_f64) { const double v = ((const double *)m.X)[id * m.D + d]; return __dmul_rn(v, v); }
+    const float v = ((const float *)m.X)[id * m.D + d];
+    return (double)__fmul_rn(v, v);
+}
+
+// Diagonal model: per-component constants of the Student's t predictive for n members
+// (:237-259): D*(gammaln((v+1)/2) - gammaln(v/2) - log(v)/2 - log(pi)/2), (v+1)/2 and 1/v, v = v_0+n.
+__device__ __forceinline__ void diag_consts(const segb_fixedvar &m, int n, double &cst, double &hv, double &iv) {
+    const double v = (double)(m.v_0 + n);
+    cst = m.D * (lgamma((v + 1.) / 2.) - lgamma(v / 2.) - 0.5 * log(v) - 0.5 * log(3.14159265358979323846));
+    hv = (v + 1.) / 2.;
+    iv = 1. / v;
+}
+
 // Shared-memory layout for the scoring kernels: xs[D] | red[40] | sk[K_max]
 struct ScoreSmem {
     double *xs, *red, *sk;

@@ -89,6 +89,7 @@ struct GibbsSmem {
     double *mu, *pp, *num, *pN;    // [per][D] statistics of the owned components
     double *lpp;                   // [per] log_prod_precision_pred
     double *pl;                    // [per] log(alpha/K_max + count)  (refreshed when counts change)
+    double *cst, *hv, *iv;         // [per] diagonal model: Student's t constants for the slot's count (diag_consts)
     double *xs;                    // [xb][D] staged embeddings
     double *vt;                    // [xb][per] scores of the staged batch against the owned components
     double *red;                   // [40]
@@ -104,16 +105,20 @@ struct GibbsSmem {
 };
 
 __host__ __device__ inline size_t gibbs_smem_bytes(int D, int K_max, int per, int xb, int M_cap, int N_cap) {
-    size_t d = (size_t)4 * per * D + 2 * per + (size_t)xb * D + (size_t)xb * per + 40 + K_max + M_cap + (N_cap + 1) + D + (3 * D + 1);
+    size_t d = (size_t)4 * per * D + 5 * per + (size_t)xb * D + (size_t)xb * per + 40 + K_max + M_cap + (N_cap + 1) + D + (3 * D + 1);
     return d * 8 + (size_t)K_max * 4 + (size_t)N_cap * 8 + ((N_cap + 15) / 16) * 16 + 64;
 }
 
-// predictive quadratic form sum_d ((mu_d - x_d)^2 * pp_d) in NumPy's pairwise order (:247-252)
-__device__ __forceinline__ double quad_form(const double *mu, const double *pp, const double *x, int D) {
-    return pairwise_sum<double>([&](int d) {
-        const double dl = __dsub_rn(mu[d], x[d]);
-        return __dmul_rn(__dmul_rn(dl, dl), pp[d]);
-    }, D);
+// per-dimension term of the predictive sum: fixed variance ((mu-x)^2 * prec_pred, :247-252) or
+// diagonal (log(1 + (m-x)^2 * inv_var / v), gaussian_components_diag.py:255-258)
+__device__ __forceinline__ double pred_term(bool diag, double mu, double pp, double x, double iv) {
+    const double dl = __dsub_rn(mu, x);
+    const double q = __dmul_rn(__dmul_rn(dl, dl), pp);
+    return diag ? log(__dadd_rn(1., __dmul_rn(q, iv))) : q;
+}
+// predictive log-density from the summed terms
+__device__ __forceinline__ double pred_value(bool diag, double acc, double c0, double lpp, double cst, double hv) {
+    return diag ? ((cst - 0.5 * lpp) - hv * acc) : ((c0 + 0.5 * lpp) - 0.5 * acc);
 }
 
 __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) {
@@ -133,6 +138,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         s.pN = q; q += (size_t)per * D;
         s.lpp = q; q += per;
         s.pl = q; q += per;
+        s.cst = q; q += per; s.hv = q; q += per; s.iv = q; q += per;
         s.xs = q; q += (size_t)xb * D;
         s.vt = q; q += (size_t)xb * per;
         s.red = q; q += 40;
@@ -163,6 +169,30 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     long long u_pos = p.u_counter ? *p.u_counter : 0;
     const double c0 = fv_norm_const(D);
     const double log_empty = log(m.alpha / KM + 0.);
+    const bool diag = (m.model == SEGB_MODEL_DIAG);
+    // diagonal model: prior predictive = Student's t with var_0 = (k_0+1)/(k_0 v_0) S_0 (:216-223)
+    double d_cst0 = 0., d_hv0 = 0., d_iv0 = 0., d_f0 = 0., d_lpv0 = 0.;
+    if (diag) {
+        diag_consts(m, 0, d_cst0, d_hv0, d_iv0);
+        d_f0 = (m.k_0 + 1.) / (m.k_0 * m.v_0);
+        d_lpv0 = pairwise_sum<double>([&](int d) { return log(d_f0 * m.precision_0[d]); }, D);
+    }
+    // log_prior(x) for the embedding staged at xrow, by one warp (same bits on every CTA)
+    auto warp_log_prior = [&](const double *xrow) -> double {
+        double acc = 0.0;
+        for (int d = lane; d < D; d += 32) {
+            const double dl = xrow[d] - m.mu_0[d];
+            acc += diag ? log(1. + d_iv0 * (dl * dl) * (1. / (d_f0 * m.precision_0[d]))) : dl * dl * m.precision_0[d];
+        }
+        acc = warp_sum(acc);
+        return diag ? (d_cst0 - 0.5 * d_lpv0 - d_hv0 * acc) : (c0 + 0.5 * m.sum_log_precision_0 - 0.5 * acc);
+    };
+    // count-dependent constants of owned slot kl
+    auto slot_consts = [&](int kl) {
+        const int n = s.counts[k_lo + kl];
+        s.pl[kl] = log(m.alpha / KM + (double)n);
+        if (diag) diag_consts(m, n, s.cst[kl], s.hv[kl], s.iv[kl]);
+    };
     unsigned tok_parity = 0;
     __syncthreads();
 
@@ -170,13 +200,24 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     // component through to the global tables (:317-325)
     auto refresh_and_publish = [&](int kl) {
         const int k = k_lo + kl;
+        const double k_N = m.k_0 + (double)s.counts[k], v_N = (double)(m.v_0 + s.counts[k]);
+        const double f = diag ? __ddiv_rn(k_N + 1., __dmul_rn(k_N, v_N)) : 0.;
         for (int d = tid; d < D; d += GB_THREADS) {
-            const double pNv = s.pN[kl * D + d], pr = m.precision[d];
-            const double ppv = __ddiv_rn(__dmul_rn(pNv, pr), __dadd_rn(pNv, pr));
-            const double muv = __ddiv_rn(s.num[kl * D + d], pNv);
+            const double pNv = s.pN[kl * D + d];
+            double ppv, muv;
+            if (diag) {                                  // gaussian_components_diag.py:332-345
+                muv = __ddiv_rn(s.num[kl * D + d], k_N);
+                const double var = __dmul_rn(f, __dsub_rn(pNv, __dmul_rn(k_N, __dmul_rn(muv, muv))));
+                ppv = __ddiv_rn(1., var);
+                s.tmp[d] = log(var);
+            } else {
+                const double pr = m.precision[d];
+                ppv = __ddiv_rn(__dmul_rn(pNv, pr), __dadd_rn(pNv, pr));
+                muv = __ddiv_rn(s.num[kl * D + d], pNv);
+                s.tmp[d] = log(ppv);
+            }
             s.pp[kl * D + d] = ppv;
             s.mu[kl * D + d] = muv;
-            s.tmp[d] = log(ppv);
             const size_t o = (size_t)d * KM + k;
             m.mu_N_numT[o] = s.num[kl * D + d]; m.prec_NT[o] = pNv; m.prec_predT[o] = ppv; m.mu_NT[o] = muv;
         }
@@ -217,9 +258,14 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             if (own) {
                 const int kl = k - k_lo;
                 for (int d = tid; d < D; d += GB_THREADS) {
-                    const double pr = m.precision[d];
-                    s.num[kl * D + d] = __dsub_rn(s.num[kl * D + d], __dmul_rn(pr, fv_x(m, id, d)));
-                    s.pN[kl * D + d] = __dsub_rn(s.pN[kl * D + d], pr);
+                    if (diag) {                              // gaussian_components_diag.py:190-193
+                        s.num[kl * D + d] = __dsub_rn(s.num[kl * D + d], fv_x(m, id, d));
+                        s.pN[kl * D + d] = __dsub_rn(s.pN[kl * D + d], fv_xsq(m, id, d));
+                    } else {
+                        const double pr = m.precision[d];
+                        s.num[kl * D + d] = __dsub_rn(s.num[kl * D + d], __dmul_rn(pr, fv_x(m, id, d)));
+                        s.pN[kl * D + d] = __dsub_rn(s.pN[kl * D + d], pr);
+                    }
                 }
                 __syncthreads();
                 refresh_and_publish(kl);
@@ -293,14 +339,12 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             double val;
             if (kl < na) {
                 const double *mu = s.mu + kl * D, *pp = s.pp + kl * D;
-                auto term = [&](int d) {
-                    const double dl = __dsub_rn(mu[d], s.xs[d]);
-                    return __dmul_rn(__dmul_rn(dl, dl), pp[d]);
-                };
+                const double iv = diag ? s.iv[kl] : 0.;
+                auto term = [&](int d) { return pred_term(diag, mu[d], pp[d], s.xs[d], iv); };
                 const double acc = (D <= 256) ? pairwise_sum_lanes16<double>(term, D, hmask, jl)
                                               : pairwise_sum<double>(term, D);
                 const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
-                val = prior + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
+                val = prior + pred_value(diag, acc, c0, s.lpp[kl], diag ? s.cst[kl] : 0., diag ? s.hv[kl] : 0.);
             } else {
                 val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + x_prior;
             }
@@ -330,6 +374,15 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         for (int d = tid; d < D; d += GB_THREADS) {
             if (restore) { s.num[kl * D + d] = s.bk[d]; s.pN[kl * D + d] = s.bk[D + d]; continue; }
             double nu = s.num[kl * D + d], pNv = s.pN[kl * D + d];
+            if (diag) {                                  // gaussian_components_diag.py:162-177
+                if (fresh) {
+                    nu = __dmul_rn(m.k_0, m.mu_0[d]);
+                    pNv = __dadd_rn(m.precision_0[d], __dmul_rn(m.k_0, __dmul_rn(m.mu_0[d], m.mu_0[d])));
+                }
+                s.num[kl * D + d] = __dadd_rn(nu, s.xs[d]);
+                s.pN[kl * D + d] = __dadd_rn(pNv, fv_xsq(m, id, d));
+                continue;
+            }
             if (fresh) { nu = __dmul_rn(m.precision_0[d], m.mu_0[d]); pNv = m.precision_0[d]; }
             s.num[kl * D + d] = __dadd_rn(nu, __dmul_rn(m.precision[d], s.xs[d]));
             s.pN[kl * D + d] = __dadd_rn(pNv, m.precision[d]);
@@ -337,7 +390,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         __syncthreads();
         if (tid == 0) {
             m.assignments[id] = k_sel;
-            s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_sel]);
+            slot_consts(kl);
         }
         refresh_and_publish(kl);
         if (restore) {       // cached precision_pred / log_prod_precision_pred go back bit for bit
@@ -372,16 +425,11 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             }
             for (int d = tid; d < D; d += GB_THREADS) s.xs[d] = fv_x(m, id, d);
             __syncthreads();
-            if (warp == 0) {                                            // log_prior(x) (:224-231), same bits on every CTA
-                double sq = 0.0;
-                for (int d = lane; d < D; d += 32) {
-                    const double dl = s.xs[d] - m.mu_0[d];
-                    sq += dl * dl * m.precision_0[d];
-                }
-                sq = warp_sum(sq);
-                if (lane == 0) s.red[39] = c0 + 0.5 * m.sum_log_precision_0 - 0.5 * sq;
+            if (warp == 0) {                                            // log_prior(x), same bits on every CTA
+                const double lp = warp_log_prior(s.xs);
+                if (lane == 0) s.red[39] = lp;
             }
-            for (int kl = tid; kl < n_own; kl += GB_THREADS) s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_lo + kl]);
+            for (int kl = tid; kl < n_own; kl += GB_THREADS) slot_consts(kl);
             __syncthreads();
             const double x_prior = s.red[39];
             assign_one(id, x_prior, (unsigned)it << 8, (k_old >= 0 && K == K_old) ? k_old : -1);
@@ -420,8 +468,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
 
         // ================= score every candidate segment (:474-511, fbgmm.py:256-285)
         const double log_norm = log((double)n_total + m.alpha);
-        for (int kl = tid; kl < n_own; kl += GB_THREADS)
-            s.pl[kl] = log(m.alpha / KM + (double)s.counts[k_lo + kl]);
+        for (int kl = tid; kl < n_own; kl += GB_THREADS) slot_consts(kl);
         __syncthreads();
         const int n_act = max(0, min(K, k_hi) - k_lo);           // owned ACTIVE components
         for (int s0 = 0; s0 < n_slots; s0 += xb) {
@@ -434,8 +481,11 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             __syncthreads();
             for (int i = tid; i < nb * n_act; i += GB_THREADS) {
                 const int bb = i / n_act, kl = i % n_act;
-                const double acc = quad_form(s.mu + kl * D, s.pp + kl * D, s.xs + bb * D, D);
-                s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm) + ((c0 + 0.5 * s.lpp[kl]) - 0.5 * acc);
+                const double *mu = s.mu + kl * D, *pp = s.pp + kl * D, *xr = s.xs + bb * D;
+                const double iv = diag ? s.iv[kl] : 0.;
+                const double acc = pairwise_sum<double>([&](int d) { return pred_term(diag, mu[d], pp[d], xr[d], iv); }, D);
+                s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm)
+                                      + pred_value(diag, acc, c0, s.lpp[kl], diag ? s.cst[kl] : 0., diag ? s.hv[kl] : 0.);
             }
             __syncthreads();
             for (int bb = tid; bb < nb; bb += GB_THREADS) {
@@ -448,13 +498,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             // log_prior of the candidates this CTA will combine (slot % G == b), one warp each
             for (int bb = warp; bb < nb; bb += GB_THREADS / 32) {
                 if ((s0 + bb) % G != b) continue;
-                double sq = 0.0;
-                for (int d = lane; d < D; d += 32) {
-                    const double dl = s.xs[bb * D + d] - m.mu_0[d];
-                    sq += dl * dl * m.precision_0[d];
-                }
-                sq = warp_sum(sq);
-                if (lane == 0) p.seg_prior[s0 + bb] = c0 + 0.5 * m.sum_log_precision_0 - 0.5 * sq;
+                const double lp = warp_log_prior(s.xs + bb * D);
+                if (lane == 0) p.seg_prior[s0 + bb] = lp;
             }
             __syncthreads();
         }

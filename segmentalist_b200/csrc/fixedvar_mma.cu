@@ -339,6 +339,7 @@ extern "C" int segb_fvmma_pack_x(const float *X, int64_t n_emb, int32_t D, void 
 extern "C" int segb_fvmma_log_marg(const segb_fixedvar *m, const void *x_tiles, void *w_tiles, int64_t n_emb,
                                    float *out, void *stream) {
     SEGB_CHECK_ARG(m && x_tiles && w_tiles && out && n_emb > 0, "null pointer");
+    SEGB_CHECK_ARG(m->model == SEGB_MODEL_FIXEDVAR, "the tensor-core log_marg is a GEMM: fixed-variance model only");
     cudaStream_t st = (cudaStream_t)stream;
     const int D = m->D, krp = k_rows_pad(m->K_max);
     const int wpb = 8;

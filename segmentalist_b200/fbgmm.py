@@ -47,8 +47,13 @@ class FBGMM(object):
         elif isinstance(assignments, str) and assignments == "each-in-own":
             assignments = np.arange(N)
         assignments = make_consecutive(np.asarray(assignments))
+        if self.covariance_type == "diag":                                   # fbgmm.py:130-137
+            from .gaussian_components_diag import GaussianComponentsDiag
+            self.components = GaussianComponentsDiag(X, self.prior, assignments, K_max=K,
+                                                     alpha=self.alpha, lms=self.lms)
+            return
         assert self.covariance_type == "fixed", (
-            "only covariance_type='fixed' is implemented on the B200 path (see DESIGN.md, out of scope)")
+            "covariance_type 'fixed' and 'diag' are implemented on the B200 path (full covariance: DESIGN.md 7)")
         self.components = GaussianComponentsFixedVar(X, self.prior, assignments, K_max=K,
                                                      alpha=self.alpha, lms=self.lms)
 

@@ -105,6 +105,11 @@ class GaussianComponentsFixedVar(object):
 
     # ---- C-ABI plumbing
     def struct(self):
+        m = self.struct_base()
+        m.sum_log_precision_0 = _sum_log_sequential(self.precision_0)
+        return m
+
+    def struct_base(self):
         m = _lib.FixedVar()
         m.D, m.K_max, m.x_is_f64, m.n_emb = self.D, self.K_max, int(self._X.dtype == torch.float64), self.N
         m.X = self._X.data_ptr()
@@ -116,7 +121,6 @@ class GaussianComponentsFixedVar(object):
         m.precision, m.mu_0, m.precision_0 = (self._precision.data_ptr(), self._mu_0.data_ptr(),
                                               self._precision_0.data_ptr())
         m.alpha, m.lms = self._alpha, self._lms
-        m.sum_log_precision_0 = _sum_log_sequential(self.precision_0)
         return m
 
     def _add_many(self, ids, ks):

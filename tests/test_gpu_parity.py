@@ -363,6 +363,76 @@ def test_unigram_with_am_resampling_golden(sb):
     npt.assert_allclose(rec["log_marg*length"], z["rec_log_marg*length"], rtol=1e-10)
 
 
+def _niw(z):
+    from segmentalist_b200.niw import NIW
+    return NIW(m_0=z["m_0"], k_0=float(z["k_0"]), v_0=int(z["v_0"]), S_0=z["S_0"])
+
+
+def test_diag_components_golden(sb):
+    """Diagonal-covariance components on the device == the reference's GaussianComponentsDiag:
+    Student's t predictive scores, statistics after add/del incl. a component deletion, log_marg,
+    and whole-model Gibbs sampling under the recorded uniforms (tests/golden/diag_components.npz)."""
+    from segmentalist_b200 import fbgmm
+    from segmentalist_b200.gaussian_components_diag import GaussianComponentsDiag
+    z = G.load("diag_components.npz")
+    c = GaussianComponentsDiag(z["X"], _niw(z), z["init_assignments"].copy(), K_max=9)
+    probe = z["probe"]
+    npt.assert_allclose(np.array([c.log_post_pred(int(i)) for i in probe]), z["post_pred0"], rtol=1e-10)
+    npt.assert_allclose(np.array([c.log_prior(int(i)) for i in probe]), z["prior0"], rtol=1e-10)
+    npt.assert_allclose(c.log_marg(), float(z["log_marg0"]), rtol=1e-10)
+    assign = z["init_assignments"]
+    c.del_item(0)
+    c.del_item(1)                                      # deletes the last component
+    c.del_item(int(np.where(assign == 0)[0][0]))
+    c.add_item(int(probe[0]), c.K)
+    c.add_item(int(probe[1]), 2)
+    npt.assert_array_equal(c.assignments, z["assignments1"])
+    npt.assert_array_equal(c.counts, z["counts1"])
+    assert c.K == int(z["K1"])
+    npt.assert_allclose(c.m_N_numerators, z["m_N_numerators1"], rtol=1e-13, atol=1e-13)
+    npt.assert_allclose(c.S_N_partials, z["S_N_partials1"], rtol=1e-13, atol=1e-13)
+    npt.assert_allclose(c.log_prod_vars, z["log_prod_vars1"], rtol=1e-11)
+    npt.assert_allclose(c.inv_vars, z["inv_vars1"], rtol=1e-10)
+    npt.assert_allclose(np.array([c.log_post_pred(int(i)) for i in probe[2:]]), z["post_pred1"], rtol=1e-10)
+    npt.assert_allclose(c.log_marg(), float(z["log_marg1"]), rtol=1e-10)
+    # whole-model Gibbs (cooperative item sweep, diagonal model)
+    random.seed(8)
+    np.random.seed(8)
+    am = fbgmm.FBGMM(z["X"], _niw(z), 3., 9, z["init_assignments"].copy(), covariance_type="diag", lms=0.9)
+    npt.assert_array_equal(am.components.assignments, z["gs_init_assignments"])
+    rec = am.gibbs_sample(2, consider_unassigned=False)
+    npt.assert_array_equal(am.components.assignments, z["gs_assignments"])
+    npt.assert_array_equal(am.components.counts, z["gs_counts"])
+    assert am.components.K == int(z["gs_K"])
+    npt.assert_allclose(rec["log_marg"], z["gs_log_marg"], rtol=1e-10)
+    npt.assert_allclose(am.components.m_N_numerators, z["gs_m_N_numerators"], rtol=1e-12, atol=1e-12)
+    npt.assert_allclose([am.log_marg_i(int(i)) for i in probe], z["gs_log_marg_i"], rtol=1e-10)
+
+
+def test_unigram_diag_golden(sb):
+    """UnigramAcousticWordseg with covariance_type='diag' (BASELINE config 5 family): identical
+    segmentations and assignments to the reference under the same random stream."""
+    from segmentalist_b200 import fbgmm, unigram_acoustic_wordseg as uaw
+    z = G.load("unigram_diag.npz")
+    mats, vids, durs, lms = G.unpack_dicts(z)
+    random.seed(9)
+    np.random.seed(9)
+    seg = uaw.UnigramAcousticWordseg(
+        fbgmm.FBGMM, 5., 8, _niw(z), mats, vids, durs, lms, p_boundary_init=0.5, beta_sent_boundary=-1,
+        n_slices_max=4, lms=1.0, wip=0.0, fb_type="standard", covariance_type="diag")
+    npt.assert_array_equal(seg.utterances.boundaries, z["init_boundaries"])
+    c = seg.acoustic_model.components
+    npt.assert_array_equal(c.assignments, z["init_assignments"])
+    rec = seg.gibbs_sample(3)
+    npt.assert_array_equal(seg.utterances.boundaries, z["boundaries"])
+    npt.assert_array_equal(c.assignments, z["assignments"])
+    npt.assert_array_equal(c.counts, z["counts"])
+    assert c.K == int(z["K"])
+    npt.assert_allclose(rec["log_marg"], z["rec_log_marg"], rtol=1e-10)
+    npt.assert_allclose(rec["log_marg*length"], z["rec_log_marg*length"], rtol=1e-10)
+    npt.assert_allclose(rec["log_prob_z"], z["rec_log_prob_z"], rtol=1e-10)
+
+
 @pytest.mark.parametrize("init", ["spread", "rand"])
 def test_kmeans_wordseg_golden(sb, init):
     """BASELINE config 1: sequential segment() and the frozen sweep vs the reference."""
