@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--no-gibbs", action="store_true", help="skip the secondary workload (BASELINE configs[1])")
     ap.add_argument("--gibbs-utts", type=int, default=2000)
     ap.add_argument("--only-gibbs", action="store_true", help="run only the secondary Gibbs workload")
+    ap.add_argument("--diag-utts", type=int, default=48)
+    ap.add_argument("--only-diag", action="store_true", help="run only the diagonal-covariance secondary workload")
     return ap.parse_args()
 
 
@@ -358,6 +360,60 @@ def run_gibbs_extra(args):
     return out
 
 
+def run_diag_extra(args):
+    """BASELINE configs[4]: diagonal-covariance FBGMM unigram segmentation, D=130, K_max=5000, long
+    utterances (100-120 landmarks), one cooperative Gibbs sweep through the reference-facing API; CPU
+    oracle timed on the first utterances of the same seeded corpus (also a parity check)."""
+    import random
+
+    import torch
+    from oracle import seg_oracle as so
+    from segmentalist_b200 import fbgmm, synth, unigram_acoustic_wordseg as uaw
+    from segmentalist_b200.niw import NIW
+    K, n_utt = 5000, args.diag_utts
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=400, n_min=100, n_max=120,
+                                                    n_slices_max=S_MAX, noise=NOISE, seed=53)
+    prior_args = dict(m_0=np.zeros(D), k_0=0.05, v_0=D + 3, S_0=0.002 * np.ones(D))
+
+    def build(mod, am_mod, prior):
+        random.seed(5)
+        np.random.seed(5)
+        return mod.UnigramAcousticWordseg(am_mod.FBGMM, 10., K, prior, mats, vids, durs, lms, p_boundary_init=0.5,
+                                          beta_sent_boundary=-1, n_slices_max=S_MAX, covariance_type="diag")
+    seg = build(uaw, fbgmm, NIW(**prior_args))
+    n_seg = int(sum(m.shape[0] for m in mats.values()))
+    order = list(range(n_utt))
+    seg._sweep(order, 1, False)                       # warm-up sweep
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    seg._sweep(order, 1, False)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    K_act = seg.acoustic_model.components.K
+    out = {"workload": "unigram_fbgmm_diag_gibbs_sweep D=130 K_max=5000 U=%d N~U{100..120} max_span=6 (BASELINE configs[4])" % n_utt,
+           "utt_per_s": n_utt / wall, "ms_per_sweep": wall * 1e3, "candidate_segments": n_seg, "K_active": K_act,
+           "student_t_log_evals_per_s": n_seg * float(K_act) * D / wall, "dtype": "f64",
+           "note": "K_active < K_max: %d tokens cannot populate 5000 components; evals counted over active components" % seg.acoustic_model.get_n_assigned()}
+    if not args.no_cpu:
+        n_cpu = 2
+        oseg = build(so, so, so.NIW(**prior_args))
+        gseg = build(uaw, fbgmm, NIW(**prior_args))
+        st = random.getstate()
+        t0 = time.perf_counter()
+        for u in range(n_cpu):
+            oseg.gibbs_sample_i(u)
+        dt = time.perf_counter() - t0
+        random.setstate(st)
+        gseg._sweep(list(range(n_cpu)), 1, False)
+        same = bool(np.array_equal(gseg.utterances.boundaries[:n_cpu], oseg.utterances.boundaries[:n_cpu]) and
+                    np.array_equal(gseg.acoustic_model.components.assignments,
+                                   oseg.acoustic_model.components.assignments))
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "utt/s", "cores": 1, "kind": "port",
+                               "sample": "%d gibbs_sample_i calls of the same seeded corpus/model" % n_cpu,
+                               "seconds": dt, "identical_samples_on_sample": same}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -600,12 +656,16 @@ def run_ours(args):
                                   "oracle port of the reference's pure functions" % (n_s, int((ids >= 0).sum()), args.K),
                         "seconds": dt, "parity_with_gpu_on_sample": parity}
 
-    gibbs = None
+    gibbs, diag_x = None, None
     if rank == 0 and world == 1 and not args.no_gibbs:
         try:
             gibbs = run_gibbs_extra(args)
         except Exception as exc:                      # the headline line must still be printed
             gibbs = {"error": repr(exc)}
+        try:
+            diag_x = run_diag_extra(args)
+        except Exception as exc:
+            diag_x = {"error": repr(exc)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
@@ -622,7 +682,7 @@ def run_ours(args):
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "roofline_dp": roofline_dp, "roofline_fixedvar_logmarg": roofline_fv, "cpu_baseline": cpu_baseline, "phases_ms": phases,
-            "secondary_gibbs_fixedvar": gibbs,
+            "secondary_gibbs_fixedvar": gibbs, "secondary_gibbs_diag": diag_x,
         }
         print(json.dumps(line))
     if world > 1:
@@ -635,6 +695,8 @@ def main():
         run_reference_arm(args)
     elif args.only_gibbs:
         print(json.dumps({"secondary_gibbs_fixedvar": run_gibbs_extra(args)}))
+    elif args.only_diag:
+        print(json.dumps({"secondary_gibbs_diag": run_diag_extra(args)}))
     else:
         run_ours(args)
 

@@ -11,8 +11,8 @@
 // Collapsed Gibbs is sequential -- every assignment sees the statistics left by the previous
 // one -- so the sweep is latency-bound, and the version that launches four kernels per
 // utterance (fixedvar.cu) spends its time pulling the [D, K_max] tables through ONE SM for every
-// token.  Here ONE cooperative launch runs the whole sweep: CTA b owns components
-// [b*per, (b+1)*per) and keeps their statistics in shared memory; every step is a short local
+// token.  Here ONE cooperative launch runs the whole sweep: CTA b owns the components k with
+// k % G == b (so the active ones are spread evenly) and keeps their statistics in shared memory; every step is a short local
 // computation followed by a grid barrier:
 //   remove   owner-local updates; the small replicated state (counts, K, n_total) is advanced
 //            identically by every CTA, so no communication unless a component dies (then the
@@ -127,7 +127,14 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     const segb_corpus &c = p.c;
     const int D = m.D, KM = m.K_max, per = p.per, xb = p.xb, S = c.S;
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k_lo = min(b * per, KM), k_hi = min(k_lo + per, KM), n_own = k_hi - k_lo;
+    // component k lives on CTA k % G as local slot k / G: the ACTIVE components 0..K-1 are spread
+    // evenly over the grid whatever K is (a contiguous split would leave most CTAs idle when
+    // K << K_max); every CTA's active slots are its first n_act(K) local slots
+    const int n_own = (b < KM) ? (KM - b + G - 1) / G : 0;
+    auto own_of = [&](int k) { return (k % G) == b; };
+    auto kl_of = [&](int k) { return k / G; };
+    auto k_of = [&](int kl) { return b + kl * G; };
+    auto n_act_of = [&](int K_) { return (K_ > b) ? min(n_own, (K_ - b + G - 1) / G) : 0; };
 
     GibbsSmem s;
     {
@@ -158,11 +165,11 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     // ---- load the owned statistics and the replicated state
     for (int i = tid; i < n_own * D; i += GB_THREADS) {
         const int kl = i / D, d = i % D;
-        const size_t o = (size_t)d * KM + (k_lo + kl);
+        const size_t o = (size_t)d * KM + k_of(kl);
         s.mu[kl * D + d] = m.mu_NT[o]; s.pp[kl * D + d] = m.prec_predT[o];
         s.num[kl * D + d] = m.mu_N_numT[o]; s.pN[kl * D + d] = m.prec_NT[o];
     }
-    for (int kl = tid; kl < n_own; kl += GB_THREADS) s.lpp[kl] = m.log_prod_prec_pred[k_lo + kl];
+    for (int kl = tid; kl < n_own; kl += GB_THREADS) s.lpp[kl] = m.log_prod_prec_pred[k_of(kl)];
     for (int k = tid; k < KM; k += GB_THREADS) s.counts[k] = m.counts[k];
     int K = *m.K;
     long long n_total = *m.n_total;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     };
     // count-dependent constants of owned slot kl
     auto slot_consts = [&](int kl) {
-        const int n = s.counts[k_lo + kl];
+        const int n = s.counts[k_of(kl)];
         s.pl[kl] = log(m.alpha / KM + (double)n);
         if (diag) diag_consts(m, n, s.cst[kl], s.hv[kl], s.iv[kl]);
     };
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     // refresh precision_pred, mu_N, log_prod_precision_pred of owned slot kl and write the
     // component through to the global tables (:317-325)
     auto refresh_and_publish = [&](int kl) {
-        const int k = k_lo + kl;
+        const int k = k_of(kl);
         const double k_N = m.k_0 + (double)s.counts[k], v_N = (double)(m.v_0 + s.counts[k]);
         const double f = diag ? __ddiv_rn(k_N + 1., __dmul_rn(k_N, v_N)) : 0.;
         for (int d = tid; d < D; d += GB_THREADS) {
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         __syncthreads();
     };
     auto zero_slot = [&](int kl) {
-        const int k = k_lo + kl;
+        const int k = k_of(kl);
         for (int d = tid; d < D; d += GB_THREADS) {
             s.mu[kl * D + d] = 0.; s.pp[kl * D + d] = 0.; s.num[kl * D + d] = 0.; s.pN[kl * D + d] = 0.;
             const size_t o = (size_t)d * KM + k;
@@ -253,10 +260,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         __syncthreads();
         if (tid == 0) s.counts[k] = cnt;
         n_total -= 1;
-        const bool own = (k >= k_lo && k < k_hi);
+        const bool own = own_of(k);
         if (cnt > 0) {
             if (own) {
-                const int kl = k - k_lo;
+                const int kl = kl_of(k);
                 for (int d = tid; d < D; d += GB_THREADS) {
                     if (diag) {                              // gaussian_components_diag.py:190-193
                         s.num[kl * D + d] = __dsub_rn(s.num[kl * D + d], fv_x(m, id, d));
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             grid_barrier(p.bar, G, tag | 0x10);   // every owner's write-through is visible
             if (k != last) {
                 if (own) {
-                    const int kl = k - k_lo;
+                    const int kl = kl_of(k);
                     for (int d = tid; d < D; d += GB_THREADS) {
                         const size_t a = (size_t)d * KM + k, o = (size_t)d * KM + last;
                         const double nu = __ldcg(m.mu_N_numT + o), pNv = __ldcg(m.prec_NT + o), ppv = __ldcg(m.prec_predT + o),
@@ -292,8 +299,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                         m.counts[k] = s.counts[last]; m.counts[last] = 0;
                     }
                 }
-                if (last >= k_lo && last < k_hi) {           // the old home forgets it (global zeroed by the new owner)
-                    const int kl = last - k_lo;
+                if (own_of(last)) {           // the old home forgets it (global zeroed by the new owner)
+                    const int kl = kl_of(last);
                     for (int d = tid; d < D; d += GB_THREADS) {
                         s.mu[kl * D + d] = 0.; s.pp[kl * D + d] = 0.; s.num[kl * D + d] = 0.; s.pN[kl * D + d] = 0.;
                     }
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                 __syncthreads();
                 if (tid == 0) { s.counts[k] = s.counts[last]; s.counts[last] = 0; }
             } else if (own) {
-                zero_slot(k - k_lo);
+                zero_slot(kl_of(k));
             }
             K = last;
             grid_barrier(p.bar, G, tag | 0x20);   // relabelled assignments are visible
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     auto assign_one = [&](int id, double x_prior, unsigned tag, int k_restore) -> int {
     double *vbuf = p.v + (size_t)tok_parity * KM;
     tok_parity ^= 1;
-    const int na = max(0, min(K, k_hi) - k_lo);
+    const int na = n_act_of(K);
     {
         // one half-warp per owned slot (the predictive sum is 130 dependent-latency terms)
         const int hw = tid >> 4, jl = tid & 15;
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             } else {
                 val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + x_prior;
             }
-            if (jl == 0) vbuf[k_lo + kl] = val;
+            if (jl == 0) vbuf[k_of(kl)] = val;
         }
     }
     grid_barrier(p.bar, G, tag | 0x50, (unsigned)(K | ((unsigned)n_total << 8) | ((unsigned)u_pos << 20)));
@@ -369,8 +376,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     if (tid == 0) s.counts[k_sel] += 1;
     if (fresh) K += 1;
     n_total += 1;
-    if (k_sel >= k_lo && k_sel < k_hi) {
-        const int kl = k_sel - k_lo;
+    if (own_of(k_sel)) {
+        const int kl = kl_of(k_sel);
         for (int d = tid; d < D; d += GB_THREADS) {
             if (restore) { s.num[kl * D + d] = s.bk[d]; s.pN[kl * D + d] = s.bk[D + d]; continue; }
             double nu = s.num[kl * D + d], pNv = s.pN[kl * D + d];
@@ -413,8 +420,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             const int K_old = K;
             __syncthreads();
             if (k_old >= 0) {
-                if (k_old >= k_lo && k_old < k_hi) {                    // cache_component_stats (:128-141)
-                    const int kl = k_old - k_lo;
+                if (own_of(k_old)) {                    // cache_component_stats (:128-141)
+                    const int kl = kl_of(k_old);
                     for (int d = tid; d < D; d += GB_THREADS) {
                         s.bk[d] = s.num[kl * D + d]; s.bk[D + d] = s.pN[kl * D + d]; s.bk[2 * D + d] = s.pp[kl * D + d];
                     }
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         const double log_norm = log((double)n_total + m.alpha);
         for (int kl = tid; kl < n_own; kl += GB_THREADS) slot_consts(kl);
         __syncthreads();
-        const int n_act = max(0, min(K, k_hi) - k_lo);           // owned ACTIVE components
+        const int n_act = n_act_of(K);           // owned ACTIVE components
         for (int s0 = 0; s0 < n_slots; s0 += xb) {
             const int nb = min(xb, n_slots - s0);
             for (int i = tid; i < nb * D; i += GB_THREADS) {
