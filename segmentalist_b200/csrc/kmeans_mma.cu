@@ -43,8 +43,11 @@ constexpr int TILE_ROWS = 128;     // rows per operand tile image
 constexpr int MT_ROWS = 256;       // embeddings per CTA work item (two A tiles)
 constexpr int NT_COLS = 128;       // components per accumulator tile
 constexpr int CHUNK = 16;          // components per candidate chunk
-constexpr int MAX_STAGES = 4;
-constexpr int EPI_PARTS = 1;         // column halves of an accumulator tile handled by separate warp sets
+constexpr int PIECE_KSTEPS = 3;                                   // K=16 steps per B ring slot
+constexpr uint32_t KSTEP_BYTES = 2 * (TILE_ROWS / 8) * 128;        // one K=16 step of a 128-row tile image
+constexpr uint32_t PIECE_BYTES = PIECE_KSTEPS * KSTEP_BYTES;
+constexpr int B_RING = 6;
+constexpr int EPI_PARTS = 2;         // column halves of an accumulator tile handled by separate warp sets
 constexpr int N_EPI_WARPS = 8 * EPI_PARTS;
 constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
@@ -95,7 +98,7 @@ struct FilterParams {
     const uint8_t *x_tiles, *w_tiles;
     Cand *cand;
     int64_t n_emb;
-    int32_t n_mtiles, n_ntiles, n_ksteps, n_stages;
+    int32_t n_mtiles, n_ntiles, n_ksteps, n_abuf;
     uint32_t tile_bytes;
     const float *x_max, *w_max;    // [2] each: corpus-wide (max ex, max nx), model-wide (max e_mu, max n_mu)
     int32_t D;
@@ -104,20 +107,26 @@ struct FilterParams {
 // Insert a chunk maximum into the running top-3.  A chunk that becomes the new BEST also records
 // which of its 16 members lie within tau_c of the chunk maximum (the only ones the refine has to
 // score); a chunk entering as runner-up keeps all 16 (it is only visited for the rare rows whose
-// runner-up chunk is inside the bound), which keeps this divergent path short.
+// runner-up chunk is inside the bound).  Only the new-best case is a (divergent) branch; the
+// runner-up / third-place updates are selects, so the common path is straight-line code.
 __device__ __forceinline__ void top3_insert(const float *vv, float cm, int cid, float tau_c, float &m1, float &m2,
                                             float &m3, int &i1, int &i2, uint32_t &k1, uint32_t &k2) {
-    if (cm > m3) {
-        if (cm > m2) {
-            m3 = m2;
-            if (cm > m1) {
-                uint32_t mk = 0;
-                const float thr = cm - tau_c;
+    const bool p2 = cm > m2;
+    m3 = p2 ? m2 : fmaxf(m3, cm);
+    if (cm > m1) {
+        // member j is kept iff vv[j] >= cm - tau_c, i.e. the sign bit of (vv[j] - thr) is clear; the
+        // sign bits are funnel-shifted into two 8-bit chains (member 15 first, so bit j = member j)
+        const float thr = cm - tau_c;
+        uint32_t hi = 0, lo = 0;
 #pragma unroll
-                for (int j = 0; j < CHUNK; ++j) mk |= (vv[j] >= thr) ? (1u << j) : 0u;
-                m2 = m1; i2 = i1; k2 = k1; m1 = cm; i1 = cid; k1 = mk;
-            } else { m2 = cm; i2 = cid; k2 = 0xffffu; }
-        } else m3 = cm;
+        for (int j = 7; j >= 0; --j) {
+            hi = __funnelshift_l(__float_as_uint(vv[8 + j] - thr), hi, 1);
+            lo = __funnelshift_l(__float_as_uint(vv[j] - thr), lo, 1);
+        }
+        m2 = m1; i2 = i1; k2 = k1;
+        m1 = cm; i1 = cid; k1 = ~((hi << 8) | lo) & 0xffffu;
+    } else {
+        m2 = p2 ? cm : m2; i2 = p2 ? cid : i2; k2 = p2 ? 0xffffu : k2;
     }
 }
 
@@ -133,23 +142,29 @@ __device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float
     }
 }
 
+// KS = number of K=16 steps when known at compile time (fully unrolled issue loop), 0 = runtime.
+template <int KS>
 __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tb = p.tile_bytes;
-    uint8_t *sA = smem;                               // 2 tiles
-    uint8_t *sB = smem + 2 * (size_t)tb;              // n_stages tiles
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.n_stages * tb);
-    // barrier slots: 0 a_full, 1 a_empty, 2..5 b_full, 6..9 b_empty, 10..11 acc_full, 12..13 acc_empty
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    const int n_ks = KS > 0 ? KS : p.n_ksteps;
+    const int n_pieces = (n_ks + PIECE_KSTEPS - 1) / PIECE_KSTEPS;
+    uint8_t *sA = smem;                                        // n_abuf x 2 tiles
+    uint8_t *sB = smem + (size_t)p.n_abuf * 2 * tb;            // ring of B_RING pieces
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)B_RING * PIECE_BYTES);
+    // barrier slots: a_full[2], a_empty[2], b_full[B_RING], b_empty[B_RING], acc_full[2], acc_empty[2]
+    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 4 + B_RING, ACC_FULL = 4 + 2 * B_RING,
+                  ACC_EMPTY = ACC_FULL + 2, N_BARS = ACC_EMPTY + 2;
+    static_assert(N_BARS * 8 + 4 <= 256, "barrier block");
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     float4 *merge = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [MT_ROWS][2] partial top-3
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     if (threadIdx.x == 0) {
-        mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
-        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(6 + s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(BAR(10 + b), 1); mbar_init(BAR(12 + b), N_EPI_WARPS); }
+        for (int i = 0; i < ACC_EMPTY; ++i) mbar_init(BAR(i), 1);
+        for (int b = 0; b < 2; ++b) mbar_init(BAR(ACC_EMPTY + b), N_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -165,60 +180,117 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t a_phase = 0, b_phase = 0;
-            int s = 0;
-            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
-                mbar_wait(BAR(1), a_phase ^ 1);
-                mbar_expect_tx(BAR(0), 2 * tb);
-                bulk_g2s(smem_u32(sA), p.x_tiles + (size_t)(2 * mt) * tb, tb, BAR(0));
-                bulk_g2s(smem_u32(sA + tb), p.x_tiles + (size_t)(2 * mt + 1) * tb, tb, BAR(0));
-                a_phase ^= 1;
+        // A (256 embeddings) is double-buffered: the next work item's tiles are requested while the
+        // current one is still being multiplied, so the tensor pipe does not drain at work-item
+        // boundaries.  B streams through a ring of K-slices ("pieces" of PIECE_KSTEPS K=16 steps of one
+        // 128-component tile, contiguous in the tile image), finer than whole tiles so that the ring
+        // gives > 1.5 tiles of look-ahead in the shared memory left over.
+        if (elect_one()) {
+            auto load_a = [&](int it, int mt) {
+                const int ab = p.n_abuf == 2 ? (it & 1) : 0;
+                const uint32_t use = p.n_abuf == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+                mbar_wait(BAR(A_EMPTY + ab), (use & 1) ^ 1);
+                mbar_expect_tx(BAR(A_FULL + ab), 2 * tb);
+                bulk_g2s(smem_u32(sA + (size_t)(2 * ab) * tb), p.x_tiles + (size_t)(2 * mt) * tb, tb, BAR(A_FULL + ab));
+                bulk_g2s(smem_u32(sA + (size_t)(2 * ab + 1) * tb), p.x_tiles + (size_t)(2 * mt + 1) * tb, tb, BAR(A_FULL + ab));
+            };
+            uint32_t b_phase = 0;
+            int s = 0, it = 0;
+            if ((int)blockIdx.x < p.n_mtiles) load_a(0, blockIdx.x);
+            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
+                const int mt_next = mt + gridDim.x;
+                const int nt_pref = p.n_abuf == 2 ? (p.n_ntiles > 4 ? 4 : p.n_ntiles - 1) : -1;
                 for (int nt = 0; nt < p.n_ntiles; ++nt) {
-                    mbar_wait(BAR(6 + s), b_phase ^ 1);
-                    mbar_expect_tx(BAR(2 + s), tb);
-                    bulk_g2s(smem_u32(sB + (size_t)s * tb), p.w_tiles + (size_t)nt * tb, tb, BAR(2 + s));
-                    if (++s == p.n_stages) { s = 0; b_phase ^= 1; }
+                    if (nt == nt_pref && mt_next < p.n_mtiles) load_a(it + 1, mt_next);
+                    const uint8_t *src = p.w_tiles + (size_t)nt * tb;
+                    for (int j = 0; j < n_pieces; ++j) {
+                        const int ks_here = (n_ks - j * PIECE_KSTEPS) < PIECE_KSTEPS ? (n_ks - j * PIECE_KSTEPS) : PIECE_KSTEPS;
+                        const uint32_t bytes = (uint32_t)ks_here * KSTEP_BYTES;
+                        mbar_wait(BAR(B_EMPTY + s), b_phase ^ 1);
+                        mbar_expect_tx(BAR(B_FULL + s), bytes);
+                        bulk_g2s(smem_u32(sB + (size_t)s * PIECE_BYTES), src + (size_t)j * PIECE_BYTES, bytes, BAR(B_FULL + s));
+                        if (++s == B_RING) { s = 0; b_phase ^= 1; }
+                    }
                 }
+                if (p.n_abuf == 1 && mt_next < p.n_mtiles) load_a(it + 1, mt_next);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The issue loop is the kernel's pacemaker: one M=128 N=128 K=16 MMA occupies the tensor pipe
+        // for 64 clocks, so the elected thread has to issue one every < 64 clocks.  Descriptors are
+        // therefore kept as 32-bit low words advanced by a constant per K step, the K loop is unrolled
+        // at compile time, and the issuer is chosen with elect.sync (see elect_one()).  The two row
+        // halves alternate per K step, so a B slice is released as soon as both have consumed it.
+        if (elect_one()) {
             const uint32_t idesc = make_idesc();
-            const uint32_t kstep_bytes = 2 * (TILE_ROWS / 8) * 128;       // two K chunks per K=16 step
-            uint32_t a_phase = 0, b_phase = 0, n_use = 0;
-            int s = 0;
-            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
-                mbar_wait(BAR(0), a_phase);
-                a_phase ^= 1;
+            constexpr uint32_t KSTEP = KSTEP_BYTES >> 4;              // descriptor units per K=16 step
+            const uint32_t a_lo_base = make_desc_lo(smem_u32(sA), TILE_ROWS);
+            const uint32_t b_lo_base = make_desc_lo(smem_u32(sB), TILE_ROWS);
+            uint32_t b_phase = 0, n_use = 0;
+            int s = 0, it = 0;
+            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
+                const int ab = p.n_abuf == 2 ? (it & 1) : 0;
+                const uint32_t use = p.n_abuf == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+                mbar_wait(BAR(A_FULL + ab), use & 1);
+                const uint32_t a_lo0 = a_lo_base + (uint32_t)(2 * ab) * (tb >> 4), a_lo1 = a_lo0 + (tb >> 4);
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                    mbar_wait(BAR(2 + s), b_phase);
-                    mbar_wait(BAR(12 + buf), acc_phase ^ 1);
+                    mbar_wait(BAR(ACC_EMPTY + buf), acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + (size_t)s * tb);
-#pragma unroll 1
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t a_addr = smem_u32(sA + (size_t)h * tb);
-                        const uint32_t d_tmem = tmem_base + (buf * 2 + h) * NT_COLS;
-                        for (int k = 0; k < p.n_ksteps; ++k)
-                            tc_mma_f16(d_tmem, make_desc(a_addr + k * kstep_bytes), make_desc(b_addr + k * kstep_bytes),
-                                       idesc, k > 0 ? 1u : 0u);
+                    const uint32_t d0 = tmem_base + (buf * 2) * NT_COLS, d1 = d0 + NT_COLS;
+                    if (KS > 0) {
+#pragma unroll
+                        for (int j = 0; j < (KS + PIECE_KSTEPS - 1) / PIECE_KSTEPS; ++j) {
+                            mbar_wait(BAR(B_FULL + s), b_phase);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo_base + (uint32_t)s * (PIECE_BYTES >> 4);
+#pragma unroll
+                            for (int kk = 0; kk < PIECE_KSTEPS; ++kk) {
+                                const int k = j * PIECE_KSTEPS + kk;
+                                if (k < KS) {
+                                    if (k == 0) {
+                                        tc_mma_f16_lo<false>(d0, a_lo0, b_lo, idesc);
+                                        tc_mma_f16_lo<false>(d1, a_lo1, b_lo, idesc);
+                                    } else {
+                                        tc_mma_f16_lo<true>(d0, a_lo0 + k * KSTEP, b_lo + kk * KSTEP, idesc);
+                                        tc_mma_f16_lo<true>(d1, a_lo1 + k * KSTEP, b_lo + kk * KSTEP, idesc);
+                                    }
+                                }
+                            }
+                            tc_commit(BAR(B_EMPTY + s));      // slice free once these MMAs have read it
+                            if (++s == B_RING) { s = 0; b_phase ^= 1; }
+                        }
+                    } else {
+                        for (int j = 0; j < n_pieces; ++j) {
+                            mbar_wait(BAR(B_FULL + s), b_phase);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo_base + (uint32_t)s * (PIECE_BYTES >> 4);
+                            for (int kk = 0; kk < PIECE_KSTEPS && j * PIECE_KSTEPS + kk < n_ks; ++kk) {
+                                const int k = j * PIECE_KSTEPS + kk;
+                                tc_mma_f16(d0, ((uint64_t)DESC_HI << 32) | (a_lo0 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_lo + kk * KSTEP), idesc, k > 0 ? 1u : 0u);
+                                tc_mma_f16(d1, ((uint64_t)DESC_HI << 32) | (a_lo1 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_lo + kk * KSTEP), idesc, k > 0 ? 1u : 0u);
+                            }
+                            tc_commit(BAR(B_EMPTY + s));
+                            if (++s == B_RING) { s = 0; b_phase ^= 1; }
+                        }
                     }
-                    tc_commit(BAR(6 + s));          // B stage free once these MMAs have read it
-                    tc_commit(BAR(10 + buf));       // accumulators ready for the epilogue
-                    if (++s == p.n_stages) { s = 0; b_phase ^= 1; }
+                    tc_commit(BAR(ACC_FULL + buf));       // accumulators ready for the epilogue
                 }
-                tc_commit(BAR(1));                  // A tiles free
+                tc_commit(BAR(A_EMPTY + ab));             // A tiles free
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue: running top-3 chunk maxima per embedding =====================
-        // warp -> (TMEM lane quadrant q = warp % 4, row half h, column part)
+        // warp -> (TMEM lane quadrant q = warp % 4, row half h, column part): 16 warps, each draining a
+        // 32-row x 64-column block of every accumulator tile with ONE tcgen05.ld; the accumulator is
+        // handed back to the MMA warp as soon as the values are in registers, before they are reduced.
         const int e = warp - 4, q = warp & 3, h = (e >> 2) & 1, part = e >> 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         constexpr int COLS = NT_COLS / EPI_PARTS;          // columns of each tile this warp reduces
+        static_assert(COLS == 64, "one x64 load per warp and tile");
         // one threshold for the whole launch: the loosest per-row tau (refine re-derives the exact per-row one)
         const float tau_c = filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D);
         uint32_t n_use = 0;
@@ -228,25 +300,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
             uint32_t k1 = 0, k2 = 0;
             for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                 const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                mbar_wait(BAR(10 + buf), acc_phase);
+                mbar_wait(BAR(ACC_FULL + buf), acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS;
-#pragma unroll
-                for (int sub = 0; sub < COLS / 64; ++sub) {
-                    float v[64];
-                    tc_ld64_wait(taddr + sub * 64, v);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float cm = v[c * 16];
-#pragma unroll
-                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
-                        top3_insert(&v[c * 16], cm, nt * (NT_COLS / CHUNK) + (part * COLS + sub * 64) / CHUNK + c, tau_c,
-                                    m1, m2, m3, i1, i2, k1, k2);
-                    }
-                }
+                float v[64];
+                tc_ld64_wait(tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS, v);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(12 + buf));
+                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float cm = v[c * 16];
+#pragma unroll
+                    for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                    top3_insert(&v[c * 16], cm, nt * (NT_COLS / CHUNK) + (part * COLS) / CHUNK + c, tau_c,
+                                m1, m2, m3, i1, i2, k1, k2);
+                }
             }
             const int r_local = h * TILE_ROWS + q * 32 + lane;
             if (EPI_PARTS == 2) {
@@ -592,24 +660,24 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     p.n_ntiles = k_pad(K_max) / NT_COLS;
     p.n_ksteps = kp_of(D) / 16;
     p.tile_bytes = (uint32_t)tile_bytes_of(D);
-    const size_t budget = 227 * 1024 - 1024 - 512 - (size_t)MT_ROWS * 32;
-    if (2 * (size_t)p.tile_bytes + 2 * (size_t)p.tile_bytes > budget) {
+    const size_t fixed = (size_t)B_RING * PIECE_BYTES + 256 + (size_t)MT_ROWS * 32 + 1024;    // ring, barriers, merge, alignment
+    const size_t budget = 227 * 1024;
+    if (2 * (size_t)p.tile_bytes + fixed > budget) {
         set_error("D=%d too large for the tensor-core scorer", D);
         return SEGB_E_UNSUPPORTED;
     }
-    int stages = (int)((budget - 2 * (size_t)p.tile_bytes) / p.tile_bytes);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    p.n_stages = stages;
-    const size_t smem = (size_t)(2 + stages) * p.tile_bytes + 256 + (size_t)MT_ROWS * 32;
+    p.n_abuf = (4 * (size_t)p.tile_bytes + fixed <= budget) ? 2 : 1;
+    const size_t smem = (size_t)p.n_abuf * 2 * p.tile_bytes + (size_t)B_RING * PIECE_BYTES + 256 + (size_t)MT_ROWS * 32;
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
         SEGB_CUDA(cudaGetDevice(&dev));
         SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    SEGB_CUDA(cudaFuncSetAttribute(kmeans_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;
-    kmeans_filter_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(p);
+    auto kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9> : kmeans_filter_kernel<0>;     // 9: D = 130 (KP = 144)
+    SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(p);
     SEGB_LAUNCH_CHECK();
     return 0;
 }

@@ -69,6 +69,32 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
+// One lane of a converged warp.  The compiler knows elect.sync yields exactly one thread, so the
+// single-thread tcgen05 / bulk-copy instructions issued under it need no per-active-lane loop
+// (with `lane == 0` every tcgen05.mma was wrapped in an ELECT / BRA.U.ANY waterfall).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Shared-memory descriptors split into words: the high word (SBO = 128 B, descriptor version 1) is the
+// same for every K-major no-swizzle operand; the low word is (addr >> 4) | (LBO >> 4) << 16, and a K
+// step only adds a constant to it (shared memory is < 256 KB, so the 14-bit address field cannot carry).
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t make_desc_lo(uint32_t saddr, int R) {
+    return ((saddr >> 4) & 0x3FFFu) | ((uint32_t)((R / 8) * 128 >> 4) << 16);
+}
+template <bool ACCUM>
+__device__ __forceinline__ void tc_mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %4};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(DESC_HI), "n"(ACCUM ? 1 : 0) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 32 lanes x 64 consecutive fp32 columns -> 64 registers per thread (thread = TMEM lane = row).
 // Load and wait live in ONE asm statement so no use of the outputs can be scheduled before
 // tcgen05.wait::ld.
