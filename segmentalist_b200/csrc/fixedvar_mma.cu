@@ -60,6 +60,7 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+template <int KS>
 __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {                                  // ===== TMA producer
+        if (elect_one()) {                                // ===== TMA producer
             uint32_t a_phase = 0, b_phase = 0;
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
                 mbar_wait(BAR(1), a_phase ^ 1);
@@ -110,12 +111,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                                  // ===== MMA issuer
+        // ===== MMA issuer: one elected thread, 32-bit descriptor words advanced by constants, K loops
+        // unrolled at compile time (KS > 0) -- ~3 instructions per tcgen05.mma, so the 64-clock MMAs are
+        // issued back to back (the first version spent ~100 clocks of scalar work per MMA).
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_mn(T_ROWS, NT_COLS);
-            const uint32_t kstep = 2 * (T_ROWS / 8) * 128;            // bytes per K=16 step (both operands)
-            const int nk = p.n_ksteps;
+            constexpr uint32_t KSTEP = (2 * (T_ROWS / 8) * 128) >> 4;  // descriptor units per K=16 step (both operands)
+            const int nk = KS > 0 ? KS : p.n_ksteps;
             uint32_t a_phase = 0, b_phase = 0, n_use = 0;
-            const uint32_t bH = smem_u32(sB), bL = smem_u32(sB + cb);
+            const uint32_t bH = make_desc_lo(smem_u32(sB), T_ROWS), bL = make_desc_lo(smem_u32(sB + cb), T_ROWS);
+            const uint32_t aH[2] = {make_desc_lo(smem_u32(sA), T_ROWS), make_desc_lo(smem_u32(sA + ta), T_ROWS)};
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
                 mbar_wait(BAR(0), a_phase);
                 a_phase ^= 1;
@@ -124,27 +129,39 @@ __global__ void __launch_bounds__(N_THREADS, 1) fv_logmarg_kernel(Params p) {
                     mbar_wait(BAR(8 + buf), acc_phase ^ 1);
                     mbar_wait(BAR(2), b_phase);                       // chunk H = [Bh, extras]
                     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t a_addr = smem_u32(sA + (size_t)h * ta);
                         const uint32_t d_tmem = tmem_base + (buf * 2 + h) * NT_COLS;
-                        for (int k = 0; k < nk; ++k)                  // xh . Bh (+ constants)
-                            tc_mma_f16(d_tmem, make_desc_r(a_addr + k * kstep, T_ROWS), make_desc_r(bH + k * kstep, T_ROWS),
-                                       idesc, k > 0 ? 1u : 0u);
-                        for (int k = 0; k < nk; ++k)                  // xl . Bh
-                            tc_mma_f16(d_tmem, make_desc_r(a_addr + (nk + k) * kstep, T_ROWS),
-                                       make_desc_r(bH + k * kstep, T_ROWS), idesc, 1u);
+                        const uint32_t aL = aH[h] + (uint32_t)nk * KSTEP;          // xl columns follow the xh columns
+                        if (KS > 0) {
+                            tc_mma_f16_lo<false>(d_tmem, aH[h], bH, idesc);       // xh . Bh (+ constants)
+#pragma unroll
+                            for (int k = 1; k < KS; ++k) tc_mma_f16_lo<true>(d_tmem, aH[h] + k * KSTEP, bH + k * KSTEP, idesc);
+#pragma unroll
+                            for (int k = 0; k < KS; ++k) tc_mma_f16_lo<true>(d_tmem, aL + k * KSTEP, bH + k * KSTEP, idesc);   // xl . Bh
+                        } else {
+                            for (int k = 0; k < nk; ++k)
+                                tc_mma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (aH[h] + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (bH + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                            for (int k = 0; k < nk; ++k)
+                                tc_mma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (aL + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (bH + k * KSTEP), idesc, 1u);
+                        }
                     }
                     tc_commit(BAR(4));                                // chunk H stage free
                     mbar_wait(BAR(3), b_phase);                       // chunk L = [Bl]
                     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t a_addr = smem_u32(sA + (size_t)h * ta);
                         const uint32_t d_tmem = tmem_base + (buf * 2 + h) * NT_COLS;
-                        for (int k = 0; k < nk; ++k)                  // xh . Bl
-                            tc_mma_f16(d_tmem, make_desc_r(a_addr + k * kstep, T_ROWS), make_desc_r(bL + k * kstep, T_ROWS),
-                                       idesc, 1u);
+                        if (KS > 0) {
+#pragma unroll
+                            for (int k = 0; k < KS; ++k) tc_mma_f16_lo<true>(d_tmem, aH[h] + k * KSTEP, bL + k * KSTEP, idesc);   // xh . Bl
+                        } else {
+                            for (int k = 0; k < nk; ++k)
+                                tc_mma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (aH[h] + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (bL + k * KSTEP), idesc, 1u);
+                        }
                     }
                     tc_commit(BAR(5));                                // chunk L stage free
                     tc_commit(BAR(6 + buf));                          // accumulators ready
@@ -363,9 +380,10 @@ extern "C" int segb_fvmma_log_marg(const segb_fixedvar *m, const void *x_tiles, 
         SEGB_CUDA(cudaGetDevice(&dev));
         SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    SEGB_CUDA(cudaFuncSetAttribute(fv_logmarg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = p.n_ksteps == 9 ? fv_logmarg_kernel<9> : fv_logmarg_kernel<0>;      // 9: D = 130 (dp = 144)
+    SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;
-    fv_logmarg_kernel<<<grid, N_THREADS, smem, st>>>(p);
+    kern<<<grid, N_THREADS, smem, st>>>(p);
     SEGB_LAUNCH_CHECK();
     return 0;
 }
