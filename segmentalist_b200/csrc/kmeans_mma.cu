@@ -572,6 +572,87 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_rows_kernel(
     }
 }
 
+// Same refine with EIGHT lanes per embedding (four embeddings per warp): lane (g, c) owns NumPy's
+// accumulators 2c and 2c+1 of block g and moves them with 8-byte loads, so the per-row bookkeeping
+// (filter record, bound, mask walk) is shared by 8 lanes instead of 16 and every load instruction
+// carries two terms.  Needs an even D (8-byte aligned rows); the combination tree is unchanged:
+// (r[2c] + r[2c+1]) locally, then xor 1 and xor 2 inside the block's four lanes.
+__global__ void __launch_bounds__(REFINE_THREADS) refine_rows8_kernel(
+    segb_kmeans m, const Cand *cand, const float *x_err, const float *w_max, int64_t n_emb, int n_chunks,
+    float *best_val, int32_t *best_k, unsigned long long *n_fallback, int32_t *fb_list) {
+    const int D = m.D, KM = m.K_max;
+    const int lane = threadIdx.x & 31, j = lane & 7, g = j >> 2, c = j & 3;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int gbase = lane & 24;
+    const float *X = (const float *)m.X;
+    const float *means = (const float *)m.means;
+    const float e_mu = w_max[0], n_mu = w_max[1];
+    int n2 = 0;
+    if (D > 128) { n2 = D / 2; n2 -= n2 % 8; }
+    const int lo_g = g == 0 ? 0 : n2;
+    const int n_g = (D > 128) ? (g == 0 ? n2 : D - n2) : (g == 0 ? D : 0);
+    const int n8_g = n_g >= 8 ? n_g - (n_g % 8) : 0;
+    const int steps = n8_g / 8;
+    const bool two_blocks = D > 128;
+
+    const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    for (int64_t row = grp_global; row < n_emb; row += grp_total) {
+        const Cand cd = cand[row];
+        const float2 xe = *reinterpret_cast<const float2 *>(x_err + 2 * row);
+        const float tau = filter_tau(xe.x, xe.y, e_mu, n_mu, D);
+        const int code = refine_decide(cd, tau, n_chunks);
+        if (code == -2) {
+            if (j == 0) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;      // -> refine_full_kernel
+            continue;
+        }
+        const float *xr = X + row * D;
+        const float2 *xr2 = reinterpret_cast<const float2 *>(xr + lo_g + 2 * c);
+        float2 xv[REFINE_MAX_STEPS];
+#pragma unroll
+        for (int i = 0; i < REFINE_MAX_STEPS; ++i) xv[i] = (i < steps) ? xr2[i * 4] : make_float2(0.f, 0.f);
+        float bv = -CUDART_INF_F;
+        int bk = 0x7fffffff;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            uint32_t mk = pass == 0 ? (cd.masks & 0xffffu) : (code >= 0 ? (cd.masks >> 16) : 0u);
+            const int chunk = pass == 0 ? cd.i1 : cd.i2;
+            while (mk) {
+                const int bit = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const int k = chunk * CHUNK + bit;
+                if (k >= KM) continue;
+                const float *mu = means + (size_t)k * D;
+                const float2 *mu2 = reinterpret_cast<const float2 *>(mu + lo_g + 2 * c);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < REFINE_MAX_STEPS; ++i) {
+                    if (i < steps) {
+                        const float2 mv = mu2[i * 4];
+                        const float d0 = __fsub_rn(mv.x, xv[i].x), d1 = __fsub_rn(mv.y, xv[i].y);
+                        const float p0 = __fmul_rn(d0, d0), p1 = __fmul_rn(d1, d1);
+                        a0 = (i == 0) ? p0 : __fadd_rn(a0, p0);
+                        a1 = (i == 0) ? p1 : __fadd_rn(a1, p1);
+                    }
+                }
+                float acc = __fadd_rn(a0, a1);                                   // r[2c] + r[2c+1]
+                acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, 1));
+                acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, 2));
+                if (n8_g == 0) acc = 0.f;
+                for (int d = lo_g + n8_g; d < lo_g + n_g; ++d) {                 // the block's n % 8 trailing terms
+                    const float dl = __fsub_rn(mu[d], xr[d]);
+                    acc = __fadd_rn(acc, __fmul_rn(dl, dl));
+                }
+                float tot = __shfl_sync(gmask, acc, gbase);
+                if (two_blocks) tot = __fadd_rn(tot, __shfl_sync(gmask, acc, gbase + 4));
+                const float v = -tot;
+                if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; }
+            }
+        }
+        if (j == 0) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
+    }
+}
+
 // Exhaustive exact scan for the rows the filter could not decide: one block per row.
 __global__ void __launch_bounds__(256) refine_full_kernel(segb_kmeans m, const int32_t *fb_list,
                                                           const unsigned long long *n_fallback, float *best_val,
@@ -700,11 +781,17 @@ extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const flo
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *fb_list = (int32_t *)work;
     SEGB_CUDA(cudaMemsetAsync(n_fallback, 0, sizeof(int64_t), st));
-    int64_t blocks = (n_emb * 16 + REFINE_THREADS - 1) / REFINE_THREADS;
+    const bool lanes8 = (m->D % 2 == 0);          // 8-byte loads need even D (rows 8-byte aligned)
+    int64_t blocks = (n_emb * (lanes8 ? 8 : 16) + REFINE_THREADS - 1) / REFINE_THREADS;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    refine_rows_kernel<<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
-        *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
-        (unsigned long long *)n_fallback, fb_list);
+    if (lanes8)
+        refine_rows8_kernel<<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
+            (unsigned long long *)n_fallback, fb_list);
+    else
+        refine_rows_kernel<<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
+            (unsigned long long *)n_fallback, fb_list);
     SEGB_LAUNCH_CHECK();
     refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(
         *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
