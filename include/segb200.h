@@ -294,6 +294,28 @@ int segb_fvmma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, v
 int segb_fvmma_log_marg(const segb_fixedvar *m, const void *x_tiles, void *w_tiles, int64_t n_emb, float *out,
                         void *stream);
 
+/* ------------------------------------------------------------------ per-iteration diagnostics */
+
+/* Both calls take the items grouped by component: `order` [n_emb] = item ids stably sorted by
+ * assignment (members keep their index order, like np.where), seg_off [K_max + 1] = start of
+ * component k's members in `order` (unassigned items, -1, come first).
+ *
+ * GaussianComponentsFixedVar.log_marg_k (gaussian_components_fixedvar.py:261-283) for every
+ * component: X[members].sum(axis=0) and np.square(X[members]).sum(axis=0) are formed in X's dtype
+ * with NumPy's row-after-row order, the closed form in float64 with separately rounded operations
+ * and NumPy's pairwise np.sum over the D terms.  out_k [K_max]: log_marg_k(k) for k < K, 0 above;
+ * log_marg() (:285-296) is their sum in component order (host).
+ * work: segb_fixedvar_log_marg_k_work_bytes() bytes of scratch.                                */
+int64_t segb_fixedvar_log_marg_k_work_bytes(int32_t K_max, int32_t D);
+int segb_fixedvar_log_marg_k(const segb_fixedvar *m, const int64_t *order, const int64_t *seg_off,
+                             void *work, double *out_k, void *stream);
+
+/* KMeansComponents.sum_neg_sqrd_norm (kmeans_components.py:234-247), per component:
+ * out_k[k] = -np.sum(deltas*deltas), deltas = mean_numerators[k]/counts[k] - X[members] (float64,
+ * NumPy's pairwise order over the flattened array); the objective is the sum over k < K (host). */
+int segb_kmeans_sum_neg_sqrd_norm_k(const segb_kmeans *m, const int64_t *order, const int64_t *seg_off,
+                                    double *out_k, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,9 @@ _PROTOS = {
     "segb_fvmma_w_tiles_bytes": (c_i64, [c_i32, c_i32]),
     "segb_fvmma_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "segb_fvmma_log_marg": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "segb_fixedvar_log_marg_k_work_bytes": (c_i64, [c_i32, c_i32]),
+    "segb_fixedvar_log_marg_k": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "segb_kmeans_sum_neg_sqrd_norm_k": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_vp]),
 }
 
 EXPORTS = sorted(_PROTOS)
@@ -137,6 +140,15 @@ def ptr(t):
 
 def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def members_by_component(assign, K_max):
+    """Items grouped by component for the diagnostics kernels: (order, seg_off) with `order` the item ids
+    stably sorted by assignment and seg_off[k] the start of component k's members (torch sort = plumbing)."""
+    order = torch.argsort(assign, stable=True)
+    seg_off = torch.searchsorted(assign[order].contiguous(),
+                                 torch.arange(K_max + 1, dtype=assign.dtype, device=assign.device))
+    return order.contiguous(), seg_off.to(torch.int64).contiguous()
 
 
 def dev(a, dtype=None):

@@ -204,44 +204,28 @@ class GaussianComponentsFixedVar(object):
     def get_assignments(self, list_of_i):
         return self.assignments[np.asarray(list_of_i)]
 
+    def _log_marg_per_component(self):
+        """log_marg_k for every component on the device (csrc/diagnostics.cu): the members' column sums in X's
+        dtype and NumPy's order, then the closed form of :270-283 in float64."""
+        work = torch.empty(_lib.lib().segb_fixedvar_log_marg_k_work_bytes(self.K_max, self.D) // 8,
+                           dtype=torch.float64, device="cuda")
+        out = torch.empty(self.K_max, dtype=torch.float64, device="cuda")
+        order, seg_off = _lib.members_by_component(self._assign, self.K_max)
+        _lib.check(_lib.lib().segb_fixedvar_log_marg_k(self.struct(), _lib.ptr(order), _lib.ptr(seg_off), _lib.ptr(work),
+                                                       _lib.ptr(out), _lib.stream_ptr()))
+        return out.cpu().numpy()
+
     def log_marg_k(self, k, _cache=None):
-        """:261-283 -- diagnostic; evaluated on the host from the mirrored assignments."""
-        assign = self.assignments if _cache is None else _cache
-        X = self.X[np.where(assign == k)]
-        N = X.shape[0]
-        return np.sum(
-            (N - 1) / 2. * np.log(self.precision)
-            - 0.5 * N * math.log(2 * np.pi)
-            - 0.5 * np.log(N / self.precision_0 + 1. / self.precision)
-            - 0.5 * self.precision * np.square(X).sum(axis=0)
-            - 0.5 * self.precision_0 * np.square(self.mu_0)
-            + 0.5 * (
-                np.square(X.sum(axis=0)) * self.precision / self.precision_0
-                + np.square(self.mu_0) * self.precision_0 / self.precision
-                + 2 * X.sum(axis=0) * self.mu_0
-            ) / (N / self.precision_0 + 1. / self.precision))
+        """:261-283 -- diagnostic, evaluated on the device."""
+        per_k = self._log_marg_per_component() if _cache is None else _cache
+        return float(per_k[k])
 
     def log_marg(self):
-        """:285-296."""
-        assign = self.assignments
-        order = np.argsort(assign, kind="stable")
-        sorted_a = assign[order]
+        """:285-296: the components' log marginals added in component order."""
+        per_k = self._log_marg_per_component()
         total = 0.
         for k in range(self.K):
-            lo, hi = np.searchsorted(sorted_a, k, "left"), np.searchsorted(sorted_a, k, "right")
-            X = self.X[order[lo:hi]]
-            N = hi - lo
-            total += np.sum(
-                (N - 1) / 2. * np.log(self.precision)
-                - 0.5 * N * math.log(2 * np.pi)
-                - 0.5 * np.log(N / self.precision_0 + 1. / self.precision)
-                - 0.5 * self.precision * np.square(X).sum(axis=0)
-                - 0.5 * self.precision_0 * np.square(self.mu_0)
-                + 0.5 * (
-                    np.square(X.sum(axis=0)) * self.precision / self.precision_0
-                    + np.square(self.mu_0) * self.precision_0 / self.precision
-                    + 2 * X.sum(axis=0) * self.mu_0
-                ) / (N / self.precision_0 + 1. / self.precision))
+            total += per_k[k]
         return total
 
 

@@ -157,15 +157,14 @@ class KMeansComponents(object):
         return [int(k) for k in self.best(list(list_of_i))[1].cpu().numpy()]
 
     def sum_neg_sqrd_norm(self):
-        """:234-247 -- diagnostic, host side from mirrored state."""
-        assign, num, counts = self.assignments, self.mean_numerators, self.counts
-        order = np.argsort(assign, kind="stable")
-        sorted_a = assign[order]
+        """:234-247 -- diagnostic, evaluated on the device (csrc/diagnostics.cu): per-component sums of
+        -|mean_numerators[k]/counts[k] - x|^2 over the assigned items, added in component order."""
+        out = torch.empty(self.K_max, dtype=torch.float64, device="cuda")
+        order, seg_off = _lib.members_by_component(self._assign, self.K_max)
+        _lib.check(_lib.lib().segb_kmeans_sum_neg_sqrd_norm_k(self.struct(), _lib.ptr(order), _lib.ptr(seg_off),
+                                                              _lib.ptr(out), _lib.stream_ptr()))
+        per_k = out.cpu().numpy()
         objective = 0
         for k in range(self.K):
-            lo, hi = np.searchsorted(sorted_a, k, "left"), np.searchsorted(sorted_a, k, "right")
-            X = self.X[order[lo:hi]]
-            mean = num[k, :] / counts[k]
-            deltas = mean - X
-            objective += -np.sum(deltas * deltas)
+            objective += per_k[k]
         return objective

@@ -646,3 +646,35 @@ def test_fixedvar_tensor_core_log_marg(sb, K_max, n_assigned, n_emb):
         ref = oam.log_marg_i(i)
         assert abs(tc[i] - ref) <= 1e-4 * abs(ref)
         assert abs(exact[i] - ref) <= 1e-11 * abs(ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_device_diagnostics_vs_oracle(sb, dtype):
+    """log_marg_k / log_marg (gaussian_components_fixedvar.py:261-296) and
+    sum_neg_sqrd_norm (kmeans_components.py:234-247) evaluated on the device from the grouped member
+    lists, against the oracle's np.where formulation.  NumPy's float32 column sums are reproduced, so
+    the float64 results agree to rounding (rtol 1e-12; north star 1e-4)."""
+    from segmentalist_b200.gaussian_components_fixedvar import FixedVarPrior, GaussianComponentsFixedVar
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    rng = np.random.RandomState(3)
+    N, D, K = 3000, 130, 37
+    X = rng.randn(N, D).astype(dtype)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    assign = rng.randint(-1, K, size=N)
+    assign[assign >= 0] = so._consecutive(assign[assign >= 0])
+    var = 0.002 * (1 + rng.rand(D))
+    prior = FixedVarPrior(var, 0.01 * rng.randn(D), var / 0.05)
+    K_max = K + 5
+    c = GaussianComponentsFixedVar(X, prior, assign.copy(), K_max=K_max)
+    o = so.FixedVarComponents(X, so.FixedVarPrior(prior.var, prior.mu_0, prior.var_0), assign.copy(), K_max=K_max)
+    per_k = c._log_marg_per_component()
+    npt.assert_allclose(per_k[:o.K], [o.log_marg_k(k) for k in range(o.K)], rtol=1e-12)
+    assert not per_k[o.K:].any()
+    npt.assert_allclose(c.log_marg(), o.log_marg(), rtol=1e-12)
+    npt.assert_allclose(c.log_marg_k(3), o.log_marg_k(3), rtol=1e-12)
+
+    np.random.seed(5)
+    km = KMeansComponents(X, assign.copy(), K_max)
+    np.random.seed(5)
+    ko = so.KMeansComponents(X, assign.copy(), K_max)
+    npt.assert_allclose(km.sum_neg_sqrd_norm(), ko.sum_neg_sqrd_norm(), rtol=1e-13)
