@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsegb200.so")
+SO_PATH = os.environ.get("SEGB_SO") or os.path.join(_HERE, "libsegb200.so")   # SEGB_SO: development builds
 _LIB = None
 
 c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p

@@ -43,10 +43,7 @@ constexpr int TILE_ROWS = 128;     // rows per operand tile image
 constexpr int MT_ROWS = 256;       // embeddings per CTA work item (two A tiles)
 constexpr int NT_COLS = 128;       // components per accumulator tile
 constexpr int CHUNK = 16;          // components per candidate chunk
-constexpr int PIECE_KSTEPS = 3;                                   // K=16 steps per B ring slot
 constexpr uint32_t KSTEP_BYTES = 2 * (TILE_ROWS / 8) * 128;        // one K=16 step of a 128-row tile image
-constexpr uint32_t PIECE_BYTES = PIECE_KSTEPS * KSTEP_BYTES;
-constexpr int B_RING = 6;
 constexpr int EPI_PARTS = 2;         // column halves of an accumulator tile handled by separate warp sets
 constexpr int N_EPI_WARPS = 8 * EPI_PARTS;
 constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
@@ -149,14 +146,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tb = p.tile_bytes;
     const int n_ks = KS > 0 ? KS : p.n_ksteps;
-    const int n_pieces = (n_ks + PIECE_KSTEPS - 1) / PIECE_KSTEPS;
     uint8_t *sA = smem;                                        // n_abuf x 2 tiles
-    uint8_t *sB = smem + (size_t)p.n_abuf * 2 * tb;            // ring of B_RING pieces
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)B_RING * PIECE_BYTES);
-    // barrier slots: a_full[2], a_empty[2], b_full[B_RING], b_empty[B_RING], acc_full[2], acc_empty[2]
-    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 4 + B_RING, ACC_FULL = 4 + 2 * B_RING,
-                  ACC_EMPTY = ACC_FULL + 2, N_BARS = ACC_EMPTY + 2;
-    static_assert(N_BARS * 8 + 4 <= 256, "barrier block");
+    uint8_t *sB = smem + (size_t)p.n_abuf * 2 * tb;            // 2 stages, stage = accumulator buffer = tile parity
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * (size_t)tb);
+    // MMA_DONE[b] (one tcgen05.commit per tile) means BOTH "B stage b may be refilled" (producer) and
+    // "accumulator pair b is complete" (epilogue): the issuing thread pays for one commit per tile.
+    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, MMA_DONE = 6, ACC_EMPTY = 8, N_BARS = 10;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     float4 *merge = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [MT_ROWS][2] partial top-3
     const uint32_t bar0 = smem_u32(bars);
@@ -182,9 +177,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
         // ===================== TMA producer =====================
         // A (256 embeddings) is double-buffered: the next work item's tiles are requested while the
         // current one is still being multiplied, so the tensor pipe does not drain at work-item
-        // boundaries.  B streams through a ring of K-slices ("pieces" of PIECE_KSTEPS K=16 steps of one
-        // 128-component tile, contiguous in the tile image), finer than whole tiles so that the ring
-        // gives > 1.5 tiles of look-ahead in the shared memory left over.
+        // boundaries.  B (one 128-component tile, L2-resident) alternates between two stages.
         if (elect_one()) {
             auto load_a = [&](int it, int mt) {
                 const int ab = p.n_abuf == 2 ? (it & 1) : 0;
@@ -194,23 +187,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 bulk_g2s(smem_u32(sA + (size_t)(2 * ab) * tb), p.x_tiles + (size_t)(2 * mt) * tb, tb, BAR(A_FULL + ab));
                 bulk_g2s(smem_u32(sA + (size_t)(2 * ab + 1) * tb), p.x_tiles + (size_t)(2 * mt + 1) * tb, tb, BAR(A_FULL + ab));
             };
-            uint32_t b_phase = 0;
-            int s = 0, it = 0;
+            uint32_t n_use = 0;
+            int it = 0;
             if ((int)blockIdx.x < p.n_mtiles) load_a(0, blockIdx.x);
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
                 const int mt_next = mt + gridDim.x;
                 const int nt_pref = p.n_abuf == 2 ? (p.n_ntiles > 4 ? 4 : p.n_ntiles - 1) : -1;
-                for (int nt = 0; nt < p.n_ntiles; ++nt) {
+                for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     if (nt == nt_pref && mt_next < p.n_mtiles) load_a(it + 1, mt_next);
-                    const uint8_t *src = p.w_tiles + (size_t)nt * tb;
-                    for (int j = 0; j < n_pieces; ++j) {
-                        const int ks_here = (n_ks - j * PIECE_KSTEPS) < PIECE_KSTEPS ? (n_ks - j * PIECE_KSTEPS) : PIECE_KSTEPS;
-                        const uint32_t bytes = (uint32_t)ks_here * KSTEP_BYTES;
-                        mbar_wait(BAR(B_EMPTY + s), b_phase ^ 1);
-                        mbar_expect_tx(BAR(B_FULL + s), bytes);
-                        bulk_g2s(smem_u32(sB + (size_t)s * PIECE_BYTES), src + (size_t)j * PIECE_BYTES, bytes, BAR(B_FULL + s));
-                        if (++s == B_RING) { s = 0; b_phase ^= 1; }
-                    }
+                    const uint32_t s = n_use & 1, use = n_use >> 1;
+                    mbar_wait(BAR(MMA_DONE + s), (use & 1) ^ 1);       // the MMAs of the stage's previous tile are done
+                    mbar_expect_tx(BAR(B_FULL + s), tb);
+                    bulk_g2s(smem_u32(sB + (size_t)s * tb), p.w_tiles + (size_t)nt * tb, tb, BAR(B_FULL + s));
                 }
                 if (p.n_abuf == 1 && mt_next < p.n_mtiles) load_a(it + 1, mt_next);
             }
@@ -218,66 +206,46 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // The issue loop is the kernel's pacemaker: one M=128 N=128 K=16 MMA occupies the tensor pipe
-        // for 64 clocks, so the elected thread has to issue one every < 64 clocks.  Descriptors are
-        // therefore kept as 32-bit low words advanced by a constant per K step, the K loop is unrolled
-        // at compile time, and the issuer is chosen with elect.sync (see elect_one()).  The two row
-        // halves alternate per K step, so a B slice is released as soon as both have consumed it.
+        // for 64 clocks, and everything the elected thread does between two tiles (barrier polls, the
+        // commit) has to fit into the few MMAs still queued.  So: descriptors are 32-bit low words
+        // advanced by a constant per K step, the K loop is unrolled at compile time, the issuer is
+        // chosen with elect.sync (see elect_one()), both barriers of a tile are polled together, and
+        // there is ONE commit per tile.
         if (elect_one()) {
             const uint32_t idesc = make_idesc();
             constexpr uint32_t KSTEP = KSTEP_BYTES >> 4;              // descriptor units per K=16 step
             const uint32_t a_lo_base = make_desc_lo(smem_u32(sA), TILE_ROWS);
             const uint32_t b_lo_base = make_desc_lo(smem_u32(sB), TILE_ROWS);
-            uint32_t b_phase = 0, n_use = 0;
-            int s = 0, it = 0;
+            uint32_t n_use = 0;
+            int it = 0;
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
                 const int ab = p.n_abuf == 2 ? (it & 1) : 0;
-                const uint32_t use = p.n_abuf == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
-                mbar_wait(BAR(A_FULL + ab), use & 1);
+                const uint32_t ause = p.n_abuf == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+                mbar_wait(BAR(A_FULL + ab), ause & 1);
                 const uint32_t a_lo0 = a_lo_base + (uint32_t)(2 * ab) * (tb >> 4), a_lo1 = a_lo0 + (tb >> 4);
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
-                    const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                    mbar_wait(BAR(ACC_EMPTY + buf), acc_phase ^ 1);
+                    const uint32_t buf = n_use & 1, use = n_use >> 1;
+                    mbar_wait2(BAR(B_FULL + buf), use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
                     tc_fence_after();
+                    const uint32_t b_lo = b_lo_base + buf * (tb >> 4);
                     const uint32_t d0 = tmem_base + (buf * 2) * NT_COLS, d1 = d0 + NT_COLS;
                     if (KS > 0) {
+                        tc_mma_f16_lo<false>(d0, a_lo0, b_lo, idesc);
+                        tc_mma_f16_lo<false>(d1, a_lo1, b_lo, idesc);
 #pragma unroll
-                        for (int j = 0; j < (KS + PIECE_KSTEPS - 1) / PIECE_KSTEPS; ++j) {
-                            mbar_wait(BAR(B_FULL + s), b_phase);
-                            tc_fence_after();
-                            const uint32_t b_lo = b_lo_base + (uint32_t)s * (PIECE_BYTES >> 4);
-#pragma unroll
-                            for (int kk = 0; kk < PIECE_KSTEPS; ++kk) {
-                                const int k = j * PIECE_KSTEPS + kk;
-                                if (k < KS) {
-                                    if (k == 0) {
-                                        tc_mma_f16_lo<false>(d0, a_lo0, b_lo, idesc);
-                                        tc_mma_f16_lo<false>(d1, a_lo1, b_lo, idesc);
-                                    } else {
-                                        tc_mma_f16_lo<true>(d0, a_lo0 + k * KSTEP, b_lo + kk * KSTEP, idesc);
-                                        tc_mma_f16_lo<true>(d1, a_lo1 + k * KSTEP, b_lo + kk * KSTEP, idesc);
-                                    }
-                                }
-                            }
-                            tc_commit(BAR(B_EMPTY + s));      // slice free once these MMAs have read it
-                            if (++s == B_RING) { s = 0; b_phase ^= 1; }
+                        for (int k = 1; k < KS; ++k) {
+                            tc_mma_f16_lo<true>(d0, a_lo0 + k * KSTEP, b_lo + k * KSTEP, idesc);
+                            tc_mma_f16_lo<true>(d1, a_lo1 + k * KSTEP, b_lo + k * KSTEP, idesc);
                         }
                     } else {
-                        for (int j = 0; j < n_pieces; ++j) {
-                            mbar_wait(BAR(B_FULL + s), b_phase);
-                            tc_fence_after();
-                            const uint32_t b_lo = b_lo_base + (uint32_t)s * (PIECE_BYTES >> 4);
-                            for (int kk = 0; kk < PIECE_KSTEPS && j * PIECE_KSTEPS + kk < n_ks; ++kk) {
-                                const int k = j * PIECE_KSTEPS + kk;
-                                tc_mma_f16(d0, ((uint64_t)DESC_HI << 32) | (a_lo0 + k * KSTEP),
-                                           ((uint64_t)DESC_HI << 32) | (b_lo + kk * KSTEP), idesc, k > 0 ? 1u : 0u);
-                                tc_mma_f16(d1, ((uint64_t)DESC_HI << 32) | (a_lo1 + k * KSTEP),
-                                           ((uint64_t)DESC_HI << 32) | (b_lo + kk * KSTEP), idesc, k > 0 ? 1u : 0u);
-                            }
-                            tc_commit(BAR(B_EMPTY + s));
-                            if (++s == B_RING) { s = 0; b_phase ^= 1; }
+                        for (int k = 0; k < n_ks; ++k) {
+                            tc_mma_f16(d0, ((uint64_t)DESC_HI << 32) | (a_lo0 + k * KSTEP),
+                                       ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                            tc_mma_f16(d1, ((uint64_t)DESC_HI << 32) | (a_lo1 + k * KSTEP),
+                                       ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
                         }
                     }
-                    tc_commit(BAR(ACC_FULL + buf));       // accumulators ready for the epilogue
+                    tc_commit(BAR(MMA_DONE + buf));       // B stage free + accumulators ready
                 }
                 tc_commit(BAR(A_EMPTY + ab));             // A tiles free
             }
@@ -300,7 +268,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
             uint32_t k1 = 0, k2 = 0;
             for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                 const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                mbar_wait(BAR(ACC_FULL + buf), acc_phase);
+                mbar_wait(BAR(MMA_DONE + buf), acc_phase);
                 tc_fence_after();
                 float v[64];
                 tc_ld64_wait(tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS, v);
@@ -741,14 +709,14 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     p.n_ntiles = k_pad(K_max) / NT_COLS;
     p.n_ksteps = kp_of(D) / 16;
     p.tile_bytes = (uint32_t)tile_bytes_of(D);
-    const size_t fixed = (size_t)B_RING * PIECE_BYTES + 256 + (size_t)MT_ROWS * 32 + 1024;    // ring, barriers, merge, alignment
+    const size_t fixed = 2 * (size_t)p.tile_bytes + 256 + (size_t)MT_ROWS * 32 + 1024;    // B stages, barriers, merge, alignment
     const size_t budget = 227 * 1024;
     if (2 * (size_t)p.tile_bytes + fixed > budget) {
         set_error("D=%d too large for the tensor-core scorer", D);
         return SEGB_E_UNSUPPORTED;
     }
     p.n_abuf = (4 * (size_t)p.tile_bytes + fixed <= budget) ? 2 : 1;
-    const size_t smem = (size_t)p.n_abuf * 2 * p.tile_bytes + (size_t)B_RING * PIECE_BYTES + 256 + (size_t)MT_ROWS * 32;
+    const size_t smem = (size_t)(p.n_abuf * 2 + 2) * p.tile_bytes + 256 + (size_t)MT_ROWS * 32;
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;

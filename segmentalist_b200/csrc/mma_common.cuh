@@ -53,6 +53,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     printf("segb mma: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
     __trap();
 }
+// Wait for TWO barriers with one poll loop: both try_wait probes are in flight together, so the
+// single issuing thread pays one shared-memory round trip per tile instead of two.
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+    uint32_t da = 0, db = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "selp.u32 %1, 1, 0, q;\n\t}"
+            : "=r"(da), "=r"(db) : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
+        if (da && db) return;
+    }
+    printf("segb mma: mbarrier pair wait timed out (block %d thread %d bars %u %u)\n", blockIdx.x, threadIdx.x, bar_a, bar_b);
+    __trap();
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

@@ -678,3 +678,59 @@ def test_device_diagnostics_vs_oracle(sb, dtype):
     np.random.seed(5)
     ko = so.KMeansComponents(X, assign.copy(), K_max)
     npt.assert_allclose(km.sum_neg_sqrd_norm(), ko.sum_neg_sqrd_norm(), rtol=1e-13)
+
+
+def test_checkpoint_resume_pickle(sb):
+    """Checkpoint/resume: a segmenter pickled after one sweep and restored --
+    together with the host RNG state, which is the user's to save, exactly as with the reference --
+    continues to the same samples as the uninterrupted run.  Covers the sequential Gibbs segmenter and
+    the k-means segmenter (device state = torch tensors; nothing else lives outside the objects)."""
+    import pickle
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf, unigram_acoustic_wordseg as uaw
+    from segmentalist_b200 import kmeans_acoustic_wordseg as kaw
+    z = G.load("unigram_ffbs.npz")
+    mats, vids, durs, lms = G.unpack_dicts(z)
+    D = 16
+    prior = gcf.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+
+    def make():
+        random.seed(2)
+        np.random.seed(2)
+        return uaw.UnigramAcousticWordseg(
+            fbgmm.FBGMM, 10., 9, prior, mats, vids, durs, lms, p_boundary_init=0.5, beta_sent_boundary=-1,
+            n_slices_max=4, lms=1.0, wip=-0.3, fb_type="standard", time_power_term=1.1)
+
+    a = make()
+    a.gibbs_sample(3)
+    b = make()
+    b.gibbs_sample(1)
+    blob, rs, nps = pickle.dumps(b), random.getstate(), np.random.get_state()
+    del b
+    random.seed(99)
+    np.random.seed(99)
+    b = pickle.loads(blob)
+    random.setstate(rs)
+    np.random.set_state(nps)
+    b.gibbs_sample(2)
+    npt.assert_array_equal(a.utterances.boundaries, b.utterances.boundaries)
+    npt.assert_array_equal(a.acoustic_model.components.assignments, b.acoustic_model.components.assignments)
+    npt.assert_array_equal(a.acoustic_model.components.mu_N_numerators, b.acoustic_model.components.mu_N_numerators)
+    npt.assert_array_equal(a.utterances.boundaries, z["boundaries"])      # and both equal the reference's run
+
+    def make_km():
+        random.seed(4)
+        np.random.seed(4)
+        return kaw.KMeansAcousticWordseg(7, mats, vids, durs, lms, n_slices_max=4, init_am_assignments="spread")
+
+    a = make_km()
+    a.segment(3)
+    b = make_km()
+    b.segment(1)
+    blob, rs, nps = pickle.dumps(b), random.getstate(), np.random.get_state()
+    b = pickle.loads(blob)
+    random.setstate(rs)
+    np.random.set_state(nps)
+    b.segment(2)
+    npt.assert_array_equal(a.utterances.boundaries, b.utterances.boundaries)
+    npt.assert_array_equal(a.acoustic_model.components.assignments, b.acoustic_model.components.assignments)
+    npt.assert_array_equal(a.acoustic_model.components.means, b.acoustic_model.components.means)
