@@ -38,8 +38,8 @@ TOTAL_UTTS = 200000
 NOISE = 0.05
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the three reported kernels,
 # from ONE `ncu --set full --clock-control none` capture of this command at the default configuration on
-# one GPU (profiles/r1_ncu_summary_v3.md).  Reported only when the run uses that configuration.
-NCU_TRAFFIC_BYTES = {"filter": 6.056337e9 + 0.669730e9, "dp": 0.193679e9 + 0.008181e9,
+# one GPU (profiles/r1_ncu_summary_v4.md).  Reported only when the run uses that configuration.
+NCU_TRAFFIC_BYTES = {"filter": 6.054860e9 + 0.668228e9, "dp": 0.193679e9 + 0.008181e9,
                      "fv_logmarg_per_row": (607.070976e6 + 4.2e6) / 1048576}
 METRIC = "utterances/sec per sweep"
 WORKLOAD = "kmeans_viterbi_frozen_sweep D=130 K=5000 U=200k max_span=6 (BASELINE configs[2])"
@@ -521,7 +521,7 @@ def run_ours(args):
                         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": ach / peak_tf,
                         "traffic": NCU_TRAFFIC_BYTES["filter"] if (world == 1 and args.utts == TOTAL_UTTS and args.K == K_MAX) else None,
-                        "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_ncu_summary_v3.md)",
+                        "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_ncu_summary_v4.md)",
                         "peak_source": peak_src,
                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops}
         cs = corpus.struct()

@@ -527,6 +527,67 @@ def golden_diag(ref_diag, ref_niw, ref_fbgmm, ref_uni):
     print("unigram_diag log_marg", rec["log_marg"], "K", cc.K, "uniforms", len(tap.uniforms))
 
 
+def golden_bigram(ref_bi, ref_fv, ref_lm):
+    """BigramAcousticWordseg (bigram_acoustic_wordseg.py) with fb_type="unigram": unigram segmentation,
+    component assignments sampled under the smoothed bigram LM (bigram_lms.py) -- SURVEY 8f rank 4 /
+    BASELINE configs[3].  Plus known-answer vectors of BigramSmoothLM itself."""
+    from segmentalist_b200 import synth
+    # --- the LM alone (the data of the reference's own main(), bigram_lms.py:118-152)
+    lm = ref_lm.BigramSmoothLM(0.1, 1., 2., 5)
+    data = [[1, 1, 3, 4, 0], [4, 4], [1, 0, 2, 2, 2, 2, 3, 1], [3, 3, 1]]
+    lm.counts_from_data(data)
+    d = {"lm_unigram_counts": lm.unigram_counts.copy(), "lm_bigram_counts": lm.bigram_counts.copy(),
+         "lm_prob_vec_i": lm.prob_vec_i(), "lm_log_prob_vec_i": lm.log_prob_vec_i(),
+         "lm_prob_vec_given_j": np.array([lm.prob_vec_given_j(j) for j in range(5)]),
+         "lm_log_prob_vec_given_j": np.array([lm.log_prob_vec_given_j(j) for j in range(5)])}
+    lm.remove_counts_from_utterance(data[2])
+    d["lm_unigram_counts_removed"] = lm.unigram_counts.copy()
+    d["lm_bigram_counts_removed"] = lm.bigram_counts.copy()
+    np.savez_compressed(os.path.join(OUT, "bigram_lm.npz"), **d)
+    # --- the segmenter
+    for tag, n_iter, lms_, kw in (("plain", 3, 1.0, {}),
+                                  ("anneal", 3, 0.8, {"anneal_schedule": "linear", "anneal_start_temp_inv": 0.5,
+                                                      "anneal_gibbs_am": True}),
+                                  ("assign_only", 2, 1.0, {"assignments_only": True})):
+        mats, vids, durs, lms = synth.make_corpus_dicts(
+            14, D=16, K_true=5, n_min=3, n_max=9, n_slices_max=4, noise=0.08, seed=23)
+        random.seed(6)
+        np.random.seed(6)
+        D = 16
+        prior = ref_fv.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+        lm_params = {"type": "smooth", "intrp_lambda": 0.15, "a": 1.5, "b": 2.5}
+        seg = ref_bi.BigramAcousticWordseg(
+            9, prior, lm_params, mats, vids, durs, lms, p_boundary_init=0.5, beta_sent_boundary=-1,
+            n_slices_max=4, lms=lms_, wip=-0.3, fb_type="unigram", time_power_term=1.1)
+        ref_bi.i_debug_monitor = -1
+        d = pack_dicts("in_", mats, vids, durs, lms)
+        d["lm_params"] = np.array([lm_params["intrp_lambda"], lm_params["a"], lm_params["b"]])
+        d["lms"] = np.array(lms_)
+        d["init_boundaries"] = seg.utterances.boundaries.copy()
+        d["init_assignments"] = seg.acoustic_model.components.assignments.copy()
+        d["init_unigram_counts"] = seg.lm.unigram_counts.copy()
+        d["init_bigram_counts"] = seg.lm.bigram_counts.copy()
+        d["init_log_prob_z"] = np.array(seg.log_prob_z())
+        with Tap() as tap:
+            rec = seg.gibbs_sample(n_iter, **kw)
+        c = seg.acoustic_model.components
+        d["uniforms"] = np.array(tap.uniforms)
+        d["orders"] = np.array(tap.orders)
+        for key in ("log_marg", "log_marg*length", "log_prob_z", "log_prob_X_given_z", "components", "n_tokens",
+                    "anneal_temp"):
+            d["rec_" + key] = np.array(rec[key], dtype=np.float64)
+        d["boundaries"] = seg.utterances.boundaries.copy()
+        d["assignments"] = c.assignments.copy()
+        d["counts"] = c.counts.copy()
+        d["K"] = np.array(c.K)
+        d["mu_N_numerators"] = c.mu_N_numerators.copy()
+        d["unigram_counts"] = seg.lm.unigram_counts.copy()
+        d["bigram_counts"] = seg.lm.bigram_counts.copy()
+        np.savez_compressed(os.path.join(OUT, "bigram_%s.npz" % tag), **d)
+        print("bigram", tag, "log_marg", rec["log_marg"], "K", c.K, "uniforms", len(tap.uniforms),
+              "tied", np.array_equal(c.counts, seg.lm.unigram_counts))
+
+
 def main():
     only = set(sys.argv[1:])                 # e.g. `make_golden.py fbgmm_gibbs` regenerates one family
     run = lambda name: (not only) or (name in only)
@@ -560,6 +621,9 @@ def main():
         if run("diag"):
             golden_diag(importlib.import_module("segmentalist.gaussian_components_diag"),
                         importlib.import_module("segmentalist.niw"), ref_fbgmm, ref_uni)
+        if run("bigram"):
+            golden_bigram(importlib.import_module("segmentalist.bigram_acoustic_wordseg"), ref_fv,
+                          importlib.import_module("segmentalist.bigram_lms"))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
