@@ -139,9 +139,10 @@ class FixedVarComponents(object):
     Restates GaussianComponentsFixedVar (gaussian_components_fixedvar.py:80-338).
     """
 
-    def __init__(self, X, prior, assignments=None, K_max=None):
+    def __init__(self, X, prior, assignments=None, K_max=None, lm=None):
         assert K_max is not None                                    # :88-89
         self.X = X
+        self.lm = lm                                                # :92 (tied bigram LM counts, :205-221)
         self.precision = 1. / prior.var                             # :84
         self.mu_0 = prior.mu_0
         self.precision_0 = 1. / prior.var_0                         # :86
@@ -199,9 +200,13 @@ class FixedVarComponents(object):
                 self._refresh_pred(k)
 
     def del_component(self, k):
-        """:190-221 (language-model tie-in omitted: out of scope)."""
+        """:190-221, incl. the language-model tie-in (:205-208, :218-221)."""
         self.K -= 1
         last = self.K
+        if k != last and self.lm is not None:
+            self.lm.unigram_counts[k] = self.lm.unigram_counts[last]
+            self.lm.bigram_counts[k, :] = self.lm.bigram_counts[last, :]
+            self.lm.bigram_counts[:, k] = self.lm.bigram_counts[:, last]
         if k != last:
             self.mu_N_numerators[k] = self.mu_N_numerators[last]
             self.precision_Ns[k, :] = self.precision_Ns[last, :]
@@ -214,6 +219,10 @@ class FixedVarComponents(object):
         self.log_prod_precision_preds[last] = 0.
         self.precision_preds[last, :].fill(0.)
         self.counts[last] = 0
+        if self.lm is not None:
+            self.lm.unigram_counts[last] = 0
+            self.lm.bigram_counts[last, :].fill(0)
+            self.lm.bigram_counts[:, last].fill(0)
 
     def _log_prod_norm(self, i, mu, log_prod_precision_pred, precision_pred):
         """:328-338 -- scalar path through the sequential C reduction."""
@@ -1140,6 +1149,220 @@ class SegmentalKMeansWordseg(object):
 # batch mode"): every utterance is scored and segmented against the SAME means
 # with the reference's pure functions, then all updates are applied.
 # ---------------------------------------------------------------------------
+
+# ---------------------------------------------------------------------------
+# Bigram LM + bigram cluster sampling   (bigram_lms.py, bigram_fbgmm.py, bigram_acoustic_wordseg.py)
+# ---------------------------------------------------------------------------
+
+class BigramSmoothLM(object):
+    """bigram_lms.py:18-113: smoothed, interpolated maximum-likelihood bigram LM."""
+
+    def __init__(self, intrp_lambda, a, b, K):
+        self.intrp_lambda, self.a, self.b, self.K = intrp_lambda, a, b, K
+        self.unigram_counts = np.zeros(K, np.int64)                 # :46-47
+        self.bigram_counts = np.zeros((K, K), np.int64)
+
+    def prob_i(self, i):                                            # :49-54
+        return (self.unigram_counts[i] + float(self.a) / self.K) / (int(self.unigram_counts.sum()) + self.a)
+
+    def prob_i_given_j(self, i, j):                                 # :56-62
+        p = (self.bigram_counts[j, i] + float(self.b) / self.K) / (self.unigram_counts[j] + float(self.b))
+        return self.intrp_lambda * self.prob_i(i) + (1 - self.intrp_lambda) * p
+
+    def log_prob_vec_i(self):                                       # :64-69
+        return (np.log(self.unigram_counts + float(self.a) / self.K)
+                - np.log(int(self.unigram_counts.sum()) + self.a))
+
+    def prob_vec_i(self):                                           # :71-76
+        return (self.unigram_counts + float(self.a) / self.K) / (int(self.unigram_counts.sum()) + self.a)
+
+    def prob_vec_given_j(self, j):                                  # :84-91
+        return (self.intrp_lambda * self.prob_vec_i() + (1 - self.intrp_lambda) *
+                (self.bigram_counts[j, :] + float(self.b) / self.K) / (self.unigram_counts[j] + float(self.b)))
+
+    def log_prob_vec_given_j(self, j):                              # :78-82
+        return np.log(self.prob_vec_given_j(j))
+
+    def counts_from_data(self, data):                               # :93-96
+        for utterance in data:
+            self.counts_from_utterance(utterance)
+
+    def counts_from_utterance(self, utterance):                     # :98-105
+        j_prev = None
+        for i_cur in utterance:
+            self.unigram_counts[i_cur] += 1
+            if j_prev is not None:
+                self.bigram_counts[j_prev, i_cur] += 1
+            j_prev = i_cur
+
+    def remove_counts_from_utterance(self, utterance):              # :107-113
+        j_prev = None
+        for i_cur in utterance:
+            self.unigram_counts[i_cur] -= 1
+            if j_prev is not None:
+                self.bigram_counts[j_prev, i_cur] -= 1
+            j_prev = i_cur
+
+
+class BigramFBGMM(object):
+    """bigram_fbgmm.py:20-100 (fixed covariance; components tied to the LM counts)."""
+
+    def __init__(self, X, prior, K, assignments, covariance_type="fixed", lms=1.0, lm=None):
+        assert covariance_type == "fixed"
+        self.prior, self.covariance_type, self.lms = prior, covariance_type, lms
+        assignments = _consecutive(np.asarray(assignments, dtype=np.int64))      # :75-79
+        self.components = FixedVarComponents(X, prior, assignments, K_max=K, lm=lm)
+
+    def log_prob_X_given_z(self):
+        return self.components.log_marg()
+
+    def get_n_assigned(self):
+        return len(np.where(self.components.assignments != -1)[0])
+
+
+class BigramAcousticWordseg(object):
+    """bigram_acoustic_wordseg.py:30-749 with fb_type="unigram": segmentation as in the unigram model
+    (scores from log_marg_i_embed_unigram), component assignments sampled under the bigram LM
+    (gibbs_sample_inside_loop_i_embed).  fb_type="bigram" is a stub in the reference (:756-789: `pass`)."""
+
+    def __init__(self, am_K, am_param_prior, lm_params, embedding_mats, vec_ids_dict, durations_dict,
+                 landmarks_dict, seed_boundaries_dict=None, seed_assignments_dict=None, covariance_type="fixed",
+                 n_slices_min=0, n_slices_max=20, min_duration=0, p_boundary_init=0.5, beta_sent_boundary=2.0,
+                 lms=1., wip=0., fb_type="bigram", init_am_assignments="rand", time_power_term=1., uniform=None):
+        assert seed_assignments_dict is None, "not restated in the oracle"
+        assert fb_type == "unigram", "the reference's bigram forward-backward is a stub"
+        self.n_slices_min, self.n_slices_max = n_slices_min, n_slices_max
+        self.beta_sent_boundary, self.wip, self.lms = beta_sent_boundary, wip, lms
+        self.time_power_term, self.fb_type = time_power_term, fb_type
+        self.uniform = uniform if uniform is not None else UniformSource()
+        embeddings, init_embeds = _init_corpus(
+            self, embedding_mats, vec_ids_dict, durations_dict, landmarks_dict,
+            seed_boundaries_dict, p_boundary_init, n_slices_min, n_slices_max, min_duration)
+        assert lm_params["type"] == "smooth"                                      # :184-189
+        self.lm = BigramSmoothLM(lm_params["intrp_lambda"], lm_params["a"], lm_params["b"], am_K)
+        assignments = -1 * np.ones(embeddings.shape[0], dtype=np.int64)
+        assert init_am_assignments == "rand"                                      # :228-243
+        assignments[init_embeds] = _consecutive(np.random.randint(0, am_K, len(init_embeds)))
+        self.acoustic_model = BigramFBGMM(embeddings, am_param_prior, am_K, assignments,
+                                          covariance_type=covariance_type, lms=lms, lm=self.lm)
+        self.set_lm_counts()
+
+    def set_lm_counts(self):                                                      # :265-267
+        for u in range(self.utterances.D):
+            self.lm.counts_from_utterance(self.get_unsup_transcript_i(u))
+
+    def get_unsup_transcript_i(self, u):                                          # :743-747
+        return list(self.acoustic_model.components.assignments[
+            np.asarray(self.utterances.get_segmented_embeds_i(u), dtype=np.int64)])
+
+    def log_prob_z(self):                                                         # :269-305
+        lm_tmp = BigramSmoothLM(self.lm.intrp_lambda, self.lm.a, self.lm.b, self.lm.K)
+        log_prob_z = 0.
+        for u in range(self.utterances.D):
+            j_prev = None
+            for i_cur in self.get_unsup_transcript_i(u):
+                if j_prev is not None:
+                    log_prob_z += np.log(lm_tmp.prob_i_given_j(i_cur, j_prev))
+                    lm_tmp.bigram_counts[j_prev, i_cur] += 1
+                else:
+                    log_prob_z += np.log(lm_tmp.prob_i(i_cur))
+                lm_tmp.unigram_counts[i_cur] += 1
+        return log_prob_z
+
+    def log_marg(self):                                                           # :307-311
+        return self.log_prob_z() + self.acoustic_model.log_prob_X_given_z()
+
+    def log_marg_i_embed_unigram(self, e):                                        # :314-330
+        c = self.acoustic_model.components
+        log_prob_z = self.lms * self.lm.log_prob_vec_i()
+        log_prob_z[:c.K] += c.log_post_pred(e)
+        log_prob_z[c.K:] += c.log_prior(e)
+        return c_logsumexp(log_prob_z)
+
+    def get_vec_embed_log_probs(self, vec_ids, durations):                        # :696-714
+        out = -np.inf * np.ones(len(vec_ids))
+        for i, e in enumerate(vec_ids):
+            if e == -1:
+                continue
+            out[i] = self.log_marg_i_embed_unigram(e)
+            if np.isnan(durations[i]):
+                out[i] = -np.inf
+            else:
+                out[i] *= durations[i] ** self.time_power_term
+        return out + self.wip
+
+    def gibbs_sample_inside_loop_i_embed(self, e, j_prev_assignment=None, anneal_temp=1):   # :333-384
+        c = self.acoustic_model.components
+        if j_prev_assignment is not None:
+            log_prob_z = np.log(self.lm.prob_vec_given_j(j_prev_assignment))
+        else:
+            log_prob_z = self.lm.log_prob_vec_i()
+        log_prob_z *= self.lms
+        log_prob_z[:c.K] += c.log_post_pred(e)
+        log_prob_z[c.K:] += c.log_prior(e)
+        if anneal_temp != 1:
+            log_prob_z = log_prob_z - c_logsumexp(log_prob_z)
+            log_prob_z_anneal = 1. / anneal_temp * log_prob_z - c_logsumexp(1. / anneal_temp * log_prob_z)
+            prob_z = np.exp(log_prob_z_anneal)
+        else:
+            prob_z = np.exp(log_prob_z - c_logsumexp(log_prob_z))
+        assert not np.isnan(np.sum(prob_z))
+        k = draw(prob_z, self.uniform())
+        if k > c.K:
+            k = c.K
+        c.add_item(e, k)
+        return k
+
+    def gibbs_sample_i(self, u, anneal_temp=1, anneal_gibbs_am=False, assignments_only=False):   # :386-543
+        utts, c = self.utterances, self.acoustic_model.components
+        self.lm.remove_counts_from_utterance(self.get_unsup_transcript_i(u))
+        for e in utts.get_segmented_embeds_i(u):
+            if e == -1:
+                continue
+            c.del_item(e)
+        log_prob = 0.
+        if not assignments_only:
+            N = utts.lengths[u]
+            n_packed = (N ** 2 + N) // 2
+            scores = self.get_vec_embed_log_probs(utts.vec_ids[u, :n_packed], utts.durations[u, :n_packed])
+            assert self.beta_sent_boundary == -1, "to check (reference :728-729)"
+            log_prob, utts.boundaries[u, :N] = forward_backward(
+                scores, math.log(1.0), N, self.n_slices_min, self.n_slices_max, u, anneal_temp,
+                uniform=self.uniform)
+        j_prev = None
+        for e in utts.get_segmented_embeds_i(u):
+            if e == -1:
+                continue
+            j_prev = self.gibbs_sample_inside_loop_i_embed(e, j_prev, anneal_temp if anneal_gibbs_am else 1)
+        self.lm.counts_from_utterance(self.get_unsup_transcript_i(u))
+        return log_prob
+
+    def gibbs_sample(self, n_iter, anneal_temps=None, anneal_gibbs_am=False, assignments_only=False,
+                     utt_orders=None):
+        """:545-694.  `utt_orders` pins random.shuffle; `anneal_temps` is the expanded schedule."""
+        record = {k: [] for k in ("sample_time", "log_marg", "log_marg*length", "log_prob_z",
+                                  "log_prob_X_given_z", "anneal_temp", "components", "n_tokens")}
+        for it in range(n_iter):
+            t0 = time.time()
+            temp = 1 if anneal_temps is None else anneal_temps[it]
+            if utt_orders is None:
+                order = list(range(self.utterances.D))
+                random.shuffle(order)
+            else:
+                order = list(utt_orders[it])
+            log_prob = 0
+            for u in order:
+                log_prob += self.gibbs_sample_i(u, temp, anneal_gibbs_am, assignments_only)
+            record["sample_time"].append(time.time() - t0)
+            record["log_marg"].append(self.log_marg())
+            record["log_marg*length"].append(log_prob)
+            record["log_prob_z"].append(self.log_prob_z())
+            record["log_prob_X_given_z"].append(self.acoustic_model.log_prob_X_given_z())
+            record["anneal_temp"].append(temp)
+            record["components"].append(self.acoustic_model.components.K)
+            record["n_tokens"].append(self.acoustic_model.get_n_assigned())
+        return record
+
 
 def frozen_kmeans_phase1(seg, utt_indices=None):
     """Pure part of the frozen sweep (means untouched): per utterance

@@ -420,3 +420,77 @@ def test_golden_kmeans_wordseg(init):
     npt.assert_array_equal(c.mean_numerators, z[p + "mean_numerators"])
     npt.assert_array_equal(rec["sum_neg_len_sqrd_norm"], z[p + "rec_sum_neg_len_sqrd_norm"])
     npt.assert_array_equal(rec["components"], z[p + "rec_components"])
+
+
+# ---------------------------------------------------------------------------
+# bigram LM + bigram cluster sampling (BASELINE configs[3])
+# ---------------------------------------------------------------------------
+
+def test_golden_bigram_lm():
+    """BigramSmoothLM (bigram_lms.py) on the data of the reference's own main() (:118-152)."""
+    z = G.load("bigram_lm.npz")
+    lm = so.BigramSmoothLM(0.1, 1., 2., 5)
+    data = [[1, 1, 3, 4, 0], [4, 4], [1, 0, 2, 2, 2, 2, 3, 1], [3, 3, 1]]
+    lm.counts_from_data(data)
+    npt.assert_array_equal(lm.unigram_counts, z["lm_unigram_counts"])
+    npt.assert_array_equal(lm.bigram_counts, z["lm_bigram_counts"])
+    npt.assert_array_equal(lm.prob_vec_i(), z["lm_prob_vec_i"])
+    npt.assert_array_equal(lm.log_prob_vec_i(), z["lm_log_prob_vec_i"])
+    for j in range(5):
+        npt.assert_array_equal(lm.prob_vec_given_j(j), z["lm_prob_vec_given_j"][j])
+        npt.assert_array_equal(lm.log_prob_vec_given_j(j), z["lm_log_prob_vec_given_j"][j])
+    # the reference's own checks (bigram_lms.py:136-152; its literal constants assume Python 2's integer a/K)
+    for i in range(5):
+        assert lm.prob_vec_i()[i] == lm.prob_i(i)
+        npt.assert_allclose(lm.prob_vec_given_j(3)[i], lm.prob_i_given_j(i, 3), rtol=1e-15)
+    npt.assert_allclose(lm.prob_i(1), (5. + 1. / 5) / (18 + 1.), rtol=1e-15)
+    lm.remove_counts_from_utterance(data[2])
+    npt.assert_array_equal(lm.unigram_counts, z["lm_unigram_counts_removed"])
+    npt.assert_array_equal(lm.bigram_counts, z["lm_bigram_counts_removed"])
+
+
+def _bigram_kw(tag):
+    if tag == "anneal":
+        return 0.8, {"anneal_gibbs_am": True}, True
+    if tag == "assign_only":
+        return 1.0, {"assignments_only": True}, False
+    return 1.0, {}, False
+
+
+@pytest.mark.parametrize("tag", ["plain", "anneal", "assign_only"])
+def test_golden_bigram_gibbs(tag):
+    """BigramAcousticWordseg(fb_type="unigram").gibbs_sample: identical samples, LM counts and traces
+    as the reference under the recorded uniform stream / utterance orders."""
+    z = G.load("bigram_%s.npz" % tag)
+    mats, vids, durs, lms = G.unpack_dicts(z)
+    lam, a, b = (float(v) for v in z["lm_params"])
+    lms_, kw, annealed = _bigram_kw(tag)
+    random.seed(6)
+    np.random.seed(6)
+    D = 16
+    prior = so.FixedVarPrior(0.002 * np.ones(D), np.zeros(D), 0.002 * np.ones(D) / 0.05)
+    seg = so.BigramAcousticWordseg(
+        9, prior, {"type": "smooth", "intrp_lambda": lam, "a": a, "b": b}, mats, vids, durs, lms,
+        p_boundary_init=0.5, beta_sent_boundary=-1, n_slices_max=4, lms=lms_, wip=-0.3, fb_type="unigram",
+        time_power_term=1.1, uniform=so.UniformSource(z["uniforms"]))
+    npt.assert_array_equal(seg.utterances.boundaries, z["init_boundaries"])
+    npt.assert_array_equal(seg.acoustic_model.components.assignments, z["init_assignments"])
+    npt.assert_array_equal(seg.lm.unigram_counts, z["init_unigram_counts"])
+    npt.assert_array_equal(seg.lm.bigram_counts, z["init_bigram_counts"])
+    npt.assert_allclose(seg.log_prob_z(), z["init_log_prob_z"], rtol=1e-13)
+    n_iter = len(z["rec_log_marg"])
+    rec = seg.gibbs_sample(n_iter, anneal_temps=list(z["rec_anneal_temp"]) if annealed else None,
+                           utt_orders=z["orders"], **kw)
+    assert seg.uniform.pos == len(z["uniforms"])
+    c = seg.acoustic_model.components
+    npt.assert_array_equal(seg.utterances.boundaries, z["boundaries"])
+    npt.assert_array_equal(c.assignments, z["assignments"])
+    npt.assert_array_equal(c.counts, z["counts"])
+    assert c.K == int(z["K"])
+    npt.assert_array_equal(seg.lm.unigram_counts, z["unigram_counts"])
+    npt.assert_array_equal(seg.lm.bigram_counts, z["bigram_counts"])
+    npt.assert_array_equal(c.counts, seg.lm.unigram_counts)          # the tie (:205-221) keeps them equal
+    npt.assert_allclose(c.mu_N_numerators, z["mu_N_numerators"], rtol=1e-13, atol=1e-12)
+    npt.assert_allclose(rec["log_marg"], z["rec_log_marg"], rtol=1e-12)
+    npt.assert_allclose(rec["log_marg*length"], z["rec_log_marg*length"], rtol=1e-12)
+    npt.assert_allclose(rec["log_prob_z"], z["rec_log_prob_z"], rtol=1e-12)
