@@ -184,6 +184,46 @@ int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t *d_items, 
                                 double anneal_temp, const double *uniforms, int64_t *u_counter,
                                 void *work, void *stream);
 
+/* ------------------------------------------------------------------ bigram LM + bigram cluster sampling (8f rank 4) */
+
+/* Device view of BigramSmoothLM (bigram_lms.py:18-113): the smoothed, interpolated
+ * maximum-likelihood bigram LM over the K = K_max component labels.  bigram_counts[j, i] =
+ * count of label i following label j (bigram_lms.py:36-38).  The counts are TIED to the
+ * acoustic model's components: when del_component moves the last component into slot k,
+ * the LM rows/columns move with it (gaussian_components_fixedvar.py:205-208, :218-221).   */
+typedef struct {
+    int32_t K;
+    double intrp_lambda, a, b;
+    int32_t *unigram_counts;   /* [K] */
+    int32_t *bigram_counts;    /* [K, K] row-major (j_prev, i_cur) */
+} segb_bigram_lm;
+
+/* segb_fixedvar_del_items with the LM tie: a component that empties takes its LM row, column
+ * and unigram count along when the last component moves into its slot.                      */
+int segb_fixedvar_del_items_lm(const segb_fixedvar *m, const segb_bigram_lm *lm, const int32_t *ids, int32_t n,
+                               const int32_t *relabel_ids, int64_t relabel_n, void *stream);
+/* counts_from_utterance (bigram_lms.py:98-105; sign = +1) / remove_counts_from_utterance
+ * (:107-113; sign = -1) for a transcript of n labels (device array).                        */
+int segb_bigram_lm_update(const segb_bigram_lm *lm, const int32_t *transcript, int32_t n, int32_t sign,
+                          void *stream);
+/* log_prob_vec_i (:64-69; j_prev < 0) or log(prob_vec_given_j(j_prev)) (:78-91): out[0..K).  */
+int segb_bigram_lm_log_prob_row(const segb_bigram_lm *lm, int32_t j_prev, double *out, void *stream);
+
+/* BigramAcousticWordseg.gibbs_sample_i (bigram_acoustic_wordseg.py:386-543, fb_type="unigram")
+ * for the utterances listed in h_order (HOST array), strictly sequential and without host
+ * synchronisation: remove the utterance's transcript from the LM and its tokens from the
+ * components (with the LM tie), score every candidate segment with log_marg_i_embed_unigram
+ * (:314-330; m->alpha must hold the LM's `a`, the counts are tied so the unigram term equals
+ * FBGMM.log_marg_i's), FFBS (skipped when assignments_only), then sample the new tokens'
+ * components left to right under the bigram prior (gibbs_sample_inside_loop_i_embed,
+ * :333-384: log_prob_vec_i for the first token, log prob_vec_given_j(previous label) after)
+ * and add the new transcript to the LM.  Buffers as segb_gibbs_sweep_fixedvar.                */
+int segb_gibbs_sweep_bigram(const segb_fixedvar *m, const segb_bigram_lm *lm, const segb_corpus *c,
+                            const int32_t *h_order, int32_t n_order, int32_t assignments_only,
+                            double time_power_term, double wip, double anneal_temp, int32_t anneal_gibbs_am,
+                            const double *uniforms, int64_t *u_counter, double *scratch_scores,
+                            double *log_probs, int32_t *status, void *stream);
+
 /* ------------------------------------------------------------------ k-means (A10-A12) */
 
 /* Device view of KMeansComponents (kmeans_components.py:18-91). `means` has X's

@@ -43,6 +43,11 @@ class KMeansM(ctypes.Structure):
                 ("counts", c_vp), ("assignments", c_vp), ("K", c_vp)]
 
 
+class BigramLM(ctypes.Structure):
+    _fields_ = [("K", c_i32), ("intrp_lambda", c_f64), ("a", c_f64), ("b", c_f64), ("unigram_counts", c_vp),
+                ("bigram_counts", c_vp)]
+
+
 _PROTOS = {
     "segb_last_error": (ctypes.c_char_p, []),
     "segb_version": (ctypes.c_int, []),
@@ -90,6 +95,13 @@ _PROTOS = {
     "segb_fvmma_w_tiles_bytes": (c_i64, [c_i32, c_i32]),
     "segb_fvmma_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "segb_fvmma_log_marg": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "segb_fixedvar_del_items_lm": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(BigramLM), c_vp, c_i32, c_vp,
+                                                  c_i64, c_vp]),
+    "segb_bigram_lm_update": (ctypes.c_int, [ctypes.POINTER(BigramLM), c_vp, c_i32, c_i32, c_vp]),
+    "segb_bigram_lm_log_prob_row": (ctypes.c_int, [ctypes.POINTER(BigramLM), c_i32, c_vp, c_vp]),
+    "segb_gibbs_sweep_bigram": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(BigramLM), ctypes.POINTER(Corpus),
+                                               c_vp, c_i32, c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                               c_vp, c_vp]),
     "segb_fixedvar_log_marg_k_work_bytes": (c_i64, [c_i32, c_i32]),
     "segb_fixedvar_log_marg_k": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "segb_kmeans_sum_neg_sqrd_norm_k": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_vp]),

@@ -87,10 +87,28 @@ __device__ void fv_add_item(const segb_fixedvar &m, int id, int k, double *tmp) 
 }
 
 // del_component (:190-221): move the last component into slot k, relabel its members.
-__device__ void fv_del_component(const segb_fixedvar &m, int k, const int32_t *relabel_ids, int64_t relabel_n) {
+__device__ void fv_del_component(const segb_fixedvar &m, int k, const int32_t *relabel_ids, int64_t relabel_n,
+                                 const segb_bigram_lm *lm = nullptr) {
     const int D = m.D, KM = m.K_max;
     const int last = *m.K - 1;
     __syncthreads();
+    if (lm) {
+        // tied bigram LM counts move with the component (:205-208), in the reference's order: the
+        // unigram count, then row `last` -> row k, then column `last` -> column k; then the old
+        // slot is cleared (:218-221)
+        const int KL = lm->K;
+        int32_t *bi = lm->bigram_counts;
+        if (k != last) {
+            if (threadIdx.x == 0) lm->unigram_counts[k] = lm->unigram_counts[last];
+            for (int i = threadIdx.x; i < KL; i += blockDim.x) bi[(size_t)k * KL + i] = bi[(size_t)last * KL + i];
+            __syncthreads();
+            for (int j = threadIdx.x; j < KL; j += blockDim.x) bi[(size_t)j * KL + k] = bi[(size_t)j * KL + last];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) lm->unigram_counts[last] = 0;
+        for (int i = threadIdx.x; i < KL; i += blockDim.x) { bi[(size_t)last * KL + i] = 0; bi[(size_t)i * KL + last] = 0; }
+        __syncthreads();
+    }
     if (k != last) {
         for (int d = threadIdx.x; d < D; d += blockDim.x) {
             const size_t a = (size_t)d * KM + k, b = (size_t)d * KM + last;
@@ -124,7 +142,7 @@ __device__ void fv_del_component(const segb_fixedvar &m, int k, const int32_t *r
 }
 
 __device__ void fv_del_item(const segb_fixedvar &m, int id, double *tmp, const int32_t *relabel_ids,
-                            int64_t relabel_n) {
+                            int64_t relabel_n, const segb_bigram_lm *lm = nullptr) {
     __syncthreads();
     const int k = m.assignments[id];
     if (k == -1) return;            // uniform across the block
@@ -134,7 +152,7 @@ __device__ void fv_del_item(const segb_fixedvar &m, int id, double *tmp, const i
     if (threadIdx.x == 0) { m.counts[k] = cnt; m.assignments[id] = -1; *m.n_total -= 1; }
     __syncthreads();
     if (cnt == 0) {
-        fv_del_component(m, k, relabel_ids, relabel_n);
+        fv_del_component(m, k, relabel_ids, relabel_n, lm);
     } else {
         const int D = m.D, KM = m.K_max;
         for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -321,6 +339,13 @@ __global__ void __launch_bounds__(256) fv_del_list_kernel(segb_fixedvar m, const
         if (ids[i] >= 0) fv_del_item(m, ids[i], smem, relabel_ids, relabel_n);
 }
 
+__global__ void __launch_bounds__(256) fv_del_list_lm_kernel(segb_fixedvar m, segb_bigram_lm lm, const int32_t *ids, int n,
+                                                             const int32_t *relabel_ids, int64_t relabel_n) {
+    extern __shared__ double smem[];
+    for (int i = 0; i < n; ++i)
+        if (ids[i] >= 0) fv_del_item(m, ids[i], smem, relabel_ids, relabel_n, &lm);
+}
+
 // ---------------------------------------------------------------- per-utterance Gibbs steps
 
 // Remove the current tokens of utterance u from the model (unigram_acoustic_wordseg.py:270-273).
@@ -404,6 +429,139 @@ __global__ void __launch_bounds__(1024) fv_assign_utt_kernel(segb_fixedvar m, se
     }
     __syncthreads();
     if (mode == 0 && threadIdx.x == 0) *u_counter = upos;
+}
+
+// ---------------------------------------------------------------- bigram LM + bigram cluster sampling
+
+// counts_from_utterance (+1, bigram_lms.py:98-105) / remove_counts_from_utterance (-1, :107-113):
+// a handful of dependent integer updates -- one thread.
+__device__ void lm_update(const segb_bigram_lm &lm, const int32_t *tr, int n, int sign) {
+    if (threadIdx.x == 0) {
+        int j_prev = -1;
+        for (int t = 0; t < n; ++t) {
+            const int i = tr[t];
+            if (i < 0) continue;
+            lm.unigram_counts[i] += sign;
+            if (j_prev >= 0) lm.bigram_counts[(size_t)j_prev * lm.K + i] += sign;
+            j_prev = i;
+        }
+    }
+    __syncthreads();
+}
+
+// sum_ints(unigram_counts) (_cython_utils.pyx), exact: block-wide integer sum.  red: >= 33 doubles.
+__device__ long long lm_total(const segb_bigram_lm &lm, double *red) {
+    long long t = 0;
+    for (int k = threadIdx.x; k < lm.K; k += blockDim.x) t += lm.unigram_counts[k];
+    return (long long)block_sum((double)t, red);      // partial sums are far below 2^53: exact
+}
+
+// One slot of log_prob_vec_i (:64-69) or log(prob_vec_given_j) (:78-91), NumPy's operation order,
+// every operation separately rounded.
+__device__ __forceinline__ double lm_log_prob(const segb_bigram_lm &lm, int j_prev, int k, double sum_a) {
+    const double uk = __dadd_rn((double)lm.unigram_counts[k], __ddiv_rn(lm.a, (double)lm.K));
+    if (j_prev < 0) return __dsub_rn(log(uk), log(sum_a));
+    const double pv = __ddiv_rn(uk, sum_a);
+    const double bj = __dadd_rn((double)lm.bigram_counts[(size_t)j_prev * lm.K + k], __ddiv_rn(lm.b, (double)lm.K));
+    const double t2 = __ddiv_rn(__dmul_rn(__dsub_rn(1., lm.intrp_lambda), bj), __dadd_rn((double)lm.unigram_counts[j_prev], lm.b));
+    return log(__dadd_rn(__dmul_rn(lm.intrp_lambda, pv), t2));
+}
+
+__global__ void __launch_bounds__(256) bg_lm_update_kernel(segb_bigram_lm lm, const int32_t *tr, int n, int sign) {
+    lm_update(lm, tr, n, sign);
+}
+
+__global__ void __launch_bounds__(256) bg_lm_row_kernel(segb_bigram_lm lm, int j_prev, double *out) {
+    __shared__ double red[40];
+    const double sum_a = __dadd_rn((double)lm_total(lm, red), lm.a);
+    for (int k = threadIdx.x; k < lm.K; k += blockDim.x) out[k] = lm_log_prob(lm, j_prev, k, sum_a);
+}
+
+// gibbs_sample_i, first part (bigram_acoustic_wordseg.py:410-417): the utterance's transcript leaves the
+// LM, then its tokens leave the components (the LM tie follows every component move).
+__global__ void __launch_bounds__(256) bg_remove_utt_kernel(segb_fixedvar m, segb_bigram_lm lm, segb_corpus c, int u) {
+    extern __shared__ double smem[];
+    const int64_t off = c.pos_off[u];
+    const int N = (int)(c.pos_off[u + 1] - off);
+    if (threadIdx.x == 0) {
+        int j_prev = -1;
+        for (int j = 0; j < N; ++j) {
+            const int id = c.tok_id[off + j];
+            if (id < 0) continue;
+            const int i = m.assignments[id];
+            lm.unigram_counts[i] -= 1;
+            if (j_prev >= 0) lm.bigram_counts[(size_t)j_prev * lm.K + i] -= 1;
+            j_prev = i;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < N; ++j) {
+        const int id = c.tok_id[off + j];
+        if (id >= 0) fv_del_item(m, id, smem, c.tok_id, c.n_pos, &lm);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) c.tok_id[off + j] = -1;
+}
+
+// gibbs_sample_inside_loop_i_embed (:333-384) for the item staged in s.xs.
+__device__ int bg_choose(const segb_fixedvar &m, const segb_bigram_lm &lm, ScoreSmem &s, int j_prev,
+                         double anneal_temp, double u) {
+    const int K = *m.K, KM = m.K_max;
+    fv_post_pred_all(m, s.xs, s.sk, K);
+    const double lprior = fv_log_prior_x(m, s.xs, s.red);
+    const double sum_a = __dadd_rn((double)lm_total(lm, s.red), lm.a);
+    double mx = neg_inf();
+    for (int k = threadIdx.x; k < KM; k += blockDim.x) {
+        const double v = __dadd_rn(__dmul_rn(lm_log_prob(lm, j_prev, k, sum_a), m.lms), (k < K ? s.sk[k] : lprior));
+        s.sk[k] = v;
+        mx = fmax(mx, v);
+    }
+    return fv_decide(s, K, KM, 0, anneal_temp, u, mx);
+}
+
+// gibbs_sample_i, last part (:483-499): sample the new tokens' components left to right under the
+// bigram prior, then add the new transcript to the LM.  When the boundaries are kept
+// (assignments_only) the tokens are those of the current segmentation.
+__global__ void __launch_bounds__(1024) bg_assign_utt_kernel(segb_fixedvar m, segb_bigram_lm lm, segb_corpus c, int u,
+                                                             double anneal_temp, const double *uniforms,
+                                                             int64_t *u_counter, const int32_t *dp_status) {
+    extern __shared__ double smem[];
+    ScoreSmem s(smem, m.D);
+    if (dp_status && *dp_status != SEGB_DP_OK) return;
+    const int64_t off = c.pos_off[u];
+    const int N = (int)(c.pos_off[u + 1] - off);
+    int64_t upos = *u_counter;
+    int j_prev = 0, k_prev = -1;
+    for (int j = 0; j < N; ++j) {
+        if (!c.bounds[off + j]) continue;
+        const int t = j + 1, l = t - j_prev;
+        j_prev = j + 1;
+        const int id = (l <= c.S) ? c.seg_id[(off + t - 1) * c.S + (l - 1)] : -1;
+        __syncthreads();
+        if (threadIdx.x == 0) c.tok_id[off + j] = id;
+        if (id < 0) continue;       // back-tracking leftovers are skipped (:485-487)
+        for (int d = threadIdx.x; d < m.D; d += blockDim.x) s.xs[d] = fv_x(m, id, d);
+        __syncthreads();
+        int k = bg_choose(m, lm, s, k_prev, anneal_temp, uniforms[upos++]);
+        __syncthreads();
+        const int Kact = *m.K;
+        if (k > Kact) k = Kact;     // several empty slots may follow the active ones (:371-372)
+        fv_add_item(m, id, k, s.sk);
+        k_prev = k;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *u_counter = upos;
+        int jp = -1;                // counts_from_utterance over the new transcript (:499)
+        for (int j = 0; j < N; ++j) {
+            const int id = c.tok_id[off + j];
+            if (id < 0) continue;
+            const int i = m.assignments[id];
+            lm.unigram_counts[i] += 1;
+            if (jp >= 0) lm.bigram_counts[(size_t)jp * lm.K + i] += 1;
+            jp = i;
+        }
+    }
 }
 
 static int score_smem_attr(const void *fn, size_t bytes) {
@@ -499,6 +657,71 @@ extern "C" int segb_gibbs_sweep_fixedvar(const segb_fixedvar *m, const segb_corp
                             log_probs + i, status + i, st);
         if (r) return r;
         fv_assign_utt_kernel<<<1, 1024, bytes, st>>>(*m, *c, u, assign_mode, assign_temp, uniforms, u_counter, status + i);
+        SEGB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int segb_fixedvar_del_items_lm(const segb_fixedvar *m, const segb_bigram_lm *lm, const int32_t *ids, int32_t n,
+                                          const int32_t *relabel_ids, int64_t relabel_n, void *stream) {
+    SEGB_CHECK_ARG(m && lm && ids && n >= 0 && lm->K == m->K_max, "null pointer");
+    if (n == 0) return 0;
+    fv_del_list_lm_kernel<<<1, 256, sizeof(double) * m->D, (cudaStream_t)stream>>>(*m, *lm, ids, n, relabel_ids, relabel_n);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_bigram_lm_update(const segb_bigram_lm *lm, const int32_t *transcript, int32_t n, int32_t sign,
+                                     void *stream) {
+    SEGB_CHECK_ARG(lm && lm->unigram_counts && lm->bigram_counts && (sign == 1 || sign == -1) && n >= 0, "bigram lm");
+    if (n == 0) return 0;
+    SEGB_CHECK_ARG(transcript, "null pointer");
+    bg_lm_update_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*lm, transcript, n, sign);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_bigram_lm_log_prob_row(const segb_bigram_lm *lm, int32_t j_prev, double *out, void *stream) {
+    SEGB_CHECK_ARG(lm && lm->unigram_counts && lm->bigram_counts && out && j_prev < lm->K, "bigram lm");
+    bg_lm_row_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*lm, j_prev, out);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_gibbs_sweep_bigram(const segb_fixedvar *m, const segb_bigram_lm *lm, const segb_corpus *c,
+                                       const int32_t *h_order, int32_t n_order, int32_t assignments_only,
+                                       double time_power_term, double wip, double anneal_temp,
+                                       int32_t anneal_gibbs_am, const double *uniforms, int64_t *u_counter,
+                                       double *scratch_scores, double *log_probs, int32_t *status, void *stream) {
+    SEGB_CHECK_ARG(m && lm && c && h_order && scratch_scores && log_probs && status && uniforms && u_counter, "null pointer");
+    SEGB_CHECK_ARG(lm->K == m->K_max && lm->unigram_counts && lm->bigram_counts, "the LM covers the K_max component labels");
+    SEGB_CHECK_ARG(m->model == SEGB_MODEL_FIXEDVAR, "bigram sampling: fixed-variance components");
+    SEGB_CHECK_ARG(c->tok_id && c->bounds, "corpus needs bounds and tok_id");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bytes = ScoreSmem::bytes(m->D, m->K_max);
+    int r;
+    if ((r = score_smem_attr((const void *)fv_score_utt_kernel, bytes))) return r;
+    if ((r = score_smem_attr((const void *)bg_assign_utt_kernel, bytes))) return r;
+    const int score_blocks = c->N_max * c->S;
+    const double assign_temp = anneal_gibbs_am ? anneal_temp : 1.0;
+    for (int i = 0; i < n_order; ++i) {
+        const int u = h_order[i];
+        SEGB_CHECK_ARG(u >= 0 && u < c->n_utt, "utterance index");
+        // remove_utt clears tok_id; when the boundaries are kept they are re-derived from `bounds` by the assign kernel
+        bg_remove_utt_kernel<<<1, 256, sizeof(double) * m->D, st>>>(*m, *lm, *c, u);
+        SEGB_LAUNCH_CHECK();
+        if (!assignments_only) {
+            fv_score_utt_kernel<<<score_blocks, 256, bytes, st>>>(*m, *c, u, time_power_term, wip, scratch_scores);
+            SEGB_LAUNCH_CHECK();
+            r = launch_dp_local(c, u, scratch_scores, SEGB_DP_FFBS, 0.0, anneal_temp, uniforms, u_counter,
+                                log_probs + i, status + i, st);
+            if (r) return r;
+        } else {
+            SEGB_CUDA(cudaMemsetAsync(log_probs + i, 0, sizeof(double), st));
+            SEGB_CUDA(cudaMemsetAsync(status + i, 0, sizeof(int32_t), st));
+        }
+        bg_assign_utt_kernel<<<1, 1024, bytes, st>>>(*m, *lm, *c, u, assign_temp, uniforms, u_counter,
+                                                     assignments_only ? nullptr : status + i);
         SEGB_LAUNCH_CHECK();
     }
     return 0;

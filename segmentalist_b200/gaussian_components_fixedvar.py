@@ -38,7 +38,6 @@ class GaussianComponentsFixedVar(object):
 
     def __init__(self, X, prior, assignments=None, K_max=None, lm=None, alpha=1.0, lms=1.0):
         assert K_max is not None, "To-do: remove this, always require `K_max`"   # :88-89
-        assert lm is None, "language-model tie-in is outside the accelerated path"
         X = np.ascontiguousarray(X)
         if X.dtype not in (np.float32, np.float64):
             X = X.astype(np.float64)
@@ -49,7 +48,8 @@ class GaussianComponentsFixedVar(object):
         self.mu_0 = np.asarray(prior.mu_0, dtype=np.float64) * np.ones(self.D)
         self.precision_0 = np.asarray(1. / prior.var_0, dtype=np.float64) * np.ones(self.D)
         self._cached_neg_half_D_log_2pi = -0.5 * self.D * math.log(2. * np.pi)
-        self.lm = None
+        self.lm = lm                  # tied bigram LM (bigram_lms.BigramSmoothLM): its counts follow del_component, :205-221
+        assert lm is None or lm.K == self.K_max
 
         dv, z = _lib.dev, lambda *s: torch.zeros(*s, dtype=torch.float64, device="cuda")
         _lib.lib()
@@ -172,6 +172,11 @@ class GaussianComponentsFixedVar(object):
         m = self.struct()
         ids_d = _lib.dev(np.asarray([i], dtype=np.int32))
         rel = self._relabel
+        if self.lm is not None:
+            _lib.check(_lib.lib().segb_fixedvar_del_items_lm(
+                m, self.lm.struct(), _lib.ptr(ids_d), 1, _lib.ptr(rel), 0 if rel is None else rel.numel(),
+                _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().segb_fixedvar_del_items(
             m, _lib.ptr(ids_d), 1, _lib.ptr(rel), 0 if rel is None else rel.numel(), _lib.stream_ptr()))
 
