@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--only-gibbs", action="store_true", help="run only the secondary Gibbs workload")
     ap.add_argument("--diag-utts", type=int, default=48)
     ap.add_argument("--only-diag", action="store_true", help="run only the diagonal-covariance secondary workload")
+    ap.add_argument("--bigram-utts", type=int, default=400)
+    ap.add_argument("--only-bigram", action="store_true", help="run only the bigram cluster-sampling secondary workload")
     return ap.parse_args()
 
 
@@ -414,6 +416,68 @@ def run_diag_extra(args):
     return out
 
 
+def run_bigram_extra(args):
+    """BASELINE configs[3]: bigram FBGMM cluster sampling (bigram_acoustic_wordseg, smoothed ML bigram LM),
+    D=130, K=5000, max_span 6, through the reference-facing API: one full sweep (segmentation + bigram
+    assignment sampling) and one assignments-only sweep (pure cluster sampling); CPU oracle timed on the
+    first utterances of the same seeded corpus (also a parity check)."""
+    import random
+
+    import torch
+    from oracle import seg_oracle as so
+    from segmentalist_b200 import bigram_acoustic_wordseg as baw, gaussian_components_fixedvar as gcf, synth
+    K, n_utt = 5000, args.bigram_utts
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K, n_min=N_LO, n_max=N_HI,
+                                                    n_slices_max=S_MAX, noise=NOISE, seed=41)
+    var = 0.002 * np.ones(D)
+    lm_params = {"type": "smooth", "intrp_lambda": 0.1, "a": 10.0, "b": 10.0}
+
+    def build(mod, prior):
+        random.seed(4)
+        np.random.seed(4)
+        return mod.BigramAcousticWordseg(K, prior, lm_params, mats, vids, durs, lms, p_boundary_init=0.5,
+                                         beta_sent_boundary=-1, n_slices_max=S_MAX, fb_type="unigram")
+    seg = build(baw, gcf.FixedVarPrior(var, np.zeros(D), var / 0.05))
+    order = list(range(n_utt))
+    seg._sweep(order, 1, False, False)                # warm-up sweep
+    torch.cuda.synchronize()
+    n_tok = seg.acoustic_model.get_n_assigned()
+    t0 = time.perf_counter()
+    seg._sweep(order, 1, False, False)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    seg._sweep(order, 1, False, True)
+    torch.cuda.synchronize()
+    wall_a = time.perf_counter() - t0
+    n_seg = int(sum(m.shape[0] for m in mats.values()))
+    out = {"workload": "bigram_fbgmm_cluster_sampling D=130 K=5000 U=%d max_span=6 (BASELINE configs[3])" % n_utt,
+           "utt_per_s": n_utt / wall, "ms_per_sweep": wall * 1e3, "candidate_segments": n_seg,
+           "assignments_only": {"ms_per_sweep": wall_a * 1e3, "tokens": int(n_tok), "tokens_per_s": n_tok / wall_a,
+                                "note": "one K_max-slot draw per token under the bigram prior row of the previous label"},
+           "K_active": seg.acoustic_model.components.K, "dtype": "f64",
+           "note": "four launches per utterance on one stream, no host synchronisation inside a sweep"}
+    if not args.no_cpu:
+        n_cpu = 4
+        oseg = build(so, so.FixedVarPrior(var, np.zeros(D), var / 0.05))
+        gseg = build(baw, gcf.FixedVarPrior(var, np.zeros(D), var / 0.05))
+        st = random.getstate()
+        t0 = time.perf_counter()
+        for u in range(n_cpu):
+            oseg.gibbs_sample_i(u)
+        dt = time.perf_counter() - t0
+        random.setstate(st)
+        gseg._sweep(list(range(n_cpu)), 1, False, False)
+        same = bool(np.array_equal(gseg.utterances.boundaries[:n_cpu], oseg.utterances.boundaries[:n_cpu]) and
+                    np.array_equal(gseg.acoustic_model.components.assignments,
+                                   oseg.acoustic_model.components.assignments) and
+                    np.array_equal(gseg.lm.unigram_counts, oseg.lm.unigram_counts))
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "utt/s", "cores": 1, "kind": "port",
+                               "sample": "%d gibbs_sample_i calls of the same seeded corpus/model" % n_cpu,
+                               "seconds": dt, "identical_samples_on_sample": same}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -656,8 +720,12 @@ def run_ours(args):
                                   "oracle port of the reference's pure functions" % (n_s, int((ids >= 0).sum()), args.K),
                         "seconds": dt, "parity_with_gpu_on_sample": parity}
 
-    gibbs, diag_x = None, None
+    gibbs, diag_x, bigram_x = None, None, None
     if rank == 0 and world == 1 and not args.no_gibbs:
+        try:
+            bigram_x = run_bigram_extra(args)
+        except Exception as exc:
+            bigram_x = {"error": repr(exc)}
         try:
             gibbs = run_gibbs_extra(args)
         except Exception as exc:                      # the headline line must still be printed
@@ -682,7 +750,7 @@ def run_ours(args):
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "roofline_dp": roofline_dp, "roofline_fixedvar_logmarg": roofline_fv, "cpu_baseline": cpu_baseline, "phases_ms": phases,
-            "secondary_gibbs_fixedvar": gibbs, "secondary_gibbs_diag": diag_x,
+            "secondary_gibbs_fixedvar": gibbs, "secondary_gibbs_diag": diag_x, "secondary_bigram": bigram_x,
         }
         print(json.dumps(line))
     if world > 1:
@@ -697,6 +765,8 @@ def main():
         print(json.dumps({"secondary_gibbs_fixedvar": run_gibbs_extra(args)}))
     elif args.only_diag:
         print(json.dumps({"secondary_gibbs_diag": run_diag_extra(args)}))
+    elif args.only_bigram:
+        print(json.dumps({"secondary_bigram": run_bigram_extra(args)}))
     else:
         run_ours(args)
 
