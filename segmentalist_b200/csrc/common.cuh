@@ -156,6 +156,18 @@ __device__ T pairwise_sum(F f, int n) {
 // group's first lane, which then adds the n % 8 leftovers one by one; the second 8-lane group
 // takes the second block when n > 128.  Bit-identical to pairwise_sum<T>(f, n).  `hmask` = the
 // 16 participating lanes of the warp, `j` = lane index within them; result on all 16 lanes.
+// pairwise_sum for the sizes that occur per embedding (n <= 256): at most ONE split, so no recursion
+// stack (the general routine keeps its stack in local memory).  Bit-identical to pairwise_sum<T>(f, n).
+template <typename T, typename F>
+__device__ __forceinline__ T pairwise_sum_le256(F f, int n) {
+    if (n <= 128) return pairwise_block<T>(f, 0, n);
+    if (n <= 256) {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return add_rn<T>(pairwise_block<T>(f, 0, n2), pairwise_block<T>(f, n2, n - n2));
+    }
+    return pairwise_sum<T>(f, n);
+}
 template <typename T, typename F>
 __device__ __forceinline__ T pairwise_sum_lanes16(F f, int n, unsigned hmask, int j) {
     const int g = j >> 3, q = j & 7;

@@ -51,36 +51,36 @@ struct GibbsParams {
     double *seg_prior;             // [M_cap] log_prior of every candidate
     double *scores;                // [M_cap] banded scores of the current utterance
     double *v;                     // [2][K_max] slot log-probabilities of the current token (double-buffered)
+    unsigned long long *prof;      // optional [16] per-phase clock totals of CTA 0 (development aid), or NULL
 };
 
-// Sense-reversing grid barrier (all CTAs are co-resident: cooperative launch).  A protocol bug
-// traps instead of hanging the GPU.
+// Grid barrier (all CTAs are co-resident: cooperative launch) on ONE monotonic counter: CTA-wide
+// bar.sync, then thread 0 arrives with a release-add and polls with acquire loads until the counter
+// reaches the next multiple of the grid size -- one L2 round trip to arrive, no reset / generation
+// write by the last arriver (the sense-reversing version cost ~4 us per barrier on the per-token
+// critical path).  The counter is zeroed by the host before every launch; a protocol bug traps
+// instead of hanging the GPU.
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned tag = 0, unsigned h = 0) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        volatile unsigned *vgen = bar + 1;
-        volatile unsigned *trace = bar + 16;                 // [n_blocks] last barrier tag of every CTA (diagnostics)
+        unsigned *trace = bar + 16;                          // [n_blocks] last barrier tag of every CTA (diagnostics)
         trace[blockIdx.x] = tag;
-        volatile unsigned *trace2 = bar + 16 + 160;
-        trace2[blockIdx.x] = h;
-        const unsigned gen = *vgen;
-        if (atomicAdd(bar, 1u) == n_blocks - 1) {
-            *bar = 0;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            unsigned spins = 0;
-            while (*vgen == gen) {
-                if (++spins > (1u << 23)) {
-                    printf("segb gibbs: grid barrier timed out: block %d at tag %x; tags of blocks 0..7: %x %x %x %x %x %x %x %x; state %x %x %x %x %x %x %x %x\n",
-                           blockIdx.x, tag, trace[0], trace[1], trace[2], trace[3], trace[4], trace[5], trace[6], trace[7],
-                           trace2[0], trace2[1], trace2[2], trace2[3], trace2[4], trace2[5], trace2[6], trace2[7]);
-                    __trap();
-                }
+        trace[160 + blockIdx.x] = h;
+        unsigned old, cur;
+        asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+        const unsigned target = (old / n_blocks + 1) * n_blocks;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+            if ((int)(cur - target) >= 0) break;
+            if (++spins > (1u << 23)) {
+                volatile unsigned *vt = trace;
+                printf("segb gibbs: grid barrier timed out: block %d at tag %x; tags of blocks 0..7: %x %x %x %x %x %x %x %x; state %x %x %x %x %x %x %x %x\n",
+                       blockIdx.x, tag, vt[0], vt[1], vt[2], vt[3], vt[4], vt[5], vt[6], vt[7],
+                       vt[160], vt[161], vt[162], vt[163], vt[164], vt[165], vt[166], vt[167]);
+                __trap();
             }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -99,6 +99,7 @@ struct GibbsSmem {
     double *tmp;                   // [D]
     double *bk;                    // [3 D + 1] cached statistics of one component (whole-model sweeps)
     int32_t *counts;               // [K_max] replicated
+    int32_t *sid;                  // [M_cap] embedding id of every banded slot of the current utterance
     int32_t *tok;                  // [N_cap] ids of the tokens being removed
     int32_t *tk;                   // [N_cap] their components (snapshot taken before anything is modified)
     uint8_t *bo;                   // [N_cap]
@@ -106,11 +107,21 @@ struct GibbsSmem {
 
 __host__ __device__ inline size_t gibbs_smem_bytes(int D, int K_max, int per, int xb, int M_cap, int N_cap) {
     size_t d = (size_t)4 * per * D + 5 * per + (size_t)xb * D + (size_t)xb * per + 40 + K_max + M_cap + (N_cap + 1) + D + (3 * D + 1);
-    return d * 8 + (size_t)K_max * 4 + (size_t)N_cap * 8 + ((N_cap + 15) / 16) * 16 + 64;
+    return d * 8 + (size_t)K_max * 4 + (size_t)M_cap * 4 + (size_t)N_cap * 8 + ((N_cap + 15) / 16) * 16 + 64;
 }
 
 // per-dimension term of the predictive sum: fixed variance ((mu-x)^2 * prec_pred, :247-252) or
 // diagonal (log(1 + (m-x)^2 * inv_var / v), gaussian_components_diag.py:255-258)
+// (branch-free variants: with the model test inside, every term is its own basic block and the eight
+// independent accumulators of the pairwise sum are no longer interleaved -- ~100 clocks per term)
+__device__ __forceinline__ double pred_term_fixed(double mu, double pp, double x) {
+    const double dl = __dsub_rn(mu, x);
+    return __dmul_rn(__dmul_rn(dl, dl), pp);
+}
+__device__ __forceinline__ double pred_term_diag(double mu, double pp, double x, double iv) {
+    const double dl = __dsub_rn(mu, x);
+    return log(__dadd_rn(1., __dmul_rn(__dmul_rn(__dmul_rn(dl, dl), pp), iv)));
+}
 __device__ __forceinline__ double pred_term(bool diag, double mu, double pp, double x, double iv) {
     const double dl = __dsub_rn(mu, x);
     const double q = __dmul_rn(__dmul_rn(dl, dl), pp);
@@ -119,6 +130,82 @@ __device__ __forceinline__ double pred_term(bool diag, double mu, double pp, dou
 // predictive log-density from the summed terms
 __device__ __forceinline__ double pred_value(bool diag, double acc, double c0, double lpp, double cst, double hv) {
     return diag ? ((cst - 0.5 * lpp) - hv * acc) : ((c0 + 0.5 * lpp) - 0.5 * acc);
+}
+
+// gibbs_sample_inside_loop_i's draw (fbgmm.py:441-463, no annealing) on the per-token critical path of the
+// cooperative sweep.  Same decision as fv_decide, restructured for latency: every thread owns a contiguous
+// chunk of the K_max slot values (independent loads), ONE exponential per slot, the draw is taken in the
+// unnormalised domain (first k with u * sum - prefix_k < 0, prefix over e_k = exp(v_k - max)), and the three
+// block-wide exchanges (max; chunk sums = total + scan bases; first hit + margin) cost one barrier each.
+// Whenever a prefix comes within 1e-9 (relative to the total) of the threshold -- where summation order
+// could change the answer -- thread 0 repeats the reference's serial subtraction over exp(v_k - lse).
+// red: >= 32 doubles of shared scratch.  Block-uniform, identical on every CTA.
+constexpr int DECIDE_PER = 8;
+__device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *red) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = GB_THREADS >> 5;
+    const int per = (KM + GB_THREADS - 1) / GB_THREADS;
+    const int lo = min(tid * per, KM), hi = min(lo + per, KM);
+    double v[DECIDE_PER];
+#pragma unroll
+    for (int i = 0; i < DECIDE_PER; ++i) v[i] = (lo + i < hi) ? __ldcg(vbuf + lo + i) : neg_inf();
+    double mx = v[0];
+#pragma unroll
+    for (int i = 1; i < DECIDE_PER; ++i) mx = fmax(mx, v[i]);
+    mx = warp_max(mx);
+    if (lane == 0) red[w] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < nw; ++i) mx = fmax(mx, red[i]);
+    double loc = 0.0;
+#pragma unroll
+    for (int i = 0; i < DECIDE_PER; ++i) { v[i] = (lo + i < hi) ? exp(v[i] - mx) : 0.0; loc += v[i]; }
+    double inc = loc;                       // inclusive scan of the chunk sums inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) red[8 + w] = inc;
+    __syncthreads();
+    double base = 0.0, sum = 0.0;
+    for (int i = 0; i < nw; ++i) { const double t = red[8 + i]; if (i < w) base += t; sum += t; }
+    const double target = u * sum;
+    double run = base + inc - loc, margin = CUDART_INF;
+    int first = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < DECIDE_PER; ++i) {
+        if (lo + i < hi) {
+            run += v[i];
+            const double r = target - run;
+            margin = fmin(margin, fabs(r));
+            if (r < 0 && first == 0x7fffffff) first = lo + i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        margin = fmin(margin, __shfl_xor_sync(FULL, margin, o));
+        first = min(first, __shfl_xor_sync(FULL, first, o));
+    }
+    if (lane == 0) { red[16 + w] = margin; red[24 + w] = (double)first; }
+    __syncthreads();
+    margin = red[16];
+    double gfirst = red[24];
+    for (int i = 1; i < nw; ++i) { margin = fmin(margin, red[16 + i]); gfirst = fmin(gfirst, red[24 + i]); }
+    int k_sel = (gfirst > 2.0e9) ? KM - 1 : (int)gfirst;
+    if (margin < 1e-9 * sum) {
+        if (tid == 0) {                     // utils.draw (utils.py:10-21) verbatim
+            const double lse = log(sum) + mx;
+            double uu = u;
+            int r = KM - 1;
+            for (int k = 0; k < KM; ++k) { uu = uu - exp(__ldcg(vbuf + k) - lse); if (uu < 0) { r = k; break; } }
+            red[32] = (double)r;
+        }
+        __syncthreads();
+        k_sel = (int)red[32];
+    }
+    __syncthreads();                        // red is reused by the caller
+    if (k_sel > K) k_sel = K;               // several empty slots at the end (fbgmm.py:459-460)
+    return k_sel;
 }
 
 __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) {
@@ -155,12 +242,21 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         s.tmp = q; q += D;
         s.bk = q; q += 3 * D + 1;
         s.counts = reinterpret_cast<int32_t *>(q);
-        s.tok = s.counts + KM;
+        s.sid = s.counts + KM;
+        s.tok = s.sid + p.M_cap;
         s.tk = s.tok + c.N_max;
         s.bo = reinterpret_cast<uint8_t *>(s.tk + c.N_max);
     }
     ScoreSmem ds(s.xs, D);          // only .red / .sk are used by fv_decide
     ds.red = s.red; ds.sk = s.sk;
+    long long t_last = clock64();
+    auto tick = [&](int ph) {
+        if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+            const long long now = clock64();
+            p.prof[ph] += (unsigned long long)(now - t_last);
+            t_last = now;
+        }
+    };
 
     // ---- load the owned statistics and the replicated state
     for (int i = tid; i < n_own * D; i += GB_THREADS) {
@@ -348,7 +444,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                 const double *mu = s.mu + kl * D, *pp = s.pp + kl * D;
                 const double iv = diag ? s.iv[kl] : 0.;
                 auto term = [&](int d) { return pred_term(diag, mu[d], pp[d], s.xs[d], iv); };
-                const double acc = (D <= 256) ? pairwise_sum_lanes16<double>(term, D, hmask, jl)
+                auto term_f = [&](int d) { return pred_term_fixed(mu[d], pp[d], s.xs[d]); };
+                auto term_d = [&](int d) { return pred_term_diag(mu[d], pp[d], s.xs[d], iv); };
+                const double acc = (D <= 256) ? (diag ? pairwise_sum_lanes16<double>(term_d, D, hmask, jl)
+                                                      : pairwise_sum_lanes16<double>(term_f, D, hmask, jl))
                                               : pairwise_sum<double>(term, D);
                 const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
                 val = prior + pred_value(diag, acc, c0, s.lpp[kl], diag ? s.cst[kl] : 0., diag ? s.hv[kl] : 0.);
@@ -358,16 +457,24 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             if (jl == 0) vbuf[k_of(kl)] = val;
         }
     }
+    tick(4);
     grid_barrier(p.bar, G, tag | 0x50, (unsigned)(K | ((unsigned)n_total << 8) | ((unsigned)u_pos << 20)));
-    double mx = neg_inf();
-    for (int k = tid; k < KM; k += GB_THREADS) {
-        const double val = __ldcg(vbuf + k);
-        s.sk[k] = val;
-        mx = fmax(mx, val);
-    }
+    tick(5);
     const double uu = (p.assign_mode == 0) ? p.uniforms[u_pos] : 0.0;
     if (p.assign_mode == 0) u_pos += 1;
-    int k_sel = fv_decide(ds, K, KM, p.assign_mode, p.assign_temp, uu, mx);
+    int k_sel;
+    if (p.assign_mode == 0 && p.assign_temp == 1.0 && KM <= GB_THREADS * DECIDE_PER) {
+        k_sel = decide_fast(vbuf, K, KM, uu, s.red);
+    } else {
+        double mx = neg_inf();
+        for (int k = tid; k < KM; k += GB_THREADS) {
+            const double val = __ldcg(vbuf + k);
+            s.sk[k] = val;
+            mx = fmax(mx, val);
+        }
+        k_sel = fv_decide(ds, K, KM, p.assign_mode, p.assign_temp, uu, mx);
+    }
+    tick(6);
     // add_item (:153-170) -- or, in whole-model sweeps, put the cached statistics back when the
     // item returns to its old component and no component died in between (fbgmm.py:397-400)
     const bool fresh = (k_sel == K);
@@ -409,6 +516,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         }
     }
     __syncthreads();
+    tick(7);
     return k_sel;
     };
 
@@ -458,12 +566,27 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         // the same utterance twice in a row: its new tokens must be visible before they are read
         if (it > 0 && p.order[it - 1] == u) grid_barrier(p.bar, G, (it << 8) | 1);
 
+        tick(8);
         // ================= remove the utterance's current tokens (:270-273)
         // snapshot of (token, component) before anything is modified: every CTA must see the same list
         for (int j = tid; j < N; j += GB_THREADS) {
             const int id = __ldcg(c.tok_id + off + j);
             s.tok[j] = id;
             s.tk[j] = (id >= 0) ? __ldcg(m.assignments + id) : -1;
+        }
+        for (int j = tid; j < n_slots; j += GB_THREADS) s.sid[j] = c.seg_id[off * S + j];
+        // one CTA pulls the NEXT utterance's embeddings and slot table into L2 while this one is sampled
+        if (it + 1 < p.n_order && b == (it % G)) {
+            const int un = p.order[it + 1];
+            const int64_t offn = c.pos_off[un];
+            const int n_sn = (int)(c.pos_off[un + 1] - offn) * S;
+            const size_t row_bytes = (size_t)D * (m.x_is_f64 ? 8 : 4);
+            for (int j = tid; j < n_sn; j += GB_THREADS) {
+                const int id = c.seg_id[offn * S + j];
+                if (id < 0) continue;
+                const char *row = (const char *)m.X + (size_t)id * row_bytes;
+                for (size_t o = 0; o < row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+            }
         }
         __syncthreads();
         for (int j = 0; j < N; ++j) {
@@ -473,6 +596,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             remove_one(id, k, (it << 8) | (j << 16), j + 1, N, false);
         }
 
+        tick(0);
         // ================= score every candidate segment (:474-511, fbgmm.py:256-285)
         const double log_norm = log((double)n_total + m.alpha);
         for (int kl = tid; kl < n_own; kl += GB_THREADS) slot_consts(kl);
@@ -480,21 +604,56 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         const int n_act = n_act_of(K);           // owned ACTIVE components
         for (int s0 = 0; s0 < n_slots; s0 += xb) {
             const int nb = min(xb, n_slots - s0);
-            for (int i = tid; i < nb * D; i += GB_THREADS) {
-                const int bb = i / D, d = i % D;
-                const int id = c.seg_id[off * S + s0 + bb];
-                s.xs[bb * D + d] = (id >= 0) ? fv_x(m, id, d) : 0.0;
+            // stage the batch's embeddings as float64: warp per row, lanes over dimensions, every load of a
+            // thread independent of the others (no per-element index arithmetic, several requests in flight)
+            {
+                constexpr int NW = GB_THREADS / 32, RPW = 4, DCH = 5;           // rows per warp / 32-wide chunks of D kept in registers
+                if (D <= 32 * DCH && !m.x_is_f64 && nb <= NW * RPW) {
+                    const float *Xf = (const float *)m.X;
+                    float v[RPW][DCH];
+#pragma unroll
+                    for (int q = 0; q < RPW; ++q) {
+                        const int bb = warp + q * NW;
+                        const int id = (bb < nb) ? s.sid[s0 + bb] : -1;
+                        const float *row = Xf + (size_t)(id < 0 ? 0 : id) * D;
+#pragma unroll
+                        for (int cch = 0; cch < DCH; ++cch) {
+                            const int d = lane + 32 * cch;
+                            v[q][cch] = (id >= 0 && d < D) ? row[d] : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < RPW; ++q) {
+                        const int bb = warp + q * NW;
+                        if (bb < nb) {
+#pragma unroll
+                            for (int cch = 0; cch < DCH; ++cch) {
+                                const int d = lane + 32 * cch;
+                                if (d < D) s.xs[bb * D + d] = (double)v[q][cch];
+                            }
+                        }
+                    }
+                } else {
+                    for (int bb = warp; bb < nb; bb += NW) {
+                        const int id = s.sid[s0 + bb];
+                        for (int d = lane; d < D; d += 32) s.xs[bb * D + d] = (id >= 0) ? fv_x(m, id, d) : 0.0;
+                    }
+                }
             }
             __syncthreads();
+            tick(11);
             for (int i = tid; i < nb * n_act; i += GB_THREADS) {
                 const int bb = i / n_act, kl = i % n_act;
                 const double *mu = s.mu + kl * D, *pp = s.pp + kl * D, *xr = s.xs + bb * D;
                 const double iv = diag ? s.iv[kl] : 0.;
-                const double acc = pairwise_sum<double>([&](int d) { return pred_term(diag, mu[d], pp[d], xr[d], iv); }, D);
+                const double acc = diag
+                    ? pairwise_sum_le256<double>([&](int d) { return pred_term_diag(mu[d], pp[d], xr[d], iv); }, D)
+                    : pairwise_sum_le256<double>([&](int d) { return pred_term_fixed(mu[d], pp[d], xr[d]); }, D);
                 s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm)
                                       + pred_value(diag, acc, c0, s.lpp[kl], diag ? s.cst[kl] : 0., diag ? s.hv[kl] : 0.);
             }
             __syncthreads();
+            tick(12);
             for (int bb = tid; bb < nb; bb += GB_THREADS) {
                 double mx = neg_inf(), t = 0.0;
                 for (int kl = 0; kl < n_act; ++kl) mx = fmax(mx, s.vt[bb * per + kl]);
@@ -504,13 +663,16 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             }
             // log_prior of the candidates this CTA will combine (slot % G == b), one warp each
             for (int bb = warp; bb < nb; bb += GB_THREADS / 32) {
-                if ((s0 + bb) % G != b) continue;
+                if ((s0 + bb) % G != b || s.sid[s0 + bb] < 0) continue;
                 const double lp = warp_log_prior(s.xs + bb * D);
                 if (lane == 0) p.seg_prior[s0 + bb] = lp;
             }
             __syncthreads();
+            tick(13);
         }
+        tick(1);
         grid_barrier(p.bar, G, (it << 8) | 0x30);
+        tick(9);
         // every CTA has taken its snapshot: the removed tokens can now be marked unassigned
         // (not earlier: a slower CTA would read an already cleared token list)
         if (b == G - 1) for (int j = tid; j < N; j += GB_THREADS) if (s.tok[j] >= 0 && s.tk[j] >= 0) m.assignments[s.tok[j]] = -1;
@@ -518,7 +680,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         // combine: CTA (slot % G) owns the slot; warp 0, lanes over CTAs
         for (int slot = b; slot < n_slots; slot += G) {
             if (warp == 0) {
-                const int id = c.seg_id[off * S + slot];
+                const int id = s.sid[slot];
                 const double du = c.seg_dur[off * S + slot];
                 double out = neg_inf();
                 if (id >= 0 && du == du) {                       // uniform over the warp
@@ -541,7 +703,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                 if (lane == 0) p.scores[slot] = out;
             }
         }
+        tick(2);
         grid_barrier(p.bar, G, (it << 8) | 0x40);
+        tick(10);
 
         // ================= DP: every CTA runs it on the same scores (:653-864)
         for (int i = tid; i < n_slots; i += GB_THREADS) s.sc[i] = __ldcg(p.scores + i);
@@ -566,6 +730,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             for (int j = tid; j < N; j += GB_THREADS) c.bounds[off + j] = s.bo[j];
         }
         __syncthreads();
+        tick(3);
         if (dp_status != SEGB_DP_OK) continue;                   // uniform over the grid
 
         // ================= assign the new tokens left to right (:339-349)
@@ -575,7 +740,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             const int t = j + 1, l = t - j_prev;
             j_prev = j + 1;
             const int slot = (t - 1) * S + (l - 1);
-            const int id = (l <= S) ? c.seg_id[off * S + slot] : -1;
+            const int id = (l <= S) ? s.sid[slot] : -1;
             if (b == 0 && tid == 0) c.tok_id[off + j] = id;
             if (id < 0) continue;                                 // back-tracking leftovers are skipped (:340-342)
             __syncthreads();
@@ -592,6 +757,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
 }
 
 static inline int gibbs_grid(int K_max, int n_sm) { return K_max < n_sm ? K_max : n_sm; }
+
+// development aid: per-phase clock totals of CTA 0 (enabled by segb_debug_gibbs_prof(…, 1))
+static unsigned long long *g_prof = nullptr;
 
 }  // namespace segb
 
@@ -641,6 +809,7 @@ extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb
     p.seg_prior = (double *)w; w += 8 * (size_t)p.M_cap;
     p.scores = (double *)w; w += 8 * (size_t)p.M_cap;
     p.v = (double *)w;
+    p.prof = g_prof;
     SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
     SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&p};
@@ -683,5 +852,15 @@ extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t
     void *args[] = {&p};
     SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel, dim3(G), dim3(GB_THREADS), args, smem, st));
     count_launch();
+    return 0;
+}
+
+// Development aid (tools/gibbs_phases.py): enable != 0 allocates / zeroes the phase counters and makes the
+// next cooperative segmenter sweeps accumulate CTA 0's clocks per phase; out16 (host) receives the totals.
+extern "C" int segb_debug_gibbs_prof(unsigned long long *out16, int enable) {
+    if (enable && !g_prof) SEGB_CUDA(cudaMalloc(&g_prof, 16 * sizeof(unsigned long long)));
+    if (out16 && g_prof) SEGB_CUDA(cudaMemcpy(out16, g_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (g_prof) SEGB_CUDA(cudaMemset(g_prof, 0, 16 * sizeof(unsigned long long)));
+    if (!enable && g_prof) { cudaFree(g_prof); g_prof = nullptr; }
     return 0;
 }
