@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     // barrier, every CTA takes the same decision, the owner of the chosen slot updates.
     // x_prior = log_prior(x); k_restore = slot whose cached statistics (s.bk) are put back when it is
     // chosen again, or -1.
+    const double *x_tok = s.xs;      // embedding of the token being assigned (a row of s.xs)
     auto assign_one = [&](int id, double x_prior, unsigned tag, int k_restore) -> int {
     double *vbuf = p.v + (size_t)tok_parity * KM;
     tok_parity ^= 1;
@@ -443,9 +444,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             if (kl < na) {
                 const double *mu = s.mu + kl * D, *pp = s.pp + kl * D;
                 const double iv = diag ? s.iv[kl] : 0.;
-                auto term = [&](int d) { return pred_term(diag, mu[d], pp[d], s.xs[d], iv); };
-                auto term_f = [&](int d) { return pred_term_fixed(mu[d], pp[d], s.xs[d]); };
-                auto term_d = [&](int d) { return pred_term_diag(mu[d], pp[d], s.xs[d], iv); };
+                auto term = [&](int d) { return pred_term(diag, mu[d], pp[d], x_tok[d], iv); };
+                auto term_f = [&](int d) { return pred_term_fixed(mu[d], pp[d], x_tok[d]); };
+                auto term_d = [&](int d) { return pred_term_diag(mu[d], pp[d], x_tok[d], iv); };
                 const double acc = (D <= 256) ? (diag ? pairwise_sum_lanes16<double>(term_d, D, hmask, jl)
                                                       : pairwise_sum_lanes16<double>(term_f, D, hmask, jl))
                                               : pairwise_sum<double>(term, D);
@@ -493,12 +494,12 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                     nu = __dmul_rn(m.k_0, m.mu_0[d]);
                     pNv = __dadd_rn(m.precision_0[d], __dmul_rn(m.k_0, __dmul_rn(m.mu_0[d], m.mu_0[d])));
                 }
-                s.num[kl * D + d] = __dadd_rn(nu, s.xs[d]);
+                s.num[kl * D + d] = __dadd_rn(nu, x_tok[d]);
                 s.pN[kl * D + d] = __dadd_rn(pNv, fv_xsq(m, id, d));
                 continue;
             }
             if (fresh) { nu = __dmul_rn(m.precision_0[d], m.mu_0[d]); pNv = m.precision_0[d]; }
-            s.num[kl * D + d] = __dadd_rn(nu, __dmul_rn(m.precision[d], s.xs[d]));
+            s.num[kl * D + d] = __dadd_rn(nu, __dmul_rn(m.precision[d], x_tok[d]));
             s.pN[kl * D + d] = __dadd_rn(pNv, m.precision[d]);
         }
         __syncthreads();
@@ -734,20 +735,37 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         if (dp_status != SEGB_DP_OK) continue;                   // uniform over the grid
 
         // ================= assign the new tokens left to right (:339-349)
-        int j_prev = 0;
-        for (int j = 0; j < N; ++j) {
-            if (!s.bo[j]) continue;
-            const int t = j + 1, l = t - j_prev;
-            j_prev = j + 1;
-            const int slot = (t - 1) * S + (l - 1);
-            const int id = (l <= S) ? s.sid[slot] : -1;
-            if (b == 0 && tid == 0) c.tok_id[off + j] = id;
-            if (id < 0) continue;                                 // back-tracking leftovers are skipped (:340-342)
-            __syncthreads();
-            for (int d = tid; d < D; d += GB_THREADS) s.xs[d] = fv_x(m, id, d);
-            __syncthreads();
-            assign_one(id, __ldcg(p.seg_prior + slot), (it << 8) | (j << 16), -1);
+        // the token list (embedding id, slot) is formed once and the tokens' embeddings are staged together
+        // (one memory latency per utterance instead of one per token); s.tok / s.tk are free again here
+        if (tid == 0) {
+            int n_t = 0, j_prev = 0;
+            for (int j = 0; j < N; ++j) {
+                if (!s.bo[j]) continue;
+                const int t = j + 1, l = t - j_prev;
+                j_prev = j + 1;
+                const int slot = (t - 1) * S + (l - 1);
+                const int id = (l <= S) ? s.sid[slot] : -1;
+                if (b == 0) c.tok_id[off + j] = id;
+                if (id < 0) continue;                             // back-tracking leftovers are skipped (:340-342)
+                s.tok[n_t] = id; s.tk[n_t] = slot; ++n_t;
+            }
+            s.red[35] = (double)n_t;
         }
+        __syncthreads();
+        const int n_new = (int)s.red[35];
+        for (int r0 = 0; r0 < n_new; r0 += xb) {
+            const int nr = min(xb, n_new - r0);
+            for (int r = warp; r < nr; r += GB_THREADS / 32) {
+                const int id = s.tok[r0 + r];
+                for (int d = lane; d < D; d += 32) s.xs[r * D + d] = fv_x(m, id, d);
+            }
+            __syncthreads();
+            for (int r = 0; r < nr; ++r) {
+                x_tok = s.xs + r * D;
+                assign_one(s.tok[r0 + r], __ldcg(p.seg_prior + s.tk[r0 + r]), (it << 8) | ((r0 + r) << 16), -1);
+            }
+        }
+        x_tok = s.xs;
     }
     if (b == 0 && tid == 0) {
         *m.K = K;
