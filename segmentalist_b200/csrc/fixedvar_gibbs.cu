@@ -603,46 +603,50 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         for (int kl = tid; kl < n_own; kl += GB_THREADS) slot_consts(kl);
         __syncthreads();
         const int n_act = n_act_of(K);           // owned ACTIVE components
+        // Embeddings of a batch are staged as float64, warp per row, lanes over dimensions.  The loads of
+        // batch i+1 are issued right after batch i has been stored, so their latency hides behind the pair
+        // evaluation of batch i (registers as the prefetch buffer).
+        constexpr int NW = GB_THREADS / 32, RPW = 4, DCH = 5;     // rows per warp / 32-wide chunks of D kept in registers
+        const bool reg_stage = (D <= 32 * DCH) && !m.x_is_f64 && (xb <= NW * RPW);
+        float v[RPW][DCH];
+        auto load_batch = [&](int s0, int nb) {
+            const float *Xf = (const float *)m.X;
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                const int bb = warp + q * NW;
+                const int id = (bb < nb) ? s.sid[s0 + bb] : -1;
+                const float *row = Xf + (size_t)(id < 0 ? 0 : id) * D;
+#pragma unroll
+                for (int cch = 0; cch < DCH; ++cch) {
+                    const int d = lane + 32 * cch;
+                    v[q][cch] = (id >= 0 && d < D) ? row[d] : 0.f;
+                }
+            }
+        };
+        if (reg_stage) load_batch(0, min(xb, n_slots));
         for (int s0 = 0; s0 < n_slots; s0 += xb) {
             const int nb = min(xb, n_slots - s0);
-            // stage the batch's embeddings as float64: warp per row, lanes over dimensions, every load of a
-            // thread independent of the others (no per-element index arithmetic, several requests in flight)
-            {
-                constexpr int NW = GB_THREADS / 32, RPW = 4, DCH = 5;           // rows per warp / 32-wide chunks of D kept in registers
-                if (D <= 32 * DCH && !m.x_is_f64 && nb <= NW * RPW) {
-                    const float *Xf = (const float *)m.X;
-                    float v[RPW][DCH];
+            if (reg_stage) {
 #pragma unroll
-                    for (int q = 0; q < RPW; ++q) {
-                        const int bb = warp + q * NW;
-                        const int id = (bb < nb) ? s.sid[s0 + bb] : -1;
-                        const float *row = Xf + (size_t)(id < 0 ? 0 : id) * D;
+                for (int q = 0; q < RPW; ++q) {
+                    const int bb = warp + q * NW;
+                    if (bb < nb) {
 #pragma unroll
                         for (int cch = 0; cch < DCH; ++cch) {
                             const int d = lane + 32 * cch;
-                            v[q][cch] = (id >= 0 && d < D) ? row[d] : 0.f;
+                            if (d < D) s.xs[bb * D + d] = (double)v[q][cch];
                         }
                     }
-#pragma unroll
-                    for (int q = 0; q < RPW; ++q) {
-                        const int bb = warp + q * NW;
-                        if (bb < nb) {
-#pragma unroll
-                            for (int cch = 0; cch < DCH; ++cch) {
-                                const int d = lane + 32 * cch;
-                                if (d < D) s.xs[bb * D + d] = (double)v[q][cch];
-                            }
-                        }
-                    }
-                } else {
-                    for (int bb = warp; bb < nb; bb += NW) {
-                        const int id = s.sid[s0 + bb];
-                        for (int d = lane; d < D; d += 32) s.xs[bb * D + d] = (id >= 0) ? fv_x(m, id, d) : 0.0;
-                    }
+                }
+            } else {
+                for (int bb = warp; bb < nb; bb += NW) {
+                    const int id = s.sid[s0 + bb];
+                    for (int d = lane; d < D; d += 32) s.xs[bb * D + d] = (id >= 0) ? fv_x(m, id, d) : 0.0;
                 }
             }
             __syncthreads();
             tick(11);
+            if (reg_stage && s0 + xb < n_slots) load_batch(s0 + xb, min(xb, n_slots - s0 - xb));
             for (int i = tid; i < nb * n_act; i += GB_THREADS) {
                 const int bb = i / n_act, kl = i % n_act;
                 const double *mu = s.mu + kl * D, *pp = s.pp + kl * D, *xr = s.xs + bb * D;
@@ -688,13 +692,21 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                     const int n_empty = KM - K;
                     const double e = m.lms * (log_empty - log_norm) + __ldcg(p.seg_prior + slot);
                     double gm = (n_empty > 0) ? e : neg_inf();
-                    for (int bb = lane; bb < G; bb += 32) gm = fmax(gm, __ldcg(p.part_m + (size_t)bb * p.M_cap + slot));
+                    // the G partial (max, sum) pairs: all loads of a lane issued together (G <= 160 -> <= 5 per lane)
+                    double pm[5], pt[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const int bb = lane + 32 * q;
+                        pm[q] = (bb < G) ? __ldcg(p.part_m + (size_t)bb * p.M_cap + slot) : neg_inf();
+                        pt[q] = (bb < G) ? __ldcg(p.part_t + (size_t)bb * p.M_cap + slot) : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) gm = fmax(gm, pm[q]);
                     gm = warp_max(gm);
                     double t = 0.0;
-                    for (int bb = lane; bb < G; bb += 32) {
-                        const double pm = __ldcg(p.part_m + (size_t)bb * p.M_cap + slot);
-                        if (pm > neg_inf()) t += __ldcg(p.part_t + (size_t)bb * p.M_cap + slot) * exp(pm - gm);
-                    }
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        if (pm[q] > neg_inf()) t += pt[q] * exp(pm[q] - gm);
                     t = warp_sum(t);
                     if (n_empty > 0) t += n_empty * exp(e - gm);
                     double val = log(t) + gm;
