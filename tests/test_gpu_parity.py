@@ -803,3 +803,31 @@ def test_bigram_gibbs_golden(sb, tag):
     ref = random.Random(6)
     # (the seeded stream position is checked indirectly: every later sample above would differ otherwise)
     del ref
+
+
+@pytest.mark.parametrize("D", [16, 64, 100, 131, 200])
+def test_mma_scorer_other_dims(sb, D):
+    """The tensor-core scorer away from the benchmark's D = 130: runtime-K issue loop (KS = 0), odd D
+    (16-lane refine), one block of NumPy's pairwise sum (D <= 128), and D = 200 where the shared-memory
+    budget only allows single-buffered A tiles.  Bit-exact against the exact float32 kernel."""
+    from segmentalist_b200 import synth
+    from segmentalist_b200.batch import MmaScorer
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    rng = np.random.RandomState(D)
+    K_max, n_emb, K_true = 700, 6000, 90
+    centres = synth.cluster_centres(K_true, D, rng)
+    z = rng.randint(0, K_true, n_emb)
+    X = synth._unit_rows(centres[z] + 0.05 * rng.standard_normal((n_emb, D)).astype(np.float32))
+    assign = -np.ones(n_emb, dtype=np.int64)
+    assign[:3000] = np.arange(3000) % K_max
+    np.random.seed(1)
+    comps = KMeansComponents(X, assign, K_max)
+    val_e, arg_e = comps.best(None)
+    mma = MmaScorer(comps)
+    val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
+    arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
+    mma.score(val, arg)
+    torch.cuda.synchronize()
+    npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
+    npt.assert_array_equal(val.cpu().numpy().view(np.int32), val_e.cpu().numpy().view(np.int32))
+    assert int(mma.n_fallback.item()) < n_emb // 2
