@@ -356,6 +356,14 @@ int segb_fixedvar_log_marg_k(const segb_fixedvar *m, const int64_t *order, const
 int segb_kmeans_sum_neg_sqrd_norm_k(const segb_kmeans *m, const int64_t *order, const int64_t *seg_off,
                                     double *out_k, void *stream);
 
+/* ------------------------------------------------------------------ development aids */
+
+/* Per-phase clock totals of CTA 0 of the cooperative Gibbs sweep (tools/gibbs_phases.py).
+ * enable != 0: allocate / zero 16 device counters; the following segb_gibbs_sweep_fixedvar_coop
+ * launches accumulate into them.  out16 (HOST array, may be NULL) receives the current totals
+ * before they are zeroed.  enable == 0 releases the counters.  Synchronous.                    */
+int segb_debug_gibbs_prof(unsigned long long *out16, int enable);
+
 #ifdef __cplusplus
 }
 #endif

@@ -771,10 +771,13 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                 const int id = s.tok[r0 + r];
                 for (int d = lane; d < D; d += 32) s.xs[r * D + d] = fv_x(m, id, d);
             }
+            // log_prior of the tokens' segments (computed in the scoring phase): fetched with the embeddings,
+            // not one L2 round trip per token on the critical path (s.al is free after the DP)
+            for (int r = tid; r < nr; r += GB_THREADS) s.al[r] = __ldcg(p.seg_prior + s.tk[r0 + r]);
             __syncthreads();
             for (int r = 0; r < nr; ++r) {
                 x_tok = s.xs + r * D;
-                assign_one(s.tok[r0 + r], __ldcg(p.seg_prior + s.tk[r0 + r]), (it << 8) | ((r0 + r) << 16), -1);
+                assign_one(s.tok[r0 + r], s.al[r], (it << 8) | ((r0 + r) << 16), -1);
             }
         }
         x_tok = s.xs;
