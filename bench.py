@@ -171,8 +171,8 @@ class ClockSampler(object):
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_mhz_min": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -655,7 +655,7 @@ def run_ours(args):
 
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
-        clocks["window"] = "warm-up + timed sweeps + kernel-alone timings (all under load)"
+        clocks["window"] = "warm-up + timed sweeps + kernel-alone timings (100 ms samples; sm_mhz_min = the power-capped clock during the GEMM launches)"
 
     # ---- end to end: host buffers in, host results out, every step
     e2e = None
