@@ -456,7 +456,7 @@ def run_bigram_extra(args):
            "assignments_only": {"ms_per_sweep": wall_a * 1e3, "tokens": int(n_tok), "tokens_per_s": n_tok / wall_a,
                                 "note": "one K_max-slot draw per token under the bigram prior row of the previous label"},
            "K_active": seg.acoustic_model.components.K, "dtype": "f64",
-           "note": "four launches per utterance on one stream, no host synchronisation inside a sweep"}
+           "note": "full sweeps: one cooperative launch (components sharded over the SMs, CTA 0 keeps the LM); assignments-only sweeps: four launches per utterance on one stream; no host synchronisation inside a sweep"}
     if not args.no_cpu:
         n_cpu = 4
         oseg = build(so, so.FixedVarPrior(var, np.zeros(D), var / 0.05))

@@ -224,6 +224,17 @@ int segb_gibbs_sweep_bigram(const segb_fixedvar *m, const segb_bigram_lm *lm, co
                             const double *uniforms, int64_t *u_counter, double *scratch_scores,
                             double *log_probs, int32_t *status, void *stream);
 
+/* The same bigram sweep as ONE cooperative launch (csrc/fixedvar_gibbs.cu, as
+ * segb_gibbs_sweep_fixedvar_coop): the owners form their slots' prior from the LM row of the
+ * previous label, CTA 0 keeps the LM tables (transcript out / in, rows and columns following a
+ * component that moves).  d_order is a DEVICE array; work: segb_gibbs_work_bytes() bytes.
+ * Full sweeps only (assignments_only: use segb_gibbs_sweep_bigram); SEGB_E_UNSUPPORTED when the
+ * model does not fit the per-CTA shared memory.                                                */
+int segb_gibbs_sweep_bigram_coop(const segb_fixedvar *m, const segb_bigram_lm *lm, const segb_corpus *c,
+                                 const int32_t *d_order, int32_t n_order, double time_power_term, double wip,
+                                 double anneal_temp, int32_t anneal_gibbs_am, const double *uniforms,
+                                 int64_t *u_counter, void *work, double *log_probs, int32_t *status, void *stream);
+
 /* ------------------------------------------------------------------ k-means (A10-A12) */
 
 /* Device view of KMeansComponents (kmeans_components.py:18-91). `means` has X's

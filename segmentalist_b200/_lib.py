@@ -103,6 +103,9 @@ _PROTOS = {
                                                c_vp, c_i32, c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                c_vp, c_vp]),
     "segb_debug_gibbs_prof": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "segb_gibbs_sweep_bigram_coop": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(BigramLM),
+                                                    ctypes.POINTER(Corpus), c_vp, c_i32, c_f64, c_f64, c_f64, c_i32, c_vp,
+                                                    c_vp, c_vp, c_vp, c_vp, c_vp]),
     "segb_fixedvar_log_marg_k_work_bytes": (c_i64, [c_i32, c_i32]),
     "segb_fixedvar_log_marg_k": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "segb_kmeans_sum_neg_sqrd_norm_k": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_vp]),

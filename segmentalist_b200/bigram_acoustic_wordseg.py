@@ -13,6 +13,7 @@ Randomness as in unigram_acoustic_wordseg.py: `random.random()` values are drawn
 reference's order and the host generator is rewound to the number used.
 """
 import logging
+import os
 import random
 import time
 
@@ -166,11 +167,26 @@ class BigramAcousticWordseg(object):
         log_probs = torch.zeros(n, dtype=torch.float64, device="cuda")
         status = torch.zeros(n, dtype=torch.int32, device="cuda")
         assert self.calc_p_continue() == 1.0
-        _lib.check(_lib.lib().segb_gibbs_sweep_bigram(
-            comps.struct(), self.lm.struct(), corpus.struct(), order_h.ctypes.data, n, int(bool(assignments_only)),
-            float(self.time_power_term), float(self.wip), float(anneal_temp), int(bool(anneal_gibbs_am)),
-            _lib.ptr(feed.dev), _lib.ptr(feed.counter), _lib.ptr(self._scratch), _lib.ptr(log_probs), _lib.ptr(status),
-            _lib.stream_ptr()))
+        lib = _lib.lib()
+        rc = _lib.E_UNSUPPORTED
+        if not assignments_only and os.environ.get("SEGB_GIBBS", "coop") != "steps":
+            # one cooperative launch for the whole sweep (components sharded over the SMs, CTA 0 keeps the LM)
+            if getattr(self, "_gibbs_work", None) is None:
+                self._gibbs_work = torch.empty(lib.segb_gibbs_work_bytes(comps.K_max, corpus.N_max, corpus.S),
+                                               dtype=torch.uint8, device="cuda")
+            rc = lib.segb_gibbs_sweep_bigram_coop(
+                comps.struct(), self.lm.struct(), corpus.struct(), _lib.ptr(_lib.dev(order_h)), n,
+                float(self.time_power_term), float(self.wip), float(anneal_temp), int(bool(anneal_gibbs_am)),
+                _lib.ptr(feed.dev), _lib.ptr(feed.counter), _lib.ptr(self._gibbs_work), _lib.ptr(log_probs),
+                _lib.ptr(status), _lib.stream_ptr())
+        if rc == _lib.E_UNSUPPORTED:
+            # assignments-only sweeps, or a model too large for per-CTA shared memory: four launches per utterance
+            rc = lib.segb_gibbs_sweep_bigram(
+                comps.struct(), self.lm.struct(), corpus.struct(), order_h.ctypes.data, n, int(bool(assignments_only)),
+                float(self.time_power_term), float(self.wip), float(anneal_temp), int(bool(anneal_gibbs_am)),
+                _lib.ptr(feed.dev), _lib.ptr(feed.counter), _lib.ptr(self._scratch), _lib.ptr(log_probs), _lib.ptr(status),
+                _lib.stream_ptr())
+        _lib.check(rc)
         st = status.cpu().numpy()
         feed.finish()
         self.utterances.boundaries[:, :] = corpus.boundaries_matrix()

@@ -168,6 +168,15 @@ __device__ __forceinline__ T pairwise_sum_le256(F f, int n) {
     }
     return pairwise_sum<T>(f, n);
 }
+// The same without the general fallback: for kernels whose launcher guarantees n <= 256 (keeps the
+// recursion stack of pairwise_sum out of their frames).
+template <typename T, typename F>
+__device__ __forceinline__ T pairwise_sum_max256(F f, int n) {
+    if (n <= 128) return pairwise_block<T>(f, 0, n);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return add_rn<T>(pairwise_block<T>(f, 0, n2), pairwise_block<T>(f, n2, n - n2));
+}
 template <typename T, typename F>
 __device__ __forceinline__ T pairwise_sum_lanes16(F f, int n, unsigned hmask, int j) {
     const int g = j >> 3, q = j & 7;

@@ -456,17 +456,6 @@ __device__ long long lm_total(const segb_bigram_lm &lm, double *red) {
     return (long long)block_sum((double)t, red);      // partial sums are far below 2^53: exact
 }
 
-// One slot of log_prob_vec_i (:64-69) or log(prob_vec_given_j) (:78-91), NumPy's operation order,
-// every operation separately rounded.
-__device__ __forceinline__ double lm_log_prob(const segb_bigram_lm &lm, int j_prev, int k, double sum_a) {
-    const double uk = __dadd_rn((double)lm.unigram_counts[k], __ddiv_rn(lm.a, (double)lm.K));
-    if (j_prev < 0) return __dsub_rn(log(uk), log(sum_a));
-    const double pv = __ddiv_rn(uk, sum_a);
-    const double bj = __dadd_rn((double)lm.bigram_counts[(size_t)j_prev * lm.K + k], __ddiv_rn(lm.b, (double)lm.K));
-    const double t2 = __ddiv_rn(__dmul_rn(__dsub_rn(1., lm.intrp_lambda), bj), __dadd_rn((double)lm.unigram_counts[j_prev], lm.b));
-    return log(__dadd_rn(__dmul_rn(lm.intrp_lambda, pv), t2));
-}
-
 __global__ void __launch_bounds__(256) bg_lm_update_kernel(segb_bigram_lm lm, const int32_t *tr, int n, int sign) {
     lm_update(lm, tr, n, sign);
 }

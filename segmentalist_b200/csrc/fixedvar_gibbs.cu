@@ -52,6 +52,8 @@ struct GibbsParams {
     double *scores;                // [M_cap] banded scores of the current utterance
     double *v;                     // [2][K_max] slot log-probabilities of the current token (double-buffered)
     unsigned long long *prof;      // optional [16] per-phase clock totals of CTA 0 (development aid), or NULL
+    segb_bigram_lm lm;             // bigram sweeps (has_lm): the LM tied to the components (bigram_lms.py)
+    int32_t has_lm;
 };
 
 // Grid barrier (all CTAs are co-resident: cooperative launch) on ONE monotonic counter: CTA-wide
@@ -208,6 +210,10 @@ __device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *
     return k_sel;
 }
 
+// ITEM: whole-model sweep over items (FBGMM.gibbs_sample) instead of utterances.  HAS_LM: bigram sweeps.
+// Separate instantiations keep one call site per step lambda, so each is inlined into its kernel (with both
+// modes in one body the compiler left the lambdas out of line and their captures went to local memory).
+template <bool ITEM, bool HAS_LM>
 __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const segb_fixedvar &m = p.m;
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     if (diag) {
         diag_consts(m, 0, d_cst0, d_hv0, d_iv0);
         d_f0 = (m.k_0 + 1.) / (m.k_0 * m.v_0);
-        d_lpv0 = pairwise_sum<double>([&](int d) { return log(d_f0 * m.precision_0[d]); }, D);
+        d_lpv0 = pairwise_sum_max256<double>([&](int d) { return log(d_f0 * m.precision_0[d]); }, D);
     }
     // log_prior(x) for the embedding staged at xrow, by one warp (same bits on every CTA)
     auto warp_log_prior = [&](const double *xrow) -> double {
@@ -326,8 +332,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         }
         __syncthreads();
         if (tid < 16) {
-            const double l = (D <= 256) ? pairwise_sum_lanes16<double>([&](int i) { return s.tmp[i]; }, D, 0xffffu, tid)
-                                        : pairwise_sum<double>([&](int i) { return s.tmp[i]; }, D);
+            const double l = pairwise_sum_lanes16<double>([&](int i) { return s.tmp[i]; }, D, 0xffffu, tid);   // D <= 256 (launcher)
             if (tid == 0) {
                 s.lpp[kl] = l;
                 m.log_prod_prec_pred[k] = l;
@@ -377,6 +382,22 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             // del_component (:190-221): the last component moves into slot k
             const int last = K - 1;
             grid_barrier(p.bar, G, tag | 0x10);   // every owner's write-through is visible
+            if (HAS_LM && b == 0) {
+                // the tied LM counts follow the component (gaussian_components_fixedvar.py:205-208, :218-221):
+                // unigram count, row `last` -> row k, then column `last` -> column k; the old slot is cleared
+                const int KL = p.lm.K;
+                int32_t *bi = p.lm.bigram_counts;
+                if (k != last) {
+                    if (tid == 0) p.lm.unigram_counts[k] = p.lm.unigram_counts[last];
+                    for (int i = tid; i < KL; i += GB_THREADS) bi[(size_t)k * KL + i] = bi[(size_t)last * KL + i];
+                    __syncthreads();
+                    for (int j = tid; j < KL; j += GB_THREADS) bi[(size_t)j * KL + k] = bi[(size_t)j * KL + last];
+                    __syncthreads();
+                }
+                if (tid == 0) p.lm.unigram_counts[last] = 0;
+                for (int i = tid; i < KL; i += GB_THREADS) { bi[(size_t)last * KL + i] = 0; bi[(size_t)i * KL + last] = 0; }
+                __syncthreads();
+            }
             if (k != last) {
                 if (own) {
                     const int kl = kl_of(k);
@@ -431,6 +452,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     // x_prior = log_prior(x); k_restore = slot whose cached statistics (s.bk) are put back when it is
     // chosen again, or -1.
     const double *x_tok = s.xs;      // embedding of the token being assigned (a row of s.xs)
+    int lm_prev = -1;                // bigram sweeps: label of the utterance's previous token, LM normaliser
+    double lm_sum_a = 0.0;
     auto assign_one = [&](int id, double x_prior, unsigned tag, int k_restore) -> int {
     double *vbuf = p.v + (size_t)tok_parity * KM;
     tok_parity ^= 1;
@@ -444,16 +467,18 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             if (kl < na) {
                 const double *mu = s.mu + kl * D, *pp = s.pp + kl * D;
                 const double iv = diag ? s.iv[kl] : 0.;
-                auto term = [&](int d) { return pred_term(diag, mu[d], pp[d], x_tok[d], iv); };
                 auto term_f = [&](int d) { return pred_term_fixed(mu[d], pp[d], x_tok[d]); };
                 auto term_d = [&](int d) { return pred_term_diag(mu[d], pp[d], x_tok[d], iv); };
-                const double acc = (D <= 256) ? (diag ? pairwise_sum_lanes16<double>(term_d, D, hmask, jl)
-                                                      : pairwise_sum_lanes16<double>(term_f, D, hmask, jl))
-                                              : pairwise_sum<double>(term, D);
-                const double prior = (p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl];
+                const double acc = diag ? pairwise_sum_lanes16<double>(term_d, D, hmask, jl)     // D <= 256 (launcher)
+                                        : pairwise_sum_lanes16<double>(term_f, D, hmask, jl);
+                // prior term: lms*log(alpha/K_max + n_k) (fbgmm.py:436), or under a bigram LM the row of the
+                // previous label, lms*log P(k | j_prev) (bigram_acoustic_wordseg.py:347-355)
+                const double prior = HAS_LM ? __dmul_rn(lm_log_prob(p.lm, lm_prev, k_of(kl), lm_sum_a), m.lms)
+                                              : ((p.assign_mode == 0) ? m.lms * s.pl[kl] : s.pl[kl]);
                 val = prior + pred_value(diag, acc, c0, s.lpp[kl], diag ? s.cst[kl] : 0., diag ? s.hv[kl] : 0.);
             } else {
-                val = ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + x_prior;
+                val = HAS_LM ? __dadd_rn(__dmul_rn(lm_log_prob(p.lm, lm_prev, k_of(kl), lm_sum_a), m.lms), x_prior)
+                               : ((p.assign_mode == 0) ? m.lms : 1.0) * log_empty + x_prior;
             }
             if (jl == 0) vbuf[k_of(kl)] = val;
         }
@@ -522,7 +547,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     };
 
     // ================= whole-model sweep: FBGMM.gibbs_sample over a list of items (fbgmm.py:357-400)
-    if (p.item_mode) {
+    if (ITEM) {
         for (int it = 0; it < p.n_order; ++it) {
             const int id = p.order[it];
             const int k_old = __ldcg(m.assignments + id);            // uniform over the grid
@@ -590,6 +615,19 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             }
         }
         __syncthreads();
+        if (HAS_LM && b == 0 && tid == 0) {
+            // remove_counts_from_utterance (bigram_lms.py:107-113) over the old transcript, before any
+            // component can move (bigram_acoustic_wordseg.py:410-417); CTA 0 owns the LM tables
+            int jp = -1;
+            for (int j = 0; j < N; ++j) {
+                if (s.tok[j] < 0 || s.tk[j] < 0) continue;
+                const int i = s.tk[j];
+                p.lm.unigram_counts[i] -= 1;
+                if (jp >= 0) p.lm.bigram_counts[(size_t)jp * p.lm.K + i] -= 1;
+                jp = i;
+            }
+        }
+        __syncthreads();
         for (int j = 0; j < N; ++j) {
             const int id = s.tok[j];
             const int k = s.tk[j];
@@ -652,8 +690,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
                 const double *mu = s.mu + kl * D, *pp = s.pp + kl * D, *xr = s.xs + bb * D;
                 const double iv = diag ? s.iv[kl] : 0.;
                 const double acc = diag
-                    ? pairwise_sum_le256<double>([&](int d) { return pred_term_diag(mu[d], pp[d], xr[d], iv); }, D)
-                    : pairwise_sum_le256<double>([&](int d) { return pred_term_fixed(mu[d], pp[d], xr[d]); }, D);
+                    ? pairwise_sum_max256<double>([&](int d) { return pred_term_diag(mu[d], pp[d], xr[d], iv); }, D)
+                    : pairwise_sum_max256<double>([&](int d) { return pred_term_fixed(mu[d], pp[d], xr[d]); }, D);
                 s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm)
                                       + pred_value(diag, acc, c0, s.lpp[kl], diag ? s.cst[kl] : 0., diag ? s.hv[kl] : 0.);
             }
@@ -765,6 +803,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
         }
         __syncthreads();
         const int n_new = (int)s.red[35];
+        lm_prev = -1;
+        lm_sum_a = __dadd_rn((double)n_total, p.lm.a);        // sum_ints(unigram_counts) + a: the counts are tied
         for (int r0 = 0; r0 < n_new; r0 += xb) {
             const int nr = min(xb, n_new - r0);
             for (int r = warp; r < nr; r += GB_THREADS / 32) {
@@ -777,10 +817,27 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             __syncthreads();
             for (int r = 0; r < nr; ++r) {
                 x_tok = s.xs + r * D;
-                assign_one(s.tok[r0 + r], s.al[r], (it << 8) | ((r0 + r) << 16), -1);
+                const int k_new = assign_one(s.tok[r0 + r], s.al[r], (it << 8) | ((r0 + r) << 16), -1);
+                if (HAS_LM) {
+                    lm_prev = k_new;
+                    if (tid == 0) s.tk[r0 + r] = k_new;           // the slot index is no longer needed
+                }
             }
         }
         x_tok = s.xs;
+        if (HAS_LM) {
+            __syncthreads();
+            if (b == 0 && tid == 0) {                           // counts_from_utterance over the new transcript (:499)
+                int jp = -1;
+                for (int r = 0; r < n_new; ++r) {
+                    const int i = s.tk[r];
+                    p.lm.unigram_counts[i] += 1;
+                    if (jp >= 0) p.lm.bigram_counts[(size_t)jp * p.lm.K + i] += 1;
+                    jp = i;
+                }
+            }
+            lm_prev = -1;
+        }
     }
     if (b == 0 && tid == 0) {
         *m.K = K;
@@ -803,11 +860,10 @@ extern "C" int64_t segb_gibbs_work_bytes(int32_t K_max, int32_t N_max, int32_t S
     return 2048 + 8 * (2 * G * M_cap + 2 * M_cap + 2 * (int64_t)K_max) + 256;
 }
 
-extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb_corpus *c, const int32_t *d_order,
-                                              int32_t n_order, int32_t fb_mode, double time_power_term, double wip,
-                                              double anneal_temp, int32_t anneal_gibbs_am, const double *uniforms,
-                                              int64_t *u_counter, void *work, double *log_probs, int32_t *status,
-                                              void *stream) {
+static int launch_gibbs_coop(const segb_fixedvar *m, const segb_bigram_lm *lm, const segb_corpus *c,
+                             const int32_t *d_order, int32_t n_order, int32_t fb_mode, double time_power_term,
+                             double wip, double anneal_temp, int32_t anneal_gibbs_am, const double *uniforms,
+                             int64_t *u_counter, void *work, double *log_probs, int32_t *status, void *stream) {
     SEGB_CHECK_ARG(m && c && d_order && work && log_probs && status, "null pointer");
     SEGB_CHECK_ARG(fb_mode == SEGB_DP_FFBS || fb_mode == SEGB_DP_VITERBI_GMM, "fb_mode");
     SEGB_CHECK_ARG(fb_mode == SEGB_DP_VITERBI_GMM || (uniforms && u_counter), "FFBS needs uniforms");
@@ -822,10 +878,13 @@ extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb
         SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     if (!coop || n_sm > 160) { set_error("cooperative launch unavailable"); return SEGB_E_UNSUPPORTED; }
+    if (m->D > 256) { set_error("the cooperative Gibbs sweep covers D <= 256"); return SEGB_E_UNSUPPORTED; }
     GibbsParams p;
     p.m = *m; p.c = *c; p.order = d_order; p.n_order = n_order; p.fb_mode = fb_mode;
     p.assign_mode = (fb_mode == SEGB_DP_FFBS) ? 0 : 1;
     p.item_mode = 0;
+    p.has_lm = lm ? 1 : 0;
+    if (lm) p.lm = *lm; else memset(&p.lm, 0, sizeof(p.lm));
     p.tpt = time_power_term; p.wip = wip; p.anneal_temp = anneal_temp;
     p.assign_temp = anneal_gibbs_am ? anneal_temp : 1.0;
     p.uniforms = uniforms; p.u_counter = u_counter; p.log_probs = log_probs; p.status = status;
@@ -844,11 +903,32 @@ extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb
     p.v = (double *)w;
     p.prof = g_prof;
     SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
-    SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const void *kern = lm ? (const void *)fv_gibbs_kernel<false, true> : (const void *)fv_gibbs_kernel<false, false>;
+    SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&p};
-    SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel, dim3(G), dim3(GB_THREADS), args, smem, st));
+    SEGB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(GB_THREADS), args, smem, st));
     count_launch();
     return 0;
+}
+
+extern "C" int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb_corpus *c, const int32_t *d_order,
+                                              int32_t n_order, int32_t fb_mode, double time_power_term, double wip,
+                                              double anneal_temp, int32_t anneal_gibbs_am, const double *uniforms,
+                                              int64_t *u_counter, void *work, double *log_probs, int32_t *status,
+                                              void *stream) {
+    return launch_gibbs_coop(m, nullptr, c, d_order, n_order, fb_mode, time_power_term, wip, anneal_temp, anneal_gibbs_am,
+                             uniforms, u_counter, work, log_probs, status, stream);
+}
+
+extern "C" int segb_gibbs_sweep_bigram_coop(const segb_fixedvar *m, const segb_bigram_lm *lm, const segb_corpus *c,
+                                            const int32_t *d_order, int32_t n_order, double time_power_term, double wip,
+                                            double anneal_temp, int32_t anneal_gibbs_am, const double *uniforms,
+                                            int64_t *u_counter, void *work, double *log_probs, int32_t *status,
+                                            void *stream) {
+    SEGB_CHECK_ARG(lm && m && lm->K == m->K_max && lm->unigram_counts && lm->bigram_counts, "the LM covers the K_max component labels");
+    SEGB_CHECK_ARG(m->model == SEGB_MODEL_FIXEDVAR, "bigram sampling: fixed-variance components");
+    return launch_gibbs_coop(m, lm, c, d_order, n_order, SEGB_DP_FFBS, time_power_term, wip, anneal_temp, anneal_gibbs_am,
+                             uniforms, u_counter, work, log_probs, status, stream);
 }
 
 extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t *d_items, int32_t n_items,
@@ -862,6 +942,7 @@ extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t
     SEGB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     if (!coop || n_sm > 160) { set_error("cooperative launch unavailable"); return SEGB_E_UNSUPPORTED; }
+    if (m->D > 256) { set_error("the cooperative Gibbs sweep covers D <= 256"); return SEGB_E_UNSUPPORTED; }
     GibbsParams p;
     memset(&p, 0, sizeof(p));
     p.m = *m;
@@ -881,9 +962,9 @@ extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t
     p.part_m = p.part_t = p.seg_prior = p.scores = nullptr;
     p.v = (double *)w;
     SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
-    SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&p};
-    SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel, dim3(G), dim3(GB_THREADS), args, smem, st));
+    SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel<true, false>, dim3(G), dim3(GB_THREADS), args, smem, st));
     count_launch();
     return 0;
 }
