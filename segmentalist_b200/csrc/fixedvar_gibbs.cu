@@ -685,15 +685,27 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
             __syncthreads();
             tick(11);
             if (reg_stage && s0 + xb < n_slots) load_batch(s0 + xb, min(xb, n_slots - s0 - xb));
-            for (int i = tid; i < nb * n_act; i += GB_THREADS) {
-                const int bb = i / n_act, kl = i % n_act;
-                const double *mu = s.mu + kl * D, *pp = s.pp + kl * D, *xr = s.xs + bb * D;
-                const double iv = diag ? s.iv[kl] : 0.;
-                const double acc = diag
-                    ? pairwise_sum_max256<double>([&](int d) { return pred_term_diag(mu[d], pp[d], xr[d], iv); }, D)
-                    : pairwise_sum_max256<double>([&](int d) { return pred_term_fixed(mu[d], pp[d], xr[d]); }, D);
-                s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm)
-                                      + pred_value(diag, acc, c0, s.lpp[kl], diag ? s.cst[kl] : 0., diag ? s.hv[kl] : 0.);
+            if (diag) {
+                // Student's t terms cost a float64 log each: a half-warp per (segment, component) pair (lane =
+                // NumPy accumulator) keeps all 256 threads busy where thread-per-pair left most of them idle
+                const int jl = tid & 15;
+                const unsigned hmask = 0xffffu << (lane & 16);
+                for (int i = tid >> 4; i < nb * n_act; i += GB_THREADS / 16) {
+                    const int bb = i / n_act, kl = i % n_act;
+                    const double *mu = s.mu + kl * D, *pp = s.pp + kl * D, *xr = s.xs + bb * D;
+                    const double iv = s.iv[kl];
+                    const double acc = pairwise_sum_lanes16<double>(
+                        [&](int d) { return pred_term_diag(mu[d], pp[d], xr[d], iv); }, D, hmask, jl);
+                    if (jl == 0)
+                        s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm) + pred_value(true, acc, c0, s.lpp[kl], s.cst[kl], s.hv[kl]);
+                }
+            } else {
+                for (int i = tid; i < nb * n_act; i += GB_THREADS) {
+                    const int bb = i / n_act, kl = i % n_act;
+                    const double *mu = s.mu + kl * D, *pp = s.pp + kl * D, *xr = s.xs + bb * D;
+                    const double acc = pairwise_sum_max256<double>([&](int d) { return pred_term_fixed(mu[d], pp[d], xr[d]); }, D);
+                    s.vt[bb * per + kl] = m.lms * (s.pl[kl] - log_norm) + pred_value(false, acc, c0, s.lpp[kl], 0., 0.);
+                }
             }
             __syncthreads();
             tick(12);
