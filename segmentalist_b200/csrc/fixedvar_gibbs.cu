@@ -210,6 +210,76 @@ __device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *
     return k_sel;
 }
 
+// decide_fast for models with more than GB_THREADS * DECIDE_PER slots (K_max = 5000): the slot values pass
+// through shared memory -- coalesced loads and the exponentials in slot-strided order, then every thread scans
+// its contiguous chunk.  Same decision rule, same exact-serial fallback.  sk: K_max doubles of shared scratch.
+__device__ int decide_fast_smem(const double *vbuf, int K, int KM, double u, double *red, double *sk) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = GB_THREADS >> 5;
+    double mx = neg_inf();
+    for (int k0 = tid; k0 < KM; k0 += 4 * GB_THREADS) {
+        double t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int k = k0 + q * GB_THREADS; t[q] = (k < KM) ? __ldcg(vbuf + k) : neg_inf(); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int k = k0 + q * GB_THREADS; if (k < KM) { sk[k] = t[q]; mx = fmax(mx, t[q]); } }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[w] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < nw; ++i) mx = fmax(mx, red[i]);
+    for (int k = tid; k < KM; k += GB_THREADS) sk[k] = exp(sk[k] - mx);
+    __syncthreads();
+    const int per = (KM + GB_THREADS - 1) / GB_THREADS;
+    const int lo = min(tid * per, KM), hi = min(lo + per, KM);
+    double loc = 0.0;
+    for (int k = lo; k < hi; ++k) loc += sk[k];
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) red[8 + w] = inc;
+    __syncthreads();
+    double base = 0.0, sum = 0.0;
+    for (int i = 0; i < nw; ++i) { const double t = red[8 + i]; if (i < w) base += t; sum += t; }
+    const double target = u * sum;
+    double run = base + inc - loc, margin = CUDART_INF;
+    int first = 0x7fffffff;
+    for (int k = lo; k < hi; ++k) {
+        run += sk[k];
+        const double r = target - run;
+        margin = fmin(margin, fabs(r));
+        if (r < 0 && first == 0x7fffffff) first = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        margin = fmin(margin, __shfl_xor_sync(FULL, margin, o));
+        first = min(first, __shfl_xor_sync(FULL, first, o));
+    }
+    if (lane == 0) { red[16 + w] = margin; red[24 + w] = (double)first; }
+    __syncthreads();
+    margin = red[16];
+    double gfirst = red[24];
+    for (int i = 1; i < nw; ++i) { margin = fmin(margin, red[16 + i]); gfirst = fmin(gfirst, red[24 + i]); }
+    int k_sel = (gfirst > 2.0e9) ? KM - 1 : (int)gfirst;
+    if (margin < 1e-9 * sum) {
+        if (tid == 0) {                     // utils.draw (utils.py:10-21) verbatim
+            const double lse = log(sum) + mx;
+            double uu = u;
+            int r = KM - 1;
+            for (int k = 0; k < KM; ++k) { uu = uu - exp(__ldcg(vbuf + k) - lse); if (uu < 0) { r = k; break; } }
+            red[32] = (double)r;
+        }
+        __syncthreads();
+        k_sel = (int)red[32];
+    }
+    __syncthreads();
+    if (k_sel > K) k_sel = K;
+    return k_sel;
+}
+
 // ITEM: whole-model sweep over items (FBGMM.gibbs_sample) instead of utterances.  HAS_LM: bigram sweeps.
 // Separate instantiations keep one call site per step lambda, so each is inlined into its kernel (with both
 // modes in one body the compiler left the lambdas out of line and their captures went to local memory).
@@ -491,6 +561,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     int k_sel;
     if (p.assign_mode == 0 && p.assign_temp == 1.0 && KM <= GB_THREADS * DECIDE_PER) {
         k_sel = decide_fast(vbuf, K, KM, uu, s.red);
+    } else if (p.assign_mode == 0 && p.assign_temp == 1.0) {
+        k_sel = decide_fast_smem(vbuf, K, KM, uu, s.red, s.sk);
     } else {
         double mx = neg_inf();
         for (int k = tid; k < KM; k += GB_THREADS) {
