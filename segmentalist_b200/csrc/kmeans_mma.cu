@@ -25,15 +25,17 @@
 // D to KP = roundup(D + 3, 16); three padding columns carry a 3-way fp16 split
 // of -|mu_k|^2/2 (x side: 1.0), so the norm rides along in the GEMM for free.
 //
-// Kernel: persistent, one CTA per SM, 384 threads, warp-specialised:
-//   warp 0  TMA producer  (A = 256 embeddings, once per work item; B = 128-component
-//                          tiles streamed through a 4-stage ring, L2-resident)
-//   warp 1  MMA issuer    (tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accumulate in TMEM,
-//                          2 row-halves x double-buffered accumulators = 512 TMEM columns)
+// Kernel: persistent, one CTA per SM, 640 threads, warp-specialised:
+//   warp 0  TMA producer  (A = 256 embeddings per work item, double-buffered; B = 128-component
+//                          tiles, L2-resident, two stages tied to the accumulator buffers)
+//   warp 1  MMA issuer    (one elected thread; tcgen05.mma kind::f16, M=128 N=128 K=16, fp32
+//                          accumulate in TMEM, 2 row-halves x double-buffered accumulators = 512
+//                          TMEM columns; unrolled issue loop, ONE commit per tile)
 //   warp 2  TMEM allocator
-//   warps 4-11 epilogue   (tcgen05.ld 32x32b: one thread owns one embedding row; running
-//                          top-3 of chunk maxima in registers; nothing but 32 B per
-//                          embedding ever goes back to HBM)
+//   warps 4-19 epilogue   (one tcgen05.ld 32x32b.x64 per warp and tile: one thread owns one
+//                          embedding row and 64 of the tile's columns; running top-3 of chunk
+//                          maxima in registers; nothing but 32 B per embedding ever goes back
+//                          to HBM)
 #include "mma_common.cuh"
 
 namespace segb {
