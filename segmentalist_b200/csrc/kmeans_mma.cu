@@ -547,7 +547,8 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_rows_kernel(
 // (filter record, bound, mask walk) is shared by 8 lanes instead of 16 and every load instruction
 // carries two terms.  Needs an even D (8-byte aligned rows); the combination tree is unchanged:
 // (r[2c] + r[2c+1]) locally, then xor 1 and xor 2 inside the block's four lanes.
-__global__ void __launch_bounds__(REFINE_THREADS) refine_rows8_kernel(
+template <int MAXS>
+__global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
     segb_kmeans m, const Cand *cand, const float *x_err, const float *w_max, int64_t n_emb, int n_chunks,
     float *best_val, int32_t *best_k, unsigned long long *n_fallback, int32_t *fb_list) {
     const int D = m.D, KM = m.K_max;
@@ -578,9 +579,9 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_rows8_kernel(
         }
         const float *xr = X + row * D;
         const float2 *xr2 = reinterpret_cast<const float2 *>(xr + lo_g + 2 * c);
-        float2 xv[REFINE_MAX_STEPS];
+        float2 xv[MAXS];
 #pragma unroll
-        for (int i = 0; i < REFINE_MAX_STEPS; ++i) xv[i] = (i < steps) ? xr2[i * 4] : make_float2(0.f, 0.f);
+        for (int i = 0; i < MAXS; ++i) xv[i] = (i < steps) ? xr2[i * 4] : make_float2(0.f, 0.f);
         float bv = -CUDART_INF_F;
         int bk = 0x7fffffff;
 #pragma unroll 1
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_rows8_kernel(
                 const float2 *mu2 = reinterpret_cast<const float2 *>(mu + lo_g + 2 * c);
                 float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < REFINE_MAX_STEPS; ++i) {
+                for (int i = 0; i < MAXS; ++i) {
                     if (i < steps) {
                         const float2 mv = mu2[i * 4];
                         const float d0 = __fsub_rn(mv.x, xv[i].x), d1 = __fsub_rn(mv.y, xv[i].y);
@@ -754,8 +755,20 @@ extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const flo
     const bool lanes8 = (m->D % 2 == 0);          // 8-byte loads need even D (rows 8-byte aligned)
     int64_t blocks = (n_emb * (lanes8 ? 8 : 16) + REFINE_THREADS - 1) / REFINE_THREADS;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    if (lanes8)
-        refine_rows8_kernel<<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+    // accumulator steps of the longer NumPy block: <= 8 for D <= 143 when split (D = 130: 64 + 66 terms)
+    int steps_max;
+    {
+        int n2 = 0;
+        if (m->D > 128) { n2 = m->D / 2; n2 -= n2 % 8; }
+        const int longest = (m->D > 128) ? (m->D - n2 > n2 ? m->D - n2 : n2) : m->D;
+        steps_max = longest / 8;
+    }
+    if (lanes8 && steps_max <= 8)
+        refine_rows8_kernel<8><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
+            (unsigned long long *)n_fallback, fb_list);
+    else if (lanes8)
+        refine_rows8_kernel<REFINE_MAX_STEPS><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
             (unsigned long long *)n_fallback, fb_list);
     else
