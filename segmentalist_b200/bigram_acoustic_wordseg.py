@@ -190,8 +190,8 @@ class BigramAcousticWordseg(object):
         st = status.cpu().numpy()
         feed.finish()
         self.utterances.boundaries[:, :] = corpus.boundaries_matrix()
-        assert np.all(st == _lib.DP_OK), "segmentation DP failed for utterances %s (status %s)" % (
-            list(order_h[st != 0]), list(st[st != 0]))
+        assert np.all(st == _lib.DP_OK), "segmentation DP failed for %d utterances, first %s (status %s)" % (
+            int((st != 0).sum()), list(order_h[st != 0][:8]), list(st[st != 0][:8]))
         lp = log_probs.cpu().numpy()
         assert not np.any(lp == -np.inf)
         return lp
