@@ -46,3 +46,20 @@ def test_no_oracle_import_in_product():
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in txt.replace("seg_oracle", "oracle") or "import oracle" not in txt
                 assert "from oracle" not in txt and "import oracle" not in txt
+
+
+def test_members_by_component_groups_like_np_where():
+    """Host logic of the device diagnostics: the stable sort of the assignments lists every component's
+    members in index order -- the order of np.where(assignments == k) in the reference
+    (gaussian_components_fixedvar.py:270, kmeans_components.py:242)."""
+    import numpy as np
+    import torch
+    from segmentalist_b200 import _lib
+    rng = np.random.RandomState(0)
+    K_max = 9
+    assign = rng.randint(-1, 7, size=200).astype(np.int32)
+    order, seg_off = _lib.members_by_component(torch.from_numpy(assign), K_max)
+    order, seg_off = order.numpy(), seg_off.numpy()
+    assert seg_off.shape == (K_max + 1,) and seg_off[0] == (assign == -1).sum() and seg_off[-1] == len(assign)
+    for k in range(K_max):
+        np.testing.assert_array_equal(order[seg_off[k]:seg_off[k + 1]], np.where(assign == k)[0])
