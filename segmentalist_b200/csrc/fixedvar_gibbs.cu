@@ -143,7 +143,7 @@ __device__ __forceinline__ double pred_value(bool diag, double acc, double c0, d
 // could change the answer -- thread 0 repeats the reference's serial subtraction over exp(v_k - lse).
 // red: >= 32 doubles of shared scratch.  Block-uniform, identical on every CTA.
 constexpr int DECIDE_PER = 8;
-__device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *red) {
+__device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *red, double inv_t) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = GB_THREADS >> 5;
     const int per = (KM + GB_THREADS - 1) / GB_THREADS;
     const int lo = min(tid * per, KM), hi = min(lo + per, KM);
@@ -160,7 +160,7 @@ __device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *
     for (int i = 1; i < nw; ++i) mx = fmax(mx, red[i]);
     double loc = 0.0;
 #pragma unroll
-    for (int i = 0; i < DECIDE_PER; ++i) { v[i] = (lo + i < hi) ? exp(v[i] - mx) : 0.0; loc += v[i]; }
+    for (int i = 0; i < DECIDE_PER; ++i) { v[i] = (lo + i < hi) ? exp(inv_t * (v[i] - mx)) : 0.0; loc += v[i]; }
     double inc = loc;                       // inclusive scan of the chunk sums inside the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -194,6 +194,7 @@ __device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *
     double gfirst = red[24];
     for (int i = 1; i < nw; ++i) { margin = fmin(margin, red[16 + i]); gfirst = fmin(gfirst, red[24 + i]); }
     int k_sel = (gfirst > 2.0e9) ? KM - 1 : (int)gfirst;
+    if (margin < 1e-9 * sum && inv_t != 1.0) { __syncthreads(); return -1; }   // annealed: the caller repeats the draw with fv_decide
     if (margin < 1e-9 * sum) {
         if (tid == 0) {                     // utils.draw (utils.py:10-21) verbatim
             const double lse = log(sum) + mx;
@@ -213,7 +214,7 @@ __device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *
 // decide_fast for models with more than GB_THREADS * DECIDE_PER slots (K_max = 5000): the slot values pass
 // through shared memory -- coalesced loads and the exponentials in slot-strided order, then every thread scans
 // its contiguous chunk.  Same decision rule, same exact-serial fallback.  sk: K_max doubles of shared scratch.
-__device__ int decide_fast_smem(const double *vbuf, int K, int KM, double u, double *red, double *sk) {
+__device__ int decide_fast_smem(const double *vbuf, int K, int KM, double u, double *red, double *sk, double inv_t) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = GB_THREADS >> 5;
     double mx = neg_inf();
     for (int k0 = tid; k0 < KM; k0 += 4 * GB_THREADS) {
@@ -228,7 +229,7 @@ __device__ int decide_fast_smem(const double *vbuf, int K, int KM, double u, dou
     __syncthreads();
     mx = red[0];
     for (int i = 1; i < nw; ++i) mx = fmax(mx, red[i]);
-    for (int k = tid; k < KM; k += GB_THREADS) sk[k] = exp(sk[k] - mx);
+    for (int k = tid; k < KM; k += GB_THREADS) sk[k] = exp(inv_t * (sk[k] - mx));
     __syncthreads();
     const int per = (KM + GB_THREADS - 1) / GB_THREADS;
     const int lo = min(tid * per, KM), hi = min(lo + per, KM);
@@ -264,6 +265,7 @@ __device__ int decide_fast_smem(const double *vbuf, int K, int KM, double u, dou
     double gfirst = red[24];
     for (int i = 1; i < nw; ++i) { margin = fmin(margin, red[16 + i]); gfirst = fmin(gfirst, red[24 + i]); }
     int k_sel = (gfirst > 2.0e9) ? KM - 1 : (int)gfirst;
+    if (margin < 1e-9 * sum && inv_t != 1.0) { __syncthreads(); return -1; }   // annealed: the caller repeats the draw with fv_decide
     if (margin < 1e-9 * sum) {
         if (tid == 0) {                     // utils.draw (utils.py:10-21) verbatim
             const double lse = log(sum) + mx;
@@ -559,11 +561,13 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     const double uu = (p.assign_mode == 0) ? p.uniforms[u_pos] : 0.0;
     if (p.assign_mode == 0) u_pos += 1;
     int k_sel;
-    if (p.assign_mode == 0 && p.assign_temp == 1.0 && KM <= GB_THREADS * DECIDE_PER) {
-        k_sel = decide_fast(vbuf, K, KM, uu, s.red);
-    } else if (p.assign_mode == 0 && p.assign_temp == 1.0) {
-        k_sel = decide_fast_smem(vbuf, K, KM, uu, s.red, s.sk);
-    } else {
+    // sampling (also annealed: p_k ~ exp((v_k - max) / T), fbgmm.py:446-449) takes the low-latency path; MAP
+    // assignment and the rare draws within 1e-9 of a CDF step under annealing use fv_decide
+    k_sel = -1;
+    if (p.assign_mode == 0)
+        k_sel = (KM <= GB_THREADS * DECIDE_PER) ? decide_fast(vbuf, K, KM, uu, s.red, 1. / p.assign_temp)
+                                                : decide_fast_smem(vbuf, K, KM, uu, s.red, s.sk, 1. / p.assign_temp);
+    if (k_sel < 0) {
         double mx = neg_inf();
         for (int k = tid; k < KM; k += GB_THREADS) {
             const double val = __ldcg(vbuf + k);
