@@ -43,8 +43,8 @@ __device__ double warp_lse_desc(F cval, int l_lo, int W, double m) {
     return log(s) + m;
 }
 
-// Forward-filter / backward-sample for the common case of the sequential Gibbs sweep: plain FFBS (no
-// annealing, n_slices_min <= 1) with a window of at most 8 spans.  Lane l-1 holds span l, so the window
+// Forward-filter / backward-sample for the common case of the sequential Gibbs sweep: FFBS (with or
+// without annealing, n_slices_min <= 1) with a window of at most 8 spans.  Lane l-1 holds span l, so the window
 // maximum is three xor steps inside lanes 0..7, every exponential is evaluated once, and the sums run in
 // the reference's order (descending span for the logsumexp, _cython_utils.pyx:13-25; ascending span for
 // the draw, :75-89) -- the same values, bit for bit, as the general routine below, at ~1/3 of its
@@ -54,6 +54,8 @@ __device__ __forceinline__ bool dp_warp_ffbs_small(const DpParams &p, const doub
                                                    int64_t ubase, int Wlim, double &total_out, int &used_out) {
     const int lane = threadIdx.x & 31;
     const int S = p.S;
+    const bool anneal = p.anneal_temp != 1.0;
+    const double inv_t = 1. / p.anneal_temp;
     for (int j = lane; j < N; j += 32) bo[j] = (j == N - 1);
     if (lane == 0) al[0] = 0.0;
     __syncwarp();
@@ -96,7 +98,28 @@ __device__ __forceinline__ bool dp_warp_ffbs_small(const DpParams &p, const doub
         const double c = win(t, W, m);
         if (m == neg_inf() || m != m) return false;               // back-tracking: general routine
         const double lse = lse_desc(c, W, m);
-        const double pl = (lane < W) ? exp(c - lse) : 0.0;
+        double pl;
+        if (anneal) {
+            // p = softmax((1/T) * log-normalised p) (unigram_acoustic_wordseg.py:731-736); the second
+            // logsumexp runs over the reversed window, i.e. in ASCENDING span order
+            const double q = (lane < W) ? inv_t * (c - lse) : neg_inf();
+            double mq = q;
+            mq = fmax(mq, __shfl_xor_sync(FULL, mq, 1));
+            mq = fmax(mq, __shfl_xor_sync(FULL, mq, 2));
+            mq = fmax(mq, __shfl_xor_sync(FULL, mq, 4));
+            mq = __shfl_sync(FULL, mq, 0);
+            const double e2 = (lane < W) ? exp(q - mq) : 0.0;
+            double y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = __shfl_sync(FULL, e2, i);
+            double s2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (i < W) s2 += y[i];
+            const double lse2 = log(s2) + mq;
+            pl = (lane < W) ? exp(q - lse2) : 0.0;
+        } else {
+            pl = (lane < W) ? exp(c - lse) : 0.0;
+        }
         double x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = __shfl_sync(FULL, pl, i);
@@ -135,7 +158,7 @@ __device__ __forceinline__ void dp_warp_body(const DpParams &p, const double *sc
     const int n_min = p.n_min;
     const int l_cut = n_min > 1 ? n_min : 1;                        // [-S : -(n_min-1)] keeps spans >= n_min
     int status = SEGB_DP_OK;
-    if (p.mode == SEGB_DP_FFBS && p.anneal_temp == 1.0 && n_min <= 1 && Wlim <= 8 && alphas_out == nullptr) {
+    if (p.mode == SEGB_DP_FFBS && n_min <= 1 && Wlim <= 8 && alphas_out == nullptr) {
         double tot;
         int usd;
         if (dp_warp_ffbs_small(p, sc, bo, N, al, ubase, Wlim, tot, usd)) {
