@@ -211,6 +211,48 @@ __device__ int decide_fast(const double *vbuf, int K, int KM, double u, double *
     return k_sel;
 }
 
+// map_assign_i's choice (fbgmm.py:465-494: first maximum of the exp-normalised vector) on the same low-latency
+// plan: the first maximum of the log-probabilities themselves, unless a second slot lies within 1e-9 of it
+// (where rounding of the exponentials could merge or reorder them) -- then -1, and the caller runs fv_decide.
+__device__ int decide_map_fast(const double *vbuf, int K, int KM, double *red) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = GB_THREADS >> 5;
+    const int per = (KM + GB_THREADS - 1) / GB_THREADS;
+    const int lo = min(tid * per, KM), hi = min(lo + per, KM);
+    double v[DECIDE_PER];
+#pragma unroll
+    for (int i = 0; i < DECIDE_PER; ++i) v[i] = (lo + i < hi) ? __ldcg(vbuf + lo + i) : neg_inf();
+    double mx = v[0];
+#pragma unroll
+    for (int i = 1; i < DECIDE_PER; ++i) mx = fmax(mx, v[i]);
+    mx = warp_max(mx);
+    if (lane == 0) red[w] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < nw; ++i) mx = fmax(mx, red[i]);
+    int near = 0, first = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < DECIDE_PER; ++i) {
+        if (lo + i < hi) {
+            near += (v[i] >= mx - 1e-9) ? 1 : 0;
+            if (v[i] == mx && first == 0x7fffffff) first = lo + i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        near += __shfl_xor_sync(FULL, near, o);
+        first = min(first, __shfl_xor_sync(FULL, first, o));
+    }
+    if (lane == 0) { red[8 + w] = (double)near; red[16 + w] = (double)first; }
+    __syncthreads();
+    double n_near = 0.0, gfirst = red[16];
+    for (int i = 0; i < nw; ++i) { n_near += red[8 + i]; gfirst = fmin(gfirst, red[16 + i]); }
+    __syncthreads();                        // red is reused by the caller
+    if (!(mx == mx) || n_near != 1.0 || gfirst > 2.0e9) return -1;
+    int k_sel = (int)gfirst;
+    if (k_sel > K) k_sel = K;
+    return k_sel;
+}
+
 // decide_fast for models with more than GB_THREADS * DECIDE_PER slots (K_max = 5000): the slot values pass
 // through shared memory -- coalesced loads and the exponentials in slot-strided order, then every thread scans
 // its contiguous chunk.  Same decision rule, same exact-serial fallback.  sk: K_max doubles of shared scratch.
@@ -561,12 +603,14 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     const double uu = (p.assign_mode == 0) ? p.uniforms[u_pos] : 0.0;
     if (p.assign_mode == 0) u_pos += 1;
     int k_sel;
-    // sampling (also annealed: p_k ~ exp((v_k - max) / T), fbgmm.py:446-449) takes the low-latency path; MAP
-    // assignment and the rare draws within 1e-9 of a CDF step under annealing use fv_decide
+    // sampling (also annealed: p_k ~ exp((v_k - max) / T), fbgmm.py:446-449) and MAP assignment take the
+    // low-latency paths; near-ties and the rare annealed draws within 1e-9 of a CDF step use fv_decide
     k_sel = -1;
     if (p.assign_mode == 0)
         k_sel = (KM <= GB_THREADS * DECIDE_PER) ? decide_fast(vbuf, K, KM, uu, s.red, 1. / p.assign_temp)
                                                 : decide_fast_smem(vbuf, K, KM, uu, s.red, s.sk, 1. / p.assign_temp);
+    else if (KM <= GB_THREADS * DECIDE_PER)
+        k_sel = decide_map_fast(vbuf, K, KM, s.red);
     if (k_sel < 0) {
         double mx = neg_inf();
         for (int k = tid; k < KM; k += GB_THREADS) {
