@@ -43,8 +43,8 @@ __device__ double warp_lse_desc(F cval, int l_lo, int W, double m) {
     return log(s) + m;
 }
 
-// Forward-filter / backward-sample for the common case of the sequential Gibbs sweep: FFBS (with or
-// without annealing, n_slices_min <= 1) with a window of at most 8 spans.  Lane l-1 holds span l, so the window
+// Forward-filter / backward-sample (and the GMM Viterbi variant) for the common case of the sequential Gibbs
+// sweep: n_slices_min <= 1 and a window of at most 8 spans, with or without annealing.  Lane l-1 holds span l, so the window
 // maximum is three xor steps inside lanes 0..7, every exponential is evaluated once, and the sums run in
 // the reference's order (descending span for the logsumexp, _cython_utils.pyx:13-25; ascending span for
 // the draw, :75-89) -- the same values, bit for bit, as the general routine below, at ~1/3 of its
@@ -54,7 +54,8 @@ __device__ __forceinline__ bool dp_warp_ffbs_small(const DpParams &p, const doub
                                                    int64_t ubase, int Wlim, double &total_out, int &used_out) {
     const int lane = threadIdx.x & 31;
     const int S = p.S;
-    const bool anneal = p.anneal_temp != 1.0;
+    const bool viterbi = (p.mode == SEGB_DP_VITERBI_GMM);        // max instead of logsumexp, argmax instead of a draw
+    const bool anneal = !viterbi && p.anneal_temp != 1.0;
     const double inv_t = 1. / p.anneal_temp;
     for (int j = lane; j < N; j += 32) bo[j] = (j == N - 1);
     if (lane == 0) al[0] = 0.0;
@@ -84,7 +85,7 @@ __device__ __forceinline__ bool dp_warp_ffbs_small(const DpParams &p, const doub
         double m;
         const double c = win(t, W, m);
         bad |= (c != c);
-        const double a_t = (m == neg_inf()) ? neg_inf() : lse_desc(c, W, m) + p.log_p_continue;
+        const double a_t = (m == neg_inf()) ? neg_inf() : (viterbi ? m : lse_desc(c, W, m) + p.log_p_continue);
         __syncwarp();
         if (lane == 0) al[t] = a_t;
         __syncwarp();
@@ -120,18 +121,30 @@ __device__ __forceinline__ bool dp_warp_ffbs_small(const DpParams &p, const doub
         } else {
             pl = (lane < W) ? exp(c - lse) : 0.0;
         }
-        double x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __shfl_sync(FULL, pl, i);
-        double uu = p.uniforms[ubase + used];
-        used++;
         int idx = W - 1;
-        bool done = false;
+        if (viterbi) {
+            // argmax of the exp-normalised window, first maximum = shortest span (:843-844)
+            double pm = pl;
+            pm = fmax(pm, __shfl_xor_sync(FULL, pm, 1));
+            pm = fmax(pm, __shfl_xor_sync(FULL, pm, 2));
+            pm = fmax(pm, __shfl_xor_sync(FULL, pm, 4));
+            pm = __shfl_sync(FULL, pm, 0);
+            const unsigned hit = __ballot_sync(FULL, lane < W && pl == pm);
+            if (hit == 0) return false;
+            idx = __ffs(hit) - 1;
+        } else {
+            double x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i < W && !done) {
-                uu = uu - x[i];
-                if (uu < 0) { idx = i; done = true; }
+            for (int i = 0; i < 8; ++i) x[i] = __shfl_sync(FULL, pl, i);
+            double uu = p.uniforms[ubase + used];
+            used++;
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < W && !done) {
+                    uu = uu - x[i];
+                    if (uu < 0) { idx = i; done = true; }
+                }
             }
         }
         const int k = idx + 1;
@@ -158,7 +171,7 @@ __device__ __forceinline__ void dp_warp_body(const DpParams &p, const double *sc
     const int n_min = p.n_min;
     const int l_cut = n_min > 1 ? n_min : 1;                        // [-S : -(n_min-1)] keeps spans >= n_min
     int status = SEGB_DP_OK;
-    if (p.mode == SEGB_DP_FFBS && n_min <= 1 && Wlim <= 8 && alphas_out == nullptr) {
+    if ((p.mode == SEGB_DP_FFBS || p.mode == SEGB_DP_VITERBI_GMM) && n_min <= 1 && Wlim <= 8 && alphas_out == nullptr) {
         double tot;
         int usd;
         if (dp_warp_ffbs_small(p, sc, bo, N, al, ubase, Wlim, tot, usd)) {

@@ -831,3 +831,33 @@ def test_mma_scorer_other_dims(sb, D):
     npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
     npt.assert_array_equal(val.cpu().numpy().view(np.int32), val_e.cpu().numpy().view(np.int32))
     assert int(mma.n_fallback.item()) < n_emb // 2
+
+
+@pytest.mark.parametrize("fb_type,anneal", [("standard", False), ("standard", True), ("viterbi", False)])
+def test_unigram_sweeps_vs_oracle_larger(sb, fb_type, anneal):
+    """The low-latency paths of the cooperative sweep (small-window FFBS / Viterbi, annealed backward
+    sampling, fast draw, MAP assignment) against the oracle on a corpus larger than the golden one:
+    identical boundaries and assignments after two sweeps under the same random stream."""
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf, synth, unigram_acoustic_wordseg as uaw
+    D, K, U, S = 24, 40, 60, 6
+    mats, vids, durs, lms = synth.make_corpus_dicts(U, D=D, K_true=15, n_min=6, n_max=18, n_slices_max=S,
+                                                    noise=0.08, seed=77)
+    var = 0.002 * np.ones(D)
+
+    def make(mod, am, pr):
+        random.seed(11)
+        np.random.seed(11)
+        return mod.UnigramAcousticWordseg(am, 10., K, pr, mats, vids, durs, lms, p_boundary_init=0.5,
+                                          beta_sent_boundary=-1, n_slices_max=S, fb_type=fb_type, lms=0.9,
+                                          time_power_term=1.1, wip=-0.2)
+    seg = make(uaw, fbgmm.FBGMM, gcf.FixedVarPrior(var, np.zeros(D), var / 0.05))
+    st = random.getstate()
+    kw = {"anneal_schedule": "linear", "anneal_start_temp_inv": 0.4, "anneal_gibbs_am": True} if anneal else {}
+    rec = seg.gibbs_sample(2, **kw)
+    oseg = make(so, so.FBGMM, so.FixedVarPrior(var, np.zeros(D), var / 0.05))
+    assert random.getstate() == st
+    temps = list(rec["anneal_temp"]) if anneal else None
+    orec = oseg.gibbs_sample(2, anneal_temps=temps, anneal_gibbs_am=anneal)
+    npt.assert_array_equal(seg.utterances.boundaries, oseg.utterances.boundaries)
+    npt.assert_array_equal(seg.acoustic_model.components.assignments, oseg.acoustic_model.components.assignments)
+    npt.assert_allclose(rec["log_marg*length"], orec["log_marg*length"], rtol=1e-10)
