@@ -132,6 +132,14 @@ int segb_fixedvar_add_items(const segb_fixedvar *m, const int32_t *ids, const in
 int segb_fixedvar_del_items(const segb_fixedvar *m, const int32_t *ids, int32_t n,
                             const int32_t *relabel_ids, int64_t relabel_n, void *stream);
 
+/* The constructor's `for k: for i in where(assignments == k): add_item(i, k)` (:111-120) into an EMPTY
+ * model, in parallel: every component replays its own members' additions in index order (same rounded
+ * operations as add_item, bit-identical statistics).  order [n_emb] = item ids stably sorted by
+ * assignment, seg_off [K_max + 1] = start of component k's members (unassigned items first);
+ * components 0..K_new-1 must all be non-empty.                                                    */
+int segb_fixedvar_build(const segb_fixedvar *m, const int64_t *order, const int64_t *seg_off, int32_t K_new,
+                        void *stream);
+
 /* log_post_pred(i) (:242-253) for k < K and log_prior(i) (:224-231) for one item:
  * out[0..K_max): active slots get the posterior predictive, the rest the prior. */
 int segb_fixedvar_log_pred_row(const segb_fixedvar *m, int32_t id, double *out, void *stream);

@@ -56,6 +56,7 @@ _PROTOS = {
                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "segb_fixedvar_add_items": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_i32, c_vp]),
     "segb_fixedvar_del_items": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "segb_fixedvar_build": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_i32, c_vp]),
     "segb_fixedvar_log_pred_row": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_i32, c_vp, c_vp]),
     "segb_fixedvar_log_marg": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_i64, c_f64, c_f64, c_vp, c_vp]),
     "segb_fixedvar_assign_items": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_i32, c_i32, c_f64, c_vp,

@@ -431,6 +431,55 @@ __global__ void __launch_bounds__(1024) fv_assign_utt_kernel(segb_fixedvar m, se
     if (mode == 0 && threadIdx.x == 0) *u_counter = upos;
 }
 
+// ---------------------------------------------------------------- bulk construction
+
+// The constructor's loop `for k: for i in where(assignments == k): add_item(i, k)` (:111-120) for a model
+// that is still EMPTY, without its one-item-at-a-time dependency: a component's statistics only depend on
+// its own members in index order, so thread (k, d) replays that component's additions for one dimension --
+// the same sequence of separately rounded operations as fv_add_item, bit for bit.  `order` = item ids
+// stably sorted by assignment, seg_off[k] = start of component k's members (as for the diagnostics).
+__global__ void fv_build_stats_kernel(segb_fixedvar m, const int64_t *order, const int64_t *seg_off, int K_new) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)K_new * m.D) return;
+    const int k = (int)(idx / m.D), d = (int)(idx % m.D);
+    const int KM = m.K_max;
+    double num, pN;
+    if (m.model == SEGB_MODEL_DIAG) {                   // gaussian_components_diag.py:162-177
+        num = __dmul_rn(m.k_0, m.mu_0[d]);
+        pN = __dadd_rn(m.precision_0[d], __dmul_rn(m.k_0, __dmul_rn(m.mu_0[d], m.mu_0[d])));
+        for (int64_t j = seg_off[k]; j < seg_off[k + 1]; ++j) {
+            num = __dadd_rn(num, fv_x(m, order[j], d));
+            pN = __dadd_rn(pN, fv_xsq(m, order[j], d));
+        }
+    } else {
+        const double pr = m.precision[d];
+        num = __dmul_rn(m.precision_0[d], m.mu_0[d]);
+        pN = m.precision_0[d];
+        for (int64_t j = seg_off[k]; j < seg_off[k + 1]; ++j) {
+            num = __dadd_rn(num, __dmul_rn(pr, fv_x(m, order[j], d)));
+            pN = __dadd_rn(pN, pr);
+        }
+    }
+    const size_t o = (size_t)d * KM + k;
+    m.mu_N_numT[o] = num;
+    m.prec_NT[o] = pN;
+}
+
+// counts, assignments and the derived tables (fv_refresh) of the freshly built components: block per component.
+__global__ void __launch_bounds__(256) fv_build_finish_kernel(segb_fixedvar m, const int64_t *order, const int64_t *seg_off,
+                                                              int K_new) {
+    extern __shared__ double smem[];
+    const int k = blockIdx.x;
+    const int64_t lo = seg_off[k], hi = seg_off[k + 1];
+    for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) m.assignments[order[j]] = k;
+    if (threadIdx.x == 0) {
+        m.counts[k] = (int32_t)(hi - lo);
+        if (k == 0) { *m.K = K_new; *m.n_total = seg_off[K_new] - seg_off[0]; }
+    }
+    __syncthreads();
+    fv_refresh(m, k, smem);
+}
+
 // ---------------------------------------------------------------- bigram LM + bigram cluster sampling
 
 // counts_from_utterance (+1, bigram_lms.py:98-105) / remove_counts_from_utterance (-1, :107-113):
@@ -713,5 +762,18 @@ extern "C" int segb_gibbs_sweep_bigram(const segb_fixedvar *m, const segb_bigram
                                                      assignments_only ? nullptr : status + i);
         SEGB_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+extern "C" int segb_fixedvar_build(const segb_fixedvar *m, const int64_t *order, const int64_t *seg_off, int32_t K_new,
+                                   void *stream) {
+    SEGB_CHECK_ARG(m && order && seg_off && K_new >= 0 && K_new <= m->K_max, "null pointer / K");
+    if (K_new == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)K_new * m->D;
+    fv_build_stats_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(*m, order, seg_off, K_new);
+    SEGB_LAUNCH_CHECK();
+    fv_build_finish_kernel<<<K_new, 256, sizeof(double) * m->D, st>>>(*m, order, seg_off, K_new);
+    SEGB_LAUNCH_CHECK();
     return 0;
 }

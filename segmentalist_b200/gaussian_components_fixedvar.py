@@ -70,9 +70,12 @@ class GaussianComponentsFixedVar(object):
             assignments = np.asarray(assignments, dtype=np.int64)                # :111-120
             assert (self.N,) == assignments.shape
             assert set(assignments).difference([-1]) == set(range(assignments.max() + 1))
-            order = np.argsort(assignments, kind="stable")
-            order = order[assignments[order] >= 0]
-            self._add_many(order, assignments[order])
+            if assignments.max() >= 0:
+                # all components at once, each replaying its members' add_item calls in index order
+                a_dev = _lib.dev(assignments.astype(np.int32))
+                order, seg_off = _lib.members_by_component(a_dev, self.K_max)
+                _lib.check(_lib.lib().segb_fixedvar_build(self.struct(), _lib.ptr(order), _lib.ptr(seg_off),
+                                                          int(assignments.max()) + 1, _lib.stream_ptr()))
 
     @classmethod
     def from_device(cls, X_dev, prior, K_max, alpha=1.0, lms=1.0):
