@@ -68,8 +68,9 @@ typedef struct {
 
 /* ------------------------------------------------------------------ DP (A5-A7) */
 
-/* Batched segmentation DP over n_utt independent utterances (warp per
- * utterance).  Replaces the three fb_func implementations named above.
+/* Batched segmentation DP over n_utt independent utterances (thread per utterance with
+ * TMA-staged score blocks for batches; warp per utterance for long spans and single
+ * utterances).  Replaces the three fb_func implementations named above.
  * scores: banded float64.  uniforms: utterance u reads uniforms[pos_off[u] + i]
  * for its i-th back-sampled segment, unless u_counter != NULL, in which case
  * the draws are taken from uniforms[*u_counter ...] and *u_counter is advanced
@@ -382,6 +383,12 @@ int segb_kmeans_sum_neg_sqrd_norm_k(const segb_kmeans *m, const int64_t *order, 
  * launches accumulate into them.  out16 (HOST array, may be NULL) receives the current totals
  * before they are zeroed.  enable == 0 releases the counters.  Synchronous.                    */
 int segb_debug_gibbs_prof(unsigned long long *out16, int enable);
+
+/* Test aid: start value of the cooperative sweeps' grid-barrier arrival counter (default 0).  The counter
+ * is 32 bits wide and wraps during long launches by design (every CTA compares its own target modulo
+ * 2^32); a base just below 2^32 forces the wrap after a few barriers.  Applies to the following
+ * segb_*_coop launches.                                                                          */
+int segb_debug_gibbs_bar_base(uint32_t base);
 
 #ifdef __cplusplus
 }

@@ -104,6 +104,7 @@ _PROTOS = {
                                                c_vp, c_i32, c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                c_vp, c_vp]),
     "segb_debug_gibbs_prof": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "segb_debug_gibbs_bar_base": (ctypes.c_int, [ctypes.c_uint32]),
     "segb_gibbs_sweep_bigram_coop": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(BigramLM),
                                                     ctypes.POINTER(Corpus), c_vp, c_i32, c_f64, c_f64, c_f64, c_i32, c_vp,
                                                     c_vp, c_vp, c_vp, c_vp, c_vp]),

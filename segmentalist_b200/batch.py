@@ -10,7 +10,7 @@ contiguous range of utterances (and their embeddings) plus a replica of the
 means, and one NCCL all-reduce of (sum_x [K_max, D] float64, cnt [K_max] int64)
 per sweep rebuilds identical means everywhere.
 
-Semantics (pinned by oracle.seg_oracle.frozen_kmeans_sweep and
+Semantics (pinned by the test oracle's frozen_kmeans_sweep and
 tests/golden/kmeans_wordseg.npz): phase 1 = the reference's pure functions
 get_vec_embed_neg_len_sqrd_norms -> forward_backward_kmeans_viterbi ->
 get_max_assignments (kmeans_acoustic_wordseg.py:334-351,449-555,

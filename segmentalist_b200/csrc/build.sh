@@ -6,6 +6,7 @@ OUT="$HERE/../libsegb200.so"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr --extended-lambda -Xcompiler -fPIC ${SEGB_NVCC_EXTRA}"
 OBJS=""
+PIDS=""
 for f in api dp fixedvar fixedvar_gibbs kmeans kmeans_mma fixedvar_mma diagnostics; do
   if [ -f "$HERE/$f.cu" ]; then
     stale=0
@@ -13,11 +14,15 @@ for f in api dp fixedvar fixedvar_gibbs kmeans kmeans_mma fixedvar_mma diagnosti
       if [ ! -f "$HERE/$f.o" ] || [ "$dep" -nt "$HERE/$f.o" ]; then stale=1; fi
     done
     if [ $stale = 1 ]; then
+      rm -f "$HERE/$f.o"          # a failed compile must not leave a stale object to link
       $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/$f.o" &
+      PIDS="$PIDS $!"
     fi
     OBJS="$OBJS $HERE/$f.o"
   fi
 done
-wait
+for pid in $PIDS; do
+  wait $pid || { echo "build.sh: a compile job failed" >&2; exit 1; }
+done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" $OBJS -lcudart
 echo "built $OUT"

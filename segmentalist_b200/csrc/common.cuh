@@ -10,6 +10,8 @@ namespace segb {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// current device id, its SM count and whether it supports cooperative launches (cached per device)
+int device_info(int *dev_out, int *n_sm_out, int *coop_out);
 
 #define SEGB_CHECK_ARG(cond, msg)                         \
     do {                                                  \

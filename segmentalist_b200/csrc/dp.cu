@@ -641,18 +641,21 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
             p.group = G;
             const int groups = (n_utt + G - 1) / G;
             auto launch = [&](auto kern) -> int {
-                // resident warps per device for this (kernel, shared-memory size): queried once
-                static void *cached_kern = nullptr;
-                static size_t cached_smem = 0;
-                static int cached_resident = 0;
-                if (cached_kern != (void *)kern || cached_smem != st_smem) {
+                // resident warps per device for this (kernel, shared-memory size, device): queried when
+                // any of the three changes (the shared-memory opt-in is a per-device function attribute);
+                // thread_local: concurrent host threads each keep their own small cache
+                static thread_local void *cached_kern = nullptr;
+                static thread_local size_t cached_smem = 0;
+                static thread_local int cached_resident = 0, cached_dev = -1;
+                int dev = 0, n_sm = 0;
+                { const int rc = device_info(&dev, &n_sm, nullptr); if (rc) return rc; }
+                if (cached_kern != (void *)kern || cached_smem != st_smem || cached_dev != dev) {
                     if (st_smem > 48 * 1024)
                         SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
-                    int dev = 0, n_sm = 0, per_sm = 0;
-                    SEGB_CUDA(cudaGetDevice(&dev));
-                    SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+                    int per_sm = 0;
                     SEGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, st_smem));
-                    cached_kern = (void *)kern; cached_smem = st_smem; cached_resident = max(1, per_sm) * n_sm;
+                    cached_kern = (void *)kern; cached_smem = st_smem; cached_dev = dev;
+                    cached_resident = max(1, per_sm) * n_sm;
                 }
                 const int blocks = min(groups, cached_resident);            // persistent warps
                 kern<<<blocks, 32, st_smem, stream>>>(p);

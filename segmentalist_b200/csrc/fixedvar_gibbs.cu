@@ -46,7 +46,8 @@ struct GibbsParams {
     double *log_probs;
     int32_t *status;
     // work area (global)
-    unsigned *bar;                 // [2] arrival count, generation
+    unsigned *bar;                 // [0] arrival counter (pre-loaded with bar_base), [16..] per-CTA trace tags
+    unsigned bar_base;             // value the host wrote into the counter before the launch
     double *part_m, *part_t;       // [G][M_cap] partial (max, sum-exp) of every candidate per CTA
     double *seg_prior;             // [M_cap] log_prior of every candidate
     double *scores;                // [M_cap] banded scores of the current utterance
@@ -58,10 +59,18 @@ struct GibbsParams {
 
 // Grid barrier (all CTAs are co-resident: cooperative launch) on ONE monotonic counter: CTA-wide
 // bar.sync, then thread 0 arrives with a release-add and polls with acquire loads until the counter
-// reaches the next multiple of the grid size -- one L2 round trip to arrive, no reset / generation
-// write by the last arriver (the sense-reversing version cost ~4 us per barrier on the per-token
-// critical path).  The counter is zeroed by the host before every launch; a protocol bug traps
-// instead of hanging the GPU.
+// reaches this CTA's next target -- one L2 round trip to arrive, no reset / generation write by the
+// last arriver (the sense-reversing version cost ~4 us per barrier on the per-token critical path).
+// Every CTA takes part in every barrier, so each keeps its own target in shared memory
+// (g_bar_target: base + generation * grid size, advanced by the grid size per barrier) and compares
+// it with the counter MODULO 2^32: the counter may wrap any number of times during a launch (a
+// whole-model sweep over 30M items arrives 4.4e9 times) because all CTAs are always within one
+// grid size (< 2^31) of each other.  The host writes the base into the counter before every launch;
+// a protocol bug traps instead of hanging the GPU.
+__shared__ unsigned g_bar_target;
+__device__ __forceinline__ void grid_barrier_init(unsigned base) {
+    if (threadIdx.x == 0) g_bar_target = base;
+}
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, unsigned tag = 0, unsigned h = 0) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -69,8 +78,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, u
         trace[blockIdx.x] = tag;
         trace[160 + blockIdx.x] = h;
         unsigned old, cur;
+        const unsigned target = g_bar_target + n_blocks;
+        g_bar_target = target;
         asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
-        const unsigned target = (old / n_blocks + 1) * n_blocks;
         unsigned spins = 0;
         for (;;) {
             asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
@@ -83,6 +93,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned n_blocks, u
                 __trap();
             }
         }
+        (void)old;
     }
     __syncthreads();
 }
@@ -343,6 +354,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     auto k_of = [&](int kl) { return b + kl * G; };
     auto n_act_of = [&](int K_) { return (K_ > b) ? min(n_own, (K_ - b + G - 1) / G) : 0; };
 
+    grid_barrier_init(p.bar_base);
     GibbsSmem s;
     {
         double *q = reinterpret_cast<double *>(gsm);
@@ -982,6 +994,15 @@ static inline int gibbs_grid(int K_max, int n_sm) { return K_max < n_sm ? K_max 
 
 // development aid: per-phase clock totals of CTA 0 (enabled by segb_debug_gibbs_prof(…, 1))
 static unsigned long long *g_prof = nullptr;
+// test aid: the value the arrival counter starts from (default 0); a value just below 2^32 makes the
+// counter wrap after a few barriers (tests/test_gpu_parity.py::test_gibbs_barrier_counter_wrap)
+static unsigned g_bar_base = 0;
+static int init_barrier(unsigned *bar, unsigned *base_out, cudaStream_t st) {
+    SEGB_CUDA(cudaMemsetAsync(bar, 0, 2048, st));
+    *base_out = g_bar_base;
+    if (g_bar_base) SEGB_CUDA(cudaMemcpyAsync(bar, &g_bar_base, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    return 0;
+}
 
 }  // namespace segb
 
@@ -1002,13 +1023,8 @@ static int launch_gibbs_coop(const segb_fixedvar *m, const segb_bigram_lm *lm, c
     SEGB_CHECK_ARG(c->tok_id && c->bounds, "corpus needs bounds and tok_id");
     if (n_order == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    static int n_sm = 0, coop = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        SEGB_CUDA(cudaGetDevice(&dev));
-        SEGB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int n_sm = 0, coop = 0;
+    { const int rc = device_info(nullptr, &n_sm, &coop); if (rc) return rc; }
     if (!coop || n_sm > 160) { set_error("cooperative launch unavailable"); return SEGB_E_UNSUPPORTED; }
     if (m->D > 256) { set_error("the cooperative Gibbs sweep covers D <= 256"); return SEGB_E_UNSUPPORTED; }
     GibbsParams p;
@@ -1025,7 +1041,7 @@ static int launch_gibbs_coop(const segb_fixedvar *m, const segb_bigram_lm *lm, c
     p.M_cap = c->N_max * c->S;
     p.xb = (p.per > 12) ? 8 : 32;
     const size_t smem = gibbs_smem_bytes(m->D, m->K_max, p.per, p.xb, p.M_cap, c->N_max);
-    if (smem > 227 * 1024) { set_error("model too large for the persistent Gibbs sweep (%zu bytes of shared memory)", smem); return SEGB_E_UNSUPPORTED; }
+    if (smem > 227 * 1024 - 16) { set_error("model too large for the persistent Gibbs sweep (%zu bytes of shared memory)", smem); return SEGB_E_UNSUPPORTED; }
     unsigned char *w = (unsigned char *)work;
     p.bar = (unsigned *)w; w += 2048;                 // count, generation, pad, per-CTA trace tags
     p.part_m = (double *)w; w += 8 * (size_t)G * p.M_cap;
@@ -1034,7 +1050,7 @@ static int launch_gibbs_coop(const segb_fixedvar *m, const segb_bigram_lm *lm, c
     p.scores = (double *)w; w += 8 * (size_t)p.M_cap;
     p.v = (double *)w;
     p.prof = g_prof;
-    SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
+    { const int rc = init_barrier(p.bar, &p.bar_base, st); if (rc) return rc; }
     const void *kern = lm ? (const void *)fv_gibbs_kernel<false, true> : (const void *)fv_gibbs_kernel<false, false>;
     SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&p};
@@ -1069,10 +1085,8 @@ extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t
     SEGB_CHECK_ARG(m && d_items && uniforms && u_counter && work, "null pointer");
     if (n_items == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0, coop = 0, n_sm = 0;
-    SEGB_CUDA(cudaGetDevice(&dev));
-    SEGB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    int coop = 0, n_sm = 0;
+    { const int rc = device_info(nullptr, &n_sm, &coop); if (rc) return rc; }
     if (!coop || n_sm > 160) { set_error("cooperative launch unavailable"); return SEGB_E_UNSUPPORTED; }
     if (m->D > 256) { set_error("the cooperative Gibbs sweep covers D <= 256"); return SEGB_E_UNSUPPORTED; }
     GibbsParams p;
@@ -1088,16 +1102,21 @@ extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t
     p.M_cap = 1;
     p.xb = 1;
     const size_t smem = gibbs_smem_bytes(m->D, m->K_max, p.per, p.xb, p.M_cap, 1);
-    if (smem > 227 * 1024) { set_error("model too large for the persistent Gibbs sweep (%zu bytes of shared memory)", smem); return SEGB_E_UNSUPPORTED; }
+    if (smem > 227 * 1024 - 16) { set_error("model too large for the persistent Gibbs sweep (%zu bytes of shared memory)", smem); return SEGB_E_UNSUPPORTED; }
     unsigned char *w = (unsigned char *)work;
     p.bar = (unsigned *)w; w += 2048;
     p.part_m = p.part_t = p.seg_prior = p.scores = nullptr;
     p.v = (double *)w;
-    SEGB_CUDA(cudaMemsetAsync(p.bar, 0, 2048, st));
+    { const int rc = init_barrier(p.bar, &p.bar_base, st); if (rc) return rc; }
     SEGB_CUDA(cudaFuncSetAttribute(fv_gibbs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&p};
     SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel<true, false>, dim3(G), dim3(GB_THREADS), args, smem, st));
     count_launch();
+    return 0;
+}
+
+extern "C" int segb_debug_gibbs_bar_base(uint32_t base) {
+    g_bar_base = base;
     return 0;
 }
 

@@ -374,12 +374,8 @@ extern "C" int segb_fvmma_log_marg(const segb_fixedvar *m, const void *x_tiles, 
         set_error("D=%d too large for the tensor-core log_marg kernel", D);
         return SEGB_E_UNSUPPORTED;
     }
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        SEGB_CUDA(cudaGetDevice(&dev));
-        SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int n_sm = 0;
+    { const int rc = device_info(nullptr, &n_sm, nullptr); if (rc) return rc; }
     auto kern = p.n_ksteps == 9 ? fv_logmarg_kernel<9> : fv_logmarg_kernel<0>;      // 9: D = 130 (dp = 144)
     SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;

@@ -720,12 +720,8 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     }
     p.n_abuf = (4 * (size_t)p.tile_bytes + fixed <= budget) ? 2 : 1;
     const size_t smem = (size_t)(p.n_abuf * 2 + 2) * p.tile_bytes + 256 + (size_t)MT_ROWS * 32;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        SEGB_CUDA(cudaGetDevice(&dev));
-        SEGB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int n_sm = 0;
+    { const int rc = device_info(nullptr, &n_sm, nullptr); if (rc) return rc; }
     const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;
     auto kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9> : kmeans_filter_kernel<0>;     // 9: D = 130 (KP = 144)
     SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
