@@ -354,6 +354,95 @@ int segb_fvmma_pack_x(const float *X, int64_t n_emb, int32_t D, void *x_tiles, v
 int segb_fvmma_log_marg(const segb_fixedvar *m, const void *x_tiles, void *w_tiles, int64_t n_emb, float *out,
                         void *stream);
 
+/* ------------------------------------------------------------------ tensor-core log_marg_i, filter-and-refine (fixed variance) */
+
+/* FBGMM.log_marg_i (fbgmm.py:256-285) for ALL n_emb embeddings against the frozen model at ONE tensor pass:
+ * the filter GEMM of segb_mma_filter (fp16 operands, fp32 TMEM accumulators) computes
+ * s^_k ~ s_k = lms*pi_k + log_post_pred_k(x) (log_prior for the empty slots, one virtual row) and keeps, per
+ * embedding, the 16-component chunks that can hold a component within T nats of the best one (rigorous
+ * rounding bound added); segb_fvf_refine re-scores those exactly in float64 (delta form, like
+ * gaussian_components_fixedvar.py:247-252) and takes the logsumexp over the exact scores.  What is dropped
+ * carries at most K_max*exp(-T) of the sum (T = 25: 7e-8).  aniso != 0: prior.var / prior.var_0 are D-vectors
+ * (gaussian_components_fixedvar.py:95-99, tests/test_gaussian_components_fixedvar.py:51-53): inner dimension
+ * [x, x*x] in two chunks.  Rows with a flat posterior (third-best chunk inside the threshold) get an
+ * exhaustive exact scan; n_fallback counts them.
+ *   segb_fvf_pack_x      once: fp16 tile image of X (+ per-row rounding-error norms x_err [2 n_emb], x_max [2])
+ *   segb_fvf_pack_model  per model state: fp16 tile image of the model in w_tiles, the exact row tables and
+ *                        per-row error norms in `model` (segb_fvf_model_bytes), model-wide maxima in w_max [4]
+ *   segb_fvf_filter      the GEMM; cand = segb_mma_cand_bytes(n_emb) bytes of per-row records
+ *   segb_fvf_refine      log_marg [n_emb] float64, map_k [n_emb] (optional): the MAP slot of map_assign_i
+ *                        (fbgmm.py:465-494; the first empty slot is K); work = segb_fvf_work_bytes(n_emb)      */
+int64_t segb_fvf_x_tiles_bytes(int64_t n_emb, int32_t D, int32_t aniso);
+int64_t segb_fvf_w_tiles_bytes(int32_t K_max, int32_t D, int32_t aniso);
+int64_t segb_fvf_model_bytes(int32_t K_max, int32_t D, int32_t aniso);
+int64_t segb_fvf_work_bytes(int64_t n_emb);
+int segb_fvf_pack_x(const float *X, int64_t n_emb, int32_t D, int32_t aniso, void *x_tiles, float *x_err,
+                    float *x_max, void *stream);
+int segb_fvf_pack_model(const segb_fixedvar *m, int32_t aniso, void *w_tiles, void *model, float *w_max,
+                        void *stream);
+int segb_fvf_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
+                    int32_t aniso, const float *x_max, const float *w_max, float T, void *cand, void *stream);
+int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, int32_t aniso, const void *model,
+                    const void *cand, const float *x_err, const float *w_max, float T, void *work,
+                    double *log_marg, int32_t *map_k, int64_t *n_fallback, void *stream);
+
+/* get_vec_embed_log_probs (unigram_acoustic_wordseg.py:474-511) from per-embedding log marginals:
+ * scores[slot] = log_marg[seg_id[slot]] * seg_dur[slot]**time_power_term + wip, -inf for absent slots /
+ * NaN durations, over landmark positions [pos_first, pos_first + n_positions).                        */
+int segb_fixedvar_band_scores(const segb_corpus *c, int64_t pos_first, int64_t n_positions,
+                              const double *log_marg, double time_power_term, double wip, double *scores,
+                              void *stream);
+
+/* Frozen-model component choice for the tokens of the current boundaries (tok_id): mode 1 = map_assign_i
+ * (fbgmm.py:465-494; choice[id] = map_k[id]); mode 0 = gibbs_sample_inside_loop_i (:422-463, anneal_temp 1):
+ * inverse-CDF draw with uniforms[pos] over the exact probabilities of the slots the filter kept, in slot
+ * order, empty slots last.  choice[id] is the raw slot index (>= K: an empty slot); add_item's clamp is
+ * applied afterwards in token order (segb_frozen_new_list / segb_frozen_clamp).                        */
+int segb_fvf_choose_tokens(const float *X, int32_t D, int32_t K_max, int32_t K, int32_t aniso, const void *model,
+                           const void *cand, const float *x_err, const float *w_max, float T,
+                           const segb_corpus *c, int64_t pos_first, int64_t n_positions, int32_t mode,
+                           const int32_t *map_k, const double *uniforms, int32_t *choice, void *stream);
+
+/* ------------------------------------------------------------------ frozen-state model update (new batch mode) */
+
+/* tok_id from bounds for utterances [utt_first, +n_utt) (utterances.py:159-174 in banded form). */
+int segb_tokens_from_bounds(const segb_corpus *c, int32_t utt_first, int32_t n_utt, void *stream);
+
+/* add_item's `k > K -> K`, `k == K` opens a component (kmeans_components.py:103-106, fbgmm.py:459-460) for a
+ * whole sweep, in token order, without host logic:
+ *   segb_frozen_new_list: ordered compaction of the tokens (positions [pos_first, +n_positions)) whose
+ *     choice[id] >= K_before into list_j (the choices) / list_id (the embedding ids), n_list[0] = count
+ *     (entries beyond `cap` are dropped; segb_frozen_clamp reports that);
+ *   [ranks exchange list_j / n_list with a fixed-size all-gather: rank order is global token order]
+ *   segb_frozen_clamp: ONE serial pass (a single warp) over the concatenated lists [world][cap]; the
+ *     resolved components of this rank's tokens are written back into choice, the new K into K_out.   */
+int64_t segb_frozen_new_work_bytes(int64_t n_positions);
+int segb_frozen_new_list(const segb_corpus *c, int64_t pos_first, int64_t n_positions, const int32_t *choice,
+                         int32_t K_before, void *work, int32_t cap, int32_t *list_j, int32_t *list_id,
+                         int32_t *n_list, void *stream);
+int segb_frozen_clamp(const int32_t *lists, const int32_t *counts, int32_t world, int32_t cap, int32_t my_rank,
+                      int32_t K_before, int32_t K_max, const int32_t *list_id, int32_t *out_k, int32_t *choice,
+                      int32_t *K_out, int32_t *overflow, void *stream);
+
+/* FBGMM frozen update.  collect: sum_x[k] += X[id], cnt[k] += 1 over the tokens (k = choice[id]) -- the
+ * buffers one all-reduce combines across ranks.  update: FBGMM.setup_components with the new assignments
+ * (fbgmm.py:96-137): labels made consecutive in order (new_label [K_max] out), statistics of every component
+ * from (sum_x, cnt) in closed form (gaussian_components_fixedvar.py:153-170, :317-325; equal to the
+ * constructor's sequential add_item sums up to float64 rounding), assignments of the tokens, K, n_total. */
+int segb_fixedvar_frozen_collect(const segb_fixedvar *m, const segb_corpus *c, int64_t pos_first,
+                                 int64_t n_positions, const int32_t *choice, double *sum_x, int64_t *cnt,
+                                 void *stream);
+int segb_fixedvar_frozen_update(const segb_fixedvar *m, const segb_corpus *c, int64_t pos_first,
+                                int64_t n_positions, const int32_t *choice, const double *sum_x,
+                                const int64_t *cnt, int32_t *new_label, void *stream);
+
+/* clean_components (kmeans_components.py:263-266) after segb_kmeans_set_means: the swap-with-last deletions
+ * of the components with cnt == 0 among the first *m->K are replayed on the counts, rows gathered, inactive
+ * slots reset to their random rows, live tokens relabelled, *m->K updated.  No host round trip.        */
+int64_t segb_kmeans_frozen_clean_work_bytes(int32_t K_max, int32_t D);
+int segb_kmeans_frozen_clean(const segb_kmeans *m, const segb_corpus *c, int64_t pos_first, int64_t n_positions,
+                             const int64_t *cnt, void *work, void *stream);
+
 /* ------------------------------------------------------------------ per-iteration diagnostics */
 
 /* Both calls take the items grouped by component: `order` [n_emb] = item ids stably sorted by

@@ -1407,3 +1407,84 @@ def frozen_kmeans_sweep(seg, utt_indices=None):
             comps.add_item(e, k)
     comps.clean_components()
     return total, plan
+
+
+# ---------------------------------------------------------------------------
+# Frozen-state FBGMM sweep (new batch mode; SURVEY 8c "oracle for the frozen-state batch mode")
+# ---------------------------------------------------------------------------
+
+def frozen_fbgmm_phase1(seg, u_fb=None, u_assign=None, utt_indices=None):
+    """Pure part of the frozen FBGMM sweep (model untouched): per utterance
+    get_vec_embed_log_probs (unigram_acoustic_wordseg.py:474-511, i.e. FBGMM.log_marg_i of every
+    candidate against the CURRENT model) -> forward_backward / forward_backward_viterbi (:653-864)
+    -> for every chosen segment the component choice of gibbs_sample_inside_loop_i (fbgmm.py:422-458,
+    fb_type "standard") or map_assign_i (:465-491, "viterbi") WITHOUT its add_item.
+    Draws: utterance u's i-th back-sampled segment uses u_fb[pos_off[u] + i]; the token ending at
+    landmark position p uses u_assign[p].  Writes the new boundaries into seg.utterances; returns
+    (per-utterance log_prob, [(embedding id, raw slot index)] in token order)."""
+    utts, am = seg.utterances, seg.acoustic_model
+    if utt_indices is None:
+        utt_indices = range(utts.D)
+    pos_off = np.concatenate([[0], np.cumsum(utts.lengths)])
+    log_probs, choices = [], []
+    for u in utt_indices:
+        N = utts.lengths[u]
+        n_packed = (N ** 2 + N) // 2
+        scores = seg.get_vec_embed_log_probs(utts.vec_ids[u, :n_packed], utts.durations[u, :n_packed])
+        log_p_continue = math.log(seg.calc_p_continue())
+        if seg.fb_type == "standard":
+            src = UniformSource(np.asarray(u_fb[pos_off[u]:pos_off[u + 1]], dtype=np.float64))
+            lp, bounds = forward_backward(scores, log_p_continue, N, seg.n_slices_min, seg.n_slices_max, u, 1,
+                                          uniform=src)
+        else:
+            lp, bounds = forward_backward_viterbi(scores, log_p_continue, N, seg.n_slices_min, seg.n_slices_max, u)
+        log_probs.append(lp)
+        utts.boundaries[u, :N] = bounds
+        for (s, e_), emb in zip(utts.get_segmented_landmark_indices(u), utts.get_segmented_embeds_i(u)):
+            if emb == -1:
+                continue
+            if seg.fb_type == "standard":
+                lpz = am._assign_scores(emb, True)
+                prob_z = np.exp(lpz - sp_logsumexp(lpz))
+                j = draw(prob_z, float(u_assign[pos_off[u] + e_ - 1]))
+            else:
+                lpz = am._assign_scores(emb, False)
+                prob_z = np.exp(lpz - sp_logsumexp(lpz))
+                j = int(np.argmax(prob_z))
+            choices.append((int(emb), int(j)))
+    return log_probs, choices
+
+
+def frozen_clamp(choices, K_before, K_max):
+    """add_item's / FBGMM's `if k > K: k = K`, a choice of slot K opening a component
+    (fbgmm.py:459-460, gaussian_components_fixedvar.py:162-165), applied in token order."""
+    K = int(K_before)
+    out = []
+    for e, j in choices:
+        k = min(j, K)
+        if k == K and K < K_max:
+            K += 1
+        out.append((e, k))
+    return out, K
+
+
+def frozen_fbgmm_sweep(seg, u_fb=None, u_assign=None):
+    """One frozen-model sweep of a UnigramAcousticWordseg oracle object (fixed-variance FBGMM).
+    Phase 1: frozen_fbgmm_phase1.  Phase 2: the choices go through add_item's clamp in token order, and
+    the model is rebuilt from the new assignments the way FBGMM.setup_components builds it
+    (fbgmm.py:96-137: labels made consecutive, then the GaussianComponentsFixedVar constructor's add_item
+    loop, gaussian_components_fixedvar.py:111-120).  Returns (sum of log_probs in utterance order, choices)."""
+    am = seg.acoustic_model
+    c = am.components
+    log_probs, choices = frozen_fbgmm_phase1(seg, u_fb, u_assign)
+    total = 0.0
+    for lp in log_probs:
+        total += lp
+    resolved, _ = frozen_clamp(choices, c.K, c.K_max)
+    assignments = -1 * np.ones(c.N, dtype=np.int64)
+    for e, k in resolved:
+        assignments[e] = k
+    if len(resolved):
+        assignments = _consecutive(assignments)
+    am.components = FixedVarComponents(c.X, am.prior, assignments, K_max=c.K_max)
+    return total, choices

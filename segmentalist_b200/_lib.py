@@ -96,6 +96,31 @@ _PROTOS = {
     "segb_fvmma_w_tiles_bytes": (c_i64, [c_i32, c_i32]),
     "segb_fvmma_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "segb_fvmma_log_marg": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "segb_fvf_x_tiles_bytes": (c_i64, [c_i64, c_i32, c_i32]),
+    "segb_fvf_w_tiles_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "segb_fvf_model_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "segb_fvf_work_bytes": (c_i64, [c_i64]),
+    "segb_fvf_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fvf_pack_model": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fvf_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, ctypes.c_float, c_vp, c_vp]),
+    "segb_fvf_refine": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, ctypes.c_float,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fixedvar_band_scores": (ctypes.c_int, [ctypes.POINTER(Corpus), c_i64, c_i64, c_vp, c_f64, c_f64, c_vp, c_vp]),
+    "segb_fvf_choose_tokens": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, ctypes.c_float,
+                                              ctypes.POINTER(Corpus), c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "segb_tokens_from_bounds": (ctypes.c_int, [ctypes.POINTER(Corpus), c_i32, c_i32, c_vp]),
+    "segb_frozen_new_work_bytes": (c_i64, [c_i64]),
+    "segb_frozen_new_list": (ctypes.c_int, [ctypes.POINTER(Corpus), c_i64, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp,
+                                            c_vp, c_vp]),
+    "segb_frozen_clamp": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                         c_vp]),
+    "segb_fixedvar_frozen_collect": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(Corpus), c_i64, c_i64, c_vp,
+                                                    c_vp, c_vp, c_vp]),
+    "segb_fixedvar_frozen_update": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(Corpus), c_i64, c_i64, c_vp,
+                                                   c_vp, c_vp, c_vp, c_vp]),
+    "segb_kmeans_frozen_clean_work_bytes": (c_i64, [c_i32, c_i32]),
+    "segb_kmeans_frozen_clean": (ctypes.c_int, [ctypes.POINTER(KMeansM), ctypes.POINTER(Corpus), c_i64, c_i64, c_vp,
+                                                c_vp, c_vp]),
     "segb_fixedvar_del_items_lm": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(BigramLM), c_vp, c_i32, c_vp,
                                                   c_i64, c_vp]),
     "segb_bigram_lm_update": (ctypes.c_int, [ctypes.POINTER(BigramLM), c_vp, c_i32, c_i32, c_vp]),

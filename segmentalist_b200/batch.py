@@ -28,7 +28,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .sharding import clamp_plan, compaction_plan, dist_on as _dist_on, reduce_packed
+from .sharding import dist_on as _dist_on, reduce_packed
 
 
 class MmaScorer(object):
@@ -152,6 +152,10 @@ class FrozenKMeansSweep(object):
         self.last_fallback = 0
         self.mma = MmaScorer(c) if scorer == "mma" else None
         self.K_host = None                     # host copy of the active-component count (no .item() per sweep)
+        # add_item's clamp and clean_components as device kernels (csrc/frozen.cu): no host logic per sweep
+        self.clamp = NewComponentClamp(corpus, c.K_max)
+        self.clean_work = torch.empty(lib.segb_kmeans_frozen_clean_work_bytes(c.K_max, c.D), dtype=torch.uint8,
+                                      device=dev)
 
     # ---- phases (each is one or two launches; no host sync inside)
     def score(self, X_host=None):
@@ -250,7 +254,9 @@ class FrozenKMeansSweep(object):
         """One frozen sweep; returns sum_neg_len_sqrd_norm (summed over all ranks).  No host
         round trip until the end: one all-reduce, one small device->host copy, one sync.
         X_host: pinned float32 host copy of the embeddings to (re)upload while scoring
-        (out-of-core / end-to-end use); None = the embeddings are already resident in HBM."""
+        (out-of-core / end-to-end use); None = the embeddings are already resident in HBM.
+        Precondition of the bit-identical means: per-component sums of the embeddings are exact in
+        float64 (true for float32 data of ordinary dynamic range; the sums are formed with atomics)."""
         c, cp = self.c, self.corpus
         if self.K_host is None:
             self.K_host = c.K
@@ -258,29 +264,28 @@ class FrozenKMeansSweep(object):
         self.score(X_host)
         self.segment()
         self.summarize()
-        self.collect()
         if K_before < c.K_max:
             self._clamp_inactive_winners(K_before)
+        self.collect()
         self.reduce_and_update()
-        K_now = self.K_host
+        self._clean_components()
         if self.scorer == "mma":
             self.flags[1:2].copy_(self.mma.n_fallback)
-        self.flags[2:3].copy_((self.cnt[:K_now] == 0).sum())
+        self.flags[2:3].copy_(c._K)
         torch.cuda.current_stream().wait_stream(self.side)
         self.flags_h.copy_(self.flags, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        n_bad, n_fb, n_empty = (int(v) for v in self.flags_h.tolist())
+        n_bad, n_fb, K_now = (int(v) for v in self.flags_h.tolist())
         assert n_bad == 0, "segmentation failed for %d utterances (status %s)" % (
             n_bad, np.unique(self.status.cpu().numpy()))
         self.last_fallback = n_fb
+        self.K_host = K_now
         # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time)
         total = float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
         if _dist_on():
             t = torch.tensor([total], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             total = float(t.item())
-        if n_empty:
-            self._clean_components(K_now)
         return total
 
     def fit(self, n_iter):
@@ -298,85 +303,243 @@ class FrozenKMeansSweep(object):
             K_before = self.K_host
             self.score()
             changed = (self.best_k[tok] != c._assign[tok]).sum().to(torch.int64).reshape(1)
-            self.collect()                                  # tokens of the unchanged boundaries, k = argmax
             if K_before < c.K_max:
                 self._clamp_inactive_winners(K_before)
+            self.collect()                                  # tokens of the unchanged boundaries, k = argmax
             self.reduce_and_update()
+            self._clean_components()
             if _dist_on():
                 dist.all_reduce(changed, op=dist.ReduceOp.SUM)
-            K_now = self.K_host
-            self.flags[2:3].copy_((self.cnt[:K_now] == 0).sum())
-            n_changed, n_empty = int(changed.item()), int(self.flags[2].item())
-            if n_empty:
-                self._clean_components(K_now)
+            n_changed, self.K_host = int(changed.item()), int(c._K.item())
             record["components"].append(self.K_host)
             record["n_mean_updates"].append(n_changed)
             if n_changed == 0:
                 break
         return record
 
-    def _clean_components(self, K_old):
-        """clean_components() (kmeans_components.py:263-266) without the per-deletion token
-        scan: the swap-with-last sequence is replayed on the host over the K counts (cheap),
-        giving for every surviving slot the component that ends up there; rows are then
-        gathered and tokens relabelled in one pass each."""
-        c = self.c
-        cnt = self.cnt[:K_old].cpu().numpy()
-        if not np.any(cnt == 0):
-            return
-        K, dst, src = compaction_plan(cnt, K_old)
-        if len(dst):
-            dst_d, src_d = _lib.dev(dst), _lib.dev(src)
-            c._mean_num[dst_d] = c._mean_num[src_d]
-            c._counts[dst_d] = c._counts[src_d]
-            c._means[dst_d] = c._means[src_d]
-            inv = torch.arange(c.K_max, dtype=torch.int32, device="cuda")
-            inv[src_d] = dst_d.to(torch.int32)
-            tok = self.corpus.tok_id[self.corpus.tok_id >= 0].long()
-            c._assign[tok] = inv[c._assign[tok].long()]
-        c._mean_num[K:K_old] = 0
-        c._counts[K:K_old] = 0
-        c._means[K:K_old] = c._rnd[K:K_old]
-        c._meansT.copy_(c._means.t())
-        c._K.fill_(int(K))
-        self.K_host = int(K)
+    def _clean_components(self):
+        """clean_components() (kmeans_components.py:263-266) on the device: the swap-with-last deletions of
+        the emptied components are replayed on the (global) counts by one thread, rows gathered and live
+        tokens relabelled in parallel (segb_kmeans_frozen_clean); K stays on the device."""
+        c, cp = self.c, self.corpus
+        _lib.check(_lib.lib().segb_kmeans_frozen_clean(c.struct(), cp.struct(), 0, cp.n_pos, _lib.ptr(self.cnt),
+                                                       _lib.ptr(self.clean_work), _lib.stream_ptr()))
 
     def _clamp_inactive_winners(self, K_before):
-        """add_item's `k > K -> K` clamp (kmeans_components.py:103-106) for tokens won by an
-        inactive slot.  Sequential by nature; resolved on the host over the (few) affected
-        tokens in utterance order, then the statistics of exactly those tokens are moved (sums of
-        float32 embeddings are exact in float64, so subtracting and re-adding a row leaves the
-        same bits as collecting again)."""
+        """add_item's `k > K -> K` clamp (kmeans_components.py:103-106) for tokens won by an inactive slot:
+        sequential in token order by nature.  Device version: the affected tokens are compacted in order,
+        ranks exchange their lists with a fixed-size all-gather, ONE serial pass by a single warp resolves
+        them, the winners are rewritten in best_k before the statistics are collected (NewComponentClamp)."""
         c, cp = self.c, self.corpus
-        flag = (self.cnt[K_before:] > 0).any().to(torch.int32).reshape(1)
+        _lib.check(_lib.lib().segb_tokens_from_bounds(cp.struct(), 0, cp.n_utt, _lib.stream_ptr()))
+        self.clamp.run(self.best_k, K_before)
+        c._K.copy_(self.clamp.K_out)
+
+
+# ---------------------------------------------------------------------------
+# Frozen-state FBGMM sweep (fixed-variance components)
+# ---------------------------------------------------------------------------
+
+LSE_T = 25.0          # nats below the best component at which a component is dropped from log_marg_i's sum
+
+
+def _is_aniso(c):
+    return not (np.all(c.precision == c.precision[0]) and np.all(c.precision_0 == c.precision_0[0]))
+
+
+class FvScorer(object):
+    """Buffers and call sequence of the tensor-core log_marg_i (segb_fvf_*): fp16 tile image of the
+    embeddings (packed once), fp16 model image + exact float64 row tables (packed per model state), the
+    32-byte per-row filter records, float64 log marginals and MAP slots out."""
+
+    def __init__(self, components, T=LSE_T):
+        lib, c, dev = _lib.lib(), components, "cuda"
+        assert c._X.dtype == torch.float32, "tensor-core log_marg needs float32 embeddings"
+        self.c, self.T = c, float(T)
+        self.aniso = int(_is_aniso(c))
+        u8 = torch.uint8
+        self.x_tiles = torch.empty(lib.segb_fvf_x_tiles_bytes(c.N, c.D, self.aniso), dtype=u8, device=dev)
+        self.w_tiles = torch.empty(lib.segb_fvf_w_tiles_bytes(c.K_max, c.D, self.aniso), dtype=u8, device=dev)
+        self.model = torch.empty(lib.segb_fvf_model_bytes(c.K_max, c.D, self.aniso), dtype=u8, device=dev)
+        self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=u8, device=dev)
+        self.work = torch.empty(lib.segb_fvf_work_bytes(c.N), dtype=u8, device=dev)
+        self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)
+        self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.w_max = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.log_marg = torch.empty(c.N, dtype=torch.float64, device=dev)
+        self.map_k = torch.empty(c.N, dtype=torch.int32, device=dev)
+        self.pack_x()
+
+    def pack_x(self):
+        c = self.c
+        _lib.check(_lib.lib().segb_fvf_pack_x(_lib.ptr(c._X), c.N, c.D, self.aniso, _lib.ptr(self.x_tiles),
+                                              _lib.ptr(self.x_err), _lib.ptr(self.x_max), _lib.stream_ptr()))
+
+    def pack_model(self):
+        _lib.check(_lib.lib().segb_fvf_pack_model(self.c.struct(), self.aniso, _lib.ptr(self.w_tiles),
+                                                  _lib.ptr(self.model), _lib.ptr(self.w_max), _lib.stream_ptr()))
+
+    def filter(self):
+        c = self.c
+        _lib.check(_lib.lib().segb_fvf_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
+                                              self.aniso, _lib.ptr(self.x_max), _lib.ptr(self.w_max), self.T,
+                                              _lib.ptr(self.cand), _lib.stream_ptr()))
+
+    def refine(self):
+        c = self.c
+        _lib.check(_lib.lib().segb_fvf_refine(_lib.ptr(c._X), c.N, c.D, c.K_max, self.aniso, _lib.ptr(self.model),
+                                              _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max), self.T,
+                                              _lib.ptr(self.work), _lib.ptr(self.log_marg), _lib.ptr(self.map_k),
+                                              _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+
+    def score(self):
+        """log_marg_i of every embedding (self.log_marg) and its MAP slot (self.map_k)."""
+        self.pack_model()
+        self.filter()
+        self.refine()
+
+
+class FrozenFBGMMSweep(object):
+    """One frozen-model sweep of the unigram FBGMM segmenter: every utterance is scored
+    (get_vec_embed_log_probs, unigram_acoustic_wordseg.py:474-511) and segmented (forward_backward /
+    forward_backward_viterbi, :653-864) against the SAME model, every new token picks its component from
+    that model (gibbs_sample_inside_loop_i / map_assign_i without the add, fbgmm.py:422-494), then the
+    model is rebuilt from the new assignments (FBGMM.setup_components, fbgmm.py:96-137).  Utterances (with
+    their embeddings) shard over ranks; ONE all-reduce of [sum_x | counts] per sweep, like the k-means
+    sweep.  Semantics pinned by the test oracle's frozen_fbgmm_sweep."""
+
+    def __init__(self, components, corpus, fb_type="standard", time_power_term=1.0, wip=0.0, T=LSE_T):
+        self.c, self.corpus = components, corpus
+        assert fb_type in ("standard", "viterbi")
+        self.fb_type, self.tpt, self.wip = fb_type, float(time_power_term), float(wip)
+        lib, c, cp, dev = _lib.lib(), components, corpus, "cuda"
+        self.lms_range_ok = True
+        if fb_type == "viterbi" and c._lms != 1.0:
+            # map_assign_i ranks the slots WITHOUT lms (fbgmm.py:475-479) while the filter ranks them with it:
+            # widen the threshold by the largest possible difference between the two rankings
+            n_tok = max(1, int(cp.n_pos))
+            T = T + abs(1.0 - c._lms) * float(np.log((c._alpha / c.K_max + n_tok) / (c._alpha / c.K_max)))
+        self.fv = FvScorer(c, T)
+        self.scores = torch.empty(cp.n_pos * cp.S, dtype=torch.float64, device=dev)
+        self.log_prob = torch.zeros(cp.n_utt, dtype=torch.float64, device=dev)
+        self.status = torch.zeros(cp.n_utt, dtype=torch.int32, device=dev)
+        self.choice = torch.full((c.N,), -1, dtype=torch.int32, device=dev)
+        self.red = torch.zeros(c.K_max * c.D + c.K_max, dtype=torch.float64, device=dev)
+        self.sum_x = self.red[:c.K_max * c.D].view(c.K_max, c.D)
+        self.cnt_f = self.red[c.K_max * c.D:]
+        self.cnt = torch.zeros(c.K_max, dtype=torch.int64, device=dev)
+        self.new_label = torch.empty(c.K_max, dtype=torch.int32, device=dev)
+        self.clamp = NewComponentClamp(cp, c.K_max)
+        self.K_host = None
+        self.last_fallback = 0
+
+    def score(self):
+        self.fv.score()
+
+    def segment(self, u_fb):
+        lib, cp, sp = _lib.lib(), self.corpus, _lib.stream_ptr()
+        cs = cp.struct()
+        _lib.check(lib.segb_fixedvar_band_scores(cs, 0, cp.n_pos, _lib.ptr(self.fv.log_marg), self.tpt, self.wip,
+                                                 _lib.ptr(self.scores), sp))
+        mode = _lib.DP_FFBS if self.fb_type == "standard" else _lib.DP_VITERBI_GMM
+        _lib.check(lib.segb_dp_banded(cs, 0, cp.n_utt, _lib.ptr(self.scores), mode, 0.0, 1.0, _lib.ptr(u_fb), None,
+                                      _lib.ptr(cp.bounds), _lib.ptr(self.log_prob), None, None,
+                                      _lib.ptr(self.status), sp))
+        _lib.check(lib.segb_tokens_from_bounds(cs, 0, cp.n_utt, sp))
+
+    def choose(self, u_assign, K_before):
+        lib, c, cp, fv, sp = _lib.lib(), self.c, self.corpus, self.fv, _lib.stream_ptr()
+        mode = 0 if self.fb_type == "standard" else 1
+        _lib.check(lib.segb_fvf_choose_tokens(_lib.ptr(c._X), c.D, c.K_max, int(K_before), fv.aniso, _lib.ptr(fv.model),
+                                              _lib.ptr(fv.cand), _lib.ptr(fv.x_err), _lib.ptr(fv.w_max), fv.T,
+                                              cp.struct(), 0, cp.n_pos, mode, _lib.ptr(fv.map_k), _lib.ptr(u_assign),
+                                              _lib.ptr(self.choice), sp))
+
+    def collect(self):
+        lib, c, cp, sp = _lib.lib(), self.c, self.corpus, _lib.stream_ptr()
+        self.red.zero_()
+        self.cnt.zero_()
+        _lib.check(lib.segb_fixedvar_frozen_collect(c.struct(), cp.struct(), 0, cp.n_pos, _lib.ptr(self.choice),
+                                                    _lib.ptr(self.sum_x), _lib.ptr(self.cnt), sp))
+
+    def reduce_and_update(self):
+        lib, c, cp, sp = _lib.lib(), self.c, self.corpus, _lib.stream_ptr()
+        reduce_packed(self.red, self.cnt_f, self.cnt)
+        c._assign.fill_(-1)
+        _lib.check(lib.segb_fixedvar_frozen_update(c.struct(), cp.struct(), 0, cp.n_pos, _lib.ptr(self.choice),
+                                                   _lib.ptr(self.sum_x), _lib.ptr(self.cnt), _lib.ptr(self.new_label), sp))
+
+    def sweep(self, u_fb=None, u_assign=None):
+        """One sweep.  u_fb / u_assign: float64 device arrays [n_pos] of uniforms (utterance u's i-th
+        back-sampled segment reads u_fb[pos_off[u] + i]; the token ending at position p reads u_assign[p]);
+        unused for fb_type "viterbi".  Returns the sum of the utterances' log_prob over all ranks."""
+        c, cp = self.c, self.corpus
+        if self.K_host is None:
+            self.K_host = c.K
+        K_before = self.K_host
+        if self.fb_type == "standard":
+            assert u_fb is not None and u_assign is not None and u_fb.numel() == cp.n_pos == u_assign.numel()
+        self.score()
+        self.segment(u_fb)
+        self.choose(u_assign, K_before)
+        if K_before < c.K_max:
+            self.clamp.run(self.choice, K_before)
+        self.collect()
+        self.reduce_and_update()
+        flags = torch.stack([(self.status != _lib.DP_OK).sum(), self.fv.n_fallback[0], c._K[0].to(torch.int64)])
+        n_bad, n_fb, K_now = (int(v) for v in flags.tolist())            # the sweep's one host sync
+        assert n_bad == 0, "segmentation failed for %d utterances (status %s)" % (
+            n_bad, np.unique(self.status.cpu().numpy()))
+        self.last_fallback, self.K_host = n_fb, K_now
+        lp = self.log_prob.cpu().numpy()
+        total = float(np.cumsum(lp)[-1]) if cp.n_utt else 0.0          # utterance-order float64 sum
         if _dist_on():
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()) == 0:
-            return
-        tid = cp.tok_id
-        k_at = torch.where(tid >= 0, c._assign[tid.clamp(min=0).long()], torch.full_like(tid, -1))
-        pos = (k_at >= K_before).nonzero().flatten()            # landmark order == token order
-        ids_d = tid[pos].long()
-        ks_old_d = k_at[pos].long()
-        ks = ks_old_d.cpu().numpy().astype(np.int64)
+            t = torch.tensor([total], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            total = float(t.item())
+        return total
+
+
+class NewComponentClamp(object):
+    """add_item's `k > K -> K` / "slot K opens a component" rule for a whole sweep on the device
+    (segb_frozen_new_list + segb_frozen_clamp): ordered compaction of the affected tokens, a fixed-size
+    all-gather across ranks (rank order = global token order), one serial pass, parallel write-back."""
+
+    def __init__(self, corpus, K_max, cap=None):
+        lib, dev = _lib.lib(), "cuda"
+        self.corpus, self.K_max = corpus, int(K_max)
+        self.cap = int(cap if cap is not None else max(1024, corpus.n_pos))
+        i32 = torch.int32
+        self.work = torch.empty(lib.segb_frozen_new_work_bytes(corpus.n_pos), dtype=torch.uint8, device=dev)
+        self.list_j = torch.zeros(self.cap, dtype=i32, device=dev)
+        self.list_id = torch.zeros(self.cap, dtype=i32, device=dev)
+        self.n_list = torch.zeros(1, dtype=i32, device=dev)
+        self.out_k = torch.zeros(self.cap, dtype=i32, device=dev)
+        self.K_out = torch.zeros(1, dtype=i32, device=dev)
+        self.overflow = torch.zeros(1, dtype=i32, device=dev)
+
+    def run(self, choice, K_before):
+        """Rewrites choice[id] of this rank's tokens in place; the new K is left in self.K_out (device)."""
+        lib, cp, sp = _lib.lib(), self.corpus, _lib.stream_ptr()
+        _lib.check(lib.segb_frozen_new_list(cp.struct(), 0, cp.n_pos, _lib.ptr(choice), int(K_before),
+                                            _lib.ptr(self.work), self.cap, _lib.ptr(self.list_j),
+                                            _lib.ptr(self.list_id), _lib.ptr(self.n_list), sp))
         if _dist_on():
-            # ranks hold consecutive utterance ranges: rank order IS the global token order
-            parts = [None] * dist.get_world_size()
-            dist.all_gather_object(parts, ks.tolist())
-            all_ks, K = clamp_plan([k for part in parts for k in part], K_before)
-            lo = sum(len(part) for part in parts[:dist.get_rank()])
-            ks_new = np.asarray(all_ks[lo:lo + len(ks)], dtype=np.int64)
+            world, rank = dist.get_world_size(), dist.get_rank()
+            if getattr(self, "_cap_all", None) is None:
+                caps = torch.tensor([self.cap], dtype=torch.int64, device="cuda")
+                dist.all_reduce(caps, op=dist.ReduceOp.MAX)              # ranks may own different numbers of positions
+                self._cap_all = int(caps.item())                         # once: the corpus split is fixed
+            cap_all = self._cap_all
+            mine = torch.zeros(cap_all, dtype=torch.int32, device="cuda")
+            mine[:self.cap] = self.list_j
+            lists = torch.empty(world * cap_all, dtype=torch.int32, device="cuda")
+            counts = torch.empty(world, dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(lists, mine)
+            dist.all_gather_into_tensor(counts, self.n_list)
         else:
-            ks_new, K = clamp_plan(ks, K_before)
-        c._K.fill_(int(K))
-        self.K_host = int(K)
-        if len(ks):
-            ks_new_d = _lib.dev(np.asarray(ks_new, dtype=np.int64))
-            rows = c._X[ids_d].to(torch.float64)
-            self.sum_x.index_add_(0, ks_old_d, -rows)
-            self.sum_x.index_add_(0, ks_new_d, rows)
-            ones = torch.ones_like(ks_old_d)
-            self.cnt.index_add_(0, ks_old_d, -ones)
-            self.cnt.index_add_(0, ks_new_d, ones)
-            c._assign[ids_d] = ks_new_d.to(torch.int32)
-            self.best_k[ids_d] = ks_new_d.to(torch.int32)
+            world, rank, cap_all, lists, counts = 1, 0, self.cap, self.list_j, self.n_list
+        _lib.check(lib.segb_frozen_clamp(_lib.ptr(lists), _lib.ptr(counts), world, cap_all, rank, int(K_before),
+                                         self.K_max, _lib.ptr(self.list_id), _lib.ptr(self.out_k), _lib.ptr(choice),
+                                         _lib.ptr(self.K_out), _lib.ptr(self.overflow), sp))

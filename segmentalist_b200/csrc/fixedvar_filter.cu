@@ -1,0 +1,609 @@
+// Tensor-core log_marg_i for the fixed-variance FBGMM, filter-and-refine form (frozen model, all
+// embeddings at once).
+//
+// Replaces, for a batch of embeddings against a frozen model,
+//   GaussianComponentsFixedVar.log_post_pred / log_prior   gaussian_components_fixedvar.py:224-253
+//   FBGMM.log_marg_i                                        fbgmm.py:256-285
+//   the scoring half of map_assign_i / gibbs_sample_inside_loop_i   fbgmm.py:422-494
+// i.e. log_marg(x) = logsumexp_k s_k(x),
+//   s_k(x) = lms*(log(alpha/K_max + n_k) - log(sum n + alpha)) + (k < K ? log_post_pred_k(x) : log_prior(x))
+// over the K_max slots (the K_max - K empty slots are one virtual component with log(K_max - K)
+// folded into its constant).
+//
+// s_k(x) = A_k + F(x).W_k is a GEMM: isotropic variances F = x, W_k = p_k mu_k with -p_k/2 |x|^2 and
+// A_k riding in split constant columns; anisotropic variances F = [x, x*x], W_k = [P_k*mu_k, -P_k/2]
+// (inner dimension 2D).  The three-pass FP32-accurate split of fixedvar_mma.cu executes
+// 3.3x the algorithmic flops.  Here ONE fp16 pass (the filter GEMM of kmeans_mma.cu with a different
+// threshold) finds, per embedding, the components that can matter: with |s^ - s| <= bound, every
+// component within T = 25 nats of the best exact score has s^ within T + 2*bound of the best s^.
+// Only those (normally one) are re-scored exactly -- float64, delta form sum_d P_kd (mu_kd - x_d)^2
+// like the reference -- and the logsumexp is taken over the exact scores; everything dropped carries
+// at most K_max * exp(-25) = 7e-8 of the sum.  Rows whose third-best 16-component chunk is still
+// inside the threshold (flat posteriors) get an exhaustive exact scan.  Result: log_marg_i to ~1e-7
+// absolute (north star: 1e-4 relative) at one tensor pass instead of three, plus the exact MAP
+// component of every embedding for free.
+#include "mma_common.cuh"
+
+namespace segb {
+namespace fvf {
+
+using namespace segb::mma;
+
+constexpr float DEAD_A = -30000.0f;      // constant of padded model rows: never inside any threshold
+constexpr int REFINE_THREADS = 256;
+
+__host__ __device__ inline int kp_of(int D, int aniso) { return ((aniso ? D + 3 : D + 6) + 15) / 16 * 16; }
+__host__ __device__ inline int nch_of(int aniso) { return aniso ? 2 : 1; }
+static inline int64_t rows_pad(int64_t n) { return (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS; }
+static inline int w_rows_pad(int K_max) { return (K_max + 1 + NT_COLS - 1) / NT_COLS * NT_COLS; }   // +1: the virtual empty slot
+
+// Exact per-component tables read by the refine (row-major so one component is one contiguous row):
+//   mu [Kr][D] | P [Kr][D] (anisotropic only) | cst_lse [Kr] | cst_map [Kr] | pk [Kr]     Kr = K_max + 1
+// cst_lse = lms*pi_k - D/2 log 2pi + 1/2 sum_d log P_kd (+ log(K_max - K) on the virtual row);
+// cst_map = log(alpha/K_max + n_k) - D/2 log 2pi + 1/2 sum_d log P_kd   (map_assign_i: no lms, fbgmm.py:475-479).
+struct ModelRows {
+    const double *mu, *P, *cst_lse, *cst_map, *pk;
+};
+__host__ __device__ inline int64_t model_doubles(int K_max, int D, int aniso) {
+    const int64_t Kr = K_max + 1;
+    return Kr * D * (aniso ? 2 : 1) + 3 * Kr;
+}
+__host__ __device__ inline ModelRows model_view(const double *base, int K_max, int D, int aniso) {
+    const int64_t Kr = K_max + 1;
+    ModelRows r;
+    r.mu = base;
+    r.P = aniso ? base + Kr * D : nullptr;
+    const double *q = base + Kr * D * (aniso ? 2 : 1);
+    r.cst_lse = q; r.cst_map = q + Kr; r.pk = q + 2 * Kr;
+    return r;
+}
+
+__device__ __forceinline__ void split2(float v, __half &hi, __half &lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// ---------------------------------------------------------------- operand packing
+
+// X image, one warp per row.
+//   isotropic   one chunk  [x^ (D), 1, 1, 1, n2h, n2h, n2l, 0..]                 n2 = |x|^2 (hi/lo split)
+//   anisotropic two chunks [x^ (D), 0..] [fp16(x*x) (D), 1, 1, 1, 0..]
+// err[2r] = |F - F^|_2, err[2r+1] = |F|_2 over the feature columns (x, and x*x when anisotropic).
+__global__ void pack_x_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad, int D, int aniso, uint8_t *tiles,
+                              float *err, float *x_max) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows_pad) return;
+    const int KP = kp_of(D, aniso), NCH = nch_of(aniso);
+    const int64_t tb = (int64_t)TILE_ROWS * KP * 2;
+    uint8_t *base = tiles + (row / TILE_ROWS) * NCH * tb;
+    const int r = (int)(row % TILE_ROWS);
+    const bool live = row < n_emb;
+    const float *xr = X + row * D;
+    __half n2h = __float2half_rn(0.f), n2l = n2h;
+    float e2 = 0.f, f2 = 0.f;
+    bool overflow = false;
+    if (!aniso) {
+        double n2 = 0.0;
+        if (live) for (int d = lane; d < D; d += 32) { const double v = xr[d]; n2 += v * v; }
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+        if (!(n2 < 60000.0)) overflow = true;
+        split2((float)n2, n2h, n2l);
+    }
+    for (int ch = lane; ch < NCH * (KP / 8); ch += 32) {
+        const int chunk = ch / (KP / 8), c0 = (ch % (KP / 8)) * 8;
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            __half out = __float2half_rn(0.f);
+            if (live) {
+                if (c < D) {
+                    const float x = xr[c];
+                    const float v = chunk == 0 ? x : __fmul_rn(x, x);
+                    if (fabsf(v) > 60000.f) overflow = true;
+                    out = __float2half_rn(v);
+                    const float dl = v - __half2float(out);
+                    e2 += dl * dl; f2 += v * v;
+                } else if (chunk == NCH - 1) {
+                    const int ecol = c - D;
+                    if (ecol < 3) out = __float2half_rn(1.f);
+                    else if (!aniso && (ecol == 3 || ecol == 4)) out = n2h;
+                    else if (!aniso && ecol == 5) out = n2l;
+                }
+            }
+            hv[j] = out;
+        }
+        *reinterpret_cast<uint4 *>(base + chunk * tb + tile_off(r, c0)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); f2 += __shfl_xor_sync(FULL, f2, o); }
+    overflow = __any_sync(FULL, overflow);
+    if (lane == 0 && live) {
+        const float eF = overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f, nF = sqrtf(f2) * 1.0001f;
+        err[2 * row] = eF;
+        err[2 * row + 1] = nF;
+        atomicMax(reinterpret_cast<int *>(x_max), __float_as_int(eF));         // non-negative floats order like their bits
+        atomicMax(reinterpret_cast<int *>(x_max) + 1, __float_as_int(nF));
+    }
+}
+
+// Model image + exact row tables, one warp per (virtual) component.  Row K (if K < K_max) stands for all
+// empty slots; rows beyond are dead.
+//   isotropic   one chunk  [B^ = fp16(p mu) (D), a0, a1, a2, ph, pl, ph, 0..]     (ph, pl) = split(-p/2)
+//   anisotropic two chunks [fp16(P*mu) (D), 0..] [fp16(-P/2) (D), a0, a1, a2, 0..]
+// w_err[4r..]: (|W - W^|_2, |W^|_2, |A|, p/2 or 0).
+__global__ void pack_w_kernel(segb_fixedvar m, int aniso, int rows_pad_, uint8_t *tiles, double *rows, float *w_err) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows_pad_) return;
+    const int D = m.D, KM = m.K_max, KP = kp_of(D, aniso), NCH = nch_of(aniso);
+    const int K = *m.K;
+    const int64_t tb = (int64_t)TILE_ROWS * KP * 2;
+    uint8_t *base = tiles + (int64_t)(row / NT_COLS) * NCH * tb;
+    const int r = row % NT_COLS;
+    const bool active = row < K, virt = (row == K && K < KM), alive = active || virt;
+    const int64_t Kr = KM + 1;
+    double *t_mu = rows, *t_P = aniso ? rows + Kr * D : nullptr;
+    double *t_lse = rows + Kr * D * (aniso ? 2 : 1), *t_map = t_lse + Kr, *t_pk = t_lse + 2 * Kr;
+    const double c0 = -0.5 * D * log(2. * 3.14159265358979323846);
+    double Ak = DEAD_A, p_iso = 0.0;
+    if (alive) {
+        double pm2 = 0.0;                                   // sum_d P_d mu_d^2
+        for (int d = lane; d < D; d += 32) {
+            const double mu = active ? m.mu_NT[(size_t)d * KM + row] : m.mu_0[d];
+            const double P = active ? m.prec_predT[(size_t)d * KM + row] : m.precision_0[d];
+            pm2 += P * mu * mu;
+            t_mu[(size_t)row * D + d] = mu;
+            if (aniso) t_P[(size_t)row * D + d] = P;
+        }
+        for (int o = 16; o > 0; o >>= 1) pm2 += __shfl_xor_sync(FULL, pm2, o);
+        p_iso = active ? m.prec_predT[row] : m.precision_0[0];
+        const double log_norm = log((double)(*m.n_total) + m.alpha);
+        const double cnt = active ? (double)m.counts[row] : 0.0;
+        const double lp = log(m.alpha / KM + cnt);
+        const double lpp = active ? m.log_prod_prec_pred[row] : m.sum_log_precision_0;
+        const double lse_c = m.lms * (lp - log_norm) + c0 + 0.5 * lpp + (virt ? log((double)(KM - K)) : 0.0);
+        Ak = lse_c - 0.5 * pm2;
+        if (lane == 0) { t_lse[row] = lse_c; t_map[row] = lp + c0 + 0.5 * lpp; t_pk[row] = p_iso; }
+    } else if (row < Kr) {
+        for (int d = lane; d < D; d += 32) { t_mu[(size_t)row * D + d] = 0.0; if (aniso) t_P[(size_t)row * D + d] = 0.0; }
+        if (lane == 0) { t_lse[row] = -CUDART_INF; t_map[row] = -CUDART_INF; t_pk[row] = 0.0; }
+    }
+    bool overflow = alive && !(fabs(Ak) < 60000.0);
+    const float Af = (float)Ak;
+    const __half a0 = __float2half_rn(Af);
+    const float r1 = Af - __half2float(a0);
+    const __half a1 = __float2half_rn(r1);
+    const __half a2 = __float2half_rn(r1 - __half2float(a1));
+    __half ph, pl;
+    split2((float)(-0.5 * p_iso), ph, pl);
+    float e2 = 0.f, n2 = 0.f;
+    for (int ch = lane; ch < NCH * (KP / 8); ch += 32) {
+        const int chunk = ch / (KP / 8), cc = (ch % (KP / 8)) * 8;
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cc + j;
+            __half out = __float2half_rn(0.f);
+            if (c < D) {
+                if (alive) {
+                    const double mu = active ? m.mu_NT[(size_t)c * KM + row] : m.mu_0[c];
+                    const double P = aniso ? (active ? m.prec_predT[(size_t)c * KM + row] : m.precision_0[c]) : p_iso;
+                    const float w = chunk == 0 ? (float)(P * mu) : (float)(-0.5 * P);
+                    if (!(fabsf(w) < 60000.f)) overflow = true;
+                    out = __float2half_rn(w);
+                    const float dl = (float)((chunk == 0 ? P * mu : -0.5 * P) - (double)__half2float(out));
+                    e2 += dl * dl;
+                    n2 += __half2float(out) * __half2float(out);
+                }
+            } else if (chunk == NCH - 1) {
+                const int ecol = c - D;
+                if (ecol == 0) out = a0;
+                else if (ecol == 1) out = a1;
+                else if (ecol == 2) out = a2;
+                else if (!aniso && alive && (ecol == 3 || ecol == 5)) out = ph;
+                else if (!aniso && alive && ecol == 4) out = pl;
+            }
+            hv[j] = out;
+        }
+        *reinterpret_cast<uint4 *>(base + chunk * tb + tile_off(r, cc)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
+    overflow = __any_sync(FULL, overflow);
+    if (lane == 0) {
+        w_err[4 * row] = alive ? (overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f) : 0.f;
+        w_err[4 * row + 1] = alive ? sqrtf(n2) * 1.0001f : 0.f;
+        w_err[4 * row + 2] = alive ? (float)fabs(Ak) * 1.0001f : 0.f;
+        w_err[4 * row + 3] = (alive && !aniso) ? (float)(0.5 * p_iso) * 1.0001f : 0.f;
+    }
+}
+
+// model-wide maxima of the four per-row quantities -> w_max[0..3]
+__global__ void wmax4_kernel(const float *w_err, int n_rows, float *w_max) {
+    __shared__ float red[4][32];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = threadIdx.x; k < n_rows; k += blockDim.x)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], w_err[4 * k + q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        for (int o = 16; o > 0; o >>= 1) v[q] = fmaxf(v[q], __shfl_xor_sync(FULL, v[q], o));
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[q][threadIdx.x >> 5] = v[q];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float x = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) x = fmaxf(x, red[threadIdx.x][i]);
+        w_max[threadIdx.x] = x;
+    }
+}
+
+// ---------------------------------------------------------------- exact refine
+
+// Exact float64 quadratic form of component row k for the embedding whose elements d = j, j+8, ... this
+// lane holds: sum_d P_kd (mu_kd - x_d)^2 over the lane's elements (isotropic: the factor p_k is applied
+// by the caller).  Eight lanes per embedding; the caller reduces over them.
+template <bool ANISO>
+__device__ __forceinline__ double quad_part(const ModelRows &t, int k, const float *xr, int D, int j) {
+    const double *mu = t.mu + (size_t)k * D;
+    double acc = 0.0;
+    if (ANISO) {
+        const double *P = t.P + (size_t)k * D;
+#pragma unroll 4
+        for (int d = j; d < D; d += 8) { const double dl = mu[d] - (double)xr[d]; acc = fma(dl * dl, P[d], acc); }
+    } else {
+#pragma unroll 4
+        for (int d = j; d < D; d += 8) { const double dl = mu[d] - (double)xr[d]; acc = fma(dl, dl, acc); }
+    }
+    return acc;
+}
+
+// Running logsumexp + MAP argmax over the exact scores fed one at a time.
+struct LseAcc {
+    double m, s, best;
+    int bk;
+    __device__ __forceinline__ void init() { m = -CUDART_INF; s = 0.0; best = -CUDART_INF; bk = 0x7fffffff; }
+    __device__ __forceinline__ void add(double v, double vmap, int k) {
+        if (v > m) { s = s * exp(m - v) + 1.0; m = v; }            // m = -inf first time: exp(-inf) = 0
+        else s += exp(v - m);
+        if (vmap > best || (vmap == best && k < bk)) { best = vmap; bk = k; }
+    }
+    __device__ __forceinline__ double lse() const { return m + log(s); }
+};
+
+// Eight lanes per embedding (four per warp): the filter record names the candidate chunks and members;
+// each is re-scored exactly and fed to the running logsumexp.  Rows the filter could not decide go to
+// fb_list for the exhaustive scan.
+template <bool ANISO>
+__global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
+    const float *X, int D, int K_max, const double *model_rows, const Cand *cand, const float *x_err,
+    const float *w_max, int KP, float T, int64_t n_emb, int n_chunks, double *log_marg, int32_t *map_k,
+    unsigned long long *n_fallback, int32_t *fb_list) {
+    const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
+    const int lane = threadIdx.x & 31, j = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int Kr = K_max + 1;
+    const W4 w4{w_max[0], w_max[1], w_max[2], w_max[3]};
+    const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    for (int64_t row = grp_global; row < n_emb; row += grp_total) {
+        const Cand cd = cand[row];
+        const float2 xe = *reinterpret_cast<const float2 *>(x_err + 2 * row);
+        const float tau = lse_tau(xe.x, xe.y, w4, KP, T);
+        const int code = refine_decide(cd, tau, n_chunks);
+        if (code == -2) {
+            if (j == 0) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;
+            continue;
+        }
+        const float *xr = X + row * D;
+        LseAcc acc;
+        acc.init();
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            // best chunk: the members within the launch-wide threshold of the chunk maximum (a superset of
+            // the members within this row's tau); second chunk: everything
+            uint32_t mk = pass == 0 ? (cd.masks & 0xffffu) : (code >= 0 ? (cd.masks >> 16) : 0u);
+            const int chunk = pass == 0 ? cd.i1 : cd.i2;
+            while (mk) {
+                const int bit = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const int k = chunk * CHUNK + bit;
+                if (k >= Kr) continue;
+                double q = quad_part<ANISO>(t, k, xr, D, j);
+                q += __shfl_xor_sync(gmask, q, 1);
+                q += __shfl_xor_sync(gmask, q, 2);
+                q += __shfl_xor_sync(gmask, q, 4);
+                const double pred = -0.5 * (ANISO ? q : t.pk[k] * q);
+                const double c_lse = t.cst_lse[k];
+                if (c_lse == -CUDART_INF) continue;                 // dead row
+                acc.add(c_lse + pred, t.cst_map[k] + pred, k);
+            }
+        }
+        if (j == 0) {
+            log_marg[row] = acc.lse();
+            if (map_k) map_k[row] = (acc.bk == 0x7fffffff) ? -1 : acc.bk;
+        }
+    }
+}
+
+// Exhaustive exact scan for the rows the filter could not decide: one block per row, threads over the
+// model rows (the virtual empty row included), block-wide logsumexp and argmax.
+template <bool ANISO>
+__global__ void __launch_bounds__(256) fv_full_kernel(const float *X, int D, int K_max, const double *model_rows,
+                                                      const int32_t *fb_list, const unsigned long long *n_fallback,
+                                                      double *log_marg, int32_t *map_k) {
+    extern __shared__ double fsm[];
+    double *xs = fsm;                      // [D]
+    double *red = fsm + D;                 // [40]
+    const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
+    const int Kr = K_max + 1;
+    const long long n = (long long)*n_fallback;
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        const int64_t row = fb_list[i];
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = (double)X[row * D + d];
+        __syncthreads();
+        // pass 1: exact scores of this thread's rows -> running (max, sum) and MAP candidate
+        LseAcc acc;
+        acc.init();
+        for (int k = threadIdx.x; k < Kr; k += blockDim.x) {
+            const double c_lse = t.cst_lse[k];
+            if (c_lse == -CUDART_INF) continue;
+            const double *mu = t.mu + (size_t)k * D;
+            double q = 0.0;
+            if (ANISO) {
+                const double *P = t.P + (size_t)k * D;
+                for (int d = 0; d < D; ++d) { const double dl = mu[d] - xs[d]; q = fma(dl * dl, P[d], q); }
+            } else {
+                for (int d = 0; d < D; ++d) { const double dl = mu[d] - xs[d]; q = fma(dl, dl, q); }
+                q *= t.pk[k];
+            }
+            acc.add(c_lse - 0.5 * q, t.cst_map[k] - 0.5 * q, k);
+        }
+        const double gm = block_max(acc.m, red);
+        const double part = (acc.m == -CUDART_INF) ? 0.0 : acc.s * exp(acc.m - gm);
+        const double gs = block_sum(part, red);
+        const double gbest = block_max(acc.best, red);
+        const double cand_k = (acc.best == gbest) ? (double)acc.bk : 4.0e9;
+        const double gk = -block_max(-cand_k, red);
+        if (threadIdx.x == 0) {
+            log_marg[row] = gm + log(gs);
+            if (map_k) map_k[row] = (int32_t)gk;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- frozen sweep pieces
+
+// get_vec_embed_log_probs (unigram_acoustic_wordseg.py:474-511) from per-embedding log marginals:
+// scores[slot] = log_marg[seg_id[slot]] * seg_dur[slot]**tpt + wip, -inf where the slot has no
+// embedding or an unusable duration.
+__global__ void fv_band_scores_kernel(segb_corpus c, int64_t slot_first, int64_t n_slots, const double *log_marg,
+                                      double tpt, double wip, double *scores) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const int64_t slot = slot_first + i;
+    const int id = c.seg_id[slot];
+    const double du = c.seg_dur[slot];
+    double v = -CUDART_INF;
+    if (id >= 0 && du == du) v = log_marg[id] * ((tpt == 1.0) ? du : pow(du, tpt)) + wip;
+    scores[slot] = v;
+}
+
+// Frozen-model component choice for the tokens of the current boundaries (one 8-lane group per landmark
+// position that ends a token).  mode 1 (map_assign_i, fbgmm.py:465-494): choice[id] = map_k[id] (already
+// exact from the refine).  mode 0 (gibbs_sample_inside_loop_i, :422-463, anneal_temp = 1): inverse-CDF
+// draw with the position's uniform over the exact probabilities of the components the filter kept, in
+// slot order, the empty slots last (one draw lands in empty slot K + floor(u_rest / p_empty)).  The
+// components the filter dropped hold < K_max * exp(-T) of the mass: the draw differs from the
+// reference's only if the uniform falls that close to a CDF step.  Rows without a usable filter record
+// (flat posteriors) walk all model rows.  The choice is the raw slot index j (>= K: an empty slot);
+// the `k > K -> K` clamp of add_item is applied afterwards in token order (segb_clamp_new_components).
+template <bool ANISO>
+__global__ void __launch_bounds__(REFINE_THREADS) fv_choose_kernel(
+    const float *X, int D, int K_max, int K, const double *model_rows, const Cand *cand, const float *x_err,
+    const float *w_max, int KP, float T, int n_chunks, segb_corpus c, int64_t pos_first, int64_t n_positions,
+    int mode, const int32_t *map_k, const double *uniforms, int32_t *choice) {
+    const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
+    const int lane = threadIdx.x & 31, j = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int Kr = K_max + 1;
+    const W4 w4{w_max[0], w_max[1], w_max[2], w_max[3]};
+    const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    for (int64_t pi = grp_global; pi < n_positions; pi += grp_total) {
+        const int64_t pos = pos_first + pi;
+        const int id = c.tok_id[pos];
+        if (id < 0) continue;
+        if (mode == 1) { if (j == 0) choice[id] = map_k[id]; continue; }
+        const double u = uniforms[pos];
+        const Cand cd = cand[id];
+        const float2 xe = *reinterpret_cast<const float2 *>(x_err + 2 * (int64_t)id);
+        const float tau = lse_tau(xe.x, xe.y, w4, KP, T);
+        const int code = refine_decide(cd, tau, n_chunks);
+        const float *xr = X + (int64_t)id * D;
+        auto score = [&](int k) -> double {                       // s_k without the constants common to all slots
+            double q = quad_part<ANISO>(t, k, xr, D, j);
+            q += __shfl_xor_sync(gmask, q, 1);
+            q += __shfl_xor_sync(gmask, q, 2);
+            q += __shfl_xor_sync(gmask, q, 4);
+            return t.cst_lse[k] - 0.5 * (ANISO ? q : t.pk[k] * q);
+        };
+        // two passes over the same candidate walk, in slot order: the logsumexp, then the subtraction
+        int ca = -1, cb = -1;                                      // chunks in ascending order
+        uint32_t ma = 0, mb = 0;
+        if (code != -2) {
+            ca = cd.i1; ma = cd.masks & 0xffffu;
+            if (code >= 0) { cb = cd.i2; mb = cd.masks >> 16; }
+            if (cb >= 0 && cb < ca) { const int tc = ca; ca = cb; cb = tc; const uint32_t tm = ma; ma = mb; mb = tm; }
+        }
+        double lse = 0.0, urest = u;
+        int pick = -1;
+#pragma unroll 1
+        for (int phase = 0; phase < 2 && pick < 0; ++phase) {
+            LseAcc acc;
+            acc.init();
+            auto visit = [&](int k) {
+                if (k >= Kr || t.cst_lse[k] == -CUDART_INF) return;
+                const double s = score(k);
+                if (phase == 0) { acc.add(s, s, k); return; }
+                if (pick >= 0) return;
+                const double pk_ = exp(s - lse);
+                if (k < K) {                                       // an active slot
+                    urest = urest - pk_;
+                    if (urest < 0) pick = k;
+                } else {                                           // the K_max - K identical empty slots
+                    const int n_empty = K_max - K;
+                    const double pe = pk_ / n_empty;
+                    int i = (int)floor(urest / pe);
+                    // the reference subtracts slot by slot: settle the rounding of the quotient
+                    while (i > 0 && urest - i * pe < 0) --i;
+                    while (i < n_empty && urest - (i + 1) * pe >= 0) ++i;
+                    if (i < n_empty) pick = K + i;
+                    urest = urest - n_empty * pe;
+                }
+            };
+            if (code != -2) {
+                for (uint32_t mk = ma; mk;) { const int bit = __ffs(mk) - 1; mk &= mk - 1; visit(ca * CHUNK + bit); }
+                if (cb >= 0) for (uint32_t mk = mb; mk;) { const int bit = __ffs(mk) - 1; mk &= mk - 1; visit(cb * CHUNK + bit); }
+            } else {
+                for (int k = 0; k < Kr; ++k) visit(k);
+            }
+            if (phase == 0) lse = acc.lse();
+        }
+        if (pick < 0) pick = K_max - 1;                            // utils.draw falls through to the last slot
+        if (j == 0) choice[id] = pick;
+    }
+}
+
+}  // namespace fvf
+}  // namespace segb
+
+using namespace segb;
+using namespace segb::fvf;
+
+extern "C" int64_t segb_fvf_x_tiles_bytes(int64_t n_emb, int32_t D, int32_t aniso) {
+    return rows_pad(n_emb) * nch_of(aniso) * kp_of(D, aniso) * 2;
+}
+extern "C" int64_t segb_fvf_w_tiles_bytes(int32_t K_max, int32_t D, int32_t aniso) {
+    return (int64_t)w_rows_pad(K_max) * nch_of(aniso) * kp_of(D, aniso) * 2;
+}
+extern "C" int64_t segb_fvf_model_bytes(int32_t K_max, int32_t D, int32_t aniso) {
+    return (model_doubles(K_max, D, aniso) + 2) * 8 + (int64_t)w_rows_pad(K_max) * 4 * sizeof(float);
+}
+extern "C" int64_t segb_fvf_work_bytes(int64_t n_emb) { return (n_emb + 64) * (int64_t)sizeof(int32_t); }
+
+extern "C" int segb_fvf_pack_x(const float *X, int64_t n_emb, int32_t D, int32_t aniso, void *x_tiles, float *x_err,
+                               float *x_max, void *stream) {
+    SEGB_CHECK_ARG(X && x_tiles && x_err && x_max && n_emb > 0 && D > 0, "null pointer");
+    const int64_t np_ = rows_pad(n_emb);
+    const int wpb = 8;
+    SEGB_CUDA(cudaMemsetAsync(x_max, 0, 2 * sizeof(float), (cudaStream_t)stream));
+    fvf::pack_x_kernel<<<(unsigned)((np_ + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        X, n_emb, np_, D, aniso ? 1 : 0, (uint8_t *)x_tiles, x_err, x_max);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+// model: segb_fvf_model_bytes() bytes = exact row tables, then the per-row error table
+static inline float *model_w_err(void *model, int K_max, int D, int aniso) {
+    return reinterpret_cast<float *>(reinterpret_cast<double *>(model) + model_doubles(K_max, D, aniso) + 2);
+}
+
+extern "C" int segb_fvf_pack_model(const segb_fixedvar *m, int32_t aniso, void *w_tiles, void *model, float *w_max,
+                                   void *stream) {
+    SEGB_CHECK_ARG(m && w_tiles && model && w_max, "null pointer");
+    SEGB_CHECK_ARG(m->model == SEGB_MODEL_FIXEDVAR, "the tensor-core log_marg is a GEMM: fixed-variance model only");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int krp = w_rows_pad(m->K_max), wpb = 8;
+    float *w_err = model_w_err(model, m->K_max, m->D, aniso ? 1 : 0);
+    fvf::pack_w_kernel<<<(krp + wpb - 1) / wpb, wpb * 32, 0, st>>>(*m, aniso ? 1 : 0, krp, (uint8_t *)w_tiles,
+                                                                    (double *)model, w_err);
+    SEGB_LAUNCH_CHECK();
+    wmax4_kernel<<<1, 256, 0, st>>>(w_err, krp, w_max);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_fvf_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
+                               int32_t aniso, const float *x_max, const float *w_max, float T, void *cand, void *stream) {
+    SEGB_CHECK_ARG(x_tiles && w_tiles && cand && x_max && w_max && n_emb > 0 && K_max > 0, "null pointer");
+    SEGB_CHECK_ARG(T > 0.f, "threshold");
+    FilterLaunch f;
+    f.x_tiles = x_tiles; f.w_tiles = w_tiles; f.cand = cand; f.n_emb = n_emb;
+    f.w_rows_pad = w_rows_pad(K_max); f.KP = kp_of(D, aniso ? 1 : 0); f.n_chunks = nch_of(aniso ? 1 : 0); f.D = D;
+    f.x_max = x_max; f.w_max = w_max; f.tau_kind = TAU_LSE; f.tau_T = T;
+    return launch_filter(f, (cudaStream_t)stream);
+}
+
+extern "C" int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, int32_t aniso,
+                               const void *model, const void *cand, const float *x_err, const float *w_max, float T,
+                               void *work, double *log_marg, int32_t *map_k, int64_t *n_fallback, void *stream) {
+    SEGB_CHECK_ARG(X && model && cand && x_err && w_max && work && log_marg && n_fallback, "null pointer");
+    SEGB_CHECK_ARG(n_emb > 0 && n_emb < (1ll << 31), "row count");
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *fb_list = (int32_t *)work;
+    SEGB_CUDA(cudaMemsetAsync(n_fallback, 0, sizeof(int64_t), st));
+    int64_t blocks = (n_emb * 8 + REFINE_THREADS - 1) / REFINE_THREADS;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const int KP = kp_of(D, aniso ? 1 : 0) * nch_of(aniso ? 1 : 0), n_chunks = w_rows_pad(K_max) / CHUNK;
+    if (aniso)
+        fv_refine_kernel<true><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
+            map_k, (unsigned long long *)n_fallback, fb_list);
+    else
+        fv_refine_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
+            map_k, (unsigned long long *)n_fallback, fb_list);
+    SEGB_LAUNCH_CHECK();
+    const size_t fsm = sizeof(double) * (D + 40);
+    if (aniso)
+        fv_full_kernel<true><<<148 * 8, 256, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
+                                                         (const unsigned long long *)n_fallback, log_marg, map_k);
+    else
+        fv_full_kernel<false><<<148 * 8, 256, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
+                                                          (const unsigned long long *)n_fallback, log_marg, map_k);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_fixedvar_band_scores(const segb_corpus *c, int64_t pos_first, int64_t n_positions,
+                                         const double *log_marg, double time_power_term, double wip, double *scores,
+                                         void *stream) {
+    SEGB_CHECK_ARG(c && log_marg && scores, "null pointer");
+    SEGB_CHECK_ARG(pos_first >= 0 && n_positions >= 0 && pos_first + n_positions <= c->n_pos, "position range");
+    if (n_positions == 0) return 0;
+    const int64_t n_slots = n_positions * c->S;
+    fv_band_scores_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        *c, pos_first * c->S, n_slots, log_marg, time_power_term, wip, scores);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_fvf_choose_tokens(const float *X, int32_t D, int32_t K_max, int32_t K, int32_t aniso,
+                                      const void *model, const void *cand, const float *x_err, const float *w_max,
+                                      float T, const segb_corpus *c, int64_t pos_first, int64_t n_positions,
+                                      int32_t mode, const int32_t *map_k, const double *uniforms, int32_t *choice,
+                                      void *stream) {
+    SEGB_CHECK_ARG(X && model && cand && x_err && w_max && c && choice, "null pointer");
+    SEGB_CHECK_ARG(mode == 0 || mode == 1, "mode");
+    SEGB_CHECK_ARG(mode == 1 ? (map_k != nullptr) : (uniforms != nullptr), "mode 1 needs map_k, mode 0 uniforms");
+    SEGB_CHECK_ARG(pos_first >= 0 && n_positions >= 0 && pos_first + n_positions <= c->n_pos, "position range");
+    SEGB_CHECK_ARG(K >= 0 && K <= K_max, "K");
+    if (n_positions == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (n_positions * 8 + REFINE_THREADS - 1) / REFINE_THREADS;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const int KP = kp_of(D, aniso ? 1 : 0) * nch_of(aniso ? 1 : 0), n_chunks = w_rows_pad(K_max) / CHUNK;
+    if (aniso)
+        fv_choose_kernel<true><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            X, D, K_max, K, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_chunks, *c, pos_first,
+            n_positions, mode, map_k, uniforms, choice);
+    else
+        fv_choose_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            X, D, K_max, K, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_chunks, *c, pos_first,
+            n_positions, mode, map_k, uniforms, choice);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}

@@ -36,8 +36,7 @@ namespace fvmma {
 using namespace segb::mma;
 
 constexpr int T_ROWS = 128;        // rows per tile image (X tiles and model chunks)
-constexpr int MT_ROWS = 256;       // embeddings per CTA work item
-constexpr int NT_COLS = 128;       // components per accumulator tile = MMA N
+// MT_ROWS = 256 embeddings per CTA work item, NT_COLS = 128 components per accumulator tile: mma_common.cuh
 constexpr int N_STAGES = 2;
 constexpr int N_THREADS = 384;
 constexpr uint32_t TMEM_COLS = 512;   // 2 halves x 2 buffers x 128 columns

@@ -41,10 +41,6 @@
 namespace segb {
 namespace mma {
 
-constexpr int TILE_ROWS = 128;     // rows per operand tile image
-constexpr int MT_ROWS = 256;       // embeddings per CTA work item (two A tiles)
-constexpr int NT_COLS = 128;       // components per accumulator tile
-constexpr int CHUNK = 16;          // components per candidate chunk
 constexpr uint32_t KSTEP_BYTES = 2 * (TILE_ROWS / 8) * 128;        // one K=16 step of a 128-row tile image
 constexpr int EPI_PARTS = 2;         // column halves of an accumulator tile handled by separate warp sets
 constexpr int N_EPI_WARPS = 8 * EPI_PARTS;
@@ -52,32 +48,8 @@ constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float PAD_BIAS = -30000.0f;   // -|mu|^2/2 stand-in for padded components: never wins
 
-struct __align__(32) Cand {        // per-embedding filter record
-    float m1, m2, m3;              // best / second / third chunk maximum of t^
-    int32_t i1, i2;                // chunk ids of m1, m2
-    uint32_t masks;                // bits 0-15: members of chunk i1 within tau of its max; 16-31: chunk i2
-    int32_t pad[2];
-};
-
 __host__ __device__ inline int kp_of(int D) { return (D + 3 + 15) / 16 * 16; }
 __host__ __device__ inline int64_t tile_bytes_of(int D) { return (int64_t)TILE_ROWS * kp_of(D) * 2; }
-// byte offset of element (r, c) inside a 128-row tile image
-__host__ __device__ inline int tile_off(int r, int c) {
-    return ((c >> 3) * (TILE_ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (c & 7) * 2;
-}
-
-// Rigorous bound on |t^ - t| for t = x.mu - |mu|^2/2 as computed by the fp16 filter GEMM:
-//   ex*|mu^| + |x|*e_mu                      fp16 rounding of the two operands (Cauchy-Schwarz)
-//   c_acc*((|x|+ex)*|mu^| + |mu|^2/2)        fp32 accumulation in the tensor core, bias split
-//   eta = (D+3)*2^-24*(|x|+|mu|)^2/2         the reference's own float32 rounding of the score
-// ex = |x - fp16(x)|, nx = |x|, e_mu = max_k |mu_k - fp16(mu_k)|, n_mu = max_k |fp16(mu_k)|.
-// A component whose t^ is more than tau = 2*bound below the best t^ cannot be the reference's argmax.
-__host__ __device__ inline float filter_tau(float ex, float nx, float e_mu, float n_mu, int D) {
-    const float c_acc = ldexpf((float)kp_of(D), -21) + ldexpf(1.f, -19);
-    const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
-    const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
-    return 2.0f * bound;
-}
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 // SBO = distance between 8-row core matrices (128 B), LBO = distance between the two
@@ -97,10 +69,12 @@ struct FilterParams {
     const uint8_t *x_tiles, *w_tiles;
     Cand *cand;
     int64_t n_emb;
-    int32_t n_mtiles, n_ntiles, n_ksteps, n_abuf;
-    uint32_t tile_bytes;
-    const float *x_max, *w_max;    // [2] each: corpus-wide (max ex, max nx), model-wide (max e_mu, max n_mu)
+    int32_t n_mtiles, n_ntiles, n_ksteps, n_abuf;     // n_ksteps: K=16 steps per inner-dimension CHUNK
+    uint32_t tile_bytes;                              // bytes of one 128-row tile image of one chunk
+    const float *x_max, *w_max;    // corpus-wide (max ex, max nx); model-wide maxima (k-means: e_mu, n_mu; FBGMM: eB, nB, |A|, p/2)
     int32_t D;
+    int32_t tau_kind;              // TAU_KMEANS: argmax filter (2 * bound); TAU_LSE: logsumexp filter (tau_T + 2 * bound)
+    float tau_T;
 };
 
 // Insert a chunk maximum into the running top-3.  A chunk that becomes the new BEST also records
@@ -141,19 +115,25 @@ __device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float
     }
 }
 
-// KS = number of K=16 steps when known at compile time (fully unrolled issue loop), 0 = runtime.
-template <int KS>
+// KS = number of K=16 steps per chunk when known at compile time (fully unrolled issue loop), 0 = runtime.
+// NCH = chunks of the inner dimension (1: k-means and isotropic FBGMM; 2: anisotropic FBGMM, whose
+// inner dimension [x | x*x] is twice as long).  With NCH = 2 an operand tile is two consecutive
+// chunk images; the B ring holds one chunk per stage (stage = chunk index), the accumulators stay
+// double-buffered by tile parity, and the issuer commits twice per tile: "chunk-0 stage free" and
+// "tile done" (= chunk-1 stage free + accumulators ready).
+template <int KS, int NCH>
 __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tb = p.tile_bytes;
     const int n_ks = KS > 0 ? KS : p.n_ksteps;
-    uint8_t *sA = smem;                                        // n_abuf x 2 tiles
-    uint8_t *sB = smem + (size_t)p.n_abuf * 2 * tb;            // 2 stages, stage = accumulator buffer = tile parity
+    uint8_t *sA = smem;                                        // n_abuf x 2 tiles x NCH chunks
+    uint8_t *sB = smem + (size_t)p.n_abuf * 2 * NCH * tb;      // 2 stages (NCH = 1: stage = accumulator buffer = tile parity)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * (size_t)tb);
     // MMA_DONE[b] (one tcgen05.commit per tile) means BOTH "B stage b may be refilled" (producer) and
     // "accumulator pair b is complete" (epilogue): the issuing thread pays for one commit per tile.
-    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, MMA_DONE = 6, ACC_EMPTY = 8, N_BARS = 10;
+    // NCH = 2 adds B_EMPTY0: the chunk-0 stage is free as soon as the tile's chunk-0 MMAs are done.
+    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, MMA_DONE = 6, ACC_EMPTY = 8, B_EMPTY0 = 10, N_BARS = 11;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     float4 *merge = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [MT_ROWS][2] partial top-3
     const uint32_t bar0 = smem_u32(bars);
@@ -162,6 +142,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
     if (threadIdx.x == 0) {
         for (int i = 0; i < ACC_EMPTY; ++i) mbar_init(BAR(i), 1);
         for (int b = 0; b < 2; ++b) mbar_init(BAR(ACC_EMPTY + b), N_EPI_WARPS);
+        mbar_init(BAR(B_EMPTY0), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -185,9 +166,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 const int ab = p.n_abuf == 2 ? (it & 1) : 0;
                 const uint32_t use = p.n_abuf == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
                 mbar_wait(BAR(A_EMPTY + ab), (use & 1) ^ 1);
-                mbar_expect_tx(BAR(A_FULL + ab), 2 * tb);
-                bulk_g2s(smem_u32(sA + (size_t)(2 * ab) * tb), p.x_tiles + (size_t)(2 * mt) * tb, tb, BAR(A_FULL + ab));
-                bulk_g2s(smem_u32(sA + (size_t)(2 * ab + 1) * tb), p.x_tiles + (size_t)(2 * mt + 1) * tb, tb, BAR(A_FULL + ab));
+                mbar_expect_tx(BAR(A_FULL + ab), 2 * NCH * tb);
+#pragma unroll
+                for (int j = 0; j < 2 * NCH; ++j)          // tiles 2mt, 2mt+1, each NCH consecutive chunk images
+                    bulk_g2s(smem_u32(sA + (size_t)(2 * NCH * ab + j) * tb),
+                             p.x_tiles + ((size_t)(2 * mt) * NCH + j) * tb, tb, BAR(A_FULL + ab));
             };
             uint32_t n_use = 0;
             int it = 0;
@@ -197,10 +180,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 const int nt_pref = p.n_abuf == 2 ? (p.n_ntiles > 4 ? 4 : p.n_ntiles - 1) : -1;
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     if (nt == nt_pref && mt_next < p.n_mtiles) load_a(it + 1, mt_next);
-                    const uint32_t s = n_use & 1, use = n_use >> 1;
-                    mbar_wait(BAR(MMA_DONE + s), (use & 1) ^ 1);       // the MMAs of the stage's previous tile are done
-                    mbar_expect_tx(BAR(B_FULL + s), tb);
-                    bulk_g2s(smem_u32(sB + (size_t)s * tb), p.w_tiles + (size_t)nt * tb, tb, BAR(B_FULL + s));
+                    if (NCH == 1) {
+                        const uint32_t s = n_use & 1, use = n_use >> 1;
+                        mbar_wait(BAR(MMA_DONE + s), (use & 1) ^ 1);       // the MMAs of the stage's previous tile are done
+                        mbar_expect_tx(BAR(B_FULL + s), tb);
+                        bulk_g2s(smem_u32(sB + (size_t)s * tb), p.w_tiles + (size_t)nt * tb, tb, BAR(B_FULL + s));
+                    } else {
+                        // chunk 0 -> stage 0: free when the previous tile's chunk-0 MMAs are done
+                        mbar_wait(BAR(B_EMPTY0), (n_use & 1) ^ 1);
+                        mbar_expect_tx(BAR(B_FULL + 0), tb);
+                        bulk_g2s(smem_u32(sB), p.w_tiles + (size_t)(2 * nt) * tb, tb, BAR(B_FULL + 0));
+                        // chunk 1 -> stage 1: free when the previous tile is done (its MMA_DONE completion)
+                        if (n_use > 0) mbar_wait(BAR(MMA_DONE + ((n_use - 1) & 1)), ((n_use - 1) >> 1) & 1);
+                        mbar_expect_tx(BAR(B_FULL + 1), tb);
+                        bulk_g2s(smem_u32(sB + tb), p.w_tiles + (size_t)(2 * nt + 1) * tb, tb, BAR(B_FULL + 1));
+                    }
                 }
                 if (p.n_abuf == 1 && mt_next < p.n_mtiles) load_a(it + 1, mt_next);
             }
@@ -224,30 +218,71 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 const int ab = p.n_abuf == 2 ? (it & 1) : 0;
                 const uint32_t ause = p.n_abuf == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
                 mbar_wait(BAR(A_FULL + ab), ause & 1);
-                const uint32_t a_lo0 = a_lo_base + (uint32_t)(2 * ab) * (tb >> 4), a_lo1 = a_lo0 + (tb >> 4);
+                const uint32_t a_lo0 = a_lo_base + (uint32_t)(2 * NCH * ab) * (tb >> 4), a_lo1 = a_lo0 + NCH * (tb >> 4);
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     const uint32_t buf = n_use & 1, use = n_use >> 1;
-                    mbar_wait2(BAR(B_FULL + buf), use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t b_lo = b_lo_base + buf * (tb >> 4);
                     const uint32_t d0 = tmem_base + (buf * 2) * NT_COLS, d1 = d0 + NT_COLS;
-                    if (KS > 0) {
-                        tc_mma_f16_lo<false>(d0, a_lo0, b_lo, idesc);
-                        tc_mma_f16_lo<false>(d1, a_lo1, b_lo, idesc);
+                    if (NCH == 1) {
+                        mbar_wait2(BAR(B_FULL + buf), use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t b_lo = b_lo_base + buf * (tb >> 4);
+                        if (KS > 0) {
+                            tc_mma_f16_lo<false>(d0, a_lo0, b_lo, idesc);
+                            tc_mma_f16_lo<false>(d1, a_lo1, b_lo, idesc);
 #pragma unroll
-                        for (int k = 1; k < KS; ++k) {
-                            tc_mma_f16_lo<true>(d0, a_lo0 + k * KSTEP, b_lo + k * KSTEP, idesc);
-                            tc_mma_f16_lo<true>(d1, a_lo1 + k * KSTEP, b_lo + k * KSTEP, idesc);
+                            for (int k = 1; k < KS; ++k) {
+                                tc_mma_f16_lo<true>(d0, a_lo0 + k * KSTEP, b_lo + k * KSTEP, idesc);
+                                tc_mma_f16_lo<true>(d1, a_lo1 + k * KSTEP, b_lo + k * KSTEP, idesc);
+                            }
+                        } else {
+                            for (int k = 0; k < n_ks; ++k) {
+                                tc_mma_f16(d0, ((uint64_t)DESC_HI << 32) | (a_lo0 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                                tc_mma_f16(d1, ((uint64_t)DESC_HI << 32) | (a_lo1 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                            }
                         }
+                        tc_commit(BAR(MMA_DONE + buf));       // B stage free + accumulators ready
                     } else {
-                        for (int k = 0; k < n_ks; ++k) {
-                            tc_mma_f16(d0, ((uint64_t)DESC_HI << 32) | (a_lo0 + k * KSTEP),
-                                       ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
-                            tc_mma_f16(d1, ((uint64_t)DESC_HI << 32) | (a_lo1 + k * KSTEP),
-                                       ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                        // chunk 0 (stage 0) opens the accumulators, chunk 1 (stage 1) completes them
+                        mbar_wait2(BAR(B_FULL + 0), n_use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
+                        tc_fence_after();
+                        if (KS > 0) {
+                            tc_mma_f16_lo<false>(d0, a_lo0, b_lo_base, idesc);
+                            tc_mma_f16_lo<false>(d1, a_lo1, b_lo_base, idesc);
+#pragma unroll
+                            for (int k = 1; k < KS; ++k) {
+                                tc_mma_f16_lo<true>(d0, a_lo0 + k * KSTEP, b_lo_base + k * KSTEP, idesc);
+                                tc_mma_f16_lo<true>(d1, a_lo1 + k * KSTEP, b_lo_base + k * KSTEP, idesc);
+                            }
+                        } else {
+                            for (int k = 0; k < n_ks; ++k) {
+                                tc_mma_f16(d0, ((uint64_t)DESC_HI << 32) | (a_lo0 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_lo_base + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                                tc_mma_f16(d1, ((uint64_t)DESC_HI << 32) | (a_lo1 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_lo_base + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                            }
                         }
+                        tc_commit(BAR(B_EMPTY0));
+                        mbar_wait(BAR(B_FULL + 1), n_use & 1);
+                        tc_fence_after();
+                        const uint32_t a_c0 = a_lo0 + (tb >> 4), a_c1 = a_lo1 + (tb >> 4), b_c = b_lo_base + (tb >> 4);
+                        if (KS > 0) {
+#pragma unroll
+                            for (int k = 0; k < KS; ++k) {
+                                tc_mma_f16_lo<true>(d0, a_c0 + k * KSTEP, b_c + k * KSTEP, idesc);
+                                tc_mma_f16_lo<true>(d1, a_c1 + k * KSTEP, b_c + k * KSTEP, idesc);
+                            }
+                        } else {
+                            for (int k = 0; k < n_ks; ++k) {
+                                tc_mma_f16(d0, ((uint64_t)DESC_HI << 32) | (a_c0 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_c + k * KSTEP), idesc, 1u);
+                                tc_mma_f16(d1, ((uint64_t)DESC_HI << 32) | (a_c1 + k * KSTEP),
+                                           ((uint64_t)DESC_HI << 32) | (b_c + k * KSTEP), idesc, 1u);
+                            }
+                        }
+                        tc_commit(BAR(MMA_DONE + buf));       // chunk-1 stage free + accumulators ready
                     }
-                    tc_commit(BAR(MMA_DONE + buf));       // B stage free + accumulators ready
                 }
                 tc_commit(BAR(A_EMPTY + ab));             // A tiles free
             }
@@ -262,7 +297,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
         constexpr int COLS = NT_COLS / EPI_PARTS;          // columns of each tile this warp reduces
         static_assert(COLS == 64, "one x64 load per warp and tile");
         // one threshold for the whole launch: the loosest per-row tau (refine re-derives the exact per-row one)
-        const float tau_c = filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D);
+        const float tau_c = p.tau_kind == TAU_KMEANS
+            ? filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D)
+            : lse_tau(p.x_max[0], p.x_max[1], W4{p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3]}, 16 * n_ks * NCH, p.tau_T);
         uint32_t n_use = 0;
         for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
             float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
@@ -456,14 +493,6 @@ __device__ __noinline__ float exact_neg_dist(const float *meansT, int KM_, int k
 // q (terms d = q, q+8, ...), the butterfly (xor 1, 2, 4) reproduces the combination tree
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) bit for bit, and the second 8-lane group handles the second
 // block when D > 128.  Loads are coalesced along d (row-major X and means).
-
-// code: -2 exhaustive scan needed, -1 best chunk suffices, >= 0 also visit that chunk.
-__device__ __forceinline__ int refine_decide(const Cand &c, float tau, int n_chunks) {
-    if (c.i1 < 0 || c.i1 >= n_chunks || !(tau < CUDART_INF_F) ||
-        (!(c.m1 - c.m3 > tau) && (c.m3 > -CUDART_INF_F))) return -2;
-    if ((c.i2 >= 0) && !(c.m1 - c.m2 > tau)) return c.i2;
-    return -1;
-}
 
 constexpr int REFINE_THREADS = 256;
 constexpr int REFINE_MAX_STEPS = 16;     // 128 terms / 8 accumulators
@@ -701,33 +730,51 @@ extern "C" int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D,
     return 0;
 }
 
-extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
-                               const float *x_max, const float *w_max, void *cand, void *stream) {
-    SEGB_CHECK_ARG(x_tiles && w_tiles && cand && x_max && w_max && n_emb > 0 && K_max > 0, "null pointer");
+namespace segb {
+namespace mma {
+int launch_filter(const FilterLaunch &f, cudaStream_t stream) {
     FilterParams p;
-    p.x_tiles = (const uint8_t *)x_tiles; p.w_tiles = (const uint8_t *)w_tiles; p.cand = (Cand *)cand;
-    p.n_emb = n_emb;
-    p.x_max = x_max; p.w_max = w_max; p.D = D;
-    p.n_mtiles = (int32_t)(rows_pad(n_emb) / MT_ROWS);
-    p.n_ntiles = k_pad(K_max) / NT_COLS;
-    p.n_ksteps = kp_of(D) / 16;
-    p.tile_bytes = (uint32_t)tile_bytes_of(D);
-    const size_t fixed = 2 * (size_t)p.tile_bytes + 256 + (size_t)MT_ROWS * 32 + 1024;    // B stages, barriers, merge, alignment
+    p.x_tiles = (const uint8_t *)f.x_tiles; p.w_tiles = (const uint8_t *)f.w_tiles; p.cand = (Cand *)f.cand;
+    p.n_emb = f.n_emb;
+    p.x_max = f.x_max; p.w_max = f.w_max; p.D = f.D;
+    p.tau_kind = f.tau_kind; p.tau_T = f.tau_T;
+    p.n_mtiles = (int32_t)(rows_pad(f.n_emb) / MT_ROWS);
+    p.n_ntiles = f.w_rows_pad / NT_COLS;
+    p.n_ksteps = f.KP / 16;
+    p.tile_bytes = (uint32_t)((int64_t)TILE_ROWS * f.KP * 2);
+    const int nch = f.n_chunks;
+    if (nch != 1 && nch != 2) { set_error("filter GEMM: 1 or 2 inner-dimension chunks"); return SEGB_E_ARG; }
+    const size_t tb = p.tile_bytes;
+    const size_t fixed = 2 * tb + 256 + (size_t)MT_ROWS * 32;            // B stages, barriers, merge buffer
     const size_t budget = 227 * 1024;
-    if (2 * (size_t)p.tile_bytes + fixed > budget) {
-        set_error("D=%d too large for the tensor-core scorer", D);
+    if (2 * nch * tb + fixed > budget) {
+        set_error("inner dimension %d x %d too large for the tensor-core scorer", nch, f.KP);
         return SEGB_E_UNSUPPORTED;
     }
-    p.n_abuf = (4 * (size_t)p.tile_bytes + fixed <= budget) ? 2 : 1;
-    const size_t smem = (size_t)(p.n_abuf * 2 + 2) * p.tile_bytes + 256 + (size_t)MT_ROWS * 32;
+    p.n_abuf = (4 * nch * tb + fixed <= budget) ? 2 : 1;
+    const size_t smem = (size_t)p.n_abuf * 2 * nch * tb + fixed;
     int n_sm = 0;
     { const int rc = device_info(nullptr, &n_sm, nullptr); if (rc) return rc; }
     const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;
-    auto kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9> : kmeans_filter_kernel<0>;     // 9: D = 130 (KP = 144)
+    void (*kern)(FilterParams);
+    if (nch == 1) kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 1> : kmeans_filter_kernel<0, 1>;     // 9: D = 130 (KP = 144)
+    else kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 2> : kmeans_filter_kernel<0, 2>;
     SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, N_THREADS, smem, stream>>>(p);
     SEGB_LAUNCH_CHECK();
     return 0;
+}
+}  // namespace mma
+}  // namespace segb
+
+extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int32_t K_max, int32_t D,
+                               const float *x_max, const float *w_max, void *cand, void *stream) {
+    SEGB_CHECK_ARG(x_tiles && w_tiles && cand && x_max && w_max && n_emb > 0 && K_max > 0, "null pointer");
+    FilterLaunch f;
+    f.x_tiles = x_tiles; f.w_tiles = w_tiles; f.cand = cand; f.n_emb = n_emb;
+    f.w_rows_pad = k_pad(K_max); f.KP = kp_of(D); f.D = D; f.x_max = x_max; f.w_max = w_max;
+    f.n_chunks = 1; f.tau_kind = TAU_KMEANS; f.tau_T = 0.f;
+    return launch_filter(f, (cudaStream_t)stream);
 }
 
 extern "C" int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max) {

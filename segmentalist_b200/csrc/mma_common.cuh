@@ -125,5 +125,89 @@ __device__ __forceinline__ void tc_ld64_wait(uint32_t taddr, float *v) {
 }
 
 
+// ---------------------------------------------------------------- filter GEMM: shared definitions
+//
+// The filter GEMM (kmeans_mma.cu: kmeans_filter_kernel) serves two scorers: the k-means
+// max / argmax (kmeans_mma.cu) and the FBGMM log_marg_i logsumexp (fixedvar_filter.cu).  Both hand
+// it fp16 tile images whose inner dimension already carries every additive constant, and both read
+// back the same per-row record: the best three 16-column chunks and member masks.
+
+constexpr int TILE_ROWS = 128;     // rows per operand tile image
+constexpr int MT_ROWS = 256;       // embeddings per CTA work item (two A tiles)
+constexpr int NT_COLS = 128;       // components per accumulator tile
+constexpr int CHUNK = 16;          // components per candidate chunk
+
+struct __align__(32) Cand {        // per-embedding filter record
+    float m1, m2, m3;              // best / second / third chunk maximum of the filter score
+    int32_t i1, i2;                // chunk ids of m1, m2
+    uint32_t masks;                // bits 0-15: members of chunk i1 within tau of its max; 16-31: chunk i2
+    int32_t pad[2];
+};
+
+// byte offset of element (r, c) inside a 128-row tile image
+__host__ __device__ inline int tile_off(int r, int c) {
+    return ((c >> 3) * (TILE_ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (c & 7) * 2;
+}
+
+// Rigorous bound on |t^ - t| for t = x.mu - |mu|^2/2 as computed by the fp16 filter GEMM:
+//   ex*|mu^| + |x|*e_mu                      fp16 rounding of the two operands (Cauchy-Schwarz)
+//   c_acc*((|x|+ex)*|mu^| + |mu|^2/2)        fp32 accumulation in the tensor core, bias split
+//   eta = (D+3)*2^-24*(|x|+|mu|)^2/2         the reference's own float32 rounding of the score
+// ex = |x - fp16(x)|, nx = |x|, e_mu = max_k |mu_k - fp16(mu_k)|, n_mu = max_k |fp16(mu_k)|.
+// A component whose t^ is more than tau = 2*bound below the best t^ cannot be the reference's argmax.
+__host__ __device__ inline float filter_tau(float ex, float nx, float e_mu, float n_mu, int D) {
+    const int kp = (D + 3 + 15) / 16 * 16;
+    const float c_acc = ldexpf((float)kp, -21) + ldexpf(1.f, -19);
+    const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
+    const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
+    return 2.0f * bound;
+}
+
+// Logsumexp filter (FBGMM log_marg_i).  The GEMM computes s^_k ~ s_k = A_k + F(x).W_k, where F are
+// the row's features (x, or [x, x*x] for anisotropic variances) and A_k plus, in the isotropic case,
+// -p_k/2 |x|^2 ride in split constant columns.  Bound on |s^ - s|:
+//   eF*nW + nF*eW                      fp16 rounding of features and weights (Cauchy-Schwarz)
+//   c_acc*((nF+eF)*nW + cmag)          fp32 accumulation over KP products
+//   2^-20*cmag                         the hi/lo splits of the constants, cmag = |A| + (p/2) nF^2
+//   2^-22*nF*nW                        float32 rounding of x*x / P*mu before the fp16 conversion
+// w4 = model-wide maxima (eW, nW, |A|, p/2).  Every component with s_k >= max_k s_k - T has
+// s^_k >= max s^ - (T + 2*bound) = max s^ - tau; the components below carry at most K*exp(-T) of
+// the sum, so a logsumexp over the exact scores of the survivors is exact to K*exp(-T) absolute.
+struct W4 { float eW, nW, Aabs, ph; };
+__host__ __device__ inline float lse_bound(float eF, float nF, W4 w, int KP) {
+    const float c_acc = ldexpf((float)KP, -21) + ldexpf(1.f, -19);
+    const float cmag = w.Aabs + w.ph * nF * nF;
+    return eF * w.nW + nF * w.eW + c_acc * ((nF + eF) * w.nW + cmag) + ldexpf(cmag, -20) + ldexpf(nF * w.nW, -22) + 1e-30f;
+}
+__host__ __device__ inline float lse_tau(float eF, float nF, W4 w, int KP, float T) {
+    return T + 2.0f * lse_bound(eF, nF, w, KP);
+}
+
+// What the refine does with a row: -2 exhaustive exact scan needed (the third-best chunk is still
+// inside the bound, or the record is unusable), -1 the best chunk suffices, >= 0 also visit that chunk.
+__device__ __forceinline__ int refine_decide(const Cand &c, float tau, int n_chunks) {
+    if (c.i1 < 0 || c.i1 >= n_chunks || !(tau < CUDART_INF_F) ||
+        (!(c.m1 - c.m3 > tau) && (c.m3 > -CUDART_INF_F))) return -2;
+    if ((c.i2 >= 0) && !(c.m1 - c.m2 > tau)) return c.i2;
+    return -1;
+}
+
+constexpr int TAU_KMEANS = 0, TAU_LSE = 1;
+
+// Launch description of the filter GEMM over pre-packed tile images (host side).
+struct FilterLaunch {
+    const void *x_tiles, *w_tiles;     // [rows_pad / 128] and [w_rows_pad / 128] tile images of KP columns
+    void *cand;                        // [n_emb] Cand records out
+    int64_t n_emb;
+    int32_t w_rows_pad;                // multiple of NT_COLS
+    int32_t KP;                        // padded inner dimension of ONE chunk (multiple of 16)
+    int32_t n_chunks;                  // 1, or 2: every tile is two consecutive chunk images of KP columns
+    int32_t D;
+    const float *x_max, *w_max;
+    int32_t tau_kind;
+    float tau_T;
+};
+int launch_filter(const FilterLaunch &f, cudaStream_t stream);
+
 }  // namespace mma
 }  // namespace segb

@@ -75,16 +75,27 @@ class FBGMM(object):
             _lib.ptr(out), _lib.stream_ptr()))
         return out.cpu().numpy()
 
-    def log_marg_all(self, tensor_cores=True):
-        """log_marg_i of EVERY embedding against the current (frozen) model in one launch.
-        tensor_cores=True: FP32-accurate tcgen05 GEMM with the logsumexp fused into the epilogue
-        (segb_fvmma_log_marg; isotropic variances, float32 embeddings; ~1e-6 relative);
-        False: the exact float64 kernel."""
+    def log_marg_all(self, tensor_cores=True, method="filter"):
+        """log_marg_i of EVERY embedding against the current (frozen) model in one pass.
+        tensor_cores=True, method="filter" (default): ONE fp16 tcgen05 pass that keeps, per embedding, the
+        components within 25 nats (+ a rigorous rounding bound) of the best one, exact float64 re-scoring of
+        those and the logsumexp over the exact scores (segb_fvf_*; isotropic or anisotropic variances,
+        float32 embeddings; ~1e-7 absolute).  method="split3": the FP32-accurate three-pass GEMM with the
+        logsumexp fused into its epilogue (segb_fvmma_log_marg; isotropic variances only; ~1e-6 relative).
+        tensor_cores=False: the exact float64 kernel."""
         c = self.components
         if not tensor_cores:
             return self.log_marg_items(np.arange(c.N))
+        assert c._X.dtype == torch.float32, "tensor-core log_marg needs float32 embeddings"
+        if method == "filter":
+            from .batch import FvScorer
+            if getattr(self, "_fv", None) is None or self._fv.c is not c:
+                self._fv = FvScorer(c)
+            self._fv.score()
+            return self._fv.log_marg.cpu().numpy()
+        assert method == "split3"
         iso = (np.all(c.precision == c.precision[0]) and np.all(c.precision_0 == c.precision_0[0]))
-        assert iso and c._X.dtype == torch.float32, "tensor-core log_marg needs isotropic variances and float32 X"
+        assert iso, "the three-pass tensor-core log_marg needs isotropic variances"
         lib = _lib.lib()
         if getattr(self, "_tc", None) is None:
             x_tiles = torch.empty(lib.segb_fvmma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device="cuda")

@@ -227,6 +227,42 @@ class UnigramAcousticWordseg(object):
             logger.info(info)
         return record_dict
 
+    # ---- frozen-state batch mode (new)
+    def segment_frozen(self, n_iter, uniforms=None):
+        """Frozen-model sweeps: every utterance is scored (tensor-core log_marg_i) and segmented (FFBS for
+        fb_type "standard", Viterbi for "viterbi") against the same model, every new token picks its
+        component from that model (sampled / MAP), then the model is rebuilt from the new assignments
+        (batch.FrozenFBGMMSweep) -- the mode that shards over GPUs.  Fixed-variance components only.
+        uniforms: optional list (one entry per iteration) of (u_fb, u_assign) float64 arrays [sum of
+        utterance lengths]; default: drawn from np.random.  Returns a record dict."""
+        from .batch import FrozenFBGMMSweep
+        comps = self.acoustic_model.components
+        assert getattr(self.acoustic_model, "covariance_type", "fixed") == "fixed", \
+            "the frozen FBGMM sweep covers fixed-variance components"
+        assert self.calc_p_continue() == 1.0
+        if getattr(self, "_frozen", None) is None:
+            self._frozen = FrozenFBGMMSweep(comps, self._corpus, fb_type=self.fb_type,
+                                            time_power_term=self.time_power_term, wip=self.wip)
+        self._frozen.K_host = None          # sequential sweeps in between may have changed K
+        n_pos = self._corpus.n_pos
+        record = {k: [] for k in ("sample_time", "log_marg*length", "components", "n_tokens", "fallback_rows")}
+        for it in range(n_iter):
+            t0 = time.time()
+            u_fb = u_assign = None
+            if self.fb_type == "standard":
+                if uniforms is not None:
+                    u_fb, u_assign = (_lib.dev(np.asarray(a, dtype=np.float64)) for a in uniforms[it])
+                else:
+                    u_fb, u_assign = _lib.dev(np.random.rand(n_pos)), _lib.dev(np.random.rand(n_pos))
+            total = self._frozen.sweep(u_fb, u_assign)
+            self.utterances.boundaries[:, :] = self._corpus.boundaries_matrix()
+            record["sample_time"].append(time.time() - t0)
+            record["log_marg*length"].append(total)
+            record["components"].append(self._frozen.K_host)
+            record["n_tokens"].append(int((self._corpus.tok_id >= 0).sum().item()))
+            record["fallback_rows"].append(self._frozen.last_fallback)
+        return record
+
     def get_vec_embed_log_probs(self, vec_ids, durations):
         """log marginals of the `vec_ids` embeddings scaled by `durations` (:474-511)."""
         return self.acoustic_model.log_marg_items(np.asarray(vec_ids), np.asarray(durations, dtype=np.float64),

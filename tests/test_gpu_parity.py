@@ -636,7 +636,7 @@ def test_fixedvar_tensor_core_log_marg(sb, K_max, n_assigned, n_emb):
     prior = gcf.FixedVarPrior(var, np.zeros(D), var / 0.05)
     am = fbgmm.FBGMM(X, prior, 10., K_max, assign.copy(), covariance_type="fixed", lms=0.9)
     exact = am.log_marg_all(tensor_cores=False)
-    tc = am.log_marg_all(tensor_cores=True)
+    tc = am.log_marg_all(tensor_cores=True, method="split3")
     rel = np.abs(tc - exact) / np.abs(exact)
     assert rel.max() < 1e-4, rel.max()
     assert rel.max() < 2e-5, rel.max()          # what the split actually delivers
@@ -861,3 +861,145 @@ def test_unigram_sweeps_vs_oracle_larger(sb, fb_type, anneal):
     npt.assert_array_equal(seg.utterances.boundaries, oseg.utterances.boundaries)
     npt.assert_array_equal(seg.acoustic_model.components.assignments, oseg.acoustic_model.components.assignments)
     npt.assert_allclose(rec["log_marg*length"], orec["log_marg*length"], rtol=1e-10)
+
+
+# ---------------------------------------------------------------------------
+# filter-and-refine log_marg_i (one tensor pass) and the frozen FBGMM sweep
+# ---------------------------------------------------------------------------
+
+def _fv_case(kind, K_max, n_assigned, n_emb, seed):
+    """(X, prior args, assignments) for the log_marg tests.  kind: "iso" peaked posteriors (the recipes'
+    S_0 = 0.002*1), "aniso" D-vector variances (tests/test_gaussian_components_fixedvar.py:51-53),
+    "flat" adversarial: a wide variance makes every component matter for every embedding."""
+    from segmentalist_b200 import synth
+    rng = np.random.RandomState(seed)
+    D = 130
+    centres = synth.cluster_centres(50, D, rng)
+    X = synth._unit_rows(centres[rng.randint(0, 50, n_emb)] + 0.05 * rng.standard_normal((n_emb, D)).astype(np.float32))
+    assign = -np.ones(n_emb, dtype=np.int64)
+    if n_assigned:
+        k_used = min(K_max - 3, max(1, n_assigned // 4))
+        assign[:n_assigned] = np.arange(n_assigned) % k_used
+    if kind == "iso":
+        var = 0.002 * np.ones(D)
+        var_0 = var / 0.05
+    elif kind == "flat":
+        var = 0.6 * np.ones(D)
+        var_0 = 2.0 * np.ones(D)
+    else:
+        var = 0.002 * (0.5 + rng.rand(D))
+        var_0 = 0.04 * (0.5 + rng.rand(D))
+    mu_0 = 0.01 * rng.standard_normal(D) if kind == "aniso" else np.zeros(D)
+    return X, (var, mu_0, var_0), assign
+
+
+@pytest.mark.parametrize("kind,K_max,n_assigned,n_emb", [
+    ("iso", 64, 300, 700), ("iso", 1000, 6000, 9000), ("iso", 40, 0, 300), ("iso", 300, 1200, 2000),
+    ("aniso", 64, 300, 700), ("aniso", 1000, 6000, 9000), ("aniso", 40, 0, 300),
+    ("flat", 64, 300, 700), ("flat", 600, 3000, 2000)])
+def test_fv_filter_log_marg(sb, kind, K_max, n_assigned, n_emb):
+    """ONE fp16 tcgen05 pass + exact float64 re-scoring of the components within 25 nats of the best
+    (segb_fvf_*) against the exact float64 kernel and the oracle's FBGMM.log_marg_i: within 1e-4 relative
+    (north star) -- in fact ~1e-7 absolute -- for isotropic and anisotropic variances, with K_act < K_max
+    (the virtual empty slot) and on flat posteriors (every row takes the exhaustive scan)."""
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf
+    X, (var, mu_0, var_0), assign = _fv_case(kind, K_max, n_assigned, n_emb, seed=K_max + len(kind))
+    am = fbgmm.FBGMM(X, gcf.FixedVarPrior(var, mu_0, var_0), 10., K_max, assign.copy(), covariance_type="fixed", lms=0.9)
+    exact = am.log_marg_all(tensor_cores=False)
+    tc = am.log_marg_all(tensor_cores=True, method="filter")
+    n_fb = int(am._fv.n_fallback.item())
+    err = np.abs(tc - exact)
+    assert (err / np.abs(exact)).max() < 1e-4
+    assert err.max() < 2e-6, err.max()                  # 7e-8 dropped mass + float64 rounding
+    if kind == "flat":
+        assert n_fb == n_emb                            # nothing is decided by the filter
+    else:
+        assert n_fb < n_emb // 4, n_fb                  # peaked posteriors: the filter decides
+    # oracle on a few items, and the MAP slot of map_assign_i (fbgmm.py:475-491)
+    oam = so.FBGMM(X, so.FixedVarPrior(var, mu_0, var_0), 10., K_max, assign.copy(), lms=0.9)
+    map_k = am._fv.map_k.cpu().numpy()
+    for i in range(0, n_emb, max(1, n_emb // 12)):
+        ref = oam.log_marg_i(i)
+        assert abs(tc[i] - ref) <= 1e-4 * abs(ref)
+        lpz = oam._assign_scores(i, False)
+        assert map_k[i] == int(np.argmax(lpz)), (i, map_k[i], int(np.argmax(lpz)))
+
+
+@pytest.mark.parametrize("fb_type,am_K,kind", [("standard", 40, "iso"), ("viterbi", 40, "iso"),
+                                                ("standard", 12, "iso"), ("viterbi", 12, "aniso"),
+                                                ("standard", 300, "aniso")])
+def test_frozen_fbgmm_sweep_vs_oracle(sb, fb_type, am_K, kind):
+    """UnigramAcousticWordseg.segment_frozen (tensor-core log_marg_i -> batched FFBS / Viterbi -> frozen
+    component choice -> device clamp -> closed-form rebuild) against the oracle's frozen_fbgmm_sweep built
+    from the reference's pure functions: identical boundaries and assignments after three sweeps under the
+    same uniforms, statistics to 1e-12.  am_K = 12 < the 15 generating clusters keeps every component
+    alive (K = K_max); am_K = 300 leaves empty slots (new components, the clamp, consecutive relabelling)."""
+    from segmentalist_b200 import fbgmm, gaussian_components_fixedvar as gcf, synth, unigram_acoustic_wordseg as uaw
+    D, U, S = 130, 50, 6
+    mats, vids, durs, lms = synth.make_corpus_dicts(U, D=D, K_true=15, n_min=6, n_max=18, n_slices_max=S,
+                                                    noise=0.05, seed=91)
+    rng = np.random.RandomState(3)
+    if kind == "iso":
+        var, var_0 = 0.002 * np.ones(D), 0.04 * np.ones(D)
+    else:
+        var, var_0 = 0.002 * (0.5 + rng.rand(D)), 0.04 * (0.5 + rng.rand(D))
+
+    def make(mod, am, pr):
+        random.seed(12)
+        np.random.seed(12)
+        return mod.UnigramAcousticWordseg(am, 10., am_K, pr, mats, vids, durs, lms, p_boundary_init=0.5,
+                                          beta_sent_boundary=-1, n_slices_max=S, fb_type=fb_type, lms=0.9,
+                                          time_power_term=1.1, wip=-0.2)
+    seg = make(uaw, fbgmm.FBGMM, gcf.FixedVarPrior(var, np.zeros(D), var_0))
+    oseg = make(so, so.FBGMM, so.FixedVarPrior(var, np.zeros(D), var_0))
+    n_pos = int(sum(seg.utterances.lengths))
+    n_it = 3
+    uni = [(rng.rand(n_pos), rng.rand(n_pos)) for _ in range(n_it)]
+    rec = seg.segment_frozen(n_it, uniforms=uni)
+    for it in range(n_it):
+        total, _ = so.frozen_fbgmm_sweep(oseg, uni[it][0], uni[it][1])
+        npt.assert_allclose(rec["log_marg*length"][it], total, rtol=1e-9)
+    c, oc = seg.acoustic_model.components, oseg.acoustic_model.components
+    npt.assert_array_equal(seg.utterances.boundaries, oseg.utterances.boundaries)
+    npt.assert_array_equal(c.assignments, oc.assignments)
+    assert c.K == oc.K
+    npt.assert_array_equal(c.counts, oc.counts)
+    npt.assert_allclose(c.mu_N_numerators, oc.mu_N_numerators, rtol=1e-12, atol=1e-12)
+    npt.assert_allclose(c.precision_preds, oc.precision_preds, rtol=1e-12)
+    npt.assert_allclose(c.log_prod_precision_preds, oc.log_prod_precision_preds, rtol=1e-12)
+    # the sequential sampler continues from the state the frozen sweeps left
+    st = random.getstate()
+    seg.gibbs_sample(1)
+    random.setstate(st)
+    oseg.uniform = so.UniformSource()
+    oseg.acoustic_model.uniform = oseg.uniform
+    oseg.gibbs_sample(1)
+    npt.assert_array_equal(seg.utterances.boundaries, oseg.utterances.boundaries)
+    npt.assert_array_equal(seg.acoustic_model.components.assignments, oseg.acoustic_model.components.assignments)
+
+
+def test_gibbs_barrier_counter_wrap(sb):
+    """The cooperative sweep's grid-barrier counter is 32 bits wide and wraps in long launches; every CTA
+    compares its own target modulo 2^32.  Starting the counter just below 2^32 forces the wrap after a
+    few barriers: the sweep must produce the same samples as with the default start."""
+    from segmentalist_b200 import _lib, fbgmm, gaussian_components_fixedvar as gcf, synth, unigram_acoustic_wordseg as uaw
+    D, K, U, S = 24, 40, 30, 6
+    mats, vids, durs, lms = synth.make_corpus_dicts(U, D=D, K_true=15, n_min=6, n_max=18, n_slices_max=S,
+                                                    noise=0.08, seed=78)
+    var = 0.002 * np.ones(D)
+
+    def run(base):
+        random.seed(13)
+        np.random.seed(13)
+        seg = uaw.UnigramAcousticWordseg(fbgmm.FBGMM, 10., K, gcf.FixedVarPrior(var, np.zeros(D), var / 0.05), mats,
+                                         vids, durs, lms, p_boundary_init=0.5, beta_sent_boundary=-1, n_slices_max=S)
+        _lib.lib().segb_debug_gibbs_bar_base(base)
+        try:
+            seg.gibbs_sample(2)
+        finally:
+            _lib.lib().segb_debug_gibbs_bar_base(0)
+        return seg.utterances.boundaries.copy(), seg.acoustic_model.components.assignments.copy()
+    b0, a0 = run(0)
+    b1, a1 = run(2 ** 32 - 1000)
+    npt.assert_array_equal(b0, b1)
+    npt.assert_array_equal(a0, a1)
