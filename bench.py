@@ -57,7 +57,11 @@ def parse_args():
     ap.add_argument("--scorer", default="mma", choices=["mma", "exact"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-gibbs", action="store_true", help="skip the secondary workload (BASELINE configs[1])")
+    ap.add_argument("--no-gibbs", action="store_true", help="skip the sequential secondary workloads (BASELINE configs[1], [3], [4])")
+    ap.add_argument("--no-fbgmm", action="store_true", help="skip the sharded frozen FBGMM sweep")
+    ap.add_argument("--no-diffuse", action="store_true", help="skip the diffuse-model k-means sweep (K_act < K_max)")
+    ap.add_argument("--fbgmm-utts", type=int, default=0, help="utterances of the frozen FBGMM sweep (default: --utts)")
+    ap.add_argument("--diffuse-utts", type=int, default=40000)
     ap.add_argument("--gibbs-utts", type=int, default=2000)
     ap.add_argument("--only-gibbs", action="store_true", help="run only the secondary Gibbs workload")
     ap.add_argument("--diag-utts", type=int, default=48)
@@ -108,14 +112,12 @@ def corpus_structure(n_utt, seed):
     return lengths, seg_id, seg_dur, b.astype(np.uint8), int(emb_off[-1])
 
 
-def make_embeddings_gpu(n_emb, K_true, seed, device):
+def make_embeddings_gpu(n_emb, centres, seed, device):
+    """x = normalise(c_z + NOISE * N(0, I)), z uniform over the rows of `centres` (device tensor)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    gc = torch.Generator(device=device)
-    gc.manual_seed(12345)                                 # centres shared by all ranks
-    centres = torch.randn(K_true, D, generator=gc, device=device)
-    centres = centres / centres.norm(dim=1, keepdim=True)
+    K_true = centres.shape[0]
     X = torch.empty(n_emb, D, dtype=torch.float32, device=device)
     Z = torch.empty(n_emb, dtype=torch.int32, device=device)
     step = 1 << 21
@@ -125,7 +127,22 @@ def make_embeddings_gpu(n_emb, K_true, seed, device):
         x = centres[z] + NOISE * torch.randn(hi - lo, D, generator=g, device=device)
         X[lo:hi] = x / x.norm(dim=1, keepdim=True)
         Z[lo:hi] = z.to(torch.int32)
-    return X, centres, Z
+    return X, Z
+
+
+CPU_SAMPLE_UTTS = 64          # head of rank 0's shard: generated on the CPU so that both arms see the same utterances
+
+
+def shard_structure(n_utt, rank):
+    """A rank's shard.  Rank 0's first CPU_SAMPLE_UTTS utterances are the fixed "head" corpus
+    (corpus_structure(CPU_SAMPLE_UTTS, 999)) whose embeddings come from sample_rows_cpu: the CPU arms
+    (cpu_baseline, --impl reference) rebuild exactly these utterances without a GPU."""
+    if rank != 0 or n_utt <= CPU_SAMPLE_UTTS:
+        return corpus_structure(n_utt, seed=1000 + rank) + (0,)
+    hl, hi_, hd, hb, hn = corpus_structure(CPU_SAMPLE_UTTS, seed=999)
+    rl, ri, rd, rb, rn = corpus_structure(n_utt - CPU_SAMPLE_UTTS, seed=1000)
+    seg_id = np.concatenate([hi_, np.where(ri >= 0, ri + hn, -1).astype(np.int32)])
+    return (np.concatenate([hl, rl]), seg_id, np.concatenate([hd, rd]), np.concatenate([hb, rb]), hn + rn, hn)
 
 
 class ClockSampler(object):
@@ -176,15 +193,53 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's pure functions on host cores
+# CPU arm: the reference's own pure functions (baseline/_ref, a py3-shimmed copy built by
+# __graft_entry__.build()) on host cores; the oracle port where that directory is absent
 # ------------------------------------------------------------------------------------------------
 
-def _oracle_segmenter(X_sub, lengths, seg_id_band, seg_dur_band, means):
-    """Wrap flat arrays into the oracle's SegmentalKMeansWordseg / KMeansComponents objects."""
+def centres_cpu(K):
+    """Cluster centres shared by all ranks and by both arms (NumPy, fixed seed)."""
+    rng = np.random.RandomState(12345)
+    c = rng.standard_normal((K, D)).astype(np.float32)
+    return (c / np.linalg.norm(c, axis=1, keepdims=True)).astype(np.float32)
+
+
+def sample_rows_cpu(n_rows, centres, seed):
+    """(X, z) of the first n_rows embeddings of a rank's shard, CPU-reproducible."""
+    rng = np.random.RandomState(seed)
+    z = rng.randint(0, centres.shape[0], n_rows)
+    X = centres[z] + NOISE * rng.standard_normal((n_rows, D)).astype(np.float32)
+    return (X / np.linalg.norm(X, axis=1, keepdims=True)).astype(np.float32), z.astype(np.int32)
+
+
+def cpu_modules():
+    """("reference", namespace over the reference's own modules) when baseline/_ref is present, else
+    ("port", the oracle module): both expose Utterances, KMeansComponents, KMeans, SegmentalKMeansWordseg,
+    forward_backward_kmeans_viterbi."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "segmentalist")):
+        try:
+            if ref not in sys.path:
+                sys.path.insert(0, ref)
+            import types
+            from segmentalist import kmeans, kmeans_acoustic_wordseg, kmeans_components, utterances
+            ns = types.SimpleNamespace(
+                Utterances=utterances.Utterances, KMeansComponents=kmeans_components.KMeansComponents,
+                KMeans=kmeans.KMeans, SegmentalKMeansWordseg=kmeans_acoustic_wordseg.SegmentalKMeansWordseg,
+                forward_backward_kmeans_viterbi=kmeans_acoustic_wordseg.forward_backward_kmeans_viterbi)
+            return "reference", ns
+        except Exception as exc:          # e.g. the Cython extension does not load on this box
+            sys.stderr.write("bench: baseline/_ref unusable (%r); timing the oracle port\n" % (exc,))
     from oracle import seg_oracle as so
+    return "port", so
+
+
+def _cpu_segmenter(ns, X_sub, lengths, seg_id_band, seg_dur_band, means):
+    """Wrap flat arrays into SegmentalKMeansWordseg / KMeansComponents objects of `ns` (the reference's
+    classes or the oracle's): attributes set directly, no constructor (the model is given)."""
     from segmentalist_b200.utterances import band_to_packed
     S = seg_id_band.shape[1]
-    utts = so.Utterances.__new__(so.Utterances)
+    utts = ns.Utterances.__new__(ns.Utterances)
     utts.lengths = [int(n) for n in lengths]
     utts.D = len(lengths)
     utts.N_max = int(max(lengths))
@@ -199,68 +254,102 @@ def _oracle_segmenter(X_sub, lengths, seg_id_band, seg_dur_band, means):
         utts.durations[u, :n_packed] = band_to_packed(seg_dur_band[pos:pos + N], N, S, np.nan)
         utts.boundaries[u, N - 1] = True
         pos += N
-    comps = so.KMeansComponents.__new__(so.KMeansComponents)
+    comps = ns.KMeansComponents.__new__(ns.KMeansComponents)
     comps.X, comps.means = X_sub, means
     comps.N, comps.D = X_sub.shape
     comps.K_max = comps.K = means.shape[0]
-    km = so.KMeans.__new__(so.KMeans)
+    km = ns.KMeans.__new__(ns.KMeans)
     km.components = comps
-    seg = so.SegmentalKMeansWordseg.__new__(so.SegmentalKMeansWordseg)
+    seg = ns.SegmentalKMeansWordseg.__new__(ns.SegmentalKMeansWordseg)
     seg.utterances, seg.acoustic_model = utts, km
     seg.n_slices_min, seg.n_slices_max, seg.wip = 0, S, 0
     return seg
 
 
-def _cpu_worker(args):
-    X_sub, lengths, seg_id_band, seg_dur_band, means = args
-    from oracle import seg_oracle as so
-    seg = _oracle_segmenter(X_sub, lengths, seg_id_band, seg_dur_band, means)
+def _cpu_phase1(ns, seg):
+    """The pure part of a frozen sweep through the CPU implementation's own functions, per utterance:
+    get_vec_embed_neg_len_sqrd_norms (kmeans_acoustic_wordseg.py:334-351) -> forward_backward_kmeans_viterbi
+    (:449-555) -> get_max_assignments (kmeans_components.py:256-261)."""
+    utts, comps = seg.utterances, seg.acoustic_model.components
+    totals, bounds, ks = [], [], []
+    for u in range(utts.D):
+        N = utts.lengths[u]
+        n_packed = (N ** 2 + N) // 2
+        scores = seg.get_vec_embed_neg_len_sqrd_norms(utts.vec_ids[u, :n_packed], utts.durations[u, :n_packed])
+        obj, b = ns.forward_backward_kmeans_viterbi(scores, N, seg.n_slices_min, seg.n_slices_max, u)
+        utts.boundaries[u, :N] = b
+        totals.append(float(obj))
+        bounds.append(np.asarray(b, dtype=bool).copy())
+        ks.append([int(k) for k in comps.get_max_assignments(utts.get_segmented_embeds_i(u))])
+    return totals, bounds, ks
+
+
+_POOL = {}
+
+
+def _pool_init(X, lengths, seg_id, seg_dur, means):
+    """Worker initialiser: the corpus sample and the model reach every process ONCE (fork + initargs),
+    not once per job inside the timed region."""
+    kind, ns = cpu_modules()
+    _POOL.update(X=X, lengths=lengths, seg_id=seg_id, seg_dur=seg_dur, means=means, ns=ns)
+
+
+def _pool_job(span):
+    u0, u1 = span
+    P = _POOL
+    pos_off = np.concatenate([[0], np.cumsum(P["lengths"])])
+    lo, hi = pos_off[u0], pos_off[u1]
+    ids = P["seg_id"][lo:hi]
+    e_lo, e_hi = ids[ids >= 0].min(), ids[ids >= 0].max() + 1
+    sub_ids = np.where(ids >= 0, ids - e_lo, -1)
+    seg = _cpu_segmenter(P["ns"], P["X"][e_lo:e_hi], P["lengths"][u0:u1], sub_ids, P["seg_dur"][lo:hi], P["means"])
     t0 = time.perf_counter()
-    totals, _, plan = so.frozen_kmeans_phase1(seg)
-    dt = time.perf_counter() - t0
-    bounds = [seg.utterances.boundaries[u, :seg.utterances.lengths[u]].copy() for u in range(seg.utterances.D)]
-    return dt, totals, bounds, [list(map(int, ks)) for _, ks in plan]
+    totals, _, _ = _cpu_phase1(P["ns"], seg)
+    return time.perf_counter() - t0, totals
+
+
+def cpu_sample(n_utt, K):
+    """The CPU-reproducible head of rank 0's shard (its first n_utt <= CPU_SAMPLE_UTTS utterances):
+    structure, embeddings and the generating centres (the model both arms score against)."""
+    lengths, seg_id, seg_dur, _, n_emb = corpus_structure(CPU_SAMPLE_UTTS, seed=999)
+    centres = centres_cpu(K)
+    X, z = sample_rows_cpu(n_emb, centres, seed=3000)
+    n_utt = min(n_utt, CPU_SAMPLE_UTTS)
+    n_pos = int(np.sum(lengths[:n_utt]))
+    ids = seg_id[:n_pos]
+    e_hi = int(ids.max()) + 1
+    return lengths[:n_utt], ids, seg_dur[:n_pos], X[:e_hi], z[:e_hi], centres
 
 
 def run_reference_arm(args):
-    """--impl reference: the oracle port (kind "port": the reference is Python 2 and cannot be
-    shipped or imported on the GPU box) on all host cores, one process per core."""
+    """--impl reference: the reference's own CPU implementation of the path (baseline/_ref; kind "reference";
+    the oracle port, kind "port", only where that directory is missing) on all host cores, one process per
+    core, on the head of the SAME seeded corpus the GPU arm uses (rank 0's first utterances) against the
+    K-component model of the generating centres."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    kind, _ = cpu_modules()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_core = 2
-    n_utt = cores * per_core
-    lengths, seg_id, seg_dur, _, n_emb = corpus_structure(n_utt, seed=777)
-    rng = np.random.RandomState(5)
-    centres = rng.standard_normal((args.K, D)).astype(np.float32)
-    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
-    z = rng.randint(0, args.K, n_emb)
-    X = centres[z] + NOISE * rng.standard_normal((n_emb, D)).astype(np.float32)
-    X = (X / np.linalg.norm(X, axis=1, keepdims=True)).astype(np.float32)
-    pos_off = np.concatenate([[0], np.cumsum(lengths)])
-    jobs = []
-    for c in range(cores):
-        us = range(c * per_core, (c + 1) * per_core)
-        lo, hi = pos_off[us[0]], pos_off[us[-1] + 1]
-        ids = seg_id[lo:hi]
-        e_lo, e_hi = ids[ids >= 0].min(), ids[ids >= 0].max() + 1
-        sub_ids = np.where(ids >= 0, ids - e_lo, -1)
-        jobs.append((X[e_lo:e_hi], lengths[us[0]:us[-1] + 1], sub_ids, seg_dur[lo:hi], centres))
+    n_utt = min(cores * per_core, CPU_SAMPLE_UTTS)
+    lengths, seg_id, seg_dur, X, _, centres = cpu_sample(n_utt, args.K)
     ctx = mp.get_context("fork")
 
     def run_pool(n_proc, n_iter):
+        per = -(-n_utt // n_proc)
+        spans = [(lo, min(n_utt, lo + per)) for lo in range(0, n_utt, per)]
         out = []
-        with ctx.Pool(n_proc) as pool:
+        with ctx.Pool(n_proc, initializer=_pool_init, initargs=(X, lengths, seg_id, seg_dur, centres)) as pool:
             for _ in range(n_iter):
                 t0 = time.perf_counter()
-                pool.map(_cpu_worker, jobs)
+                pool.map(_pool_job, spans)
                 out.append(time.perf_counter() - t0)
         return out
-    # NumPy's large temporaries make the port memory-bound; on some hosts fewer processes than
+    # NumPy's large temporaries make the CPU path memory-bound; on some hosts fewer processes than
     # cores are faster.  Calibrate once (untimed) and use the best process count.
-    calib = {n: run_pool(n, 2)[1] for n in sorted({1, max(1, cores // 2), cores})}   # 2nd pass: imports warm
+    calib = {n: run_pool(n, 2)[1] for n in sorted({1, max(1, cores // 2), min(cores, n_utt)})}   # 2nd pass: imports warm
     used = min(calib, key=calib.get)
     times = run_pool(used, args.warmup + args.steps)[args.warmup:]
     per_step = float(np.mean(times))
@@ -270,10 +359,14 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "K": args.K, "D": D, "max_span": S_MAX,
-                   "sample": "%d utterances per step (2 per core) scored against the full K=%d model" % (n_utt, args.K)},
-        "cpu_baseline": {"value": value, "unit": "utt/s", "cores": used, "kind": "port",
-                         "sample": "%d utterances per step, %d processes (host has %d cores; calibration s/step: %s)"
-                                   % (n_utt, used, cores, {k: round(v, 2) for k, v in calib.items()})},
+                   "sample": "the first %d utterances of the GPU arm's corpus (rank 0, same seeds) per step, scored "
+                             "against the full K=%d model" % (n_utt, args.K)},
+        "cpu_baseline": {"value": value, "unit": "utt/s", "cores": used, "kind": kind,
+                         "sample": "%d utterances per step, %d processes (host has %d cores; calibration s/step: %s); "
+                                   "%s" % (n_utt, used, cores, {k: round(v, 2) for k, v in calib.items()},
+                                           "kamperh/segmentalist's own classes and functions from baseline/_ref "
+                                           "(py2->py3 text shim, numerics untouched)" if kind == "reference"
+                                           else "oracle port (baseline/_ref missing)")},
         "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -482,17 +575,376 @@ def run_bigram_extra(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
-def run_ours(args):
+# ------------------------------------------------------------------------------------------------
+# helpers of the GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def _checksum(t):
+    """Order-sensitive 64-bit checksum of a tensor's bits (device, no host copy of the data)."""
+    import torch
+    v = t.contiguous().view(torch.uint8).to(torch.int64)
+    w = (torch.arange(v.numel(), device=v.device, dtype=torch.int64) % 65521) + 1
+    return torch.stack([v.sum(), (v * w).sum()])
+
+
+def _sub_corpus(lengths, seg_id, seg_dur, bounds0, lo_u, hi_u):
+    """Utterances [lo_u, hi_u) of a flat corpus with embedding ids rebased to the shard."""
+    pos_off = np.concatenate([[0], np.cumsum(lengths)])
+    p0, p1 = int(pos_off[lo_u]), int(pos_off[hi_u])
+    ids = seg_id[p0:p1]
+    e_lo, e_hi = int(ids[ids >= 0].min()), int(ids.max()) + 1
+    return lengths[lo_u:hi_u], np.where(ids >= 0, ids - e_lo, -1).astype(np.int32), seg_dur[p0:p1], bounds0[p0:p1], p0, p1, e_lo, e_hi
+
+
+def multi_gpu_parity(args, world, rank, dev, sweep, comps):
+    """(a) after the sweeps' all-reduce every rank holds bit-identical means / numerators / counts;
+    (b) an N-rank sweep over a small fixed corpus equals the 1-rank sweep of the same corpus: k-means
+    (means bit for bit, boundaries, assignments; the initial model is diffuse, so inactive slots win tokens
+    and the device clamp / compaction run across ranks) and the frozen FBGMM sweep (decisions identical,
+    statistics to 1e-13)."""
+    import torch
+    import torch.distributed as dist
+    from segmentalist_b200 import sharding
+    from segmentalist_b200.batch import FrozenFBGMMSweep, FrozenKMeansSweep
+    from segmentalist_b200.gaussian_components_fixedvar import FixedVarPrior, GaussianComponentsFixedVar
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    from segmentalist_b200.utterances import DeviceCorpus
+    out = {}
+    if comps is not None:
+        cs = torch.cat([_checksum(comps._means), _checksum(comps._mean_num), _checksum(comps._counts)])
+        if world > 1:
+            allc = [torch.empty_like(cs) for _ in range(world)]
+            dist.all_gather(allc, cs)
+            out["means_identical_across_ranks"] = bool(all(torch.equal(a, allc[0]) for a in allc))
+        else:
+            out["means_identical_across_ranks"] = True
+
+    # ---- small fixed corpus, identical on every rank
+    U_s, K_s, K_true = 1024, 256, 64
+    lengths, seg_id, seg_dur, bounds0, n_emb = corpus_structure(U_s, seed=4242)
+    centres = torch.from_numpy(centres_cpu(K_true)).to(dev)
+    X, _ = make_embeddings_gpu(n_emb, centres, seed=4243, device=dev)
+    rnd = X[torch.arange(K_s, device=dev) * 37 % n_emb].clone()
+    var = 0.002 * np.ones(D)
+    n_pos = int(lengths.sum())
+    g = torch.Generator(device=dev).manual_seed(99)
+    uni = [(torch.rand(n_pos, dtype=torch.float64, device=dev, generator=g),
+            torch.rand(n_pos, dtype=torch.float64, device=dev, generator=g)) for _ in range(2)]
+
+    def run(lo_u, hi_u, local):
+        ln, ids, dur, b0, p0, p1, e_lo, e_hi = _sub_corpus(lengths, seg_id, seg_dur, bounds0, lo_u, hi_u)
+        Xs = X[e_lo:e_hi].contiguous()
+        res = {}
+        ctx = sharding.local_only() if local else None
+        if ctx:
+            ctx.__enter__()
+        try:
+            # k-means: diffuse initial model (token i -> component (global id * 7919) % K_s)
+            corpus = DeviceCorpus(ln, ids, dur, b0, 0, S_MAX, S_MAX)
+            c = KMeansComponents.from_device(Xs, K_s, rnd)
+            tok = corpus.tok_id[corpus.tok_id >= 0].long()
+            c._assign[tok] = (((tok + e_lo) * 7919) % K_s).to(torch.int32)
+            sw = FrozenKMeansSweep(c, corpus, wip=0.0, scorer="mma")
+            sw.init_means_from_assignments()
+            tot = [sw.sweep() for _ in range(3)]
+            res["km"] = (c._means.clone(), corpus.bounds.clone(), c._assign.clone(), int(c._K.item()), tot)
+            # frozen FBGMM sweep (FFBS + sampled components), trained-like start
+            corpus2 = DeviceCorpus(ln, ids, dur, b0, 0, S_MAX, S_MAX)
+            f = GaussianComponentsFixedVar.from_device(Xs, FixedVarPrior(var, np.zeros(D), var / 0.05), K_s, alpha=10., lms=1.0)
+            tok = corpus2.tok_id[corpus2.tok_id >= 0].long()
+            f._assign[tok] = (((tok + e_lo) * 7919) % K_s).to(torch.int32)
+            fs = FrozenFBGMMSweep(f, corpus2, fb_type="standard")
+            fs.init_from_assignments()
+            tot2 = [fs.sweep(u[0][p0:p1].contiguous(), u[1][p0:p1].contiguous()) for u in uni]
+            res["fb"] = (f._mu_NT.clone(), corpus2.bounds.clone(), f._assign.clone(), int(f._K.item()), tot2,
+                         f._counts.clone())
+        finally:
+            if ctx:
+                ctx.__exit__(None, None, None)
+        return res, (p0, p1, e_lo, e_hi)
+
+    full, _ = run(0, U_s, True)
+    lo_u, hi_u = sharding.shard_ranges(U_s, world)[rank]
+    part, (p0, p1, e_lo, e_hi) = run(lo_u, hi_u, False)
+    km_f, km_p = full["km"], part["km"]
+    ok_km = (torch.equal(km_f[0], km_p[0]) and torch.equal(km_f[1][p0:p1], km_p[1]) and
+             torch.equal(km_f[2][e_lo:e_hi], km_p[2]) and km_f[3] == km_p[3] and
+             all(abs(a - b) <= 1e-9 * abs(a) for a, b in zip(km_f[4], km_p[4])))
+    fb_f, fb_p = full["fb"], part["fb"]
+    ok_fb = (torch.equal(fb_f[1][p0:p1], fb_p[1]) and torch.equal(fb_f[2][e_lo:e_hi], fb_p[2]) and fb_f[3] == fb_p[3] and
+             torch.equal(fb_f[5], fb_p[5]) and
+             bool(torch.allclose(fb_f[0], fb_p[0], rtol=1e-13, atol=1e-300)) and
+             all(abs(a - b) <= 1e-9 * abs(a) for a, b in zip(fb_f[4], fb_p[4])))
+    flags = torch.tensor([int(ok_km), int(ok_fb)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    out["nrank_equals_1rank_kmeans_small_corpus"] = bool(flags[0].item())
+    out["nrank_equals_1rank_fbgmm_small_corpus"] = bool(flags[1].item())
+    out["small_corpus"] = {"utterances": U_s, "K_max": K_s, "K_after_kmeans": km_f[3], "K_after_fbgmm": fb_f[3],
+                           "sweeps": 3, "note": "diffuse initial model: inactive-slot wins, device clamp and compaction across ranks"}
+    return out
+
+
+def fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed):
+    """FBGMM.log_marg_i of n rows x K_max slots on tensor cores: ONE fp16 tcgen05 pass (the filter GEMM)
+    + exact float64 refine, against a trained-like model (component = generating cluster)."""
+    import torch
+    from segmentalist_b200 import fbgmm as fbgmm_mod
+    from segmentalist_b200.batch import FvScorer
+    from segmentalist_b200.gaussian_components_fixedvar import FixedVarPrior, GaussianComponentsFixedVar
+    out = {}
+    for aniso in (False, True):
+        n_fv = min(M, (4 if not aniso else 1) * 1024 * 1024)
+        rng = np.random.RandomState(0)
+        var = 0.002 * (0.5 + rng.rand(D)) if aniso else 0.002 * np.ones(D)
+        var_0 = 0.04 * (0.5 + rng.rand(D)) if aniso else var / 0.05
+        am = fbgmm_mod.FBGMM.__new__(fbgmm_mod.FBGMM)
+        am.alpha, am.lms, am.covariance_type = 10., 1.0, "fixed"
+        am.components = GaussianComponentsFixedVar.from_device(X[:n_fv], FixedVarPrior(var, np.zeros(D), var_0),
+                                                               args.K, alpha=10., lms=1.0)
+        n_tok = min(n_fv, 20 * args.K)
+        zh = Z[:n_tok].cpu().numpy()
+        _, first = np.unique(zh, return_index=True)        # labels in order of first appearance
+        rank_of = np.empty(args.K, dtype=np.int64)
+        rank_of[zh[np.sort(first)]] = np.arange(len(first))
+        am.components._add_many(np.arange(n_tok), rank_of[zh])
+        fv = FvScorer(am.components)
+        fv.score()
+        t_pack, t_filter, t_refine = timed(fv.pack_model, 3), timed(fv.filter, 3), timed(fv.refine, 3)
+        fl = (4.0 if aniso else 2.0) * D * n_fv * args.K
+        ids = np.arange(n_tok, n_tok + 2048) if n_fv >= n_tok + 2048 else np.arange(min(2048, n_fv))
+        exact = am.log_marg_items(ids)
+        got = fv.log_marg[torch.from_numpy(ids).to(fv.log_marg.device)].cpu().numpy()
+        rel = float((np.abs(got - exact) / np.abs(exact)).max())
+        kp = 16 * ((D + (3 if aniso else 6) + 15) // 16) * (2 if aniso else 1)
+        r = {"kernel": "kmeans_filter_kernel<%s> as the log_marg_i filter (ONE fp16 tcgen05 pass, fp32 TMEM, top-3 chunk epilogue) "
+                       "+ fv_refine_kernel (exact float64 re-scoring of the kept components, logsumexp)" % ("9,2" if aniso else "9,1"),
+             "bound": "tensor", "achieved": fl / (t_filter * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+             "frac": fl / (t_filter * 1e-3) / 1e12 / peak_tf, "peak_source": peak_src,
+             "kernel_ms": t_filter, "refine_ms": t_refine, "pack_model_ms": t_pack,
+             "frac_incl_refine_and_pack": fl / ((t_filter + t_refine + t_pack) * 1e-3) / 1e12 / peak_tf,
+             "rows": n_fv, "K": args.K, "K_active": am.components.K, "anisotropic_variances": aniso,
+             "algorithmic_flops_per_launch": fl,
+             "algorithmic_flops_note": "%d*D per segment x component evaluation (SURVEY 8d)" % (4 if aniso else 2),
+             "executed_tflops": 2.0 * kp * n_fv * 128 * ((args.K + 1 + 127) // 128) / (t_filter * 1e-3) / 1e12,
+             "fallback_rows": int(fv.n_fallback.item()), "max_rel_err_vs_exact_float64": rel,
+             "threshold_nats": fv.T}
+        if not aniso:
+            tr = ncu_traffic("fv_filter_kernel")
+            r["traffic"] = tr["bytes_per_launch"] if (tr and args.K == K_MAX and n_fv == 4 * 1024 * 1024) else None
+            r["traffic_source"] = tr.get("source") if tr else None
+            r["algorithmic_bytes_per_launch"] = float(fv.x_tiles.numel() + fv.cand.numel())
+            out = r
+        else:
+            out["anisotropic"] = r
+        del fv, am
+    return out
+
+
+def fbgmm_frozen_secondary(args, world, rank, dev, X, Z, corpus, lengths, seg_id, seg_dur, n_head, peak_tf, barrier,
+                           max_over_ranks):
+    """The sharded frozen-model sweep of the unigram FBGMM segmenter (UnigramAcousticWordseg.segment_frozen's
+    engine) on the SAME corpus as the headline: tensor-core log_marg_i -> banded scores -> batched FFBS ->
+    sampled components -> one all-reduce of [sum_x | counts] -> closed-form rebuild.  Device time, max over
+    ranks; CPU-oracle parity on the head of rank 0's shard."""
     import torch
     import torch.distributed as dist
     from segmentalist_b200 import _lib
+    from segmentalist_b200.batch import FrozenFBGMMSweep
+    from segmentalist_b200.gaussian_components_fixedvar import FixedVarPrior, GaussianComponentsFixedVar
+    var = 0.002 * np.ones(D)
+    comps = GaussianComponentsFixedVar.from_device(X, FixedVarPrior(var, np.zeros(D), var / 0.05), args.K, alpha=10., lms=1.0)
+    sweep = FrozenFBGMMSweep(comps, corpus, fb_type="standard", time_power_term=1.0, wip=0.0)
+    _lib.check(_lib.lib().segb_tokens_from_bounds(corpus.struct(), 0, corpus.n_utt, _lib.stream_ptr()))
+    tok = corpus.tok_id[corpus.tok_id >= 0].long()
+    comps._assign.fill_(-1)
+    comps._assign[tok] = Z[tok]
+    sweep.init_from_assignments()
+    n_pos = corpus.n_pos
+    g = torch.Generator(device=dev).manual_seed(500 + rank)
+
+    def uniforms():
+        return (torch.rand(n_pos, dtype=torch.float64, device=dev, generator=g),
+                torch.rand(n_pos, dtype=torch.float64, device=dev, generator=g))
+    for _ in range(2):
+        sweep.sweep(*uniforms())
+    barrier()
+    steps = max(2, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fb = 0
+    for _ in range(steps):
+        sweep.sweep(*uniforms())
+        fb += sweep.last_fallback
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    phases = sweep.profile_phases(*uniforms())
+    out = {"workload": "unigram_fbgmm_frozen_sweep D=130 K=%d U=%d max_span=6 FFBS + sampled components, sharded x%d"
+                       % (args.K, args.utts, world),
+           "utt_per_s": args.utts / (ms * 1e-3), "ms_per_sweep": ms, "n_gpus": world, "K_active": sweep.K_host,
+           "fallback_rows_per_sweep": fb / steps, "phases_ms": phases,
+           "segment_component_evals_per_s": float(X.shape[0]) * args.K * world / (ms * 1e-3), "dtype": "f64 scores (fp16 tensor filter + float64 refine)"}
+    # ---- CPU oracle on the head of rank 0's shard: same model state, same uniforms
+    if rank == 0 and not args.no_cpu and n_head:
+        from oracle import seg_oracle as so
+        n_s = min(16, corpus.n_utt)
+        hi = int(corpus.pos_off_h[n_s])
+        ids = seg_id[:hi]
+        e_hi = int(ids.max()) + 1
+        oc = so.FixedVarComponents.__new__(so.FixedVarComponents)
+        oc.X = X[:e_hi].cpu().numpy()
+        oc.N, oc.D, oc.K_max, oc.K = e_hi, D, args.K, comps.K
+        oc.precision, oc.mu_0, oc.precision_0 = comps.precision, comps.mu_0, comps.precision_0
+        oc.mu_N_numerators, oc.precision_Ns = comps.mu_N_numerators, comps.precision_Ns
+        oc.precision_preds, oc.log_prod_precision_preds = comps.precision_preds, comps.log_prod_precision_preds
+        oc.counts, oc.lm = comps.counts, None
+        oc.neg_half_D_log_2pi = -0.5 * D * np.log(2. * np.pi)
+        oc.assignments = -1 * np.ones(e_hi, dtype=np.int64)
+        am = so.FBGMM.__new__(so.FBGMM)
+        am.alpha, am.lms, am.covariance_type, am.components, am.prior = 10., 1.0, "fixed", oc, None
+        oseg = so.UnigramAcousticWordseg.__new__(so.UnigramAcousticWordseg)
+        oseg.utterances = _cpu_segmenter(so, oc.X, lengths[:n_s], ids, seg_dur[:hi], np.zeros((1, D), np.float32)).utterances
+        oseg.acoustic_model, oseg.fb_type = am, "standard"
+        oseg.n_slices_min, oseg.n_slices_max, oseg.wip, oseg.time_power_term, oseg.beta_sent_boundary = 0, S_MAX, 0.0, 1.0, -1
+        u_fb, u_as = uniforms()
+        sweep.sweep(u_fb, u_as)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lps, choices = so.frozen_fbgmm_phase1(oseg, u_fb[:hi].cpu().numpy(), u_as[:hi].cpu().numpy(), range(n_s))
+        dt = time.perf_counter() - t0
+        gpu_b = corpus.bounds[:hi].cpu().numpy().astype(bool)
+        cpu_b = np.concatenate([oseg.utterances.boundaries[u, :lengths[u]] for u in range(n_s)])
+        gpu_choice = sweep.choice.cpu().numpy()
+        gpu_lp = sweep.log_prob[:n_s].cpu().numpy()
+        same = bool(np.array_equal(gpu_b, cpu_b) and all(int(gpu_choice[e]) == j for e, j in choices) and
+                    np.allclose(gpu_lp, np.asarray(lps), rtol=1e-9))
+        out["cpu_baseline"] = {"value": n_s / dt, "unit": "utt/s", "cores": 1, "kind": "port",
+                               "sample": "the first %d utterances of rank 0's shard: get_vec_embed_log_probs + forward_backward + "
+                                         "component draws of the oracle against the full K=%d model" % (n_s, args.K),
+                               "seconds": dt, "identical_decisions_on_sample": same}
+    return out
+
+
+def kmeans_diffuse_secondary(args, world, rank, dev, barrier, max_over_ranks):
+    """The hard case for the filter and for the host-free update: K_true = 200 generating clusters, K_max =
+    5000 components initialised "spread" (token t -> component t mod K): a diffuse model, components dying
+    (K_act < K_max), inactive slots (random data rows) winning tokens, undecided rows.  Three untimed sweeps
+    (the first ones are dominated by exhaustive scans of the flat initial model), then timed sweeps; device
+    time, max over ranks; CPU parity (raw argmax incl. inactive-slot wins, boundaries) on rank 0's first
+    utterances."""
+    import torch
+    import torch.distributed as dist
     from segmentalist_b200.batch import FrozenKMeansSweep
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    from segmentalist_b200.utterances import DeviceCorpus
+    total = args.diffuse_utts
+    n_utt = total // world + (1 if rank < total % world else 0)
+    lengths, seg_id, seg_dur, bounds0, n_emb = corpus_structure(n_utt, seed=7000 + rank)
+    centres = torch.from_numpy(centres_cpu(200)).to(dev)
+    X, _ = make_embeddings_gpu(n_emb, centres, seed=7100 + rank, device=dev)
+    corpus = DeviceCorpus(lengths, seg_id, seg_dur, bounds0, 0, S_MAX, S_MAX)
+    rnd = X[torch.randperm(n_emb, device=dev, generator=torch.Generator(device=dev).manual_seed(8))[:args.K]].clone()
+    if world > 1:
+        dist.broadcast(rnd, src=0)
+    comps = KMeansComponents.from_device(X, args.K, rnd)
+    tok = corpus.tok_id[corpus.tok_id >= 0].long()
+    comps._assign[tok] = ((torch.arange(tok.numel(), device=dev) + 1000003 * rank) % args.K).to(torch.int32)
+    sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer="mma")
+    sweep.init_means_from_assignments()
+    traj = []
+    for _ in range(3):
+        sweep.sweep()
+        traj.append((sweep.K_host, sweep.last_fallback))
+    barrier()
+    steps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sweep.sweep()
+        traj.append((sweep.K_host, sweep.last_fallback))
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    out = {"workload": "kmeans_viterbi_frozen_sweep, diffuse model: D=130 K_max=%d K_true=200 U=%d spread init, sharded x%d"
+                       % (args.K, total, world),
+           "utt_per_s": total / (ms * 1e-3), "ms_per_sweep": ms, "n_gpus": world,
+           "K_active_and_fallback_rows_per_sweep_rank0": traj, "phases_ms": sweep.profile_phases(),
+           "note": "clamp of inactive-slot winners and clean_components run as device kernels (csrc/frozen.cu), "
+                   "lists exchanged with a fixed-size all-gather; no host logic per sweep"}
+    if rank == 0 and not args.no_cpu:
+        kind, ns = cpu_modules()
+        n_s = min(8, corpus.n_utt)
+        hi = int(corpus.pos_off_h[n_s])
+        ids = seg_id[:hi]
+        e_hi = int(ids.max()) + 1
+        means_now = comps._means.cpu().numpy()
+        sweep.score()
+        sweep.segment()
+        torch.cuda.synchronize()
+        gpu_bounds = corpus.bounds[:hi].cpu().numpy().astype(bool)
+        gpu_k = sweep.best_k[:e_hi].cpu().numpy()
+        seg = _cpu_segmenter(ns, X[:e_hi].cpu().numpy(), lengths[:n_s], ids, seg_dur[:hi], means_now)
+        _, bounds, ks = _cpu_phase1(ns, seg)
+        same = bool(np.array_equal(np.concatenate(bounds), gpu_bounds))
+        n_inactive = 0
+        for u in range(n_s):
+            emb = seg.utterances.get_segmented_embeds_i(u)
+            same = same and [int(gpu_k[e]) for e in emb] == ks[u]
+            n_inactive += sum(1 for k in ks[u] if k >= sweep.K_host)
+        out["parity_with_cpu_on_sample"] = {"identical": same, "kind": kind, "utterances": n_s,
+                                            "tokens_won_by_inactive_slots": n_inactive, "K_active": sweep.K_host}
+    return out
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU (and let first-touch place the pinned
+    staging buffers on that NUMA node).  At 4-8 ranks the end-to-end path is host-bound: in round 1 every
+    rank ran on NUMA node 0's cores with its pinned buffers wherever the process had landed.  Best effort:
+    a cpuset that excludes the GPU's node leaves the affinity unchanged."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        ideal = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = ideal & allowed
+        info.update(gpu_local_cpus=len(ideal), allowed_cpus=len(allowed), usable=len(use))
+        if use:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+            info["cpus"] = "%d-%d" % (min(use), max(use))
+    except Exception as exc:
+        info["error"] = repr(exc)
+    return info
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the committed
+    ncu capture (profiles/r2_ncu_traffic.json: written by tools/summarize_ncu.py from the .ncu-rep of this
+    command at the default configuration), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        return d.get(kernel)
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from segmentalist_b200 import _lib, sharding
+    from segmentalist_b200.batch import FrozenFBGMMSweep, FrozenKMeansSweep, FvScorer
     from segmentalist_b200.kmeans_components import KMeansComponents
     from segmentalist_b200.utterances import DeviceCorpus
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -504,10 +956,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- this rank's shard (strong scaling: args.utts in total)
+    def max_over_ranks(v):
+        t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- this rank's shard (strong scaling: args.utts in total).  Centres come from NumPy (shared by all
+    # ranks and by the CPU arms); rank 0's first CPU_SAMPLE_UTTS utterances are generated on the CPU.
     n_utt = args.utts // world + (1 if rank < args.utts % world else 0)
-    lengths, seg_id, seg_dur, bounds0, n_emb = corpus_structure(n_utt, seed=1000 + rank)
-    X, centres, Z = make_embeddings_gpu(n_emb, args.K, seed=2000 + rank, device=dev)
+    lengths, seg_id, seg_dur, bounds0, n_emb, n_head = shard_structure(n_utt, rank)
+    centres_h = centres_cpu(args.K)
+    X, Z = make_embeddings_gpu(n_emb, torch.from_numpy(centres_h).to(dev), seed=2000 + rank, device=dev)
+    if n_head:
+        Xh, zh = sample_rows_cpu(n_head, centres_h, seed=3000)
+        X[:n_head] = torch.from_numpy(Xh).to(dev)
+        Z[:n_head] = torch.from_numpy(zh).to(dev)
     corpus = DeviceCorpus(lengths, seg_id, seg_dur, bounds0, 0, S_MAX, S_MAX)
     perm = torch.randperm(n_emb, device=dev, generator=torch.Generator(device=dev).manual_seed(7))[:args.K]
     rnd = X[perm].clone()
@@ -515,21 +989,16 @@ def run_ours(args):
         dist.broadcast(rnd, src=0)
     comps = KMeansComponents.from_device(X, args.K, rnd)
     # initial model: every token starts in the component of its generating cluster, so all K_max
-    # components are populated and stay alive (K_act = K_max -- otherwise the inactive
-    # slots, which hold random data rows, win tokens and the benchmark measures host-side
-    # clamp/compaction logic instead of the scoring + DP path)
+    # components are populated and stay alive (K_act = K_max); the diffuse case (K_act < K_max,
+    # inactive slots winning tokens, undecided rows) is measured separately below (secondary_kmeans_diffuse)
     tok = corpus.tok_id[corpus.tok_id >= 0].long()
     comps._assign[tok] = Z[tok]
-    del Z
     sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer)
     sweep.init_means_from_assignments()
     n_pos, M = corpus.n_pos, n_emb
     evals_per_sweep_local = float(M) * args.K
 
     # ---- warm-up + timed region (device time, max over ranks)
-    # nvidia-smi clock / throttle sampling: started before the warm-up sweeps and stopped after the
-    # kernel-alone timings below, so that short timed regions (25 ms at 8 GPUs) still get samples;
-    # every sampled interval is under load
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         sweep.sweep()
@@ -545,15 +1014,20 @@ def run_ours(args):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = lib.segb_launch_count() - launches0
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     tot = torch.tensor([evals_per_sweep_local, float(M), float(fallback)], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(elapsed_ms)
     ms_per_step = elapsed_ms / args.steps
     value = args.utts / (ms_per_step * 1e-3)
     evals_per_s = float(tot[0].item()) / (ms_per_step * 1e-3)
+
+    # ---- multi-GPU parity gates (every N; trivially true at N = 1)
+    parity = {}
+    try:
+        parity = multi_gpu_parity(args, world, rank, dev, sweep, comps)
+    except Exception as exc:
+        parity = {"error": repr(exc)}
 
     # ---- dominant kernel alone: tcgen05 filter GEMM (tensor roofline) and the DP kernel (HBM roofline)
     peaks = {}
@@ -566,92 +1040,65 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json, bf16 dense burst)" if "bf16_tflops" in peaks else "fallback"
     roofline, roofline_dp = None, None
     phases = sweep.profile_phases()
+    default_cfg = (world == 1 and args.utts == TOTAL_UTTS and args.K == K_MAX)
     if rank == 0:
-        reps = 5
         sp = _lib.stream_ptr()
         if args.scorer == "mma":
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             sweep.mma.filter()
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                sweep.mma.filter()
-            e1.record()
-            torch.cuda.synchronize()
-            k_ms = e0.elapsed_time(e1) / reps
+            k_ms = timed(sweep.mma.filter, 5)
             flops = 2.0 * D * M * args.K                  # algorithmic: 2*D per segment x component eval
             ach = flops / (k_ms * 1e-3) / 1e12
+            tr = ncu_traffic("kmeans_filter_kernel") if default_cfg else None
             roofline = {"kernel": "kmeans_filter_kernel (tcgen05 fp16 -> fp32 TMEM, fused top-3 epilogue)",
                         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": ach / peak_tf,
-                        "traffic": NCU_TRAFFIC_BYTES["filter"] if (world == 1 and args.utts == TOTAL_UTTS and args.K == K_MAX) else None,
-                        "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_ncu_summary_v4.md)",
+                        "traffic": tr["bytes_per_launch"] if tr else None,
+                        "traffic_source": tr.get("source") if tr else None,
+                        "algorithmic_bytes_per_launch": float(sweep.mma.x_tiles.numel() + sweep.mma.cand.numel()),
                         "peak_source": peak_src,
                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops}
         cs = corpus.struct()
-        # a 50 us kernel: 20 launches timed one by one (CUDA events around each), median reported.  The filter
-        # launches above leave the GPU at its power-capped clock (~1.5 GHz); the DP is bound by float64
-        # compare throughput, so its time follows the SM clock -- both the time right after the GEMMs
-        # ("under_load") and after a one-second pause (clocks recovered) are given.
-        def time_dp(reps=20):
+
+        def time_dp(mode, reps=20, u=None):
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
             torch.cuda.synchronize()
             for a, b_ in evs:
                 a.record()
-                _lib.check(lib.segb_dp_banded(cs, 0, corpus.n_utt, _lib.ptr(sweep.scores), _lib.DP_VITERBI_KMEANS, 0.0,
-                                              1.0, None, None, _lib.ptr(corpus.bounds), _lib.ptr(sweep.log_prob), None,
+                _lib.check(lib.segb_dp_banded(cs, 0, corpus.n_utt, _lib.ptr(sweep.scores), mode, 0.0,
+                                              1.0, _lib.ptr(u), None, _lib.ptr(corpus.bounds), _lib.ptr(sweep.log_prob), None,
                                               None, _lib.ptr(sweep.status), sp))
                 b_.record()
             torch.cuda.synchronize()
             ts = sorted(a.elapsed_time(b_) for a, b_ in evs)
             return ts[len(ts) // 2], ts[0]
-        dp_ms_load, _ = time_dp()
+        dp_ms_load, _ = time_dp(_lib.DP_VITERBI_KMEANS)
         time.sleep(1.0)
-        dp_ms, dp_ms_best = time_dp()
+        dp_ms, dp_ms_best = time_dp(_lib.DP_VITERBI_KMEANS)
+        u_dp = torch.rand(n_pos, dtype=torch.float64, device=dev)
+        ffbs_ms, _ = time_dp(_lib.DP_FFBS, reps=5, u=u_dp)
+        sweep.segment()                                        # leave Viterbi boundaries behind
         dp_bytes = 8.0 * n_pos * S_MAX + n_pos + 8.0 * corpus.n_utt + 8.0 * (corpus.n_utt + 1) + 4.0 * corpus.n_utt
+        tr = ncu_traffic("dp_staged_kernel") if default_cfg else None
         roofline_dp = {"kernel": "dp_staged_kernel (Viterbi, float64 banded scores, cp.async.bulk staging, thread per utterance)", "bound": "hbm",
                        "achieved": dp_bytes / (dp_ms * 1e-3) / 1e9, "peak": peak_bw, "unit": "GB/s",
                        "frac": dp_bytes / (dp_ms * 1e-3) / 1e9 / peak_bw,
-                       "traffic": NCU_TRAFFIC_BYTES["dp"] if (world == 1 and args.utts == TOTAL_UTTS) else None,
+                       "frac_under_load": dp_bytes / (dp_ms_load * 1e-3) / 1e9 / peak_bw,
+                       "traffic": tr["bytes_per_launch"] if tr else None,
+                       "traffic_source": tr.get("source") if tr else None,
                        "kernel_ms": dp_ms, "kernel_ms_best": dp_ms_best, "kernel_ms_under_load": dp_ms_load,
+                       "ffbs_kernel_ms": ffbs_ms, "ffbs_frac": (dp_bytes + 8.0 * n_pos) / (ffbs_ms * 1e-3) / 1e9 / peak_bw,
                        "timing": "median of 20 individually timed launches after a 1 s pause; under_load = same, "
-                                 "immediately after the back-to-back filter launches (power-capped SM clock)",
+                                 "immediately after the back-to-back filter launches (power-capped SM clock); "
+                                 "ffbs = the batched forward-filter backward-sample variant (exp/log bound)",
                        "algorithmic_bytes_per_launch": dp_bytes}
 
-    # ---- the other scoring kernel: FBGMM log_marg_i as an FP32-accurate tcgen05 GEMM + fused logsumexp
+    # ---- the other scoring kernel: FBGMM log_marg_i, ONE fp16 tcgen05 pass + exact float64 refine
     roofline_fv = None
     if rank == 0 and args.scorer == "mma":
-        from segmentalist_b200 import fbgmm as fbgmm_mod
-        from segmentalist_b200.gaussian_components_fixedvar import FixedVarPrior, GaussianComponentsFixedVar
-        n_fv = min(M, 4 * 1024 * 1024)
-        var = 0.002 * np.ones(D)
-        am = fbgmm_mod.FBGMM.__new__(fbgmm_mod.FBGMM)
-        am.alpha, am.lms, am.covariance_type = 10., 1.0, "fixed"
-        am.components = GaussianComponentsFixedVar.from_device(X[:n_fv], FixedVarPrior(var, np.zeros(D), var / 0.05),
-                                                               args.K, alpha=10., lms=1.0)
-        n_tok = 4 * args.K
-        am.components._add_many(np.arange(n_tok), np.arange(n_tok) % args.K)
-        am.log_marg_all(tensor_cores=True)                      # packs X, warms up
-        x_t, w_t, out_t = am._tc
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            _lib.check(lib.segb_fvmma_log_marg(am.components.struct(), _lib.ptr(x_t), _lib.ptr(w_t), n_fv,
-                                               _lib.ptr(out_t), _lib.stream_ptr()))
-        e1.record()
-        torch.cuda.synchronize()
-        fv_ms = e0.elapsed_time(e1) / 3
-        fl = 2.0 * D * n_fv * args.K
-        roofline_fv = {"kernel": "fv_logmarg_kernel (tcgen05 fp16 hi/lo split x3 passes -> fp32 TMEM, fused online logsumexp)",
-                       "bound": "tensor", "achieved": fl / (fv_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                       "frac": fl / (fv_ms * 1e-3) / 1e12 / peak_tf,
-                       "traffic": NCU_TRAFFIC_BYTES["fv_logmarg_per_row"] * n_fv if args.K == K_MAX else None,
-                       "kernel_ms": fv_ms,
-                       "rows": n_fv, "K": args.K, "algorithmic_flops_per_launch": fl,
-                       "executed_tflops": fl / (fv_ms * 1e-3) / 1e12 * (3 * 16 * ((D + 6 + 15) // 16)) / D,
-                       "note": "FP32-accurate split = 3 tensor passes over the padded inner dimension (3*144/130 = 3.3 executed flops per algorithmic flop): algorithmic ceiling ~0.30 of peak; executed_tflops is what the tensor pipe actually did"}
-        del am
+        try:
+            roofline_fv = fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed)
+        except Exception as exc:
+            roofline_fv = {"error": repr(exc)}
 
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
@@ -692,46 +1139,63 @@ def run_ours(args):
         barrier()
         wall = (time.perf_counter() - t0) / n_e2e
         dev_ms = ev0.elapsed_time(ev1) / n_e2e
-        te = torch.tensor([max(wall * 1e3, dev_ms)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        te = max_over_ranks(max(wall * 1e3, dev_ms))
         h2d = X_host.numel() * 4 + means_host.numel() * 4
         d2h = bounds_host.numel() + assign_host.numel() * 4 + means_host.numel() * 4 + 8
-        e2e = {"value": args.utts / (float(te.item()) * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()),
-               "note": "per rank: pinned-host X (1M-row chunks on a copy stream, overlapped with fp16 tile packing + filter + refine) + means -> HBM, sweep, boundaries/assignments/means back"}
+        e2e = {"value": args.utts / (te * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": te, "numa": numa,
+               "note": "per rank: pinned-host X (1M-row chunks on a copy stream, overlapped with fp16 tile packing + filter + refine) + means -> HBM, sweep, boundaries/assignments/means back; each rank bound to its GPU's CPUs (numa)"}
+        del X_host
 
-    # ---- CPU baseline + parity gate on a bounded sample (rank 0)
+    # ---- CPU baseline + parity gate on the CPU-reproducible head of rank 0's shard
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu:
-        n_s = min(args.cpu_sample, corpus.n_utt)
+    if rank == 0 and not args.no_cpu and n_head:
+        kind, ns = cpu_modules()
+        n_s = min(args.cpu_sample, CPU_SAMPLE_UTTS, corpus.n_utt)
         hi = int(corpus.pos_off_h[n_s])
         ids = seg_id[:hi]
         e_hi = int(ids.max()) + 1
         means_now = comps._means.cpu().numpy()
-        # GPU answers for the same utterances under the same (current) means
-        sweep.score()
+        sweep.score()                                   # GPU answers for the same utterances, same means
         sweep.segment()
         torch.cuda.synchronize()
         gpu_bounds = corpus.bounds[:hi].cpu().numpy().astype(bool)
         gpu_tot = sweep.log_prob[:n_s].cpu().numpy()
         gpu_k = sweep.best_k[:e_hi].cpu().numpy()
-        dt, totals, bounds, ks = _cpu_worker((X[:e_hi].cpu().numpy(), lengths[:n_s], ids, seg_dur[:hi], means_now))
-        cpu_bounds = np.concatenate(bounds)
-        parity = bool(np.array_equal(cpu_bounds, gpu_bounds) and np.array_equal(np.asarray(totals), gpu_tot))
-        # chosen-segment assignments
-        seg = _oracle_segmenter(X[:e_hi].cpu().numpy(), lengths[:n_s], ids, seg_dur[:hi], means_now)
+        seg = _cpu_segmenter(ns, X[:e_hi].cpu().numpy(), lengths[:n_s], ids, seg_dur[:hi], means_now)
+        t0 = time.perf_counter()
+        totals, bounds, ks = _cpu_phase1(ns, seg)
+        dt = time.perf_counter() - t0
+        parity_cpu = bool(np.array_equal(np.concatenate(bounds), gpu_bounds) and np.array_equal(np.asarray(totals), gpu_tot))
         for u in range(n_s):
-            seg.utterances.boundaries[u, :lengths[u]] = bounds[u]
             emb = seg.utterances.get_segmented_embeds_i(u)
-            parity = parity and [int(gpu_k[e]) for e in emb] == ks[u]
-        cpu_baseline = {"value": n_s / dt, "unit": "utt/s", "cores": 1, "kind": "port",
-                        "sample": "%d utterances (%d candidate segments) of rank 0's shard vs the full K=%d model; "
-                                  "oracle port of the reference's pure functions" % (n_s, int((ids >= 0).sum()), args.K),
-                        "seconds": dt, "parity_with_gpu_on_sample": parity}
+            parity_cpu = parity_cpu and [int(gpu_k[e]) for e in emb] == ks[u]
+        cpu_baseline = {"value": n_s / dt, "unit": "utt/s", "cores": 1, "kind": kind,
+                        "sample": "the first %d utterances (%d candidate segments) of rank 0's shard vs the full K=%d model; %s"
+                                  % (n_s, int((ids >= 0).sum()), args.K,
+                                     "the reference's own functions (baseline/_ref)" if kind == "reference"
+                                     else "oracle port of the reference's pure functions"),
+                        "seconds": dt, "parity_with_gpu_on_sample": parity_cpu}
+
+    # ---- sharded FBGMM sweep (frozen-model UnigramAcousticWordseg mode): every N
+    fbgmm_frozen = None
+    if not args.no_fbgmm:
+        try:
+            fbgmm_frozen = fbgmm_frozen_secondary(args, world, rank, dev, X, Z, corpus, lengths, seg_id, seg_dur,
+                                                  n_head, peak_tf, barrier, max_over_ranks)
+        except Exception as exc:
+            fbgmm_frozen = {"error": repr(exc)}
+    diffuse = None
+    if not args.no_diffuse:
+        try:
+            diffuse = kmeans_diffuse_secondary(args, world, rank, dev, barrier, max_over_ranks)
+        except Exception as exc:
+            diffuse = {"error": repr(exc)}
 
     gibbs, diag_x, bigram_x = None, None, None
     if rank == 0 and world == 1 and not args.no_gibbs:
+        del sweep, comps
+        torch.cuda.empty_cache()
         try:
             bigram_x = run_bigram_extra(args)
         except Exception as exc:
@@ -745,6 +1209,10 @@ def run_ours(args):
         except Exception as exc:
             diag_x = {"error": repr(exc)}
     if rank == 0:
+        if roofline is not None:
+            # the driver keeps `roofline`: the other kernels' rooflines ride inside it
+            roofline["others"] = [r for r in (roofline_dp, roofline_fv) if r]
+            roofline["fallback_rows_per_sweep"] = float(tot[2].item()) / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -752,14 +1220,14 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "utterances": args.utts, "K": args.K, "D": D, "max_span": S_MAX,
                        "candidate_segments": int(tot[1].item()), "scorer": args.scorer,
                        "init": "tokens start in the component of their generating cluster (K_act = K_max)",
-                       "K_active": int(sweep.K_host),
                        "parallelism": "utterance shards x%d + NCCL all-reduce(sum_x, counts)" % world,
-                       "l2": "inputs (fp16 tile image %.1f GB per rank) exceed L2; no flush needed"
-                             % (sweep.mma.x_tiles.numel() / 1e9 if args.scorer == "mma" else X.numel() * 4 / 1e9)},
+                       "l2": "inputs (%.1f GB of embeddings per rank) exceed L2; no flush needed" % (X.numel() * 4 / 1e9)},
             "segment_component_evals_per_s": evals_per_s,
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "roofline_dp": roofline_dp, "roofline_fixedvar_logmarg": roofline_fv, "cpu_baseline": cpu_baseline, "phases_ms": phases,
+            "roofline_dp": roofline_dp, "roofline_fixedvar_logmarg": roofline_fv, "cpu_baseline": cpu_baseline,
+            "phases_ms": phases, "parity": parity,
+            "secondary_fbgmm_frozen": fbgmm_frozen, "secondary_kmeans_diffuse": diffuse,
             "secondary_gibbs_fixedvar": gibbs, "secondary_gibbs_diag": diag_x, "secondary_bigram": bigram_x,
         }
         print(json.dumps(line))

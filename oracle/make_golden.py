@@ -61,8 +61,17 @@ def shim_text(src, is_pyx=False):
     return s
 
 
-def build_shimmed_reference():
-    tmp = tempfile.mkdtemp(prefix="segref_")
+def build_shimmed_reference(target=None):
+    """Copy + shim + build the reference.  target=None: a throw-away temp directory (fixtures);
+    otherwise `target` (the git-ignored baseline/_ref, which travels to the GPU box like the built
+    .so files so that `bench.py --impl reference` can time the reference itself)."""
+    if target is None:
+        tmp = tempfile.mkdtemp(prefix="segref_")
+    else:
+        tmp = target
+        if os.path.isdir(tmp):
+            shutil.rmtree(tmp)
+        os.makedirs(tmp)
     pkg = os.path.join(tmp, "segmentalist")
     shutil.copytree(os.path.join(REF, "segmentalist"), pkg)
     files = [os.path.join(dp, fn) for dp, _, fns in os.walk(pkg) for fn in fns]
@@ -86,7 +95,9 @@ def build_shimmed_reference():
             "['segmentalist/_cython_utils.pyx'], include_dirs=[numpy.get_include()])],"
             "language_level=3))\n")
     subprocess.check_call([sys.executable, "setup.py", "-q", "build_ext", "--inplace"], cwd=tmp)
-    sys.path.insert(0, tmp)
+    shutil.rmtree(os.path.join(tmp, "build"), ignore_errors=True)
+    if target is None:
+        sys.path.insert(0, tmp)
     return tmp
 
 

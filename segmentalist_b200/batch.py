@@ -340,7 +340,8 @@ class FrozenKMeansSweep(object):
 # Frozen-state FBGMM sweep (fixed-variance components)
 # ---------------------------------------------------------------------------
 
-LSE_T = 25.0          # nats below the best component at which a component is dropped from log_marg_i's sum
+LSE_T = 20.0          # nats below the best component at which a component is dropped from log_marg_i's sum
+                      # (what is dropped is at most K_max * exp(-20) = 1e-5 of the sum for K_max = 5000)
 
 
 def _is_aniso(c):
@@ -469,6 +470,48 @@ class FrozenFBGMMSweep(object):
         c._assign.fill_(-1)
         _lib.check(lib.segb_fixedvar_frozen_update(c.struct(), cp.struct(), 0, cp.n_pos, _lib.ptr(self.choice),
                                                    _lib.ptr(self.sum_x), _lib.ptr(self.cnt), _lib.ptr(self.new_label), sp))
+
+    def init_from_assignments(self):
+        """Build the replicated model from the current (sharded) assignments of the current tokens
+        (labels 0..K-1, all in use): used once before the first distributed sweep."""
+        c, cp = self.c, self.corpus
+        self.choice.copy_(c._assign)
+        self.collect()
+        self.reduce_and_update()
+        self.K_host = int(c._K.item())
+
+    def profile_phases(self, u_fb=None, u_assign=None):
+        """Device time of each phase of one sweep (CUDA events on the launching stream); the model is
+        advanced exactly as by sweep().  Diagnostic for bench.py / profiles/."""
+        names, evs = [], [torch.cuda.Event(enable_timing=True)]
+        evs[0].record()
+
+        def mark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            names.append(name)
+            evs.append(e)
+        c = self.c
+        K_before = self.K_host if self.K_host is not None else c.K
+        self.fv.pack_model()
+        mark("pack_model")
+        self.fv.filter()
+        mark("filter_gemm")
+        self.fv.refine()
+        mark("refine_exact")
+        self.segment(u_fb)
+        mark("band_scores+dp+tokens")
+        self.choose(u_assign, K_before)
+        if K_before < c.K_max:
+            self.clamp.run(self.choice, K_before)
+        mark("choose_components")
+        self.collect()
+        mark("collect_tokens")
+        self.reduce_and_update()
+        mark("allreduce+rebuild")
+        torch.cuda.synchronize()
+        self.K_host = int(c._K.item())
+        return {n: evs[i].elapsed_time(evs[i + 1]) for i, n in enumerate(names)}
 
     def sweep(self, u_fb=None, u_assign=None):
         """One sweep.  u_fb / u_assign: float64 device arrays [n_pos] of uniforms (utterance u's i-th

@@ -37,23 +37,27 @@ __host__ __device__ inline int nch_of(int aniso) { return aniso ? 2 : 1; }
 static inline int64_t rows_pad(int64_t n) { return (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS; }
 static inline int w_rows_pad(int K_max) { return (K_max + 1 + NT_COLS - 1) / NT_COLS * NT_COLS; }   // +1: the virtual empty slot
 
-// Exact per-component tables read by the refine (row-major so one component is one contiguous row):
-//   mu [Kr][D] | P [Kr][D] (anisotropic only) | cst_lse [Kr] | cst_map [Kr] | pk [Kr]     Kr = K_max + 1
+// Exact per-component tables read by the refine (row-major so one component is one contiguous row) and,
+// transposed (component index fastest), by the exhaustive scan:
+//   mu [Kr][D] | P [Kr][D] (anisotropic only) | muT [D][Kr] | PT [D][Kr] (anisotropic only)
+//   | cst_lse [Kr] | cst_map [Kr] | pk [Kr]                                              Kr = K_max + 1
 // cst_lse = lms*pi_k - D/2 log 2pi + 1/2 sum_d log P_kd (+ log(K_max - K) on the virtual row);
 // cst_map = log(alpha/K_max + n_k) - D/2 log 2pi + 1/2 sum_d log P_kd   (map_assign_i: no lms, fbgmm.py:475-479).
 struct ModelRows {
-    const double *mu, *P, *cst_lse, *cst_map, *pk;
+    const double *mu, *P, *muT, *PT, *cst_lse, *cst_map, *pk;
 };
 __host__ __device__ inline int64_t model_doubles(int K_max, int D, int aniso) {
     const int64_t Kr = K_max + 1;
-    return Kr * D * (aniso ? 2 : 1) + 3 * Kr;
+    return 2 * Kr * D * (aniso ? 2 : 1) + 3 * Kr;
 }
 __host__ __device__ inline ModelRows model_view(const double *base, int K_max, int D, int aniso) {
-    const int64_t Kr = K_max + 1;
+    const int64_t Kr = K_max + 1, n = Kr * D;
     ModelRows r;
     r.mu = base;
-    r.P = aniso ? base + Kr * D : nullptr;
-    const double *q = base + Kr * D * (aniso ? 2 : 1);
+    r.P = aniso ? base + n : nullptr;
+    r.muT = base + n * (aniso ? 2 : 1);
+    r.PT = aniso ? r.muT + n : nullptr;
+    const double *q = base + 2 * n * (aniso ? 2 : 1);
     r.cst_lse = q; r.cst_map = q + Kr; r.pk = q + 2 * Kr;
     return r;
 }
@@ -144,7 +148,8 @@ __global__ void pack_w_kernel(segb_fixedvar m, int aniso, int rows_pad_, uint8_t
     const bool active = row < K, virt = (row == K && K < KM), alive = active || virt;
     const int64_t Kr = KM + 1;
     double *t_mu = rows, *t_P = aniso ? rows + Kr * D : nullptr;
-    double *t_lse = rows + Kr * D * (aniso ? 2 : 1), *t_map = t_lse + Kr, *t_pk = t_lse + 2 * Kr;
+    double *t_muT = rows + Kr * D * (aniso ? 2 : 1), *t_PT = aniso ? t_muT + Kr * D : nullptr;
+    double *t_lse = rows + 2 * Kr * D * (aniso ? 2 : 1), *t_map = t_lse + Kr, *t_pk = t_lse + 2 * Kr;
     const double c0 = -0.5 * D * log(2. * 3.14159265358979323846);
     double Ak = DEAD_A, p_iso = 0.0;
     if (alive) {
@@ -154,7 +159,8 @@ __global__ void pack_w_kernel(segb_fixedvar m, int aniso, int rows_pad_, uint8_t
             const double P = active ? m.prec_predT[(size_t)d * KM + row] : m.precision_0[d];
             pm2 += P * mu * mu;
             t_mu[(size_t)row * D + d] = mu;
-            if (aniso) t_P[(size_t)row * D + d] = P;
+            t_muT[(size_t)d * Kr + row] = mu;
+            if (aniso) { t_P[(size_t)row * D + d] = P; t_PT[(size_t)d * Kr + row] = P; }
         }
         for (int o = 16; o > 0; o >>= 1) pm2 += __shfl_xor_sync(FULL, pm2, o);
         p_iso = active ? m.prec_predT[row] : m.precision_0[0];
@@ -166,7 +172,10 @@ __global__ void pack_w_kernel(segb_fixedvar m, int aniso, int rows_pad_, uint8_t
         Ak = lse_c - 0.5 * pm2;
         if (lane == 0) { t_lse[row] = lse_c; t_map[row] = lp + c0 + 0.5 * lpp; t_pk[row] = p_iso; }
     } else if (row < Kr) {
-        for (int d = lane; d < D; d += 32) { t_mu[(size_t)row * D + d] = 0.0; if (aniso) t_P[(size_t)row * D + d] = 0.0; }
+        for (int d = lane; d < D; d += 32) {
+            t_mu[(size_t)row * D + d] = 0.0; t_muT[(size_t)d * Kr + row] = 0.0;
+            if (aniso) { t_P[(size_t)row * D + d] = 0.0; t_PT[(size_t)d * Kr + row] = 0.0; }
+        }
         if (lane == 0) { t_lse[row] = -CUDART_INF; t_map[row] = -CUDART_INF; t_pk[row] = 0.0; }
     }
     bool overflow = alive && !(fabs(Ak) < 60000.0);
@@ -248,6 +257,22 @@ template <bool ANISO>
 __device__ __forceinline__ double quad_part(const ModelRows &t, int k, const float *xr, int D, int j) {
     const double *mu = t.mu + (size_t)k * D;
     double acc = 0.0;
+    if ((D & 1) == 0) {
+        // even D: rows are 8-byte (x) / 16-byte (tables) aligned -- two elements per load, two chains
+        double acc1 = 0.0;
+        const double *P = ANISO ? t.P + (size_t)k * D : nullptr;
+#pragma unroll 3
+        for (int d = 2 * j; d < D; d += 16) {
+            const float2 xv = *reinterpret_cast<const float2 *>(xr + d);
+            const double2 mv = *reinterpret_cast<const double2 *>(mu + d);
+            const double d0 = mv.x - (double)xv.x, d1 = mv.y - (double)xv.y;
+            if (ANISO) {
+                const double2 pv = *reinterpret_cast<const double2 *>(P + d);
+                acc = fma(d0 * d0, pv.x, acc); acc1 = fma(d1 * d1, pv.y, acc1);
+            } else { acc = fma(d0, d0, acc); acc1 = fma(d1, d1, acc1); }
+        }
+        return acc + acc1;
+    }
     if (ANISO) {
         const double *P = t.P + (size_t)k * D;
 #pragma unroll 4
@@ -265,11 +290,12 @@ struct LseAcc {
     int bk;
     __device__ __forceinline__ void init() { m = -CUDART_INF; s = 0.0; best = -CUDART_INF; bk = 0x7fffffff; }
     __device__ __forceinline__ void add(double v, double vmap, int k) {
-        if (v > m) { s = s * exp(m - v) + 1.0; m = v; }            // m = -inf first time: exp(-inf) = 0
+        if (m == -CUDART_INF) { m = v; s = 1.0; }                  // first score: no exponential
+        else if (v > m) { s = s * exp(m - v) + 1.0; m = v; }
         else s += exp(v - m);
         if (vmap > best || (vmap == best && k < bk)) { best = vmap; bk = k; }
     }
-    __device__ __forceinline__ double lse() const { return m + log(s); }
+    __device__ __forceinline__ double lse() const { return s == 1.0 ? m : m + log(s); }
 };
 
 // Eight lanes per embedding (four per warp): the filter record names the candidate chunks and members;
@@ -327,49 +353,72 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
     }
 }
 
-// Exhaustive exact scan for the rows the filter could not decide: one block per row, threads over the
-// model rows (the virtual empty row included), block-wide logsumexp and argmax.
+// Exhaustive exact scan for the rows the filter could not decide.  A block takes FULL_R rows at a time:
+// their embeddings sit in shared memory as float64 ([d][r], so one 16-byte read serves two rows), every
+// thread walks its components through the TRANSPOSED tables (coalesced over k) and keeps FULL_R running
+// quadratic forms in registers -- the model is streamed once per FULL_R rows instead of once per row.
+// Then per row a block-wide logsumexp / first-argmax over the threads' partial results.
+constexpr int FULL_R = 16, FULL_THREADS = 256;
 template <bool ANISO>
-__global__ void __launch_bounds__(256) fv_full_kernel(const float *X, int D, int K_max, const double *model_rows,
-                                                      const int32_t *fb_list, const unsigned long long *n_fallback,
-                                                      double *log_marg, int32_t *map_k) {
+__global__ void __launch_bounds__(FULL_THREADS) fv_full_kernel(const float *X, int D, int K_max, const double *model_rows,
+                                                               const int32_t *fb_list, const unsigned long long *n_fallback,
+                                                               double *log_marg, int32_t *map_k) {
     extern __shared__ double fsm[];
-    double *xs = fsm;                      // [D]
-    double *red = fsm + D;                 // [40]
+    double *xs = fsm;                      // [D][FULL_R]
+    double *red = fsm + (size_t)D * FULL_R;   // [40]
     const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
     const int Kr = K_max + 1;
     const long long n = (long long)*n_fallback;
-    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
-        const int64_t row = fb_list[i];
+    for (long long base = (long long)blockIdx.x * FULL_R; base < n; base += (long long)gridDim.x * FULL_R) {
+        const int nr = (int)min((long long)FULL_R, n - base);
         __syncthreads();
-        for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = (double)X[row * D + d];
+        for (int i = threadIdx.x; i < D * FULL_R; i += blockDim.x) {
+            const int r = i / D, d = i % D;
+            xs[d * FULL_R + r] = r < nr ? (double)X[(int64_t)fb_list[base + r] * D + d] : 0.0;
+        }
         __syncthreads();
-        // pass 1: exact scores of this thread's rows -> running (max, sum) and MAP candidate
-        LseAcc acc;
-        acc.init();
+        LseAcc acc[FULL_R];
+#pragma unroll
+        for (int r = 0; r < FULL_R; ++r) acc[r].init();
         for (int k = threadIdx.x; k < Kr; k += blockDim.x) {
             const double c_lse = t.cst_lse[k];
             if (c_lse == -CUDART_INF) continue;
-            const double *mu = t.mu + (size_t)k * D;
-            double q = 0.0;
-            if (ANISO) {
-                const double *P = t.P + (size_t)k * D;
-                for (int d = 0; d < D; ++d) { const double dl = mu[d] - xs[d]; q = fma(dl * dl, P[d], q); }
-            } else {
-                for (int d = 0; d < D; ++d) { const double dl = mu[d] - xs[d]; q = fma(dl, dl, q); }
-                q *= t.pk[k];
+            double q[FULL_R];
+#pragma unroll
+            for (int r = 0; r < FULL_R; ++r) q[r] = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double mu = t.muT[(size_t)d * Kr + k];
+                const double P = ANISO ? t.PT[(size_t)d * Kr + k] : 1.0;
+                const double2 *xr = reinterpret_cast<const double2 *>(xs + d * FULL_R);
+#pragma unroll
+                for (int r2 = 0; r2 < FULL_R / 2; ++r2) {
+                    const double2 xv = xr[r2];
+                    const double d0 = mu - xv.x, d1 = mu - xv.y;
+                    if (ANISO) { q[2 * r2] = fma(d0 * d0, P, q[2 * r2]); q[2 * r2 + 1] = fma(d1 * d1, P, q[2 * r2 + 1]); }
+                    else { q[2 * r2] = fma(d0, d0, q[2 * r2]); q[2 * r2 + 1] = fma(d1, d1, q[2 * r2 + 1]); }
+                }
             }
-            acc.add(c_lse - 0.5 * q, t.cst_map[k] - 0.5 * q, k);
+            const double pk = ANISO ? 1.0 : t.pk[k], c_map = t.cst_map[k];
+#pragma unroll
+            for (int r = 0; r < FULL_R; ++r) {
+                const double pred = -0.5 * pk * q[r];
+                acc[r].add(c_lse + pred, c_map + pred, k);
+            }
         }
-        const double gm = block_max(acc.m, red);
-        const double part = (acc.m == -CUDART_INF) ? 0.0 : acc.s * exp(acc.m - gm);
-        const double gs = block_sum(part, red);
-        const double gbest = block_max(acc.best, red);
-        const double cand_k = (acc.best == gbest) ? (double)acc.bk : 4.0e9;
-        const double gk = -block_max(-cand_k, red);
-        if (threadIdx.x == 0) {
-            log_marg[row] = gm + log(gs);
-            if (map_k) map_k[row] = (int32_t)gk;
+#pragma unroll
+        for (int r = 0; r < FULL_R; ++r) {
+            if (r >= nr) break;                                     // block-uniform
+            const double gm = block_max(acc[r].m, red);
+            const double part = (acc[r].m == -CUDART_INF) ? 0.0 : acc[r].s * exp(acc[r].m - gm);
+            const double gs = block_sum(part, red);
+            const double gbest = block_max(acc[r].best, red);
+            const double cand_k = (acc[r].best == gbest) ? (double)acc[r].bk : 4.0e9;
+            const double gk = -block_max(-cand_k, red);
+            if (threadIdx.x == 0) {
+                const int64_t row = fb_list[base + r];
+                log_marg[row] = gm + log(gs);
+                if (map_k) map_k[row] = (int32_t)gk;
+            }
         }
     }
 }
@@ -557,13 +606,14 @@ extern "C" int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t
             X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
             map_k, (unsigned long long *)n_fallback, fb_list);
     SEGB_LAUNCH_CHECK();
-    const size_t fsm = sizeof(double) * (D + 40);
+    const size_t fsm = sizeof(double) * ((size_t)D * FULL_R + 40);
+    if (fsm > 48 * 1024) { set_error("D=%d too large for the exhaustive log_marg scan", D); return SEGB_E_UNSUPPORTED; }
     if (aniso)
-        fv_full_kernel<true><<<148 * 8, 256, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
-                                                         (const unsigned long long *)n_fallback, log_marg, map_k);
+        fv_full_kernel<true><<<148 * 4, FULL_THREADS, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
+                                                                  (const unsigned long long *)n_fallback, log_marg, map_k);
     else
-        fv_full_kernel<false><<<148 * 8, 256, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
-                                                          (const unsigned long long *)n_fallback, log_marg, map_k);
+        fv_full_kernel<false><<<148 * 4, FULL_THREADS, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
+                                                                   (const unsigned long long *)n_fallback, log_marg, map_k);
     SEGB_LAUNCH_CHECK();
     return 0;
 }

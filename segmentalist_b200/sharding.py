@@ -12,8 +12,25 @@ import torch
 import torch.distributed as dist
 
 
+_LOCAL_ONLY = 0
+
+
+class local_only(object):
+    """Context manager: inside it the sweeps behave as a single rank even when a process group is
+    initialised (used to compare an N-rank sweep with the 1-rank sweep of the same corpus)."""
+
+    def __enter__(self):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY += 1
+
+    def __exit__(self, *exc):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY -= 1
+        return False
+
+
 def dist_on():
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return (not _LOCAL_ONLY) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def shard_ranges(n_utt, world):

@@ -66,6 +66,7 @@ def timed(fn, reps):
 t_pack = timed(fv.pack_model, args.reps)
 t_filter = timed(fv.filter, args.reps)
 t_refine = timed(fv.refine, args.reps)
+
 fl = (4.0 if args.aniso else 2.0) * D * args.rows * K
 out = fv.log_marg.cpu().numpy()
 ids = np.arange(n_tok, n_tok + 4096) if args.rows >= n_tok + 4096 else np.arange(min(4096, args.rows))
