@@ -582,7 +582,7 @@ def run_bigram_extra(args):
 def _checksum(t):
     """Order-sensitive 64-bit checksum of a tensor's bits (device, no host copy of the data)."""
     import torch
-    v = t.contiguous().view(torch.uint8).to(torch.int64)
+    v = t.contiguous().reshape(-1).view(torch.uint8).to(torch.int64)
     w = (torch.arange(v.numel(), device=v.device, dtype=torch.int64) % 65521) + 1
     return torch.stack([v.sum(), (v * w).sum()])
 
