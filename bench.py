@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--K", type=int, default=K_MAX)
     ap.add_argument("--cpu-sample", type=int, default=32, help="utterances timed by the CPU baseline leg")
     ap.add_argument("--scorer", default="mma", choices=["mma", "exact"])
+    ap.add_argument("--two-kernel", action="store_true", help="pre-packed fp16 image + filter kernel + refine kernel instead of the fused score kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gibbs", action="store_true", help="skip the sequential secondary workloads (BASELINE configs[1], [3], [4])")
@@ -710,15 +711,20 @@ def fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed):
         am.components._add_many(np.arange(n_tok), rank_of[zh])
         fv = FvScorer(am.components)
         fv.score()
-        t_pack, t_filter, t_refine = timed(fv.pack_model, 3), timed(fv.filter, 3), timed(fv.refine, 3)
+        if fv.fused:
+            t_pack, t_filter, t_refine = timed(fv.pack_model, 3), timed(fv.fused_score, 3), 0.0
+        else:
+            t_pack, t_filter, t_refine = timed(fv.pack_model, 3), timed(fv.filter, 3), timed(fv.refine, 3)
         fl = (4.0 if aniso else 2.0) * D * n_fv * args.K
         ids = np.arange(n_tok, n_tok + 2048) if n_fv >= n_tok + 2048 else np.arange(min(2048, n_fv))
         exact = am.log_marg_items(ids)
         got = fv.log_marg[torch.from_numpy(ids).to(fv.log_marg.device)].cpu().numpy()
         rel = float((np.abs(got - exact) / np.abs(exact)).max())
         kp = 16 * ((D + (3 if aniso else 6) + 15) // 16) * (2 if aniso else 1)
-        r = {"kernel": "kmeans_filter_kernel<%s> as the log_marg_i filter (ONE fp16 tcgen05 pass, fp32 TMEM, top-3 chunk epilogue) "
-                       "+ fv_refine_kernel (exact float64 re-scoring of the kept components, logsumexp)" % ("9,2" if aniso else "9,1"),
+        r = {"kernel": ("score_fused_kernel<fv> (fp32 rows in, ONE fp16 tcgen05 pass, exact float64 re-scoring of the kept "
+                        "components + logsumexp behind the GEMM: the whole log_marg_i step)" if fv.fused else
+                        "kmeans_filter_kernel<%s> as the log_marg_i filter (ONE fp16 tcgen05 pass, fp32 TMEM, top-3 chunk epilogue) "
+                        "+ fv_refine_kernel (exact float64 re-scoring of the kept components, logsumexp)" % ("9,2" if aniso else "9,1")),
              "bound": "tensor", "achieved": fl / (t_filter * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
              "frac": fl / (t_filter * 1e-3) / 1e12 / peak_tf, "peak_source": peak_src,
              "kernel_ms": t_filter, "refine_ms": t_refine, "pack_model_ms": t_pack,
@@ -730,10 +736,10 @@ def fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed):
              "fallback_rows": int(fv.n_fallback.item()), "max_rel_err_vs_exact_float64": rel,
              "threshold_nats": fv.T}
         if not aniso:
-            tr = ncu_traffic("fv_filter_kernel")
+            tr = ncu_traffic("score_fused_kernel_fv" if fv.fused else "fv_filter_kernel")
             r["traffic"] = tr["bytes_per_launch"] if (tr and args.K == K_MAX and n_fv == 4 * 1024 * 1024) else None
             r["traffic_source"] = tr.get("source") if tr else None
-            r["algorithmic_bytes_per_launch"] = float(fv.x_tiles.numel() + fv.cand.numel())
+            r["algorithmic_bytes_per_launch"] = float(n_fv * D * 4 + 12 * n_fv) if fv.fused else float(fv.x_tiles.numel() + fv.cand.numel())
             out = r
         else:
             out["anisotropic"] = r
@@ -993,8 +999,9 @@ def run_ours(args):
     # inactive slots winning tokens, undecided rows) is measured separately below (secondary_kmeans_diffuse)
     tok = corpus.tok_id[corpus.tok_id >= 0].long()
     comps._assign[tok] = Z[tok]
-    sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer)
+    sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer, fused=(False if args.two_kernel else None))
     sweep.init_means_from_assignments()
+    sweep_fused = bool(sweep.mma is not None and sweep.mma.fused)
     n_pos, M = corpus.n_pos, n_emb
     evals_per_sweep_local = float(M) * args.K
 
@@ -1044,17 +1051,23 @@ def run_ours(args):
     if rank == 0:
         sp = _lib.stream_ptr()
         if args.scorer == "mma":
-            sweep.mma.filter()
-            k_ms = timed(sweep.mma.filter, 5)
+            fused = sweep.mma.fused
+            run_k = (lambda: sweep.mma.fused_score(sweep.best_val, sweep.best_k)) if fused else sweep.mma.filter
+            run_k()
+            k_ms = timed(run_k, 5)
             flops = 2.0 * D * M * args.K                  # algorithmic: 2*D per segment x component eval
             ach = flops / (k_ms * 1e-3) / 1e12
-            tr = ncu_traffic("kmeans_filter_kernel") if default_cfg else None
-            roofline = {"kernel": "kmeans_filter_kernel (tcgen05 fp16 -> fp32 TMEM, fused top-3 epilogue)",
+            kname = "score_fused_kernel" if fused else "kmeans_filter_kernel"
+            tr = ncu_traffic(kname) if default_cfg else None
+            roofline = {"kernel": ("score_fused_kernel<kmeans> (fp32 rows -> fp16 operand tiles in shared memory, tcgen05 fp16 -> fp32 "
+                                   "TMEM, top-3 epilogue, exact float32 refine of the survivors: the whole scoring step)" if fused
+                                   else "kmeans_filter_kernel (tcgen05 fp16 -> fp32 TMEM, fused top-3 epilogue)"),
                         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": ach / peak_tf,
                         "traffic": tr["bytes_per_launch"] if tr else None,
                         "traffic_source": tr.get("source") if tr else None,
-                        "algorithmic_bytes_per_launch": float(sweep.mma.x_tiles.numel() + sweep.mma.cand.numel()),
+                        "algorithmic_bytes_per_launch": float(X.numel() * 4 + 8 * M) if fused else
+                                                        float(sweep.mma.x_tiles.numel() + sweep.mma.cand.numel()),
                         "peak_source": peak_src,
                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops}
         cs = corpus.struct()
@@ -1221,6 +1234,7 @@ def run_ours(args):
                        "candidate_segments": int(tot[1].item()), "scorer": args.scorer,
                        "init": "tokens start in the component of their generating cluster (K_act = K_max)",
                        "parallelism": "utterance shards x%d + NCCL all-reduce(sum_x, counts)" % world,
+                       "fused_scorer": bool(args.scorer == "mma" and sweep_fused),
                        "l2": "inputs (%.1f GB of embeddings per rank) exceed L2; no flush needed" % (X.numel() * 4 / 1e9)},
             "segment_component_evals_per_s": evals_per_s,
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,

@@ -371,7 +371,8 @@ int segb_fvmma_log_marg(const segb_fixedvar *m, const void *x_tiles, void *w_til
  *                        per-row error norms in `model` (segb_fvf_model_bytes), model-wide maxima in w_max [4]
  *   segb_fvf_filter      the GEMM; cand = segb_mma_cand_bytes(n_emb) bytes of per-row records
  *   segb_fvf_refine      log_marg [n_emb] float64, map_k [n_emb] (optional): the MAP slot of map_assign_i
- *                        (fbgmm.py:465-494; the first empty slot is K); work = segb_fvf_work_bytes(n_emb)      */
+ *                        (fbgmm.py:465-494; the first empty slot is K); rec_out (optional, 16 bytes per row): the
+ *                        thresholded row records segb_fvf_choose_tokens draws from; work = segb_fvf_work_bytes(n_emb) */
 int64_t segb_fvf_x_tiles_bytes(int64_t n_emb, int32_t D, int32_t aniso);
 int64_t segb_fvf_w_tiles_bytes(int32_t K_max, int32_t D, int32_t aniso);
 int64_t segb_fvf_model_bytes(int32_t K_max, int32_t D, int32_t aniso);
@@ -384,7 +385,24 @@ int segb_fvf_filter(const void *x_tiles, const void *w_tiles, int64_t n_emb, int
                     int32_t aniso, const float *x_max, const float *w_max, float T, void *cand, void *stream);
 int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, int32_t aniso, const void *model,
                     const void *cand, const float *x_err, const float *w_max, float T, void *work,
-                    double *log_marg, int32_t *map_k, int64_t *n_fallback, void *stream);
+                    double *log_marg, int32_t *map_k, void *rec_out, int64_t *n_fallback, void *stream);
+
+/* ------------------------------------------------------------------ fused scoring: fp32 embeddings in, results out */
+
+/* The same two scorers as ONE kernel that reads the fp32 embeddings once (csrc/score_fused.cu): four aux warps
+ * convert the next 256 rows to the fp16 operand layout directly in shared memory (no resident fp16 image of
+ * X, no pack pass) and re-score the previous 256 rows' surviving candidates exactly while the tensor pipe
+ * works on the current ones; the per-row filter records never leave shared memory.
+ *   segb_fused_kmeans_best  = segb_mma_filter + segb_mma_refine (w_tiles / w_max from segb_mma_pack_means);
+ *                             rows [0, n_emb) of m->X.  Same bits out.  D even, <= 142 (else the two-kernel path).
+ *   segb_fused_fv_log_marg  = segb_fvf_filter + segb_fvf_refine for isotropic variances (w_tiles / model / w_max
+ *                             from segb_fvf_pack_model with aniso = 0).
+ * work: (n_emb + 64) * 4 bytes (list of the rows left to the exhaustive scan); n_fallback (device) is reset.   */
+int segb_fused_kmeans_best(const segb_kmeans *m, const void *w_tiles, const float *w_max, int64_t n_emb,
+                           void *work, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
+int segb_fused_fv_log_marg(const float *X, int64_t n_emb, int32_t D, int32_t K_max, const void *w_tiles,
+                           const void *model, const float *w_max, float T, void *work, double *log_marg,
+                           int32_t *map_k, void *rec_out, int64_t *n_fallback, void *stream);
 
 /* get_vec_embed_log_probs (unigram_acoustic_wordseg.py:474-511) from per-embedding log marginals:
  * scores[slot] = log_marg[seg_id[slot]] * seg_dur[slot]**time_power_term + wip, -inf for absent slots /
@@ -399,9 +417,9 @@ int segb_fixedvar_band_scores(const segb_corpus *c, int64_t pos_first, int64_t n
  * order, empty slots last.  choice[id] is the raw slot index (>= K: an empty slot); add_item's clamp is
  * applied afterwards in token order (segb_frozen_new_list / segb_frozen_clamp).                        */
 int segb_fvf_choose_tokens(const float *X, int32_t D, int32_t K_max, int32_t K, int32_t aniso, const void *model,
-                           const void *cand, const float *x_err, const float *w_max, float T,
-                           const segb_corpus *c, int64_t pos_first, int64_t n_positions, int32_t mode,
-                           const int32_t *map_k, const double *uniforms, int32_t *choice, void *stream);
+                           const void *recs, const segb_corpus *c, int64_t pos_first, int64_t n_positions,
+                           int32_t mode, const int32_t *map_k, const double *uniforms, int32_t *choice,
+                           void *stream);
 
 /* ------------------------------------------------------------------ frozen-state model update (new batch mode) */
 

@@ -104,10 +104,13 @@ _PROTOS = {
     "segb_fvf_pack_model": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_i32, c_vp, c_vp, c_vp, c_vp]),
     "segb_fvf_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, ctypes.c_float, c_vp, c_vp]),
     "segb_fvf_refine": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, ctypes.c_float,
-                                       c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fused_kmeans_best": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fused_fv_log_marg": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, ctypes.c_float, c_vp, c_vp,
+                                              c_vp, c_vp, c_vp, c_vp]),
     "segb_fixedvar_band_scores": (ctypes.c_int, [ctypes.POINTER(Corpus), c_i64, c_i64, c_vp, c_f64, c_f64, c_vp, c_vp]),
-    "segb_fvf_choose_tokens": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, ctypes.c_float,
-                                              ctypes.POINTER(Corpus), c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fvf_choose_tokens": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, ctypes.POINTER(Corpus), c_i64,
+                                              c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "segb_tokens_from_bounds": (ctypes.c_int, [ctypes.POINTER(Corpus), c_i32, c_i32, c_vp]),
     "segb_frozen_new_work_bytes": (c_i64, [c_i64]),
     "segb_frozen_new_list": (ctypes.c_int, [ctypes.POINTER(Corpus), c_i64, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp,

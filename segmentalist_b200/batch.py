@@ -31,26 +31,39 @@ from . import _lib
 from .sharding import dist_on as _dist_on, reduce_packed
 
 
-class MmaScorer(object):
-    """Buffers and call sequence of the tensor-core scorer (segb_mma_*): fp16 tile images of
-    the embeddings (packed once) and of the means (packed per sweep), the 32-byte per-row
-    filter records, and the per-row / per-component rounding-error norms behind the rigorous
-    candidate threshold."""
+def fused_supported(D):
+    """The fused score kernel (csrc/score_fused.cu) double-buffers two 128-row operand tiles of
+    roundup(D + 6, 16) fp16 columns next to two model tiles: D <= 138; its k-means refine needs an even D."""
+    return D % 2 == 0 and D <= 138
 
-    def __init__(self, components):
+
+class MmaScorer(object):
+    """Buffers and call sequence of the tensor-core k-means scorer.
+
+    fused=True (default where supported): ONE kernel per sweep reads the fp32 embeddings once, converts them
+    to fp16 operand tiles in shared memory, runs the filter GEMM and re-scores the surviving candidates
+    exactly (segb_fused_kmeans_best) -- no fp16 image of X, no per-row filter records in HBM.
+    fused=False: the two-kernel path (segb_mma_filter over a pre-packed fp16 tile image of X, then
+    segb_mma_refine) with its 32-byte per-row records and per-row rounding-error norms.  Same bits out."""
+
+    def __init__(self, components, fused=None):
         lib, c, dev = _lib.lib(), components, "cuda"
         assert c._X.dtype == torch.float32, "tensor-core scorer needs float32 embeddings"
         self.c = c
-        self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
+        self.fused = fused_supported(c.D) if fused is None else bool(fused)
+        assert not self.fused or fused_supported(c.D)
         self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
-        self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
         self.work = torch.empty(lib.segb_mma_refine_work_bytes(c.N, c.K_max), dtype=torch.uint8, device=dev)
-        self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)              # (|dx|, |x|) per row
         self.w_err = torch.empty(2 * (c.K_max + 128), dtype=torch.float32, device=dev)  # (|dmu|, |mu^|)
-        self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
         self.w_max = torch.zeros(2, dtype=torch.float32, device=dev)
         self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.pack_x()
+        self.x_tiles = self.cand = self.x_err = self.x_max = None
+        if not self.fused:
+            self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
+            self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
+            self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)              # (|dx|, |x|) per row
+            self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
+            self.pack_x()
 
     def pack_x(self):
         c = self.c
@@ -74,17 +87,27 @@ class MmaScorer(object):
                                               _lib.ptr(self.w_max), c.N, _lib.ptr(self.work), _lib.ptr(best_val),
                                               _lib.ptr(best_k), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
 
+    def fused_score(self, best_val, best_k):
+        """The model image must be current (pack_means)."""
+        c = self.c
+        _lib.check(_lib.lib().segb_fused_kmeans_best(c.struct(), _lib.ptr(self.w_tiles), _lib.ptr(self.w_max), c.N,
+                                                     _lib.ptr(self.work), _lib.ptr(best_val), _lib.ptr(best_k),
+                                                     _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+
     def score(self, best_val, best_k):
         self.pack_means()
-        self.filter()
-        self.refine(best_val, best_k)
+        if self.fused:
+            self.fused_score(best_val, best_k)
+        else:
+            self.filter()
+            self.refine(best_val, best_k)
 
     def score_streamed(self, X_host, best_val, best_k, chunk_rows=1 << 20):
         """Score embeddings that still live in (pinned) HOST memory: the rows are uploaded in
-        chunks on a copy stream while the previous chunk is packed to fp16 tiles, filtered and
-        refined on the compute stream, so the sweep costs max(PCIe, compute) instead of their
-        sum.  Chunks start on 256-row boundaries (whole operand tiles); every kernel is the
-        same C-ABI call as in score(), handed pointers offset to the chunk."""
+        chunks on a copy stream while the previous chunk is scored on the compute stream, so the
+        sweep costs max(PCIe, compute) instead of their sum.  Chunks start on 256-row boundaries
+        (whole work items); every kernel is the same C-ABI call as in score(), handed pointers
+        offset to the chunk."""
         import ctypes
         lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
         assert X_host.shape == c._X.shape and X_host.dtype == torch.float32 and X_host.is_pinned()
@@ -96,11 +119,12 @@ class MmaScorer(object):
         self.copy_stream.wait_stream(main)             # earlier kernels may still read X
         self.pack_means()
         self.fb_total.zero_()
-        kp2 = lib.segb_mma_x_tiles_bytes(256, c.D) // 256        # bytes of tile image per row
-        rec = lib.segb_mma_cand_bytes(1)
         m = c.struct()
         x_base = c._X.data_ptr()
         vp = ctypes.c_void_p
+        if not self.fused:
+            kp2 = lib.segb_mma_x_tiles_bytes(256, c.D) // 256        # bytes of tile image per row
+            rec = lib.segb_mma_cand_bytes(1)
         for lo in range(0, c.N, chunk_rows):
             hi = min(c.N, lo + chunk_rows)
             n = hi - lo
@@ -109,23 +133,27 @@ class MmaScorer(object):
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
             main.wait_event(ev)
-            xt = vp(self.x_tiles.data_ptr() + lo * kp2)
-            xe = vp(self.x_err.data_ptr() + 8 * lo)
-            cd = vp(self.cand.data_ptr() + rec * lo)
-            _lib.check(lib.segb_mma_pack_x(vp(x_base + 4 * c.D * lo), n, c.D, xt, xe, _lib.ptr(self.x_max), sp))
-            _lib.check(lib.segb_mma_filter(xt, _lib.ptr(self.w_tiles), n, c.K_max, c.D, _lib.ptr(self.x_max),
-                                           _lib.ptr(self.w_max), cd, sp))
             m.X, m.n_emb = x_base + 4 * c.D * lo, n
-            _lib.check(lib.segb_mma_refine(m, cd, xe, _lib.ptr(self.w_max), n, _lib.ptr(self.work),
-                                           vp(best_val.data_ptr() + 4 * lo), vp(best_k.data_ptr() + 4 * lo),
-                                           _lib.ptr(self.n_fallback), sp))
+            bv, bk = vp(best_val.data_ptr() + 4 * lo), vp(best_k.data_ptr() + 4 * lo)
+            if self.fused:
+                _lib.check(lib.segb_fused_kmeans_best(m, _lib.ptr(self.w_tiles), _lib.ptr(self.w_max), n,
+                                                      _lib.ptr(self.work), bv, bk, _lib.ptr(self.n_fallback), sp))
+            else:
+                xt = vp(self.x_tiles.data_ptr() + lo * kp2)
+                xe = vp(self.x_err.data_ptr() + 8 * lo)
+                cd = vp(self.cand.data_ptr() + rec * lo)
+                _lib.check(lib.segb_mma_pack_x(vp(x_base + 4 * c.D * lo), n, c.D, xt, xe, _lib.ptr(self.x_max), sp))
+                _lib.check(lib.segb_mma_filter(xt, _lib.ptr(self.w_tiles), n, c.K_max, c.D, _lib.ptr(self.x_max),
+                                               _lib.ptr(self.w_max), cd, sp))
+                _lib.check(lib.segb_mma_refine(m, cd, xe, _lib.ptr(self.w_max), n, _lib.ptr(self.work), bv, bk,
+                                               _lib.ptr(self.n_fallback), sp))
             self.fb_total += self.n_fallback
         self.n_fallback.copy_(self.fb_total)
 
 
 class FrozenKMeansSweep(object):
 
-    def __init__(self, components, corpus, wip=0.0, scorer="auto"):
+    def __init__(self, components, corpus, wip=0.0, scorer="auto", fused=None):
         self.c, self.corpus, self.wip = components, corpus, float(wip)
         lib = _lib.lib()
         c = components
@@ -150,7 +178,7 @@ class FrozenKMeansSweep(object):
         self.log_prob_h = torch.zeros(corpus.n_utt, dtype=torch.float64).pin_memory()
         self.side = torch.cuda.Stream()
         self.last_fallback = 0
-        self.mma = MmaScorer(c) if scorer == "mma" else None
+        self.mma = MmaScorer(c, fused=fused) if scorer == "mma" else None
         self.K_host = None                     # host copy of the active-component count (no .item() per sweep)
         # add_item's clamp and clean_components as device kernels (csrc/frozen.cu): no host logic per sweep
         self.clamp = NewComponentClamp(corpus, c.K_max)
@@ -231,7 +259,12 @@ class FrozenKMeansSweep(object):
             names.append(name)
             evs.append(e)
         c = self.c
-        if self.scorer == "mma":
+        if self.scorer == "mma" and self.mma.fused:
+            self.mma.pack_means()
+            mark("pack_means")
+            self.mma.fused_score(self.best_val, self.best_k)
+            mark("score_fused(convert+filter_gemm+refine)")
+        elif self.scorer == "mma":
             self.mma.pack_means()
             mark("pack_means")
             self.mma.filter()
@@ -349,28 +382,35 @@ def _is_aniso(c):
 
 
 class FvScorer(object):
-    """Buffers and call sequence of the tensor-core log_marg_i (segb_fvf_*): fp16 tile image of the
-    embeddings (packed once), fp16 model image + exact float64 row tables (packed per model state), the
-    32-byte per-row filter records, float64 log marginals and MAP slots out."""
+    """Buffers and call sequence of the tensor-core log_marg_i (segb_fvf_* / segb_fused_fv_log_marg): fp16
+    model image + exact float64 row tables (packed per model state), float64 log marginals and MAP slots
+    out.  fused=True (default for isotropic variances where supported): one kernel reads the fp32 embeddings
+    once; fused=False: pre-packed fp16 tile image of X, filter GEMM, refine kernel (the anisotropic path).
+    keep_records: also keep the 16-byte thresholded row records (needed to DRAW components afterwards)."""
 
-    def __init__(self, components, T=LSE_T):
+    def __init__(self, components, T=LSE_T, fused=None, keep_records=False):
         lib, c, dev = _lib.lib(), components, "cuda"
         assert c._X.dtype == torch.float32, "tensor-core log_marg needs float32 embeddings"
         self.c, self.T = c, float(T)
         self.aniso = int(_is_aniso(c))
+        can_fuse = (not self.aniso) and c.D <= 138
+        self.fused = can_fuse if fused is None else (bool(fused) and can_fuse)
         u8 = torch.uint8
-        self.x_tiles = torch.empty(lib.segb_fvf_x_tiles_bytes(c.N, c.D, self.aniso), dtype=u8, device=dev)
         self.w_tiles = torch.empty(lib.segb_fvf_w_tiles_bytes(c.K_max, c.D, self.aniso), dtype=u8, device=dev)
         self.model = torch.empty(lib.segb_fvf_model_bytes(c.K_max, c.D, self.aniso), dtype=u8, device=dev)
-        self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=u8, device=dev)
         self.work = torch.empty(lib.segb_fvf_work_bytes(c.N), dtype=u8, device=dev)
-        self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)
-        self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
         self.w_max = torch.zeros(4, dtype=torch.float32, device=dev)
         self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
         self.log_marg = torch.empty(c.N, dtype=torch.float64, device=dev)
         self.map_k = torch.empty(c.N, dtype=torch.int32, device=dev)
-        self.pack_x()
+        self.recs = torch.empty(16 * c.N, dtype=u8, device=dev) if keep_records else None
+        self.x_tiles = self.cand = self.x_err = self.x_max = None
+        if not self.fused:
+            self.x_tiles = torch.empty(lib.segb_fvf_x_tiles_bytes(c.N, c.D, self.aniso), dtype=u8, device=dev)
+            self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=u8, device=dev)
+            self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)
+            self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
+            self.pack_x()
 
     def pack_x(self):
         c = self.c
@@ -392,13 +432,24 @@ class FvScorer(object):
         _lib.check(_lib.lib().segb_fvf_refine(_lib.ptr(c._X), c.N, c.D, c.K_max, self.aniso, _lib.ptr(self.model),
                                               _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max), self.T,
                                               _lib.ptr(self.work), _lib.ptr(self.log_marg), _lib.ptr(self.map_k),
-                                              _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+                                              _lib.ptr(self.recs), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+
+    def fused_score(self):
+        """The model image must be current (pack_model)."""
+        c = self.c
+        _lib.check(_lib.lib().segb_fused_fv_log_marg(_lib.ptr(c._X), c.N, c.D, c.K_max, _lib.ptr(self.w_tiles),
+                                                     _lib.ptr(self.model), _lib.ptr(self.w_max), self.T,
+                                                     _lib.ptr(self.work), _lib.ptr(self.log_marg), _lib.ptr(self.map_k),
+                                                     _lib.ptr(self.recs), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
 
     def score(self):
         """log_marg_i of every embedding (self.log_marg) and its MAP slot (self.map_k)."""
         self.pack_model()
-        self.filter()
-        self.refine()
+        if self.fused:
+            self.fused_score()
+        else:
+            self.filter()
+            self.refine()
 
 
 class FrozenFBGMMSweep(object):
@@ -410,7 +461,7 @@ class FrozenFBGMMSweep(object):
     their embeddings) shard over ranks; ONE all-reduce of [sum_x | counts] per sweep, like the k-means
     sweep.  Semantics pinned by the test oracle's frozen_fbgmm_sweep."""
 
-    def __init__(self, components, corpus, fb_type="standard", time_power_term=1.0, wip=0.0, T=LSE_T):
+    def __init__(self, components, corpus, fb_type="standard", time_power_term=1.0, wip=0.0, T=LSE_T, fused=None):
         self.c, self.corpus = components, corpus
         assert fb_type in ("standard", "viterbi")
         self.fb_type, self.tpt, self.wip = fb_type, float(time_power_term), float(wip)
@@ -421,7 +472,7 @@ class FrozenFBGMMSweep(object):
             # widen the threshold by the largest possible difference between the two rankings
             n_tok = max(1, int(cp.n_pos))
             T = T + abs(1.0 - c._lms) * float(np.log((c._alpha / c.K_max + n_tok) / (c._alpha / c.K_max)))
-        self.fv = FvScorer(c, T)
+        self.fv = FvScorer(c, T, fused=fused, keep_records=(fb_type == "standard"))
         self.scores = torch.empty(cp.n_pos * cp.S, dtype=torch.float64, device=dev)
         self.log_prob = torch.zeros(cp.n_utt, dtype=torch.float64, device=dev)
         self.status = torch.zeros(cp.n_utt, dtype=torch.int32, device=dev)
@@ -453,9 +504,8 @@ class FrozenFBGMMSweep(object):
         lib, c, cp, fv, sp = _lib.lib(), self.c, self.corpus, self.fv, _lib.stream_ptr()
         mode = 0 if self.fb_type == "standard" else 1
         _lib.check(lib.segb_fvf_choose_tokens(_lib.ptr(c._X), c.D, c.K_max, int(K_before), fv.aniso, _lib.ptr(fv.model),
-                                              _lib.ptr(fv.cand), _lib.ptr(fv.x_err), _lib.ptr(fv.w_max), fv.T,
-                                              cp.struct(), 0, cp.n_pos, mode, _lib.ptr(fv.map_k), _lib.ptr(u_assign),
-                                              _lib.ptr(self.choice), sp))
+                                              _lib.ptr(fv.recs), cp.struct(), 0, cp.n_pos, mode, _lib.ptr(fv.map_k),
+                                              _lib.ptr(u_assign), _lib.ptr(self.choice), sp))
 
     def collect(self):
         lib, c, cp, sp = _lib.lib(), self.c, self.corpus, _lib.stream_ptr()
@@ -495,10 +545,14 @@ class FrozenFBGMMSweep(object):
         K_before = self.K_host if self.K_host is not None else c.K
         self.fv.pack_model()
         mark("pack_model")
-        self.fv.filter()
-        mark("filter_gemm")
-        self.fv.refine()
-        mark("refine_exact")
+        if self.fv.fused:
+            self.fv.fused_score()
+            mark("score_fused(convert+filter_gemm+refine)")
+        else:
+            self.fv.filter()
+            mark("filter_gemm")
+            self.fv.refine()
+            mark("refine_exact")
         self.segment(u_fb)
         mark("band_scores+dp+tokens")
         self.choose(u_assign, K_before)

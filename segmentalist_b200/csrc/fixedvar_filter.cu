@@ -23,6 +23,7 @@
 // absolute (north star: 1e-4 relative) at one tensor pass instead of three, plus the exact MAP
 // component of every embedding for free.
 #include "mma_common.cuh"
+#include "fv_refine.cuh"
 
 namespace segb {
 namespace fvf {
@@ -32,35 +33,8 @@ using namespace segb::mma;
 constexpr float DEAD_A = -30000.0f;      // constant of padded model rows: never inside any threshold
 constexpr int REFINE_THREADS = 256;
 
-__host__ __device__ inline int kp_of(int D, int aniso) { return ((aniso ? D + 3 : D + 6) + 15) / 16 * 16; }
-__host__ __device__ inline int nch_of(int aniso) { return aniso ? 2 : 1; }
 static inline int64_t rows_pad(int64_t n) { return (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS; }
 static inline int w_rows_pad(int K_max) { return (K_max + 1 + NT_COLS - 1) / NT_COLS * NT_COLS; }   // +1: the virtual empty slot
-
-// Exact per-component tables read by the refine (row-major so one component is one contiguous row) and,
-// transposed (component index fastest), by the exhaustive scan:
-//   mu [Kr][D] | P [Kr][D] (anisotropic only) | muT [D][Kr] | PT [D][Kr] (anisotropic only)
-//   | cst_lse [Kr] | cst_map [Kr] | pk [Kr]                                              Kr = K_max + 1
-// cst_lse = lms*pi_k - D/2 log 2pi + 1/2 sum_d log P_kd (+ log(K_max - K) on the virtual row);
-// cst_map = log(alpha/K_max + n_k) - D/2 log 2pi + 1/2 sum_d log P_kd   (map_assign_i: no lms, fbgmm.py:475-479).
-struct ModelRows {
-    const double *mu, *P, *muT, *PT, *cst_lse, *cst_map, *pk;
-};
-__host__ __device__ inline int64_t model_doubles(int K_max, int D, int aniso) {
-    const int64_t Kr = K_max + 1;
-    return 2 * Kr * D * (aniso ? 2 : 1) + 3 * Kr;
-}
-__host__ __device__ inline ModelRows model_view(const double *base, int K_max, int D, int aniso) {
-    const int64_t Kr = K_max + 1, n = Kr * D;
-    ModelRows r;
-    r.mu = base;
-    r.P = aniso ? base + n : nullptr;
-    r.muT = base + n * (aniso ? 2 : 1);
-    r.PT = aniso ? r.muT + n : nullptr;
-    const double *q = base + 2 * n * (aniso ? 2 : 1);
-    r.cst_lse = q; r.cst_map = q + Kr; r.pk = q + 2 * Kr;
-    return r;
-}
 
 __device__ __forceinline__ void split2(float v, __half &hi, __half &lo) {
     hi = __float2half_rn(v);
@@ -250,54 +224,6 @@ __global__ void wmax4_kernel(const float *w_err, int n_rows, float *w_max) {
 
 // ---------------------------------------------------------------- exact refine
 
-// Exact float64 quadratic form of component row k for the embedding whose elements d = j, j+8, ... this
-// lane holds: sum_d P_kd (mu_kd - x_d)^2 over the lane's elements (isotropic: the factor p_k is applied
-// by the caller).  Eight lanes per embedding; the caller reduces over them.
-template <bool ANISO>
-__device__ __forceinline__ double quad_part(const ModelRows &t, int k, const float *xr, int D, int j) {
-    const double *mu = t.mu + (size_t)k * D;
-    double acc = 0.0;
-    if ((D & 1) == 0) {
-        // even D: rows are 8-byte (x) / 16-byte (tables) aligned -- two elements per load, two chains
-        double acc1 = 0.0;
-        const double *P = ANISO ? t.P + (size_t)k * D : nullptr;
-#pragma unroll 3
-        for (int d = 2 * j; d < D; d += 16) {
-            const float2 xv = *reinterpret_cast<const float2 *>(xr + d);
-            const double2 mv = *reinterpret_cast<const double2 *>(mu + d);
-            const double d0 = mv.x - (double)xv.x, d1 = mv.y - (double)xv.y;
-            if (ANISO) {
-                const double2 pv = *reinterpret_cast<const double2 *>(P + d);
-                acc = fma(d0 * d0, pv.x, acc); acc1 = fma(d1 * d1, pv.y, acc1);
-            } else { acc = fma(d0, d0, acc); acc1 = fma(d1, d1, acc1); }
-        }
-        return acc + acc1;
-    }
-    if (ANISO) {
-        const double *P = t.P + (size_t)k * D;
-#pragma unroll 4
-        for (int d = j; d < D; d += 8) { const double dl = mu[d] - (double)xr[d]; acc = fma(dl * dl, P[d], acc); }
-    } else {
-#pragma unroll 4
-        for (int d = j; d < D; d += 8) { const double dl = mu[d] - (double)xr[d]; acc = fma(dl, dl, acc); }
-    }
-    return acc;
-}
-
-// Running logsumexp + MAP argmax over the exact scores fed one at a time.
-struct LseAcc {
-    double m, s, best;
-    int bk;
-    __device__ __forceinline__ void init() { m = -CUDART_INF; s = 0.0; best = -CUDART_INF; bk = 0x7fffffff; }
-    __device__ __forceinline__ void add(double v, double vmap, int k) {
-        if (m == -CUDART_INF) { m = v; s = 1.0; }                  // first score: no exponential
-        else if (v > m) { s = s * exp(m - v) + 1.0; m = v; }
-        else s += exp(v - m);
-        if (vmap > best || (vmap == best && k < bk)) { best = vmap; bk = k; }
-    }
-    __device__ __forceinline__ double lse() const { return s == 1.0 ? m : m + log(s); }
-};
-
 // Eight lanes per embedding (four per warp): the filter record names the candidate chunks and members;
 // each is re-scored exactly and fed to the running logsumexp.  Rows the filter could not decide go to
 // fb_list for the exhaustive scan.
@@ -305,7 +231,7 @@ template <bool ANISO>
 __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
     const float *X, int D, int K_max, const double *model_rows, const Cand *cand, const float *x_err,
     const float *w_max, int KP, float T, int64_t n_emb, int n_chunks, double *log_marg, int32_t *map_k,
-    unsigned long long *n_fallback, int32_t *fb_list) {
+    RowRec *rec_out, unsigned long long *n_fallback, int32_t *fb_list) {
     const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
     const int lane = threadIdx.x & 31, j = lane & 7;
     const unsigned gmask = 0xffu << (lane & 24);
@@ -318,34 +244,12 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
         const float2 xe = *reinterpret_cast<const float2 *>(x_err + 2 * row);
         const float tau = lse_tau(xe.x, xe.y, w4, KP, T);
         const int code = refine_decide(cd, tau, n_chunks);
+        if (rec_out && j == 0) rec_out[row] = RowRec{cd.i1, cd.i2, cd.masks, code};
         if (code == -2) {
             if (j == 0) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;
             continue;
         }
-        const float *xr = X + row * D;
-        LseAcc acc;
-        acc.init();
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            // best chunk: the members within the launch-wide threshold of the chunk maximum (a superset of
-            // the members within this row's tau); second chunk: everything
-            uint32_t mk = pass == 0 ? (cd.masks & 0xffffu) : (code >= 0 ? (cd.masks >> 16) : 0u);
-            const int chunk = pass == 0 ? cd.i1 : cd.i2;
-            while (mk) {
-                const int bit = __ffs(mk) - 1;
-                mk &= mk - 1;
-                const int k = chunk * CHUNK + bit;
-                if (k >= Kr) continue;
-                double q = quad_part<ANISO>(t, k, xr, D, j);
-                q += __shfl_xor_sync(gmask, q, 1);
-                q += __shfl_xor_sync(gmask, q, 2);
-                q += __shfl_xor_sync(gmask, q, 4);
-                const double pred = -0.5 * (ANISO ? q : t.pk[k] * q);
-                const double c_lse = t.cst_lse[k];
-                if (c_lse == -CUDART_INF) continue;                 // dead row
-                acc.add(c_lse + pred, t.cst_map[k] + pred, k);
-            }
-        }
+        const LseAcc acc = fv_exact_row8<ANISO>(t, Kr, D, X + row * D, cd.i1, cd.i2, cd.masks, code, j, gmask);
         if (j == 0) {
             log_marg[row] = acc.lse();
             if (map_k) map_k[row] = (acc.bk == 0x7fffffff) ? -1 : acc.bk;
@@ -451,14 +355,12 @@ __global__ void fv_band_scores_kernel(segb_corpus c, int64_t slot_first, int64_t
 // the `k > K -> K` clamp of add_item is applied afterwards in token order (segb_clamp_new_components).
 template <bool ANISO>
 __global__ void __launch_bounds__(REFINE_THREADS) fv_choose_kernel(
-    const float *X, int D, int K_max, int K, const double *model_rows, const Cand *cand, const float *x_err,
-    const float *w_max, int KP, float T, int n_chunks, segb_corpus c, int64_t pos_first, int64_t n_positions,
-    int mode, const int32_t *map_k, const double *uniforms, int32_t *choice) {
+    const float *X, int D, int K_max, int K, const double *model_rows, const RowRec *recs, segb_corpus c,
+    int64_t pos_first, int64_t n_positions, int mode, const int32_t *map_k, const double *uniforms, int32_t *choice) {
     const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
     const int lane = threadIdx.x & 31, j = lane & 7;
     const unsigned gmask = 0xffu << (lane & 24);
     const int Kr = K_max + 1;
-    const W4 w4{w_max[0], w_max[1], w_max[2], w_max[3]};
     const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
     for (int64_t pi = grp_global; pi < n_positions; pi += grp_total) {
@@ -467,10 +369,8 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_choose_kernel(
         if (id < 0) continue;
         if (mode == 1) { if (j == 0) choice[id] = map_k[id]; continue; }
         const double u = uniforms[pos];
-        const Cand cd = cand[id];
-        const float2 xe = *reinterpret_cast<const float2 *>(x_err + 2 * (int64_t)id);
-        const float tau = lse_tau(xe.x, xe.y, w4, KP, T);
-        const int code = refine_decide(cd, tau, n_chunks);
+        const RowRec cd = recs[id];
+        const int code = cd.code;
         const float *xr = X + (int64_t)id * D;
         auto score = [&](int k) -> double {                       // s_k without the constants common to all slots
             double q = quad_part<ANISO>(t, k, xr, D, j);
@@ -489,6 +389,11 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_choose_kernel(
         }
         double lse = 0.0, urest = u;
         int pick = -1;
+        if (code == -1 && __popc(ma) == 1) {
+            // one slot holds all the mass the filter kept: no scoring needed unless it is the empty one
+            const int k1 = ca * CHUNK + (__ffs(ma) - 1);
+            if (k1 < K) pick = k1;
+        }
 #pragma unroll 1
         for (int phase = 0; phase < 2 && pick < 0; ++phase) {
             LseAcc acc;
@@ -524,6 +429,21 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_choose_kernel(
         if (pick < 0) pick = K_max - 1;                            // utils.draw falls through to the last slot
         if (j == 0) choice[id] = pick;
     }
+}
+
+// exhaustive exact scan of the rows listed in fb_list[0 .. *n_fallback)
+int launch_full(const float *X, int D, int K_max, int aniso, const void *model, const int32_t *fb_list,
+                const int64_t *n_fallback, double *log_marg, int32_t *map_k, cudaStream_t st) {
+    const size_t fsm = sizeof(double) * ((size_t)D * FULL_R + 40);
+    if (fsm > 48 * 1024) { set_error("D=%d too large for the exhaustive log_marg scan", D); return SEGB_E_UNSUPPORTED; }
+    if (aniso)
+        fv_full_kernel<true><<<148 * 4, FULL_THREADS, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
+                                                                  (const unsigned long long *)n_fallback, log_marg, map_k);
+    else
+        fv_full_kernel<false><<<148 * 4, FULL_THREADS, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
+                                                                   (const unsigned long long *)n_fallback, log_marg, map_k);
+    SEGB_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace fvf
@@ -588,7 +508,8 @@ extern "C" int segb_fvf_filter(const void *x_tiles, const void *w_tiles, int64_t
 
 extern "C" int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, int32_t aniso,
                                const void *model, const void *cand, const float *x_err, const float *w_max, float T,
-                               void *work, double *log_marg, int32_t *map_k, int64_t *n_fallback, void *stream) {
+                               void *work, double *log_marg, int32_t *map_k, void *rec_out, int64_t *n_fallback,
+                               void *stream) {
     SEGB_CHECK_ARG(X && model && cand && x_err && w_max && work && log_marg && n_fallback, "null pointer");
     SEGB_CHECK_ARG(n_emb > 0 && n_emb < (1ll << 31), "row count");
     cudaStream_t st = (cudaStream_t)stream;
@@ -600,22 +521,13 @@ extern "C" int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t
     if (aniso)
         fv_refine_kernel<true><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
-            map_k, (unsigned long long *)n_fallback, fb_list);
+            map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list);
     else
         fv_refine_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
-            map_k, (unsigned long long *)n_fallback, fb_list);
+            map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list);
     SEGB_LAUNCH_CHECK();
-    const size_t fsm = sizeof(double) * ((size_t)D * FULL_R + 40);
-    if (fsm > 48 * 1024) { set_error("D=%d too large for the exhaustive log_marg scan", D); return SEGB_E_UNSUPPORTED; }
-    if (aniso)
-        fv_full_kernel<true><<<148 * 4, FULL_THREADS, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
-                                                                  (const unsigned long long *)n_fallback, log_marg, map_k);
-    else
-        fv_full_kernel<false><<<148 * 4, FULL_THREADS, fsm, st>>>(X, D, K_max, (const double *)model, fb_list,
-                                                                   (const unsigned long long *)n_fallback, log_marg, map_k);
-    SEGB_LAUNCH_CHECK();
-    return 0;
+    return fvf::launch_full(X, D, K_max, aniso ? 1 : 0, model, fb_list, n_fallback, log_marg, map_k, st);
 }
 
 extern "C" int segb_fixedvar_band_scores(const segb_corpus *c, int64_t pos_first, int64_t n_positions,
@@ -632,11 +544,11 @@ extern "C" int segb_fixedvar_band_scores(const segb_corpus *c, int64_t pos_first
 }
 
 extern "C" int segb_fvf_choose_tokens(const float *X, int32_t D, int32_t K_max, int32_t K, int32_t aniso,
-                                      const void *model, const void *cand, const float *x_err, const float *w_max,
-                                      float T, const segb_corpus *c, int64_t pos_first, int64_t n_positions,
-                                      int32_t mode, const int32_t *map_k, const double *uniforms, int32_t *choice,
-                                      void *stream) {
-    SEGB_CHECK_ARG(X && model && cand && x_err && w_max && c && choice, "null pointer");
+                                      const void *model, const void *recs, const segb_corpus *c, int64_t pos_first,
+                                      int64_t n_positions, int32_t mode, const int32_t *map_k, const double *uniforms,
+                                      int32_t *choice, void *stream) {
+    SEGB_CHECK_ARG(X && model && c && choice, "null pointer");
+    SEGB_CHECK_ARG(mode == 1 || recs, "mode 0 needs the row records");
     SEGB_CHECK_ARG(mode == 0 || mode == 1, "mode");
     SEGB_CHECK_ARG(mode == 1 ? (map_k != nullptr) : (uniforms != nullptr), "mode 1 needs map_k, mode 0 uniforms");
     SEGB_CHECK_ARG(pos_first >= 0 && n_positions >= 0 && pos_first + n_positions <= c->n_pos, "position range");
@@ -645,15 +557,14 @@ extern "C" int segb_fvf_choose_tokens(const float *X, int32_t D, int32_t K_max, 
     cudaStream_t st = (cudaStream_t)stream;
     int64_t blocks = (n_positions * 8 + REFINE_THREADS - 1) / REFINE_THREADS;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    const int KP = kp_of(D, aniso ? 1 : 0) * nch_of(aniso ? 1 : 0), n_chunks = w_rows_pad(K_max) / CHUNK;
     if (aniso)
         fv_choose_kernel<true><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
-            X, D, K_max, K, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_chunks, *c, pos_first,
-            n_positions, mode, map_k, uniforms, choice);
+            X, D, K_max, K, (const double *)model, (const RowRec *)recs, *c, pos_first, n_positions, mode, map_k,
+            uniforms, choice);
     else
         fv_choose_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
-            X, D, K_max, K, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_chunks, *c, pos_first,
-            n_positions, mode, map_k, uniforms, choice);
+            X, D, K_max, K, (const double *)model, (const RowRec *)recs, *c, pos_first, n_positions, mode, map_k,
+            uniforms, choice);
     SEGB_LAUNCH_CHECK();
     return 0;
 }

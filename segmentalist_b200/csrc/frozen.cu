@@ -258,15 +258,39 @@ __global__ void fv_relabel_kernel(segb_corpus c, int64_t pos_first, int64_t n_po
 // ---- k-means clean_components replayed on the counts (single thread), then applied in parallel
 // slot_src[s] = the component that ends up in slot s after the swap-with-last deletions of the
 // emptied components in descending order (kmeans_components.py:263-266 -> :149-166).
-__global__ void km_compaction_plan_kernel(const long long *cnt, const int32_t *K_old_p, int32_t *slot_src, int32_t *inv,
-                                          int32_t *K_new) {
+__global__ void __launch_bounds__(1024) km_compaction_plan_kernel(const long long *cnt, const int32_t *K_old_p,
+                                                                  int32_t *slot_src, int32_t *inv, int32_t *K_new,
+                                                                  int32_t *empties) {
+    // Parallel part: identity map and the list of emptied components in DESCENDING order (block scan over
+    // the reversed index range).  Serial part (thread 0): the swap-with-last replay over that list only --
+    // normally empty or a handful of entries, so the kernel costs microseconds, not K dependent loads.
+    __shared__ int wsum[32];
+    __shared__ int carry;
     const int K_old = *K_old_p;
+    if (threadIdx.x == 0) carry = 0;
     for (int k = threadIdx.x; k < K_old; k += blockDim.x) slot_src[k] = k;
     __syncthreads();
+    for (int lo = 0; lo < K_old; lo += 1024) {
+        const int i = lo + threadIdx.x;                       // position in the reversed range
+        const int k = K_old - 1 - i;
+        const int v = (i < K_old && cnt[k] == 0) ? 1 : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        int wb = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wb += wsum[w];
+        const int c0 = carry;
+        if (v) empties[c0 + wb + inc - 1] = k;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c0 + wb + inc;
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
+        const int n_empty = carry;
         int K = K_old;
-        for (int k = K_old - 1; k >= 0; --k) {
-            if (cnt[k] != 0) continue;
+        for (int i = 0; i < n_empty; ++i) {
+            const int k = empties[i];
             --K;
             if (k != K) slot_src[k] = slot_src[K];
         }
@@ -405,11 +429,11 @@ extern "C" int segb_fixedvar_frozen_update(const segb_fixedvar *m, const segb_co
 
 extern "C" int segb_kmeans_frozen_clean(const segb_kmeans *m, const segb_corpus *c, int64_t pos_first,
                                         int64_t n_positions, const int64_t *cnt, void *work, void *stream) {
-    // work: segb_kmeans_frozen_clean_work_bytes() bytes: slot_src [K_max] | inv [K_max] | K_new, K_old | snapshots
+    // work: segb_kmeans_frozen_clean_work_bytes() bytes: slot_src [K_max] | inv [K_max] | empties [K_max] | K_new, K_old | snapshots
     SEGB_CHECK_ARG(m && c && cnt && work, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int KM = m->K_max, D = m->D;
-    int32_t *slot_src = (int32_t *)work, *inv = slot_src + KM, *K_new = inv + KM;
+    int32_t *slot_src = (int32_t *)work, *inv = slot_src + KM, *empties = inv + KM, *K_new = empties + KM;
     unsigned char *q = (unsigned char *)(K_new + 2);
     q += (16 - ((uintptr_t)q & 15)) & 15;
     double *num_in = (double *)q; q += sizeof(double) * (size_t)KM * D;
@@ -419,7 +443,7 @@ extern "C" int segb_kmeans_frozen_clean(const segb_kmeans *m, const segb_corpus 
     SEGB_CUDA(cudaMemcpyAsync(num_in, m->mean_num, sizeof(double) * (size_t)KM * D, cudaMemcpyDeviceToDevice, st));
     SEGB_CUDA(cudaMemcpyAsync(cnt_in, cnt, sizeof(long long) * (size_t)KM, cudaMemcpyDeviceToDevice, st));
     SEGB_CUDA(cudaMemcpyAsync(means_in, m->means, esz * (size_t)KM * D, cudaMemcpyDeviceToDevice, st));
-    km_compaction_plan_kernel<<<1, 1024, 0, st>>>((const long long *)cnt, m->K, slot_src, inv, K_new);
+    km_compaction_plan_kernel<<<1, 1024, 0, st>>>((const long long *)cnt, m->K, slot_src, inv, K_new, empties);
     SEGB_LAUNCH_CHECK();
     if (m->x_is_f64)
         km_compaction_apply_kernel<double><<<KM, 128, 0, st>>>(*m, slot_src, K_new, num_in, cnt_in, (const double *)means_in);
@@ -435,5 +459,5 @@ extern "C" int segb_kmeans_frozen_clean(const segb_kmeans *m, const segb_corpus 
 }
 
 extern "C" int64_t segb_kmeans_frozen_clean_work_bytes(int32_t K_max, int32_t D) {
-    return (int64_t)(2 * K_max + 2) * 4 + 16 + (int64_t)K_max * D * 8 + (int64_t)K_max * 8 + (int64_t)K_max * D * 8;
+    return (int64_t)(3 * K_max + 2) * 4 + 16 + (int64_t)K_max * D * 8 + (int64_t)K_max * 8 + (int64_t)K_max * D * 8;
 }

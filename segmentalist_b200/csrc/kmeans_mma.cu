@@ -37,6 +37,7 @@
 //                          maxima in registers; nothing but 32 B per embedding ever goes back
 //                          to HBM)
 #include "mma_common.cuh"
+#include "refine_rows.cuh"
 
 namespace segb {
 namespace mma {
@@ -76,44 +77,6 @@ struct FilterParams {
     int32_t tau_kind;              // TAU_KMEANS: argmax filter (2 * bound); TAU_LSE: logsumexp filter (tau_T + 2 * bound)
     float tau_T;
 };
-
-// Insert a chunk maximum into the running top-3.  A chunk that becomes the new BEST also records
-// which of its 16 members lie within tau_c of the chunk maximum (the only ones the refine has to
-// score); a chunk entering as runner-up keeps all 16 (it is only visited for the rare rows whose
-// runner-up chunk is inside the bound).  Only the new-best case is a (divergent) branch; the
-// runner-up / third-place updates are selects, so the common path is straight-line code.
-__device__ __forceinline__ void top3_insert(const float *vv, float cm, int cid, float tau_c, float &m1, float &m2,
-                                            float &m3, int &i1, int &i2, uint32_t &k1, uint32_t &k2) {
-    const bool p2 = cm > m2;
-    m3 = p2 ? m2 : fmaxf(m3, cm);
-    if (cm > m1) {
-        // member j is kept iff vv[j] >= cm - tau_c, i.e. the sign bit of (vv[j] - thr) is clear; the
-        // sign bits are funnel-shifted into two 8-bit chains (member 15 first, so bit j = member j)
-        const float thr = cm - tau_c;
-        uint32_t hi = 0, lo = 0;
-#pragma unroll
-        for (int j = 7; j >= 0; --j) {
-            hi = __funnelshift_l(__float_as_uint(vv[8 + j] - thr), hi, 1);
-            lo = __funnelshift_l(__float_as_uint(vv[j] - thr), lo, 1);
-        }
-        m2 = m1; i2 = i1; k2 = k1;
-        m1 = cm; i1 = cid; k1 = ~((hi << 8) | lo) & 0xffffu;
-    } else {
-        m2 = p2 ? cm : m2; i2 = p2 ? cid : i2; k2 = p2 ? 0xffffu : k2;
-    }
-}
-
-// same insertion with the member mask already known (merging two partial top-3 lists)
-__device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float &m1, float &m2, float &m3, int &i1,
-                                           int &i2, uint32_t &k1, uint32_t &k2) {
-    if (cm > m3) {
-        if (cm > m2) {
-            m3 = m2;
-            if (cm > m1) { m2 = m1; i2 = i1; k2 = k1; m1 = cm; i1 = cid; k1 = mk; }
-            else { m2 = cm; i2 = cid; k2 = mk; }
-        } else m3 = cm;
-    }
-}
 
 // KS = number of K=16 steps per chunk when known at compile time (fully unrolled issue loop), 0 = runtime.
 // NCH = chunks of the inner dimension (1: k-means and isotropic FBGMM; 2: anisotropic FBGMM, whose
@@ -581,20 +544,11 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
     segb_kmeans m, const Cand *cand, const float *x_err, const float *w_max, int64_t n_emb, int n_chunks,
     float *best_val, int32_t *best_k, unsigned long long *n_fallback, int32_t *fb_list) {
     const int D = m.D, KM = m.K_max;
-    const int lane = threadIdx.x & 31, j = lane & 7, g = j >> 2, c = j & 3;
-    const unsigned gmask = 0xffu << (lane & 24);
-    const int gbase = lane & 24;
+    const int lane = threadIdx.x & 31, j = lane & 7;
+    const Row8Geom geo(D, lane);
     const float *X = (const float *)m.X;
     const float *means = (const float *)m.means;
     const float e_mu = w_max[0], n_mu = w_max[1];
-    int n2 = 0;
-    if (D > 128) { n2 = D / 2; n2 -= n2 % 8; }
-    const int lo_g = g == 0 ? 0 : n2;
-    const int n_g = (D > 128) ? (g == 0 ? n2 : D - n2) : (g == 0 ? D : 0);
-    const int n8_g = n_g >= 8 ? n_g - (n_g % 8) : 0;
-    const int steps = n8_g / 8;
-    const bool two_blocks = D > 128;
-
     const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
     for (int64_t row = grp_global; row < n_emb; row += grp_total) {
@@ -606,49 +560,9 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
             if (j == 0) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;      // -> refine_full_kernel
             continue;
         }
-        const float *xr = X + row * D;
-        const float2 *xr2 = reinterpret_cast<const float2 *>(xr + lo_g + 2 * c);
-        float2 xv[MAXS];
-#pragma unroll
-        for (int i = 0; i < MAXS; ++i) xv[i] = (i < steps) ? xr2[i * 4] : make_float2(0.f, 0.f);
-        float bv = -CUDART_INF_F;
-        int bk = 0x7fffffff;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            uint32_t mk = pass == 0 ? (cd.masks & 0xffffu) : (code >= 0 ? (cd.masks >> 16) : 0u);
-            const int chunk = pass == 0 ? cd.i1 : cd.i2;
-            while (mk) {
-                const int bit = __ffs(mk) - 1;
-                mk &= mk - 1;
-                const int k = chunk * CHUNK + bit;
-                if (k >= KM) continue;
-                const float *mu = means + (size_t)k * D;
-                const float2 *mu2 = reinterpret_cast<const float2 *>(mu + lo_g + 2 * c);
-                float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                for (int i = 0; i < MAXS; ++i) {
-                    if (i < steps) {
-                        const float2 mv = mu2[i * 4];
-                        const float d0 = __fsub_rn(mv.x, xv[i].x), d1 = __fsub_rn(mv.y, xv[i].y);
-                        const float p0 = __fmul_rn(d0, d0), p1 = __fmul_rn(d1, d1);
-                        a0 = (i == 0) ? p0 : __fadd_rn(a0, p0);
-                        a1 = (i == 0) ? p1 : __fadd_rn(a1, p1);
-                    }
-                }
-                float acc = __fadd_rn(a0, a1);                                   // r[2c] + r[2c+1]
-                acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, 1));
-                acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, 2));
-                if (n8_g == 0) acc = 0.f;
-                for (int d = lo_g + n8_g; d < lo_g + n_g; ++d) {                 // the block's n % 8 trailing terms
-                    const float dl = __fsub_rn(mu[d], xr[d]);
-                    acc = __fadd_rn(acc, __fmul_rn(dl, dl));
-                }
-                float tot = __shfl_sync(gmask, acc, gbase);
-                if (two_blocks) tot = __fadd_rn(tot, __shfl_sync(gmask, acc, gbase + 4));
-                const float v = -tot;
-                if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; }
-            }
-        }
+        float bv;
+        int bk;
+        km_exact_row8<MAXS>(means, KM, D, X + row * D, cd.i1, cd.i2, cd.masks, code, geo, bv, bk);
         if (j == 0) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
     }
 }
@@ -777,6 +691,19 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     return launch_filter(f, (cudaStream_t)stream);
 }
 
+namespace segb {
+namespace mma {
+// exhaustive exact scan of the rows listed in fb_list[0 .. *n_fallback)
+int launch_refine_full(const segb_kmeans *m, const int32_t *fb_list, const int64_t *n_fallback, float *best_val,
+                       int32_t *best_k, cudaStream_t st) {
+    refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(
+        *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace mma
+}  // namespace segb
+
 extern "C" int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max) {
     (void)K_max;
     return (n_emb + 64) * (int64_t)sizeof(int32_t);
@@ -819,8 +746,5 @@ extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const flo
             *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
             (unsigned long long *)n_fallback, fb_list);
     SEGB_LAUNCH_CHECK();
-    refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(
-        *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
-    SEGB_LAUNCH_CHECK();
-    return 0;
+    return launch_refine_full(m, fb_list, n_fallback, best_val, best_k, st);
 }

@@ -192,6 +192,48 @@ __device__ __forceinline__ int refine_decide(const Cand &c, float tau, int n_chu
     return -1;
 }
 
+// Insert a chunk maximum into the running top-3.  A chunk that becomes the new BEST also records
+// which of its 16 members lie within tau_c of the chunk maximum (the only ones the refine has to
+// score); a chunk entering as runner-up keeps all 16 (it is only visited for the rare rows whose
+// runner-up chunk is inside the bound).  Only the new-best case is a (divergent) branch; the
+// runner-up / third-place updates are selects, so the common path is straight-line code.
+__device__ __forceinline__ void top3_insert(const float *vv, float cm, int cid, float tau_c, float &m1, float &m2,
+                                            float &m3, int &i1, int &i2, uint32_t &k1, uint32_t &k2) {
+    const bool p2 = cm > m2;
+    m3 = p2 ? m2 : fmaxf(m3, cm);
+    if (cm > m1) {
+        // member j is kept iff vv[j] >= cm - tau_c, i.e. the sign bit of (vv[j] - thr) is clear; the
+        // sign bits are funnel-shifted into two 8-bit chains (member 15 first, so bit j = member j)
+        const float thr = cm - tau_c;
+        uint32_t hi = 0, lo = 0;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            hi = __funnelshift_l(__float_as_uint(vv[8 + j] - thr), hi, 1);
+            lo = __funnelshift_l(__float_as_uint(vv[j] - thr), lo, 1);
+        }
+        m2 = m1; i2 = i1; k2 = k1;
+        m1 = cm; i1 = cid; k1 = ~((hi << 8) | lo) & 0xffffu;
+    } else {
+        m2 = p2 ? cm : m2; i2 = p2 ? cid : i2; k2 = p2 ? 0xffffu : k2;
+    }
+}
+
+// same insertion with the member mask already known (merging two partial top-3 lists)
+__device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float &m1, float &m2, float &m3, int &i1,
+                                           int &i2, uint32_t &k1, uint32_t &k2) {
+    if (cm > m3) {
+        if (cm > m2) {
+            m3 = m2;
+            if (cm > m1) { m2 = m1; i2 = i1; k2 = k1; m1 = cm; i1 = cid; k1 = mk; }
+            else { m2 = cm; i2 = cid; k2 = mk; }
+        } else m3 = cm;
+    }
+}
+
+// What survives of a filter record once the row's threshold has been applied: the chunks to visit, the
+// member masks and refine_decide's code.  16 bytes.
+struct __align__(16) RowRec { int32_t i1, i2; uint32_t masks; int32_t code; };
+
 constexpr int TAU_KMEANS = 0, TAU_LSE = 1;
 
 // Launch description of the filter GEMM over pre-packed tile images (host side).
@@ -208,6 +250,16 @@ struct FilterLaunch {
     float tau_T;
 };
 int launch_filter(const FilterLaunch &f, cudaStream_t stream);
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (load + wait in one statement)
+__device__ __forceinline__ void tc_ld32_wait(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
 
 }  // namespace mma
 }  // namespace segb

@@ -479,10 +479,15 @@ def test_kmeans_wordseg_golden(sb, init):
     npt.assert_array_equal(rec["components"], z[p + "rec_components"])
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("K_max,n_emb,K_true,noise", [(300, 5000, 40, 0.05), (1000, 3000, 1000, 0.05),
-                                                       (37, 700, 5, 0.3), (5000, 2100, 200, 0.05)])
-def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
-    """tcgen05 filter GEMM + refine == exact SIMT scorer == oracle (float32 bit patterns, argmax)."""
+                                                       (37, 700, 5, 0.3), (5000, 2100, 200, 0.05),
+                                                       (700, 100000, 700, 0.05)])
+def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise, fused):
+    """tcgen05 filter GEMM + refine == exact SIMT scorer == oracle (float32 bit patterns, argmax), for the
+    fused kernel (fp32 rows converted in shared memory, refine behind the GEMM) and the two-kernel path.
+    100000 rows: every CTA of the persistent kernels takes several work items (operand double buffering,
+    record hand-over between epilogue and refine warps)."""
     from segmentalist_b200 import _lib, synth
     from segmentalist_b200.kmeans_components import KMeansComponents
     rng = np.random.RandomState(K_max)
@@ -496,7 +501,7 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
     comps = KMeansComponents(X, assign, K_max)
     val_e, arg_e = comps.best(None)
     from segmentalist_b200.batch import MmaScorer
-    mma = MmaScorer(comps)
+    mma = MmaScorer(comps, fused=fused)
     val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
     arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
     mma.score(val, arg)
@@ -504,11 +509,12 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise):
     torch.cuda.synchronize()
     npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
     npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
-    # the filter's own approximate maxima track the exact ones (sanity of the GEMM itself)
-    rec = cand.cpu().numpy().view(np.float32).reshape(n_emb, 8)
-    xn = (X.astype(np.float64) ** 2).sum(axis=1)
-    approx_s = 2.0 * rec[:, 0] - xn
-    assert np.max(np.abs(approx_s - val_e.cpu().numpy())) < 5e-3
+    if not fused:
+        # the filter's own approximate maxima track the exact ones (sanity of the GEMM itself)
+        rec = cand.cpu().numpy().view(np.float32).reshape(n_emb, 8)
+        xn = (X.astype(np.float64) ** 2).sum(axis=1)
+        approx_s = 2.0 * rec[:, 0] - xn
+        assert np.max(np.abs(approx_s - val_e.cpu().numpy())) < 5e-3
     assert int(nfb.item()) < n_emb // 2
     # oracle spot check on a few rows (C emulation of NumPy float32 order)
     import ctypes
@@ -550,9 +556,10 @@ def test_frozen_fit_equals_reference_kmeans_fit(sb):
     npt.assert_array_equal(c.means, oc.means)
 
 
-def test_mma_scorer_streamed_from_host(sb):
+@pytest.mark.parametrize("fused", [True, False])
+def test_mma_scorer_streamed_from_host(sb, fused):
     """Scoring embeddings uploaded chunk by chunk from pinned host memory (copy stream overlapped
-    with packing + filter + refine) gives the same bits as scoring the resident matrix; the
+    with scoring) gives the same bits as scoring the resident matrix; the
     device copy of X is scrambled first so that only the streamed upload can make it pass."""
     from segmentalist_b200 import synth
     from segmentalist_b200.batch import MmaScorer
@@ -565,7 +572,7 @@ def test_mma_scorer_streamed_from_host(sb):
     assign[:1500] = np.arange(1500) % K_max
     np.random.seed(1)
     comps = KMeansComponents(X, assign, K_max)
-    mma = MmaScorer(comps)
+    mma = MmaScorer(comps, fused=fused)
     val0 = torch.empty(n_emb, dtype=torch.float32, device="cuda")
     arg0 = torch.empty(n_emb, dtype=torch.int32, device="cuda")
     mma.score(val0, arg0)
@@ -809,7 +816,8 @@ def test_bigram_gibbs_golden(sb, tag):
 def test_mma_scorer_other_dims(sb, D):
     """The tensor-core scorer away from the benchmark's D = 130: runtime-K issue loop (KS = 0), odd D
     (16-lane refine), one block of NumPy's pairwise sum (D <= 128), and D = 200 where the shared-memory
-    budget only allows single-buffered A tiles.  Bit-exact against the exact float32 kernel."""
+    budget only allows single-buffered A tiles (D = 16, 64, 100 take the fused kernel, 131 and 200 the
+    two-kernel path).  Bit-exact against the exact float32 kernel."""
     from segmentalist_b200 import synth
     from segmentalist_b200.batch import MmaScorer
     from segmentalist_b200.kmeans_components import KMeansComponents
@@ -917,6 +925,14 @@ def test_fv_filter_log_marg(sb, kind, K_max, n_assigned, n_emb):
     exact = am.log_marg_all(tensor_cores=False)
     tc = am.log_marg_all(tensor_cores=True, method="filter")
     n_fb = int(am._fv.n_fallback.item())
+    if am._fv.fused:
+        # the two-kernel path (pre-packed fp16 image, filter, refine) must agree with the fused kernel
+        from segmentalist_b200.batch import FvScorer
+        fv2 = FvScorer(am.components, fused=False)
+        fv2.score()
+        tc2 = fv2.log_marg.cpu().numpy()
+        npt.assert_allclose(tc2, tc, rtol=1e-12, atol=1e-12)
+        npt.assert_array_equal(fv2.map_k.cpu().numpy(), am._fv.map_k.cpu().numpy())
     err = np.abs(tc - exact)
     assert (err / np.abs(exact)).max() < 1e-4
     assert err.max() < 2e-5, err.max()                  # dropped mass <= K_max * exp(-20) + float64 rounding

@@ -24,6 +24,7 @@ ap.add_argument("--tokens-per-k", type=int, default=4)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--aniso", action="store_true")
 ap.add_argument("--noise", type=float, default=0.05)
+ap.add_argument("--two-kernel", action="store_true")
 args = ap.parse_args()
 D, K = 130, args.K
 K_true = args.K_true or K
@@ -48,7 +49,7 @@ _, first = np.unique(zh, return_index=True)        # component = cluster, labels
 rank = np.empty(K_true, dtype=np.int64)
 rank[zh[np.sort(first)]] = np.arange(len(first))
 am.components._add_many(np.arange(n_tok), rank[zh])
-fv = FvScorer(am.components)
+fv = FvScorer(am.components, fused=(False if args.two_kernel else None))
 fv.score()
 torch.cuda.synchronize()
 
@@ -64,15 +65,17 @@ def timed(fn, reps):
 
 
 t_pack = timed(fv.pack_model, args.reps)
-t_filter = timed(fv.filter, args.reps)
-t_refine = timed(fv.refine, args.reps)
+if fv.fused:
+    t_filter, t_refine = timed(fv.fused_score, args.reps), 0.0
+else:
+    t_filter, t_refine = timed(fv.filter, args.reps), timed(fv.refine, args.reps)
 
 fl = (4.0 if args.aniso else 2.0) * D * args.rows * K
 out = fv.log_marg.cpu().numpy()
 ids = np.arange(n_tok, n_tok + 4096) if args.rows >= n_tok + 4096 else np.arange(min(4096, args.rows))
 exact = am.log_marg_items(ids)
 err = np.abs(out[ids] - exact)
-print(json.dumps({"rows": args.rows, "K": K, "K_act": am.components.K, "aniso": bool(args.aniso),
+print(json.dumps({"fused": fv.fused, "rows": args.rows, "K": K, "K_act": am.components.K, "aniso": bool(args.aniso),
                   "pack_model_ms": t_pack, "filter_ms": t_filter, "refine_ms": t_refine,
                   "filter_tflops_algorithmic": fl / t_filter / 1e9,
                   "score_tflops_algorithmic": fl / (t_pack + t_filter + t_refine) / 1e9,
