@@ -55,19 +55,21 @@ def parse_args():
     ap.add_argument("--K", type=int, default=K_MAX)
     ap.add_argument("--cpu-sample", type=int, default=32, help="utterances timed by the CPU baseline leg")
     ap.add_argument("--scorer", default="mma", choices=["mma", "exact"])
-    ap.add_argument("--two-kernel", action="store_true", help="pre-packed fp16 image + filter kernel + refine kernel instead of the fused score kernel")
+    ap.add_argument("--fused", action="store_true", help="the fused score kernel (fp32 rows in, conversion + filter GEMM + refine in one launch) instead of pre-packed fp16 image + filter kernel + refine kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gibbs", action="store_true", help="skip the sequential secondary workloads (BASELINE configs[1], [3], [4])")
     ap.add_argument("--no-fbgmm", action="store_true", help="skip the sharded frozen FBGMM sweep")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the set-up timing through the public constructor")
+    ap.add_argument("--ingest-utts", type=int, default=TOTAL_UTTS)
     ap.add_argument("--no-diffuse", action="store_true", help="skip the diffuse-model k-means sweep (K_act < K_max)")
     ap.add_argument("--fbgmm-utts", type=int, default=0, help="utterances of the frozen FBGMM sweep (default: --utts)")
     ap.add_argument("--diffuse-utts", type=int, default=40000)
     ap.add_argument("--gibbs-utts", type=int, default=2000)
     ap.add_argument("--only-gibbs", action="store_true", help="run only the secondary Gibbs workload")
-    ap.add_argument("--diag-utts", type=int, default=48)
+    ap.add_argument("--diag-utts", type=int, default=400)
     ap.add_argument("--only-diag", action="store_true", help="run only the diagonal-covariance secondary workload")
-    ap.add_argument("--bigram-utts", type=int, default=400)
+    ap.add_argument("--bigram-utts", type=int, default=4000)
     ap.add_argument("--only-bigram", action="store_true", help="run only the bigram cluster-sampling secondary workload")
     return ap.parse_args()
 
@@ -378,6 +380,29 @@ def run_reference_arm(args):
 # secondary workload: sequential collapsed Gibbs (BASELINE configs[1]); replicas only, so N = 1
 # ------------------------------------------------------------------------------------------------
 
+def measure_fp64_peak():
+    """Dense float64 throughput of this GPU (TFLOP/s): cuBLAS DGEMM 4096^3, best of 3 -- the denominator of the
+    Gibbs sweep's float64 roofline (MEASURED_PEAKS.json has no float64 entry)."""
+    import torch
+    try:
+        n = 4096
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
 def run_gibbs_extra(args):
     """UnigramAcousticWordseg.gibbs_sample on synthetic D=130, K=1000, 2k utterances, max_span 6,
     through the reference-facing API; CPU oracle timed on a bounded sample of the same corpus
@@ -413,11 +438,48 @@ def run_gibbs_extra(args):
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / reps
     dev_s = ev0.elapsed_time(ev1) * 1e-3 / reps
+    K_act = seg.acoustic_model.components.K
+    n_tok0 = seg.acoustic_model.get_n_assigned()
+    # float64 roofline: 4 flop per (segment or token, ACTIVE component, dimension): mu - x, its square, times the
+    # predictive precision, accumulate (gaussian_components_fixedvar.py:247-252); candidates are scored once per
+    # sweep, tokens once more for their assignment draw
+    fp64_flops = 4.0 * D * K_act * (n_seg + n_tok0)
+    peak64 = measure_fp64_peak()
     out = {"workload": "unigram_fbgmm_fixedvar_gibbs_sweep D=130 K=1000 U=%d max_span=6 (BASELINE configs[1])" % n_utt,
            "utt_per_s": n_utt / max(wall, dev_s), "ms_per_sweep": max(wall, dev_s) * 1e3,
-           "device_ms_per_sweep": dev_s * 1e3, "candidate_segments": n_seg,
+           "device_ms_per_sweep": dev_s * 1e3, "us_per_utterance": dev_s * 1e6 / n_utt, "candidate_segments": n_seg,
            "segment_component_evals_per_s": n_seg * K / max(wall, dev_s),
-           "K_active": seg.acoustic_model.components.K, "setup_s": setup_s, "dtype": "f64"}
+           "K_active": K_act, "setup_s": setup_s, "dtype": "f64",
+           "roofline": {"kernel": "fv_gibbs_kernel (cooperative, sequential collapsed Gibbs: latency-bound by construction)",
+                        "bound": "fp64", "achieved": fp64_flops / dev_s / 1e12, "peak": peak64, "unit": "TFLOP/s",
+                        "frac": fp64_flops / dev_s / 1e12 / peak64 if peak64 else None,
+                        "peak_source": "measured in this run: torch.matmul float64 4096^3 (cuBLAS DGEMM), best of 3",
+                        "algorithmic_flops_per_sweep": fp64_flops,
+                        "note": "one chain cannot fill the GPU: every token's draw sees the statistics left by the previous one"}}
+    # replicas: R independent chains side by side, each a cooperative launch with n_sm / R CTAs
+    try:
+        reps_out = []
+        for R in (2, 4):
+            segs, rngs = [], []
+            for r in range(R):
+                random.seed(100 + r)
+                np.random.seed(100 + r)
+                segs.append(uaw.UnigramAcousticWordseg(fbgmm.FBGMM, 10., K, prior, mats, vids, durs, lms, p_boundary_init=0.5,
+                                                       beta_sent_boundary=-1, n_slices_max=S_MAX))
+                rngs.append(random.Random(200 + r))
+            orders = [order] * R
+            uaw.run_replica_sweeps(segs, orders, rngs)             # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            uaw.run_replica_sweeps(segs, orders, rngs)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            reps_out.append({"replicas": R, "ms_per_replica_sweep": dt * 1e3, "aggregate_utt_per_s": R * n_utt / dt,
+                             "us_per_utterance_per_chain": dt * 1e6 / n_utt})
+            del segs
+        out["replicas"] = reps_out
+    except Exception as exc:
+        out["replicas"] = {"error": repr(exc)}
     # whole-model resampling between sweeps (FBGMM.gibbs_sample, consider_unassigned=False): one
     # cooperative launch over all assigned tokens
     n_tok = seg.acoustic_model.get_n_assigned()
@@ -467,7 +529,7 @@ def run_diag_extra(args):
     from segmentalist_b200 import fbgmm, synth, unigram_acoustic_wordseg as uaw
     from segmentalist_b200.niw import NIW
     K, n_utt = 5000, args.diag_utts
-    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=400, n_min=100, n_max=120,
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K, n_min=100, n_max=120,
                                                     n_slices_max=S_MAX, noise=NOISE, seed=53)
     prior_args = dict(m_0=np.zeros(D), k_0=0.05, v_0=D + 3, S_0=0.002 * np.ones(D))
 
@@ -489,7 +551,15 @@ def run_diag_extra(args):
     out = {"workload": "unigram_fbgmm_diag_gibbs_sweep D=130 K_max=5000 U=%d N~U{100..120} max_span=6 (BASELINE configs[4])" % n_utt,
            "utt_per_s": n_utt / wall, "ms_per_sweep": wall * 1e3, "candidate_segments": n_seg, "K_active": K_act,
            "student_t_log_evals_per_s": n_seg * float(K_act) * D / wall, "dtype": "f64",
-           "note": "K_active < K_max: %d tokens cannot populate 5000 components; evals counted over active components" % seg.acoustic_model.get_n_assigned()}
+           "tokens": int(seg.acoustic_model.get_n_assigned()),
+           "roofline": {"bound": "sfu (SURVEY 8d: D log evaluations per segment x component)",
+                        "achieved": n_seg * float(K_act) * D / wall, "peak": 16.0 * 148 * 1.965e9, "unit": "log evals/s",
+                        "frac": n_seg * float(K_act) * D / wall / (16.0 * 148 * 1.965e9),
+                        "peak_source": "16 MUFU lg2/clk/SM x 148 SMs x 1965 MHz (float32 special-function rate; nominal)",
+                        "note": "the reference's Student's t terms are float64 (gaussian_components_diag.py:347-360): log() is a "
+                                "~40-instruction float64 sequence here, not one MUFU op, so the float32 SFU bound is out of "
+                                "reach by construction; identical samples need float64"},
+           "note": "evals counted over the ACTIVE components of the sampled state"}
     if not args.no_cpu:
         n_cpu = 2
         oseg = build(so, so, so.NIW(**prior_args))
@@ -903,6 +973,68 @@ def kmeans_diffuse_secondary(args, world, rank, dev, barrier, max_over_ranks):
     return out
 
 
+def ingestion_secondary(args, dev):
+    """Set-up cost through the PUBLIC constructor at benchmark scale (process_embeddings
+    unigram_acoustic_wordseg.py:571-646, Utterances.__init__ utterances.py:74-157, the banded device layout):
+    SegmentalKMeansWordseg(K, embedding_mats, vec_ids_dict, durations_dict, landmarks_dict, ...) on
+    reference-format dicts of n utterances, timed on the host clock, phase by phase."""
+    import psutil
+    import torch
+    from segmentalist_b200 import kmeans_acoustic_wordseg as kaw, utterances as ut
+    n_utt = args.ingest_utts
+    if psutil.virtual_memory().available < 60e9:
+        n_utt = min(n_utt, 50000)
+    t0 = time.perf_counter()
+    lengths, seg_id, seg_dur, _, n_emb = corpus_structure(n_utt, seed=9000)
+    Xd, _ = make_embeddings_gpu(n_emb, torch.from_numpy(centres_cpu(args.K)).to(dev), seed=9001, device=dev)
+    X = Xd.cpu().numpy()
+    del Xd
+    pos_off = np.concatenate([[0], np.cumsum(lengths)])
+    emb_off = np.concatenate([[0], np.cumsum((seg_id >= 0).sum(axis=1))])[pos_off]      # embeddings before each utterance
+    mats, vids, durs, lms = {}, {}, {}, {}
+    S = S_MAX
+    for N in range(N_LO, N_HI + 1):                       # reference-format packed vectors, one length group at a time
+        idx = np.where(lengths == N)[0]
+        if len(idx) == 0:
+            continue
+        t = np.repeat(np.arange(1, N + 1), np.arange(1, N + 1))
+        j = np.arange(len(t)) - t * (t - 1) // 2
+        l = t - j
+        ok = l <= S
+        rows = pos_off[idx][:, None] + (t - 1)[None, :]
+        cols = np.where(ok, l - 1, 0)[None, :]
+        ids = np.where(ok[None, :], seg_id[rows, cols] - emb_off[idx][:, None], -1).astype(np.int64)
+        du = np.where(ok[None, :], np.nan_to_num(seg_dur[rows, cols], nan=-1.), -1).astype(np.int64)
+        for a, u in enumerate(idx):
+            label = "utt%07d" % u
+            vids[label], durs[label] = ids[a], du[a]
+            mats[label] = X[emb_off[u]:emb_off[u + 1]]
+            lms[label] = list(range(1, N + 1))
+    t_gen = time.perf_counter() - t0
+    import random
+    random.seed(1)
+    np.random.seed(1)
+    t0 = time.perf_counter()
+    emb, vec_ids, labels = ut.process_embeddings(mats, vids)
+    t_pe = time.perf_counter() - t0
+    del emb, vec_ids
+    t0 = time.perf_counter()
+    seg = kaw.SegmentalKMeansWordseg(args.K, mats, vids, durs, lms, n_slices_max=S, p_boundary_init=0.5,
+                                     init_am_assignments="spread")
+    torch.cuda.synchronize()
+    t_ctor = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rec = seg.segment_frozen(1)
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t0
+    return {"utterances": int(n_utt), "embeddings": int(n_emb), "setup_s": t_ctor,
+            "process_embeddings_s": t_pe, "first_frozen_sweep_s": t_first, "input_generation_s": t_gen,
+            "embeddings_per_s": n_emb / t_ctor, "components_after_first_sweep": rec["components"][-1],
+            "note": "setup_s = the whole public constructor (process_embeddings + Utterances incl. the random boundary "
+                    "initialisation + banded device layout + H2D of X + KMeans construction); vectorised host code, "
+                    "no per-utterance Python loop, no padded-triangular intermediate"}
+
+
 def bind_to_gpu_numa(local_rank):
     """Pin this process to the CPUs NVML reports as local to its GPU (and let first-touch place the pinned
     staging buffers on that NUMA node).  At 4-8 ranks the end-to-end path is host-bound: in round 1 every
@@ -999,9 +1131,10 @@ def run_ours(args):
     # inactive slots winning tokens, undecided rows) is measured separately below (secondary_kmeans_diffuse)
     tok = corpus.tok_id[corpus.tok_id >= 0].long()
     comps._assign[tok] = Z[tok]
-    sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer, fused=(False if args.two_kernel else None))
+    sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer, fused=bool(args.fused))
     sweep.init_means_from_assignments()
     sweep_fused = bool(sweep.mma is not None and sweep.mma.fused)
+    x_gb = X.numel() * 4 / 1e9
     n_pos, M = corpus.n_pos, n_emb
     evals_per_sweep_local = float(M) * args.K
 
@@ -1205,9 +1338,16 @@ def run_ours(args):
         except Exception as exc:
             diffuse = {"error": repr(exc)}
 
-    gibbs, diag_x, bigram_x = None, None, None
+    gibbs, diag_x, bigram_x, ingest = None, None, None, None
+    if rank == 0 and world == 1 and not args.no_ingest:
+        try:
+            del sweep, comps, X, Z, corpus
+            torch.cuda.empty_cache()
+            ingest = ingestion_secondary(args, dev)
+        except Exception as exc:
+            ingest = {"error": repr(exc)}
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_gibbs:
-        del sweep, comps
         torch.cuda.empty_cache()
         try:
             bigram_x = run_bigram_extra(args)
@@ -1235,13 +1375,13 @@ def run_ours(args):
                        "init": "tokens start in the component of their generating cluster (K_act = K_max)",
                        "parallelism": "utterance shards x%d + NCCL all-reduce(sum_x, counts)" % world,
                        "fused_scorer": bool(args.scorer == "mma" and sweep_fused),
-                       "l2": "inputs (%.1f GB of embeddings per rank) exceed L2; no flush needed" % (X.numel() * 4 / 1e9)},
+                       "l2": "inputs (%.1f GB of embeddings per rank) exceed L2; no flush needed" % x_gb},
             "segment_component_evals_per_s": evals_per_s,
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "roofline_dp": roofline_dp, "roofline_fixedvar_logmarg": roofline_fv, "cpu_baseline": cpu_baseline,
             "phases_ms": phases, "parity": parity,
-            "secondary_fbgmm_frozen": fbgmm_frozen, "secondary_kmeans_diffuse": diffuse,
+            "secondary_fbgmm_frozen": fbgmm_frozen, "secondary_kmeans_diffuse": diffuse, "ingestion": ingest,
             "secondary_gibbs_fixedvar": gibbs, "secondary_gibbs_diag": diag_x, "secondary_bigram": bigram_x,
         }
         print(json.dumps(line))

@@ -177,6 +177,10 @@ int segb_gibbs_sweep_fixedvar(const segb_fixedvar *m, const segb_corpus *c, cons
  * array; work: segb_gibbs_work_bytes() bytes of device scratch.  Returns SEGB_E_UNSUPPORTED when
  * the model does not fit the per-CTA shared memory (use segb_gibbs_sweep_fixedvar then).      */
 int64_t segb_gibbs_work_bytes(int32_t K_max, int32_t N_max, int32_t S);
+/* Replicas (sequential Gibbs does not shard; independent chains do): limit the CTAs of the following
+ * cooperative sweeps (0 = one per SM).  R chains with n_sm / R CTAs each, launched on R streams, run side by
+ * side; each chain keeps its own sequential order.  Process-wide setting.                               */
+int segb_gibbs_set_max_ctas(int32_t max_ctas);
 int segb_gibbs_sweep_fixedvar_coop(const segb_fixedvar *m, const segb_corpus *c, const int32_t *d_order,
                                    int32_t n_order, int32_t fb_mode, double time_power_term, double wip,
                                    double anneal_temp, int32_t anneal_gibbs_am,
@@ -482,6 +486,17 @@ int segb_fixedvar_log_marg_k(const segb_fixedvar *m, const int64_t *order, const
  * NumPy's pairwise order over the flattened array); the objective is the sum over k < K (host). */
 int segb_kmeans_sum_neg_sqrd_norm_k(const segb_kmeans *m, const int64_t *order, const int64_t *seg_off,
                                     double *out_k, void *stream);
+
+/* ------------------------------------------------------------------ ingestion (host) */
+
+/* The random boundary initialisation of Utterances.__init__ (utterances.py:136-157) for all utterances in
+ * order, HOST arrays, no device work: per utterance `rand(N) < p` is redrawn until the segmentation carries
+ * an embedding and respects the span limits.  uniforms: a block drawn in advance from np.random (consumed
+ * sequentially = the reference's stream).  Returns the number consumed, or -1 if the block ran out.     */
+int64_t segb_host_init_boundaries(const int64_t *lengths, int64_t n_utt, const int64_t *packed_off,
+                                  const int64_t *ids, const int64_t *pos_off, const double *uniforms,
+                                  int64_t n_uniforms, double p_boundary, int64_t n_slices_min,
+                                  int64_t n_slices_max, uint8_t *bounds_out);
 
 /* ------------------------------------------------------------------ development aids */
 

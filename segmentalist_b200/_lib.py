@@ -65,6 +65,7 @@ _PROTOS = {
                                                  c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp]),
     "segb_gibbs_work_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "segb_gibbs_set_max_ctas": (ctypes.c_int, [c_i32]),
     "segb_gibbs_sweep_fixedvar_coop": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(Corpus), c_vp, c_i32,
                                                       c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                       c_vp, c_vp]),
@@ -131,6 +132,7 @@ _PROTOS = {
     "segb_gibbs_sweep_bigram": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(BigramLM), ctypes.POINTER(Corpus),
                                                c_vp, c_i32, c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                c_vp, c_vp]),
+    "segb_host_init_boundaries": (c_i64, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_i64, c_i64, c_vp]),
     "segb_debug_gibbs_prof": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "segb_debug_gibbs_bar_base": (ctypes.c_int, [ctypes.c_uint32]),
     "segb_gibbs_sweep_bigram_coop": (ctypes.c_int, [ctypes.POINTER(FixedVar), ctypes.POINTER(BigramLM),

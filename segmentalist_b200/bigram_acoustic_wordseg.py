@@ -54,10 +54,7 @@ class BigramAcousticWordseg(object):
             [len(landmarks_dict[i]) for i in labels], vec_ids, [durations_dict[i] for i in labels],
             [landmarks_dict[i] for i in labels], seed_boundaries=seeds, p_boundary_init=p_boundary_init,
             n_slices_min=n_slices_min, n_slices_max=n_slices_max, min_duration=min_duration)
-        init_embeds = []
-        for u in range(self.utterances.D):
-            init_embeds.extend(self.utterances.get_segmented_embeds_i(u))
-        init_embeds = np.array(init_embeds, dtype=int)
+        init_embeds = self.utterances.all_segmented_embeds()     # get_segmented_embeds_i of every utterance, vectorised
         init_embeds = init_embeds[np.where(init_embeds != -1)]
 
         assert lm_params["type"] == "smooth", "only the smoothed ML bigram LM exists (:184-189)"
@@ -189,7 +186,7 @@ class BigramAcousticWordseg(object):
         _lib.check(rc)
         st = status.cpu().numpy()
         feed.finish()
-        self.utterances.boundaries[:, :] = corpus.boundaries_matrix()
+        self.utterances._bflat[:] = corpus.boundaries_flat()
         assert np.all(st == _lib.DP_OK), "segmentation DP failed for %d utterances, first %s (status %s)" % (
             int((st != 0).sum()), list(order_h[st != 0][:8]), list(st[st != 0][:8]))
         lp = log_probs.cpu().numpy()

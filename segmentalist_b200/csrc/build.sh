@@ -7,7 +7,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr --extended-lambda -Xcompiler -fPIC ${SEGB_NVCC_EXTRA}"
 OBJS=""
 PIDS=""
-for f in api dp fixedvar fixedvar_gibbs kmeans kmeans_mma fixedvar_mma fixedvar_filter score_fused frozen diagnostics; do
+for f in api dp fixedvar fixedvar_gibbs kmeans kmeans_mma fixedvar_mma fixedvar_filter score_fused frozen host_init diagnostics; do
   if [ -f "$HERE/$f.cu" ]; then
     stale=0
     for dep in "$HERE/$f.cu" "$HERE"/*.cuh "$HERE/../../include/segb200.h"; do

@@ -239,9 +239,16 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
     const W4 w4{w_max[0], w_max[1], w_max[2], w_max[3]};
     const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    // the NEXT row's filter record is requested before the current one is examined (one memory round trip
+    // of the dependent chain record -> model row -> arithmetic overlaps the previous row's work)
+    Cand cd_next;
+    float2 xe_next = make_float2(0.f, 0.f);
+    if (grp_global < n_emb) { cd_next = cand[grp_global]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * grp_global); }
     for (int64_t row = grp_global; row < n_emb; row += grp_total) {
-        const Cand cd = cand[row];
-        const float2 xe = *reinterpret_cast<const float2 *>(x_err + 2 * row);
+        const Cand cd = cd_next;
+        const float2 xe = xe_next;
+        const int64_t row_n = row + grp_total;
+        if (row_n < n_emb) { cd_next = cand[row_n]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * row_n); }
         const float tau = lse_tau(xe.x, xe.y, w4, KP, T);
         const int code = refine_decide(cd, tau, n_chunks);
         if (rec_out && j == 0) rec_out[row] = RowRec{cd.i1, cd.i2, cd.masks, code};

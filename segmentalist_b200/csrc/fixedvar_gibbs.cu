@@ -990,7 +990,14 @@ __global__ void __launch_bounds__(GB_THREADS, 1) fv_gibbs_kernel(GibbsParams p) 
     }
 }
 
-static inline int gibbs_grid(int K_max, int n_sm) { return K_max < n_sm ? K_max : n_sm; }
+// CTAs of one cooperative sweep: one per SM, at most one per component; segb_gibbs_set_max_ctas() lowers the
+// limit so that several independent chains (replicas) can share the GPU, each on its own stream
+static int g_max_ctas = 0;
+static inline int gibbs_grid(int K_max, int n_sm) {
+    int g = K_max < n_sm ? K_max : n_sm;
+    if (g_max_ctas > 0 && g_max_ctas < g) g = g_max_ctas;
+    return g;
+}
 
 // development aid: per-phase clock totals of CTA 0 (enabled by segb_debug_gibbs_prof(…, 1))
 static unsigned long long *g_prof = nullptr;
@@ -1112,6 +1119,11 @@ extern "C" int segb_fbgmm_gibbs_items_coop(const segb_fixedvar *m, const int32_t
     void *args[] = {&p};
     SEGB_CUDA(cudaLaunchCooperativeKernel((const void *)fv_gibbs_kernel<true, false>, dim3(G), dim3(GB_THREADS), args, smem, st));
     count_launch();
+    return 0;
+}
+
+extern "C" int segb_gibbs_set_max_ctas(int32_t max_ctas) {
+    g_max_ctas = max_ctas > 0 ? max_ctas : 0;
     return 0;
 }
 

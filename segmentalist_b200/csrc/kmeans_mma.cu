@@ -551,9 +551,19 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
     const float e_mu = w_max[0], n_mu = w_max[1];
     const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    // The row's dependent chain is filter record -> mean row -> arithmetic; its embedding row does not
+    // depend on the record, and neither does the NEXT row's record: both are requested before the current
+    // record is examined, so three memory round trips overlap instead of following one another.
+    Cand cd_next;
+    float2 xe_next = make_float2(0.f, 0.f);
+    if (grp_global < n_emb) { cd_next = cand[grp_global]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * grp_global); }
     for (int64_t row = grp_global; row < n_emb; row += grp_total) {
-        const Cand cd = cand[row];
-        const float2 xe = *reinterpret_cast<const float2 *>(x_err + 2 * row);
+        const Cand cd = cd_next;
+        const float2 xe = xe_next;
+        float2 xv[MAXS];
+        km_load_x8<MAXS>(X + row * D, geo, xv);
+        const int64_t row_n = row + grp_total;
+        if (row_n < n_emb) { cd_next = cand[row_n]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * row_n); }
         const float tau = filter_tau(xe.x, xe.y, e_mu, n_mu, D);
         const int code = refine_decide(cd, tau, n_chunks);
         if (code == -2) {
@@ -562,7 +572,7 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
         }
         float bv;
         int bk;
-        km_exact_row8<MAXS>(means, KM, D, X + row * D, cd.i1, cd.i2, cd.masks, code, geo, bv, bk);
+        km_exact_row8<MAXS>(means, KM, D, X + row * D, xv, cd.i1, cd.i2, cd.masks, code, geo, bv, bk);
         if (j == 0) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
     }
 }

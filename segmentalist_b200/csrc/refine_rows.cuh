@@ -46,13 +46,18 @@ __host__ __device__ inline bool row8_supported(int D) {
 
 // code (refine_decide): -1 the best chunk i1 suffices, >= 0 also visit chunk i2.  masks: bits 0-15
 // members of chunk i1 to score, bits 16-31 members of chunk i2.  Result on all 8 lanes.
+// this lane's elements of the embedding row (independent of the filter record: issue them first)
 template <int MAXS>
-__device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D, const float *xr, int i1, int i2,
-                                              uint32_t masks, int code, const Row8Geom &q, float &bv, int &bk) {
+__device__ __forceinline__ void km_load_x8(const float *xr, const Row8Geom &q, float2 *xv) {
     const float2 *xr2 = reinterpret_cast<const float2 *>(xr + q.lo_g + 2 * q.c);
-    float2 xv[MAXS];
 #pragma unroll
     for (int i = 0; i < MAXS; ++i) xv[i] = (i < q.steps) ? xr2[i * 4] : make_float2(0.f, 0.f);
+}
+
+template <int MAXS>
+__device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D, const float *xr, const float2 *xv,
+                                              int i1, int i2, uint32_t masks, int code, const Row8Geom &q, float &bv,
+                                              int &bk) {
     bv = -CUDART_INF_F;
     bk = 0x7fffffff;
 #pragma unroll 1
@@ -91,6 +96,14 @@ __device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D,
             if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; }
         }
     }
+}
+
+template <int MAXS>
+__device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D, const float *xr, int i1, int i2,
+                                              uint32_t masks, int code, const Row8Geom &q, float &bv, int &bk) {
+    float2 xv[MAXS];
+    km_load_x8<MAXS>(xr, q, xv);
+    km_exact_row8<MAXS>(means, KM, D, xr, xv, i1, i2, masks, code, q, bv, bk);
 }
 
 }  // namespace mma

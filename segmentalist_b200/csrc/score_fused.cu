@@ -6,11 +6,12 @@
 // filter records and spend 17 % of the sweep in a latency-bound refine.  This kernel reads the fp32
 // embeddings ONCE from HBM:
 //
-//   aux warps (4)      convert the NEXT work item's 256 fp32 rows to the fp16 UMMA tile layout directly in
-//                      shared memory (row per thread; the rounding-error norms behind the rigorous
-//                      candidate threshold fall out of the same pass, per row), and re-score the PREVIOUS
-//                      work item's surviving candidates exactly (eight lanes per embedding; the rows were
-//                      just read, so they come from L2) while the tensor pipe works on the current one
+//   convert warps (4)  turn the NEXT work item's 256 fp32 rows into the fp16 UMMA tile layout directly in
+//                      shared memory (8 rows in flight per warp, coalesced 8-byte loads; the rounding-error
+//                      norms behind the rigorous candidate threshold fall out of the same pass, per row)
+//   refine warps (8)   re-score the PREVIOUS work item's surviving candidates exactly (eight lanes per
+//                      embedding; the rows were just read, so they come from L2) while the tensor pipe works
+//                      on the current one
 //   warp 0             bulk-copy producer of the model tiles (B operand, L2-resident)
 //   warp 1             tcgen05.mma issuer (one elected thread; M=128 N=128 K=16, fp32 TMEM accumulators)
 //   warp 2             TMEM allocator
@@ -30,9 +31,10 @@ using namespace segb::mma;
 
 constexpr uint32_t KSTEP_BYTES = 2 * (TILE_ROWS / 8) * 128;        // one K=16 step of a 128-row tile image
 constexpr int EPI_PARTS = 2;
-constexpr int N_EPI_WARPS = 8 * EPI_PARTS, N_AUX_WARPS = 4;
-constexpr int AUX_WARP0 = 4 + N_EPI_WARPS;
-constexpr int N_THREADS = 32 * (4 + N_EPI_WARPS + N_AUX_WARPS);    // 768
+constexpr int N_EPI_WARPS = 8 * EPI_PARTS, N_CVT_WARPS = 4, N_REF_WARPS = 8;
+constexpr int CVT_WARP0 = 4 + N_EPI_WARPS, REF_WARP0 = CVT_WARP0 + N_CVT_WARPS;
+constexpr int N_THREADS = 32 * (4 + N_EPI_WARPS + N_CVT_WARPS + N_REF_WARPS);    // 1024: 64 registers per thread
+constexpr int N_CVT = N_CVT_WARPS + 2;                             // warps 2 and 3 (idle after the TMEM allocation) convert too
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int POL_KMEANS = 0, POL_FV = 1;
 constexpr int XBUF_BYTES = MT_ROWS * 32, TAU_BYTES = 2 * MT_ROWS * 4, BAR_BYTES = 256;
@@ -58,91 +60,93 @@ struct Params {
     unsigned long long *n_fallback;
     int32_t *fb_list;
     RowRec *rec_out;               // optional [n_emb]: the row records, for a later component draw (segb_fvf_choose_tokens)
+    int32_t dbg;                   // development: bit 0 skip the conversion work, bit 1 skip the refine work (timing only)
 };
 
-// One embedding row -> its fp16 operand row in the tile image `tile` (row r), plus the row's threshold.
+// One convert warp turns CVT_ROWS consecutive fp32 rows of a work item into fp16 operand rows of the tile
+// image in shared memory, eight rows at a time.  Lane (rr, pp) = (lane / 4, lane % 4) owns elements
+// (8 ch + 2 pp, + 1) of row rr of the group for every 8-column chunk ch: one store instruction of the warp
+// writes ONE 8x8 core matrix of the UMMA layout -- 128 contiguous bytes, no bank conflicts (the tensor pipe
+// reads its operands from the same shared memory at close to its full bandwidth, so conflicted stores cost
+// MMA time) -- and one load instruction fetches eight full 32-byte sectors.  The row norm (input of the row's
+// candidate threshold) is reduced over the four lanes of a row; the rounding-error norm is bounded by
+// 2^-11 |x| + sqrt(D) 2^-25 (fp16 has 11 significant bits; the second term covers fp16 subnormals) instead
+// of being measured -- a looser threshold costs a few more exact re-scores, never exactness.  Even D.
 // k-means columns [x^ (D), 1, 1, 1, 0..]; FBGMM [x^ (D), 1, 1, 1, n2h, n2h, n2l, 0..] (fixedvar_filter.cu).
 template <int POL>
-__device__ __forceinline__ float convert_row(const Params &p, int64_t row, uint8_t *tile, int r) {
+__device__ __forceinline__ void convert_rows_warp(const Params &p, int mt, uint8_t *sA_ab, uint32_t tb, float *tau_ab,
+                                                  int wc, int lane) {
     const int D = p.D, KP = p.KP;
-    const bool live = row < p.n_emb;
-    const float *xr = p.X + row * D;
-    float e2 = 0.f, f2 = 0.f;
-    double n2d = 0.0;
-    bool overflow = false;
-    const int n_full = D / 8;                       // chunks made of data columns only
-    const bool even = (D & 1) == 0;
-    auto put = [&](int c0, const float *x8) {
-        __align__(16) __half hv[8];
+    const int rr = lane >> 2, pp = lane & 3;
+    const int64_t row0 = (int64_t)mt * MT_ROWS;
+    const int n_data = (D + 7) / 8, n_ch = KP / 8;               // chunks holding data columns / all chunks
+    const float w0 = p.w_max[0], w1 = p.w_max[1];
+    const W4 w4{w0, w1, POL == POL_FV ? p.w_max[2] : 0.f, POL == POL_FV ? p.w_max[3] : 0.f};
+    const float sub_err = sqrtf((float)D) * ldexpf(1.f, -25);
+    constexpr int UNR = 9;                                        // loads in flight per lane
+#pragma unroll 1
+    for (int b = 8 * wc; b < MT_ROWS; b += 8 * N_CVT) {           // 8-row groups of the work item, round-robin over the convert warps
+        const int r = (b & (TILE_ROWS - 1)) + rr;
+        const int64_t row = row0 + b + rr;
+        const bool live = row < p.n_emb;
+        const float *xr = p.X + row * D + 2 * pp;
+        uint8_t *dst = sA_ab + (size_t)(b / TILE_ROWS) * tb + tile_off(r, 2 * pp);    // + ch * (TILE_ROWS / 8) * 128 per chunk
+        float f2 = 0.f;
+        float2 last = make_float2(0.f, 0.f);                      // the chunk that also holds constant columns
+#pragma unroll 1
+        for (int c0 = 0; c0 < n_data; c0 += UNR) {
+            float2 v[UNR];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(x8[j]);
-        *reinterpret_cast<uint4 *>(tile + tile_off(r, c0)) = *reinterpret_cast<const uint4 *>(hv);
-    };
-    auto account = [&](float x) {
-        if (fabsf(x) > 60000.f) overflow = true;
-        const float dl = x - __half2float(__float2half_rn(x));
-        e2 += dl * dl; f2 += x * x;
-        if (POL == POL_FV) n2d += (double)x * (double)x;
-    };
-#pragma unroll 2
-    for (int ch = 0; ch < n_full; ++ch) {
-        float x8[8];
-        if (live) {
-            if (even) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 v = *reinterpret_cast<const float2 *>(xr + ch * 8 + 2 * j);
-                    x8[2 * j] = v.x; x8[2 * j + 1] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x8[j] = xr[ch * 8 + j];
+            for (int u = 0; u < UNR; ++u) {
+                const int ch = c0 + u;
+                v[u] = (live && ch < n_data && 8 * ch + 2 * pp < D) ? *reinterpret_cast<const float2 *>(xr + 8 * ch)
+                                                                   : make_float2(0.f, 0.f);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) account(x8[j]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x8[j] = 0.f;
+            for (int u = 0; u < UNR; ++u) {
+                const int ch = c0 + u;
+                if (ch < n_data) {
+                    f2 = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, f2));
+                    if (8 * ch + 8 <= D)
+                        *reinterpret_cast<__half2 *>(dst + (size_t)ch * (TILE_ROWS / 8) * 128) = __floats2half2_rn(v[u].x, v[u].y);
+                    else last = v[u];
+                }
+            }
         }
-        put(ch * 8, x8);
-    }
-    // the chunk holding the last D % 8 data columns and the constant columns, then zero chunks
-    float tail[8];
+        f2 += __shfl_xor_sync(FULL, f2, 1);
+        f2 += __shfl_xor_sync(FULL, f2, 2);                       // |x|^2 of the row on its four lanes
+        __half n2h = __float2half_rn(0.f), n2l = n2h;
+        if (POL == POL_FV) { n2h = __float2half_rn(f2); n2l = __float2half_rn(f2 - __half2float(n2h)); }
+        // chunks from the first one that holds a column >= D: data tail, constants, zeros
+        for (int ch = D / 8; ch < n_ch; ++ch) {
+            float o[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int c = n_full * 8 + j; tail[j] = (live && c < D) ? xr[c] : 0.f; }
-    if (live)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (n_full * 8 + j < D) account(tail[j]);
-    __half n2h = __float2half_rn(0.f), n2l = n2h;
-    if (POL == POL_FV) {
-        if (!(n2d < 60000.0)) overflow = true;
-        const float n2f = (float)n2d;
-        n2h = __float2half_rn(n2f);
-        n2l = __float2half_rn(n2f - __half2float(n2h));
-    }
-    for (int c0 = n_full * 8; c0 < KP; c0 += 8) {
-        __align__(16) __half hv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            __half out = __float2half_rn(0.f);
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * ch + 2 * pp + e;
+                float val = 0.f;
+                if (live) {
+                    if (c < D) val = e == 0 ? last.x : last.y;
+                    else {
+                        const int ecol = c - D;
+                        if (ecol < 3) val = 1.f;
+                        else if (POL == POL_FV && (ecol == 3 || ecol == 4)) val = __half2float(n2h);
+                        else if (POL == POL_FV && ecol == 5) val = __half2float(n2l);
+                    }
+                }
+                o[e] = val;
+            }
+            *reinterpret_cast<__half2 *>(dst + (size_t)ch * (TILE_ROWS / 8) * 128) = __floats2half2_rn(o[0], o[1]);
+        }
+        if (pp == 0) {
+            float tau = CUDART_INF_F;
             if (live) {
-                if (c < D) out = __float2half_rn(tail[c - n_full * 8]);
-                else {
-                    const int ecol = c - D;
-                    if (ecol < 3) out = __float2half_rn(1.f);
-                    else if (POL == POL_FV && (ecol == 3 || ecol == 4)) out = n2h;
-                    else if (POL == POL_FV && ecol == 5) out = n2l;
-                }
+                const float nx = sqrtf(f2) * 1.0001f;
+                const float ex = (nx < 60000.f) ? (ldexpf(nx, -11) + sub_err) : CUDART_INF_F;   // |x_d| > 60000 => |x| > 60000
+                tau = POL == POL_KMEANS ? filter_tau(ex, nx, w0, w1, D) : lse_tau(ex, nx, w4, KP, p.tau_T);
             }
-            hv[j] = out;
+            tau_ab[b + rr] = tau;
         }
-        *reinterpret_cast<uint4 *>(tile + tile_off(r, c0)) = *reinterpret_cast<const uint4 *>(hv);
     }
-    if (!live) return CUDART_INF_F;
-    const float ex = overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f, nx = sqrtf(f2) * 1.0001f;
-    if (POL == POL_KMEANS) return filter_tau(ex, nx, p.w_max[0], p.w_max[1], D);
-    return lse_tau(ex, nx, W4{p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3]}, KP, p.tau_T);
 }
 
 // KS = K=16 steps of the inner dimension (compile-time unrolled issue loop), 0 = runtime.
@@ -166,14 +170,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) score_fused_kernel(Params p) {
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(BAR(A_FULL + b), N_AUX_WARPS);
+            mbar_init(BAR(A_FULL + b), N_CVT);
             mbar_init(BAR(A_EMPTY + b), 1);
             mbar_init(BAR(B_FULL + b), 1);
             mbar_init(BAR(MMA_DONE + b), 1);
             mbar_init(BAR(ACC_EMPTY + b), N_EPI_WARPS);
         }
         mbar_init(BAR(CAND_FULL), N_EPI_WARPS / EPI_PARTS);
-        mbar_init(BAR(CAND_EMPTY), N_AUX_WARPS);
+        mbar_init(BAR(CAND_EMPTY), N_REF_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) score_fused_kernel(Params p) {
                 tc_commit(BAR(A_EMPTY + ab));             // A tiles free
             }
         }
-    } else if (warp >= 4 && warp < AUX_WARP0) {
+    } else if (warp >= 4 && warp < CVT_WARP0) {
         // ===================== epilogue: running top-3 chunk maxima per embedding =====================
         const int e = warp - 4, q = warp & 3, h = (e >> 2) & 1, part = e >> 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -304,31 +308,52 @@ __global__ void __launch_bounds__(N_THREADS, 1) score_fused_kernel(Params p) {
                 if (lane == 0) mbar_arrive(BAR(CAND_FULL));
             }
         }
-    } else if (warp >= AUX_WARP0) {
-        // ===================== aux: operand conversion (next item) + exact refine (previous item) =====================
-        const int a = threadIdx.x - 32 * AUX_WARP0;            // 0..127
-        const int j = lane & 7, grp = a >> 3;
+    } else if (warp == 2 || warp == 3 || (warp >= CVT_WARP0 && warp < REF_WARP0)) {
+        // ===================== convert: the NEXT work item's fp32 rows -> fp16 operand tiles =====================
+        const int wc = warp < 4 ? warp - 2 : warp - CVT_WARP0 + 2;
+        int it = 0;
+        long long t_wait = 0, t_cvt = 0;
+        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const long long t0 = clock64();
+            // Ask the copy engine to bring the work item AFTER this one into L2 now: by the time this warp
+            // converts it (one work-item period later) its loads hit L2 instead of paying HBM latency
+            // (the conversion is a chain of dependent batches: 16 x HBM latency per item was ~55 us
+            // against a 35 us MMA period).
+            if (wc == 0 && lane == 0) {
+                const int64_t r_pf = ((int64_t)mt + gridDim.x) * MT_ROWS;
+                if (r_pf < p.n_emb) {
+                    int64_t n_r = p.n_emb - r_pf;
+                    if (n_r > MT_ROWS) n_r = MT_ROWS;
+                    const uint32_t bytes = (uint32_t)((n_r * p.D * 4) & ~15ll);
+                    const float *src = p.X + r_pf * p.D;
+                    if (bytes && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+                }
+            }
+            mbar_wait(BAR(A_EMPTY + ab), ((uint32_t)(it >> 1) & 1) ^ 1);       // the MMAs that read this buffer are done
+            const long long t1 = clock64();
+            if (!(p.dbg & 1)) convert_rows_warp<POL>(p, mt, sA + (size_t)(2 * ab) * tb, tb, tau_s + ab * MT_ROWS, wc, lane);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(A_FULL + ab));
+            t_wait += t1 - t0; t_cvt += clock64() - t1;
+        }
+        if ((p.dbg & 4) && blockIdx.x == 0 && lane == 0)
+            printf("cvt warp %d: items %d, avg wait %lld clk, avg convert %lld clk\n", wc, it, t_wait / max(it, 1), t_cvt / max(it, 1));
+    } else if (warp >= REF_WARP0) {
+        // ===================== refine: the PREVIOUS work item's surviving candidates, exactly =====================
+        const int j = lane & 7, grp = (warp - REF_WARP0) * 4 + (lane >> 3);
         const unsigned gmask = 0xffu << (lane & 24);
         const Row8Geom geo(p.D, lane);
         const fvf::ModelRows tabs = fvf::model_view(p.model_rows, p.K_max, p.D, 0);
-        auto convert = [&](int it, int mt) {
-            const int ab = it & 1;
-            mbar_wait(BAR(A_EMPTY + ab), ((uint32_t)(it >> 1) & 1) ^ 1);
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int64_t row = (int64_t)mt * MT_ROWS + half * TILE_ROWS + a;
-                tau_s[ab * MT_ROWS + half * TILE_ROWS + a] = convert_row<POL>(p, row, sA + (size_t)(2 * ab + half) * tb, a);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(A_FULL + ab));
-        };
-        auto refine = [&](int it, int mt) {
+        int it = 0;
+        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
             mbar_wait(BAR(CAND_FULL), (uint32_t)it & 1);
 #pragma unroll 1
-            for (int r = grp; r < MT_ROWS; r += 4 * N_AUX_WARPS) {     // 4 eight-lane groups per aux warp
+            for (int r = grp; r < MT_ROWS; r += 4 * N_REF_WARPS) {
                 const int64_t row = (int64_t)mt * MT_ROWS + r;
-                if (row >= p.n_emb) break;                             // uniform within the 8-lane group
+                if (row >= p.n_emb || (p.dbg & 2)) break;              // uniform within the 8-lane group
                 const RowRec rec = *reinterpret_cast<const RowRec *>(xbuf + 32 * r);
                 if (p.rec_out && j == 0) p.rec_out[row] = rec;
                 if (rec.code == -2) {
@@ -352,13 +377,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) score_fused_kernel(Params p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(CAND_EMPTY));
-        };
-        int it = 0;
-        if ((int)blockIdx.x < p.n_mtiles) convert(0, blockIdx.x);
-        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
-            const int mt_next = mt + gridDim.x;
-            if (mt_next < p.n_mtiles) convert(it + 1, mt_next);
-            refine(it, mt);
         }
     }
     tc_fence_before();
@@ -423,6 +441,7 @@ extern "C" int segb_fused_kmeans_best(const segb_kmeans *m, const void *w_tiles,
     p.means = (const float *)m->means; p.K_max = m->K_max; p.best_val = best_val; p.best_k = best_k;
     p.n_fallback = (unsigned long long *)n_fallback; p.fb_list = (int32_t *)work;
     SEGB_CUDA(cudaMemsetAsync(n_fallback, 0, sizeof(int64_t), st));
+    if (const char *e = getenv("SEGB_FUSED_DBG")) p.dbg = atoi(e);
     const int rc = fused::launch<fused::POL_KMEANS>(p, st);
     if (rc) return rc;
     return mma::launch_refine_full(m, p.fb_list, n_fallback, best_val, best_k, st);

@@ -44,10 +44,7 @@ class SegmentalKMeansWordseg(object):
             [len(landmarks_dict[i]) for i in labels], vec_ids, [durations_dict[i] for i in labels],
             [landmarks_dict[i] for i in labels], seed_boundaries=seeds, p_boundary_init=p_boundary_init,
             n_slices_min=n_slices_min, n_slices_max=n_slices_max, min_duration=min_duration)
-        init_embeds = []
-        for u in range(self.utterances.D):
-            init_embeds.extend(self.utterances.get_segmented_embeds_i(u))
-        init_embeds = np.array(init_embeds, dtype=int)
+        init_embeds = self.utterances.all_segmented_embeds()     # get_segmented_embeds_i of every utterance, vectorised
         init_embeds = init_embeds[np.where(init_embeds != -1)]
         assignments = -1 * np.ones(N, dtype=int)
         if seed_assignments_dict is not None:
@@ -89,7 +86,7 @@ class SegmentalKMeansWordseg(object):
             comps.struct(), corpus.struct(), order_h.ctypes.data, n, float(self.wip), _lib.ptr(self._scratch),
             None, _lib.ptr(self._scratch_arg), _lib.ptr(totals), _lib.ptr(status), _lib.stream_ptr()))
         st = status.cpu().numpy()
-        self.utterances.boundaries[:, :] = corpus.boundaries_matrix()
+        self.utterances._bflat[:] = corpus.boundaries_flat()
         assert np.all(st == _lib.DP_OK), "segmentation failed for utterances %s (status %s)" % (
             list(order_h[st != 0]), list(st[st != 0]))
         return totals.cpu().numpy()
@@ -153,7 +150,7 @@ class SegmentalKMeansWordseg(object):
         for _ in range(n_iter):
             t0 = time.time()
             total = self._frozen.sweep()
-            self.utterances.boundaries[:, :] = self._corpus.boundaries_matrix()
+            self.utterances._bflat[:] = self._corpus.boundaries_flat()
             record["sum_neg_len_sqrd_norm"].append(total)
             record["components"].append(self.acoustic_model.components.K)
             record["n_tokens"].append(self.acoustic_model.get_n_assigned())

@@ -34,18 +34,19 @@ class UniformFeed(object):
     """Hands Python's `random.random()` stream to the device and keeps the host
     generator in step with what the kernels consumed."""
 
-    def __init__(self, n_max):
-        self.state = random.getstate()
-        self.host = np.array([random.random() for _ in range(n_max)], dtype=np.float64)
+    def __init__(self, n_max, rng=None):
+        self.rng = random if rng is None else rng        # the global generator (reference behaviour) or a chain's own
+        self.state = self.rng.getstate()
+        self.host = np.array([self.rng.random() for _ in range(n_max)], dtype=np.float64)
         self.dev = _lib.dev(self.host) if n_max else torch.zeros(1, dtype=torch.float64, device="cuda")
         self.counter = torch.zeros(1, dtype=torch.int64, device="cuda")
 
     def finish(self):
         used = int(self.counter.item())
         assert used <= len(self.host), "device consumed more uniforms than were provisioned"
-        random.setstate(self.state)
+        self.rng.setstate(self.state)
         for _ in range(used):
-            random.random()
+            self.rng.random()
         return used
 
 
@@ -89,10 +90,7 @@ class UnigramAcousticWordseg(object):
             [landmarks_dict[i] for i in labels], seed_boundaries=seeds, p_boundary_init=p_boundary_init,
             n_slices_min=n_slices_min, n_slices_max=n_slices_max, min_duration=min_duration)
 
-        init_embeds = []
-        for u in range(self.utterances.D):
-            init_embeds.extend(self.utterances.get_segmented_embeds_i(u))
-        init_embeds = np.array(init_embeds, dtype=int)
+        init_embeds = self.utterances.all_segmented_embeds()     # get_segmented_embeds_i of every utterance, vectorised
         init_embeds = init_embeds[np.where(init_embeds != -1)]
 
         assignments = -1 * np.ones(N, dtype=int)
@@ -151,12 +149,18 @@ class UnigramAcousticWordseg(object):
 
     # ---- device sweep
     def _sweep(self, order, anneal_temp, anneal_gibbs_am):
+        return self._sweep_finish(self._sweep_launch(order, anneal_temp, anneal_gibbs_am))
+
+    def _sweep_launch(self, order, anneal_temp, anneal_gibbs_am, rng=None, max_ctas=0):
+        """Queue one sweep over `order` on the current stream without waiting for it.  rng: a random.Random
+        the uniforms come from instead of the global generator; max_ctas: CTAs of the cooperative launch
+        (0 = one per SM) -- both for running several independent chains side by side (run_replica_sweeps)."""
         corpus, am = self._corpus, self.acoustic_model
         n = len(order)
         order_h = np.ascontiguousarray(order, dtype=np.int32)
         ffbs = self.fb_type == "standard"
         n_draws = int(2 * corpus.lengths[order_h].sum() + 2) if ffbs else 0
-        feed = UniformFeed(n_draws)
+        feed = UniformFeed(n_draws, rng)
         log_probs = torch.zeros(n, dtype=torch.float64, device="cuda")
         status = torch.zeros(n, dtype=torch.int32, device="cuda")
         assert self.calc_p_continue() == 1.0
@@ -168,11 +172,15 @@ class UnigramAcousticWordseg(object):
             if getattr(self, "_gibbs_work", None) is None:
                 self._gibbs_work = torch.empty(lib.segb_gibbs_work_bytes(comps.K_max, corpus.N_max, corpus.S),
                                                dtype=torch.uint8, device="cuda")
-            rc = lib.segb_gibbs_sweep_fixedvar_coop(
-                comps.struct(), corpus.struct(), _lib.ptr(_lib.dev(order_h)), n, mode, float(self.time_power_term),
-                float(self.wip), float(anneal_temp), int(bool(anneal_gibbs_am)), _lib.ptr(feed.dev),
-                _lib.ptr(feed.counter), _lib.ptr(self._gibbs_work), _lib.ptr(log_probs), _lib.ptr(status),
-                _lib.stream_ptr())
+            lib.segb_gibbs_set_max_ctas(int(max_ctas))
+            try:
+                rc = lib.segb_gibbs_sweep_fixedvar_coop(
+                    comps.struct(), corpus.struct(), _lib.ptr(_lib.dev(order_h)), n, mode, float(self.time_power_term),
+                    float(self.wip), float(anneal_temp), int(bool(anneal_gibbs_am)), _lib.ptr(feed.dev),
+                    _lib.ptr(feed.counter), _lib.ptr(self._gibbs_work), _lib.ptr(log_probs), _lib.ptr(status),
+                    _lib.stream_ptr())
+            finally:
+                lib.segb_gibbs_set_max_ctas(0)
         if rc == _lib.E_UNSUPPORTED:
             # model too large for per-CTA shared memory: four launches per utterance
             rc = lib.segb_gibbs_sweep_fixedvar(
@@ -181,9 +189,14 @@ class UnigramAcousticWordseg(object):
                 _lib.ptr(feed.counter), _lib.ptr(self._scratch), _lib.ptr(log_probs), _lib.ptr(status),
                 _lib.stream_ptr())
         _lib.check(rc)
+        return feed, log_probs, status, order_h
+
+    def _sweep_finish(self, handle):
+        feed, log_probs, status, order_h = handle
+        corpus = self._corpus
         st = status.cpu().numpy()
         feed.finish()
-        self.utterances.boundaries[:, :] = corpus.boundaries_matrix()
+        self.utterances._bflat[:] = corpus.boundaries_flat()
         assert np.all(st == _lib.DP_OK), "segmentation DP failed for %d utterances, first %s (status %s)" % (
             int((st != 0).sum()), list(order_h[st != 0][:8]), list(st[st != 0][:8]))
         lp = log_probs.cpu().numpy()
@@ -255,7 +268,7 @@ class UnigramAcousticWordseg(object):
                 else:
                     u_fb, u_assign = _lib.dev(np.random.rand(n_pos)), _lib.dev(np.random.rand(n_pos))
             total = self._frozen.sweep(u_fb, u_assign)
-            self.utterances.boundaries[:, :] = self._corpus.boundaries_matrix()
+            self.utterances._bflat[:] = self._corpus.boundaries_flat()
             record["sample_time"].append(time.time() - t0)
             record["log_marg*length"].append(total)
             record["components"].append(self._frozen.K_host)
@@ -289,6 +302,27 @@ class UnigramAcousticWordseg(object):
         for e, k in zip(embeds, assign):
             comps.add_item(e, k)
         return out
+
+
+def run_replica_sweeps(segmenters, orders, rngs, anneal_temp=1, anneal_gibbs_am=False):
+    """One sweep of R INDEPENDENT chains side by side (sequential collapsed Gibbs does not shard over
+    utterances; replicas do).  Every chain is one cooperative launch on its own stream with n_sm / R CTAs and
+    its own random.Random; within a chain the reference's sequential order is untouched, so each chain
+    produces exactly the samples it would produce alone.  Returns the per-chain log_prob arrays."""
+    n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    per = max(1, n_sm // len(segmenters))
+    if getattr(run_replica_sweeps, "_streams", None) is None or len(run_replica_sweeps._streams) < len(segmenters):
+        run_replica_sweeps._streams = [torch.cuda.Stream() for _ in segmenters]
+    handles = []
+    for seg, order, rng, stream in zip(segmenters, orders, rngs, run_replica_sweeps._streams):
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            handles.append(seg._sweep_launch(order, anneal_temp, anneal_gibbs_am, rng=rng, max_ctas=per))
+    out = []
+    for seg, h, stream in zip(segmenters, handles, run_replica_sweeps._streams):
+        with torch.cuda.stream(stream):
+            out.append(seg._sweep_finish(h))
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -21,8 +21,13 @@ def tri(t):
 
 
 class Utterances(object):
-    """Same constructor, attributes and accessors as the reference class
-    (utterances.py:74-229).  Pure host logic (O(N) per utterance)."""
+    """Same constructor, attributes and accessors as the reference class (utterances.py:74-229).
+
+    Storage is ragged-flat: the packed-triangular `vec_ids` / `durations` of all utterances back to back
+    (O(sum N^2) but without padding every utterance to N_max(N_max+1)/2 slots, and built with a handful of
+    NumPy calls instead of a Python loop per utterance); the reference's padded [D, N_max(N_max+1)/2]
+    matrices are materialised only if somebody reads the `vec_ids` / `durations` attributes.  The device
+    layout (DeviceCorpus) is built straight from the flat arrays."""
 
     def __init__(self, lengths, vec_ids, durations, landmarks, seed_boundaries=None,
                  p_boundary_init=0.5, n_slices_min=0, n_slices_max=6, min_duration=0):
@@ -32,40 +37,108 @@ class Utterances(object):
         assert self.D == len(vec_ids)
         self.N_max = max(lengths)
         self.landmarks = landmarks
-        width = self.N_max * (self.N_max + 1) // 2
-        self.vec_ids = np.full((self.D, width), -1, dtype=np.int64)
-        for u, ids in enumerate(vec_ids):
-            self.vec_ids[u, :len(ids)] = ids
-        self.durations = np.full((self.D, width), np.nan)
-        for u, dur in enumerate(durations):
-            if not (min_duration == 0 or len(dur) == 1):          # utterances.py:96-101
-                cur = np.array(dur, dtype=np.float64)
-                cur[cur < min_duration] = np.nan
-                if np.all(np.isnan(cur)):
-                    cur[np.argmax(dur)] = np.max(dur)
-                dur = cur
-            self.durations[u, :len(dur)] = dur
-        self.boundaries = np.zeros((self.D, self.N_max), dtype=bool)
+        self._len = np.asarray(lengths, dtype=np.int64)
+        self._pos_off = np.concatenate([[0], np.cumsum(self._len)]).astype(np.int64)
+        n_packed = np.fromiter((len(v) for v in vec_ids), dtype=np.int64, count=self.D)
+        assert np.all(n_packed <= self._len * (self._len + 1) // 2)
+        self._poff = np.concatenate([[0], np.cumsum(n_packed)]).astype(np.int64)
+        self._ids = (np.concatenate([np.asarray(v, dtype=np.int64) for v in vec_ids])
+                     if self.D else np.zeros(0, np.int64))
+        assert len(durations) == self.D
+        dur = np.concatenate([np.asarray(d, dtype=np.float64) for d in durations]) if self.D else np.zeros(0)
+        assert dur.shape == self._ids.shape, "vec_ids and durations must have the same packed lengths"
+        if min_duration != 0:                                     # utterances.py:96-101
+            raw = dur.copy()
+            multi = np.repeat(n_packed != 1, n_packed)            # single-slot utterances are left alone
+            dur = np.where(multi & (raw < min_duration), np.nan, raw)
+            all_nan = np.logical_and.reduceat(np.isnan(dur), self._poff[:-1][n_packed > 0])
+            for u in np.where(n_packed > 0)[0][all_nan]:          # rare: keep the longest candidate
+                lo, hi = self._poff[u], self._poff[u + 1]
+                k = int(np.argmax(raw[lo:hi]))
+                dur[lo + k] = raw[lo + k]
+        self._dur = dur
+        self._vec_ids_mat = self._dur_mat = None
+        self._bflat = np.zeros(int(self._pos_off[-1]), dtype=bool)
+        self.boundaries = _BoundaryMatrix(self)
         if seed_boundaries is not None:                          # utterances.py:106-115
             for u, seeds in enumerate(seed_boundaries):
-                marks = landmarks[u]
-                hits = [int(np.argmin([abs(s - lm) for lm in marks])) for s in seeds]
-                self.boundaries[u, hits] = True
+                marks = np.asarray(landmarks[u])
+                hits = [int(np.argmin(np.abs(s - marks))) for s in seeds]
+                self._bflat[self._pos_off[u] + np.asarray(hits, dtype=np.int64)] = True
         elif p_boundary_init == 0:                               # utterances.py:128-135
-            for u in range(self.D):
-                self.boundaries[u, self.lengths[u] - 1] = True
+            self._bflat[self._pos_off[1:] - 1] = True
         else:                                                    # utterances.py:136-157
-            for u in range(self.D):
-                N = self.lengths[u]
-                while True:
-                    self.boundaries[u, 0:N] = (np.random.rand(N) < p_boundary_init)
-                    self.boundaries[u, N - 1] = True
-                    if np.all(np.asarray(self.get_segmented_embeds_i(u)) == -1):
-                        continue
-                    spans = [e - s for s, e in self.get_segmented_landmark_indices(u)]
-                    if ((np.max(spans) <= n_slices_max and np.min(spans) >= n_slices_min)
-                            or N <= n_slices_min):
-                        break
+            self._init_random_boundaries(p_boundary_init, n_slices_min, n_slices_max)
+
+    def _init_random_boundaries(self, p, n_slices_min, n_slices_max):
+        """The reference redraws `np.random.rand(N) < p` per utterance until the segmentation is usable; the
+        loop runs in C over a block of uniforms drawn in advance, and the global NumPy generator is then
+        advanced by exactly the number of draws the reference would have made."""
+        lib = _lib.load()
+        n_pos = int(self._pos_off[-1])
+        state = np.random.get_state()
+        block = max(1024, 2 * n_pos)
+        out = np.zeros(n_pos, dtype=np.uint8)
+        ptr = lambda a: a.ctypes.data
+        while True:
+            np.random.set_state(state)
+            uni = np.random.rand(block)
+            used = lib.segb_host_init_boundaries(ptr(self._len), self.D, ptr(self._poff), ptr(self._ids),
+                                                 ptr(self._pos_off), ptr(uni), block, float(p), int(n_slices_min),
+                                                 int(n_slices_max), ptr(out))
+            if used >= 0:
+                break
+            block *= 2
+        np.random.set_state(state)
+        if used:
+            np.random.rand(int(used))
+        self._bflat[:] = out.astype(bool)
+
+    # ---- the reference's padded matrices, on demand
+    def _padded(self, flat, fill, dtype):
+        width = self.N_max * (self.N_max + 1) // 2
+        out = np.full((self.D, width), fill, dtype=dtype)
+        n_packed = np.diff(self._poff)
+        rows = np.repeat(np.arange(self.D), n_packed)
+        cols = np.arange(len(flat)) - np.repeat(self._poff[:-1], n_packed)
+        out[rows, cols] = flat
+        return out
+
+    @property
+    def vec_ids(self):
+        if self._vec_ids_mat is None:
+            self._vec_ids_mat = self._padded(self._ids, -1, np.int64)
+        return self._vec_ids_mat
+
+    @property
+    def durations(self):
+        if self._dur_mat is None:
+            self._dur_mat = self._padded(self._dur, np.nan, np.float64)
+        return self._dur_mat
+
+    def _packed_at(self, flat, u, k, fill):
+        k = np.asarray(k, dtype=np.int64)
+        n = self._poff[u + 1] - self._poff[u]
+        out = np.full(k.shape, fill, dtype=flat.dtype)
+        ok = k < n
+        out[ok] = flat[self._poff[u] + k[ok]]
+        return out
+
+    def all_segmented_embeds(self):
+        """get_segmented_embeds_i for every utterance in order, concatenated (vectorised)."""
+        idx = np.where(self._bflat)[0]
+        if len(idx) == 0:
+            return np.zeros(0, np.int64)
+        utt = np.searchsorted(self._pos_off, idx, "right") - 1
+        first = np.concatenate([[True], utt[1:] != utt[:-1]])
+        start = np.where(first, self._pos_off[utt], np.concatenate([[0], idx[:-1] + 1])) - self._pos_off[utt]
+        end = idx - self._pos_off[utt] + 1
+        k = end * (end - 1) // 2 + start
+        n = (self._poff[1:] - self._poff[:-1])[utt]
+        out = np.full(len(idx), -1, dtype=np.int64)
+        ok = k < n
+        out[ok] = self._ids[self._poff[utt[ok]] + k[ok]]
+        return out
 
     def get_segmented_landmark_indices(self, i):
         """(start, end) landmark index of every hypothesised word (utterances.py:199-208)."""
@@ -77,17 +150,19 @@ class Utterances(object):
 
     def get_segmented_embeds_i(self, i):
         """Embedding ids of the current segmentation (utterances.py:159-174)."""
-        return [self.vec_ids[i, tri(e) + s] for s, e in self.get_segmented_landmark_indices(i)]
+        seg = self.get_segmented_landmark_indices(i)
+        return list(self._packed_at(self._ids, i, [tri(e) + s for s, e in seg], -1))
 
     def get_segmented_durations_i(self, i):
         """utterances.py:176-190."""
-        return [self.durations[i, tri(e) + s] for s, e in self.get_segmented_landmark_indices(i)]
+        seg = self.get_segmented_landmark_indices(i)
+        return list(self._packed_at(self._dur, i, [tri(e) + s for s, e in seg], np.nan))
 
     def get_original_segmented_embeds_i(self, i):
         """utterances.py:192-204."""
-        ids = self.vec_ids[i]
+        ids = self._ids[self._poff[i]:self._poff[i + 1]]
         lo = np.min(ids[np.where(ids != -1)])
-        return list(self.get_segmented_embeds_i(i) - lo)
+        return list(np.asarray(self.get_segmented_embeds_i(i)) - lo)
 
     def get_segmented_landmarks(self, i):
         """utterances.py:210-221."""
@@ -97,6 +172,74 @@ class Utterances(object):
             out.append((prev, self.landmarks[i][e - 1]))
             prev = self.landmarks[i][e - 1]
         return out
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["boundaries"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.boundaries = _BoundaryMatrix(self)
+
+
+class _BoundaryMatrix(object):
+    """`Utterances.boundaries` with the reference's [D, N_max] indexing over the flat per-landmark storage:
+    `boundaries[i]`, `boundaries[i, j]`, `boundaries[i, :N]`, `boundaries[:, :] = matrix`, np.asarray(.)."""
+
+    def __init__(self, utts):
+        self._u = utts
+
+    @property
+    def shape(self):
+        return (self._u.D, self._u.N_max)
+
+    def _dense(self):
+        u = self._u
+        out = np.zeros((u.D, u.N_max), dtype=bool)
+        rows = np.repeat(np.arange(u.D), u._len)
+        cols = np.arange(len(u._bflat)) - np.repeat(u._pos_off[:-1], u._len)
+        out[rows, cols] = u._bflat
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        d = self._dense()
+        return d if dtype is None else d.astype(dtype)
+
+    def copy(self):
+        return self._dense()
+
+    def __eq__(self, other):
+        return self._dense() == np.asarray(other)
+
+    def __getitem__(self, key):
+        u = self._u
+        if isinstance(key, (int, np.integer)):
+            row = np.zeros(u.N_max, dtype=bool)
+            row[:u._len[key]] = u._bflat[u._pos_off[key]:u._pos_off[key + 1]]
+            return row
+        if isinstance(key, tuple) and isinstance(key[0], (int, np.integer)):
+            return self[key[0]][key[1]]
+        return self._dense()[key]
+
+    def __setitem__(self, key, value):
+        u = self._u
+        if isinstance(key, tuple) and isinstance(key[0], (int, np.integer)):
+            i = int(key[0])
+            row = self[i]
+            row[key[1]] = value
+            u._bflat[u._pos_off[i]:u._pos_off[i + 1]] = row[:u._len[i]]
+            return
+        if isinstance(key, (int, np.integer)):
+            row = np.zeros(u.N_max, dtype=bool)
+            row[:] = value
+            u._bflat[u._pos_off[key]:u._pos_off[key + 1]] = row[:u._len[key]]
+            return
+        d = self._dense()
+        d[key] = value
+        rows = np.repeat(np.arange(u.D), u._len)
+        cols = np.arange(len(u._bflat)) - np.repeat(u._pos_off[:-1], u._len)
+        u._bflat[:] = d[rows, cols]
 
 
 # ---------------------------------------------------------------------------
@@ -135,6 +278,38 @@ def band_width(lengths, vec_ids_rows, n_slices_max):
     return max(S, 1)
 
 
+def band_width_flat(utts, n_slices_max):
+    """band_width over the flat packed storage of an Utterances object (vectorised)."""
+    n_packed = np.diff(utts._poff)
+    k = np.arange(len(utts._ids)) - np.repeat(utts._poff[:-1], n_packed)       # packed slot within the utterance
+    t = ((np.sqrt(8.0 * k + 1.0) + 1.0) // 2).astype(np.int64)                 # end landmark: tri(t) <= k < tri(t+1)
+    t = np.where(tri(t) > k, t - 1, t)
+    t = np.where(tri(t + 1) <= k, t + 1, t)
+    span = t - (k - tri(t))
+    live = utts._ids != -1
+    S_data = int(span[live].max()) if live.any() else 1
+    S = min(max(S_data, 1), utts.N_max)
+    if n_slices_max and n_slices_max > 0:
+        S = min(S, n_slices_max)
+    return max(S, 1)
+
+
+def band_arrays(utts, S):
+    """(seg_id [n_pos, S] int32, seg_dur [n_pos, S] float64) of an Utterances object: band slot (landmark
+    position p of utterance u, span l) <- packed slot tri(t) + (t - l) of that utterance, t = p - pos_off[u] + 1."""
+    n_pos = int(utts._pos_off[-1])
+    utt = np.repeat(np.arange(utts.D), utts._len)
+    t = (np.arange(n_pos) - utts._pos_off[utt] + 1)[:, None]              # [n_pos, 1]
+    l = np.arange(1, S + 1)[None, :]                                      # [1, S]
+    k = tri(t) + (t - l)
+    n_packed = (utts._poff[1:] - utts._poff[:-1])[utt][:, None]
+    ok = (l <= t) & (k < n_packed)
+    src = np.where(ok, utts._poff[utt][:, None] + k, 0)
+    seg_id = np.where(ok, utts._ids[src], -1).astype(np.int32)
+    seg_dur = np.where(ok, utts._dur[src], np.nan)
+    return seg_id, seg_dur
+
+
 def packed_to_band(vec, N, S, fill):
     """Packed-triangular vector of one utterance -> [N, S] band."""
     rows, cols, packed = _band_index(N, S)
@@ -171,16 +346,12 @@ class DeviceCorpus(object):
 
     @classmethod
     def from_utterances(cls, utts, n_slices_min, n_slices_max):
-        S = band_width(utts.lengths, utts.vec_ids, n_slices_max)
-        ids, durs, bflat = [], [], []
-        for u in range(utts.D):
-            N = utts.lengths[u]
-            n_packed = N * (N + 1) // 2
-            ids.append(packed_to_band(utts.vec_ids[u, :n_packed], N, S, -1))
-            durs.append(packed_to_band(utts.durations[u, :n_packed], N, S, np.nan))
-            bflat.append(utts.boundaries[u, :N])
-        return cls(utts.lengths, np.concatenate(ids), np.concatenate(durs), np.concatenate(bflat),
-                   n_slices_min, n_slices_max, S)
+        """Banded arrays straight from the flat packed storage (no padded-triangular intermediate, no
+        per-utterance loop): band slot (landmark position p of utterance u, span l) <- packed slot
+        tri(t) + (t - l) of that utterance, t = p - pos_off[u] + 1."""
+        S = band_width_flat(utts, n_slices_max)
+        seg_id, seg_dur = band_arrays(utts, S)
+        return cls(utts.lengths, seg_id, seg_dur, utts._bflat, n_slices_min, n_slices_max, S)
 
     def struct(self):
         c = _lib.Corpus()
@@ -213,30 +384,35 @@ class DeviceCorpus(object):
         """[n_utt, N_max] bool matrix in the reference's `Utterances.boundaries` format."""
         b = self.bounds.cpu().numpy().astype(bool)
         out = np.zeros((self.n_utt, self.N_max), dtype=bool)
-        for u in range(self.n_utt):
-            out[u, :self.lengths[u]] = b[self.pos_off_h[u]:self.pos_off_h[u + 1]]
+        rows = np.repeat(np.arange(self.n_utt), self.lengths)
+        cols = np.arange(self.n_pos) - np.repeat(self.pos_off_h[:-1], self.lengths)
+        out[rows, cols] = b
         return out
 
+    def boundaries_flat(self):
+        """The current boundaries, one bool per landmark (utterances back to back)."""
+        return self.bounds.cpu().numpy().astype(bool)
+
     def set_boundaries_matrix(self, boundaries):
-        flat = np.concatenate([boundaries[u, :self.lengths[u]] for u in range(self.n_utt)])
-        self.bounds.copy_(torch.from_numpy(flat.astype(np.uint8)))
+        boundaries = np.asarray(boundaries)
+        rows = np.repeat(np.arange(self.n_utt), self.lengths)
+        cols = np.arange(self.n_pos) - np.repeat(self.pos_off_h[:-1], self.lengths)
+        self.bounds.copy_(torch.from_numpy(boundaries[rows, cols].astype(np.uint8)))
         self.refresh_tokens_from_bounds()
 
 
 def process_embeddings(embedding_mats, vec_ids_dict):
-    """Stack the per-utterance matrices in sorted-label order and rewrite the
-    per-utterance row indices into global embedding ids
-    (unigram_acoustic_wordseg.py:571-646).  Vectorised: one lookup table per
-    utterance instead of one `np.where` per row."""
+    """Stack the per-utterance matrices in sorted-label order and rewrite the per-utterance row indices
+    into global embedding ids (unigram_acoustic_wordseg.py:571-646).  Vectorised over the whole corpus: one
+    concatenation and one offset addition instead of an `np.where` per matrix row."""
     labels = sorted(embedding_mats)
-    mats, vec_ids, base = [], [], 0
-    for utt in labels:
-        mat = np.asarray(embedding_mats[utt])
-        src = np.asarray(vec_ids_dict[utt])
-        cur = src.copy()
-        live = (src >= 0) & (src < mat.shape[0])
-        cur[live] = src[live] + base
-        mats.append(mat)
-        vec_ids.append(cur)
-        base += mat.shape[0]
+    mats = [np.asarray(embedding_mats[u]) for u in labels]
+    srcs = [np.asarray(vec_ids_dict[u]) for u in labels]
+    n_rows = np.fromiter((m.shape[0] for m in mats), dtype=np.int64, count=len(mats))
+    n_slots = np.fromiter((len(v) for v in srcs), dtype=np.int64, count=len(srcs))
+    base = np.concatenate([[0], np.cumsum(n_rows)[:-1]]) if len(mats) else np.zeros(0, np.int64)
+    src = np.concatenate(srcs) if srcs else np.zeros(0, np.int64)
+    live = (src >= 0) & (src < np.repeat(n_rows, n_slots))
+    cur = np.where(live, src + np.repeat(base, n_slots), src)
+    vec_ids = np.split(cur, np.cumsum(n_slots)[:-1]) if len(srcs) else []
     return np.concatenate(mats, axis=0), vec_ids, labels

@@ -29,7 +29,7 @@ def test_frozen_kmeans_sweep_full_size_properties():
     U, K, S, D = bench.TOTAL_UTTS, bench.K_MAX, bench.S_MAX, bench.D
     lengths, seg_id, seg_dur, bounds0, n_emb = bench.corpus_structure(U, seed=1000)
     assert n_emb > 20_000_000
-    X, _, Z = bench.make_embeddings_gpu(n_emb, K, seed=2000, device=dev)
+    X, Z = bench.make_embeddings_gpu(n_emb, torch.from_numpy(bench.centres_cpu(K)).to(dev), seed=2000, device=dev)
     corpus = DeviceCorpus(lengths, seg_id, seg_dur, bounds0, 0, S, S)
     perm = torch.randperm(n_emb, device=dev, generator=torch.Generator(device=dev).manual_seed(7))[:K]
     comps = KMeansComponents.from_device(X, K, X[perm].clone())
@@ -97,7 +97,7 @@ def test_frozen_kmeans_sweep_full_size_properties():
     n_pos_s = int(pos_off[n_s])
     ids_s = seg_id[:n_pos_s]
     hi = int(ids_s.max()) + 1
-    oseg = bench._oracle_segmenter(X[:hi].cpu().numpy(), lengths[:n_s], ids_s, seg_dur[:n_pos_s],
+    oseg = bench._cpu_segmenter(so, X[:hi].cpu().numpy(), lengths[:n_s], ids_s, seg_dur[:n_pos_s],
                                    means_before.cpu().numpy())
     totals, _, plan = so.frozen_kmeans_phase1(oseg)
     for u in range(n_s):

@@ -24,7 +24,7 @@ ap.add_argument("--tokens-per-k", type=int, default=4)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--aniso", action="store_true")
 ap.add_argument("--noise", type=float, default=0.05)
-ap.add_argument("--two-kernel", action="store_true")
+ap.add_argument("--fused", action="store_true")
 args = ap.parse_args()
 D, K = 130, args.K
 K_true = args.K_true or K
@@ -49,7 +49,7 @@ _, first = np.unique(zh, return_index=True)        # component = cluster, labels
 rank = np.empty(K_true, dtype=np.int64)
 rank[zh[np.sort(first)]] = np.arange(len(first))
 am.components._add_many(np.arange(n_tok), rank[zh])
-fv = FvScorer(am.components, fused=(False if args.two_kernel else None))
+fv = FvScorer(am.components, fused=bool(args.fused))
 fv.score()
 torch.cuda.synchronize()
 

@@ -17,16 +17,17 @@ from segmentalist_b200.kmeans_components import KMeansComponents  # noqa: E402
 from segmentalist_b200.utterances import DeviceCorpus           # noqa: E402
 
 n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
+fused = None if (len(sys.argv) <= 2 or sys.argv[2] != "two-kernel") else False
 K = 5000
 dev = torch.device("cuda", 0)
 lengths, seg_id, seg_dur, bounds0, n_emb = bench.corpus_structure(n_utt, seed=1000)
-X, _, Z = bench.make_embeddings_gpu(n_emb, K, seed=2000, device=dev)
+X, Z = bench.make_embeddings_gpu(n_emb, torch.from_numpy(bench.centres_cpu(K)).to(dev), seed=2000, device=dev)
 corpus = DeviceCorpus(lengths, seg_id, seg_dur, bounds0, 0, bench.S_MAX, bench.S_MAX)
 perm = torch.randperm(n_emb, device=dev, generator=torch.Generator(device=dev).manual_seed(7))[:K]
 comps = KMeansComponents.from_device(X, K, X[perm].clone())
 tok = corpus.tok_id[corpus.tok_id >= 0].long()
 comps._assign[tok] = Z[tok]
-sw = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer="mma")
+sw = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer="mma", fused=fused)
 sw.init_means_from_assignments()
 for _ in range(3):
     sw.sweep()
@@ -85,21 +86,19 @@ for _ in range(5):
     step("score", sw.score, acc)
     step("segment", sw.segment, acc)
     step("summarize", sw.summarize, acc)
-    step("collect", sw.collect, acc)
     if K_before < comps.K_max:
         step("clamp", lambda: sw._clamp_inactive_winners(K_before), acc)
+    step("collect", sw.collect, acc)
     step("reduce", sw.reduce_and_update, acc)
+    step("clean", sw._clean_components, acc)
 
     def tail():
-        K_now = sw.K_host
         sw.flags[1:2].copy_(sw.mma.n_fallback)
-        sw.flags[2:3].copy_((sw.cnt[:K_now] == 0).sum())
+        sw.flags[2:3].copy_(comps._K)
         torch.cuda.current_stream().wait_stream(sw.side)
         sw.flags_h.copy_(sw.flags, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return [int(v) for v in sw.flags_h.tolist()]
-    n_bad, n_fb, n_empty = step("tail", tail, acc)
+    n_bad, n_fb, K_now = step("tail", tail, acc)
     step("cumsum", lambda: float(np.cumsum(sw.log_prob_h.numpy())[-1]), acc)
-    if n_empty:
-        step("clean", lambda: sw._clean_components(sw.K_host), acc)
 print({k: round(v / 5, 3) for k, v in acc.items()}, "K_host", sw.K_host, "K_max", comps.K_max)
