@@ -529,7 +529,10 @@ def run_diag_extra(args):
     from segmentalist_b200 import fbgmm, synth, unigram_acoustic_wordseg as uaw
     from segmentalist_b200.niw import NIW
     K, n_utt = 5000, args.diag_utts
-    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K, n_min=100, n_max=120,
+    # 15 tokens per generating cluster keep ~1000 components alive under the sampler (with K_true = K_max = 5000
+    # and this many tokens every cluster has ~3 tokens and the chain collapses them into one component); a corpus
+    # with tokens >> 5000 * 15 would need minutes per sweep on this float64-log-bound path
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=1000, n_min=100, n_max=120,
                                                     n_slices_max=S_MAX, noise=NOISE, seed=53)
     prior_args = dict(m_0=np.zeros(D), k_0=0.05, v_0=D + 3, S_0=0.002 * np.ones(D))
 
@@ -591,7 +594,7 @@ def run_bigram_extra(args):
     from oracle import seg_oracle as so
     from segmentalist_b200 import bigram_acoustic_wordseg as baw, gaussian_components_fixedvar as gcf, synth
     K, n_utt = 5000, args.bigram_utts
-    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K, n_min=N_LO, n_max=N_HI,
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K // 2, n_min=N_LO, n_max=N_HI,
                                                     n_slices_max=S_MAX, noise=NOISE, seed=41)
     var = 0.002 * np.ones(D)
     lm_params = {"type": "smooth", "intrp_lambda": 0.1, "a": 10.0, "b": 10.0}

@@ -280,6 +280,11 @@ int segb_kmeans_best(const segb_kmeans *m, const int32_t *ids, int64_t n, void *
 int segb_kmeans_add_items(const segb_kmeans *m, const int32_t *ids, const int32_t *ks, int32_t n,
                           void *stream);
 int segb_kmeans_del_items(const segb_kmeans *m, const int32_t *ids, int32_t n, void *stream);
+/* The constructor's add loop (:79-81) into an EMPTY model for all components in parallel, every component
+ * summing its members in index order (bit-identical statistics); order / seg_off as in segb_fixedvar_build,
+ * components 0..K_new-1 all non-empty.                                                                 */
+int segb_kmeans_build(const segb_kmeans *m, const int64_t *order, const int64_t *seg_off, int32_t K_new,
+                      void *stream);
 int segb_kmeans_clean(const segb_kmeans *m, const int32_t *relabel_ids, int64_t relabel_n, void *stream);
 /* KMeans.fit M-step (kmeans.py:149-151): del_item(ids[i]); add_item(ids[i], ks[i]) in list order. */
 int segb_kmeans_move_items(const segb_kmeans *m, const int32_t *ids, const int32_t *ks, int32_t n, void *stream);

@@ -74,6 +74,7 @@ _PROTOS = {
     "segb_kmeans_neg_sqrd_norm_row": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_i32, c_vp, c_vp]),
     "segb_kmeans_best": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_i64, c_vp, c_vp, c_vp]),
     "segb_kmeans_add_items": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_i32, c_vp]),
+    "segb_kmeans_build": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_i32, c_vp]),
     "segb_kmeans_del_items": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_i32, c_vp]),
     "segb_kmeans_move_items": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_i32, c_vp]),
     "segb_kmeans_clean": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_i64, c_vp]),

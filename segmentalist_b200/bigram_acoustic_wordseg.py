@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .fbgmm import make_consecutive
 from .bigram_fbgmm import BigramFBGMM
 from .bigram_lms import BigramSmoothLM
 from .unigram_acoustic_wordseg import UniformFeed, _anneal_iter
@@ -64,11 +65,7 @@ class BigramAcousticWordseg(object):
         assert seed_assignments_dict is None, "seed assignments: not supported on the device path"
         if init_am_assignments == "rand":                                       # :228-243
             a = np.random.randint(0, am_K, len(init_embeds))
-            for k in range(a.max()):
-                while len(np.nonzero(a == k)[0]) == 0:
-                    a[np.where(a > k)] -= 1
-                if a.max() == k:
-                    break
+            a = make_consecutive(a)
             assignments[init_embeds] = a
         elif init_am_assignments == "one-by-one":
             assert False                                                        # :245-246

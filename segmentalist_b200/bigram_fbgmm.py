@@ -6,6 +6,7 @@ the segment scores (bigram_acoustic_wordseg.py:314-330).
 """
 import numpy as np
 
+from .fbgmm import make_consecutive
 from .gaussian_components_fixedvar import GaussianComponentsFixedVar
 
 
@@ -27,11 +28,7 @@ class BigramFBGMM(object):
             assignments = np.random.randint(0, K, N)
         elif isinstance(assignments, str) and assignments == "each-in-own":
             assignments = np.arange(N)
-        for k in range(assignments.max()):
-            while len(np.nonzero(assignments == k)[0]) == 0:
-                assignments[np.where(assignments > k)] -= 1
-            if assignments.max() == k:
-                break
+        assignments = make_consecutive(assignments)
         assert self.covariance_type == "fixed", "bigram sampling on the device: fixed-variance components"
         alpha = 1.0 if lm is None else float(lm.a)
         self.components = GaussianComponentsFixedVar(X, self.prior, assignments, K_max=K, lm=lm, alpha=alpha,

@@ -323,6 +323,31 @@ __global__ void km_set_means_kernel(segb_kmeans m, const double *sum_x, const lo
     }
 }
 
+// The constructor's add loop (kmeans_components.py:79-81: add_item for every assigned item, component by
+// component in index order) for all components at once: block k sums its own members in index order with
+// the same separately rounded float64 additions as km_add_item, so mean_numerators, counts and means come
+// out bit-identical to the sequential loop.  order / seg_off as in segb_fixedvar_build.
+template <typename T>
+__global__ void __launch_bounds__(128) km_build_kernel(segb_kmeans m, const int64_t *order, const int64_t *seg_off, int K_new) {
+    const int k = blockIdx.x;
+    if (k >= K_new) return;
+    const int64_t lo = seg_off[k], hi = seg_off[k + 1];
+    const int cnt = (int)(hi - lo);
+    for (int d = threadIdx.x; d < m.D; d += blockDim.x) {
+        double acc = 0.0;
+        for (int64_t i = lo; i < hi; ++i) acc = __dadd_rn(acc, (double)KM<T>::X(m)[(size_t)order[i] * m.D + d]);
+        const size_t o = (size_t)k * m.D + d;
+        m.mean_num[o] = acc;
+        if (cnt > 0) {
+            const T v = (T)__ddiv_rn(acc, (double)cnt);
+            KM<T>::means(m)[o] = v;
+            KM<T>::meansT(m)[(size_t)d * m.K_max + k] = v;
+        }
+    }
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) m.assignments[order[i]] = k;
+    if (threadIdx.x == 0) { m.counts[k] = cnt; if (k == 0) *m.K = K_new; }
+}
+
 static size_t km_smem(const segb_kmeans *m) { return sizeof(double) * (40 + (size_t)m->D + 8); }
 
 }  // namespace segb
@@ -360,6 +385,17 @@ extern "C" int segb_kmeans_add_items(const segb_kmeans *m, const int32_t *ids, c
     cudaStream_t st = (cudaStream_t)stream;
     KM_DISPATCH(m, (km_add_list_kernel<float><<<1, 256, 0, st>>>(*m, ids, ks, n)),
                 (km_add_list_kernel<double><<<1, 256, 0, st>>>(*m, ids, ks, n)));
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_kmeans_build(const segb_kmeans *m, const int64_t *order, const int64_t *seg_off, int32_t K_new,
+                                 void *stream) {
+    SEGB_CHECK_ARG(m && order && seg_off && K_new >= 0 && K_new <= m->K_max, "null pointer");
+    if (K_new == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    KM_DISPATCH(m, (km_build_kernel<float><<<K_new, 128, 0, st>>>(*m, order, seg_off, K_new)),
+                (km_build_kernel<double><<<K_new, 128, 0, st>>>(*m, order, seg_off, K_new)));
     SEGB_LAUNCH_CHECK();
     return 0;
 }

@@ -18,12 +18,17 @@ from .gaussian_components_fixedvar import GaussianComponentsFixedVar
 
 
 def make_consecutive(assignments):
-    """Relabel so that the used labels are 0..max without gaps (fbgmm.py:124-128)."""
-    for k in range(assignments.max()):
-        while len(np.nonzero(assignments == k)[0]) == 0:
-            assignments[np.where(assignments > k)] -= 1
-        if assignments.max() == k:
-            break
+    """Relabel so that the used labels are 0..max without gaps (fbgmm.py:124-128).  The reference shifts every
+    label above an unused one down, one unused label at a time (a full-array scan per label); the result is the
+    order-preserving renumbering of the used labels, computed here in one pass.  In place, like the reference."""
+    live = assignments >= 0
+    if not live.any():
+        return assignments
+    used = np.bincount(assignments[live]) > 0
+    if used.all():
+        return assignments
+    new_label = np.cumsum(used) - 1
+    assignments[live] = new_label[assignments[live]]
     return assignments
 
 

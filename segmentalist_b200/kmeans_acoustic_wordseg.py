@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, kmeans
+from .fbgmm import make_consecutive
 from .batch import FrozenKMeansSweep
 from .unigram_acoustic_wordseg import _dp_single
 from .utterances import DeviceCorpus, Utterances, process_embeddings
@@ -51,11 +52,7 @@ class SegmentalKMeansWordseg(object):
             assert False, "to-do"                                               # :148-149
         elif init_am_assignments == "rand":                                     # :181-196
             a = np.random.randint(0, am_K, len(init_embeds))
-            for k in range(a.max()):
-                while len(np.nonzero(a == k)[0]) == 0:
-                    a[np.where(a > k)] -= 1
-                if a.max() == k:
-                    break
+            a = make_consecutive(a)
             assignments[init_embeds] = a
         elif init_am_assignments == "spread":                                   # :198-207
             n = len(init_embeds)

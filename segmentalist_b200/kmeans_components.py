@@ -24,8 +24,8 @@ class KMeansComponents(object):
         self.K_max = int(K_max)
         assignments = np.asarray(assignments, dtype=np.int64)
         assert (self.N,) == assignments.shape
-        used = np.unique(assignments[assignments >= 0])
-        assert np.array_equal(used, np.arange(assignments.max() + 1))       # labels 0..max, no gaps (:69-70)
+        n_lab = int(assignments.max()) + 1
+        assert np.all(np.bincount(assignments[assignments >= 0], minlength=n_lab) > 0)   # labels 0..max, no gaps (:69-70)
         self.setup_random_means()                                           # :75-76
         _lib.lib()
         tdt = torch.float64 if X.dtype == np.float64 else torch.float32
@@ -39,9 +39,11 @@ class KMeansComponents(object):
         self._K = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._row = torch.empty(self.K_max, dtype=tdt, device="cuda")
         self._relabel = None
-        order = np.argsort(assignments, kind="stable")                      # :79-81
-        order = order[assignments[order] >= 0]
-        self._add_many(order, assignments[order])
+        if n_lab > 0:                                                       # :79-81, all components in parallel
+            a_dev = _lib.dev(assignments.astype(np.int32))
+            order, seg_off = _lib.members_by_component(a_dev, self.K_max)
+            _lib.check(_lib.lib().segb_kmeans_build(self.struct(), _lib.ptr(order), _lib.ptr(seg_off), n_lab,
+                                                    _lib.stream_ptr()))
 
     @classmethod
     def from_device(cls, X_dev, K_max, random_means_dev):

@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .fbgmm import make_consecutive
 from .utterances import DeviceCorpus, Utterances, band_to_packed, packed_to_band, process_embeddings, tri
 
 logger = logging.getLogger(__name__)
@@ -117,11 +118,7 @@ class UnigramAcousticWordseg(object):
                 assert am_K >= max(self.seed_to_cluster.values()) + 1
         elif init_am_assignments == "rand":                                     # :206-223
             a = np.random.randint(0, am_K, len(init_embeds))
-            for k in range(a.max()):
-                while len(np.nonzero(a == k)[0]) == 0:
-                    a[np.where(a > k)] -= 1
-                if a.max() == k:
-                    break
+            a = make_consecutive(a)
             assignments[init_embeds] = a
         elif init_am_assignments == "one-by-one":                               # :225-236
             one_by_one = True
