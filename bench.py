@@ -534,7 +534,9 @@ def run_diag_extra(args):
     # with tokens >> 5000 * 15 would need minutes per sweep on this float64-log-bound path
     mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=1000, n_min=100, n_max=120,
                                                     n_slices_max=S_MAX, noise=NOISE, seed=53)
-    prior_args = dict(m_0=np.zeros(D), k_0=0.05, v_0=D + 3, S_0=0.002 * np.ones(D))
+    # S_0 / v_0 = the corpus's within-cluster variance scale (with S_0 = 0.002 a new component's predictive is 130x
+    # narrower than the data and a long chain collapses every token into one diffuse component)
+    prior_args = dict(m_0=np.zeros(D), k_0=0.05, v_0=D + 3, S_0=0.002 * (D + 3) * np.ones(D))
 
     def build(mod, am_mod, prior):
         random.seed(5)
@@ -820,6 +822,18 @@ def fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed):
     return out
 
 
+def world_has_head(n_head, world):
+    """Whether rank 0's shard starts with the CPU-reproducible head -- decided identically on every rank
+    (n_head itself is 0 on the other ranks)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return bool(n_head)
+    t = torch.tensor([int(bool(n_head))], device="cuda", dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(t.item())
+
+
 def fbgmm_frozen_secondary(args, world, rank, dev, X, Z, corpus, lengths, seg_id, seg_dur, n_head, peak_tf, barrier,
                            max_over_ranks):
     """The sharded frozen-model sweep of the unigram FBGMM segmenter (UnigramAcousticWordseg.segment_frozen's
@@ -864,8 +878,18 @@ def fbgmm_frozen_secondary(args, world, rank, dev, X, Z, corpus, lengths, seg_id
            "utt_per_s": args.utts / (ms * 1e-3), "ms_per_sweep": ms, "n_gpus": world, "K_active": sweep.K_host,
            "fallback_rows_per_sweep": fb / steps, "phases_ms": phases,
            "segment_component_evals_per_s": float(X.shape[0]) * args.K * world / (ms * 1e-3), "dtype": "f64 scores (fp16 tensor filter + float64 refine)"}
-    # ---- CPU oracle on the head of rank 0's shard: same model state, same uniforms
-    if rank == 0 and not args.no_cpu and n_head:
+    # ---- CPU oracle on the head of rank 0's shard: same model state, same uniforms.  The sweep itself is a
+    # collective (all-reduce of the statistics): EVERY rank runs it; rank 0 keeps the model state from before it.
+    check = (not args.no_cpu) and world_has_head(n_head, world)
+    if check:
+        pre = None
+        if rank == 0:
+            pre = dict(K=comps.K, mu_N_numerators=comps.mu_N_numerators, precision_Ns=comps.precision_Ns,
+                       precision_preds=comps.precision_preds, log_prod=comps.log_prod_precision_preds, counts=comps.counts)
+        u_fb, u_as = uniforms()
+        sweep.sweep(u_fb, u_as)
+        torch.cuda.synchronize()
+    if check and rank == 0:
         from oracle import seg_oracle as so
         n_s = min(16, corpus.n_utt)
         hi = int(corpus.pos_off_h[n_s])
@@ -873,11 +897,11 @@ def fbgmm_frozen_secondary(args, world, rank, dev, X, Z, corpus, lengths, seg_id
         e_hi = int(ids.max()) + 1
         oc = so.FixedVarComponents.__new__(so.FixedVarComponents)
         oc.X = X[:e_hi].cpu().numpy()
-        oc.N, oc.D, oc.K_max, oc.K = e_hi, D, args.K, comps.K
+        oc.N, oc.D, oc.K_max, oc.K = e_hi, D, args.K, pre["K"]
         oc.precision, oc.mu_0, oc.precision_0 = comps.precision, comps.mu_0, comps.precision_0
-        oc.mu_N_numerators, oc.precision_Ns = comps.mu_N_numerators, comps.precision_Ns
-        oc.precision_preds, oc.log_prod_precision_preds = comps.precision_preds, comps.log_prod_precision_preds
-        oc.counts, oc.lm = comps.counts, None
+        oc.mu_N_numerators, oc.precision_Ns = pre["mu_N_numerators"], pre["precision_Ns"]
+        oc.precision_preds, oc.log_prod_precision_preds = pre["precision_preds"], pre["log_prod"]
+        oc.counts, oc.lm = pre["counts"], None
         oc.neg_half_D_log_2pi = -0.5 * D * np.log(2. * np.pi)
         oc.assignments = -1 * np.ones(e_hi, dtype=np.int64)
         am = so.FBGMM.__new__(so.FBGMM)
@@ -886,9 +910,6 @@ def fbgmm_frozen_secondary(args, world, rank, dev, X, Z, corpus, lengths, seg_id
         oseg.utterances = _cpu_segmenter(so, oc.X, lengths[:n_s], ids, seg_dur[:hi], np.zeros((1, D), np.float32)).utterances
         oseg.acoustic_model, oseg.fb_type = am, "standard"
         oseg.n_slices_min, oseg.n_slices_max, oseg.wip, oseg.time_power_term, oseg.beta_sent_boundary = 0, S_MAX, 0.0, 1.0, -1
-        u_fb, u_as = uniforms()
-        sweep.sweep(u_fb, u_as)
-        torch.cuda.synchronize()
         t0 = time.perf_counter()
         lps, choices = so.frozen_fbgmm_phase1(oseg, u_fb[:hi].cpu().numpy(), u_as[:hi].cpu().numpy(), range(n_s))
         dt = time.perf_counter() - t0
@@ -1089,7 +1110,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that fails alone must not leave the others waiting for the driver's time limit
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = _lib.lib()
 
     def barrier():
