@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument("--no-diffuse", action="store_true", help="skip the diffuse-model k-means sweep (K_act < K_max)")
     ap.add_argument("--fbgmm-utts", type=int, default=0, help="utterances of the frozen FBGMM sweep (default: --utts)")
     ap.add_argument("--diffuse-utts", type=int, default=40000)
+    ap.add_argument("--only-diffuse", action="store_true", help="run only the diffuse-model k-means secondary (one GPU)")
     ap.add_argument("--gibbs-utts", type=int, default=2000)
     ap.add_argument("--only-gibbs", action="store_true", help="run only the secondary Gibbs workload")
     ap.add_argument("--diag-utts", type=int, default=400)
@@ -1419,6 +1420,14 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.only_diffuse:
+        import torch
+        torch.cuda.set_device(0)
+
+        def _sync():
+            torch.cuda.synchronize()
+        print(json.dumps({"secondary_kmeans_diffuse": kmeans_diffuse_secondary(
+            args, 1, 0, torch.device("cuda", 0), _sync, lambda v: float(v))}))
     elif args.only_gibbs:
         print(json.dumps({"secondary_gibbs_fixedvar": run_gibbs_extra(args)}))
     elif args.only_diag:

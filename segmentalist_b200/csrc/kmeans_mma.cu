@@ -577,6 +577,116 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
     }
 }
 
+// Exhaustive exact scan for the rows the filter could not decide, FULLB_R rows per block pass: the rows sit
+// in shared memory ([d][r], one 16-byte read serves four rows), every thread walks its components through the
+// transposed means (coalesced over k) and keeps, for each of the rows, NumPy's eight running accumulators of
+// the current pairwise block in registers -- the means are streamed once per FULLB_R rows instead of once per
+// row (the one-row-per-block version below read 2.6 MB of L2 per undecided row: 51 ms for 230k rows of a
+// diffuse model).  Same separately rounded operations and combination tree as exact_neg_dist: bit-exact.
+// D <= 256 (at most one split of NumPy's pairwise sum).
+constexpr int FULLB_R = 8, FULLB_THREADS = 256;
+__global__ void __launch_bounds__(FULLB_THREADS) refine_full_blocked_kernel(segb_kmeans m, const int32_t *fb_list,
+                                                                            const unsigned long long *n_fallback,
+                                                                            float *best_val, int32_t *best_k) {
+    extern __shared__ float fsm[];
+    float *xs = fsm;                                   // [D][FULLB_R]
+    float *rv = fsm + (size_t)m.D * FULLB_R;           // [FULLB_R][8] per-warp best value
+    int *rk = (int *)(rv + FULLB_R * 8);               // [FULLB_R][8] per-warp best index
+    const int D = m.D, KM = m.K_max;
+    const float *X = (const float *)m.X;
+    const float *meansT = (const float *)m.meansT;
+    const long long n = (long long)*n_fallback;
+    int n2 = 0;
+    if (D > 128) { n2 = D / 2; n2 -= n2 % 8; }
+    const int n_blocks = D > 128 ? 2 : 1;
+    for (long long base = (long long)blockIdx.x * FULLB_R; base < n; base += (long long)gridDim.x * FULLB_R) {
+        const int nr = (int)min((long long)FULLB_R, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < D * FULLB_R; i += blockDim.x) {
+            const int r = i / D, d = i % D;
+            xs[d * FULLB_R + r] = r < nr ? X[(int64_t)fb_list[base + r] * D + d] : 0.f;
+        }
+        __syncthreads();
+        float bv[FULLB_R];
+        int bk[FULLB_R];
+#pragma unroll
+        for (int r = 0; r < FULLB_R; ++r) { bv[r] = -CUDART_INF_F; bk[r] = 0x7fffffff; }
+        for (int k = threadIdx.x; k < KM; k += blockDim.x) {
+            float tot[FULLB_R];
+#pragma unroll
+            for (int r = 0; r < FULLB_R; ++r) tot[r] = 0.f;
+            for (int b = 0; b < n_blocks; ++b) {
+                const int lo = b == 0 ? 0 : n2, nb = D > 128 ? (b == 0 ? n2 : D - n2) : D;
+                const int n8 = nb >= 8 ? nb - (nb % 8) : 0;
+                float res[FULLB_R];
+                if (n8 > 0) {
+                    float acc[FULLB_R][8];
+                    for (int i = 0; i < n8; i += 8) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int d = lo + i + j;
+                            const float mu = meansT[(size_t)d * KM + k];
+                            const float4 xa = *reinterpret_cast<const float4 *>(xs + d * FULLB_R);
+                            const float4 xb = *reinterpret_cast<const float4 *>(xs + d * FULLB_R + 4);
+                            const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                            for (int r = 0; r < FULLB_R; ++r) {
+                                const float dl = __fsub_rn(mu, xr[r]);
+                                const float pr = __fmul_rn(dl, dl);
+                                acc[r][j] = (i == 0) ? pr : __fadd_rn(acc[r][j], pr);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < FULLB_R; ++r)
+                        res[r] = __fadd_rn(__fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3])),
+                                           __fadd_rn(__fadd_rn(acc[r][4], acc[r][5]), __fadd_rn(acc[r][6], acc[r][7])));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < FULLB_R; ++r) res[r] = 0.f;
+                }
+                for (int d = lo + n8; d < lo + nb; ++d) {                 // the block's n % 8 trailing terms
+                    const float mu = meansT[(size_t)d * KM + k];
+#pragma unroll
+                    for (int r = 0; r < FULLB_R; ++r) {
+                        const float dl = __fsub_rn(mu, xs[d * FULLB_R + r]);
+                        res[r] = __fadd_rn(res[r], __fmul_rn(dl, dl));
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < FULLB_R; ++r) tot[r] = b == 0 ? res[r] : __fadd_rn(tot[r], res[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < FULLB_R; ++r) {
+                const float v = -tot[r];
+                if (v > bv[r] || bk[r] == 0x7fffffff) { bv[r] = v; bk[r] = k; }       // k ascending per thread: first max
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < FULLB_R; ++r) {
+            float v = bv[r];
+            int kk = bk[r];
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, v, o);
+                const int ok = __shfl_xor_sync(FULL, kk, o);
+                if (ov > v || (ov == v && ok < kk)) { v = ov; kk = ok; }
+            }
+            if ((threadIdx.x & 31) == 0) { rv[r * 8 + (threadIdx.x >> 5)] = v; rk[r * 8 + (threadIdx.x >> 5)] = kk; }
+        }
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            const int r = threadIdx.x;
+            float v = rv[r * 8];
+            int kk = rk[r * 8];
+            for (int w = 1; w < FULLB_THREADS / 32; ++w)
+                if (rv[r * 8 + w] > v || (rv[r * 8 + w] == v && rk[r * 8 + w] < kk)) { v = rv[r * 8 + w]; kk = rk[r * 8 + w]; }
+            const int64_t row = fb_list[base + r];
+            best_val[row] = v;
+            best_k[row] = (kk == 0x7fffffff) ? -1 : kk;
+        }
+    }
+}
+
 // Exhaustive exact scan for the rows the filter could not decide: one block per row.
 __global__ void __launch_bounds__(256) refine_full_kernel(segb_kmeans m, const int32_t *fb_list,
                                                           const unsigned long long *n_fallback, float *best_val,
@@ -706,8 +816,14 @@ namespace mma {
 // exhaustive exact scan of the rows listed in fb_list[0 .. *n_fallback)
 int launch_refine_full(const segb_kmeans *m, const int32_t *fb_list, const int64_t *n_fallback, float *best_val,
                        int32_t *best_k, cudaStream_t st) {
-    refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(
-        *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
+    const size_t smem_b = sizeof(float) * ((size_t)m->D * FULLB_R + FULLB_R * 8) + sizeof(int) * FULLB_R * 8;
+    int n2 = m->D / 2; n2 -= n2 % 8;
+    if (m->D <= 256 && smem_b <= 48 * 1024)
+        refine_full_blocked_kernel<<<148 * 4, FULLB_THREADS, smem_b, st>>>(
+            *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
+    else
+        refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(
+            *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
     SEGB_LAUNCH_CHECK();
     return 0;
 }
