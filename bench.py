@@ -68,9 +68,11 @@ def parse_args():
     ap.add_argument("--only-diffuse", action="store_true", help="run only the diffuse-model k-means secondary (one GPU)")
     ap.add_argument("--gibbs-utts", type=int, default=2000)
     ap.add_argument("--only-gibbs", action="store_true", help="run only the secondary Gibbs workload")
-    ap.add_argument("--diag-utts", type=int, default=400)
+    ap.add_argument("--diag-utts", type=int, default=800)
+    ap.add_argument("--diag-k-true", type=int, default=5000)
+    ap.add_argument("--diag-init", default="one-by-one", choices=["rand", "one-by-one"])
     ap.add_argument("--only-diag", action="store_true", help="run only the diagonal-covariance secondary workload")
-    ap.add_argument("--bigram-utts", type=int, default=4000)
+    ap.add_argument("--bigram-utts", type=int, default=8000)
     ap.add_argument("--only-bigram", action="store_true", help="run only the bigram cluster-sampling secondary workload")
     return ap.parse_args()
 
@@ -530,21 +532,28 @@ def run_diag_extra(args):
     from segmentalist_b200 import fbgmm, synth, unigram_acoustic_wordseg as uaw
     from segmentalist_b200.niw import NIW
     K, n_utt = 5000, args.diag_utts
-    # 15 tokens per generating cluster keep ~1000 components alive under the sampler (with K_true = K_max = 5000
-    # and this many tokens every cluster has ~3 tokens and the chain collapses them into one component); a corpus
-    # with tokens >> 5000 * 15 would need minutes per sweep on this float64-log-bound path
-    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=1000, n_min=100, n_max=120,
+    # K_true = K_max generating clusters and the reference's "one-by-one" initialisation (every token is added by a
+    # collapsed Gibbs draw against the tokens before it, unigram_acoustic_wordseg.py:225-236): cluster mates join
+    # the component their first token opened, so the chain starts -- and stays -- with about one component per
+    # generating cluster that has tokens.  (A "rand" start puts 3 unrelated tokens into each of the 5000 slots;
+    # with no free slot to open, the chain then collapses everything into one broad component.)
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=args.diag_k_true, n_min=100, n_max=120,
                                                     n_slices_max=S_MAX, noise=NOISE, seed=53)
     # S_0 / v_0 = the corpus's within-cluster variance scale (with S_0 = 0.002 a new component's predictive is 130x
     # narrower than the data and a long chain collapses every token into one diffuse component)
     prior_args = dict(m_0=np.zeros(D), k_0=0.05, v_0=D + 3, S_0=0.002 * (D + 3) * np.ones(D))
 
-    def build(mod, am_mod, prior):
+    def build(mod, am_mod, prior, init=None):
         random.seed(5)
         np.random.seed(5)
         return mod.UnigramAcousticWordseg(am_mod.FBGMM, 10., K, prior, mats, vids, durs, lms, p_boundary_init=0.5,
-                                          beta_sent_boundary=-1, n_slices_max=S_MAX, covariance_type="diag")
+                                          beta_sent_boundary=-1, n_slices_max=S_MAX, covariance_type="diag",
+                                          init_am_assignments=init or args.diag_init)
+    t_setup = time.perf_counter()
     seg = build(uaw, fbgmm, NIW(**prior_args))
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    K_init = seg.acoustic_model.components.K
     n_seg = int(sum(m.shape[0] for m in mats.values()))
     order = list(range(n_utt))
     seg._sweep(order, 1, False)                       # warm-up sweep
@@ -554,8 +563,10 @@ def run_diag_extra(args):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     K_act = seg.acoustic_model.components.K
-    out = {"workload": "unigram_fbgmm_diag_gibbs_sweep D=130 K_max=5000 U=%d N~U{100..120} max_span=6 (BASELINE configs[4])" % n_utt,
+    out = {"workload": "unigram_fbgmm_diag_gibbs_sweep D=130 K_max=5000 K_true=%d U=%d N~U{100..120} max_span=6 %s init "
+                       "(BASELINE configs[4])" % (args.diag_k_true, n_utt, args.diag_init),
            "utt_per_s": n_utt / wall, "ms_per_sweep": wall * 1e3, "candidate_segments": n_seg, "K_active": K_act,
+           "K_after_init": K_init, "setup_s": t_setup,
            "student_t_log_evals_per_s": n_seg * float(K_act) * D / wall, "dtype": "f64",
            "tokens": int(seg.acoustic_model.get_n_assigned()),
            "roofline": {"bound": "sfu (SURVEY 8d: D log evaluations per segment x component)",
@@ -567,9 +578,11 @@ def run_diag_extra(args):
                                 "reach by construction; identical samples need float64"},
            "note": "evals counted over the ACTIVE components of the sampled state"}
     if not args.no_cpu:
+        # the pure-Python oracle cannot afford the one-by-one start (one K x D Student's t evaluation per token in
+        # NumPy): parity and the CPU rate are taken on the "rand" start of the same corpus (all 5000 slots occupied)
         n_cpu = 2
-        oseg = build(so, so, so.NIW(**prior_args))
-        gseg = build(uaw, fbgmm, NIW(**prior_args))
+        oseg = build(so, so, so.NIW(**prior_args), "rand")
+        gseg = build(uaw, fbgmm, NIW(**prior_args), "rand")
         st = random.getstate()
         t0 = time.perf_counter()
         for u in range(n_cpu):
@@ -581,7 +594,7 @@ def run_diag_extra(args):
                     np.array_equal(gseg.acoustic_model.components.assignments,
                                    oseg.acoustic_model.components.assignments))
         out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "utt/s", "cores": 1, "kind": "port",
-                               "sample": "%d gibbs_sample_i calls of the same seeded corpus/model" % n_cpu,
+                               "sample": "%d gibbs_sample_i calls of the same seeded corpus, 'rand' start (5000 occupied slots)" % n_cpu,
                                "seconds": dt, "identical_samples_on_sample": same}
     return out
 
@@ -597,7 +610,7 @@ def run_bigram_extra(args):
     from oracle import seg_oracle as so
     from segmentalist_b200 import bigram_acoustic_wordseg as baw, gaussian_components_fixedvar as gcf, synth
     K, n_utt = 5000, args.bigram_utts
-    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K // 2, n_min=N_LO, n_max=N_HI,
+    mats, vids, durs, lms = synth.make_corpus_dicts(n_utt, D=D, K_true=K, n_min=N_LO, n_max=N_HI,
                                                     n_slices_max=S_MAX, noise=NOISE, seed=41)
     var = 0.002 * np.ones(D)
     lm_params = {"type": "smooth", "intrp_lambda": 0.1, "a": 10.0, "b": 10.0}
@@ -621,7 +634,7 @@ def run_bigram_extra(args):
     torch.cuda.synchronize()
     wall_a = time.perf_counter() - t0
     n_seg = int(sum(m.shape[0] for m in mats.values()))
-    out = {"workload": "bigram_fbgmm_cluster_sampling D=130 K=5000 U=%d max_span=6 (BASELINE configs[3])" % n_utt,
+    out = {"workload": "bigram_fbgmm_cluster_sampling D=130 K=K_true=5000 U=%d max_span=6 (BASELINE configs[3])" % n_utt,
            "utt_per_s": n_utt / wall, "ms_per_sweep": wall * 1e3, "candidate_segments": n_seg,
            "assignments_only": {"ms_per_sweep": wall_a * 1e3, "tokens": int(n_tok), "tokens_per_s": n_tok / wall_a,
                                 "note": "one K_max-slot draw per token under the bigram prior row of the previous label"},
@@ -1172,6 +1185,8 @@ def run_ours(args):
     barrier()
     launches0 = lib.segb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sweep.mma is not None:
+        sweep.mma.timing = []              # CUDA events around the scoring kernels of every timed sweep
     ev0.record()
     fallback = 0
     for _ in range(args.steps):
@@ -1180,6 +1195,10 @@ def run_ours(args):
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
+    in_sweep_ms = None
+    if sweep.mma is not None:
+        tm, sweep.mma.timing = sweep.mma.timing, None
+        in_sweep_ms = (sum(e[0].elapsed_time(e[1]) for e in tm) / len(tm), sum(e[1].elapsed_time(e[2]) for e in tm) / len(tm))
     launches = lib.segb_launch_count() - launches0
     tot = torch.tensor([evals_per_sweep_local, float(M), float(fallback)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -1214,9 +1233,11 @@ def run_ours(args):
             fused = sweep.mma.fused
             run_k = (lambda: sweep.mma.fused_score(sweep.best_val, sweep.best_k)) if fused else sweep.mma.filter
             run_k()
-            k_ms = timed(run_k, 5)
+            k_ms_b2b = timed(run_k, 5)                    # five launches back to back: 100 ms of pure tensor work
+            k_ms = in_sweep_ms[0]                         # the launches of the timed sweeps themselves
             flops = 2.0 * D * M * args.K                  # algorithmic: 2*D per segment x component eval
             ach = flops / (k_ms * 1e-3) / 1e12
+            peak_sus = float(peaks.get("bf16_tflops_sustained", 0.0)) or None
             kname = "score_fused_kernel" if fused else "kmeans_filter_kernel"
             tr = ncu_traffic(kname) if default_cfg else None
             roofline = {"kernel": ("score_fused_kernel<kmeans> (fp32 rows -> fp16 operand tiles in shared memory, tcgen05 fp16 -> fp32 "
@@ -1229,7 +1250,13 @@ def run_ours(args):
                         "algorithmic_bytes_per_launch": float(X.numel() * 4 + 8 * M) if fused else
                                                         float(sweep.mma.x_tiles.numel() + sweep.mma.cand.numel()),
                         "peak_source": peak_src,
-                        "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops}
+                        "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
+                        "timing": "kernel_ms = mean over the launches INSIDE the %d timed sweeps (CUDA events on the launching "
+                                  "stream around the kernel); kernel_ms_back_to_back = 5 launches of the kernel alone with "
+                                  "nothing between them (the power-capped clock of a pure tensor loop)" % args.steps,
+                        "kernel_ms_back_to_back": k_ms_b2b, "frac_back_to_back": flops / (k_ms_b2b * 1e-3) / 1e12 / peak_tf,
+                        "frac_of_sustained_peak": (ach / peak_sus) if peak_sus else None,
+                        "refine_ms_in_sweep": in_sweep_ms[1]}
         cs = corpus.struct()
 
         def time_dp(mode, reps=20, u=None):

@@ -347,6 +347,19 @@ int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max);
 int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_max,
                     int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
                     void *stream);
+/* Same refine with a SECOND-LEVEL tensor pass in front of the exhaustive scan (models with many
+ * near-duplicate components -- a diffuse k-means state, K_true << K_max -- leave more than three chunks
+ * inside the bound for many rows): the undecided rows' fp16 images are gathered into a compact tile
+ * image, the filter GEMM runs over them again with a bitmap epilogue (every component whose filter
+ * score reaches best - tau of the first pass), and only the flagged components are re-scored exactly.
+ * Same bits out (kmeans_components.py:225-232).  x_tiles / w_tiles: the images segb_mma_filter read.
+ * work: segb_mma_refine2_work_bytes() bytes (the first n_emb/8 undecided rows take the second-level
+ * pass; a smaller buffer, down to segb_mma_refine_work_bytes(), lowers that capacity; the rest get
+ * the exhaustive scan).  n_fallback counts the rows the top-3 records could not decide.           */
+int64_t segb_mma_refine2_work_bytes(int64_t n_emb, int32_t K_max, int32_t D);
+int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const void *w_tiles, const void *cand,
+                     const float *x_err, const float *w_max, int64_t n_emb, void *work, int64_t work_bytes,
+                     float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
 
 /* ------------------------------------------------------------------ tensor-core log_marg_i (fixed variance) */
 

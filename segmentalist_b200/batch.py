@@ -56,11 +56,15 @@ class MmaScorer(object):
         self.fused = False if fused is None else bool(fused)
         assert not self.fused or fused_supported(c.D)
         self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
-        self.work = torch.empty(lib.segb_mma_refine_work_bytes(c.N, c.K_max), dtype=torch.uint8, device=dev)
+        # refine scratch: list of undecided rows + (two-kernel path) their compact fp16 image, thresholds and
+        # candidate bitmaps for the second-level tensor pass
+        self.work = torch.empty(lib.segb_mma_refine_work_bytes(c.N, c.K_max) if self.fused else
+                                lib.segb_mma_refine2_work_bytes(c.N, c.K_max, c.D), dtype=torch.uint8, device=dev)
         self.w_err = torch.empty(2 * (c.K_max + 128), dtype=torch.float32, device=dev)  # (|dmu|, |mu^|)
         self.w_max = torch.zeros(2, dtype=torch.float32, device=dev)
         self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
         self.x_tiles = self.cand = self.x_err = self.x_max = None
+        self.timing = None      # a list: score() appends (start, after filter/fused kernel, after refine) CUDA events
         if not self.fused:
             self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
             self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
@@ -86,9 +90,10 @@ class MmaScorer(object):
 
     def refine(self, best_val, best_k):
         c = self.c
-        _lib.check(_lib.lib().segb_mma_refine(c.struct(), _lib.ptr(self.cand), _lib.ptr(self.x_err),
-                                              _lib.ptr(self.w_max), c.N, _lib.ptr(self.work), _lib.ptr(best_val),
-                                              _lib.ptr(best_k), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+        _lib.check(_lib.lib().segb_mma_refine2(c.struct(), _lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles),
+                                               _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max), c.N,
+                                               _lib.ptr(self.work), self.work.numel(), _lib.ptr(best_val),
+                                               _lib.ptr(best_k), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
 
     def fused_score(self, best_val, best_k):
         """The model image must be current (pack_means)."""
@@ -99,11 +104,22 @@ class MmaScorer(object):
 
     def score(self, best_val, best_k):
         self.pack_means()
+        ev = None
+        if self.timing is not None:          # device time of the kernels INSIDE a running sweep (bench.py roofline)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         if self.fused:
             self.fused_score(best_val, best_k)
+            if ev:
+                ev[1].record()
         else:
             self.filter()
+            if ev:
+                ev[1].record()
             self.refine(best_val, best_k)
+        if ev:
+            ev[2].record()
+            self.timing.append(ev)
 
     def score_streamed(self, X_host, best_val, best_k, chunk_rows=1 << 20):
         """Score embeddings that still live in (pinned) HOST memory: the rows are uploaded in
@@ -148,8 +164,9 @@ class MmaScorer(object):
                 _lib.check(lib.segb_mma_pack_x(vp(x_base + 4 * c.D * lo), n, c.D, xt, xe, _lib.ptr(self.x_max), sp))
                 _lib.check(lib.segb_mma_filter(xt, _lib.ptr(self.w_tiles), n, c.K_max, c.D, _lib.ptr(self.x_max),
                                                _lib.ptr(self.w_max), cd, sp))
-                _lib.check(lib.segb_mma_refine(m, cd, xe, _lib.ptr(self.w_max), n, _lib.ptr(self.work), bv, bk,
-                                               _lib.ptr(self.n_fallback), sp))
+                _lib.check(lib.segb_mma_refine2(m, xt, _lib.ptr(self.w_tiles), cd, xe, _lib.ptr(self.w_max), n,
+                                                _lib.ptr(self.work), self.work.numel(), bv, bk,
+                                                _lib.ptr(self.n_fallback), sp))
             self.fb_total += self.n_fallback
         self.n_fallback.copy_(self.fb_total)
 

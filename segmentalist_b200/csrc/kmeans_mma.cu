@@ -76,6 +76,12 @@ struct FilterParams {
     int32_t D;
     int32_t tau_kind;              // TAU_KMEANS: argmax filter (2 * bound); TAU_LSE: logsumexp filter (tau_T + 2 * bound)
     float tau_T;
+    // second-level pass over the rows the top-3 records could not decide (EPI = 1): the row count lives on the
+    // device, every row has its own threshold and gets a bitmap of ALL the components at or above it
+    const unsigned long long *n_rows_dev;   // rows = min(*n_rows_dev, rows_cap)
+    int64_t rows_cap;
+    const float *thr;              // [rows_cap] per-row threshold (best filter score - tau of the first pass)
+    uint32_t *bitmap;              // [rows_cap][n_ntiles * 4] bit k of a row: filter score of component k >= thr
 };
 
 // KS = number of K=16 steps per chunk when known at compile time (fully unrolled issue loop), 0 = runtime.
@@ -84,10 +90,17 @@ struct FilterParams {
 // chunk images; the B ring holds one chunk per stage (stage = chunk index), the accumulators stay
 // double-buffered by tile parity, and the issuer commits twice per tile: "chunk-0 stage free" and
 // "tile done" (= chunk-1 stage free + accumulators ready).
-template <int KS, int NCH>
+// EPI = 0: running top-3 chunk maxima per row (Cand records); EPI = 1: per-row bitmap of the components whose
+// score reaches the row's threshold (second-level pass, device-side row count).
+template <int KS, int NCH, int EPI = 0>
 __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (EPI == 1) {
+        const unsigned long long n_dev = *p.n_rows_dev;
+        p.n_emb = (int64_t)(n_dev < (unsigned long long)p.rows_cap ? n_dev : (unsigned long long)p.rows_cap);
+        p.n_mtiles = (int32_t)((p.n_emb + MT_ROWS - 1) / MT_ROWS);
+    }
     const uint32_t tb = p.tile_bytes;
     const int n_ks = KS > 0 ? KS : p.n_ksteps;
     uint8_t *sA = smem;                                        // n_abuf x 2 tiles x NCH chunks
@@ -264,6 +277,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
             ? filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D)
             : lse_tau(p.x_max[0], p.x_max[1], W4{p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3]}, 16 * n_ks * NCH, p.tau_T);
         uint32_t n_use = 0;
+        if (EPI == 1) {
+            // bit j of word w of a row = component 32 w + j reaches the row's threshold: the sign bits of
+            // (score - thr) funnel-shifted into two words per tile and thread, 8 bytes per tile to HBM
+            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+                const int64_t row = (int64_t)mt * MT_ROWS + h * TILE_ROWS + q * 32 + lane;
+                const float thr = p.thr[row];
+                uint2 *out = reinterpret_cast<uint2 *>(p.bitmap + row * (int64_t)(p.n_ntiles * 4)) + part;
+                for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
+                    const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
+                    mbar_wait(BAR(MMA_DONE + buf), acc_phase);
+                    tc_fence_after();
+                    float v[64];
+                    tc_ld64_wait(tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS, v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+                    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+                    for (int j = 31; j >= 0; --j) {
+                        w0 = __funnelshift_l(__float_as_uint(v[j] - thr), w0, 1);
+                        w1 = __funnelshift_l(__float_as_uint(v[32 + j] - thr), w1, 1);
+                    }
+                    out[2 * nt] = make_uint2(~w0, ~w1);
+                }
+            }
+        } else
         for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
             float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
             int i1 = -1, i2 = -1;
@@ -577,6 +616,97 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
     }
 }
 
+
+// ---- second-level pass over the rows the top-3 records could not decide ----------------------------------
+// A model with many near-duplicate components (a diffuse k-means state: K_true << K_max) leaves more than
+// three 16-component chunks inside the error bound of the best score, and an exhaustive exact scan of such a
+// row costs K_max * D * 3 float operations.  Instead the undecided rows are gathered into a compact fp16 tile
+// image, the SAME filter GEMM runs over them once more with a different epilogue -- a bitmap of every component
+// whose filter score reaches the row's threshold (best score - tau, both known from the first pass) -- and only
+// those components (tens, not thousands) are re-scored exactly.  Rigour is unchanged: the reference's winner k*
+// has t^(k*) >= t(k*) - b >= t(k1) - b >= t^(k1) - 2b = m1 - tau for ANY filter scores within b of the truth.
+
+// one warp per undecided row i: fp16 row of the tile image -> compact tile image, thr[i] = m1 - tau(row);
+// the rows that pad the last 256-row work item are zeroed and get thr = +inf (empty bitmap)
+__global__ void __launch_bounds__(256) gather_undecided_kernel(const uint8_t *x_tiles, const Cand *cand, const float *x_err,
+                                                               const float *w_max, const int32_t *fb_list,
+                                                               const unsigned long long *n_fallback, int64_t rows_cap,
+                                                               int D, int KP, uint8_t *fb_tiles, float *thr) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_dev = *n_fallback;
+    const int64_t n = (int64_t)(n_dev < (unsigned long long)rows_cap ? n_dev : (unsigned long long)rows_cap);
+    const int64_t n_pad = (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS;
+    const int64_t tile_b = (int64_t)TILE_ROWS * KP * 2;
+    const int64_t w_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t w_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = w_global; i < n_pad; i += w_total) {
+        uint8_t *dst = fb_tiles + (i / TILE_ROWS) * tile_b;
+        const int ri = (int)(i % TILE_ROWS);
+        if (i < n) {
+            const int64_t row = fb_list[i];
+            const uint8_t *src = x_tiles + (row / TILE_ROWS) * tile_b;
+            const int rr = (int)(row % TILE_ROWS);
+            for (int ch = lane; ch < KP / 8; ch += 32)
+                *reinterpret_cast<uint4 *>(dst + tile_off(ri, ch * 8)) = *reinterpret_cast<const uint4 *>(src + tile_off(rr, ch * 8));
+            if (lane == 0) {
+                const Cand c = cand[row];
+                const float tau = filter_tau(x_err[2 * row], x_err[2 * row + 1], w_max[0], w_max[1], D);
+                // unusable record or unbounded error: every component stays a candidate
+                thr[i] = (c.i1 >= 0 && tau < CUDART_INF_F && c.m1 > -CUDART_INF_F) ? c.m1 - tau : -CUDART_INF_F;
+            }
+        } else {
+            for (int ch = lane; ch < KP / 8; ch += 32)
+                *reinterpret_cast<uint4 *>(dst + tile_off(ri, ch * 8)) = make_uint4(0, 0, 0, 0);
+            if (lane == 0) thr[i] = CUDART_INF_F;
+        }
+    }
+}
+
+// eight lanes per undecided row: exact score (same routine and bits as refine_rows8_kernel) of every component
+// flagged in the row's bitmap, first maximum in component order.  A row with an empty bitmap (cannot happen for
+// finite data; NaN scores) goes to the exhaustive scan through unres_list.
+template <int MAXS>
+__global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
+    segb_kmeans m, const int32_t *fb_list, const unsigned long long *n_fallback, int64_t rows_cap, const uint32_t *bitmap,
+    int n_words, float *best_val, int32_t *best_k, unsigned long long *n_unres, int32_t *unres_list) {
+    const int D = m.D, KM = m.K_max;
+    const int lane = threadIdx.x & 31, j = lane & 7;
+    const Row8Geom geo(D, lane);
+    const float *X = (const float *)m.X;
+    const float *means = (const float *)m.means;
+    const unsigned long long n_dev = *n_fallback;
+    const int64_t n = (int64_t)(n_dev < (unsigned long long)rows_cap ? n_dev : (unsigned long long)rows_cap);
+    const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    for (int64_t i = grp_global; i < n; i += grp_total) {
+        const int64_t row = fb_list[i];
+        float2 xv[MAXS];
+        km_load_x8<MAXS>(X + row * D, geo, xv);
+        const uint32_t *bm = bitmap + i * n_words;
+        float bv = -CUDART_INF_F;
+        int bk = 0x7fffffff;
+        for (int w0 = 0; w0 < n_words; w0 += 8) {
+            // lane j of the group fetches word w0 + j; the eight words are then walked by the whole group
+            const uint32_t mine = (w0 + j < n_words) ? bm[w0 + j] : 0u;
+            if (__ballot_sync(geo.gmask, mine != 0u) == 0u) continue;
+            for (int t = 0; t < 8; ++t) {
+                uint32_t bits = __shfl_sync(geo.gmask, mine, geo.gbase + t);
+                while (bits) {
+                    const int k = (w0 + t) * 32 + (__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    if (k >= KM) continue;
+                    const float v = km_exact_one8<MAXS>(means, D, X + row * D, xv, k, geo);
+                    if (v > bv || bk == 0x7fffffff) { bv = v; bk = k; }          // k ascending: first maximum
+                }
+            }
+        }
+        if (j == 0) {
+            if (bk == 0x7fffffff) unres_list[atomicAdd(n_unres, 1ull)] = (int32_t)row;
+            else { best_val[row] = bv; best_k[row] = bk; }
+        }
+    }
+}
+
 // Exhaustive exact scan for the rows the filter could not decide, FULLB_R rows per block pass: the rows sit
 // in shared memory ([d][r], one 16-byte read serves four rows), every thread walks its components through the
 // transposed means (coalesced over k) and keeps, for each of the rows, NumPy's eight running accumulators of
@@ -587,7 +717,7 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
 constexpr int FULLB_R = 8, FULLB_THREADS = 256;
 __global__ void __launch_bounds__(FULLB_THREADS) refine_full_blocked_kernel(segb_kmeans m, const int32_t *fb_list,
                                                                             const unsigned long long *n_fallback,
-                                                                            float *best_val, int32_t *best_k) {
+                                                                            long long first, float *best_val, int32_t *best_k) {
     extern __shared__ float fsm[];
     float *xs = fsm;                                   // [D][FULLB_R]
     float *rv = fsm + (size_t)m.D * FULLB_R;           // [FULLB_R][8] per-warp best value
@@ -595,11 +725,11 @@ __global__ void __launch_bounds__(FULLB_THREADS) refine_full_blocked_kernel(segb
     const int D = m.D, KM = m.K_max;
     const float *X = (const float *)m.X;
     const float *meansT = (const float *)m.meansT;
-    const long long n = (long long)*n_fallback;
+    const long long n = (long long)*n_fallback;          // rows [first, n) of the list
     int n2 = 0;
     if (D > 128) { n2 = D / 2; n2 -= n2 % 8; }
     const int n_blocks = D > 128 ? 2 : 1;
-    for (long long base = (long long)blockIdx.x * FULLB_R; base < n; base += (long long)gridDim.x * FULLB_R) {
+    for (long long base = first + (long long)blockIdx.x * FULLB_R; base < n; base += (long long)gridDim.x * FULLB_R) {
         const int nr = (int)min((long long)FULLB_R, n - base);
         __syncthreads();
         for (int i = threadIdx.x; i < D * FULLB_R; i += blockDim.x) {
@@ -689,8 +819,8 @@ __global__ void __launch_bounds__(FULLB_THREADS) refine_full_blocked_kernel(segb
 
 // Exhaustive exact scan for the rows the filter could not decide: one block per row.
 __global__ void __launch_bounds__(256) refine_full_kernel(segb_kmeans m, const int32_t *fb_list,
-                                                          const unsigned long long *n_fallback, float *best_val,
-                                                          int32_t *best_k) {
+                                                          const unsigned long long *n_fallback, long long first,
+                                                          float *best_val, int32_t *best_k) {
     extern __shared__ float fsm[];
     float *xs = fsm;                      // [D]
     float *rv = fsm + m.D;                // [8] per-warp best value
@@ -699,7 +829,7 @@ __global__ void __launch_bounds__(256) refine_full_kernel(segb_kmeans m, const i
     const float *X = (const float *)m.X;
     const float *meansT = (const float *)m.meansT;
     const long long n = (long long)*n_fallback;
-    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+    for (long long i = first + blockIdx.x; i < n; i += gridDim.x) {
         const int64_t row = fb_list[i];
         __syncthreads();
         for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = X[row * D + d];
@@ -766,8 +896,10 @@ extern "C" int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D,
 
 namespace segb {
 namespace mma {
-int launch_filter(const FilterLaunch &f, cudaStream_t stream) {
+static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n_rows_dev, int64_t rows_cap,
+                              const float *thr, uint32_t *bitmap, cudaStream_t stream) {
     FilterParams p;
+    p.n_rows_dev = n_rows_dev; p.rows_cap = rows_cap; p.thr = thr; p.bitmap = bitmap;
     p.x_tiles = (const uint8_t *)f.x_tiles; p.w_tiles = (const uint8_t *)f.w_tiles; p.cand = (Cand *)f.cand;
     p.n_emb = f.n_emb;
     p.x_max = f.x_max; p.w_max = f.w_max; p.D = f.D;
@@ -791,13 +923,17 @@ int launch_filter(const FilterLaunch &f, cudaStream_t stream) {
     { const int rc = device_info(nullptr, &n_sm, nullptr); if (rc) return rc; }
     const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;
     void (*kern)(FilterParams);
-    if (nch == 1) kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 1> : kmeans_filter_kernel<0, 1>;     // 9: D = 130 (KP = 144)
+    if (n_rows_dev) {
+        if (nch != 1) { set_error("second-level filter pass: one inner-dimension chunk"); return SEGB_E_ARG; }
+        kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 1, 1> : kmeans_filter_kernel<0, 1, 1>;
+    } else if (nch == 1) kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 1> : kmeans_filter_kernel<0, 1>;     // 9: D = 130 (KP = 144)
     else kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 2> : kmeans_filter_kernel<0, 2>;
     SEGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, N_THREADS, smem, stream>>>(p);
     SEGB_LAUNCH_CHECK();
     return 0;
 }
+int launch_filter(const FilterLaunch &f, cudaStream_t stream) { return launch_filter_impl(f, nullptr, 0, nullptr, nullptr, stream); }
 }  // namespace mma
 }  // namespace segb
 
@@ -814,18 +950,21 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
 namespace segb {
 namespace mma {
 // exhaustive exact scan of the rows listed in fb_list[0 .. *n_fallback)
-int launch_refine_full(const segb_kmeans *m, const int32_t *fb_list, const int64_t *n_fallback, float *best_val,
-                       int32_t *best_k, cudaStream_t st) {
+static int launch_refine_full_from(const segb_kmeans *m, const int32_t *fb_list, const int64_t *n_fallback, int64_t first,
+                                   float *best_val, int32_t *best_k, cudaStream_t st) {
     const size_t smem_b = sizeof(float) * ((size_t)m->D * FULLB_R + FULLB_R * 8) + sizeof(int) * FULLB_R * 8;
-    int n2 = m->D / 2; n2 -= n2 % 8;
     if (m->D <= 256 && smem_b <= 48 * 1024)
         refine_full_blocked_kernel<<<148 * 4, FULLB_THREADS, smem_b, st>>>(
-            *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
+            *m, fb_list, (const unsigned long long *)n_fallback, (long long)first, best_val, best_k);
     else
         refine_full_kernel<<<148 * 8, 256, sizeof(float) * (m->D + 16), st>>>(
-            *m, fb_list, (const unsigned long long *)n_fallback, best_val, best_k);
+            *m, fb_list, (const unsigned long long *)n_fallback, (long long)first, best_val, best_k);
     SEGB_LAUNCH_CHECK();
     return 0;
+}
+int launch_refine_full(const segb_kmeans *m, const int32_t *fb_list, const int64_t *n_fallback, float *best_val,
+                       int32_t *best_k, cudaStream_t st) {
+    return launch_refine_full_from(m, fb_list, n_fallback, 0, best_val, best_k, st);
 }
 }  // namespace mma
 }  // namespace segb
@@ -835,9 +974,11 @@ extern "C" int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max) {
     return (n_emb + 64) * (int64_t)sizeof(int32_t);
 }
 
-extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_max,
-                               int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
-                               void *stream) {
+// first stage of both refine entry points: every row's surviving candidates re-scored exactly, the rows the
+// record cannot decide appended to fb_list (count in n_fallback)
+static int refine_rows_stage(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_max,
+                             int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
+                             void *stream) {
     SEGB_CHECK_ARG(m && cand && x_err && w_max && work && best_val && best_k && n_fallback, "null pointer");
     SEGB_CHECK_ARG(!m->x_is_f64, "tensor-core scorer needs float32 embeddings");
     SEGB_CHECK_ARG(n_emb < (1ll << 31), "too many embeddings for one refine call");
@@ -872,5 +1013,90 @@ extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const flo
             *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
             (unsigned long long *)n_fallback, fb_list);
     SEGB_LAUNCH_CHECK();
-    return launch_refine_full(m, fb_list, n_fallback, best_val, best_k, st);
+    return 0;
+}
+
+extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_max,
+                               int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
+                               void *stream) {
+    const int rc = refine_rows_stage(m, cand, x_err, w_max, n_emb, work, best_val, best_k, n_fallback, stream);
+    if (rc) return rc;
+    return launch_refine_full(m, (const int32_t *)work, n_fallback, best_val, best_k, (cudaStream_t)stream);
+}
+
+// ---- refine with the second-level tensor pass (segb_mma_refine2) --------------------------------------------
+// work layout: [fb_list (n_emb + 64) int32 | n_unres (256 B) | unres_list cap int32 | thr cap float |
+//               fb_tiles cap * KP * 2 | bitmap cap * (K_pad / 32) * 4], every part 256-byte aligned;
+// cap = undecided rows the second-level pass can take (the rest get the exhaustive scan).
+namespace {
+struct Work2 { int64_t off_unres_n, off_unres, off_thr, off_tiles, off_bitmap, total; };
+inline int64_t al256(int64_t v) { return (v + 255) / 256 * 256; }
+inline Work2 work2_layout(int64_t n_emb, int32_t K_max, int32_t D, int64_t cap) {
+    Work2 w;
+    w.off_unres_n = al256((n_emb + 64) * (int64_t)sizeof(int32_t));
+    w.off_unres = w.off_unres_n + 256;
+    w.off_thr = w.off_unres + al256(cap * 4);
+    w.off_tiles = w.off_thr + al256(cap * 4);
+    w.off_bitmap = w.off_tiles + al256(cap * (int64_t)kp_of(D) * 2);
+    w.total = w.off_bitmap + al256(cap * (int64_t)(k_pad(K_max) / 32) * 4);
+    return w;
+}
+inline int64_t default_cap(int64_t n_emb) {
+    int64_t cap = rows_pad(n_emb / 8);
+    if (cap < 16 * MT_ROWS) cap = 16 * MT_ROWS;
+    if (cap > rows_pad(n_emb)) cap = rows_pad(n_emb);
+    return cap;
+}
+}  // namespace
+
+extern "C" int64_t segb_mma_refine2_work_bytes(int64_t n_emb, int32_t K_max, int32_t D) {
+    return work2_layout(n_emb, K_max, D, default_cap(n_emb)).total;
+}
+
+extern "C" int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const void *w_tiles, const void *cand,
+                                const float *x_err, const float *w_max, int64_t n_emb, void *work, int64_t work_bytes,
+                                float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
+    SEGB_CHECK_ARG(m && x_tiles && w_tiles, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the largest cap (a multiple of 256 rows) whose layout fits the caller's buffer
+    int64_t cap = default_cap(n_emb);
+    while (cap > 0 && work2_layout(n_emb, m->K_max, m->D, cap).total > work_bytes) cap -= MT_ROWS;
+    const bool second = cap > 0 && row8_supported(m->D) && row8_steps_max(m->D) <= REFINE_MAX_STEPS;
+    if (!second) {
+        SEGB_CHECK_ARG(work_bytes >= segb_mma_refine_work_bytes(n_emb, m->K_max), "refine2: work buffer too small");
+        return segb_mma_refine(m, cand, x_err, w_max, n_emb, work, best_val, best_k, n_fallback, stream);
+    }
+    int rc = refine_rows_stage(m, cand, x_err, w_max, n_emb, work, best_val, best_k, n_fallback, stream);
+    if (rc) return rc;
+    const Work2 w = work2_layout(n_emb, m->K_max, m->D, cap);
+    uint8_t *wb = (uint8_t *)work;
+    const int32_t *fb_list = (const int32_t *)work;
+    unsigned long long *n_unres = (unsigned long long *)(wb + w.off_unres_n);
+    int32_t *unres_list = (int32_t *)(wb + w.off_unres);
+    float *thr = (float *)(wb + w.off_thr);
+    uint8_t *fb_tiles = wb + w.off_tiles;
+    uint32_t *bitmap = (uint32_t *)(wb + w.off_bitmap);
+    const unsigned long long *n_fb = (const unsigned long long *)n_fallback;
+    SEGB_CUDA(cudaMemsetAsync(n_unres, 0, sizeof(unsigned long long), st));
+    gather_undecided_kernel<<<148 * 8, 256, 0, st>>>((const uint8_t *)x_tiles, (const Cand *)cand, x_err, w_max, fb_list, n_fb,
+                                                     cap, m->D, kp_of(m->D), fb_tiles, thr);
+    SEGB_LAUNCH_CHECK();
+    FilterLaunch f;
+    f.x_tiles = fb_tiles; f.w_tiles = w_tiles; f.cand = nullptr; f.n_emb = cap;       // grid sized for cap; rows from the device
+    f.w_rows_pad = k_pad(m->K_max); f.KP = kp_of(m->D); f.D = m->D; f.x_max = w_max; f.w_max = w_max;
+    f.n_chunks = 1; f.tau_kind = TAU_KMEANS; f.tau_T = 0.f;
+    rc = launch_filter_impl(f, n_fb, cap, thr, bitmap, st);
+    if (rc) return rc;
+    const int n_words = k_pad(m->K_max) / 32;
+    if (row8_steps_max(m->D) <= 8)
+        refine_bitmap_kernel<8><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, cap, bitmap, n_words, best_val, best_k,
+                                                                    n_unres, unres_list);
+    else
+        refine_bitmap_kernel<REFINE_MAX_STEPS><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, cap, bitmap, n_words,
+                                                                                   best_val, best_k, n_unres, unres_list);
+    SEGB_LAUNCH_CHECK();
+    // rows beyond the pass's capacity, and rows it could not resolve: exhaustive exact scan
+    rc = launch_refine_full_from(m, fb_list, n_fallback, cap, best_val, best_k, st);
+    if (rc) return rc;
+    return launch_refine_full_from(m, unres_list, (const int64_t *)n_unres, 0, best_val, best_k, st);
 }

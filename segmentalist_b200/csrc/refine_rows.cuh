@@ -54,6 +54,36 @@ __device__ __forceinline__ void km_load_x8(const float *xr, const Row8Geom &q, f
     for (int i = 0; i < MAXS; ++i) xv[i] = (i < q.steps) ? xr2[i * 4] : make_float2(0.f, 0.f);
 }
 
+// exact score of ONE component for the row held in xv (result on all 8 lanes of the group)
+template <int MAXS>
+__device__ __forceinline__ float km_exact_one8(const float *means, int D, const float *xr, const float2 *xv, int k,
+                                               const Row8Geom &q) {
+    const float *mu = means + (size_t)k * D;
+    const float2 *mu2 = reinterpret_cast<const float2 *>(mu + q.lo_g + 2 * q.c);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXS; ++i) {
+        if (i < q.steps) {
+            const float2 mv = mu2[i * 4];
+            const float d0 = __fsub_rn(mv.x, xv[i].x), d1 = __fsub_rn(mv.y, xv[i].y);
+            const float p0 = __fmul_rn(d0, d0), p1 = __fmul_rn(d1, d1);
+            a0 = (i == 0) ? p0 : __fadd_rn(a0, p0);
+            a1 = (i == 0) ? p1 : __fadd_rn(a1, p1);
+        }
+    }
+    float acc = __fadd_rn(a0, a1);                                   // r[2c] + r[2c+1]
+    acc = __fadd_rn(acc, __shfl_xor_sync(q.gmask, acc, 1));
+    acc = __fadd_rn(acc, __shfl_xor_sync(q.gmask, acc, 2));
+    if (q.n8_g == 0) acc = 0.f;
+    for (int d = q.lo_g + q.n8_g; d < q.lo_g + q.n_g; ++d) {         // the block's n % 8 trailing terms
+        const float dl = __fsub_rn(mu[d], xr[d]);
+        acc = __fadd_rn(acc, __fmul_rn(dl, dl));
+    }
+    float tot = __shfl_sync(q.gmask, acc, q.gbase);
+    if (q.two_blocks) tot = __fadd_rn(tot, __shfl_sync(q.gmask, acc, q.gbase + 4));
+    return -tot;
+}
+
 template <int MAXS>
 __device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D, const float *xr, const float2 *xv,
                                               int i1, int i2, uint32_t masks, int code, const Row8Geom &q, float &bv,
@@ -69,30 +99,7 @@ __device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D,
             mk &= mk - 1;
             const int k = chunk * CHUNK + bit;
             if (k >= KM) continue;
-            const float *mu = means + (size_t)k * D;
-            const float2 *mu2 = reinterpret_cast<const float2 *>(mu + q.lo_g + 2 * q.c);
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int i = 0; i < MAXS; ++i) {
-                if (i < q.steps) {
-                    const float2 mv = mu2[i * 4];
-                    const float d0 = __fsub_rn(mv.x, xv[i].x), d1 = __fsub_rn(mv.y, xv[i].y);
-                    const float p0 = __fmul_rn(d0, d0), p1 = __fmul_rn(d1, d1);
-                    a0 = (i == 0) ? p0 : __fadd_rn(a0, p0);
-                    a1 = (i == 0) ? p1 : __fadd_rn(a1, p1);
-                }
-            }
-            float acc = __fadd_rn(a0, a1);                                   // r[2c] + r[2c+1]
-            acc = __fadd_rn(acc, __shfl_xor_sync(q.gmask, acc, 1));
-            acc = __fadd_rn(acc, __shfl_xor_sync(q.gmask, acc, 2));
-            if (q.n8_g == 0) acc = 0.f;
-            for (int d = q.lo_g + q.n8_g; d < q.lo_g + q.n_g; ++d) {         // the block's n % 8 trailing terms
-                const float dl = __fsub_rn(mu[d], xr[d]);
-                acc = __fadd_rn(acc, __fmul_rn(dl, dl));
-            }
-            float tot = __shfl_sync(q.gmask, acc, q.gbase);
-            if (q.two_blocks) tot = __fadd_rn(tot, __shfl_sync(q.gmask, acc, q.gbase + 4));
-            const float v = -tot;
+            const float v = km_exact_one8<MAXS>(means, D, xr, xv, k, q);
             if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; }
         }
     }

@@ -530,6 +530,46 @@ def test_mma_scorer_bit_exact_vs_simt(sb, K_max, n_emb, K_true, noise, fused):
     npt.assert_array_equal(bv, val.cpu().numpy()[ids])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("small_work", [False, True])
+def test_mma_scorer_near_duplicate_components(sb, small_work):
+    """A diffuse model: 12 generating clusters spread over 640 components, so every row has ~50 near-duplicate
+    candidates scattered over > 3 chunks and the top-3 filter records cannot decide it.  The second-level
+    tensor pass (compact image of the undecided rows, bitmap epilogue, exact re-score of the flagged
+    components: segb_mma_refine2) must give the same bits as the exact SIMT scorer; with a work buffer that
+    only fits 4096 second-level rows the remainder takes the exhaustive scan (also the same bits)."""
+    from segmentalist_b200 import _lib, synth
+    from segmentalist_b200.batch import MmaScorer
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    rng = np.random.RandomState(4242)
+    n_emb, K_max, K_true = 60000, 640, 12
+    centres = synth.cluster_centres(K_true, 130, rng)
+    z = rng.randint(0, K_true, n_emb)
+    X = synth._unit_rows(centres[z] + 0.05 * rng.standard_normal((n_emb, 130)).astype(np.float32))
+    # component k holds tokens of cluster k % K_true only: near-duplicates sit K_true apart, i.e. in different chunks
+    assign = -np.ones(n_emb, dtype=np.int64)
+    half = n_emb // 2
+    assign[:half] = z[:half] + K_true * (np.arange(half) % (K_max // K_true))
+    np.random.seed(1)
+    comps = KMeansComponents(X, assign, K_max)
+    val_e, arg_e = comps.best(None)
+    mma = MmaScorer(comps, fused=False)
+    if small_work:
+        lib = _lib.lib()
+        full = lib.segb_mma_refine2_work_bytes(n_emb, K_max, 130)
+        base = lib.segb_mma_refine_work_bytes(n_emb, K_max)
+        per_row = (full - base) // (16 * 256 if n_emb // 8 < 16 * 256 else (n_emb // 8 + 255) // 256 * 256)
+        mma.work = torch.empty(base + 1024 + per_row * 4096 + 2048, dtype=torch.uint8, device="cuda")
+    val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
+    arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
+    mma.score(val, arg)
+    torch.cuda.synchronize()
+    n_fb = int(mma.n_fallback.item())
+    assert n_fb > 8192, "the case must exercise the second-level pass (%d undecided rows)" % n_fb
+    npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
+    npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
+
+
 def test_frozen_fit_equals_reference_kmeans_fit(sb):
     """FrozenKMeansSweep.fit (sharded hard-assignment E-step + all-reduce M-step) == the reference's
     KMeans.fit(n, consider_unassigned=False) (kmeans.py:97-173) applied to the segmenter's tokens."""

@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """Turn ncu CSV exports (launch list + `--page raw` of a `--set full` capture) into the markdown
-summaries kept under profiles/.   usage: summarize_ncu.py TITLE launches.csv raw.csv [raw2.csv ...]"""
+summaries kept under profiles/.   usage: summarize_ncu.py [--traffic-json OUT.json] TITLE launches.csv raw.csv [raw2.csv ...]
+
+--traffic-json also writes {short kernel name: {"bytes_per_launch": dram read + write of the first captured
+launch, "duration_ms", "source": raw csv + kernel}} -- the file bench.py's roofline `traffic` keys cite."""
 import csv
+import json
+import os
+import re
 import sys
 from collections import OrderedDict
 
@@ -58,7 +64,46 @@ def raw_tables(path):
     return "\n".join(out)
 
 
+def _to_bytes(v, unit):
+    return float(v.replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+
+
+def _to_ms(v, unit):
+    return float(v.replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3,
+                                         "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3}[unit]
+
+
+def traffic_json(raws):
+    out = {}
+    for path in raws:
+        rows = list(csv.reader(open(path, errors="replace")))
+        hdr, units = rows[0], rows[1]
+        ki = hdr.index("Kernel Name")
+        ir, iw, it = (hdr.index(m) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"))
+        for r in rows[2:]:
+            short = re.sub(r"^void\s+", "", r[ki])
+            short = re.split(r"[<(]", short)[0].split("::")[-1]
+            if short in out and out[short]["_file"] == path:
+                continue
+            if short in out:                    # same kernel captured by another command: key it by file
+                short = "%s@%s" % (short, os.path.basename(path))
+                if short in out:
+                    continue
+            out[short] = {"bytes_per_launch": _to_bytes(r[ir], units[ir]) + _to_bytes(r[iw], units[iw]),
+                          "dram_read_bytes": _to_bytes(r[ir], units[ir]), "dram_write_bytes": _to_bytes(r[iw], units[iw]),
+                          "duration_ms_under_ncu": _to_ms(r[it], units[it]), "_file": path,
+                          "source": "ncu --set full --clock-control none, first captured launch of `%s` (%s)" % (
+                              r[ki][:80], os.path.basename(path))}
+    for v in out.values():
+        del v["_file"]
+    return out
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "--traffic-json":
+        tj = sys.argv[2]
+        del sys.argv[1:3]
+        json.dump(traffic_json(sys.argv[3:]), open(tj, "w"), indent=1)
     title, launches, raws = sys.argv[1], sys.argv[2], sys.argv[3:]
     print("# %s\n" % title)
     print("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`), share of device time\n")
