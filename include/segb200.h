@@ -505,6 +505,13 @@ int segb_fixedvar_log_marg_k(const segb_fixedvar *m, const int64_t *order, const
 int segb_kmeans_sum_neg_sqrd_norm_k(const segb_kmeans *m, const int64_t *order, const int64_t *seg_off,
                                     double *out_k, void *stream);
 
+/* GaussianComponentsDiag.log_marg_k (gaussian_components_diag.py:271-288) for every component, from the
+ * device-resident sufficient statistics (no member gathering: the closed form needs only counts,
+ * m_N_numerators and S_N_partials); the two np.log(..).sum() in NumPy's pairwise order.
+ * out_k [K_max]: log_marg_k(k) for k < K, 0 above; log_marg() (:290-301) is their sum in component
+ * order (host).  m->model must be SEGB_MODEL_DIAG.                                               */
+int segb_diag_log_marg_k(const segb_fixedvar *m, double *out_k, void *stream);
+
 /* ------------------------------------------------------------------ ingestion (host) */
 
 /* The random boundary initialisation of Utterances.__init__ (utterances.py:136-157) for all utterances in

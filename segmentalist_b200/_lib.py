@@ -145,6 +145,7 @@ _PROTOS = {
     "segb_fixedvar_log_marg_k_work_bytes": (c_i64, [c_i32, c_i32]),
     "segb_fixedvar_log_marg_k": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "segb_kmeans_sum_neg_sqrd_norm_k": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_vp]),
+    "segb_diag_log_marg_k": (ctypes.c_int, [ctypes.POINTER(FixedVar), c_vp, c_vp]),
 }
 
 EXPORTS = sorted(_PROTOS)

@@ -81,9 +81,46 @@ __global__ void km_objective_kernel(segb_kmeans m, const int64_t *order, const i
     out_k[k] = -s;
 }
 
+// GaussianComponentsDiag.log_marg_k (gaussian_components_diag.py:271-288) from the device tables: thread per
+// component, the two np.log(..).sum() in NumPy's pairwise order, separately rounded elementwise operations.
+// Tables are [D, K_max]: mu_N_numT = m_N_numerators^T, prec_NT = S_N_partials^T; precision_0 = S_0.
+__global__ void diag_log_marg_k_kernel(segb_fixedvar m, double *out_k) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m.K_max) return;
+    if (k >= *m.K) { out_k[k] = 0.0; return; }
+    const int D = m.D, KM = m.K_max;
+    const double n = (double)m.counts[k];
+    const double k_N = __dadd_rn(m.k_0, n);
+    const double v_0 = (double)m.v_0, v_N = __dadd_rn(v_0, n);
+    const double log_pi = log(CUDART_PI);
+    const double sum_log_S0 = pairwise_sum<double>([&](int d) { return log(m.precision_0[d]); }, D);
+    const double sum_log_SN = pairwise_sum<double>([&](int d) {
+        const double m_N = __ddiv_rn(m.mu_N_numT[(size_t)d * KM + k], k_N);
+        const double S_N = __dsub_rn(m.prec_NT[(size_t)d * KM + k], __dmul_rn(k_N, __dmul_rn(m_N, m_N)));
+        return log(S_N);
+    }, D);
+    const double Dd = (double)D;
+    // - n*D/2*log_pi + D/2*log(k_0) - D/2*log(k_N) + v_0/2*sum(log S_0) - v_N/2*sum(log S_N) + D*(gammaln(v_N/2) - gammaln(v_0/2))
+    double r = -__dmul_rn(__ddiv_rn(__dmul_rn(n, Dd), 2.0), log_pi);
+    r = __dadd_rn(r, __dmul_rn(__ddiv_rn(Dd, 2.0), log(m.k_0)));
+    r = __dsub_rn(r, __dmul_rn(__ddiv_rn(Dd, 2.0), log(k_N)));
+    r = __dadd_rn(r, __dmul_rn(__ddiv_rn(v_0, 2.0), sum_log_S0));
+    r = __dsub_rn(r, __dmul_rn(__ddiv_rn(v_N, 2.0), sum_log_SN));
+    r = __dadd_rn(r, __dmul_rn(Dd, __dsub_rn(lgamma(__ddiv_rn(v_N, 2.0)), lgamma(__ddiv_rn(v_0, 2.0)))));
+    out_k[k] = r;
+}
+
 }  // namespace segb
 
 using namespace segb;
+
+extern "C" int segb_diag_log_marg_k(const segb_fixedvar *m, double *out_k, void *stream) {
+    SEGB_CHECK_ARG(m && out_k, "null pointer");
+    SEGB_CHECK_ARG(m->model == SEGB_MODEL_DIAG, "segb_diag_log_marg_k: diagonal-covariance components only");
+    diag_log_marg_k_kernel<<<(m->K_max + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*m, out_k);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int64_t segb_fixedvar_log_marg_k_work_bytes(int32_t K_max, int32_t D) { return (int64_t)2 * K_max * D * 8; }
 

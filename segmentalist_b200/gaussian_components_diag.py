@@ -96,25 +96,19 @@ class GaussianComponentsDiag(GaussianComponentsFixedVar):
         return float(self.D * (gammaln((v + 1) / 2.) - gammaln(v / 2.) - 0.5 * math.log(v) - 0.5 * self._cached_log_pi)
                      - 0.5 * np.log(var).sum() - (v + 1.) / 2. * np.log(1. + 1. / v * np.square(delta) / var).sum())
 
-    # ---- diagnostics: closed forms from the mirrored sufficient statistics (O(K D))
-    def log_marg_k(self, k, _stats=None):
+    # ---- diagnostics: closed form over the device-resident sufficient statistics (segb_diag_log_marg_k)
+    def _log_marg_all_k(self):
+        out = torch.empty(self.K_max, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().segb_diag_log_marg_k(self.struct(), _lib.ptr(out), _lib.stream_ptr()))
+        return out.cpu().numpy()
+
+    def log_marg_k(self, k):
         """:270-288."""
-        num, part, counts = _stats if _stats is not None else (self.m_N_numerators, self.S_N_partials, self.counts)
-        pr = self.prior
-        k_N = pr.k_0 + counts[k]
-        v_N = pr.v_0 + counts[k]
-        m_N = num[k] / k_N
-        S_N = part[k] - k_N * np.square(m_N)
-        return (- counts[k] * self.D / 2. * self._cached_log_pi
-                + self.D / 2. * math.log(pr.k_0) - self.D / 2. * math.log(k_N)
-                + pr.v_0 / 2. * np.log(self.S_0).sum()
-                - v_N / 2. * np.log(S_N).sum()
-                + self.D * (gammaln(v_N / 2.) - gammaln(pr.v_0 / 2.)))
+        return float(self._log_marg_all_k()[k])
 
     def log_marg(self):
-        """:290-301."""
-        stats = (self.m_N_numerators, self.S_N_partials, self.counts)
-        total = 0.
-        for k in range(self.K):
-            total += self.log_marg_k(k, stats)
-        return total
+        """:290-301: the per-component values are added in component order like the reference's loop."""
+        K = self.K
+        if K == 0:
+            return 0.
+        return float(np.cumsum(self._log_marg_all_k()[:K])[-1])

@@ -380,6 +380,11 @@ def test_diag_components_golden(sb):
     npt.assert_allclose(np.array([c.log_post_pred(int(i)) for i in probe]), z["post_pred0"], rtol=1e-10)
     npt.assert_allclose(np.array([c.log_prior(int(i)) for i in probe]), z["prior0"], rtol=1e-10)
     npt.assert_allclose(c.log_marg(), float(z["log_marg0"]), rtol=1e-10)
+    # per-component values of the device kernel (segb_diag_log_marg_k) vs the oracle's closed form
+    oc = so.DiagComponents(z["X"], so.NIW(m_0=z["m_0"], k_0=float(z["k_0"]), v_0=int(z["v_0"]), S_0=z["S_0"]),
+                           z["init_assignments"].copy(), K_max=9)
+    for k in range(c.K):
+        npt.assert_allclose(c.log_marg_k(k), oc.log_marg_k(k), rtol=1e-12)
     assign = z["init_assignments"]
     c.del_item(0)
     c.del_item(1)                                      # deletes the last component
