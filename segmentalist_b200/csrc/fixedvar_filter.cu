@@ -508,7 +508,7 @@ extern "C" int segb_fvf_filter(const void *x_tiles, const void *w_tiles, int64_t
     SEGB_CHECK_ARG(T > 0.f, "threshold");
     FilterLaunch f;
     f.x_tiles = x_tiles; f.w_tiles = w_tiles; f.cand = cand; f.n_emb = n_emb;
-    f.w_rows_pad = w_rows_pad(K_max); f.KP = kp_of(D, aniso ? 1 : 0); f.n_chunks = nch_of(aniso ? 1 : 0); f.D = D;
+    f.w_rows_pad = w_rows_pad(K_max); f.w_rows = K_max + 1; f.KP = kp_of(D, aniso ? 1 : 0); f.n_chunks = nch_of(aniso ? 1 : 0); f.D = D;
     f.x_max = x_max; f.w_max = w_max; f.tau_kind = TAU_LSE; f.tau_T = T;
     return launch_filter(f, (cudaStream_t)stream);
 }

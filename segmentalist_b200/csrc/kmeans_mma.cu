@@ -60,8 +60,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46);
 }
 // kind::f16 instruction descriptor: A,B = fp16 K-major, D = fp32, M = 128, N = 128
-__device__ __forceinline__ uint32_t make_idesc() {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NT_COLS >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n_cols = NT_COLS) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- filter GEMM
@@ -71,6 +71,9 @@ struct FilterParams {
     Cand *cand;
     int64_t n_emb;
     int32_t n_mtiles, n_ntiles, n_ksteps, n_abuf;     // n_ksteps: K=16 steps per inner-dimension CHUNK
+    int32_t n_last_cols;           // MMA width of the LAST accumulator tile (multiple of 16): padding components beyond it
+                                   // are never multiplied, and the epilogue skips their (stale) TMEM columns
+    int32_t n_chunks_valid;        // 16-component chunks that were computed = (n_ntiles - 1) * 8 + n_last_cols / 16
     uint32_t tile_bytes;                              // bytes of one 128-row tile image of one chunk
     const float *x_max, *w_max;    // corpus-wide (max ex, max nx); model-wide maxima (k-means: e_mu, n_mu; FBGMM: eB, nB, |A|, p/2)
     int32_t D;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
         // chosen with elect.sync (see elect_one()), both barriers of a tile are polled together, and
         // there is ONE commit per tile.
         if (elect_one()) {
-            const uint32_t idesc = make_idesc();
+            const uint32_t idesc_full = make_idesc(), idesc_last = make_idesc(p.n_last_cols);
             constexpr uint32_t KSTEP = KSTEP_BYTES >> 4;              // descriptor units per K=16 step
             const uint32_t a_lo_base = make_desc_lo(smem_u32(sA), TILE_ROWS);
             const uint32_t b_lo_base = make_desc_lo(smem_u32(sB), TILE_ROWS);
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     const uint32_t buf = n_use & 1, use = n_use >> 1;
                     const uint32_t d0 = tmem_base + (buf * 2) * NT_COLS, d1 = d0 + NT_COLS;
+                    const uint32_t idesc = (nt == p.n_ntiles - 1) ? idesc_last : idesc_full;
                     if (NCH == 1) {
                         mbar_wait2(BAR(B_FULL + buf), use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
                         tc_fence_after();
@@ -299,7 +303,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                         w0 = __funnelshift_l(__float_as_uint(v[j] - thr), w0, 1);
                         w1 = __funnelshift_l(__float_as_uint(v[32 + j] - thr), w1, 1);
                     }
-                    out[2 * nt] = make_uint2(~w0, ~w1);
+                    // columns past the last tile's MMA width hold an earlier tile's scores
+                    const int n_cols = (p.n_chunks_valid - (nt * (NT_COLS / CHUNK) + (part * COLS) / CHUNK)) * CHUNK;
+                    const uint32_t k0 = n_cols >= 32 ? 0xffffffffu : (n_cols <= 0 ? 0u : ((1u << n_cols) - 1u));
+                    const uint32_t k1 = n_cols >= 64 ? 0xffffffffu : (n_cols <= 32 ? 0u : ((1u << (n_cols - 32)) - 1u));
+                    out[2 * nt] = make_uint2(~w0 & k0, ~w1 & k1);
                 }
             }
         } else
@@ -316,13 +324,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+                const int cid0 = nt * (NT_COLS / CHUNK) + (part * COLS) / CHUNK;
+                const int n_c = p.n_chunks_valid - cid0;             // < 4 only in the last tile
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float cm = v[c * 16];
+                    if (c < n_c) {
+                        float cm = v[c * 16];
 #pragma unroll
-                    for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
-                    top3_insert(&v[c * 16], cm, nt * (NT_COLS / CHUNK) + (part * COLS) / CHUNK + c, tau_c,
-                                m1, m2, m3, i1, i2, k1, k2);
+                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                        top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                    }
                 }
             }
             const int r_local = h * TILE_ROWS + q * 32 + lane;
@@ -906,6 +917,12 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
     p.tau_kind = f.tau_kind; p.tau_T = f.tau_T;
     p.n_mtiles = (int32_t)(rows_pad(f.n_emb) / MT_ROWS);
     p.n_ntiles = f.w_rows_pad / NT_COLS;
+    {
+        int last = f.w_rows > 0 ? f.w_rows - (p.n_ntiles - 1) * NT_COLS : NT_COLS;
+        last = (last + 15) / 16 * 16;
+        p.n_last_cols = last < 16 ? 16 : (last > NT_COLS ? NT_COLS : last);
+        p.n_chunks_valid = (p.n_ntiles - 1) * (NT_COLS / CHUNK) + p.n_last_cols / CHUNK;
+    }
     p.n_ksteps = f.KP / 16;
     p.tile_bytes = (uint32_t)((int64_t)TILE_ROWS * f.KP * 2);
     const int nch = f.n_chunks;
@@ -942,7 +959,7 @@ extern "C" int segb_mma_filter(const void *x_tiles, const void *w_tiles, int64_t
     SEGB_CHECK_ARG(x_tiles && w_tiles && cand && x_max && w_max && n_emb > 0 && K_max > 0, "null pointer");
     FilterLaunch f;
     f.x_tiles = x_tiles; f.w_tiles = w_tiles; f.cand = cand; f.n_emb = n_emb;
-    f.w_rows_pad = k_pad(K_max); f.KP = kp_of(D); f.D = D; f.x_max = x_max; f.w_max = w_max;
+    f.w_rows_pad = k_pad(K_max); f.w_rows = K_max; f.KP = kp_of(D); f.D = D; f.x_max = x_max; f.w_max = w_max;
     f.n_chunks = 1; f.tau_kind = TAU_KMEANS; f.tau_T = 0.f;
     return launch_filter(f, (cudaStream_t)stream);
 }
@@ -1083,7 +1100,7 @@ extern "C" int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const
     SEGB_LAUNCH_CHECK();
     FilterLaunch f;
     f.x_tiles = fb_tiles; f.w_tiles = w_tiles; f.cand = nullptr; f.n_emb = cap;       // grid sized for cap; rows from the device
-    f.w_rows_pad = k_pad(m->K_max); f.KP = kp_of(m->D); f.D = m->D; f.x_max = w_max; f.w_max = w_max;
+    f.w_rows_pad = k_pad(m->K_max); f.w_rows = m->K_max; f.KP = kp_of(m->D); f.D = m->D; f.x_max = w_max; f.w_max = w_max;
     f.n_chunks = 1; f.tau_kind = TAU_KMEANS; f.tau_T = 0.f;
     rc = launch_filter_impl(f, n_fb, cap, thr, bitmap, st);
     if (rc) return rc;

@@ -242,6 +242,8 @@ struct FilterLaunch {
     void *cand;                        // [n_emb] Cand records out
     int64_t n_emb;
     int32_t w_rows_pad;                // multiple of NT_COLS
+    int32_t w_rows = 0;                // rows that are not padding (0: unknown, all of w_rows_pad): the last
+                                       // accumulator tile is computed only as wide as they reach
     int32_t KP;                        // padded inner dimension of ONE chunk (multiple of 16)
     int32_t n_chunks;                  // 1, or 2: every tile is two consecutive chunk images of KP columns
     int32_t D;
