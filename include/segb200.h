@@ -43,6 +43,10 @@ extern "C" {
 #define SEGB_DP_FFBS           0  /* unigram_acoustic_wordseg.py:653-756 forward_backward */
 #define SEGB_DP_VITERBI_GMM    1  /* unigram_acoustic_wordseg.py:759-864 forward_backward_viterbi */
 #define SEGB_DP_VITERBI_KMEANS 2  /* kmeans_acoustic_wordseg.py:449-555 forward_backward_kmeans_viterbi */
+/* OR-ed into `mode`: the caller vouches that `scores` hold no NaN and no +inf (-inf = unusable segment is fine),
+ * e.g. because they come from segb_kmeans_band_scores over finite embeddings.  The batched k-means Viterbi
+ * kernel then skips its per-candidate NaN compares (status never becomes SEGB_DP_NAN); other paths ignore it. */
+#define SEGB_DP_SCORES_FINITE  0x100
 
 const char *segb_last_error(void);
 int segb_version(void);

@@ -18,6 +18,7 @@ _LIB = None
 c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
 DP_FFBS, DP_VITERBI_GMM, DP_VITERBI_KMEANS = 0, 1, 2
+DP_SCORES_FINITE = 0x100        # OR-ed into the mode: scores hold no NaN / +inf (include/segb200.h)
 DP_OK, DP_INFEASIBLE, DP_EMPTY_SLICE, DP_NAN = 0, 1, 2, 3
 E_UNSUPPORTED = -2
 

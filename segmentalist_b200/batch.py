@@ -198,6 +198,10 @@ class FrozenKMeansSweep(object):
         self.log_prob_h = torch.zeros(corpus.n_utt, dtype=torch.float64).pin_memory()
         self.side = torch.cuda.Stream()
         self.last_fallback = 0
+        # finite embeddings (a finite sum has no NaN / inf term) give finite or -inf band scores, so the DP may skip
+        # its NaN compares (SEGB_DP_SCORES_FINITE); embeddings streamed from the host are not vouched for
+        self.scores_finite = bool(torch.isfinite(c._X.sum(dtype=torch.float64)).item()) and np.isfinite(self.wip)
+        self._streamed = False
         self.mma = MmaScorer(c, fused=fused) if scorer == "mma" else None
         self.K_host = None                     # host copy of the active-component count (no .item() per sweep)
         # add_item's clamp and clean_components as device kernels (csrc/frozen.cu): no host logic per sweep
@@ -209,6 +213,7 @@ class FrozenKMeansSweep(object):
     def score(self, X_host=None):
         lib, c, sp = _lib.lib(), self.c, _lib.stream_ptr()
         m = c.struct()
+        self._streamed = X_host is not None
         if X_host is not None:
             assert self.scorer == "mma", "streaming from host memory uses the tensor-core scorer"
             self.mma.score_streamed(X_host, self.best_val, self.best_k)
@@ -222,7 +227,8 @@ class FrozenKMeansSweep(object):
         cs = cp.struct()
         _lib.check(lib.segb_kmeans_band_scores(c.struct(), cs, 0, cp.n_pos, _lib.ptr(self.best_val), self.wip,
                                                _lib.ptr(self.scores), sp))
-        _lib.check(lib.segb_dp_banded(cs, 0, cp.n_utt, _lib.ptr(self.scores), _lib.DP_VITERBI_KMEANS, 0.0, 1.0,
+        mode = _lib.DP_VITERBI_KMEANS | (_lib.DP_SCORES_FINITE if self.scores_finite and not self._streamed else 0)
+        _lib.check(lib.segb_dp_banded(cs, 0, cp.n_utt, _lib.ptr(self.scores), mode, 0.0, 1.0,
                                       None, None, _lib.ptr(cp.bounds), _lib.ptr(self.log_prob), None, None,
                                       _lib.ptr(self.status), sp))
 

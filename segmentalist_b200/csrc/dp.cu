@@ -388,34 +388,40 @@ __device__ __forceinline__ void dp_load_row(const double *row_ptr, double (&row)
 }
 
 // tau % SB == J; FIRST: tau == 0 (every candidate opens its position).
-template <int MODE, int SB, int J, bool FIRST>
+// NANCHK = false: the caller vouches for scores without NaN / +inf (SEGB_DP_SCORES_FINITE), so no candidate
+// can be NaN: the per-candidate NaN compares go (3 of the step's 10 DSETPs, the FP64 pipe's slowest instruction),
+// and the -inf test of the new alpha becomes an integer compare of its high word.
+template <int MODE, int SB, int J, bool FIRST, bool NANCHK>
 __device__ __forceinline__ void dp_skew_step(DpSkewState<SB> &st, const double *sc, int tau, int Nf, bool &bad,
-                                             uint8_t *bp, double *al) {
+                                             bool &any_dead, uint8_t *bp, double *al) {
 #pragma unroll
     for (int l = 1; l <= SB; ++l) {
         constexpr int dummy = 0; (void)dummy;
         const int r = (J + l) % SB;
         const double c = st.R[r][l - 1] + st.a;
-        const bool nanc = (c != c);
-        if (FIRST || l == SB) { st.m[r] = c; st.ix[r] = l - 1; st.nf[r] = nanc; }
+        const bool nanc = NANCHK ? (c != c) : false;
+        if (FIRST || l == SB) { st.m[r] = c; st.ix[r] = l - 1; if (NANCHK) st.nf[r] = nanc; }
         else {
             const bool keep = st.m[r] > c;
             st.m[r] = keep ? st.m[r] : c;
             st.ix[r] = keep ? st.ix[r] : l - 1;
-            st.nf[r] |= nanc;
+            if (NANCHK) st.nf[r] |= nanc;
         }
     }
     constexpr int r1 = (J + 1) % SB;
     const double a_new = st.m[r1];
-    bad |= (st.nf[r1] && (tau + 1 <= Nf));
-    if (MODE == SEGB_DP_VITERBI_KMEANS) bp[(tau + 1) * 32] = (a_new == neg_inf()) ? (uint8_t)0xff : (uint8_t)st.ix[r1];
+    if (NANCHK) bad |= (st.nf[r1] && (tau + 1 <= Nf));
+    const bool dead = NANCHK ? (a_new == neg_inf()) : (__double2hiint(a_new) == (int)0xFFF00000);
+    any_dead |= dead;                    // some window was all -inf: the backward pass needs its walk-left branch
+    if (MODE == SEGB_DP_VITERBI_KMEANS) bp[(tau + 1) * 32] = dead ? (uint8_t)0xff : (uint8_t)st.ix[r1];
     else al[(tau + 1) * 32] = a_new;
     st.a = a_new;
     dp_load_row<SB>(sc + (tau + SB) * SB, st.R[r1]);          // row of position tau + 1 + SB
 }
 
-template <int MODE, int SB>
-__device__ __forceinline__ void dp_forward_skewed(const double *sc, int Nf, int Nf_w, bool &bad, uint8_t *bp, double *al) {
+template <int MODE, int SB, bool NANCHK>
+__device__ __forceinline__ void dp_forward_skewed(const double *sc, int Nf, int Nf_w, bool &bad, bool &any_dead, uint8_t *bp,
+                                                  double *al) {
     DpSkewState<SB> st;
     static_for_while<1, SB + 1>([&](auto tc) {
         constexpr int T = decltype(tc)::value;
@@ -424,30 +430,30 @@ __device__ __forceinline__ void dp_forward_skewed(const double *sc, int Nf, int 
     });
     st.a = 0.0;
     if (Nf_w < 1) return;
-    dp_skew_step<MODE, SB, 0, true>(st, sc, 0, Nf, bad, bp, al);
+    dp_skew_step<MODE, SB, 0, true, NANCHK>(st, sc, 0, Nf, bad, any_dead, bp, al);
     static_for_while<1, SB>([&](auto jc) {
         constexpr int J = decltype(jc)::value;
         if (J >= Nf_w) return false;
-        dp_skew_step<MODE, SB, J, false>(st, sc, J, Nf, bad, bp, al);
+        dp_skew_step<MODE, SB, J, false, NANCHK>(st, sc, J, Nf, bad, any_dead, bp, al);
         return true;
     });
     int tau0 = SB;
     for (; tau0 + SB <= Nf_w; tau0 += SB) {                   // SB steps, straight-line
         static_for_while<0, SB>([&](auto jc) {
             constexpr int J = decltype(jc)::value;
-            dp_skew_step<MODE, SB, J, false>(st, sc, tau0 + J, Nf, bad, bp, al);
+            dp_skew_step<MODE, SB, J, false, NANCHK>(st, sc, tau0 + J, Nf, bad, any_dead, bp, al);
             return true;
         });
     }
     static_for_while<0, SB>([&](auto jc) {
         constexpr int J = decltype(jc)::value;
         if (tau0 + J >= Nf_w) return false;
-        dp_skew_step<MODE, SB, J, false>(st, sc, tau0 + J, Nf, bad, bp, al);
+        dp_skew_step<MODE, SB, J, false, NANCHK>(st, sc, tau0 + J, Nf, bad, any_dead, bp, al);
         return true;
     });
 }
 
-template <int MODE, int SB>
+template <int MODE, int SB, bool NANCHK = true>
 __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
     extern __shared__ __align__(128) unsigned char dp_sm[];
     constexpr bool AL_SMEM = (MODE != SEGB_DP_VITERBI_KMEANS);
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
         const int phase = (int)((uintptr_t)bo & 3);
         uint8_t *bs0 = bo_s + phase;
         for (int wd = lane; wd * 4 < phase + n_bytes; wd += 32) reinterpret_cast<uint32_t *>(bo_s)[wd] = 0u;
-        bool bad = false;
+        bool bad = false, any_dead = false;
         if (AL_SMEM) al[0] = 0.0;
         mma::mbar_wait(bar, parity);
         parity ^= 1;
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
                 });
             }
         } else {
-            dp_forward_skewed<MODE, SB>(sc, Nf, Nf_w, bad, bp, al);
+            dp_forward_skewed<MODE, SB, NANCHK>(sc, Nf, Nf_w, bad, any_dead, bp, al);
         }
 
         int status = bad ? SEGB_DP_NAN : SEGB_DP_OK, used = 0;
@@ -556,7 +562,18 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
                 bs[N - 1] = 1;
                 int t = N;
                 double pend = 0.0;
-                if (status == SEGB_DP_OK) {
+                if (status == SEGB_DP_OK && !any_dead) {
+                    // every window had a finite candidate: no walk-left branch in the chase
+                    while (true) {
+                        const int b = bp[t * 32];
+                        total += pend;
+                        pend = sc[(t - 1) * SB + b];
+                        t = t - b - 1;
+                        if (t <= 0) break;
+                        bs[t - 1] = 1;
+                    }
+                    total += pend;
+                } else if (status == SEGB_DP_OK) {
                     while (true) {
                         int b = bp[t * 32];
                         total += pend;
@@ -619,6 +636,8 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
               double log_p_continue, double anneal_temp, const double *uniforms, int64_t *u_counter,
               uint8_t *bounds_out, double *log_prob, double *alphas, int32_t *n_draws, int32_t *status,
               cudaStream_t stream, int scores_local = 0) {
+    const bool scores_finite = (mode & SEGB_DP_SCORES_FINITE) != 0;
+    mode &= ~SEGB_DP_SCORES_FINITE;
     DpParams p;
     p.scores_local = scores_local;
     p.group = 32;
@@ -664,6 +683,8 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
             };
             auto by_band = [&](auto mc) -> int {
                 constexpr int M = decltype(mc)::value;
+                if (M == SEGB_DP_VITERBI_KMEANS && scores_finite && c->S == 6)      // the frozen k-means sweep's shape
+                    return launch(dp_staged_kernel<SEGB_DP_VITERBI_KMEANS, 6, false>);
                 switch (c->S) {
                     case 2: return launch(dp_staged_kernel<M, 2>);
                     case 4: return launch(dp_staged_kernel<M, 4>);
@@ -709,10 +730,10 @@ extern "C" int segb_dp_banded(const segb_corpus *c, int32_t utt_first, int32_t n
                               double *log_prob, double *alphas, int32_t *n_draws, int32_t *status,
                               void *stream) {
     SEGB_CHECK_ARG(c && scores && bounds_out && log_prob && status, "null pointer");
-    SEGB_CHECK_ARG(mode >= 0 && mode <= 2, "mode");
+    SEGB_CHECK_ARG((mode & ~SEGB_DP_SCORES_FINITE) >= 0 && (mode & ~SEGB_DP_SCORES_FINITE) <= 2, "mode");
     SEGB_CHECK_ARG(n_utt >= 0 && utt_first >= 0 && utt_first + n_utt <= c->n_utt, "utterance range");
     SEGB_CHECK_ARG(c->S >= 1, "band width");
-    SEGB_CHECK_ARG(mode != SEGB_DP_FFBS || uniforms, "FFBS needs uniforms");
+    SEGB_CHECK_ARG((mode & ~SEGB_DP_SCORES_FINITE) != SEGB_DP_FFBS || uniforms, "FFBS needs uniforms");
     SEGB_CHECK_ARG(!u_counter || n_utt <= 1, "u_counter implies a single utterance");
     if (n_utt == 0) return 0;
     return segb::launch_dp(c, utt_first, n_utt, scores, mode, log_p_continue, anneal_temp, uniforms,

@@ -27,7 +27,7 @@ def sb():
     return pkg
 
 
-def _run_dp_batch(cases, S_band, n_min, n_max, mode, temp):
+def _run_dp_batch(cases, S_band, n_min, n_max, mode, temp, want_alphas=True):
     """cases: list of dict(vec, N, u).  Returns per-case (status, log_prob, bounds, alphas, n_draws)."""
     from segmentalist_b200 import _lib
     from segmentalist_b200.utterances import DeviceCorpus, packed_to_band
@@ -47,7 +47,8 @@ def _run_dp_batch(cases, S_band, n_min, n_max, mode, temp):
     nd = torch.zeros(n, dtype=torch.int32, device="cuda")
     st = torch.zeros(n, dtype=torch.int32, device="cuda")
     _lib.check(_lib.lib().segb_dp_banded(corpus.struct(), 0, n, _lib.ptr(scores), mode, 0.0, float(temp),
-                                         _lib.ptr(uni_d), None, _lib.ptr(corpus.bounds), _lib.ptr(lp), _lib.ptr(al),
+                                         _lib.ptr(uni_d), None, _lib.ptr(corpus.bounds), _lib.ptr(lp),
+                                         _lib.ptr(al) if want_alphas else None,
                                          _lib.ptr(nd), _lib.ptr(st), _lib.stream_ptr()))
     b = corpus.bounds.cpu().numpy().astype(bool)
     al = al.cpu().numpy()
@@ -632,6 +633,42 @@ def test_mma_scorer_streamed_from_host(sb, fused):
     npt.assert_array_equal(val1.cpu().numpy(), val0.cpu().numpy())
     npt.assert_array_equal(comps._X.cpu().numpy(), X)
     assert int(mma.n_fallback.item()) == fb0
+
+
+@pytest.mark.parametrize("flag", [0, 0x100])
+@pytest.mark.parametrize("hole_choices", [(0.0,), (0.0, 0.05, 0.3), (0.6,)])
+def test_dp_staged_kmeans_viterbi_vs_oracle(sb, flag, hole_choices):
+    """The staged k-means Viterbi kernel as the frozen sweep launches it (no alphas requested; S = 6, N <= 26),
+    with and without SEGB_DP_SCORES_FINITE (no per-candidate NaN compares, integer -inf test, branch-free
+    pointer chase when no window was all -inf): boundaries, objective and status equal the oracle's
+    forward_backward_kmeans_viterbi on dense bands, bands with -inf holes (walk-left back-tracking) and bands so
+    sparse that some utterances are infeasible."""
+    rng = np.random.RandomState(900 + len(hole_choices) + int(100 * hole_choices[-1]))
+    S, cases = 6, []
+    for _ in range(3001):
+        N = int(rng.randint(1, 27))
+        vec = -np.inf * np.ones(N * (N + 1) // 2)
+        hole = rng.choice(hole_choices)
+        for t in range(1, N + 1):
+            for j in range(max(0, t - S), t):
+                if rng.rand() < hole:
+                    continue
+                vec[t * (t - 1) // 2 + j] = rng.randn() * 6 - 2
+        cases.append(dict(vec=vec, N=N, u=rng.rand(N + 1)))
+    res = _run_dp_batch(cases, S, 0, S, 2 | flag, 1.0, want_alphas=False)
+    n_ok = n_bad = 0
+    for c, (st, lp, b, al, nd) in zip(cases, res):
+        ost, olp, ob, oal, oused = so.dp_packed_c(c["vec"], c["N"], 0, S, 2, c["u"], 1.0)
+        assert st == ost, (st, ost, c["N"])
+        if ost != 0:
+            n_bad += 1
+            continue
+        n_ok += 1
+        assert np.array_equal(b, ob)
+        assert lp == olp                     # same summation order: bit-identical objective
+    assert n_ok > 300
+    if hole_choices == (0.6,):
+        assert n_bad > 50                    # infeasible utterances are reported, not mis-segmented
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
