@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--K", type=int, default=K_MAX)
     ap.add_argument("--cpu-sample", type=int, default=32, help="utterances timed by the CPU baseline leg")
     ap.add_argument("--scorer", default="mma", choices=["mma", "exact"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp8"],
+                    help="first-level filter GEMM of the k-means scorer: fp16 (kind::f16) or e4m3 (kind::f8f6f4) with the fp16 pass as second level")
     ap.add_argument("--fused", action="store_true", help="the fused score kernel (fp32 rows in, conversion + filter GEMM + refine in one launch) instead of pre-packed fp16 image + filter kernel + refine kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -1171,7 +1173,7 @@ def run_ours(args):
     # inactive slots winning tokens, undecided rows) is measured separately below (secondary_kmeans_diffuse)
     tok = corpus.tok_id[corpus.tok_id >= 0].long()
     comps._assign[tok] = Z[tok]
-    sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer, fused=bool(args.fused))
+    sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer, fused=bool(args.fused), precision=args.precision)
     sweep.init_means_from_assignments()
     sweep_fused = bool(sweep.mma is not None and sweep.mma.fused)
     x_gb = X.numel() * 4 / 1e9
@@ -1240,21 +1242,27 @@ def run_ours(args):
             peak_sus = float(peaks.get("bf16_tflops_sustained", 0.0)) or None
             kname = "score_fused_kernel" if fused else "kmeans_filter_kernel"
             tr = ncu_traffic(kname) if default_cfg else None
+            fp8 = bool(sweep.mma.fp8)
+            pk_tf, pk_src = peak_tf, peak_src
+            if fp8:       # e4m3 dense rate = 2 x the bf16 rate; MEASURED_PEAKS.json has no fp8 entry
+                pk_tf, pk_src, peak_sus = 2.0 * peak_tf, "2 x " + peak_src + " (e4m3 runs at twice the bf16 rate; no measured fp8 entry)", (2.0 * peak_sus if peak_sus else None)
             roofline = {"kernel": ("score_fused_kernel<kmeans> (fp32 rows -> fp16 operand tiles in shared memory, tcgen05 fp16 -> fp32 "
                                    "TMEM, top-3 epilogue, exact float32 refine of the survivors: the whole scoring step)" if fused
+                                   else "kmeans_filter_kernel<F8> (tcgen05 kind::f8f6f4 e4m3 -> fp32 TMEM, fused top-3 epilogue; first level of "
+                                        "the e4m3 -> fp16 -> exact cascade)" if fp8
                                    else "kmeans_filter_kernel (tcgen05 fp16 -> fp32 TMEM, fused top-3 epilogue)"),
-                        "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": ach / peak_tf,
+                        "bound": "tensor", "achieved": ach, "peak": pk_tf, "unit": "TFLOP/s",
+                        "frac": ach / pk_tf,
                         "traffic": tr["bytes_per_launch"] if tr else None,
                         "traffic_source": tr.get("source") if tr else None,
                         "algorithmic_bytes_per_launch": float(X.numel() * 4 + 8 * M) if fused else
                                                         float(sweep.mma.x_tiles.numel() + sweep.mma.cand.numel()),
-                        "peak_source": peak_src,
+                        "peak_source": pk_src,
                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
                         "timing": "kernel_ms = mean over the launches INSIDE the %d timed sweeps (CUDA events on the launching "
                                   "stream around the kernel); kernel_ms_back_to_back = 5 launches of the kernel alone with "
                                   "nothing between them (the power-capped clock of a pure tensor loop)" % args.steps,
-                        "kernel_ms_back_to_back": k_ms_b2b, "frac_back_to_back": flops / (k_ms_b2b * 1e-3) / 1e12 / peak_tf,
+                        "kernel_ms_back_to_back": k_ms_b2b, "frac_back_to_back": flops / (k_ms_b2b * 1e-3) / 1e12 / pk_tf,
                         "frac_of_sustained_peak": (ach / peak_sus) if peak_sus else None,
                         "refine_ms_in_sweep": in_sweep_ms[1]}
         cs = corpus.struct()
@@ -1444,6 +1452,7 @@ def run_ours(args):
                        "init": "tokens start in the component of their generating cluster (K_act = K_max)",
                        "parallelism": "utterance shards x%d + NCCL all-reduce(sum_x, counts)" % world,
                        "fused_scorer": bool(args.scorer == "mma" and sweep_fused),
+                       "filter_precision": ("e4m3 first level, fp16 second level" if (sweep.mma is not None and sweep.mma.fp8) else "fp16"),
                        "l2": "inputs (%.1f GB of embeddings per rank) exceed L2; no flush needed" % x_gb},
             "segment_component_evals_per_s": evals_per_s,
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,

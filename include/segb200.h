@@ -357,12 +357,36 @@ int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, 
  * image, the filter GEMM runs over them again with a bitmap epilogue (every component whose filter
  * score reaches best - tau of the first pass), and only the flagged components are re-scored exactly.
  * Same bits out (kmeans_components.py:225-232).  x_tiles / w_tiles: the images segb_mma_filter read.
- * work: segb_mma_refine2_work_bytes() bytes (the first n_emb/8 undecided rows take the second-level
- * pass; a smaller buffer, down to segb_mma_refine_work_bytes(), lowers that capacity; the rest get
- * the exhaustive scan).  n_fallback counts the rows the top-3 records could not decide.           */
+ * work: segb_mma_refine2_work_bytes() bytes: the undecided list is worked off in rounds of n_emb/8 rows
+ * (a smaller buffer shortens the rounds; below one 256-row round the call falls back to
+ * segb_mma_refine).  n_fallback counts the rows the top-3 records could not decide; only rows with an
+ * empty bitmap (NaN scores) still take the exhaustive scan.                                       */
 int64_t segb_mma_refine2_work_bytes(int64_t n_emb, int32_t K_max, int32_t D);
 int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const void *w_tiles, const void *cand,
                      const float *x_err, const float *w_max, int64_t n_emb, void *work, int64_t work_bytes,
+                     float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
+
+/* e4m3 FIRST-LEVEL filter for the k-means scorer (kind::f8f6f4: twice the MMA rate, half the operand bytes).
+ * Same contract as segb_mma_*: a rigorous per-row bound on the filter's error decides which components can be the
+ * reference's argmax (kmeans_components.py:225-232); the survivors are re-scored exactly, so max / first argmax
+ * stay bit-identical.  The e4m3 bound is ~100x looser than the fp16 one: it decides rows whose best component is
+ * well separated (a trained model); the rest go through an fp16 second-level pass (segb_mma8_refine), then the
+ * exhaustive scan.  `scale`: a power of two that brings the operands into e4m3's normal range -- callers pick
+ * the largest one with scale * max|x_d| <= 448 and scale * max|x| <= 448 (means are averages of embeddings).
+ *   x_tiles8 / w_tiles8: e4m3 tile images (segb_mma8_*_tiles_bytes), x_err8 [2 n_emb], x_max8 [2],
+ *   w_err8 [4 (K_max + 128)], w_max8 [4] = (e_mu, n_mu, e_bias, bias_max) in the scaled space.
+ * segb_mma8_refine: w_tiles16 / w_max16 from segb_mma_pack_means (the second level runs in fp16 over a compact image
+ * converted on the fly from the fp32 rows: no resident fp16 image of X); work: segb_mma_refine2_work_bytes().     */
+int64_t segb_mma8_x_tiles_bytes(int64_t n_emb, int32_t D);
+int64_t segb_mma8_w_tiles_bytes(int32_t K_max, int32_t D);
+int segb_mma8_pack_x(const float *X, int64_t n_emb, int32_t D, float scale, void *x_tiles8, float *x_err8,
+                     float *x_max8, void *stream);
+int segb_mma8_pack_means(const float *means, int32_t K_max, int32_t D, float scale, void *w_tiles8, float *w_err8,
+                         float *w_max8, void *stream);
+int segb_mma8_filter(const void *x_tiles8, const void *w_tiles8, int64_t n_emb, int32_t K_max, int32_t D,
+                     const float *x_max8, const float *w_max8, void *cand, void *stream);
+int segb_mma8_refine(const segb_kmeans *m, const void *cand, const float *x_err8, const float *w_max8, float scale,
+                     const void *w_tiles16, const float *w_max16, int64_t n_emb, void *work, int64_t work_bytes,
                      float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
 
 /* ------------------------------------------------------------------ tensor-core log_marg_i (fixed variance) */

@@ -49,12 +49,17 @@ class MmaScorer(object):
     takes 23.8 ms against 19.5 + 3.7 ms for filter + refine: it trades ~3 % of sweep time for
     6.7 GB of HBM and the packing pass, which pays when X streams in from the host or memory is tight."""
 
-    def __init__(self, components, fused=None):
+    def __init__(self, components, fused=None, precision="fp16"):
         lib, c, dev = _lib.lib(), components, "cuda"
         assert c._X.dtype == torch.float32, "tensor-core scorer needs float32 embeddings"
+        assert precision in ("fp16", "fp8")
         self.c = c
         self.fused = False if fused is None else bool(fused)
         assert not self.fused or fused_supported(c.D)
+        # precision="fp8": the first-level filter runs in e4m3 (segb_mma8_*: twice the MMA rate, a 2.6x smaller image
+        # of X); rows it cannot decide take the fp16 second-level pass.  Needs an even D (8-lane refine).
+        self.fp8 = precision == "fp8" and not self.fused and c.D % 2 == 0
+        self.scale = 1.0
         self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
         # refine scratch: list of undecided rows + (two-kernel path) their compact fp16 image, thresholds and
         # candidate bitmaps for the second-level tensor pass
@@ -65,15 +70,38 @@ class MmaScorer(object):
         self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
         self.x_tiles = self.cand = self.x_err = self.x_max = None
         self.timing = None      # a list: score() appends (start, after filter/fused kernel, after refine) CUDA events
-        if not self.fused:
+        if self.fp8:
+            self.scale = self.pick_scale(c._X)
+            self.x_tiles = torch.empty(lib.segb_mma8_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
+            self.w_tiles8 = torch.empty(lib.segb_mma8_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
+            self.w_err8 = torch.empty(4 * (c.K_max + 128), dtype=torch.float32, device=dev)
+            self.w_max8 = torch.zeros(4, dtype=torch.float32, device=dev)
+        elif not self.fused:
             self.x_tiles = torch.empty(lib.segb_mma_x_tiles_bytes(c.N, c.D), dtype=torch.uint8, device=dev)
+        if not self.fused:
             self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=torch.uint8, device=dev)
             self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)              # (|dx|, |x|) per row
             self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
             self.pack_x()
 
+    @staticmethod
+    def pick_scale(X, chunk=1 << 20):
+        """The largest power of two s with s * max|x_d| <= 448 (e4m3's largest finite value) and s * max|x| <= 448
+        (so that s^2 |mu|^2 / 2 fits three e4m3 terms times the 256.0 constant column; means are averages of rows)."""
+        lo, hi = torch.aminmax(X)
+        max_elem = max(abs(float(lo)), abs(float(hi)))
+        max_norm = 0.0
+        for i in range(0, X.shape[0], chunk):
+            max_norm = max(max_norm, float(torch.linalg.vector_norm(X[i:i + chunk], dim=1).max()))
+        lim = max(max_elem, max_norm, 1e-30)
+        return float(2.0 ** np.floor(np.log2(448.0 / lim))) if np.isfinite(lim) else 1.0
+
     def pack_x(self):
         c = self.c
+        if self.fp8:
+            _lib.check(_lib.lib().segb_mma8_pack_x(_lib.ptr(c._X), c.N, c.D, self.scale, _lib.ptr(self.x_tiles),
+                                                   _lib.ptr(self.x_err), _lib.ptr(self.x_max), _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().segb_mma_pack_x(_lib.ptr(c._X), c.N, c.D, _lib.ptr(self.x_tiles), _lib.ptr(self.x_err),
                                               _lib.ptr(self.x_max), _lib.stream_ptr()))
 
@@ -81,15 +109,29 @@ class MmaScorer(object):
         c = self.c
         _lib.check(_lib.lib().segb_mma_pack_means(_lib.ptr(c._means), c.K_max, c.D, _lib.ptr(self.w_tiles),
                                                   _lib.ptr(self.w_err), _lib.ptr(self.w_max), _lib.stream_ptr()))
+        if self.fp8:
+            _lib.check(_lib.lib().segb_mma8_pack_means(_lib.ptr(c._means), c.K_max, c.D, self.scale, _lib.ptr(self.w_tiles8),
+                                                       _lib.ptr(self.w_err8), _lib.ptr(self.w_max8), _lib.stream_ptr()))
 
     def filter(self):
         c = self.c
+        if self.fp8:
+            _lib.check(_lib.lib().segb_mma8_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles8), c.N, c.K_max, c.D,
+                                                   _lib.ptr(self.x_max), _lib.ptr(self.w_max8), _lib.ptr(self.cand),
+                                                   _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().segb_mma_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
                                               _lib.ptr(self.x_max), _lib.ptr(self.w_max), _lib.ptr(self.cand),
                                               _lib.stream_ptr()))
 
     def refine(self, best_val, best_k):
         c = self.c
+        if self.fp8:
+            _lib.check(_lib.lib().segb_mma8_refine(c.struct(), _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max8),
+                                                   self.scale, _lib.ptr(self.w_tiles), _lib.ptr(self.w_max), c.N,
+                                                   _lib.ptr(self.work), self.work.numel(), _lib.ptr(best_val),
+                                                   _lib.ptr(best_k), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().segb_mma_refine2(c.struct(), _lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles),
                                                _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max), c.N,
                                                _lib.ptr(self.work), self.work.numel(), _lib.ptr(best_val),
@@ -142,7 +184,7 @@ class MmaScorer(object):
         x_base = c._X.data_ptr()
         vp = ctypes.c_void_p
         if not self.fused:
-            kp2 = lib.segb_mma_x_tiles_bytes(256, c.D) // 256        # bytes of tile image per row
+            kp2 = (lib.segb_mma8_x_tiles_bytes(256, c.D) if self.fp8 else lib.segb_mma_x_tiles_bytes(256, c.D)) // 256   # bytes of tile image per row
             rec = lib.segb_mma_cand_bytes(1)
         for lo in range(0, c.N, chunk_rows):
             hi = min(c.N, lo + chunk_rows)
@@ -157,6 +199,16 @@ class MmaScorer(object):
             if self.fused:
                 _lib.check(lib.segb_fused_kmeans_best(m, _lib.ptr(self.w_tiles), _lib.ptr(self.w_max), n,
                                                       _lib.ptr(self.work), bv, bk, _lib.ptr(self.n_fallback), sp))
+            elif self.fp8:
+                xt = vp(self.x_tiles.data_ptr() + lo * kp2)
+                xe = vp(self.x_err.data_ptr() + 8 * lo)
+                cd = vp(self.cand.data_ptr() + rec * lo)
+                _lib.check(lib.segb_mma8_pack_x(vp(x_base + 4 * c.D * lo), n, c.D, self.scale, xt, xe, _lib.ptr(self.x_max), sp))
+                _lib.check(lib.segb_mma8_filter(xt, _lib.ptr(self.w_tiles8), n, c.K_max, c.D, _lib.ptr(self.x_max),
+                                                _lib.ptr(self.w_max8), cd, sp))
+                _lib.check(lib.segb_mma8_refine(m, cd, xe, _lib.ptr(self.w_max8), self.scale, _lib.ptr(self.w_tiles),
+                                                _lib.ptr(self.w_max), n, _lib.ptr(self.work), self.work.numel(), bv, bk,
+                                                _lib.ptr(self.n_fallback), sp))
             else:
                 xt = vp(self.x_tiles.data_ptr() + lo * kp2)
                 xe = vp(self.x_err.data_ptr() + 8 * lo)
@@ -173,7 +225,7 @@ class MmaScorer(object):
 
 class FrozenKMeansSweep(object):
 
-    def __init__(self, components, corpus, wip=0.0, scorer="auto", fused=None):
+    def __init__(self, components, corpus, wip=0.0, scorer="auto", fused=None, precision="fp16"):
         self.c, self.corpus, self.wip = components, corpus, float(wip)
         lib = _lib.lib()
         c = components
@@ -202,7 +254,7 @@ class FrozenKMeansSweep(object):
         # its NaN compares (SEGB_DP_SCORES_FINITE); embeddings streamed from the host are not vouched for
         self.scores_finite = bool(torch.isfinite(c._X.sum(dtype=torch.float64)).item()) and np.isfinite(self.wip)
         self._streamed = False
-        self.mma = MmaScorer(c, fused=fused) if scorer == "mma" else None
+        self.mma = MmaScorer(c, fused=fused, precision=precision) if scorer == "mma" else None
         self.K_host = None                     # host copy of the active-component count (no .item() per sweep)
         # add_item's clamp and clean_components as device kernels (csrc/frozen.cu): no host logic per sweep
         self.clamp = NewComponentClamp(corpus, c.K_max)

@@ -36,6 +36,7 @@
 //                          embedding row and 64 of the tile's columns; running top-3 of chunk
 //                          maxima in registers; nothing but 32 B per embedding ever goes back
 //                          to HBM)
+#include <cuda_fp8.h>
 #include "mma_common.cuh"
 #include "refine_rows.cuh"
 
@@ -74,6 +75,7 @@ struct FilterParams {
     int32_t n_last_cols;           // MMA width of the LAST accumulator tile (multiple of 16): padding components beyond it
                                    // are never multiplied, and the epilogue skips their (stale) TMEM columns
     int32_t n_chunks_valid;        // 16-component chunks that were computed = (n_ntiles - 1) * 8 + n_last_cols / 16
+    int32_t n_valid_last;          // real components in the last computed chunk (1..16); F8 masks the padding ones
     uint32_t tile_bytes;                              // bytes of one 128-row tile image of one chunk
     const float *x_max, *w_max;    // corpus-wide (max ex, max nx); model-wide maxima (k-means: e_mu, n_mu; FBGMM: eB, nB, |A|, p/2)
     int32_t D;
@@ -81,8 +83,8 @@ struct FilterParams {
     float tau_T;
     // second-level pass over the rows the top-3 records could not decide (EPI = 1): the row count lives on the
     // device, every row has its own threshold and gets a bitmap of ALL the components at or above it
-    const unsigned long long *n_rows_dev;   // rows = min(*n_rows_dev, rows_cap)
-    int64_t rows_cap;
+    const unsigned long long *n_rows_dev;   // rows = clamp(*n_rows_dev - rows_first, 0, rows_cap): one round of the undecided list
+    int64_t rows_cap, rows_first;
     const float *thr;              // [rows_cap] per-row threshold (best filter score - tau of the first pass)
     uint32_t *bitmap;              // [rows_cap][n_ntiles * 4] bit k of a row: filter score of component k >= thr
 };
@@ -95,13 +97,14 @@ struct FilterParams {
 // "tile done" (= chunk-1 stage free + accumulators ready).
 // EPI = 0: running top-3 chunk maxima per row (Cand records); EPI = 1: per-row bitmap of the components whose
 // score reaches the row's threshold (second-level pass, device-side row count).
-template <int KS, int NCH, int EPI = 0>
+// F8: e4m3 operands (kind::f8f6f4; a K step is 32 elements = the same 32 bytes per row), NCH = 1 only.
+template <int KS, int NCH, int EPI = 0, bool F8 = false>
 __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (EPI == 1) {
-        const unsigned long long n_dev = *p.n_rows_dev;
-        p.n_emb = (int64_t)(n_dev < (unsigned long long)p.rows_cap ? n_dev : (unsigned long long)p.rows_cap);
+        const int64_t left = (int64_t)*p.n_rows_dev - p.rows_first;
+        p.n_emb = left < 0 ? 0 : (left < p.rows_cap ? left : p.rows_cap);
         p.n_mtiles = (int32_t)((p.n_emb + MT_ROWS - 1) / MT_ROWS);
     }
     const uint32_t tb = p.tile_bytes;
@@ -206,7 +209,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                         mbar_wait2(BAR(B_FULL + buf), use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t b_lo = b_lo_base + buf * (tb >> 4);
-                        if (KS > 0) {
+                        if (F8 && KS > 0) {
+                            tc_mma_f8_lo<false>(d0, a_lo0, b_lo, idesc);
+                            tc_mma_f8_lo<false>(d1, a_lo1, b_lo, idesc);
+#pragma unroll
+                            for (int k = 1; k < KS; ++k) {
+                                tc_mma_f8_lo<true>(d0, a_lo0 + k * KSTEP, b_lo + k * KSTEP, idesc);
+                                tc_mma_f8_lo<true>(d1, a_lo1 + k * KSTEP, b_lo + k * KSTEP, idesc);
+                            }
+                        } else if (F8) {
+                            for (int k = 0; k < n_ks; ++k) {
+                                tc_mma_f8(d0, ((uint64_t)DESC_HI << 32) | (a_lo0 + k * KSTEP),
+                                          ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                                tc_mma_f8(d1, ((uint64_t)DESC_HI << 32) | (a_lo1 + k * KSTEP),
+                                          ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
+                            }
+                        } else if (KS > 0) {
                             tc_mma_f16_lo<false>(d0, a_lo0, b_lo, idesc);
                             tc_mma_f16_lo<false>(d1, a_lo1, b_lo, idesc);
 #pragma unroll
@@ -279,6 +297,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
         // one threshold for the whole launch: the loosest per-row tau (refine re-derives the exact per-row one)
         const float tau_c = p.tau_kind == TAU_KMEANS
             ? filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D)
+            : p.tau_kind == TAU_KMEANS_FP8
+            ? filter_tau8(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3], p.D)
             : lse_tau(p.x_max[0], p.x_max[1], W4{p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3]}, 16 * n_ks * NCH, p.tau_T);
         uint32_t n_use = 0;
         if (EPI == 1) {
@@ -330,8 +350,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 for (int c = 0; c < 4; ++c) {
                     if (c < n_c) {
                         float cm = v[c * 16];
+                        if (F8 && cid0 + c == p.n_chunks_valid - 1 && p.n_valid_last < CHUNK) {
+                            // e4m3 cannot carry a "never wins" bias: the padding components of the last chunk are left
+                            // out of its maximum (their member bits may be set; the refine skips k >= K_max)
 #pragma unroll
-                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                            for (int j = 1; j < 16; ++j) cm = fmaxf(cm, j < p.n_valid_last ? v[c * 16 + j] : -CUDART_INF_F);
+                        } else {
+#pragma unroll
+                            for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                        }
                         top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
                     }
                 }
@@ -589,10 +616,12 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_rows_kernel(
 // (filter record, bound, mask walk) is shared by 8 lanes instead of 16 and every load instruction
 // carries two terms.  Needs an even D (8-byte aligned rows); the combination tree is unchanged:
 // (r[2c] + r[2c+1]) locally, then xor 1 and xor 2 inside the block's four lanes.
+// fp8: the records come from the e4m3 filter pass: x_err / w_max hold the e4m3 rounding-error norms of the scaled
+// operands (w_max = (e_mu, n_mu, e_bias, bias_max)) and the threshold is filter_tau8's.
 template <int MAXS>
 __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
     segb_kmeans m, const Cand *cand, const float *x_err, const float *w_max, int64_t n_emb, int n_chunks,
-    float *best_val, int32_t *best_k, unsigned long long *n_fallback, int32_t *fb_list) {
+    float *best_val, int32_t *best_k, unsigned long long *n_fallback, int32_t *fb_list, int fp8 = 0) {
     const int D = m.D, KM = m.K_max;
     const int lane = threadIdx.x & 31, j = lane & 7;
     const Row8Geom geo(D, lane);
@@ -614,7 +643,7 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
         km_load_x8<MAXS>(X + row * D, geo, xv);
         const int64_t row_n = row + grp_total;
         if (row_n < n_emb) { cd_next = cand[row_n]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * row_n); }
-        const float tau = filter_tau(xe.x, xe.y, e_mu, n_mu, D);
+        const float tau = fp8 ? filter_tau8(xe.x, xe.y, e_mu, n_mu, w_max[2], w_max[3], D) : filter_tau(xe.x, xe.y, e_mu, n_mu, D);
         const int code = refine_decide(cd, tau, n_chunks);
         if (code == -2) {
             if (j == 0) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;      // -> refine_full_kernel
@@ -641,11 +670,12 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
 // the rows that pad the last 256-row work item are zeroed and get thr = +inf (empty bitmap)
 __global__ void __launch_bounds__(256) gather_undecided_kernel(const uint8_t *x_tiles, const Cand *cand, const float *x_err,
                                                                const float *w_max, const int32_t *fb_list,
-                                                               const unsigned long long *n_fallback, int64_t rows_cap,
+                                                               const unsigned long long *n_fallback, int64_t first, int64_t rows_cap,
                                                                int D, int KP, uint8_t *fb_tiles, float *thr) {
     const int lane = threadIdx.x & 31;
-    const unsigned long long n_dev = *n_fallback;
-    const int64_t n = (int64_t)(n_dev < (unsigned long long)rows_cap ? n_dev : (unsigned long long)rows_cap);
+    const int64_t left = (int64_t)*n_fallback - first;            // this round: rows [first, first + rows_cap) of the list
+    const int64_t n = left < 0 ? 0 : (left < rows_cap ? left : rows_cap);
+    fb_list += first;
     const int64_t n_pad = (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS;
     const int64_t tile_b = (int64_t)TILE_ROWS * KP * 2;
     const int64_t w_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -678,15 +708,16 @@ __global__ void __launch_bounds__(256) gather_undecided_kernel(const uint8_t *x_
 // finite data; NaN scores) goes to the exhaustive scan through unres_list.
 template <int MAXS>
 __global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
-    segb_kmeans m, const int32_t *fb_list, const unsigned long long *n_fallback, int64_t rows_cap, const uint32_t *bitmap,
-    int n_words, float *best_val, int32_t *best_k, unsigned long long *n_unres, int32_t *unres_list) {
+    segb_kmeans m, const int32_t *fb_list, const unsigned long long *n_fallback, int64_t first, int64_t rows_cap,
+    const uint32_t *bitmap, int n_words, float *best_val, int32_t *best_k, unsigned long long *n_unres, int32_t *unres_list) {
     const int D = m.D, KM = m.K_max;
     const int lane = threadIdx.x & 31, j = lane & 7;
     const Row8Geom geo(D, lane);
     const float *X = (const float *)m.X;
     const float *means = (const float *)m.means;
-    const unsigned long long n_dev = *n_fallback;
-    const int64_t n = (int64_t)(n_dev < (unsigned long long)rows_cap ? n_dev : (unsigned long long)rows_cap);
+    const int64_t left = (int64_t)*n_fallback - first;
+    const int64_t n = left < 0 ? 0 : (left < rows_cap ? left : rows_cap);
+    fb_list += first;
     const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
     for (int64_t i = grp_global; i < n; i += grp_total) {
@@ -714,6 +745,184 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
         if (j == 0) {
             if (bk == 0x7fffffff) unres_list[atomicAdd(n_unres, 1ull)] = (int32_t)row;
             else { best_val[row] = bv; best_k[row] = bk; }
+        }
+    }
+}
+
+
+// ---- e4m3 first-level filter: operand packing ----------------------------------------------------------------
+// The e4m3 pass (kind::f8f6f4: twice the MMA rate and half the operand bytes of the fp16 pass) decides the rows
+// whose best component is well separated -- a trained model -- with the same rigorous-bound logic; what it cannot
+// decide goes to the fp16 second-level pass.  Operands are scaled by a common power of two `scale` (exact) into
+// e4m3's normal range; three constant columns (x side 256.0) carry a three-term e4m3 representation of
+// -scale^2 |mu|^2 / 2 / 256.  Error norms are the ACTUAL rounding errors of the scaled operands.
+__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+__device__ __forceinline__ float from_e4m3(uint8_t b) { return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3))); }
+constexpr float BIAS_COL8 = 256.0f;
+
+// one warp per row; lane ch packs the 16-element chunk ch.  err[2r] = |s x - e4m3(s x)|_2, err[2r+1] = |s x|_2
+__global__ void pack_x8_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad, int D, int KP, float scale, uint8_t *tiles,
+                               float *err, float *x_max) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows_pad) return;
+    uint8_t *base = tiles + (row / TILE_ROWS) * ((int64_t)TILE_ROWS * KP);
+    const int r = (int)(row % TILE_ROWS);
+    float e2 = 0.f, n2 = 0.f;
+    for (int ch = lane; ch < KP / 16; ch += 32) {
+        __align__(16) uint8_t hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = ch * 16 + j;
+            float x = 0.f;
+            if (row < n_emb) {
+                if (c < D) x = X[row * D + c] * scale;
+                else if (c < D + 3) x = BIAS_COL8;
+            }
+            const uint8_t q = to_e4m3(x);
+            hv[j] = q;
+            if (c < D) { const float dl = x - from_e4m3(q); e2 += dl * dl; n2 += x * x; }
+        }
+        *reinterpret_cast<uint4 *>(base + tile_off8(r, ch * 16)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
+    if (lane == 0 && row < n_emb) {
+        float ex = sqrtf(e2) * 1.0001f, nx = sqrtf(n2) * 1.0001f;
+        if (!(ex < CUDART_INF_F) || !(nx < CUDART_INF_F)) ex = nx = CUDART_INF_F;      // NaN / inf rows: never decided here
+        err[2 * row] = ex;
+        err[2 * row + 1] = nx;
+        atomicMax(reinterpret_cast<int *>(x_max), __float_as_int(ex));
+        atomicMax(reinterpret_cast<int *>(x_max) + 1, __float_as_int(nx));
+    }
+}
+
+// means image; err[4k..] = (|s mu - e4m3(s mu)|, |e4m3(s mu)|, |bias - represented bias|, |bias|); padded rows are zeros
+// (the filter's epilogue masks them).
+__global__ void pack_w8_kernel(const float *means, int K_max, int K_pad, int D, int KP, float scale, uint8_t *tiles, float *err) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= K_pad) return;
+    uint8_t *base = tiles + (int64_t)(row / TILE_ROWS) * ((int64_t)TILE_ROWS * KP);
+    const int r = row % TILE_ROWS;
+    double nrm = 0.0;
+    if (row < K_max)
+        for (int d = lane; d < D; d += 32) { const double v = (double)means[(int64_t)row * D + d] * scale; nrm += v * v; }
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(FULL, nrm, o);
+    const float bias = (row < K_max) ? (float)(-0.5 * nrm) : 0.f;                  // scaled space
+    const float t0 = bias / BIAS_COL8;
+    const uint8_t b0 = to_e4m3(t0);
+    const float r1 = t0 - from_e4m3(b0);
+    const uint8_t b1 = to_e4m3(r1);
+    const float r2 = r1 - from_e4m3(b1);
+    const uint8_t b2 = to_e4m3(r2);
+    const float e_bias = fabsf(r2 - from_e4m3(b2)) * BIAS_COL8 * 1.0001f + fabsf(bias) * 2e-7f;   // + float32 rounding of the split
+    float e2 = 0.f, n2 = 0.f;
+    for (int ch = lane; ch < KP / 16; ch += 32) {
+        __align__(16) uint8_t hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = ch * 16 + j;
+            uint8_t q = 0;
+            if (c < D) {
+                const float x = (row < K_max) ? means[(int64_t)row * D + c] * scale : 0.f;
+                q = to_e4m3(x);
+                const float dq = from_e4m3(q), dl = x - dq;
+                e2 += dl * dl;
+                n2 += dq * dq;
+            } else if (row < K_max) {
+                if (c == D) q = b0;
+                else if (c == D + 1) q = b1;
+                else if (c == D + 2) q = b2;
+            }
+            hv[j] = q;
+        }
+        *reinterpret_cast<uint4 *>(base + tile_off8(r, ch * 16)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
+    if (lane == 0) {
+        const bool live = row < K_max;
+        float em = sqrtf(e2) * 1.0001f, nm = sqrtf(n2) * 1.0001f;
+        if (!(em < CUDART_INF_F) || !(nm < CUDART_INF_F) || !(e_bias < CUDART_INF_F)) em = CUDART_INF_F;
+        err[4 * row] = live ? em : 0.f;
+        err[4 * row + 1] = live ? nm : 0.f;
+        err[4 * row + 2] = live ? e_bias : 0.f;
+        err[4 * row + 3] = live ? fabsf(bias) : 0.f;
+    }
+}
+
+// model-wide maxima of the four per-component quantities -> w_max[0..3]
+__global__ void wmax4_kernel(const float *w_err, int K_max, float *w_max) {
+    __shared__ float red[4][32];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = threadIdx.x; k < K_max; k += blockDim.x)
+        for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], w_err[4 * k + i]);
+    for (int i = 0; i < 4; ++i) {
+        for (int o = 16; o > 0; o >>= 1) v[i] = fmaxf(v[i], __shfl_xor_sync(FULL, v[i], o));
+        if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float r = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, red[threadIdx.x][w]);
+        w_max[threadIdx.x] = r;
+    }
+}
+
+// Second level after the e4m3 pass: no resident fp16 image of X exists, so the undecided rows are converted from
+// the fp32 embeddings on the fly (one warp per row, as pack_x_kernel) into the compact fp16 tile image, and the
+// row's threshold for the fp16 bitmap pass follows from the e4m3 record: the reference's winner k* has
+// t(k*) >= t(k1) >= m1/s^2 - b8, hence t16^(k*) >= m1/s^2 - b8 - b16 (b8, b16: the two passes' error bounds).
+__global__ void __launch_bounds__(256) gather_convert_undecided_kernel(
+    const float *X, const Cand *cand, const float *x_err8, const float *w_max8, float scale, const float *w_max16,
+    const int32_t *fb_list, const unsigned long long *n_fallback, int64_t first, int64_t rows_cap, int D, int KP, uint8_t *fb_tiles,
+    float *thr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t left = (int64_t)*n_fallback - first;
+    const int64_t n = left < 0 ? 0 : (left < rows_cap ? left : rows_cap);
+    fb_list += first;
+    const int64_t n_pad = (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS;
+    const int64_t tile_b = (int64_t)TILE_ROWS * KP * 2;
+    const int64_t w_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t w_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float inv_s2 = 1.0f / (scale * scale);
+    for (int64_t i = w_global; i < n_pad; i += w_total) {
+        uint8_t *dst = fb_tiles + (i / TILE_ROWS) * tile_b;
+        const int ri = (int)(i % TILE_ROWS);
+        const int64_t row = i < n ? (int64_t)fb_list[i] : -1;
+        float e2 = 0.f, n2 = 0.f;
+        bool overflow = false;
+        for (int ch = lane; ch < KP / 8; ch += 32) {
+            __align__(16) __half hv[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int c = ch * 8 + jj;
+                float x = 0.f;
+                if (row >= 0) {
+                    if (c < D) x = X[row * D + c];
+                    else if (c < D + 3) x = 1.0f;
+                }
+                if (fabsf(x) > 60000.f) overflow = true;
+                const __half hx = __float2half_rn(x);
+                hv[jj] = hx;
+                if (c < D) { const float dl = x - __half2float(hx); e2 += dl * dl; n2 += x * x; }
+            }
+            *reinterpret_cast<uint4 *>(dst + tile_off(ri, ch * 8)) = *reinterpret_cast<const uint4 *>(hv);
+        }
+        for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
+        overflow = __any_sync(FULL, overflow);
+        if (lane == 0) {
+            float t = CUDART_INF_F;                              // padding rows: empty bitmap
+            if (row >= 0) {
+                const Cand c = cand[row];
+                const float ex16 = overflow ? CUDART_INF_F : sqrtf(e2) * 1.0001f, nx = sqrtf(n2) * 1.0001f;
+                const float tau16 = filter_tau(ex16, nx, w_max16[0], w_max16[1], D);
+                const float tau8 = filter_tau8(x_err8[2 * row], x_err8[2 * row + 1], w_max8[0], w_max8[1], w_max8[2], w_max8[3], D);
+                const float lo = c.m1 * inv_s2 - 0.5f * tau8 * inv_s2 - 0.5f * tau16;
+                // one float32 rounding in each of the three terms: widen by 2^-21 of their magnitudes
+                const float slack = ldexpf(fabsf(c.m1 * inv_s2) + tau8 * inv_s2 + tau16, -21);
+                t = (c.i1 >= 0 && tau8 < CUDART_INF_F && tau16 < CUDART_INF_F && c.m1 > -CUDART_INF_F) ? lo - slack : -CUDART_INF_F;
+            }
+            thr[i] = t;
         }
     }
 }
@@ -907,10 +1116,10 @@ extern "C" int segb_mma_pack_means(const float *means, int32_t K_max, int32_t D,
 
 namespace segb {
 namespace mma {
-static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n_rows_dev, int64_t rows_cap,
+static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n_rows_dev, int64_t rows_first, int64_t rows_cap,
                               const float *thr, uint32_t *bitmap, cudaStream_t stream) {
     FilterParams p;
-    p.n_rows_dev = n_rows_dev; p.rows_cap = rows_cap; p.thr = thr; p.bitmap = bitmap;
+    p.n_rows_dev = n_rows_dev; p.rows_first = rows_first; p.rows_cap = rows_cap; p.thr = thr; p.bitmap = bitmap;
     p.x_tiles = (const uint8_t *)f.x_tiles; p.w_tiles = (const uint8_t *)f.w_tiles; p.cand = (Cand *)f.cand;
     p.n_emb = f.n_emb;
     p.x_max = f.x_max; p.w_max = f.w_max; p.D = f.D;
@@ -922,9 +1131,12 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
         last = (last + 15) / 16 * 16;
         p.n_last_cols = last < 16 ? 16 : (last > NT_COLS ? NT_COLS : last);
         p.n_chunks_valid = (p.n_ntiles - 1) * (NT_COLS / CHUNK) + p.n_last_cols / CHUNK;
+        const int rows = f.w_rows > 0 ? f.w_rows : f.w_rows_pad;
+        p.n_valid_last = rows - (p.n_chunks_valid - 1) * CHUNK;
+        if (p.n_valid_last > CHUNK) p.n_valid_last = CHUNK;
     }
-    p.n_ksteps = f.KP / 16;
-    p.tile_bytes = (uint32_t)((int64_t)TILE_ROWS * f.KP * 2);
+    p.n_ksteps = f.fp8 ? f.KP / 32 : f.KP / 16;                          // 32 bytes of K per row and instruction either way
+    p.tile_bytes = (uint32_t)((int64_t)TILE_ROWS * f.KP * (f.fp8 ? 1 : 2));
     const int nch = f.n_chunks;
     if (nch != 1 && nch != 2) { set_error("filter GEMM: 1 or 2 inner-dimension chunks"); return SEGB_E_ARG; }
     const size_t tb = p.tile_bytes;
@@ -940,7 +1152,10 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
     { const int rc = device_info(nullptr, &n_sm, nullptr); if (rc) return rc; }
     const int grid = p.n_mtiles < n_sm ? p.n_mtiles : n_sm;
     void (*kern)(FilterParams);
-    if (n_rows_dev) {
+    if (f.fp8) {
+        if (nch != 1 || n_rows_dev || f.w_rows <= 0) { set_error("fp8 filter pass: one chunk, top-3 epilogue, known component count"); return SEGB_E_ARG; }
+        kern = p.n_ksteps == 5 ? kmeans_filter_kernel<5, 1, 0, true> : kmeans_filter_kernel<0, 1, 0, true>;   // 5: D = 130 (KP = 160)
+    } else if (n_rows_dev) {
         if (nch != 1) { set_error("second-level filter pass: one inner-dimension chunk"); return SEGB_E_ARG; }
         kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 1, 1> : kmeans_filter_kernel<0, 1, 1>;
     } else if (nch == 1) kern = p.n_ksteps == 9 ? kmeans_filter_kernel<9, 1> : kmeans_filter_kernel<0, 1>;     // 9: D = 130 (KP = 144)
@@ -950,7 +1165,7 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
     SEGB_LAUNCH_CHECK();
     return 0;
 }
-int launch_filter(const FilterLaunch &f, cudaStream_t stream) { return launch_filter_impl(f, nullptr, 0, nullptr, nullptr, stream); }
+int launch_filter(const FilterLaunch &f, cudaStream_t stream) { return launch_filter_impl(f, nullptr, 0, 0, nullptr, nullptr, stream); }
 }  // namespace mma
 }  // namespace segb
 
@@ -995,7 +1210,7 @@ extern "C" int64_t segb_mma_refine_work_bytes(int64_t n_emb, int32_t K_max) {
 // record cannot decide appended to fb_list (count in n_fallback)
 static int refine_rows_stage(const segb_kmeans *m, const void *cand, const float *x_err, const float *w_max,
                              int64_t n_emb, void *work, float *best_val, int32_t *best_k, int64_t *n_fallback,
-                             void *stream) {
+                             void *stream, int fp8 = 0) {
     SEGB_CHECK_ARG(m && cand && x_err && w_max && work && best_val && best_k && n_fallback, "null pointer");
     SEGB_CHECK_ARG(!m->x_is_f64, "tensor-core scorer needs float32 embeddings");
     SEGB_CHECK_ARG(n_emb < (1ll << 31), "too many embeddings for one refine call");
@@ -1017,14 +1232,15 @@ static int refine_rows_stage(const segb_kmeans *m, const void *cand, const float
         const int longest = (m->D > 128) ? (m->D - n2 > n2 ? m->D - n2 : n2) : m->D;
         steps_max = longest / 8;
     }
+    if (fp8 && !lanes8) { set_error("e4m3 filter records need an even D"); return SEGB_E_UNSUPPORTED; }
     if (lanes8 && steps_max <= 8)
         refine_rows8_kernel<8><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
-            (unsigned long long *)n_fallback, fb_list);
+            (unsigned long long *)n_fallback, fb_list, fp8);
     else if (lanes8)
         refine_rows8_kernel<REFINE_MAX_STEPS><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
-            (unsigned long long *)n_fallback, fb_list);
+            (unsigned long long *)n_fallback, fb_list, fp8);
     else
         refine_rows_kernel<<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
@@ -1042,9 +1258,9 @@ extern "C" int segb_mma_refine(const segb_kmeans *m, const void *cand, const flo
 }
 
 // ---- refine with the second-level tensor pass (segb_mma_refine2) --------------------------------------------
-// work layout: [fb_list (n_emb + 64) int32 | n_unres (256 B) | unres_list cap int32 | thr cap float |
+// work layout: [fb_list (n_emb + 64) int32 | n_unres (256 B) | unres_list (n_emb + 64) int32 | thr cap float |
 //               fb_tiles cap * KP * 2 | bitmap cap * (K_pad / 32) * 4], every part 256-byte aligned;
-// cap = undecided rows the second-level pass can take (the rest get the exhaustive scan).
+// cap = undecided rows one ROUND of the second-level pass takes (the list is worked off in ceil(n_emb / cap) rounds).
 namespace {
 struct Work2 { int64_t off_unres_n, off_unres, off_thr, off_tiles, off_bitmap, total; };
 inline int64_t al256(int64_t v) { return (v + 255) / 256 * 256; }
@@ -1052,7 +1268,7 @@ inline Work2 work2_layout(int64_t n_emb, int32_t K_max, int32_t D, int64_t cap) 
     Work2 w;
     w.off_unres_n = al256((n_emb + 64) * (int64_t)sizeof(int32_t));
     w.off_unres = w.off_unres_n + 256;
-    w.off_thr = w.off_unres + al256(cap * 4);
+    w.off_thr = w.off_unres + al256((n_emb + 64) * (int64_t)sizeof(int32_t));       // any row may end up unresolved (NaN data)
     w.off_tiles = w.off_thr + al256(cap * 4);
     w.off_bitmap = w.off_tiles + al256(cap * (int64_t)kp_of(D) * 2);
     w.total = w.off_bitmap + al256(cap * (int64_t)(k_pad(K_max) / 32) * 4);
@@ -1095,25 +1311,112 @@ extern "C" int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const
     uint32_t *bitmap = (uint32_t *)(wb + w.off_bitmap);
     const unsigned long long *n_fb = (const unsigned long long *)n_fallback;
     SEGB_CUDA(cudaMemsetAsync(n_unres, 0, sizeof(unsigned long long), st));
-    gather_undecided_kernel<<<148 * 8, 256, 0, st>>>((const uint8_t *)x_tiles, (const Cand *)cand, x_err, w_max, fb_list, n_fb,
-                                                     cap, m->D, kp_of(m->D), fb_tiles, thr);
-    SEGB_LAUNCH_CHECK();
     FilterLaunch f;
     f.x_tiles = fb_tiles; f.w_tiles = w_tiles; f.cand = nullptr; f.n_emb = cap;       // grid sized for cap; rows from the device
     f.w_rows_pad = k_pad(m->K_max); f.w_rows = m->K_max; f.KP = kp_of(m->D); f.D = m->D; f.x_max = w_max; f.w_max = w_max;
     f.n_chunks = 1; f.tau_kind = TAU_KMEANS; f.tau_T = 0.f;
-    rc = launch_filter_impl(f, n_fb, cap, thr, bitmap, st);
-    if (rc) return rc;
     const int n_words = k_pad(m->K_max) / 32;
-    if (row8_steps_max(m->D) <= 8)
-        refine_bitmap_kernel<8><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, cap, bitmap, n_words, best_val, best_k,
-                                                                    n_unres, unres_list);
-    else
-        refine_bitmap_kernel<REFINE_MAX_STEPS><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, cap, bitmap, n_words,
-                                                                                   best_val, best_k, n_unres, unres_list);
+    // the undecided list is worked off in rounds of `cap` rows: the launch count is fixed (the list length lives on
+    // the device), rounds past its end find nothing to do
+    for (int64_t first = 0; first < n_emb; first += cap) {
+        gather_undecided_kernel<<<148 * 8, 256, 0, st>>>((const uint8_t *)x_tiles, (const Cand *)cand, x_err, w_max, fb_list, n_fb,
+                                                         first, cap, m->D, kp_of(m->D), fb_tiles, thr);
+        SEGB_LAUNCH_CHECK();
+        rc = launch_filter_impl(f, n_fb, first, cap, thr, bitmap, st);
+        if (rc) return rc;
+        if (row8_steps_max(m->D) <= 8)
+            refine_bitmap_kernel<8><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words, best_val,
+                                                                        best_k, n_unres, unres_list);
+        else
+            refine_bitmap_kernel<REFINE_MAX_STEPS><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words,
+                                                                                       best_val, best_k, n_unres, unres_list);
+        SEGB_LAUNCH_CHECK();
+    }
+    // rows the bitmap pass could not resolve (empty bitmap: NaN scores): exhaustive exact scan
+    return launch_refine_full_from(m, unres_list, (const int64_t *)n_unres, 0, best_val, best_k, st);
+}
+
+
+// ---- e4m3 first-level filter (segb_mma8_*) -------------------------------------------------------------------
+static inline int64_t rows_pad8(int64_t n) { return (n + MT_ROWS - 1) / MT_ROWS * MT_ROWS; }
+
+extern "C" int64_t segb_mma8_x_tiles_bytes(int64_t n_emb, int32_t D) { return rows_pad8(n_emb) * kp8_of(D); }
+extern "C" int64_t segb_mma8_w_tiles_bytes(int32_t K_max, int32_t D) { return (int64_t)k_pad(K_max) * kp8_of(D); }
+
+extern "C" int segb_mma8_pack_x(const float *X, int64_t n_emb, int32_t D, float scale, void *x_tiles8, float *x_err8,
+                                float *x_max8, void *stream) {
+    SEGB_CHECK_ARG(X && x_tiles8 && x_err8 && x_max8 && n_emb > 0 && D > 0 && scale > 0.f, "null pointer");
+    const int64_t np_ = rows_pad8(n_emb);
+    const int wpb = 8;
+    SEGB_CUDA(cudaMemsetAsync(x_max8, 0, 2 * sizeof(float), (cudaStream_t)stream));
+    pack_x8_kernel<<<(unsigned)((np_ + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        X, n_emb, np_, D, kp8_of(D), scale, (uint8_t *)x_tiles8, x_err8, x_max8);
     SEGB_LAUNCH_CHECK();
-    // rows beyond the pass's capacity, and rows it could not resolve: exhaustive exact scan
-    rc = launch_refine_full_from(m, fb_list, n_fallback, cap, best_val, best_k, st);
+    return 0;
+}
+
+extern "C" int segb_mma8_pack_means(const float *means, int32_t K_max, int32_t D, float scale, void *w_tiles8, float *w_err8,
+                                    float *w_max8, void *stream) {
+    SEGB_CHECK_ARG(means && w_tiles8 && w_err8 && w_max8 && K_max > 0 && D > 0 && scale > 0.f, "null pointer");
+    const int kp_rows = k_pad(K_max);
+    const int wpb = 8;
+    pack_w8_kernel<<<(kp_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+        means, K_max, kp_rows, D, kp8_of(D), scale, (uint8_t *)w_tiles8, w_err8);
+    SEGB_LAUNCH_CHECK();
+    wmax4_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w_err8, K_max, w_max8);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_mma8_filter(const void *x_tiles8, const void *w_tiles8, int64_t n_emb, int32_t K_max, int32_t D,
+                                const float *x_max8, const float *w_max8, void *cand, void *stream) {
+    SEGB_CHECK_ARG(x_tiles8 && w_tiles8 && cand && x_max8 && w_max8 && n_emb > 0 && K_max > 0, "null pointer");
+    FilterLaunch f;
+    f.x_tiles = x_tiles8; f.w_tiles = w_tiles8; f.cand = cand; f.n_emb = n_emb;
+    f.w_rows_pad = k_pad(K_max); f.w_rows = K_max; f.KP = kp8_of(D); f.D = D; f.x_max = x_max8; f.w_max = w_max8;
+    f.n_chunks = 1; f.tau_kind = TAU_KMEANS_FP8; f.tau_T = 0.f; f.fp8 = 1;
+    return launch_filter(f, (cudaStream_t)stream);
+}
+
+extern "C" int segb_mma8_refine(const segb_kmeans *m, const void *cand, const float *x_err8, const float *w_max8, float scale,
+                                const void *w_tiles16, const float *w_max16, int64_t n_emb, void *work, int64_t work_bytes,
+                                float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
+    SEGB_CHECK_ARG(m && cand && x_err8 && w_max8 && w_tiles16 && w_max16 && scale > 0.f, "null pointer");
+    SEGB_CHECK_ARG(row8_supported(m->D) && row8_steps_max(m->D) <= REFINE_MAX_STEPS, "e4m3 scorer: unsupported D");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t cap = default_cap(n_emb);
+    while (cap > 0 && work2_layout(n_emb, m->K_max, m->D, cap).total > work_bytes) cap -= MT_ROWS;
+    SEGB_CHECK_ARG(cap > 0, "segb_mma8_refine: work buffer too small (segb_mma_refine2_work_bytes)");
+    int rc = refine_rows_stage(m, cand, x_err8, w_max8, n_emb, work, best_val, best_k, n_fallback, stream, 1);
     if (rc) return rc;
+    const Work2 w = work2_layout(n_emb, m->K_max, m->D, cap);
+    uint8_t *wb = (uint8_t *)work;
+    const int32_t *fb_list = (const int32_t *)work;
+    unsigned long long *n_unres = (unsigned long long *)(wb + w.off_unres_n);
+    int32_t *unres_list = (int32_t *)(wb + w.off_unres);
+    float *thr = (float *)(wb + w.off_thr);
+    uint8_t *fb_tiles = wb + w.off_tiles;
+    uint32_t *bitmap = (uint32_t *)(wb + w.off_bitmap);
+    const unsigned long long *n_fb = (const unsigned long long *)n_fallback;
+    SEGB_CUDA(cudaMemsetAsync(n_unres, 0, sizeof(unsigned long long), st));
+    FilterLaunch f;
+    f.x_tiles = fb_tiles; f.w_tiles = w_tiles16; f.cand = nullptr; f.n_emb = cap;
+    f.w_rows_pad = k_pad(m->K_max); f.w_rows = m->K_max; f.KP = kp_of(m->D); f.D = m->D; f.x_max = w_max16; f.w_max = w_max16;
+    f.n_chunks = 1; f.tau_kind = TAU_KMEANS; f.tau_T = 0.f;
+    const int n_words = k_pad(m->K_max) / 32;
+    for (int64_t first = 0; first < n_emb; first += cap) {             // rounds of `cap` undecided rows (see segb_mma_refine2)
+        gather_convert_undecided_kernel<<<148 * 8, 256, 0, st>>>((const float *)m->X, (const Cand *)cand, x_err8, w_max8, scale,
+                                                                 w_max16, fb_list, n_fb, first, cap, m->D, kp_of(m->D), fb_tiles, thr);
+        SEGB_LAUNCH_CHECK();
+        rc = launch_filter_impl(f, n_fb, first, cap, thr, bitmap, st);
+        if (rc) return rc;
+        if (row8_steps_max(m->D) <= 8)
+            refine_bitmap_kernel<8><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words, best_val,
+                                                                        best_k, n_unres, unres_list);
+        else
+            refine_bitmap_kernel<REFINE_MAX_STEPS><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words,
+                                                                                       best_val, best_k, n_unres, unres_list);
+        SEGB_LAUNCH_CHECK();
+    }
     return launch_refine_full_from(m, unres_list, (const int64_t *)n_unres, 0, best_val, best_k, st);
 }

@@ -86,6 +86,13 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
 // One lane of a converged warp.  The compiler knows elect.sync yields exactly one thread, so the
 // single-thread tcgen05 / bulk-copy instructions issued under it need no per-active-lane loop
 // (with `lane == 0` every tcgen05.mma was wrapped in an ELECT / BRA.U.ANY waterfall).
@@ -100,6 +107,18 @@ __device__ __forceinline__ bool elect_one() {
 constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
 __device__ __forceinline__ uint32_t make_desc_lo(uint32_t saddr, int R) {
     return ((saddr >> 4) & 0x3FFFu) | ((uint32_t)((R / 8) * 128 >> 4) << 16);
+}
+// kind::f8f6f4 with e4m3 operands: the same 32 bytes of K per row and instruction (K = 32 elements), the same
+// K-major no-swizzle descriptors and -- e4m3 and f16 both being format code 0 -- the same instruction descriptor
+template <bool ACCUM>
+__device__ __forceinline__ void tc_mma_f8_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %4};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(DESC_HI), "n"(ACCUM ? 1 : 0) : "memory");
 }
 template <bool ACCUM>
 __device__ __forceinline__ void tc_mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
@@ -149,6 +168,12 @@ __host__ __device__ inline int tile_off(int r, int c) {
     return ((c >> 3) * (TILE_ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (c & 7) * 2;
 }
 
+// byte offset of element (r, c) inside a 128-row tile image of 1-byte (fp8) elements: the same 8-row x 16-byte core
+// matrices, 16 elements per core-matrix row instead of 8
+__host__ __device__ inline int tile_off8(int r, int c) {
+    return ((c >> 4) * (TILE_ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (c & 15);
+}
+
 // Rigorous bound on |t^ - t| for t = x.mu - |mu|^2/2 as computed by the fp16 filter GEMM:
 //   ex*|mu^| + |x|*e_mu                      fp16 rounding of the two operands (Cauchy-Schwarz)
 //   c_acc*((|x|+ex)*|mu^| + |mu|^2/2)        fp32 accumulation in the tensor core, bias split
@@ -160,6 +185,21 @@ __host__ __device__ inline float filter_tau(float ex, float nx, float e_mu, floa
     const float c_acc = ldexpf((float)kp, -21) + ldexpf(1.f, -19);
     const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
     const float bound = ex * n_mu + nx * e_mu + c_acc * ((nx + ex) * n_mu + 0.5f * n_mu * n_mu + 1e-30f) + eta;
+    return 2.0f * bound;
+}
+
+// The same bound for the fp8 (e4m3) first-level filter.  Operands are scaled by a common power of two s (exact), so
+// every quantity below lives in the scaled space (scores x s^2); ex / e_mu are the actual e4m3 rounding-error norms
+// measured at packing time, e_bias the largest error of the three-term e4m3 representation of -s^2|mu|^2/2.
+// Products of two e4m3 numbers are exact in fp32; the accumulation term C_ACC8 * (sum of |products|) was
+// calibrated against float64 dot products of the quantised operands (tools/fp8_acc_microbench.py: the largest
+// observed |error| / (|x^||mu^| + |bias|) is 1.0e-7 x KP/32; C_ACC8 leaves a factor > 8).
+constexpr float C_ACC8_PER_STEP = 1.0f / 1048576.0f;          // 2^-20 per K = 32 step
+__host__ __device__ inline int kp8_of(int D) { return (D + 3 + 31) / 32 * 32; }
+__host__ __device__ inline float filter_tau8(float ex, float nx, float e_mu, float n_mu, float e_bias, float bias_max, int D) {
+    const float c_acc = C_ACC8_PER_STEP * (float)(kp8_of(D) / 32) + ldexpf(1.f, -19);
+    const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
+    const float bound = ex * n_mu + nx * e_mu + e_bias + c_acc * ((nx + ex) * n_mu + 1.1f * bias_max + 1e-30f) + eta;
     return 2.0f * bound;
 }
 
@@ -234,7 +274,7 @@ __device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float
 // member masks and refine_decide's code.  16 bytes.
 struct __align__(16) RowRec { int32_t i1, i2; uint32_t masks; int32_t code; };
 
-constexpr int TAU_KMEANS = 0, TAU_LSE = 1;
+constexpr int TAU_KMEANS = 0, TAU_LSE = 1, TAU_KMEANS_FP8 = 2;      // FP8: w_max = (e_mu, n_mu, e_bias, bias_max), scaled space
 
 // Launch description of the filter GEMM over pre-packed tile images (host side).
 struct FilterLaunch {
@@ -250,6 +290,7 @@ struct FilterLaunch {
     const float *x_max, *w_max;
     int32_t tau_kind;
     float tau_T;
+    int32_t fp8 = 0;                   // operands are e4m3 tile images (KP bytes per row), kind::f8f6f4
 };
 int launch_filter(const FilterLaunch &f, cudaStream_t stream);
 

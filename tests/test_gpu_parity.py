@@ -542,8 +542,8 @@ def test_mma_scorer_near_duplicate_components(sb, small_work):
     """A diffuse model: 12 generating clusters spread over 640 components, so every row has ~50 near-duplicate
     candidates scattered over > 3 chunks and the top-3 filter records cannot decide it.  The second-level
     tensor pass (compact image of the undecided rows, bitmap epilogue, exact re-score of the flagged
-    components: segb_mma_refine2) must give the same bits as the exact SIMT scorer; with a work buffer that
-    only fits 4096 second-level rows the remainder takes the exhaustive scan (also the same bits)."""
+    components: segb_mma_refine2) must give the same bits as the exact SIMT scorer; the undecided list is worked
+    off in rounds (8 by default, ~15 with a work buffer that only fits ~4096 rows per round)."""
     from segmentalist_b200 import _lib, synth
     from segmentalist_b200.batch import MmaScorer
     from segmentalist_b200.kmeans_components import KMeansComponents
@@ -574,6 +574,63 @@ def test_mma_scorer_near_duplicate_components(sb, small_work):
     assert n_fb > 8192, "the case must exercise the second-level pass (%d undecided rows)" % n_fb
     npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
     npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
+
+
+@pytest.mark.parametrize("K_max,n_emb,K_true,noise,data", [
+    (300, 5000, 40, 0.05, "unit"), (1000, 3000, 1000, 0.05, "unit"), (37, 700, 5, 0.3, "unit"),
+    (5000, 2100, 200, 0.05, "unit"), (700, 100000, 700, 0.05, "unit"), (640, 30000, 12, 0.05, "dup"),
+    (500, 4000, 500, 0.05, "wide"), (500, 4000, 50, 0.2, "tiny"), (700, 60000, 700, 0.05, "trained"),
+    (5000, 40000, 5000, 0.05, "trained")])
+def test_mma_scorer_fp8_first_level(sb, K_max, n_emb, K_true, noise, data):
+    """e4m3 first-level filter (segb_mma8_*: kind::f8f6f4, scaled operands, three-term e4m3 bias) + exact refine, with
+    the fp16 second-level pass for the rows the e4m3 bound cannot decide == the exact SIMT scorer, float32 bit patterns
+    and argmax.  Cases: separable clusters (decided in e4m3), a diffuse model with near-duplicate components (everything
+    goes to the second level), embeddings with a wide dynamic range (elements far below e4m3's normal range after
+    scaling) and tiny magnitudes (scale 2^k with large k)."""
+    from segmentalist_b200 import synth
+    from segmentalist_b200.batch import MmaScorer
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    rng = np.random.RandomState(K_max + 7)
+    centres = synth.cluster_centres(K_true, 130, rng)
+    z = rng.randint(0, K_true, n_emb)
+    if data == "trained":
+        z[:K_true] = np.arange(K_true)                 # every generating cluster has a member among the assigned rows
+    X = synth._unit_rows(centres[z] + noise * rng.standard_normal((n_emb, 130)).astype(np.float32))
+    if data == "wide":
+        X = (X * np.exp(2.0 * rng.standard_normal((n_emb, 1)))).astype(np.float32)       # row norms over ~4 decades
+    if data == "tiny":
+        X = (X * 1e-3).astype(np.float32)
+    assign = -np.ones(n_emb, dtype=np.int64)
+    n_assigned = min(n_emb, max(K_max * 2, n_emb // 2))
+    if data == "dup":
+        assign[:n_assigned] = z[:n_assigned] + K_true * (np.arange(n_assigned) % (K_max // K_true))
+    elif data == "trained":
+        assign[:n_assigned] = z[:n_assigned]           # every component holds one generating cluster (all are populated)
+        assert len(np.unique(z[:n_assigned])) == K_max
+    else:
+        assign[:n_assigned] = np.arange(n_assigned) % K_max
+    np.random.seed(1)
+    comps = KMeansComponents(X, assign, K_max)
+    val_e, arg_e = comps.best(None)
+    mma = MmaScorer(comps, precision="fp8")
+    assert mma.fp8
+    val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
+    arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
+    mma.score(val, arg)
+    torch.cuda.synchronize()
+    n_fb = int(mma.n_fallback.item())
+    npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
+    npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
+    # the e4m3 pass's own best-chunk maxima track the exact scores (sanity of the scaled GEMM): t = (s - |x|^2) / 2
+    rec = mma.cand.cpu().numpy().view(np.float32).reshape(n_emb, 8)
+    xn = (X.astype(np.float64) ** 2).sum(axis=1)
+    approx_s = 2.0 * rec[:, 0] / mma.scale ** 2 - xn
+    ref = val_e.cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(approx_s - ref) / (np.sqrt(xn) * np.sqrt(xn.max()) + 1e-30)) < 0.3      # ~2 * (ex n_mu + nx e_mu) / s^2
+    if data == "trained":
+        assert n_fb < n_emb // 20, n_fb                # separable clusters, trained model: the e4m3 pass decides
+    if data == "dup":
+        assert n_fb > n_emb // 2                       # near-duplicates: second level
 
 
 def test_frozen_fit_equals_reference_kmeans_fit(sb):
