@@ -72,6 +72,7 @@ struct FilterParams {
     Cand *cand;
     int64_t n_emb;
     int32_t n_mtiles, n_ntiles, n_ksteps, n_abuf;     // n_ksteps: K=16 steps per inner-dimension CHUNK
+    int32_t n_bstage;              // NCH = 1: B ring depth (2, 4 or 8 tiles; a power of two).  NCH = 2: two stages = the two chunks
     int32_t n_last_cols;           // MMA width of the LAST accumulator tile (multiple of 16): padding components beyond it
                                    // are never multiplied, and the epilogue skips their (stale) TMEM columns
     int32_t n_chunks_valid;        // 16-component chunks that were computed = (n_ntiles - 1) * 8 + n_last_cols / 16
@@ -110,12 +111,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
     const uint32_t tb = p.tile_bytes;
     const int n_ks = KS > 0 ? KS : p.n_ksteps;
     uint8_t *sA = smem;                                        // n_abuf x 2 tiles x NCH chunks
-    uint8_t *sB = smem + (size_t)p.n_abuf * 2 * NCH * tb;      // 2 stages (NCH = 1: stage = accumulator buffer = tile parity)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * (size_t)tb);
-    // MMA_DONE[b] (one tcgen05.commit per tile) means BOTH "B stage b may be refilled" (producer) and
+    const uint32_t NB = NCH == 1 ? (uint32_t)p.n_bstage : 2u;  // B ring: tile n_use lives in stage n_use % NB, its accumulators in pair n_use % 2
+    const uint32_t nb_sh = NB == 8 ? 3u : (NB == 4 ? 2u : 1u);
+    uint8_t *sB = smem + (size_t)p.n_abuf * 2 * NCH * tb;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NB * (size_t)tb);
+    // MMA_DONE[s] (one tcgen05.commit per tile, s = the tile's B stage) means BOTH "B stage s may be refilled" (producer) and
     // "accumulator pair b is complete" (epilogue): the issuing thread pays for one commit per tile.
     // NCH = 2 adds B_EMPTY0: the chunk-0 stage is free as soon as the tile's chunk-0 MMAs are done.
-    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, MMA_DONE = 6, ACC_EMPTY = 8, B_EMPTY0 = 10, N_BARS = 11;
+    // With the e4m3 operands a tile's MMAs take 640 clocks, less than the L2 round trip of the next B tile: the ring is
+    // then deeper than the two accumulator pairs (measured: 2 stages 18.5 ms, see profiles/r2_experiments.md).
+    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, MMA_DONE = 12, ACC_EMPTY = 20, B_EMPTY0 = 22, N_BARS = 23;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     float4 *merge = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [MT_ROWS][2] partial top-3
     const uint32_t bar0 = smem_u32(bars);
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     if (nt == nt_pref && mt_next < p.n_mtiles) load_a(it + 1, mt_next);
                     if (NCH == 1) {
-                        const uint32_t s = n_use & 1, use = n_use >> 1;
+                        const uint32_t s = n_use & (NB - 1), use = n_use >> nb_sh;
                         mbar_wait(BAR(MMA_DONE + s), (use & 1) ^ 1);       // the MMAs of the stage's previous tile are done
                         mbar_expect_tx(BAR(B_FULL + s), tb);
                         bulk_g2s(smem_u32(sB + (size_t)s * tb), p.w_tiles + (size_t)nt * tb, tb, BAR(B_FULL + s));
@@ -206,9 +211,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                     const uint32_t d0 = tmem_base + (buf * 2) * NT_COLS, d1 = d0 + NT_COLS;
                     const uint32_t idesc = (nt == p.n_ntiles - 1) ? idesc_last : idesc_full;
                     if (NCH == 1) {
-                        mbar_wait2(BAR(B_FULL + buf), use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
+                        const uint32_t s = n_use & (NB - 1);
+                        mbar_wait2(BAR(B_FULL + s), (n_use >> nb_sh) & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
                         tc_fence_after();
-                        const uint32_t b_lo = b_lo_base + buf * (tb >> 4);
+                        const uint32_t b_lo = b_lo_base + s * (tb >> 4);
                         if (F8 && KS > 0) {
                             tc_mma_f8_lo<false>(d0, a_lo0, b_lo, idesc);
                             tc_mma_f8_lo<false>(d1, a_lo1, b_lo, idesc);
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                                            ((uint64_t)DESC_HI << 32) | (b_lo + k * KSTEP), idesc, k > 0 ? 1u : 0u);
                             }
                         }
-                        tc_commit(BAR(MMA_DONE + buf));       // B stage free + accumulators ready
+                        tc_commit(BAR(MMA_DONE + s));         // B stage free + accumulators ready
                     } else {
                         // chunk 0 (stage 0) opens the accumulators, chunk 1 (stage 1) completes them
                         mbar_wait2(BAR(B_FULL + 0), n_use & 1, BAR(ACC_EMPTY + buf), (use & 1) ^ 1);
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 uint2 *out = reinterpret_cast<uint2 *>(p.bitmap + row * (int64_t)(p.n_ntiles * 4)) + part;
                 for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                     const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                    mbar_wait(BAR(MMA_DONE + buf), acc_phase);
+                    mbar_wait(BAR(MMA_DONE + (NCH == 1 ? (n_use & (NB - 1)) : buf)), NCH == 1 ? (n_use >> nb_sh) & 1 : acc_phase);
                     tc_fence_after();
                     float v[64];
                     tc_ld64_wait(tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS, v);
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
             uint32_t k1 = 0, k2 = 0;
             for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
                 const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                mbar_wait(BAR(MMA_DONE + buf), acc_phase);
+                mbar_wait(BAR(MMA_DONE + (NCH == 1 ? (n_use & (NB - 1)) : buf)), NCH == 1 ? (n_use >> nb_sh) & 1 : acc_phase);
                 tc_fence_after();
                 float v[64];
                 tc_ld64_wait(tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS, v);
@@ -345,21 +351,33 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
                 const int cid0 = nt * (NT_COLS / CHUNK) + (part * COLS) / CHUNK;
-                const int n_c = p.n_chunks_valid - cid0;             // < 4 only in the last tile
+                if (nt + 1 < p.n_ntiles) {
+                    // every tile but the last: four full chunks, straight-line (one uniform branch per tile instead of
+                    // per-chunk validity tests in the hot loop)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < n_c) {
+                    for (int c = 0; c < 4; ++c) {
                         float cm = v[c * 16];
-                        if (F8 && cid0 + c == p.n_chunks_valid - 1 && p.n_valid_last < CHUNK) {
-                            // e4m3 cannot carry a "never wins" bias: the padding components of the last chunk are left
-                            // out of its maximum (their member bits may be set; the refine skips k >= K_max)
 #pragma unroll
-                            for (int j = 1; j < 16; ++j) cm = fmaxf(cm, j < p.n_valid_last ? v[c * 16 + j] : -CUDART_INF_F);
-                        } else {
-#pragma unroll
-                            for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
-                        }
+                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
                         top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                    }
+                } else {
+                    const int n_c = p.n_chunks_valid - cid0;         // chunks of the last tile that were computed
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < n_c) {
+                            float cm = v[c * 16];
+                            if (F8 && cid0 + c == p.n_chunks_valid - 1 && p.n_valid_last < CHUNK) {
+                                // e4m3 cannot carry a "never wins" bias: the padding components of the last chunk are
+                                // left out of its maximum (their member bits may be set; the refine skips k >= K_max)
+#pragma unroll
+                                for (int j = 1; j < 16; ++j) cm = fmaxf(cm, j < p.n_valid_last ? v[c * 16 + j] : -CUDART_INF_F);
+                            } else {
+#pragma unroll
+                                for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                            }
+                            top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                        }
                     }
                 }
             }
@@ -1140,13 +1158,19 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
     const int nch = f.n_chunks;
     if (nch != 1 && nch != 2) { set_error("filter GEMM: 1 or 2 inner-dimension chunks"); return SEGB_E_ARG; }
     const size_t tb = p.tile_bytes;
-    const size_t fixed = 2 * tb + 256 + (size_t)MT_ROWS * 32;            // B stages, barriers, merge buffer
+    const size_t fixed0 = 256 + (size_t)MT_ROWS * 32;                   // barriers, merge buffer
+    size_t fixed = 2 * tb + fixed0;                                     // + B stages
     const size_t budget = 227 * 1024;
     if (2 * nch * tb + fixed > budget) {
         set_error("inner dimension %d x %d too large for the tensor-core scorer", nch, f.KP);
         return SEGB_E_UNSUPPORTED;
     }
     p.n_abuf = (4 * nch * tb + fixed <= budget) ? 2 : 1;
+    p.n_bstage = 2;
+    if (nch == 1)           // deepen the B ring while double-buffered A still fits (e4m3: 4 x 20 KB A + 4..8 x 20 KB B)
+        while (p.n_bstage < 8 && p.n_abuf == 2 && 4 * tb + 2 * p.n_bstage * tb + fixed0 <= budget) p.n_bstage *= 2;
+    if (const char *env = getenv("SEGB_FILTER_BSTAGES")) { const int v = atoi(env); if (nch == 1 && (v == 2 || v == 4 || v == 8) && (size_t)p.n_abuf * 2 * tb + v * tb + fixed0 <= budget) p.n_bstage = v; }
+    fixed = (size_t)p.n_bstage * tb + fixed0;
     const size_t smem = (size_t)p.n_abuf * 2 * nch * tb + fixed;
     int n_sm = 0;
     { const int rc = device_info(nullptr, &n_sm, nullptr); if (rc) return rc; }
