@@ -55,8 +55,9 @@ def parse_args():
     ap.add_argument("--K", type=int, default=K_MAX)
     ap.add_argument("--cpu-sample", type=int, default=32, help="utterances timed by the CPU baseline leg")
     ap.add_argument("--scorer", default="mma", choices=["mma", "exact"])
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp8"],
-                    help="first-level filter GEMM of the k-means scorer: fp16 (kind::f16) or e4m3 (kind::f8f6f4) with the fp16 pass as second level")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp16", "fp8"],
+                    help="first-level filter GEMM of the k-means scorer: fp16 (kind::f16), e4m3 (kind::f8f6f4) with the fp16 pass as "
+                         "second level, or auto (e4m3 until a sweep leaves > 35 %% of the rows undecided)")
     ap.add_argument("--fused", action="store_true", help="the fused score kernel (fp32 rows in, conversion + filter GEMM + refine in one launch) instead of pre-packed fp16 image + filter kernel + refine kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -986,6 +987,7 @@ def kmeans_diffuse_secondary(args, world, rank, dev, barrier, max_over_ranks):
                        % (args.K, total, world),
            "utt_per_s": total / (ms * 1e-3), "ms_per_sweep": ms, "n_gpus": world,
            "K_active_and_fallback_rows_per_sweep_rank0": traj, "phases_ms": sweep.profile_phases(),
+           "filter_precision": "auto -> " + ("e4m3 first level" if sweep.mma.fp8 else "fp16 (the e4m3 pass left > 35 % of the rows undecided in the first sweep)"),
            "note": "clamp of inactive-slot winners and clean_components run as device kernels (csrc/frozen.cu), "
                    "lists exchanged with a fixed-size all-gather; no host logic per sweep"}
     if rank == 0 and not args.no_cpu:

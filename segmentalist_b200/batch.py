@@ -94,7 +94,9 @@ class MmaScorer(object):
         for i in range(0, X.shape[0], chunk):
             max_norm = max(max_norm, float(torch.linalg.vector_norm(X[i:i + chunk], dim=1).max()))
         lim = max(max_elem, max_norm, 1e-30)
-        return float(2.0 ** np.floor(np.log2(448.0 / lim))) if np.isfinite(lim) else 1.0
+        if not np.isfinite(lim):
+            return 1.0
+        return float(2.0 ** min(40.0, np.floor(np.log2(448.0 / lim))))      # s^2 * scores must stay inside float32
 
     def pack_x(self):
         c = self.c
@@ -225,8 +227,15 @@ class MmaScorer(object):
 
 class FrozenKMeansSweep(object):
 
-    def __init__(self, components, corpus, wip=0.0, scorer="auto", fused=None, precision="fp16"):
+    # precision of the tensor-core scorer's first-level filter: "fp16", "fp8" (e4m3 first level, fp16 second level) or
+    # "auto" = start in e4m3 and fall back to fp16 for good once a sweep leaves more than AUTO_FP16_FRACTION of the rows to
+    # the second level (a diffuse model: the e4m3 pass would only add work).  Results are bit-identical in every mode.
+    AUTO_FP16_FRACTION = 0.35
+
+    def __init__(self, components, corpus, wip=0.0, scorer="auto", fused=None, precision="auto"):
         self.c, self.corpus, self.wip = components, corpus, float(wip)
+        assert precision in ("auto", "fp16", "fp8")
+        self.precision_mode = precision
         lib = _lib.lib()
         c = components
         if scorer == "auto":
@@ -254,7 +263,8 @@ class FrozenKMeansSweep(object):
         # its NaN compares (SEGB_DP_SCORES_FINITE); embeddings streamed from the host are not vouched for
         self.scores_finite = bool(torch.isfinite(c._X.sum(dtype=torch.float64)).item()) and np.isfinite(self.wip)
         self._streamed = False
-        self.mma = MmaScorer(c, fused=fused, precision=precision) if scorer == "mma" else None
+        self._fused = fused
+        self.mma = MmaScorer(c, fused=fused, precision="fp16" if precision == "fp16" else "fp8") if scorer == "mma" else None
         self.K_host = None                     # host copy of the active-component count (no .item() per sweep)
         # add_item's clamp and clean_components as device kernels (csrc/frozen.cu): no host logic per sweep
         self.clamp = NewComponentClamp(corpus, c.K_max)
@@ -391,6 +401,13 @@ class FrozenKMeansSweep(object):
             n_bad, np.unique(self.status.cpu().numpy()))
         self.last_fallback = n_fb
         self.K_host = K_now
+        if (self.precision_mode == "auto" and self.mma is not None and self.mma.fp8 and
+                n_fb > self.AUTO_FP16_FRACTION * c.N):
+            # the e4m3 pass decided too little: this model is served better by the fp16 first level
+            timing = self.mma.timing
+            self.mma = None                                 # release the e4m3 image before the fp16 one is built
+            self.mma = MmaScorer(c, fused=self._fused, precision="fp16")
+            self.mma.timing = timing
         # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time)
         total = float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
         if _dist_on():

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < ACC_EMPTY; ++i) mbar_init(BAR(i), 1);
-        for (int b = 0; b < 2; ++b) mbar_init(BAR(ACC_EMPTY + b), N_EPI_WARPS);
+        // top-3 epilogue: accumulator pair b is drained by the 8 warps of set b; bitmap epilogue: by all 16 warps
+        for (int b = 0; b < 2; ++b) mbar_init(BAR(ACC_EMPTY + b), EPI == 1 ? N_EPI_WARPS : N_EPI_WARPS / 2);
         mbar_init(BAR(B_EMPTY0), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -336,73 +337,85 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                     out[2 * nt] = make_uint2(~w0 & k0, ~w1 & k1);
                 }
             }
-        } else
-        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
-            float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
-            int i1 = -1, i2 = -1;
-            uint32_t k1 = 0, k2 = 0;
-            for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
-                const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
-                mbar_wait(BAR(MMA_DONE + (NCH == 1 ? (n_use & (NB - 1)) : buf)), NCH == 1 ? (n_use >> nb_sh) & 1 : acc_phase);
-                tc_fence_after();
-                float v[64];
-                tc_ld64_wait(tmem_base + lane_base + (buf * 2 + h) * NT_COLS + part * COLS, v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
-                const int cid0 = nt * (NT_COLS / CHUNK) + (part * COLS) / CHUNK;
-                if (nt + 1 < p.n_ntiles) {
-                    // every tile but the last: four full chunks, straight-line (one uniform branch per tile instead of
-                    // per-chunk validity tests in the hot loop)
+        } else {
+            // Two SETS of eight warps drain alternate tiles: set s owns accumulator pair s (= tiles of parity s) and takes
+            // all 128 columns of its tile in two 64-column loads.  While one set waits for its tcgen05.ld the other one
+            // is reducing, so TMEM reads and issue slots overlap instead of alternating for all 16 warps at once (the
+            // e4m3 pass is bound by this epilogue, not by the MMAs).  The sets' partial top-3 lists of a row meet through
+            // shared memory at the end of every work item.
+            const int set = part;                              // e >> 3
+            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+                float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+                int i1 = -1, i2 = -1;
+                uint32_t k1 = 0, k2 = 0;
+                for (int nt = 0; nt < p.n_ntiles; ++nt, ++n_use) {
+                    if ((int)(n_use & 1) != set) continue;
+                    const uint32_t buf = n_use & 1, acc_phase = (n_use >> 1) & 1;
+                    mbar_wait(BAR(MMA_DONE + (NCH == 1 ? (n_use & (NB - 1)) : buf)), NCH == 1 ? (n_use >> nb_sh) & 1 : acc_phase);
+                    tc_fence_after();
+                    const bool last_tile = nt + 1 == p.n_ntiles;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float cm = v[c * 16];
+                    for (int half = 0; half < 2; ++half) {
+                        float v[64];
+                        tc_ld64_wait(tmem_base + lane_base + (buf * 2 + h) * NT_COLS + half * COLS, v);
+                        if (half == 1) {                       // both halves are in registers: hand the accumulator back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+                        }
+                        const int cid0 = nt * (NT_COLS / CHUNK) + (half * COLS) / CHUNK;
+                        if (!last_tile) {
+                            // every tile but the last: four full chunks, straight-line
 #pragma unroll
-                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
-                        top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
-                    }
-                } else {
-                    const int n_c = p.n_chunks_valid - cid0;         // chunks of the last tile that were computed
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (c < n_c) {
-                            float cm = v[c * 16];
-                            if (F8 && cid0 + c == p.n_chunks_valid - 1 && p.n_valid_last < CHUNK) {
-                                // e4m3 cannot carry a "never wins" bias: the padding components of the last chunk are
-                                // left out of its maximum (their member bits may be set; the refine skips k >= K_max)
-#pragma unroll
-                                for (int j = 1; j < 16; ++j) cm = fmaxf(cm, j < p.n_valid_last ? v[c * 16 + j] : -CUDART_INF_F);
-                            } else {
+                            for (int c = 0; c < 4; ++c) {
+                                float cm = v[c * 16];
 #pragma unroll
                                 for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                                top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
                             }
-                            top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                        } else {
+                            const int n_c = p.n_chunks_valid - cid0;         // chunks of the last tile that were computed
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                if (c < n_c) {
+                                    float cm = v[c * 16];
+                                    if (F8 && cid0 + c == p.n_chunks_valid - 1 && p.n_valid_last < CHUNK) {
+                                        // e4m3 cannot carry a "never wins" bias: the padding components of the last chunk
+                                        // are left out of its maximum (their member bits may be set; the refine skips
+                                        // k >= K_max)
+#pragma unroll
+                                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, j < p.n_valid_last ? v[c * 16 + j] : -CUDART_INF_F);
+                                    } else {
+#pragma unroll
+                                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                                    }
+                                    top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                                }
+                            }
                         }
                     }
                 }
-            }
-            const int r_local = h * TILE_ROWS + q * 32 + lane;
-            if (EPI_PARTS == 2) {
-                // the two column parts of a row meet through shared memory
-                if (part == 1) {
+                const int r_local = h * TILE_ROWS + q * 32 + lane;
+                // the two sets' lists of a row meet through shared memory
+                if (set == 1) {
                     merge[2 * r_local] = make_float4(m1, m2, m3, __int_as_float(i1));
                     merge[2 * r_local + 1] = make_float4(__int_as_float(i2), __uint_as_float(k1), __uint_as_float(k2), 0.f);
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * N_EPI_WARPS) : "memory");
-                if (part == 0) {
+                if (set == 0) {
                     const float4 a = merge[2 * r_local], b = merge[2 * r_local + 1];
                     top3_merge(a.x, __float_as_int(a.w), __float_as_uint(b.y), m1, m2, m3, i1, i2, k1, k2);
                     top3_merge(a.y, __float_as_int(b.x), __float_as_uint(b.z), m1, m2, m3, i1, i2, k1, k2);
                     if (a.z > m3) m3 = a.z;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * N_EPI_WARPS) : "memory");
-            }
-            const int64_t row = (int64_t)mt * MT_ROWS + r_local;
-            if (part == 0 && row < p.n_emb) {
-                Cand c;
-                c.m1 = m1; c.m2 = m2; c.m3 = m3; c.i1 = i1; c.i2 = i2;
-                c.masks = (k1 & 0xffffu) | (k2 << 16); c.pad[0] = c.pad[1] = 0;
-                p.cand[row] = c;
+                const int64_t row = (int64_t)mt * MT_ROWS + r_local;
+                if (set == 0 && row < p.n_emb) {
+                    Cand c;
+                    c.m1 = m1; c.m2 = m2; c.m3 = m3; c.i1 = i1; c.i2 = i2;
+                    c.masks = (k1 & 0xffffu) | (k2 << 16); c.pad[0] = c.pad[1] = 0;
+                    p.cand[row] = c;
+                }
             }
         }
     }
