@@ -1178,6 +1178,7 @@ def run_ours(args):
     sweep = FrozenKMeansSweep(comps, corpus, wip=0.0, scorer=args.scorer, fused=bool(args.fused), precision=args.precision)
     sweep.init_means_from_assignments()
     sweep_fused = bool(sweep.mma is not None and sweep.mma.fused)
+    filter_precision = None
     x_gb = X.numel() * 4 / 1e9
     n_pos, M = corpus.n_pos, n_emb
     evals_per_sweep_local = float(M) * args.K
@@ -1200,6 +1201,7 @@ def run_ours(args):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     in_sweep_ms = None
+    filter_precision = ("e4m3 first level, fp16 second level" if (sweep.mma is not None and sweep.mma.fp8) else "fp16")   # after "auto" settled
     if sweep.mma is not None:
         tm, sweep.mma.timing = sweep.mma.timing, None
         in_sweep_ms = (sum(e[0].elapsed_time(e[1]) for e in tm) / len(tm), sum(e[1].elapsed_time(e[2]) for e in tm) / len(tm))
@@ -1454,7 +1456,7 @@ def run_ours(args):
                        "init": "tokens start in the component of their generating cluster (K_act = K_max)",
                        "parallelism": "utterance shards x%d + NCCL all-reduce(sum_x, counts)" % world,
                        "fused_scorer": bool(args.scorer == "mma" and sweep_fused),
-                       "filter_precision": ("e4m3 first level, fp16 second level" if (sweep.mma is not None and sweep.mma.fp8) else "fp16"),
+                       "filter_precision": filter_precision,
                        "l2": "inputs (%.1f GB of embeddings per rank) exceed L2; no flush needed" % x_gb},
             "segment_component_evals_per_s": evals_per_s,
             "fallback_rows_per_sweep": float(tot[2].item()) / args.steps,
