@@ -1244,9 +1244,10 @@ def run_ours(args):
             flops = 2.0 * D * M * args.K                  # algorithmic: 2*D per segment x component eval
             ach = flops / (k_ms * 1e-3) / 1e12
             peak_sus = float(peaks.get("bf16_tflops_sustained", 0.0)) or None
-            kname = "score_fused_kernel" if fused else "kmeans_filter_kernel"
-            tr = ncu_traffic(kname) if default_cfg else None
             fp8 = bool(sweep.mma.fp8)
+            # r2_ncu_traffic.json: the default (e4m3) filter under its plain name, the fp16 one keyed by its capture file
+            kname = "score_fused_kernel" if fused else ("kmeans_filter_kernel" if fp8 else "kmeans_filter_kernel@r2_raw_kmeans16.csv")
+            tr = ncu_traffic(kname) if default_cfg else None
             pk_tf, pk_src = peak_tf, peak_src
             if fp8:       # e4m3 dense rate = 2 x the bf16 rate; MEASURED_PEAKS.json has no fp8 entry
                 pk_tf, pk_src, peak_sus = 2.0 * peak_tf, "2 x " + peak_src + " (e4m3 runs at twice the bf16 rate; no measured fp8 entry)", (2.0 * peak_sus if peak_sus else None)

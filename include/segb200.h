@@ -360,11 +360,13 @@ int segb_mma_refine(const segb_kmeans *m, const void *cand, const float *x_err, 
  * work: segb_mma_refine2_work_bytes() bytes: the undecided list is worked off in rounds of n_emb/8 rows
  * (a smaller buffer shortens the rounds; below one 256-row round the call falls back to
  * segb_mma_refine).  n_fallback counts the rows the top-3 records could not decide; only rows with an
- * empty bitmap (NaN scores) still take the exhaustive scan.                                       */
+ * empty bitmap (NaN scores) still take the exhaustive scan.  max_rounds > 0 limits the rounds that are
+ * launched (a caller that knows the previous sweep's count saves the empty launches); undecided rows
+ * beyond them take the exhaustive scan -- still exact, only slower.  0 = as many as n_emb may need.     */
 int64_t segb_mma_refine2_work_bytes(int64_t n_emb, int32_t K_max, int32_t D);
 int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const void *w_tiles, const void *cand,
                      const float *x_err, const float *w_max, int64_t n_emb, void *work, int64_t work_bytes,
-                     float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
+                     int32_t max_rounds, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
 
 /* e4m3 FIRST-LEVEL filter for the k-means scorer (kind::f8f6f4: twice the MMA rate, half the operand bytes).
  * Same contract as segb_mma_*: a rigorous per-row bound on the filter's error decides which components can be the
@@ -387,7 +389,7 @@ int segb_mma8_filter(const void *x_tiles8, const void *w_tiles8, int64_t n_emb, 
                      const float *x_max8, const float *w_max8, void *cand, void *stream);
 int segb_mma8_refine(const segb_kmeans *m, const void *cand, const float *x_err8, const float *w_max8, float scale,
                      const void *w_tiles16, const float *w_max16, int64_t n_emb, void *work, int64_t work_bytes,
-                     float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
+                     int32_t max_rounds, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream);
 
 /* ------------------------------------------------------------------ tensor-core log_marg_i (fixed variance) */
 

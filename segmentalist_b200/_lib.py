@@ -96,15 +96,15 @@ _PROTOS = {
     "segb_mma_refine": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                        c_vp]),
     "segb_mma_refine2_work_bytes": (c_i64, [c_i64, c_i32, c_i32]),
-    "segb_mma_refine2": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp,
-                                        c_vp, c_vp, c_vp]),
+    "segb_mma_refine2": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32,
+                                        c_vp, c_vp, c_vp, c_vp]),
     "segb_mma8_x_tiles_bytes": (c_i64, [c_i64, c_i32]),
     "segb_mma8_w_tiles_bytes": (c_i64, [c_i32, c_i32]),
     "segb_mma8_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
     "segb_mma8_pack_means": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
     "segb_mma8_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "segb_mma8_refine": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_i64, c_vp,
-                                        c_i64, c_vp, c_vp, c_vp, c_vp]),
+                                        c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "segb_fvmma_x_tiles_bytes": (c_i64, [c_i64, c_i32]),
     "segb_fvmma_w_tiles_bytes": (c_i64, [c_i32, c_i32]),
     "segb_fvmma_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),

@@ -69,6 +69,9 @@ class MmaScorer(object):
         self.w_max = torch.zeros(2, dtype=torch.float32, device=dev)
         self.n_fallback = torch.zeros(1, dtype=torch.int64, device=dev)
         self.x_tiles = self.cand = self.x_err = self.x_max = None
+        # second-level rounds to launch per refine call: 0 = as many as all rows may need (first use); a sweep that knows
+        # the previous count of undecided rows sets it to what twice that count needs (rows beyond take the exhaustive scan)
+        self.max_rounds = 0
         self.timing = None      # a list: score() appends (start, after filter/fused kernel, after refine) CUDA events
         if self.fp8:
             self.scale = self.pick_scale(c._X)
@@ -83,6 +86,12 @@ class MmaScorer(object):
             self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)              # (|dx|, |x|) per row
             self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
             self.pack_x()
+
+    def rounds_for(self, n_rows):
+        """Second-level rounds that n_rows undecided rows need with this scorer's work buffer (a round takes n_emb / 8
+        rows, in whole 256-row work items)."""
+        cap = max(16 * 256, (self.c.N // 8 + 255) // 256 * 256)
+        return int(max(1, -(-int(n_rows) // cap)))
 
     @staticmethod
     def pick_scale(X, chunk=1 << 20):
@@ -131,12 +140,12 @@ class MmaScorer(object):
         if self.fp8:
             _lib.check(_lib.lib().segb_mma8_refine(c.struct(), _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max8),
                                                    self.scale, _lib.ptr(self.w_tiles), _lib.ptr(self.w_max), c.N,
-                                                   _lib.ptr(self.work), self.work.numel(), _lib.ptr(best_val),
+                                                   _lib.ptr(self.work), self.work.numel(), self.max_rounds, _lib.ptr(best_val),
                                                    _lib.ptr(best_k), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
             return
         _lib.check(_lib.lib().segb_mma_refine2(c.struct(), _lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles),
                                                _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max), c.N,
-                                               _lib.ptr(self.work), self.work.numel(), _lib.ptr(best_val),
+                                               _lib.ptr(self.work), self.work.numel(), self.max_rounds, _lib.ptr(best_val),
                                                _lib.ptr(best_k), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
 
     def fused_score(self, best_val, best_k):
@@ -209,7 +218,7 @@ class MmaScorer(object):
                 _lib.check(lib.segb_mma8_filter(xt, _lib.ptr(self.w_tiles8), n, c.K_max, c.D, _lib.ptr(self.x_max),
                                                 _lib.ptr(self.w_max8), cd, sp))
                 _lib.check(lib.segb_mma8_refine(m, cd, xe, _lib.ptr(self.w_max8), self.scale, _lib.ptr(self.w_tiles),
-                                                _lib.ptr(self.w_max), n, _lib.ptr(self.work), self.work.numel(), bv, bk,
+                                                _lib.ptr(self.w_max), n, _lib.ptr(self.work), self.work.numel(), self.max_rounds, bv, bk,
                                                 _lib.ptr(self.n_fallback), sp))
             else:
                 xt = vp(self.x_tiles.data_ptr() + lo * kp2)
@@ -219,7 +228,7 @@ class MmaScorer(object):
                 _lib.check(lib.segb_mma_filter(xt, _lib.ptr(self.w_tiles), n, c.K_max, c.D, _lib.ptr(self.x_max),
                                                _lib.ptr(self.w_max), cd, sp))
                 _lib.check(lib.segb_mma_refine2(m, xt, _lib.ptr(self.w_tiles), cd, xe, _lib.ptr(self.w_max), n,
-                                                _lib.ptr(self.work), self.work.numel(), bv, bk,
+                                                _lib.ptr(self.work), self.work.numel(), self.max_rounds, bv, bk,
                                                 _lib.ptr(self.n_fallback), sp))
             self.fb_total += self.n_fallback
         self.n_fallback.copy_(self.fb_total)
@@ -401,6 +410,8 @@ class FrozenKMeansSweep(object):
             n_bad, np.unique(self.status.cpu().numpy()))
         self.last_fallback = n_fb
         self.K_host = K_now
+        if self.mma is not None and not self.mma.fused:
+            self.mma.max_rounds = self.mma.rounds_for(2 * n_fb + 4096)
         if (self.precision_mode == "auto" and self.mma is not None and self.mma.fp8 and
                 n_fb > self.AUTO_FP16_FRACTION * c.N):
             # the e4m3 pass decided too little: this model is served better by the fp16 first level

@@ -1325,7 +1325,7 @@ extern "C" int64_t segb_mma_refine2_work_bytes(int64_t n_emb, int32_t K_max, int
 
 extern "C" int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const void *w_tiles, const void *cand,
                                 const float *x_err, const float *w_max, int64_t n_emb, void *work, int64_t work_bytes,
-                                float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
+                                int32_t max_rounds, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
     SEGB_CHECK_ARG(m && x_tiles && w_tiles, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     // the largest cap (a multiple of 256 rows) whose layout fits the caller's buffer
@@ -1355,7 +1355,8 @@ extern "C" int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const
     const int n_words = k_pad(m->K_max) / 32;
     // the undecided list is worked off in rounds of `cap` rows: the launch count is fixed (the list length lives on
     // the device), rounds past its end find nothing to do
-    for (int64_t first = 0; first < n_emb; first += cap) {
+    int64_t first = 0;
+    for (int round = 0; first < n_emb && (max_rounds <= 0 || round < max_rounds); first += cap, ++round) {
         gather_undecided_kernel<<<148 * 8, 256, 0, st>>>((const uint8_t *)x_tiles, (const Cand *)cand, x_err, w_max, fb_list, n_fb,
                                                          first, cap, m->D, kp_of(m->D), fb_tiles, thr);
         SEGB_LAUNCH_CHECK();
@@ -1369,7 +1370,9 @@ extern "C" int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const
                                                                                        best_val, best_k, n_unres, unres_list);
         SEGB_LAUNCH_CHECK();
     }
-    // rows the bitmap pass could not resolve (empty bitmap: NaN scores): exhaustive exact scan
+    // undecided rows beyond the rounds the caller asked for, and rows the bitmap pass could not resolve (empty bitmap:
+    // NaN scores): exhaustive exact scan
+    if (first < n_emb) { rc = launch_refine_full_from(m, fb_list, n_fallback, first, best_val, best_k, st); if (rc) return rc; }
     return launch_refine_full_from(m, unres_list, (const int64_t *)n_unres, 0, best_val, best_k, st);
 }
 
@@ -1417,7 +1420,7 @@ extern "C" int segb_mma8_filter(const void *x_tiles8, const void *w_tiles8, int6
 
 extern "C" int segb_mma8_refine(const segb_kmeans *m, const void *cand, const float *x_err8, const float *w_max8, float scale,
                                 const void *w_tiles16, const float *w_max16, int64_t n_emb, void *work, int64_t work_bytes,
-                                float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
+                                int32_t max_rounds, float *best_val, int32_t *best_k, int64_t *n_fallback, void *stream) {
     SEGB_CHECK_ARG(m && cand && x_err8 && w_max8 && w_tiles16 && w_max16 && scale > 0.f, "null pointer");
     SEGB_CHECK_ARG(row8_supported(m->D) && row8_steps_max(m->D) <= REFINE_MAX_STEPS, "e4m3 scorer: unsupported D");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1441,7 +1444,8 @@ extern "C" int segb_mma8_refine(const segb_kmeans *m, const void *cand, const fl
     f.w_rows_pad = k_pad(m->K_max); f.w_rows = m->K_max; f.KP = kp_of(m->D); f.D = m->D; f.x_max = w_max16; f.w_max = w_max16;
     f.n_chunks = 1; f.tau_kind = TAU_KMEANS; f.tau_T = 0.f;
     const int n_words = k_pad(m->K_max) / 32;
-    for (int64_t first = 0; first < n_emb; first += cap) {             // rounds of `cap` undecided rows (see segb_mma_refine2)
+    int64_t first = 0;
+    for (int round = 0; first < n_emb && (max_rounds <= 0 || round < max_rounds); first += cap, ++round) {   // rounds (see segb_mma_refine2)
         gather_convert_undecided_kernel<<<148 * 8, 256, 0, st>>>((const float *)m->X, (const Cand *)cand, x_err8, w_max8, scale,
                                                                  w_max16, fb_list, n_fb, first, cap, m->D, kp_of(m->D), fb_tiles, thr);
         SEGB_LAUNCH_CHECK();
@@ -1455,5 +1459,6 @@ extern "C" int segb_mma8_refine(const segb_kmeans *m, const void *cand, const fl
                                                                                        best_val, best_k, n_unres, unres_list);
         SEGB_LAUNCH_CHECK();
     }
+    if (first < n_emb) { rc = launch_refine_full_from(m, fb_list, n_fallback, first, best_val, best_k, st); if (rc) return rc; }
     return launch_refine_full_from(m, unres_list, (const int64_t *)n_unres, 0, best_val, best_k, st);
 }
