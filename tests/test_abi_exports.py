@@ -64,3 +64,21 @@ def test_members_by_component_groups_like_np_where():
     assert seg_off.shape == (K_max + 1,) and seg_off[0] == (assign == -1).sum() and seg_off[-1] == len(assign)
     for k in range(K_max):
         np.testing.assert_array_equal(order[seg_off[k]:seg_off[k + 1]], np.where(assign == k)[0])
+
+
+def test_e4m3_scale_choice():
+    """Host logic of the e4m3 first-level filter: the operand scale is the largest power of two that keeps every
+    scaled element and every scaled row norm inside e4m3's finite range (448), so that s^2 |mu|^2 / 2 fits three e4m3
+    terms times the 256.0 constant column (means are averages of rows)."""
+    import numpy as np
+    import torch
+    from segmentalist_b200.batch import MmaScorer
+    rng = np.random.RandomState(0)
+    for mag in (1e-4, 0.03, 1.0, 37.0, 5e3):
+        X = torch.from_numpy((rng.standard_normal((1000, 130)) * mag).astype(np.float32))
+        s = MmaScorer.pick_scale(X, chunk=256)
+        assert s > 0 and np.log2(s) == int(np.log2(s))
+        lim = max(float(X.abs().max()), float(torch.linalg.vector_norm(X, dim=1).max()))
+        assert s * lim <= 448.0 and 2 * s * lim > 448.0
+    assert MmaScorer.pick_scale(torch.zeros(10, 4)) == 2.0 ** 40          # degenerate data: capped, finite
+    assert MmaScorer.pick_scale(torch.full((3, 4), float("inf"))) == 1.0
