@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
     constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, MMA_DONE = 12, ACC_EMPTY = 20, B_EMPTY0 = 22, N_BARS = 23;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     float4 *merge = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [MT_ROWS][2] partial top-3
+    // F8: parked scores of every epilogue thread's current best chunk (top3_insert_snap), 4 x 512 float4 = 32 KB
+    float4 *snap_all = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256 + (size_t)MT_ROWS * 32);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -344,6 +346,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
             // e4m3 pass is bound by this epilogue, not by the MMAs).  The sets' partial top-3 lists of a row meet through
             // shared memory at the end of every work item.
             const int set = part;                              // e >> 3
+            float4 *snap = snap_all + (threadIdx.x - 128);     // this thread's slot (epilogue threads are 128 .. 639)
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
                 float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
                 int i1 = -1, i2 = -1;
@@ -371,7 +374,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                                 float cm = v[c * 16];
 #pragma unroll
                                 for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
-                                top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                                if (F8) top3_insert_snap(&v[c * 16], cm, cid0 + c, snap, m1, m2, m3, i1, i2);
+                                else top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
                             }
                         } else {
                             const int n_c = p.n_chunks_valid - cid0;         // chunks of the last tile that were computed
@@ -389,11 +393,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
 #pragma unroll
                                         for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
                                     }
-                                    top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                                    if (F8) top3_insert_snap(&v[c * 16], cm, cid0 + c, snap, m1, m2, m3, i1, i2);
+                                    else top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
                                 }
                             }
                         }
                     }
+                }
+                if (F8) {                                       // the deferred member mask of this set's best chunk
+                    k1 = i1 >= 0 ? top3_snapshot_mask(snap, m1, tau_c) : 0u;
+                    k2 = 0xffffu;
                 }
                 const int r_local = h * TILE_ROWS + q * 32 + lane;
                 // the two sets' lists of a row meet through shared memory
@@ -1171,7 +1180,7 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
     const int nch = f.n_chunks;
     if (nch != 1 && nch != 2) { set_error("filter GEMM: 1 or 2 inner-dimension chunks"); return SEGB_E_ARG; }
     const size_t tb = p.tile_bytes;
-    const size_t fixed0 = 256 + (size_t)MT_ROWS * 32;                   // barriers, merge buffer
+    const size_t fixed0 = 256 + (size_t)MT_ROWS * 32 + (f.fp8 ? (size_t)4 * SNAP_STRIDE * 16 : 0);   // barriers, merge buffer, F8: parked best chunks
     size_t fixed = 2 * tb + fixed0;                                     // + B stages
     const size_t budget = 227 * 1024;
     if (2 * nch * tb + fixed > budget) {

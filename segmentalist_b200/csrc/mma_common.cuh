@@ -270,6 +270,42 @@ __device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float
     }
 }
 
+// The same insertion with the member mask DEFERRED: a chunk that becomes the new best only parks its 16 scores in a
+// per-thread shared-memory slot (four 16-byte stores; snap[q * SNAP_STRIDE] with consecutive threads 16 bytes apart:
+// conflict-free), and the mask is formed once per row and work item by top3_snapshot_mask.  A new-best event costs
+// the WHOLE warp ~8 instructions instead of ~38 (16 x (FADD + SHF)) -- and with 32 independent rows per warp such
+// events hit 45 % of all chunk visits.  A best chunk that is demoted to runner-up keeps all 16 members.
+constexpr int SNAP_STRIDE = 512;      // float4 slots per quarter: one per epilogue thread
+__device__ __forceinline__ void top3_insert_snap(const float *vv, float cm, int cid, float4 *snap, float &m1, float &m2,
+                                                 float &m3, int &i1, int &i2) {
+    const bool p2 = cm > m2;
+    m3 = p2 ? m2 : fmaxf(m3, cm);
+    if (cm > m1) {
+        snap[0 * SNAP_STRIDE] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        snap[1 * SNAP_STRIDE] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+        snap[2 * SNAP_STRIDE] = make_float4(vv[8], vv[9], vv[10], vv[11]);
+        snap[3 * SNAP_STRIDE] = make_float4(vv[12], vv[13], vv[14], vv[15]);
+        m2 = m1; i2 = i1;
+        m1 = cm; i1 = cid;
+    } else {
+        m2 = p2 ? cm : m2; i2 = p2 ? cid : i2;
+    }
+}
+// members of the parked best chunk within tau_c of its maximum m1 (bit j = member j)
+__device__ __forceinline__ uint32_t top3_snapshot_mask(const float4 *snap, float m1, float tau_c) {
+    const float thr = m1 - tau_c;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int qd = 3; qd >= 0; --qd) {
+        const float4 f = snap[qd * SNAP_STRIDE];
+        bits = __funnelshift_l(__float_as_uint(f.w - thr), bits, 1);
+        bits = __funnelshift_l(__float_as_uint(f.z - thr), bits, 1);
+        bits = __funnelshift_l(__float_as_uint(f.y - thr), bits, 1);
+        bits = __funnelshift_l(__float_as_uint(f.x - thr), bits, 1);
+    }
+    return ~bits & 0xffffu;
+}
+
 // What survives of a filter record once the row's threshold has been applied: the chunks to visit, the
 // member masks and refine_decide's code.  16 bytes.
 struct __align__(16) RowRec { int32_t i1, i2; uint32_t masks; int32_t code; };
