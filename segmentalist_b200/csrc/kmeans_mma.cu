@@ -371,9 +371,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                             // every tile but the last: four full chunks, straight-line
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                float cm = v[c * 16];
-#pragma unroll
-                                for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
+                                const float cm = chunk_max16(&v[c * 16]);
                                 if (F8) top3_insert_snap(&v[c * 16], cm, cid0 + c, snap, m1, m2, m3, i1, i2);
                                 else top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
                             }

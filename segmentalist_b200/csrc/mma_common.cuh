@@ -232,6 +232,16 @@ __device__ __forceinline__ int refine_decide(const Cand &c, float tau, int n_chu
     return -1;
 }
 
+// Maximum of a 16-score chunk as a depth-3 tree of 3-input maxima (8 FMNMX3/FMNMX like the linear chain, but the
+// epilogue is latency-sensitive: four chunks x a chain of eight dependent instructions leave the schedulers idle).
+__device__ __forceinline__ float chunk_max16(const float *v) {
+    const float a0 = fmaxf(fmaxf(v[0], v[1]), v[2]), a1 = fmaxf(fmaxf(v[3], v[4]), v[5]);
+    const float a2 = fmaxf(fmaxf(v[6], v[7]), v[8]), a3 = fmaxf(fmaxf(v[9], v[10]), v[11]);
+    const float a4 = fmaxf(fmaxf(v[12], v[13]), v[14]);
+    const float b0 = fmaxf(fmaxf(a0, a1), a2), b1 = fmaxf(fmaxf(a3, a4), v[15]);
+    return fmaxf(b0, b1);
+}
+
 // Insert a chunk maximum into the running top-3.  A chunk that becomes the new BEST also records
 // which of its 16 members lie within tau_c of the chunk maximum (the only ones the refine has to
 // score); a chunk entering as runner-up keeps all 16 (it is only visited for the rare rows whose
