@@ -659,7 +659,7 @@ def test_frozen_fit_equals_reference_kmeans_fit(sb):
     npt.assert_array_equal(c.means, oc.means)
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, False, "fp8"])
 def test_mma_scorer_streamed_from_host(sb, fused):
     """Scoring embeddings uploaded chunk by chunk from pinned host memory (copy stream overlapped
     with scoring) gives the same bits as scoring the resident matrix; the
@@ -675,11 +675,16 @@ def test_mma_scorer_streamed_from_host(sb, fused):
     assign[:1500] = np.arange(1500) % K_max
     np.random.seed(1)
     comps = KMeansComponents(X, assign, K_max)
-    mma = MmaScorer(comps, fused=fused)
+    # "fp8": the two-kernel path with the e4m3 first level (what bench.py's end-to-end step runs by default)
+    mma = MmaScorer(comps, precision="fp8") if fused == "fp8" else MmaScorer(comps, fused=fused)
+    assert mma.fp8 == (fused == "fp8")
     val0 = torch.empty(n_emb, dtype=torch.float32, device="cuda")
     arg0 = torch.empty(n_emb, dtype=torch.int32, device="cuda")
     mma.score(val0, arg0)
     fb0 = int(mma.n_fallback.item())
+    val_e, arg_e = comps.best(None)                      # exact SIMT scorer on the resident matrix
+    npt.assert_array_equal(arg0.cpu().numpy(), arg_e.cpu().numpy())
+    npt.assert_array_equal(val0.cpu().numpy(), val_e.cpu().numpy())
     X_host = torch.from_numpy(np.ascontiguousarray(X)).pin_memory()
     comps._X.fill_(0.25)
     val1 = torch.full((n_emb,), -1.0, dtype=torch.float32, device="cuda")
