@@ -474,23 +474,35 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
     }
     __syncwarp();
 
-    // persistent warp: groups of G consecutive utterances (lane = utterance), grid-strided; the
-    // next group's offsets are requested before this group's copy is awaited and consumed
-    // after its compute.  The group's score rows are contiguous in HBM: ONE bulk copy.
-    const int n_groups = (p.n_utt + G - 1) / G;
-    auto group_offsets = [&](int g, int64_t &o0, int64_t &o1, bool &valid) {
-        const int u_local = g * G + lane;
-        valid = g < n_groups && lane < G && u_local < p.n_utt;
-        const int u = p.utt_first + (valid ? u_local : 0);
+    // persistent warp: a contiguous range of utterances, worked off in groups of consecutive utterances
+    // (lane = utterance); the next group's offsets are requested before this group's copy is awaited and
+    // consumed after its compute.  The group's score rows are contiguous in HBM: ONE bulk copy.
+    // A group takes as many utterances (<= 32) as fit the staging buffers (G * N_cap landmarks): the buffers
+    // are sized for G utterances of the LONGEST length, so with average-length utterances all 32 lanes work
+    // (round 1 always took G = 26 of them: 8 rounds per warp at 200k utterances instead of 7).
+    const int u_lo = (int)((long long)blockIdx.x * p.n_utt / gridDim.x);
+    const int u_hi = (int)((long long)(blockIdx.x + 1) * p.n_utt / gridDim.x);
+    // every lane runs to the group's longest utterance and prefetches SB rows ahead, i.e. it reads up to N_cap + SB rows
+    // past ITS OWN start: the group's rows must end N_cap rows before the end of the staging buffer (G * N_cap + S + 1)
+    const int budget = (G - 1) * N_cap;
+    auto group_offsets = [&](int u_start, int64_t &o0, int64_t &o1, bool &valid) {
+        const int idx = u_start + lane;
+        const bool in_range = idx < u_hi;
+        const int u = p.utt_first + (in_range ? idx : u_hi - 1);      // out-of-range lanes re-read the last utterance
         o0 = p.pos_off[u];
         o1 = p.pos_off[u + 1];
+        const int64_t base = __shfl_sync(FULL, o0, 0);
+        valid = in_range && (o1 - base) <= budget;                     // a prefix of the lanes (offsets ascend)
     };
-    int64_t off, o1, off_next, o1_next;
-    bool valid, valid_next;
-    group_offsets(blockIdx.x, off, o1, valid);
+    int64_t off = 0, o1 = 0, off_next = 0, o1_next = 0;
+    bool valid = false, valid_next = false;
+    int u_start = u_lo;
+    if (u_start < u_hi) group_offsets(u_start, off, o1, valid);
     int N = valid ? (int)(o1 - off) : 0;
     uint32_t parity = 0;
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    while (u_start < u_hi) {
+        const int n_here = __popc(__ballot_sync(FULL, valid));        // >= 1: one utterance always fits
+        const int u_next = u_start + n_here;
         const int64_t off0 = __shfl_sync(FULL, off, 0);
         int64_t end = valid ? off + N : 0;
         // uniform trip count: every lane runs to the longest utterance of the group
@@ -511,9 +523,10 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
                 mma::mbar_arrive(bar);
             }
         }
-        group_offsets(g + gridDim.x, off_next, o1_next, valid_next);
+        valid_next = false;
+        if (u_next < u_hi) group_offsets(u_next, off_next, o1_next, valid_next);
         const double *sc = sc_s + (valid ? (off - off0) * SB : 0);
-        const int u_local = g * G + lane;
+        const int u_local = u_start + lane;
         // boundary bytes are staged with the same 4-byte phase as their destination in HBM
         uint8_t *bo = p.bounds + off0;
         const int phase = (int)((uintptr_t)bo & 3);
@@ -626,6 +639,7 @@ __global__ void __launch_bounds__(32) dp_staged_kernel(DpParams p) {
         }
         __syncwarp();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // slots are rewritten by the copy engine
+        u_start = u_next;
         off = off_next;
         valid = valid_next;
         N = valid ? (int)(o1_next - off_next) : 0;
@@ -658,7 +672,7 @@ int launch_dp(const segb_corpus *c, int32_t utt_first, int32_t n_utt, const doub
         if (!scores_local && !u_counter && n_utt >= 32 && (c->S % 2) == 0 && Wlim == c->S && G >= 16 &&
             ((uintptr_t)scores & 15) == 0 && st_smem <= 72 * 1024 && !(alphas && !al_smem)) {
             p.group = G;
-            const int groups = (n_utt + G - 1) / G;
+            const int groups = (n_utt + 31) / 32;               // warps worth launching: each takes a contiguous range
             auto launch = [&](auto kern) -> int {
                 // resident warps per device for this (kernel, shared-memory size, device): queried when
                 // any of the three changes (the shared-memory opt-in is a per-device function attribute);
