@@ -237,14 +237,19 @@ class MmaScorer(object):
 class FrozenKMeansSweep(object):
 
     # precision of the tensor-core scorer's first-level filter: "fp16", "fp8" (e4m3 first level, fp16 second level) or
-    # "auto" = start in e4m3 and fall back to fp16 for good once a sweep leaves more than AUTO_FP16_FRACTION of the rows to
-    # the second level (a diffuse model: the e4m3 pass would only add work).  Results are bit-identical in every mode.
+    # "auto" = start in e4m3 and fall back to fp16 once a sweep leaves more than AUTO_FP16_FRACTION of the rows to the
+    # second level (a diffuse model: the e4m3 pass would only add work); the e4m3 level is tried again after
+    # AUTO_RETRY_SWEEPS sweeps (a model that has converged to separated components is served better by it), with the
+    # interval doubling after every failed retry.  Results are bit-identical in every mode.
     AUTO_FP16_FRACTION = 0.35
+    AUTO_RETRY_SWEEPS = 8
 
     def __init__(self, components, corpus, wip=0.0, scorer="auto", fused=None, precision="auto"):
         self.c, self.corpus, self.wip = components, corpus, float(wip)
         assert precision in ("auto", "fp16", "fp8")
         self.precision_mode = precision
+        self._auto_interval = self.AUTO_RETRY_SWEEPS        # sweeps to stay in fp16 before e4m3 is tried again
+        self._auto_countdown = 0
         lib = _lib.lib()
         c = components
         if scorer == "auto":
@@ -412,13 +417,23 @@ class FrozenKMeansSweep(object):
         self.K_host = K_now
         if self.mma is not None and not self.mma.fused:
             self.mma.max_rounds = self.mma.rounds_for(2 * n_fb + 4096)
-        if (self.precision_mode == "auto" and self.mma is not None and self.mma.fp8 and
-                n_fb > self.AUTO_FP16_FRACTION * c.N):
-            # the e4m3 pass decided too little: this model is served better by the fp16 first level
-            timing = self.mma.timing
-            self.mma = None                                 # release the e4m3 image before the fp16 one is built
-            self.mma = MmaScorer(c, fused=self._fused, precision="fp16")
-            self.mma.timing = timing
+        if self.precision_mode == "auto" and self.mma is not None and not self.mma.fused and c.D % 2 == 0:
+            switch_to = None
+            if self.mma.fp8 and n_fb > self.AUTO_FP16_FRACTION * c.N:
+                # the e4m3 pass decided too little: this model is served better by the fp16 first level -- for a while
+                switch_to, self._auto_countdown = "fp16", self._auto_interval
+                self._auto_interval = min(2 * self._auto_interval, 1 << 20)
+            elif not self.mma.fp8:
+                self._auto_countdown -= 1
+                if self._auto_countdown <= 0:
+                    switch_to = "fp8"                        # try the e4m3 level again
+            elif self.mma.fp8 and n_fb <= self.AUTO_FP16_FRACTION * c.N:
+                self._auto_interval = self.AUTO_RETRY_SWEEPS  # e4m3 works: a later fallback starts with a short interval
+            if switch_to is not None:
+                timing = self.mma.timing
+                self.mma = None                             # release one image of X before the other one is built
+                self.mma = MmaScorer(c, fused=self._fused, precision=switch_to)
+                self.mma.timing = timing
         # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time)
         total = float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
         if _dist_on():

@@ -633,6 +633,36 @@ def test_mma_scorer_fp8_first_level(sb, K_max, n_emb, K_true, noise, data):
         assert n_fb > n_emb // 2                       # near-duplicates: second level
 
 
+def test_frozen_sweep_auto_precision_policy(sb):
+    """precision="auto": a diffuse model (many near-duplicate components) leaves most rows to the second level, so the
+    sweep falls back to the fp16 first level, retries e4m3 after AUTO_RETRY_SWEEPS sweeps, falls back again with a
+    doubled interval -- and every sweep gives exactly what the fp16-only sweep gives."""
+    from segmentalist_b200 import kmeans_acoustic_wordseg as kaw, synth
+    from segmentalist_b200.batch import FrozenKMeansSweep
+    mats, vids, durs, lms = synth.make_corpus_dicts(120, D=130, K_true=4, n_min=8, n_max=14, n_slices_max=4, seed=21)
+
+    def build(precision):
+        random.seed(5)
+        np.random.seed(5)
+        seg = kaw.KMeansAcousticWordseg(96, mats, vids, durs, lms, n_slices_max=4, init_am_assignments="spread")
+        return seg, FrozenKMeansSweep(seg.acoustic_model.components, seg._corpus, wip=seg.wip, scorer="mma",
+                                      precision=precision)
+    seg_a, sw_a = build("auto")
+    seg_h, sw_h = build("fp16")
+    sw_a.AUTO_RETRY_SWEEPS = 2
+    sw_a._auto_interval = 2
+    modes = []
+    for _ in range(9):
+        modes.append("fp8" if sw_a.mma.fp8 else "fp16")
+        ta, th = sw_a.sweep(), sw_h.sweep()
+        assert ta == th
+        npt.assert_array_equal(seg_a._corpus.bounds.cpu().numpy(), seg_h._corpus.bounds.cpu().numpy())
+        npt.assert_array_equal(seg_a.acoustic_model.components.assignments, seg_h.acoustic_model.components.assignments)
+        npt.assert_array_equal(seg_a.acoustic_model.components.means, seg_h.acoustic_model.components.means)
+    # e4m3, then 2 sweeps of fp16, retry, then 4 sweeps of fp16, retry
+    assert modes == ["fp8", "fp16", "fp16", "fp8", "fp16", "fp16", "fp16", "fp16", "fp8"], modes
+
+
 def test_frozen_fit_equals_reference_kmeans_fit(sb):
     """FrozenKMeansSweep.fit (sharded hard-assignment E-step + all-reduce M-step) == the reference's
     KMeans.fit(n, consider_unassigned=False) (kmeans.py:97-173) applied to the segmenter's tokens."""
