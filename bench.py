@@ -786,7 +786,7 @@ def fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed):
     from segmentalist_b200.batch import FvScorer
     from segmentalist_b200.gaussian_components_fixedvar import FixedVarPrior, GaussianComponentsFixedVar
     out = {}
-    for aniso in (False, True):
+    for aniso, prec in ((False, "fp16"), (False, "fp8"), (True, "fp16")):
         n_fv = min(M, (4 if not aniso else 1) * 1024 * 1024)
         rng = np.random.RandomState(0)
         var = 0.002 * (0.5 + rng.rand(D)) if aniso else 0.002 * np.ones(D)
@@ -801,8 +801,9 @@ def fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed):
         rank_of = np.empty(args.K, dtype=np.int64)
         rank_of[zh[np.sort(first)]] = np.arange(len(first))
         am.components._add_many(np.arange(n_tok), rank_of[zh])
-        fv = FvScorer(am.components)
+        fv = FvScorer(am.components, precision=prec)
         fv.score()
+        pk_tf, pk_src = (2.0 * peak_tf, "2 x " + peak_src + " (e4m3 rate; no measured fp8 entry)") if fv.fp8 else (peak_tf, peak_src)
         if fv.fused:
             t_pack, t_filter, t_refine = timed(fv.pack_model, 3), timed(fv.fused_score, 3), 0.0
         else:
@@ -813,22 +814,28 @@ def fv_logmarg_roofline(args, X, Z, M, peak_tf, peak_src, timed):
         got = fv.log_marg[torch.from_numpy(ids).to(fv.log_marg.device)].cpu().numpy()
         rel = float((np.abs(got - exact) / np.abs(exact)).max())
         kp = 16 * ((D + (3 if aniso else 6) + 15) // 16) * (2 if aniso else 1)
+        if fv.fp8:
+            kp = 32 * ((D + 21 + 31) // 32)
         r = {"kernel": ("score_fused_kernel<fv> (fp32 rows in, ONE fp16 tcgen05 pass, exact float64 re-scoring of the kept "
                         "components + logsumexp behind the GEMM: the whole log_marg_i step)" if fv.fused else
+                        "kmeans_filter_kernel<5,1,0,F8> as the log_marg_i filter (ONE e4m3 tcgen05 pass, kind::f8f6f4) + fv_refine_kernel "
+                        "(exact float64 re-scoring of the kept components, logsumexp); undecided rows -> exhaustive scan" if fv.fp8 else
                         "kmeans_filter_kernel<%s> as the log_marg_i filter (ONE fp16 tcgen05 pass, fp32 TMEM, top-3 chunk epilogue) "
                         "+ fv_refine_kernel (exact float64 re-scoring of the kept components, logsumexp)" % ("9,2" if aniso else "9,1")),
-             "bound": "tensor", "achieved": fl / (t_filter * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-             "frac": fl / (t_filter * 1e-3) / 1e12 / peak_tf, "peak_source": peak_src,
+             "bound": "tensor", "achieved": fl / (t_filter * 1e-3) / 1e12, "peak": pk_tf, "unit": "TFLOP/s",
+             "frac": fl / (t_filter * 1e-3) / 1e12 / pk_tf, "peak_source": pk_src,
              "kernel_ms": t_filter, "refine_ms": t_refine, "pack_model_ms": t_pack,
-             "frac_incl_refine_and_pack": fl / ((t_filter + t_refine + t_pack) * 1e-3) / 1e12 / peak_tf,
+             "frac_incl_refine_and_pack": fl / ((t_filter + t_refine + t_pack) * 1e-3) / 1e12 / pk_tf,
              "rows": n_fv, "K": args.K, "K_active": am.components.K, "anisotropic_variances": aniso,
              "algorithmic_flops_per_launch": fl,
              "algorithmic_flops_note": "%d*D per segment x component evaluation (SURVEY 8d)" % (4 if aniso else 2),
              "executed_tflops": 2.0 * kp * n_fv * 128 * ((args.K + 1 + 127) // 128) / (t_filter * 1e-3) / 1e12,
              "fallback_rows": int(fv.n_fallback.item()), "max_rel_err_vs_exact_float64": rel,
              "threshold_nats": fv.T}
-        if not aniso:
-            tr = ncu_traffic("score_fused_kernel_fv" if fv.fused else "fv_filter_kernel")
+        if fv.fp8:
+            out["e4m3_first_level"] = r
+        elif not aniso:
+            tr = ncu_traffic("score_fused_kernel_fv" if fv.fused else "kmeans_filter_kernel@r2_raw_fv.csv")
             r["traffic"] = tr["bytes_per_launch"] if (tr and args.K == K_MAX and n_fv == 4 * 1024 * 1024) else None
             r["traffic_source"] = tr.get("source") if tr else None
             r["algorithmic_bytes_per_launch"] = float(n_fv * D * 4 + 12 * n_fv) if fv.fused else float(fv.x_tiles.numel() + fv.cand.numel())

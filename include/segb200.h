@@ -439,6 +439,28 @@ int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, int
                     const void *cand, const float *x_err, const float *w_max, float T, void *work,
                     double *log_marg, int32_t *map_k, void *rec_out, int64_t *n_fallback, void *stream);
 
+/* e4m3 FIRST LEVEL of the same filter (isotropic variances; kind::f8f6f4).  Operands are scaled by powers of two (sx
+ * for the embeddings, alpha for |x|^2 -- callers pick the largest ones with sx * max|x_d| <= 448, sx * max|x| <= 448 and
+ * alpha * max|x|^2 <= 448; the weight scale is chosen on the device from the model); constants ride in two-term e4m3
+ * splits and dead model rows are pushed out of reach by sixteen +-448 columns.  The bound (lse_bound8, measured rounding
+ * errors) is ~40 nats at p ~ 500, so with T = 20 the pass decides rows whose best component is > 100 nats ahead of the
+ * fourth-best chunk -- a trained model; other rows take the exhaustive exact scan (n_fallback): callers watch that
+ * count and go back to segb_fvf_* when it is not small.  Call order: segb_fvf_pack_model(aniso = 0) [exact row tables,
+ * w_max16] -> segb_fvf8_pack_model -> segb_fvf8_filter -> segb_fvf8_refine.  log_marg_i / MAP slot / row records as
+ * segb_fvf_refine.  w_err8: segb_fvf8_w_err_bytes(); w_max8 [8].                                                        */
+int64_t segb_fvf8_x_tiles_bytes(int64_t n_emb, int32_t D);
+int64_t segb_fvf8_w_tiles_bytes(int32_t K_max, int32_t D);
+int64_t segb_fvf8_w_err_bytes(int32_t K_max);
+int segb_fvf8_pack_x(const float *X, int64_t n_emb, int32_t D, float sx, float alpha, void *x_tiles8, float *x_err8,
+                     float *x_max8, void *stream);
+int segb_fvf8_pack_model(int32_t K_max, int32_t D, const void *model, const float *w_max16, float sx, float alpha,
+                         void *w_tiles8, float *w_err8, float *w_max8, void *stream);
+int segb_fvf8_filter(const void *x_tiles8, const void *w_tiles8, int64_t n_emb, int32_t K_max, int32_t D,
+                     const float *x_max8, const float *w_max8, float sx, float alpha, float T, void *cand, void *stream);
+int segb_fvf8_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, const void *model, const void *cand,
+                     const float *x_err8, const float *w_max8, float sx, float alpha, float T, void *work,
+                     double *log_marg, int32_t *map_k, void *rec_out, int64_t *n_fallback, void *stream);
+
 /* ------------------------------------------------------------------ fused scoring: fp32 embeddings in, results out */
 
 /* The same two scorers as ONE kernel that reads the fp32 embeddings once (csrc/score_fused.cu): four aux warps

@@ -118,6 +118,14 @@ _PROTOS = {
     "segb_fvf_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, ctypes.c_float, c_vp, c_vp]),
     "segb_fvf_refine": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, ctypes.c_float,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fvf8_x_tiles_bytes": (c_i64, [c_i64, c_i32]),
+    "segb_fvf8_w_tiles_bytes": (c_i64, [c_i32, c_i32]),
+    "segb_fvf8_w_err_bytes": (c_i64, [c_i32]),
+    "segb_fvf8_pack_x": (ctypes.c_int, [c_vp, c_i64, c_i32, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fvf8_pack_model": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
+    "segb_fvf8_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp]),
+    "segb_fvf8_refine": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp]),
     "segb_fused_kmeans_best": (ctypes.c_int, [ctypes.POINTER(KMeansM), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "segb_fused_fv_log_marg": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, ctypes.c_float, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp]),

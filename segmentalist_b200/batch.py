@@ -510,9 +510,10 @@ class FvScorer(object):
     (see MmaScorer for the trade-off).
     keep_records: also keep the 16-byte thresholded row records (needed to DRAW components afterwards)."""
 
-    def __init__(self, components, T=LSE_T, fused=None, keep_records=False):
+    def __init__(self, components, T=LSE_T, fused=None, keep_records=False, precision="fp16"):
         lib, c, dev = _lib.lib(), components, "cuda"
         assert c._X.dtype == torch.float32, "tensor-core log_marg needs float32 embeddings"
+        assert precision in ("fp16", "fp8")
         self.c, self.T = c, float(T)
         self.aniso = int(_is_aniso(c))
         can_fuse = (not self.aniso) and fused_supported(c.D)
@@ -527,8 +528,22 @@ class FvScorer(object):
         self.map_k = torch.empty(c.N, dtype=torch.int32, device=dev)
         self.recs = torch.empty(16 * c.N, dtype=u8, device=dev) if keep_records else None
         self.x_tiles = self.cand = self.x_err = self.x_max = None
-        if not self.fused:
+        # precision="fp8": e4m3 first level (segb_fvf8_*; isotropic variances, two-kernel path).  Rows it cannot decide
+        # take the exhaustive scan, so callers watch n_fallback (FrozenFBGMMSweep falls back to fp16 by itself).
+        self.fp8 = precision == "fp8" and not self.fused and not self.aniso
+        if self.fp8:
+            self.sx = MmaScorer.pick_scale(c._X)
+            n2_max = 0.0
+            for i in range(0, c.N, 1 << 20):
+                n2_max = max(n2_max, float((c._X[i:i + (1 << 20)].double() ** 2).sum(dim=1).max()))
+            self.alpha = float(2.0 ** min(40.0, np.floor(np.log2(448.0 / max(n2_max, 1e-30)))))
+            self.x_tiles = torch.empty(lib.segb_fvf8_x_tiles_bytes(c.N, c.D), dtype=u8, device=dev)
+            self.w_tiles8 = torch.empty(lib.segb_fvf8_w_tiles_bytes(c.K_max, c.D), dtype=u8, device=dev)
+            self.w_err8 = torch.empty(lib.segb_fvf8_w_err_bytes(c.K_max), dtype=u8, device=dev)
+            self.w_max8 = torch.zeros(8, dtype=torch.float32, device=dev)
+        elif not self.fused:
             self.x_tiles = torch.empty(lib.segb_fvf_x_tiles_bytes(c.N, c.D, self.aniso), dtype=u8, device=dev)
+        if not self.fused:
             self.cand = torch.empty(lib.segb_mma_cand_bytes(c.N), dtype=u8, device=dev)
             self.x_err = torch.empty(2 * c.N, dtype=torch.float32, device=dev)
             self.x_max = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -536,21 +551,41 @@ class FvScorer(object):
 
     def pack_x(self):
         c = self.c
+        if self.fp8:
+            _lib.check(_lib.lib().segb_fvf8_pack_x(_lib.ptr(c._X), c.N, c.D, self.sx, self.alpha, _lib.ptr(self.x_tiles),
+                                                   _lib.ptr(self.x_err), _lib.ptr(self.x_max), _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().segb_fvf_pack_x(_lib.ptr(c._X), c.N, c.D, self.aniso, _lib.ptr(self.x_tiles),
                                               _lib.ptr(self.x_err), _lib.ptr(self.x_max), _lib.stream_ptr()))
 
     def pack_model(self):
         _lib.check(_lib.lib().segb_fvf_pack_model(self.c.struct(), self.aniso, _lib.ptr(self.w_tiles),
                                                   _lib.ptr(self.model), _lib.ptr(self.w_max), _lib.stream_ptr()))
+        if self.fp8:
+            c = self.c
+            _lib.check(_lib.lib().segb_fvf8_pack_model(c.K_max, c.D, _lib.ptr(self.model), _lib.ptr(self.w_max), self.sx,
+                                                       self.alpha, _lib.ptr(self.w_tiles8), _lib.ptr(self.w_err8),
+                                                       _lib.ptr(self.w_max8), _lib.stream_ptr()))
 
     def filter(self):
         c = self.c
+        if self.fp8:
+            _lib.check(_lib.lib().segb_fvf8_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles8), c.N, c.K_max, c.D,
+                                                   _lib.ptr(self.x_max), _lib.ptr(self.w_max8), self.sx, self.alpha, self.T,
+                                                   _lib.ptr(self.cand), _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().segb_fvf_filter(_lib.ptr(self.x_tiles), _lib.ptr(self.w_tiles), c.N, c.K_max, c.D,
                                               self.aniso, _lib.ptr(self.x_max), _lib.ptr(self.w_max), self.T,
                                               _lib.ptr(self.cand), _lib.stream_ptr()))
 
     def refine(self):
         c = self.c
+        if self.fp8:
+            _lib.check(_lib.lib().segb_fvf8_refine(_lib.ptr(c._X), c.N, c.D, c.K_max, _lib.ptr(self.model), _lib.ptr(self.cand),
+                                                   _lib.ptr(self.x_err), _lib.ptr(self.w_max8), self.sx, self.alpha, self.T,
+                                                   _lib.ptr(self.work), _lib.ptr(self.log_marg), _lib.ptr(self.map_k),
+                                                   _lib.ptr(self.recs), _lib.ptr(self.n_fallback), _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().segb_fvf_refine(_lib.ptr(c._X), c.N, c.D, c.K_max, self.aniso, _lib.ptr(self.model),
                                               _lib.ptr(self.cand), _lib.ptr(self.x_err), _lib.ptr(self.w_max), self.T,
                                               _lib.ptr(self.work), _lib.ptr(self.log_marg), _lib.ptr(self.map_k),
@@ -583,9 +618,17 @@ class FrozenFBGMMSweep(object):
     their embeddings) shard over ranks; ONE all-reduce of [sum_x | counts] per sweep, like the k-means
     sweep.  Semantics pinned by the test oracle's frozen_fbgmm_sweep."""
 
-    def __init__(self, components, corpus, fb_type="standard", time_power_term=1.0, wip=0.0, T=LSE_T, fused=None):
+    # precision of the scorer's first-level filter: "fp16", "fp8" (e4m3; isotropic variances) or "auto" = e4m3 until a
+    # sweep leaves more than AUTO_FP16_FRACTION of the rows undecided (they take the exhaustive scan, which is slow: the
+    # e4m3 pass only serves trained models), then fp16 for good.  Same results in every mode.
+    AUTO_FP16_FRACTION = 0.002
+
+    def __init__(self, components, corpus, fb_type="standard", time_power_term=1.0, wip=0.0, T=LSE_T, fused=None,
+                 precision="auto"):
         self.c, self.corpus = components, corpus
         assert fb_type in ("standard", "viterbi")
+        assert precision in ("auto", "fp16", "fp8")
+        self.precision_mode = precision
         self.fb_type, self.tpt, self.wip = fb_type, float(time_power_term), float(wip)
         lib, c, cp, dev = _lib.lib(), components, corpus, "cuda"
         self.lms_range_ok = True
@@ -594,7 +637,9 @@ class FrozenFBGMMSweep(object):
             # widen the threshold by the largest possible difference between the two rankings
             n_tok = max(1, int(cp.n_pos))
             T = T + abs(1.0 - c._lms) * float(np.log((c._alpha / c.K_max + n_tok) / (c._alpha / c.K_max)))
-        self.fv = FvScorer(c, T, fused=fused, keep_records=(fb_type == "standard"))
+        self._fv_args = (T, fused, fb_type == "standard")
+        self.fv = FvScorer(c, T, fused=fused, keep_records=(fb_type == "standard"),
+                           precision="fp16" if precision == "fp16" else "fp8")
         self.scores = torch.empty(cp.n_pos * cp.S, dtype=torch.float64, device=dev)
         self.log_prob = torch.zeros(cp.n_utt, dtype=torch.float64, device=dev)
         self.status = torch.zeros(cp.n_utt, dtype=torch.int32, device=dev)
@@ -711,6 +756,10 @@ class FrozenFBGMMSweep(object):
         assert n_bad == 0, "segmentation failed for %d utterances (status %s)" % (
             n_bad, np.unique(self.status.cpu().numpy()))
         self.last_fallback, self.K_host = n_fb, K_now
+        if self.precision_mode == "auto" and self.fv.fp8 and n_fb > self.AUTO_FP16_FRACTION * c.N:
+            T_, fused_, keep_ = self._fv_args
+            self.fv = None                                   # release the e4m3 image before the fp16 one is built
+            self.fv = FvScorer(c, T_, fused=fused_, keep_records=keep_, precision="fp16")
         lp = self.log_prob.cpu().numpy()
         total = float(np.cumsum(lp)[-1]) if cp.n_utt else 0.0          # utterance-order float64 sum
         if _dist_on():

@@ -22,6 +22,7 @@
 // inside the threshold (flat posteriors) get an exhaustive exact scan.  Result: log_marg_i to ~1e-7
 // absolute (north star: 1e-4 relative) at one tensor pass instead of three, plus the exact MAP
 // component of every embedding for free.
+#include <cuda_fp8.h>
 #include "mma_common.cuh"
 #include "fv_refine.cuh"
 
@@ -222,6 +223,180 @@ __global__ void wmax4_kernel(const float *w_err, int n_rows, float *w_max) {
     }
 }
 
+
+// ---------------------------------------------------------------- e4m3 first level (isotropic variances)
+// The same filter with e4m3 operands (kind::f8f6f4: twice the MMA rate; the fp16 pass is power-bound).  Scaled space:
+// features sx * x, weights sw * p_k mu_k; five constant columns carry A_k = 256 (a0 + a1) and -p_k/2 |x|^2 =
+// (u0 + u1)(v0 + v1) - u1 v1 in two-term e4m3 splits; sixteen further columns (x side 448, dead model rows -448)
+// give dead rows a score no live row can reach, which e4m3's range would not allow in a single constant.
+// lse_bound8 (mma_common.cuh) is rigorous for what is measured here; with T = 20 nats the threshold is ~100 nats, so
+// the pass decides the rows of a TRAINED model (best component > 100 nats ahead of the fourth-best chunk) and leaves
+// the rest to the exhaustive scan -- callers fall back to the fp16 first level when that happens too often.
+__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+__device__ __forceinline__ float from_e4m3(uint8_t b) { return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3))); }
+constexpr float FV8_CA = 256.0f, FV8_DEAD = 448.0f;
+constexpr int FV8_NCONST = 5, FV8_NDEAD = 16;
+
+__device__ __forceinline__ int tile_off8(int r, int c) {                     // 1-byte elements: 16 per core-matrix row
+    return ((c >> 4) * (TILE_ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (c & 15);
+}
+
+// sw = the largest power of two that keeps the scaled weights, the A constants and the v constants inside e4m3
+// (w_max16 = (eW, nW, |A|, p/2) of the fp16 packing pass); scales[0] = sw
+__global__ void fv8_scales_kernel(const float *w_max16, float sx, float alpha, float *scales) {
+    const float nW = fmaxf(w_max16[1], 1e-30f), Aabs = fmaxf(w_max16[2], 1e-30f), ph = fmaxf(w_max16[3], 1e-30f);
+    const float lim = fminf(fminf(FV8_DEAD / nW, FV8_DEAD * alpha / (sx * ph)), FV8_DEAD * FV8_CA / (sx * Aabs));
+    int e = (int)floorf(log2f(lim));
+    e = e < -40 ? -40 : (e > 40 ? 40 : e);
+    scales[0] = ldexpf(1.0f, e);
+}
+
+// X image, one warp per row: [e4m3(sx x) (D), 256, 256, u0, u0, u1, 448 x 16, 0..], u = alpha |x|^2.
+// err[2r] = |sx x - e4m3(sx x)|_2, err[2r+1] = |sx x|_2.
+__global__ void pack_x8_kernel(const float *X, int64_t n_emb, int64_t n_rows_pad, int D, int KP, float sx, float alpha,
+                               uint8_t *tiles, float *err, float *x_max) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows_pad) return;
+    uint8_t *base = tiles + (row / TILE_ROWS) * ((int64_t)TILE_ROWS * KP);
+    const int r = (int)(row % TILE_ROWS);
+    const bool live = row < n_emb;
+    const float *xr = X + row * D;
+    double n2 = 0.0;
+    if (live) for (int d = lane; d < D; d += 32) { const double v = xr[d]; n2 += v * v; }
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+    const float u = (float)(alpha * n2);
+    const bool bad_u = !(u <= FV8_DEAD);
+    const uint8_t u0 = to_e4m3(u), u1 = to_e4m3(u - from_e4m3(u0));
+    float e2 = 0.f, f2 = 0.f;
+    for (int ch = lane; ch < KP / 16; ch += 32) {
+        __align__(16) uint8_t hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = ch * 16 + j;
+            uint8_t q = 0;
+            if (live) {
+                if (c < D) {
+                    const float v = xr[c] * sx;
+                    q = to_e4m3(v);
+                    const float dl = v - from_e4m3(q);
+                    e2 += dl * dl; f2 += v * v;
+                } else {
+                    const int ecol = c - D;
+                    if (ecol < 2) q = to_e4m3(FV8_CA);
+                    else if (ecol == 2 || ecol == 3) q = u0;
+                    else if (ecol == 4) q = u1;
+                    else if (ecol < FV8_NCONST + FV8_NDEAD) q = to_e4m3(FV8_DEAD);
+                }
+            }
+            hv[j] = q;
+        }
+        *reinterpret_cast<uint4 *>(base + tile_off8(r, ch * 16)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); f2 += __shfl_xor_sync(FULL, f2, o); }
+    if (lane == 0 && live) {
+        float eF = sqrtf(e2) * 1.0001f, nF = sqrtf(f2) * 1.0001f;
+        if (bad_u || !(eF < CUDART_INF_F) || !(nF < CUDART_INF_F)) eF = nF = CUDART_INF_F;     // never decided by this pass
+        err[2 * row] = eF;
+        err[2 * row + 1] = nF;
+        atomicMax(reinterpret_cast<int *>(x_max), __float_as_int(eF));
+        atomicMax(reinterpret_cast<int *>(x_max) + 1, __float_as_int(nF));
+    }
+}
+
+// Model image from the exact row tables of pack_w_kernel, one warp per (virtual) component:
+// [e4m3(sw p mu) (D), a0, a1, v0, v1, v0, dead ? -448 : 0 (x 16), 0..], a = S A / 256, v = -S (p / 2) / alpha.
+// w_err8[8r..] = (eW, nW, |S A|, 256 |a - a0 - a1|, |v|, |v1|, |v - v0 - v1|, 0).
+__global__ void pack_w8_kernel(const double *model_rows, int K_max, int D, int KP, int rows_pad_, float sx, float alpha,
+                               const float *scales, uint8_t *tiles, float *w_err8) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows_pad_) return;
+    const ModelRows t = model_view(model_rows, K_max, D, 0);
+    const int Kr = K_max + 1;
+    const float sw = scales[0];
+    const double S = (double)sx * sw;
+    uint8_t *base = tiles + (int64_t)(row / NT_COLS) * ((int64_t)TILE_ROWS * KP);
+    const int r = row % NT_COLS;
+    const bool alive = row < Kr && t.cst_lse[row] > -CUDART_INF;
+    double p = 0.0, A = 0.0;
+    if (alive) {
+        p = t.pk[row];
+        double m2 = 0.0;
+        for (int d = lane; d < D; d += 32) { const double mu = t.mu[(size_t)row * D + d]; m2 += mu * mu; }
+        for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(FULL, m2, o);
+        A = t.cst_lse[row] - 0.5 * p * m2;
+    }
+    const float a = (float)(S * A / FV8_CA), v = (float)(-S * 0.5 * p / alpha);
+    const uint8_t a0 = to_e4m3(a), a1 = to_e4m3(a - from_e4m3(a0));
+    const uint8_t v0 = to_e4m3(v), v1 = to_e4m3(v - from_e4m3(v0));
+    const float dA = FV8_CA * fabsf(a - from_e4m3(a0) - from_e4m3(a1)) * 1.0001f + (float)fabs(S * A) * 2e-7f;
+    const float dv = fabsf(v - from_e4m3(v0) - from_e4m3(v1)) * 1.0001f + fabsf(v) * 2e-7f;
+    float e2 = 0.f, n2 = 0.f;
+    for (int ch = lane; ch < KP / 16; ch += 32) {
+        __align__(16) uint8_t hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = ch * 16 + j;
+            uint8_t q = 0;
+            if (c < D) {
+                if (alive) {
+                    const double w = p * t.mu[(size_t)row * D + c] * sw;
+                    q = to_e4m3((float)w);
+                    const float dq = from_e4m3(q), dl = (float)(w - (double)dq);
+                    e2 += dl * dl; n2 += dq * dq;
+                }
+            } else {
+                const int ecol = c - D;
+                if (alive) {
+                    if (ecol == 0) q = a0;
+                    else if (ecol == 1) q = a1;
+                    else if (ecol == 2 || ecol == 4) q = v0;
+                    else if (ecol == 3) q = v1;
+                } else if (ecol >= FV8_NCONST && ecol < FV8_NCONST + FV8_NDEAD) q = to_e4m3(-FV8_DEAD);
+            }
+            hv[j] = q;
+        }
+        *reinterpret_cast<uint4 *>(base + tile_off8(r, ch * 16)) = *reinterpret_cast<const uint4 *>(hv);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_xor_sync(FULL, e2, o); n2 += __shfl_xor_sync(FULL, n2, o); }
+    if (lane == 0) {
+        float eW = sqrtf(e2) * 1.0001f;
+        const bool sat = !(fabsf(a) <= FV8_DEAD) || !(fabsf(v) <= FV8_DEAD);      // constants outside e4m3: the bound is void
+        if (sat || !(eW < CUDART_INF_F)) eW = CUDART_INF_F;
+        float *o = w_err8 + 8 * (size_t)row;
+        o[0] = alive ? eW : 0.f;
+        o[1] = alive ? sqrtf(n2) * 1.0001f : 0.f;
+        o[2] = alive ? (float)fabs(S * A) * 1.0001f : 0.f;
+        o[3] = alive ? dA : 0.f;
+        o[4] = alive ? fabsf(v) * 1.0001f : 0.f;
+        o[5] = alive ? fabsf(from_e4m3(v1)) : 0.f;
+        o[6] = alive ? dv : 0.f;
+        o[7] = 0.f;
+    }
+}
+
+// model-wide maxima of the seven per-row quantities -> w_max8[0..6]; w_max8[7] = sw
+__global__ void wmax8_kernel(const float *w_err8, int n_rows, const float *scales, float *w_max8) {
+    __shared__ float red[8][32];
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = threadIdx.x; k < n_rows; k += blockDim.x)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], w_err8[8 * (size_t)k + q]);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        for (int o = 16; o > 0; o >>= 1) v[q] = fmaxf(v[q], __shfl_xor_sync(FULL, v[q], o));
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) red[q][threadIdx.x >> 5] = v[q];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float x = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) x = fmaxf(x, red[threadIdx.x][i]);
+        w_max8[threadIdx.x] = threadIdx.x == 7 ? scales[0] : x;
+    }
+}
+
 // ---------------------------------------------------------------- exact refine
 
 // Eight lanes per embedding (four per warp): the filter record names the candidate chunks and members;
@@ -231,7 +406,8 @@ template <bool ANISO>
 __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
     const float *X, int D, int K_max, const double *model_rows, const Cand *cand, const float *x_err,
     const float *w_max, int KP, float T, int64_t n_emb, int n_chunks, double *log_marg, int32_t *map_k,
-    RowRec *rec_out, unsigned long long *n_fallback, int32_t *fb_list) {
+    RowRec *rec_out, unsigned long long *n_fallback, int32_t *fb_list, int fp8 = 0, float sx = 1.f, float alpha = 1.f) {
+    // fp8: the records come from the e4m3 pass (scaled scores): x_err / w_max are its error norms (W8), threshold lse_tau8
     const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
     const int lane = threadIdx.x & 31, j = lane & 7;
     const unsigned gmask = 0xffu << (lane & 24);
@@ -249,7 +425,9 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
         const float2 xe = xe_next;
         const int64_t row_n = row + grp_total;
         if (row_n < n_emb) { cd_next = cand[row_n]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * row_n); }
-        const float tau = lse_tau(xe.x, xe.y, w4, KP, T);
+        const float tau = fp8 ? lse_tau8(xe.x, xe.y, W8{w_max[0], w_max[1], w_max[2], w_max[3], w_max[4], w_max[5], w_max[6], w_max[7]},
+                                         sx, alpha, D, T)
+                              : lse_tau(xe.x, xe.y, w4, KP, T);
         const int code = refine_decide(cd, tau, n_chunks);
         if (rec_out && j == 0) rec_out[row] = RowRec{cd.i1, cd.i2, cd.masks, code};
         if (code == -2) {
@@ -535,6 +713,70 @@ extern "C" int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t
             map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list);
     SEGB_LAUNCH_CHECK();
     return fvf::launch_full(X, D, K_max, aniso ? 1 : 0, model, fb_list, n_fallback, log_marg, map_k, st);
+}
+
+
+// ---- e4m3 first level (isotropic variances) ------------------------------------------------------------------
+extern "C" int64_t segb_fvf8_x_tiles_bytes(int64_t n_emb, int32_t D) { return rows_pad(n_emb) * kp8_fv_of(D); }
+extern "C" int64_t segb_fvf8_w_tiles_bytes(int32_t K_max, int32_t D) { return (int64_t)w_rows_pad(K_max) * kp8_fv_of(D); }
+extern "C" int64_t segb_fvf8_w_err_bytes(int32_t K_max) { return ((int64_t)w_rows_pad(K_max) * 8 + 16) * sizeof(float); }
+
+extern "C" int segb_fvf8_pack_x(const float *X, int64_t n_emb, int32_t D, float sx, float alpha, void *x_tiles8, float *x_err8,
+                                float *x_max8, void *stream) {
+    SEGB_CHECK_ARG(X && x_tiles8 && x_err8 && x_max8 && n_emb > 0 && D > 0 && sx > 0.f && alpha > 0.f, "null pointer");
+    const int64_t np_ = rows_pad(n_emb);
+    const int wpb = 8;
+    SEGB_CUDA(cudaMemsetAsync(x_max8, 0, 2 * sizeof(float), (cudaStream_t)stream));
+    fvf::pack_x8_kernel<<<(unsigned)((np_ + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        X, n_emb, np_, D, kp8_fv_of(D), sx, alpha, (uint8_t *)x_tiles8, x_err8, x_max8);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+// after segb_fvf_pack_model(aniso = 0): `model` holds the exact row tables, w_max16 the fp16 pass's maxima
+extern "C" int segb_fvf8_pack_model(int32_t K_max, int32_t D, const void *model, const float *w_max16, float sx, float alpha,
+                                    void *w_tiles8, float *w_err8, float *w_max8, void *stream) {
+    SEGB_CHECK_ARG(model && w_max16 && w_tiles8 && w_err8 && w_max8 && sx > 0.f && alpha > 0.f, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int krp = w_rows_pad(K_max), wpb = 8;
+    float *scales = w_err8 + (size_t)krp * 8;                       // 16 spare floats behind the table
+    fv8_scales_kernel<<<1, 1, 0, st>>>(w_max16, sx, alpha, scales);
+    SEGB_LAUNCH_CHECK();
+    pack_w8_kernel<<<(krp + wpb - 1) / wpb, wpb * 32, 0, st>>>((const double *)model, K_max, D, kp8_fv_of(D), krp, sx, alpha,
+                                                                scales, (uint8_t *)w_tiles8, w_err8);
+    SEGB_LAUNCH_CHECK();
+    wmax8_kernel<<<1, 256, 0, st>>>(w_err8, krp, scales, w_max8);
+    SEGB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int segb_fvf8_filter(const void *x_tiles8, const void *w_tiles8, int64_t n_emb, int32_t K_max, int32_t D,
+                                const float *x_max8, const float *w_max8, float sx, float alpha, float T, void *cand,
+                                void *stream) {
+    SEGB_CHECK_ARG(x_tiles8 && w_tiles8 && cand && x_max8 && w_max8 && n_emb > 0 && K_max > 0, "null pointer");
+    SEGB_CHECK_ARG(T > 0.f, "threshold");
+    FilterLaunch f;
+    f.x_tiles = x_tiles8; f.w_tiles = w_tiles8; f.cand = cand; f.n_emb = n_emb;
+    f.w_rows_pad = w_rows_pad(K_max); f.w_rows = K_max + 1; f.KP = kp8_fv_of(D); f.n_chunks = 1; f.D = D;
+    f.x_max = x_max8; f.w_max = w_max8; f.tau_kind = TAU_LSE_FP8; f.tau_T = T; f.fp8 = 1; f.sx = sx; f.alpha = alpha;
+    return launch_filter(f, (cudaStream_t)stream);
+}
+
+extern "C" int segb_fvf8_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, const void *model, const void *cand,
+                                const float *x_err8, const float *w_max8, float sx, float alpha, float T, void *work,
+                                double *log_marg, int32_t *map_k, void *rec_out, int64_t *n_fallback, void *stream) {
+    SEGB_CHECK_ARG(X && model && cand && x_err8 && w_max8 && work && log_marg && n_fallback, "null pointer");
+    SEGB_CHECK_ARG(n_emb > 0 && n_emb < (1ll << 31), "row count");
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *fb_list = (int32_t *)work;
+    SEGB_CUDA(cudaMemsetAsync(n_fallback, 0, sizeof(int64_t), st));
+    int64_t blocks = (n_emb * 8 + REFINE_THREADS - 1) / REFINE_THREADS;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    fv_refine_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+        X, D, K_max, (const double *)model, (const Cand *)cand, x_err8, w_max8, kp8_fv_of(D), T, n_emb, w_rows_pad(K_max) / CHUNK,
+        log_marg, map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list, 1, sx, alpha);
+    SEGB_LAUNCH_CHECK();
+    return fvf::launch_full(X, D, K_max, 0, model, fb_list, n_fallback, log_marg, map_k, st);
 }
 
 extern "C" int segb_fixedvar_band_scores(const segb_corpus *c, int64_t pos_first, int64_t n_positions,

@@ -82,6 +82,7 @@ struct FilterParams {
     int32_t D;
     int32_t tau_kind;              // TAU_KMEANS: argmax filter (2 * bound); TAU_LSE: logsumexp filter (tau_T + 2 * bound)
     float tau_T;
+    float sx, alpha;               // TAU_LSE_FP8: feature scale and |x|^2 scale of the e4m3 images
     // second-level pass over the rows the top-3 records could not decide (EPI = 1): the row count lives on the
     // device, every row has its own threshold and gets a bitmap of ALL the components at or above it
     const unsigned long long *n_rows_dev;   // rows = clamp(*n_rows_dev - rows_first, 0, rows_cap): one round of the undecided list
@@ -308,6 +309,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
             ? filter_tau(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.D)
             : p.tau_kind == TAU_KMEANS_FP8
             ? filter_tau8(p.x_max[0], p.x_max[1], p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3], p.D)
+            : p.tau_kind == TAU_LSE_FP8
+            ? lse_tau8(p.x_max[0], p.x_max[1], W8{p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3], p.w_max[4], p.w_max[5], p.w_max[6], p.w_max[7]},
+                       p.sx, p.alpha, p.D, p.tau_T)
             : lse_tau(p.x_max[0], p.x_max[1], W4{p.w_max[0], p.w_max[1], p.w_max[2], p.w_max[3]}, 16 * n_ks * NCH, p.tau_T);
         uint32_t n_use = 0;
         if (EPI == 1) {
@@ -1161,7 +1165,7 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
     p.x_tiles = (const uint8_t *)f.x_tiles; p.w_tiles = (const uint8_t *)f.w_tiles; p.cand = (Cand *)f.cand;
     p.n_emb = f.n_emb;
     p.x_max = f.x_max; p.w_max = f.w_max; p.D = f.D;
-    p.tau_kind = f.tau_kind; p.tau_T = f.tau_T;
+    p.tau_kind = f.tau_kind; p.tau_T = f.tau_T; p.sx = f.sx; p.alpha = f.alpha;
     p.n_mtiles = (int32_t)(rows_pad(f.n_emb) / MT_ROWS);
     p.n_ntiles = f.w_rows_pad / NT_COLS;
     {

@@ -223,6 +223,28 @@ __host__ __device__ inline float lse_tau(float eF, float nF, W4 w, int KP, float
     return T + 2.0f * lse_bound(eF, nF, w, KP);
 }
 
+// The logsumexp filter with e4m3 operands (isotropic variances).  Scaled space: features sx * x, weights sw * p_k mu_k,
+// scores S = sx * sw times the true ones.  Constant columns: A_k as 256 * (a0 + a1), and -p_k/2 |x|^2 as
+// (u0 + u1)(v0 + v1) without the u1 v1 product, u = alpha |x|^2, v = -S (p_k / 2) / alpha (two-term e4m3 splits).
+// w8 = model-wide maxima measured at packing time:
+//   eW |sw W - e4m3|_2, nW |e4m3(sw W)|_2, Aabs |S A|, dA = 256 |a - a0 - a1|, vabs |v|, v1abs |v1|, dv |v - v0 - v1|, sw.
+// The row's u-side errors follow from e4m3's relative rounding error 2^-4 (normal range; 2^-10 absolute below it):
+//   |u1| <= 2^-4 u (1 + 2^-4) + 2^-10,  |u - u0 - u1| <= 2^-8 u + 2^-9.
+struct W8 { float eW, nW, Aabs, dA, vabs, v1abs, dv, sw; };
+__host__ __device__ inline float lse_bound8(float eF, float nF, const W8 &w, float sx, float alpha, int D) {
+    const int kp = (D + 5 + 16 + 31) / 32 * 32;
+    const float c_acc = C_ACC8_PER_STEP * (float)(kp / 32) + ldexpf(1.f, -19);
+    const float u = alpha * (nF / sx) * (nF / sx);                 // nF already carries a 1.0001 factor
+    const float u1 = 0.0665f * u + 0.001f, du = 0.0040f * u + 0.002f;
+    return eF * w.nW + nF * w.eW + w.dA + u1 * w.v1abs + du * w.vabs + u * w.dv
+         + c_acc * ((nF + eF) * w.nW + w.Aabs + (u + u1) * (w.vabs + w.v1abs)) + 1e-30f;
+}
+// tau in the scaled space: S * T + 2 * bound
+__host__ __device__ inline float lse_tau8(float eF, float nF, const W8 &w, float sx, float alpha, int D, float T) {
+    return sx * w.sw * T + 2.0f * lse_bound8(eF, nF, w, sx, alpha, D);
+}
+__host__ __device__ inline int kp8_fv_of(int D) { return (D + 5 + 16 + 31) / 32 * 32; }   // + 5 constants + 16 "dead row" columns
+
 // What the refine does with a row: -2 exhaustive exact scan needed (the third-best chunk is still
 // inside the bound, or the record is unusable), -1 the best chunk suffices, >= 0 also visit that chunk.
 __device__ __forceinline__ int refine_decide(const Cand &c, float tau, int n_chunks) {
@@ -320,7 +342,7 @@ __device__ __forceinline__ uint32_t top3_snapshot_mask(const float4 *snap, float
 // member masks and refine_decide's code.  16 bytes.
 struct __align__(16) RowRec { int32_t i1, i2; uint32_t masks; int32_t code; };
 
-constexpr int TAU_KMEANS = 0, TAU_LSE = 1, TAU_KMEANS_FP8 = 2;      // FP8: w_max = (e_mu, n_mu, e_bias, bias_max), scaled space
+constexpr int TAU_KMEANS = 0, TAU_LSE = 1, TAU_KMEANS_FP8 = 2, TAU_LSE_FP8 = 3;   // KMEANS_FP8: w_max = (e_mu, n_mu, e_bias, bias_max); LSE_FP8: w_max = W8
 
 // Launch description of the filter GEMM over pre-packed tile images (host side).
 struct FilterLaunch {
@@ -337,6 +359,7 @@ struct FilterLaunch {
     int32_t tau_kind;
     float tau_T;
     int32_t fp8 = 0;                   // operands are e4m3 tile images (KP bytes per row), kind::f8f6f4
+    float sx = 1.f, alpha = 1.f;       // TAU_LSE_FP8: feature scale and |x|^2 scale
 };
 int launch_filter(const FilterLaunch &f, cudaStream_t stream);
 

@@ -1108,6 +1108,19 @@ def test_fv_filter_log_marg(sb, kind, K_max, n_assigned, n_emb):
         tc2 = fv2.log_marg.cpu().numpy()
         npt.assert_allclose(tc2, tc, rtol=0, atol=2e-5)      # the two paths bound the rounding error differently: other survivors
         npt.assert_array_equal(fv2.map_k.cpu().numpy(), am._fv.map_k.cpu().numpy())
+    if kind in ("iso", "peaked", "flat"):
+        # e4m3 first level (segb_fvf8_*): same answers; a trained model is decided by it, everything else takes the
+        # exhaustive scan
+        from segmentalist_b200.batch import FvScorer
+        fv8 = FvScorer(am.components, precision="fp8")
+        assert fv8.fp8
+        fv8.score()
+        tc8 = fv8.log_marg.cpu().numpy()
+        npt.assert_allclose(tc8, exact, rtol=1e-4, atol=0)
+        assert np.abs(tc8 - exact).max() < 2e-5
+        npt.assert_array_equal(fv8.map_k.cpu().numpy(), am._fv.map_k.cpu().numpy())
+        if kind == "peaked":
+            assert int(fv8.n_fallback.item()) < n_emb // 20, int(fv8.n_fallback.item())
     err = np.abs(tc - exact)
     assert (err / np.abs(exact)).max() < 1e-4
     assert err.max() < 2e-5, err.max()                  # dropped mass <= K_max * exp(-20) + float64 rounding
