@@ -901,7 +901,8 @@ def fbgmm_frozen_secondary(args, world, rank, dev, X, Z, corpus, lengths, seg_id
                        % (args.K, args.utts, world),
            "utt_per_s": args.utts / (ms * 1e-3), "ms_per_sweep": ms, "n_gpus": world, "K_active": sweep.K_host,
            "fallback_rows_per_sweep": fb / steps, "phases_ms": phases,
-           "segment_component_evals_per_s": float(X.shape[0]) * args.K * world / (ms * 1e-3), "dtype": "f64 scores (fp16 tensor filter + float64 refine)"}
+           "segment_component_evals_per_s": float(X.shape[0]) * args.K * world / (ms * 1e-3), "dtype": "f64 scores (%s tensor filter + float64 refine)" % ("e4m3" if sweep.fv.fp8 else "fp16"),
+           "filter_precision": "auto -> " + ("e4m3 first level" if sweep.fv.fp8 else "fp16")}
     # ---- CPU oracle on the head of rank 0's shard: same model state, same uniforms.  The sweep itself is a
     # collective (all-reduce of the statistics): EVERY rank runs it; rank 0 keeps the model state from before it.
     check = (not args.no_cpu) and world_has_head(n_head, world)
