@@ -263,13 +263,14 @@ class FrozenKMeansSweep(object):
         self.log_prob = torch.zeros(corpus.n_utt, dtype=torch.float64, device=dev)
         self.status = torch.zeros(corpus.n_utt, dtype=torch.int32, device=dev)
         # one flat float64 buffer = what a sweep all-reduces: [sum_x (K_max*D) | counts (K_max)]
-        self.red = torch.zeros(c.K_max * c.D + c.K_max, dtype=torch.float64, device=dev)
+        self.red = torch.zeros(c.K_max * c.D + c.K_max + 1, dtype=torch.float64, device=dev)
         self.sum_x = self.red[:c.K_max * c.D].view(c.K_max, c.D)
-        self.cnt_f = self.red[c.K_max * c.D:]
+        self.cnt_f = self.red[c.K_max * c.D:c.K_max * c.D + c.K_max]
+        self.obj = self.red[c.K_max * c.D + c.K_max:]         # several ranks: the sweep objective rides in the same all-reduce
         self.cnt = torch.zeros(c.K_max, dtype=torch.int64, device=dev)
         # end-of-sweep scalars read with ONE device->host copy: [bad DP statuses, fallback rows, emptied components]
-        self.flags = torch.zeros(3, dtype=torch.int64, device=dev)
-        self.flags_h = torch.zeros(3, dtype=torch.int64).pin_memory()
+        self.flags = torch.zeros(4, dtype=torch.int64, device=dev)            # [3]: bits of the all-reduced objective
+        self.flags_h = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.log_prob_h = torch.zeros(corpus.n_utt, dtype=torch.float64).pin_memory()
         self.side = torch.cuda.Stream()
         self.last_fallback = 0
@@ -329,7 +330,8 @@ class FrozenKMeansSweep(object):
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             self.flags[0:1].copy_((self.status != _lib.DP_OK).sum())
-            self.log_prob_h.copy_(self.log_prob, non_blocking=True)
+            if not _dist_on():
+                self.log_prob_h.copy_(self.log_prob, non_blocking=True)
 
     def reduce_and_update(self):
         """All-reduce the sufficient statistics over ranks (NCCL over NVLink) -- ONE collective
@@ -402,15 +404,21 @@ class FrozenKMeansSweep(object):
         if K_before < c.K_max:
             self._clamp_inactive_winners(K_before)
         self.collect()
+        if _dist_on():
+            # with several ranks the reference's single serial sum cannot be formed anyway: each rank contributes a
+            # device-side sum of its utterances' objectives to the sweep's one all-reduce (no second collective, no
+            # copy of the per-utterance values to the host)
+            self.obj.copy_(self.log_prob.sum().reshape(1))
         self.reduce_and_update()
         self._clean_components()
         if self.scorer == "mma":
             self.flags[1:2].copy_(self.mma.n_fallback)
         self.flags[2:3].copy_(c._K)
+        self.flags[3:4].copy_(self.obj.view(torch.int64))
         torch.cuda.current_stream().wait_stream(self.side)
         self.flags_h.copy_(self.flags, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        n_bad, n_fb, K_now = (int(v) for v in self.flags_h.tolist())
+        n_bad, n_fb, K_now, obj_bits = (int(v) for v in self.flags_h.tolist())
         assert n_bad == 0, "segmentation failed for %d utterances (status %s)" % (
             n_bad, np.unique(self.status.cpu().numpy()))
         self.last_fallback = n_fb
@@ -434,13 +442,10 @@ class FrozenKMeansSweep(object):
                 self.mma = None                             # release one image of X before the other one is built
                 self.mma = MmaScorer(c, fused=self._fused, precision=switch_to)
                 self.mma.timing = timing
-        # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time)
-        total = float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
         if _dist_on():
-            t = torch.tensor([total], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            total = float(t.item())
-        return total
+            return float(np.array([obj_bits], dtype=np.int64).view(np.float64)[0])
+        # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time)
+        return float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
 
     def fit(self, n_iter):
         """Frozen hard-assignment E-step + M-step over the CURRENT tokens -- KMeans.fit(n_iter,
