@@ -25,6 +25,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--aniso", action="store_true")
 ap.add_argument("--noise", type=float, default=0.05)
 ap.add_argument("--fused", action="store_true")
+ap.add_argument("--fp8", action="store_true", help="e4m3 first-level filter (isotropic variances)")
 args = ap.parse_args()
 D, K = 130, args.K
 K_true = args.K_true or K
@@ -49,7 +50,7 @@ _, first = np.unique(zh, return_index=True)        # component = cluster, labels
 rank = np.empty(K_true, dtype=np.int64)
 rank[zh[np.sort(first)]] = np.arange(len(first))
 am.components._add_many(np.arange(n_tok), rank[zh])
-fv = FvScorer(am.components, fused=bool(args.fused))
+fv = FvScorer(am.components, fused=bool(args.fused), precision="fp8" if args.fp8 else "fp16")
 fv.score()
 torch.cuda.synchronize()
 
@@ -75,7 +76,7 @@ out = fv.log_marg.cpu().numpy()
 ids = np.arange(n_tok, n_tok + 4096) if args.rows >= n_tok + 4096 else np.arange(min(4096, args.rows))
 exact = am.log_marg_items(ids)
 err = np.abs(out[ids] - exact)
-print(json.dumps({"fused": fv.fused, "rows": args.rows, "K": K, "K_act": am.components.K, "aniso": bool(args.aniso),
+print(json.dumps({"fused": fv.fused, "e4m3_first_level": bool(fv.fp8), "rows": args.rows, "K": K, "K_act": am.components.K, "aniso": bool(args.aniso),
                   "pack_model_ms": t_pack, "filter_ms": t_filter, "refine_ms": t_refine,
                   "filter_tflops_algorithmic": fl / t_filter / 1e9,
                   "score_tflops_algorithmic": fl / (t_pack + t_filter + t_refine) / 1e9,

@@ -19,6 +19,11 @@ F="python tools/fvf_microbench.py --tokens-per-k 20 --reps 1"
 $F > gpurun_out/ncu_plain_fv.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled \
     -k regex:"kmeans_filter_kernelILi9ELi1ELi0ELb0|fv_refine_kernel" -s 2 -c 2 -o gpurun_out/r2_prof_fv -f $F > gpurun_out/ncu_f.log 2>&1
+# the same with the e4m3 first level (isotropic variances)
+F8="python tools/fvf_microbench.py --tokens-per-k 20 --reps 1 --fp8"
+$F8 > gpurun_out/ncu_plain_fv8.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled \
+    -k regex:"kmeans_filter_kernelILi5ELi1ELi0ELb1|fv_refine_kernel" -s 2 -c 2 -o gpurun_out/r2_prof_fv8 -f $F8 > gpurun_out/ncu_f8.log 2>&1
 # the diffuse model: second-level pass (gather, bitmap filter, bitmap refine) of a steady-state sweep
 D="python bench.py --only-diffuse --no-cpu"
 $D > gpurun_out/ncu_plain_dif.log 2>&1 || exit 1
@@ -29,7 +34,7 @@ ncu --set full --clock-control none --import-source on --kernel-name-base mangle
 G="python tools/fvf_microbench.py --tokens-per-k 20 --reps 1 --fused --rows 2097152"
 $G > gpurun_out/ncu_plain_fused.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:"score_fused_kernel" -s 1 -c 1 -o gpurun_out/r2_prof_fused -f $G > gpurun_out/ncu_g.log 2>&1
-for r in kmeans kmeans16 fv dif fused; do
+for r in kmeans kmeans16 fv fv8 dif fused; do
   ncu -i gpurun_out/r2_prof_$r.ncu-rep --page raw --csv > gpurun_out/r2_raw_$r.csv 2>/dev/null
 done
 ls -la gpurun_out/*.ncu-rep
