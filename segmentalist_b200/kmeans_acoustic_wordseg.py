@@ -133,15 +133,17 @@ class SegmentalKMeansWordseg(object):
         return record_dict
 
     # ---- frozen-state batch mode (new)
-    def segment_frozen(self, n_iter, n_iter_inbetween_kmeans=0, scorer="auto"):
+    def segment_frozen(self, n_iter, n_iter_inbetween_kmeans=0, scorer="auto", precision="auto"):
         """Frozen-means sweeps: score + Viterbi for every utterance against the same
         means, then rebuild the means from the new tokens (KMeans.fit semantics,
         kmeans.py:124-171, applied to segmentation); n_iter_inbetween_kmeans > 0 runs that many
         frozen hard-assignment steps over the current tokens after every sweep
-        (kmeans_acoustic_wordseg.py:414-417), sharded like the sweep.  Returns a record dict."""
+        (kmeans_acoustic_wordseg.py:414-417), sharded like the sweep.  precision: first-level filter of the tensor-core
+        scorer, "auto" / "fp16" / "fp8" (e4m3 cascade; bit-identical results, see batch.FrozenKMeansSweep).  Returns a
+        record dict."""
         if self._frozen is None:
             self._frozen = FrozenKMeansSweep(self.acoustic_model.components, self._corpus, wip=self.wip,
-                                             scorer=scorer)
+                                             scorer=scorer, precision=precision)
         self._frozen.K_host = None      # sequential sweeps / fit() in between may have changed K
         record = {"sum_neg_len_sqrd_norm": [], "components": [], "n_tokens": [], "sample_time": []}
         for _ in range(n_iter):

@@ -238,13 +238,14 @@ class UnigramAcousticWordseg(object):
         return record_dict
 
     # ---- frozen-state batch mode (new)
-    def segment_frozen(self, n_iter, uniforms=None):
+    def segment_frozen(self, n_iter, uniforms=None, precision="auto"):
         """Frozen-model sweeps: every utterance is scored (tensor-core log_marg_i) and segmented (FFBS for
         fb_type "standard", Viterbi for "viterbi") against the same model, every new token picks its
         component from that model (sampled / MAP), then the model is rebuilt from the new assignments
         (batch.FrozenFBGMMSweep) -- the mode that shards over GPUs.  Fixed-variance components only.
         uniforms: optional list (one entry per iteration) of (u_fb, u_assign) float64 arrays [sum of
-        utterance lengths]; default: drawn from np.random.  Returns a record dict."""
+        utterance lengths]; default: drawn from np.random.  precision: first-level filter of the scorer, "auto" /
+        "fp16" / "fp8" (e4m3; same results, see batch.FrozenFBGMMSweep).  Returns a record dict."""
         from .batch import FrozenFBGMMSweep
         comps = self.acoustic_model.components
         assert getattr(self.acoustic_model, "covariance_type", "fixed") == "fixed", \
@@ -252,7 +253,7 @@ class UnigramAcousticWordseg(object):
         assert self.calc_p_continue() == 1.0
         if getattr(self, "_frozen", None) is None:
             self._frozen = FrozenFBGMMSweep(comps, self._corpus, fb_type=self.fb_type,
-                                            time_power_term=self.time_power_term, wip=self.wip)
+                                            time_power_term=self.time_power_term, wip=self.wip, precision=precision)
         self._frozen.K_host = None          # sequential sweeps in between may have changed K
         n_pos = self._corpus.n_pos
         record = {k: [] for k in ("sample_time", "log_marg*length", "components", "n_tokens", "fallback_rows")}
