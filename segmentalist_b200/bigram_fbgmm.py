@@ -38,4 +38,5 @@ class BigramFBGMM(object):
         return self.components.log_marg()
 
     def get_n_assigned(self):
-        return len(np.where(self.components.assignments != -1)[0])
+        # counted on the device: `components.assignments` would mirror the whole vector to the host first
+        return int((self.components._assign != -1).sum().item())

@@ -182,4 +182,5 @@ class FBGMM(object):
         return self.log_prob_z() + self.log_prob_X_given_z()
 
     def get_n_assigned(self):
-        return len(np.where(self.components.assignments != -1)[0])
+        # counted on the device: `components.assignments` would mirror the whole vector to the host first
+        return int((self.components._assign != -1).sum().item())

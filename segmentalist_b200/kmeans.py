@@ -69,4 +69,5 @@ class KMeans(object):
         return record_dict
 
     def get_n_assigned(self):
-        return len(np.where(self.components.assignments != -1)[0])
+        # counted on the device: `components.assignments` would mirror the whole vector to the host first
+        return int((self.components._assign != -1).sum().item())
