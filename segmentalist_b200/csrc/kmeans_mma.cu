@@ -14,7 +14,11 @@
 // which chunks can contain the true winner; those (normally 16 components out
 // of K_max) are re-scored by the exact float32 routine the SIMT path uses, so
 // max and first-argmax come out bit-identical to the reference.  Rows whose
-// third-best chunk is still inside the bound fall back to a full exact scan.
+// third-best chunk is still inside the bound go to a SECOND-LEVEL tensor pass (compact
+// image of those rows, bitmap epilogue, exact re-score of the flagged components), and only
+// rows that even that cannot resolve (NaN data) to a full exact scan.  The default first
+// level runs in e4m3 (segb_mma8_*: scaled operands, its own rigorous bound), with the fp16
+// pass as its second level: a cascade e4m3 -> fp16 -> exact.
 //
 // Memory layout (designed for the copy engine, not for humans): X and the means
 // are stored in HBM as fp16 "tile images": consecutive 128-row tiles, each
@@ -27,15 +31,20 @@
 //
 // Kernel: persistent, one CTA per SM, 640 threads, warp-specialised:
 //   warp 0  TMA producer  (A = 256 embeddings per work item, double-buffered; B = 128-component
-//                          tiles, L2-resident, two stages tied to the accumulator buffers)
-//   warp 1  MMA issuer    (one elected thread; tcgen05.mma kind::f16, M=128 N=128 K=16, fp32
-//                          accumulate in TMEM, 2 row-halves x double-buffered accumulators = 512
-//                          TMEM columns; unrolled issue loop, ONE commit per tile)
+//                          tiles, L2-resident, a ring of 2 (fp16) or 4 (e4m3) stages)
+//   warp 1  MMA issuer    (one elected thread; tcgen05.mma kind::f16 or kind::f8f6f4, M=128 N=128, 32 bytes of
+//                          K per row and instruction, fp32 accumulate in TMEM, 2 row-halves x double-buffered
+//                          accumulators = 512 TMEM columns; unrolled issue loop, ONE commit per tile; the last
+//                          tile only as wide as the components reach)
 //   warp 2  TMEM allocator
-//   warps 4-19 epilogue   (one tcgen05.ld 32x32b.x64 per warp and tile: one thread owns one
-//                          embedding row and 64 of the tile's columns; running top-3 of chunk
-//                          maxima in registers; nothing but 32 B per embedding ever goes back
-//                          to HBM)
+//   warps 4-19 epilogue   (two SETS of eight warps drain alternate tiles: set s owns accumulator pair s and takes
+//                          its tile in two tcgen05.ld 32x32b.x64 -- one thread owns one embedding row; running
+//                          top-3 of chunk maxima in registers; nothing but 32 B per embedding ever goes back to
+//                          HBM.  Variants: EPI = 1 writes a per-row bitmap of the components above the row's
+//                          threshold instead (second-level pass over undecided rows, row count on the device);
+//                          F8 defers the member mask of the best chunk through a shared-memory snapshot.)
+// The same kernel is the first level of the FBGMM log_marg_i filter (fixedvar_filter.cu: logsumexp thresholds,
+// NCH = 2 inner-dimension chunks for anisotropic variances).
 #include <cuda_fp8.h>
 #include "mma_common.cuh"
 #include "refine_rows.cuh"
