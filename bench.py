@@ -1277,6 +1277,8 @@ def run_ours(args):
                                   "nothing between them (the power-capped clock of a pure tensor loop)" % args.steps,
                         "kernel_ms_back_to_back": k_ms_b2b, "frac_back_to_back": flops / (k_ms_b2b * 1e-3) / 1e12 / pk_tf,
                         "frac_of_sustained_peak": (ach / peak_sus) if peak_sus else None,
+                        "frac_of_measured_bf16_peak": ach / peak_tf,      # e4m3 first level: algorithmic rate against the bf16 figure
+                        "filter_precision": "e4m3" if fp8 else "fp16",
                         "refine_ms_in_sweep": in_sweep_ms[1]}
         cs = corpus.struct()
 
