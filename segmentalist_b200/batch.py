@@ -58,7 +58,8 @@ class MmaScorer(object):
         assert not self.fused or fused_supported(c.D)
         # precision="fp8": the first-level filter runs in e4m3 (segb_mma8_*: twice the MMA rate, a 2.6x smaller image
         # of X); rows it cannot decide take the fp16 second-level pass.  Needs an even D (8-lane refine).
-        self.fp8 = precision == "fp8" and not self.fused and c.D % 2 == 0
+        # K_max <= 65536: the pass keeps its top-3 as packed keys with 12-bit chunk ids (mma_common.cuh, KEY_ID_BITS).
+        self.fp8 = precision == "fp8" and not self.fused and c.D % 2 == 0 and c.K_max <= 65536
         self.scale = 1.0
         self.w_tiles = torch.empty(lib.segb_mma_w_tiles_bytes(c.K_max, c.D), dtype=torch.uint8, device=dev)
         # refine scratch: list of undecided rows + (two-kernel path) their compact fp16 image, thresholds and
@@ -273,6 +274,7 @@ class FrozenKMeansSweep(object):
         self.flags_h = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.log_prob_h = torch.zeros(corpus.n_utt, dtype=torch.float64).pin_memory()
         self.side = torch.cuda.Stream()
+        self.log_prob_ready = torch.cuda.Event()             # the per-utterance objectives have reached pinned memory
         self.last_fallback = 0
         # finite embeddings (a finite sum has no NaN / inf term) give finite or -inf band scores, so the DP may skip
         # its NaN compares (SEGB_DP_SCORES_FINITE); embeddings streamed from the host are not vouched for
@@ -332,6 +334,7 @@ class FrozenKMeansSweep(object):
             self.flags[0:1].copy_((self.status != _lib.DP_OK).sum())
             if not _dist_on():
                 self.log_prob_h.copy_(self.log_prob, non_blocking=True)
+                self.log_prob_ready.record(self.side)
 
     def reduce_and_update(self):
         """All-reduce the sufficient statistics over ranks (NCCL over NVLink) -- ONE collective
@@ -417,6 +420,12 @@ class FrozenKMeansSweep(object):
         self.flags[3:4].copy_(self.obj.view(torch.int64))
         torch.cuda.current_stream().wait_stream(self.side)
         self.flags_h.copy_(self.flags, non_blocking=True)
+        objective = None
+        if not _dist_on():
+            # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time) -- a serial
+            # chain of n_utt additions on the host, formed while the device still collects the tokens and rebuilds the means
+            self.log_prob_ready.synchronize()
+            objective = float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
         torch.cuda.current_stream().synchronize()
         n_bad, n_fb, K_now, obj_bits = (int(v) for v in self.flags_h.tolist())
         assert n_bad == 0, "segmentation failed for %d utterances (status %s)" % (
@@ -444,8 +453,7 @@ class FrozenKMeansSweep(object):
                 self.mma.timing = timing
         if _dist_on():
             return float(np.array([obj_bits], dtype=np.int64).view(np.float64)[0])
-        # objective: utterance-order float64 sum (the reference accumulates it one utterance at a time)
-        return float(np.cumsum(self.log_prob_h.numpy())[-1]) if cp.n_utt else 0.0
+        return objective
 
     def fit(self, n_iter):
         """Frozen hard-assignment E-step + M-step over the CURRENT tokens -- KMeans.fit(n_iter,
@@ -535,7 +543,7 @@ class FvScorer(object):
         self.x_tiles = self.cand = self.x_err = self.x_max = None
         # precision="fp8": e4m3 first level (segb_fvf8_*; isotropic variances, two-kernel path).  Rows it cannot decide
         # take the exhaustive scan, so callers watch n_fallback (FrozenFBGMMSweep falls back to fp16 by itself).
-        self.fp8 = precision == "fp8" and not self.fused and not self.aniso
+        self.fp8 = precision == "fp8" and not self.fused and not self.aniso and c.K_max <= 65536 - 16   # 12-bit chunk ids
         if self.fp8:
             self.sx = MmaScorer.pick_scale(c._X)
             n2_max = 0.0

@@ -151,13 +151,16 @@ __device__ void km_best_of(const segb_kmeans &m, const T *xs, double *red, T &be
     const int KM_ = m.K_max;
     T bv = neg_inf_t<T>();
     int bk = 0x7fffffff;
+    // NumPy: max() of an array with a NaN is NaN and argmax() is the index of the FIRST NaN (kmeans_components.py:228-232
+    // on an embedding with a NaN element).  A NaN score therefore competes as +inf (scores are <= 0, so +inf is free).
     for (int k = threadIdx.x; k < KM_; k += blockDim.x) {
-        const T v = km_neg_dist<T>(KM<T>::meansT(m) + k, KM_, xs, m.D);
+        T v = km_neg_dist<T>(KM<T>::meansT(m) + k, KM_, xs, m.D);
+        if (v != v) v = -neg_inf_t<T>();
         if (v > bv || bk == 0x7fffffff) { bv = v; bk = k; }
     }
     double vmax; int kmax;
     block_argmax((double)bv, bk, red, vmax, kmax);
-    best_v = (T)vmax;
+    best_v = vmax == (double)CUDART_INF ? (T)CUDART_NAN : (T)vmax;
     best_k = kmax;
 }
 

@@ -384,9 +384,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
                             // every tile but the last: four full chunks, straight-line
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const float cm = chunk_max16(&v[c * 16]);
-                                if (F8) top3_insert_snap(&v[c * 16], cm, cid0 + c, snap, m1, m2, m3, i1, i2);
-                                else top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
+                                // F8: m1 >= m2 >= m3 are packed keys (top3_insert_key), unpacked after the last tile
+                                if (F8) top3_insert_key(&v[c * 16], chunk_max16_floor(&v[c * 16]), (uint32_t)(cid0 + c), snap, m1, m2, m3);
+                                else top3_insert(&v[c * 16], chunk_max16(&v[c * 16]), cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
                             }
                         } else {
                             const int n_c = p.n_chunks_valid - cid0;         // chunks of the last tile that were computed
@@ -404,14 +404,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
 #pragma unroll
                                         for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[c * 16 + j]);
                                     }
-                                    if (F8) top3_insert_snap(&v[c * 16], cm, cid0 + c, snap, m1, m2, m3, i1, i2);
+                                    if (F8) top3_insert_key(&v[c * 16], fmaxf(cm, KEY_FLOOR), (uint32_t)(cid0 + c), snap, m1, m2, m3);
                                     else top3_insert(&v[c * 16], cm, cid0 + c, tau_c, m1, m2, m3, i1, i2, k1, k2);
                                 }
                             }
                         }
                     }
                 }
-                if (F8) {                                       // the deferred member mask of this set's best chunk
+                if (F8) {                                       // keys -> (maximum, chunk id); the deferred member mask of this set's best chunk
+                    key_unpack(m1, m1, i1);
+                    key_unpack(m2, m2, i2);
+                    if (!(m3 > KEY_FLOOR_TEST)) m3 = -CUDART_INF_F;
                     k1 = i1 >= 0 ? top3_snapshot_mask(snap, m1, tau_c) : 0u;
                     k2 = 0xffffu;
                 }
@@ -1211,6 +1214,7 @@ static int launch_filter_impl(const FilterLaunch &f, const unsigned long long *n
     void (*kern)(FilterParams);
     if (f.fp8) {
         if (nch != 1 || n_rows_dev || f.w_rows <= 0) { set_error("fp8 filter pass: one chunk, top-3 epilogue, known component count"); return SEGB_E_ARG; }
+        if (p.n_ntiles * (NT_COLS / CHUNK) > (1 << KEY_ID_BITS)) { set_error("fp8 filter pass: K_max <= 65536 (chunk ids ride in 12 mantissa bits of the packed top-3 keys)"); return SEGB_E_UNSUPPORTED; }
         kern = p.n_ksteps == 5 ? kmeans_filter_kernel<5, 1, 0, true> : kmeans_filter_kernel<0, 1, 0, true>;   // 5: D = 130 (KP = 160)
     } else if (n_rows_dev) {
         if (nch != 1) { set_error("second-level filter pass: one inner-dimension chunk"); return SEGB_E_ARG; }

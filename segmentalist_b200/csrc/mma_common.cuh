@@ -195,9 +195,18 @@ __host__ __device__ inline float filter_tau(float ex, float nx, float e_mu, floa
 // calibrated against float64 dot products of the quantised operands (tools/fp8_acc_microbench.py: the largest
 // observed |error| / (|x^||mu^| + |bias|) is 1.0e-7 x KP/32; C_ACC8 leaves a factor > 8).
 constexpr float C_ACC8_PER_STEP = 1.0f / 1048576.0f;          // 2^-20 per K = 32 step
+// The e4m3 pass keeps its running top-3 as PACKED KEYS (top3_insert_key): the chunk id replaces the low KEY_ID_BITS
+// mantissa bits of the chunk maximum, so the record's m1 / m2 / m3 are within 2^(KEY_ID_BITS - 23) |score| of the
+// chunk maxima.  |score| <= the magnitude the accumulation term already multiplies, so the keys cost one more
+// relative term there (1.05: the magnitude expression bounds the computed score up to its own small error terms).
+constexpr int KEY_ID_BITS = 12;                                // chunk ids < 4096: K_max <= 65536 for the e4m3 pass
+constexpr uint32_t KEY_ID_MASK = (1u << KEY_ID_BITS) - 1u;
+constexpr float C_KEY8 = 1.05f / (float)(1u << (23 - KEY_ID_BITS));
+constexpr float KEY_FLOOR = -3.0e38f;                          // NaN chunk maxima enter as this (a key must not be NaN)
+constexpr float KEY_FLOOR_TEST = -2.9e38f;                     // keys above this belong to a real chunk
 __host__ __device__ inline int kp8_of(int D) { return (D + 3 + 31) / 32 * 32; }
 __host__ __device__ inline float filter_tau8(float ex, float nx, float e_mu, float n_mu, float e_bias, float bias_max, int D) {
-    const float c_acc = C_ACC8_PER_STEP * (float)(kp8_of(D) / 32) + ldexpf(1.f, -19);
+    const float c_acc = C_ACC8_PER_STEP * (float)(kp8_of(D) / 32) + ldexpf(1.f, -19) + C_KEY8;
     const float eta = 0.5f * ldexpf((float)(D + 3), -24) * (nx + n_mu + e_mu) * (nx + n_mu + e_mu);
     const float bound = ex * n_mu + nx * e_mu + e_bias + c_acc * ((nx + ex) * n_mu + 1.1f * bias_max + 1e-30f) + eta;
     return 2.0f * bound;
@@ -233,7 +242,7 @@ __host__ __device__ inline float lse_tau(float eF, float nF, W4 w, int KP, float
 struct W8 { float eW, nW, Aabs, dA, vabs, v1abs, dv, sw; };
 __host__ __device__ inline float lse_bound8(float eF, float nF, const W8 &w, float sx, float alpha, int D) {
     const int kp = (D + 5 + 16 + 31) / 32 * 32;
-    const float c_acc = C_ACC8_PER_STEP * (float)(kp / 32) + ldexpf(1.f, -19);
+    const float c_acc = C_ACC8_PER_STEP * (float)(kp / 32) + ldexpf(1.f, -19) + C_KEY8;     // C_KEY8: packed top-3 keys
     const float u = alpha * (nF / sx) * (nF / sx);                 // nF already carries a 1.0001 factor
     const float u1 = 0.0665f * u + 0.001f, du = 0.0040f * u + 0.002f;
     return eF * w.nW + nF * w.eW + w.dA + u1 * w.v1abs + du * w.vabs + u * w.dv
@@ -262,6 +271,15 @@ __device__ __forceinline__ float chunk_max16(const float *v) {
     const float a4 = fmaxf(fmaxf(v[12], v[13]), v[14]);
     const float b0 = fmaxf(fmaxf(a0, a1), a2), b1 = fmaxf(fmaxf(a3, a4), v[15]);
     return fmaxf(b0, b1);
+}
+
+// the same tree ending in a 3-input maximum with KEY_FLOOR: never NaN (fmaxf drops NaN operands), same instruction count
+__device__ __forceinline__ float chunk_max16_floor(const float *v) {
+    const float a0 = fmaxf(fmaxf(v[0], v[1]), v[2]), a1 = fmaxf(fmaxf(v[3], v[4]), v[5]);
+    const float a2 = fmaxf(fmaxf(v[6], v[7]), v[8]), a3 = fmaxf(fmaxf(v[9], v[10]), v[11]);
+    const float a4 = fmaxf(fmaxf(v[12], v[13]), v[14]);
+    const float b0 = fmaxf(fmaxf(a0, a1), a2), b1 = fmaxf(fmaxf(a3, a4), v[15]);
+    return fmaxf(fmaxf(b0, b1), KEY_FLOOR);
 }
 
 // Insert a chunk maximum into the running top-3.  A chunk that becomes the new BEST also records
@@ -322,6 +340,32 @@ __device__ __forceinline__ void top3_insert_snap(const float *vv, float cm, int 
     } else {
         m2 = p2 ? cm : m2; i2 = p2 ? cid : i2;
     }
+}
+// The e4m3 pass's insertion: the running top-3 are three PACKED KEYS a1 >= a2 >= a3 -- the chunk maximum with the
+// chunk id in its low KEY_ID_BITS mantissa bits (filter_tau8 / lse_bound8 carry the 2^-11 relative term this costs).
+// Keys of different chunks differ, a key orders like its maximum, and the id travels with the value, so the update
+// is a five-instruction min / max network instead of compares and selects on (value, id) pairs; the new-best
+// snapshot is as in top3_insert_snap.  cm must not be NaN (chunk_max16_floor).
+__device__ __forceinline__ void top3_insert_key(const float *vv, float cm, uint32_t cid, float4 *snap, float &a1, float &a2,
+                                                float &a3) {
+    const float key = __uint_as_float((__float_as_uint(cm) & ~KEY_ID_MASK) | cid);
+    if (key > a1) {
+        snap[0 * SNAP_STRIDE] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        snap[1 * SNAP_STRIDE] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+        snap[2 * SNAP_STRIDE] = make_float4(vv[8], vv[9], vv[10], vv[11]);
+        snap[3 * SNAP_STRIDE] = make_float4(vv[12], vv[13], vv[14], vv[15]);
+    }
+    const float t1 = fminf(a1, key);
+    a1 = fmaxf(a1, key);
+    const float t2 = fminf(a2, t1);
+    a2 = fmaxf(a2, t1);
+    a3 = fmaxf(a3, t2);
+}
+// (value, chunk id) of a key; a slot that never saw a real chunk (-inf, or the floor of an all-NaN chunk) -> (-inf, -1)
+__device__ __forceinline__ void key_unpack(float a, float &m, int &i) {
+    const bool real = a > KEY_FLOOR_TEST;
+    m = real ? a : -CUDART_INF_F;
+    i = real ? (int)(__float_as_uint(a) & KEY_ID_MASK) : -1;
 }
 // members of the parked best chunk within tau_c of its maximum m1 (bit j = member j)
 __device__ __forceinline__ uint32_t top3_snapshot_mask(const float4 *snap, float m1, float tau_c) {

@@ -633,6 +633,42 @@ def test_mma_scorer_fp8_first_level(sb, K_max, n_emb, K_true, noise, data):
         assert n_fb > n_emb // 2                       # near-duplicates: second level
 
 
+@pytest.mark.parametrize("precision", ["fp16", "fp8"])
+def test_mma_scorer_nan_rows(sb, precision):
+    """Embeddings with NaN elements (unassigned rows, so the means stay finite): every filter score of such a row is
+    NaN, no chunk enters its top-3 (packed keys in the e4m3 pass: an all-NaN chunk maximum enters as the key floor and
+    is unpacked as 'no chunk'), the row goes to the exhaustive exact scan and comes out as the exact scorer gives it."""
+    from segmentalist_b200 import synth
+    from segmentalist_b200.batch import MmaScorer
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    rng = np.random.RandomState(11)
+    K_max, n_emb = 200, 6000
+    centres = synth.cluster_centres(K_max, 130, rng)
+    z = rng.randint(0, K_max, n_emb)
+    z[:K_max] = np.arange(K_max)
+    X = synth._unit_rows(centres[z] + 0.05 * rng.standard_normal((n_emb, 130)).astype(np.float32))
+    bad = np.array([3000, 3001, 4500, 5999])
+    X[bad[0], :] = np.nan
+    X[bad[1], 7] = np.nan
+    X[bad[2], 129] = np.nan
+    X[bad[3], 0] = np.nan
+    assign = -np.ones(n_emb, dtype=np.int64)
+    assign[:2500] = z[:2500]
+    np.random.seed(1)
+    comps = KMeansComponents(X, assign, K_max)
+    val_e, arg_e = comps.best(None)
+    mma = MmaScorer(comps, precision=precision)
+    assert mma.fp8 == (precision == "fp8")
+    val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
+    arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
+    mma.score(val, arg)
+    torch.cuda.synchronize()
+    assert int(mma.n_fallback.item()) >= len(bad)
+    npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
+    npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
+    assert np.isnan(val.cpu().numpy()[bad]).all()
+
+
 def test_frozen_sweep_auto_precision_policy(sb):
     """precision="auto": a diffuse model (many near-duplicate components) leaves most rows to the second level, so the
     sweep falls back to the fp16 first level, retries e4m3 after AUTO_RETRY_SWEEPS sweeps, falls back again with a
