@@ -402,11 +402,13 @@ __global__ void wmax8_kernel(const float *w_err8, int n_rows, const float *scale
 // Eight lanes per embedding (four per warp): the filter record names the candidate chunks and members;
 // each is re-scored exactly and fed to the running logsumexp.  Rows the filter could not decide go to
 // fb_list for the exhaustive scan.
-template <bool ANISO>
+// DC: the embedding dimension when known at compile time (0 = runtime): constant trip counts and offsets in quad_part
+template <bool ANISO, int DC = 0>
 __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
-    const float *X, int D, int K_max, const double *model_rows, const Cand *cand, const float *x_err,
+    const float *X, int D_rt, int K_max, const double *model_rows, const Cand *cand, const float *x_err,
     const float *w_max, int KP, float T, int64_t n_emb, int n_chunks, double *log_marg, int32_t *map_k,
     RowRec *rec_out, unsigned long long *n_fallback, int32_t *fb_list, int fp8 = 0, float sx = 1.f, float alpha = 1.f) {
+    const int D = DC ? DC : D_rt;
     // fp8: the records come from the e4m3 pass (scaled scores): x_err / w_max are its error norms (W8), threshold lse_tau8
     const ModelRows t = model_view(model_rows, K_max, D, ANISO ? 1 : 0);
     const int lane = threadIdx.x & 31, j = lane & 7;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
             if (j == 0) fb_list[atomicAdd(n_fallback, 1ull)] = (int32_t)row;
             continue;
         }
-        const LseAcc acc = fv_exact_row8<ANISO>(t, Kr, D, X + row * D, cd.i1, cd.i2, cd.masks, code, j, gmask);
+        const LseAcc acc = fv_exact_row8<ANISO, DC>(t, Kr, D, X + row * D, cd.i1, cd.i2, cd.masks, code, j, gmask);
         if (j == 0) {
             log_marg[row] = acc.lse();
             if (map_k) map_k[row] = (acc.bk == 0x7fffffff) ? -1 : acc.bk;
@@ -707,6 +709,10 @@ extern "C" int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t
         fv_refine_kernel<true><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
             map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list);
+    else if (D == 130)                   // the dimension of the BASELINE configurations, specialised
+        fv_refine_kernel<false, 130><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
+            map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list);
     else
         fv_refine_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             X, D, K_max, (const double *)model, (const Cand *)cand, x_err, w_max, KP, T, n_emb, n_chunks, log_marg,
@@ -772,9 +778,14 @@ extern "C" int segb_fvf8_refine(const float *X, int64_t n_emb, int32_t D, int32_
     SEGB_CUDA(cudaMemsetAsync(n_fallback, 0, sizeof(int64_t), st));
     int64_t blocks = (n_emb * 8 + REFINE_THREADS - 1) / REFINE_THREADS;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    fv_refine_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
-        X, D, K_max, (const double *)model, (const Cand *)cand, x_err8, w_max8, kp8_fv_of(D), T, n_emb, w_rows_pad(K_max) / CHUNK,
-        log_marg, map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list, 1, sx, alpha);
+    if (D == 130)
+        fv_refine_kernel<false, 130><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            X, D, K_max, (const double *)model, (const Cand *)cand, x_err8, w_max8, kp8_fv_of(D), T, n_emb, w_rows_pad(K_max) / CHUNK,
+            log_marg, map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list, 1, sx, alpha);
+    else
+        fv_refine_kernel<false><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            X, D, K_max, (const double *)model, (const Cand *)cand, x_err8, w_max8, kp8_fv_of(D), T, n_emb, w_rows_pad(K_max) / CHUNK,
+            log_marg, map_k, (RowRec *)rec_out, (unsigned long long *)n_fallback, fb_list, 1, sx, alpha);
     SEGB_LAUNCH_CHECK();
     return fvf::launch_full(X, D, K_max, 0, model, fb_list, n_fallback, log_marg, map_k, st);
 }

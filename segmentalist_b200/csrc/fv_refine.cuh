@@ -40,10 +40,30 @@ __host__ __device__ inline ModelRows model_view(const double *base, int K_max, i
 // Exact float64 quadratic form of component row k for the embedding whose elements d = j, j+8, ... this
 // lane holds: sum_d P_kd (mu_kd - x_d)^2 over the lane's elements (isotropic: the factor p_k is applied
 // by the caller).  Eight lanes per embedding; the caller reduces over them.
-template <bool ANISO>
+template <bool ANISO, int DC = 0>
 __device__ __forceinline__ double quad_part(const ModelRows &t, int k, const float *xr, int D, int j) {
     const double *mu = t.mu + (size_t)k * D;
     double acc = 0.0;
+    if (DC > 0 && (DC & 1) == 0) {
+        // dimension known at compile time: the same two chains, fully unrolled (all loads of the row in flight at once)
+        double acc1 = 0.0;
+        const double *P = ANISO ? t.P + (size_t)k * DC : nullptr;
+        const float *xj = xr + 2 * j;
+        const double *mj = t.mu + (size_t)k * DC + 2 * j;
+#pragma unroll
+        for (int i = 0; i < (DC + 15) / 16; ++i) {
+            if (16 * i + 14 < DC || 2 * j + 16 * i < DC) {
+                const float2 xv = *reinterpret_cast<const float2 *>(xj + 16 * i);
+                const double2 mv = *reinterpret_cast<const double2 *>(mj + 16 * i);
+                const double d0 = mv.x - (double)xv.x, d1 = mv.y - (double)xv.y;
+                if (ANISO) {
+                    const double2 pv = *reinterpret_cast<const double2 *>(P + 2 * j + 16 * i);
+                    acc = fma(d0 * d0, pv.x, acc); acc1 = fma(d1 * d1, pv.y, acc1);
+                } else { acc = fma(d0, d0, acc); acc1 = fma(d1, d1, acc1); }
+            }
+        }
+        return acc + acc1;
+    }
     if ((D & 1) == 0) {
         // even D: rows are 8-byte (x) / 16-byte (tables) aligned -- two elements per load, two chains
         double acc1 = 0.0;
@@ -88,7 +108,7 @@ struct LseAcc {
 
 // The exact logsumexp (and MAP slot) of one embedding over the candidates the filter kept, by EIGHT lanes.
 // code (refine_decide): -1 the best chunk i1 suffices, >= 0 also visit chunk i2; masks as in Cand.
-template <bool ANISO>
+template <bool ANISO, int DC = 0>
 __device__ __forceinline__ LseAcc fv_exact_row8(const ModelRows &t, int Kr, int D, const float *xr, int i1, int i2,
                                                 uint32_t masks, int code, int j, unsigned gmask) {
     LseAcc acc;
@@ -103,7 +123,7 @@ __device__ __forceinline__ LseAcc fv_exact_row8(const ModelRows &t, int Kr, int 
             mk &= mk - 1;
             const int k = chunk * CHUNK + bit;
             if (k >= Kr) continue;
-            double q = quad_part<ANISO>(t, k, xr, D, j);
+            double q = quad_part<ANISO, DC>(t, k, xr, D, j);
             q += __shfl_xor_sync(gmask, q, 1);
             q += __shfl_xor_sync(gmask, q, 2);
             q += __shfl_xor_sync(gmask, q, 4);

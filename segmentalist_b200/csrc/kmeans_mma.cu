@@ -672,11 +672,13 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_rows_kernel(
 // (r[2c] + r[2c+1]) locally, then xor 1 and xor 2 inside the block's four lanes.
 // fp8: the records come from the e4m3 filter pass: x_err / w_max hold the e4m3 rounding-error norms of the scaled
 // operands (w_max = (e_mu, n_mu, e_bias, bias_max)) and the threshold is filter_tau8's.
-template <int MAXS>
+// DC: the embedding dimension when known at compile time (0 = runtime): the per-lane step counts, load offsets and the
+// n % 8 tail become constants, which removes the predicates and address arithmetic of the generic unrolled loops.
+template <int MAXS, int DC = 0>
 __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
     segb_kmeans m, const Cand *cand, const float *x_err, const float *w_max, int64_t n_emb, int n_chunks,
     float *best_val, int32_t *best_k, unsigned long long *n_fallback, int32_t *fb_list, int fp8 = 0) {
-    const int D = m.D, KM = m.K_max;
+    const int D = DC ? DC : m.D, KM = m.K_max;
     const int lane = threadIdx.x & 31, j = lane & 7;
     const Row8Geom geo(D, lane);
     const float *X = (const float *)m.X;
@@ -1294,7 +1296,11 @@ static int refine_rows_stage(const segb_kmeans *m, const void *cand, const float
         steps_max = longest / 8;
     }
     if (fp8 && !lanes8) { set_error("e4m3 filter records need an even D"); return SEGB_E_UNSUPPORTED; }
-    if (lanes8 && steps_max <= 8)
+    if (lanes8 && m->D == 130)               // the dimension of the BASELINE configurations, specialised
+        refine_rows8_kernel<8, 130><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
+            *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
+            (unsigned long long *)n_fallback, fb_list, fp8);
+    else if (lanes8 && steps_max <= 8)
         refine_rows8_kernel<8><<<(unsigned)blocks, REFINE_THREADS, 0, st>>>(
             *m, (const Cand *)cand, x_err, w_max, n_emb, k_pad(m->K_max) / CHUNK, best_val, best_k,
             (unsigned long long *)n_fallback, fb_list, fp8);
