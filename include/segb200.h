@@ -378,7 +378,9 @@ int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const void *w_ti
  *   x_tiles8 / w_tiles8: e4m3 tile images (segb_mma8_*_tiles_bytes), x_err8 [2 n_emb], x_max8 [2],
  *   w_err8 [4 (K_max + 128)], w_max8 [4] = (e_mu, n_mu, e_bias, bias_max) in the scaled space.
  * segb_mma8_refine: w_tiles16 / w_max16 from segb_mma_pack_means (the second level runs in fp16 over a compact image
- * converted on the fly from the fp32 rows: no resident fp16 image of X); work: segb_mma_refine2_work_bytes().     */
+ * converted on the fly from the fp32 rows: no resident fp16 image of X); work: segb_mma_refine2_work_bytes().
+ * The record's m1 / m2 / m3 are PACKED KEYS (chunk id in the low 12 mantissa bits of the chunk maximum; filter_tau8
+ * carries the 2^-11 relative term): segb_mma8_filter returns SEGB_E_UNSUPPORTED for K_max > 65536 -- use segb_mma_*. */
 int64_t segb_mma8_x_tiles_bytes(int64_t n_emb, int32_t D);
 int64_t segb_mma8_w_tiles_bytes(int32_t K_max, int32_t D);
 int segb_mma8_pack_x(const float *X, int64_t n_emb, int32_t D, float scale, void *x_tiles8, float *x_err8,
@@ -447,7 +449,8 @@ int segb_fvf_refine(const float *X, int64_t n_emb, int32_t D, int32_t K_max, int
  * fourth-best chunk -- a trained model; other rows take the exhaustive exact scan (n_fallback): callers watch that
  * count and go back to segb_fvf_* when it is not small.  Call order: segb_fvf_pack_model(aniso = 0) [exact row tables,
  * w_max16] -> segb_fvf8_pack_model -> segb_fvf8_filter -> segb_fvf8_refine.  log_marg_i / MAP slot / row records as
- * segb_fvf_refine.  w_err8: segb_fvf8_w_err_bytes(); w_max8 [8].                                                        */
+ * segb_fvf_refine.  w_err8: segb_fvf8_w_err_bytes(); w_max8 [8].  Packed top-3 keys as in segb_mma8_filter
+ * (lse_bound8 carries their term): K_max + 1 <= 65536.                                                                  */
 int64_t segb_fvf8_x_tiles_bytes(int64_t n_emb, int32_t D);
 int64_t segb_fvf8_w_tiles_bytes(int32_t K_max, int32_t D);
 int64_t segb_fvf8_w_err_bytes(int32_t K_max);

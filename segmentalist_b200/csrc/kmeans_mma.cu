@@ -762,11 +762,11 @@ __global__ void __launch_bounds__(256) gather_undecided_kernel(const uint8_t *x_
 // eight lanes per undecided row: exact score (same routine and bits as refine_rows8_kernel) of every component
 // flagged in the row's bitmap, first maximum in component order.  A row with an empty bitmap (cannot happen for
 // finite data; NaN scores) goes to the exhaustive scan through unres_list.
-template <int MAXS>
+template <int MAXS, int DC = 0>           // DC: the dimension when known at compile time (see refine_rows8_kernel)
 __global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
     segb_kmeans m, const int32_t *fb_list, const unsigned long long *n_fallback, int64_t first, int64_t rows_cap,
     const uint32_t *bitmap, int n_words, float *best_val, int32_t *best_k, unsigned long long *n_unres, int32_t *unres_list) {
-    const int D = m.D, KM = m.K_max;
+    const int D = DC ? DC : m.D, KM = m.K_max;
     const int lane = threadIdx.x & 31, j = lane & 7;
     const Row8Geom geo(D, lane);
     const float *X = (const float *)m.X;
@@ -1392,7 +1392,10 @@ extern "C" int segb_mma_refine2(const segb_kmeans *m, const void *x_tiles, const
         SEGB_LAUNCH_CHECK();
         rc = launch_filter_impl(f, n_fb, first, cap, thr, bitmap, st);
         if (rc) return rc;
-        if (row8_steps_max(m->D) <= 8)
+        if (m->D == 130)
+            refine_bitmap_kernel<8, 130><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words, best_val,
+                                                                             best_k, n_unres, unres_list);
+        else if (row8_steps_max(m->D) <= 8)
             refine_bitmap_kernel<8><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words, best_val,
                                                                         best_k, n_unres, unres_list);
         else
@@ -1481,7 +1484,10 @@ extern "C" int segb_mma8_refine(const segb_kmeans *m, const void *cand, const fl
         SEGB_LAUNCH_CHECK();
         rc = launch_filter_impl(f, n_fb, first, cap, thr, bitmap, st);
         if (rc) return rc;
-        if (row8_steps_max(m->D) <= 8)
+        if (m->D == 130)
+            refine_bitmap_kernel<8, 130><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words, best_val,
+                                                                             best_k, n_unres, unres_list);
+        else if (row8_steps_max(m->D) <= 8)
             refine_bitmap_kernel<8><<<148 * 8, REFINE_THREADS, 0, st>>>(*m, fb_list, n_fb, first, cap, bitmap, n_words, best_val,
                                                                         best_k, n_unres, unres_list);
         else
