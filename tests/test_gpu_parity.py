@@ -669,6 +669,35 @@ def test_mma_scorer_nan_rows(sb, precision):
     assert np.isnan(val.cpu().numpy()[bad]).all()
 
 
+def test_mma_scorer_fp8_needs_12_bit_chunk_ids(sb):
+    """The e4m3 pass packs chunk ids into 12 mantissa bits of its top-3 keys: beyond K_max = 65536 the C entry point
+    refuses (SEGB_E_UNSUPPORTED -> AssertionError) and MmaScorer(precision="fp8") quietly takes the fp16 first level."""
+    from segmentalist_b200 import _lib, synth
+    from segmentalist_b200.batch import MmaScorer
+    from segmentalist_b200.kmeans_components import KMeansComponents
+    rng = np.random.RandomState(5)
+    K_max, n_emb = 65536 + 128, 3000
+    X = synth._unit_rows(rng.standard_normal((n_emb, 130)).astype(np.float32))
+    assign = -np.ones(n_emb, dtype=np.int64)
+    assign[:2000] = np.arange(2000)
+    np.random.seed(1)
+    comps = KMeansComponents(X, assign, K_max)
+    val_e, arg_e = comps.best(None)
+    mma = MmaScorer(comps, precision="fp8")
+    assert not mma.fp8
+    val = torch.empty(n_emb, dtype=torch.float32, device="cuda")
+    arg = torch.empty(n_emb, dtype=torch.int32, device="cuda")
+    mma.score(val, arg)
+    torch.cuda.synchronize()
+    npt.assert_array_equal(arg.cpu().numpy(), arg_e.cpu().numpy())
+    npt.assert_array_equal(val.cpu().numpy(), val_e.cpu().numpy())
+    lib = _lib.lib()
+    dummy = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+    with pytest.raises(AssertionError):
+        _lib.check(lib.segb_mma8_filter(_lib.ptr(dummy), _lib.ptr(dummy), 256, K_max, 130, _lib.ptr(dummy), _lib.ptr(dummy),
+                                        _lib.ptr(dummy), _lib.stream_ptr()))
+
+
 def test_frozen_sweep_auto_precision_policy(sb):
     """precision="auto": a diffuse model (many near-duplicate components) leaves most rows to the second level, so the
     sweep falls back to the fp16 first level, retries e4m3 after AUTO_RETRY_SWEEPS sweeps, falls back again with a
