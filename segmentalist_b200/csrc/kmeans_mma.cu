@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) kmeans_filter_kernel(FilterParam
     constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, MMA_DONE = 12, ACC_EMPTY = 20, B_EMPTY0 = 22, N_BARS = 23;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     float4 *merge = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [MT_ROWS][2] partial top-3
-    // F8: parked scores of every epilogue thread's current best chunk (top3_insert_snap), 4 x 512 float4 = 32 KB
+    // F8: parked scores of every epilogue thread's current best chunk (top3_insert_key), 4 x 512 float4 = 32 KB
     float4 *snap_all = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(bars) + 256 + (size_t)MT_ROWS * 32);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };

@@ -320,32 +320,17 @@ __device__ __forceinline__ void top3_merge(float cm, int cid, uint32_t mk, float
     }
 }
 
-// The same insertion with the member mask DEFERRED: a chunk that becomes the new best only parks its 16 scores in a
-// per-thread shared-memory slot (four 16-byte stores; snap[q * SNAP_STRIDE] with consecutive threads 16 bytes apart:
+// The e4m3 pass defers the member mask: a chunk that becomes the new best only parks its 16 scores in a per-thread
+// shared-memory slot (four 16-byte stores; snap[q * SNAP_STRIDE] with consecutive threads 16 bytes apart:
 // conflict-free), and the mask is formed once per row and work item by top3_snapshot_mask.  A new-best event costs
 // the WHOLE warp ~8 instructions instead of ~38 (16 x (FADD + SHF)) -- and with 32 independent rows per warp such
 // events hit 45 % of all chunk visits.  A best chunk that is demoted to runner-up keeps all 16 members.
 constexpr int SNAP_STRIDE = 512;      // float4 slots per quarter: one per epilogue thread
-__device__ __forceinline__ void top3_insert_snap(const float *vv, float cm, int cid, float4 *snap, float &m1, float &m2,
-                                                 float &m3, int &i1, int &i2) {
-    const bool p2 = cm > m2;
-    m3 = p2 ? m2 : fmaxf(m3, cm);
-    if (cm > m1) {
-        snap[0 * SNAP_STRIDE] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        snap[1 * SNAP_STRIDE] = make_float4(vv[4], vv[5], vv[6], vv[7]);
-        snap[2 * SNAP_STRIDE] = make_float4(vv[8], vv[9], vv[10], vv[11]);
-        snap[3 * SNAP_STRIDE] = make_float4(vv[12], vv[13], vv[14], vv[15]);
-        m2 = m1; i2 = i1;
-        m1 = cm; i1 = cid;
-    } else {
-        m2 = p2 ? cm : m2; i2 = p2 ? cid : i2;
-    }
-}
 // The e4m3 pass's insertion: the running top-3 are three PACKED KEYS a1 >= a2 >= a3 -- the chunk maximum with the
 // chunk id in its low KEY_ID_BITS mantissa bits (filter_tau8 / lse_bound8 carry the 2^-11 relative term this costs).
 // Keys of different chunks differ, a key orders like its maximum, and the id travels with the value, so the update
-// is a five-instruction min / max network instead of compares and selects on (value, id) pairs; the new-best
-// snapshot is as in top3_insert_snap.  cm must not be NaN (chunk_max16_floor).
+// is a five-instruction min / max network instead of compares and selects on (value, id) pairs; a new best parks its
+// scores in the snapshot slot (four predicated stores).  cm must not be NaN (chunk_max16_floor).
 __device__ __forceinline__ void top3_insert_key(const float *vv, float cm, uint32_t cid, float4 *snap, float &a1, float &a2,
                                                 float &a3) {
     const float key = __uint_as_float((__float_as_uint(cm) & ~KEY_ID_MASK) | cid);
