@@ -99,6 +99,6 @@ for _ in range(5):
         sw.flags_h.copy_(sw.flags, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return [int(v) for v in sw.flags_h.tolist()]
-    n_bad, n_fb, K_now = step("tail", tail, acc)
+    n_bad, n_fb, K_now = step("tail", tail, acc)[:3]
     step("cumsum", lambda: float(np.cumsum(sw.log_prob_h.numpy())[-1]), acc)
 print({k: round(v / 5, 3) for k, v in acc.items()}, "K_host", sw.K_host, "K_max", comps.K_max)
