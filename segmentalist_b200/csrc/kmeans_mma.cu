@@ -697,6 +697,8 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
         const float2 xe = xe_next;
         float2 xv[MAXS];
         km_load_x8<MAXS>(X + row * D, geo, xv);
+        float2 xt[ROW8_TAIL];
+        km_load_xtail8(X + row * D, geo, xt);
         const int64_t row_n = row + grp_total;
         if (row_n < n_emb) { cd_next = cand[row_n]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * row_n); }
         const float tau = fp8 ? filter_tau8(xe.x, xe.y, e_mu, n_mu, w_max[2], w_max[3], D) : filter_tau(xe.x, xe.y, e_mu, n_mu, D);
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(REFINE_THREADS, 4) refine_rows8_kernel(
         }
         float bv;
         int bk;
-        km_exact_row8<MAXS>(means, KM, D, X + row * D, xv, cd.i1, cd.i2, cd.masks, code, geo, bv, bk);
+        km_exact_row8<MAXS>(means, KM, D, X + row * D, xv, cd.i1, cd.i2, cd.masks, code, geo, bv, bk, xt);
         if (j == 0) { best_val[row] = bv; best_k[row] = (bk == 0x7fffffff) ? -1 : bk; }
     }
 }
@@ -780,6 +782,8 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
         const int64_t row = fb_list[i];
         float2 xv[MAXS];
         km_load_x8<MAXS>(X + row * D, geo, xv);
+        float2 xt[ROW8_TAIL];
+        km_load_xtail8(X + row * D, geo, xt);
         const uint32_t *bm = bitmap + i * n_words;
         float bv = -CUDART_INF_F;
         int bk = 0x7fffffff;
@@ -793,7 +797,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
                     const int k = (w0 + t) * 32 + (__ffs(bits) - 1);
                     bits &= bits - 1;
                     if (k >= KM) continue;
-                    const float v = km_exact_one8<MAXS>(means, D, X + row * D, xv, k, geo);
+                    const float v = km_exact_one8<MAXS>(means, D, X + row * D, xv, k, geo, xt);
                     if (v > bv || bk == 0x7fffffff) { bv = v; bk = k; }          // k ascending: first maximum
                 }
             }

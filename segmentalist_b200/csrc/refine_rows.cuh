@@ -53,13 +53,30 @@ __device__ __forceinline__ void km_load_x8(const float *xr, const Row8Geom &q, f
 #pragma unroll
     for (int i = 0; i < MAXS; ++i) xv[i] = (i < q.steps) ? xr2[i * 4] : make_float2(0.f, 0.f);
 }
+// The block's n % 8 trailing elements (an even count <= 6 for even D: 8-byte loads), requested WITH the row's other
+// loads: read one at a time inside km_exact_one8's tail loop they were a second DRAM round trip on the row's
+// dependent chain (the row's last sector is touched by no other load).
+constexpr int ROW8_TAIL = 3;
+__device__ __forceinline__ void km_load_xtail8(const float *xr, const Row8Geom &q, float2 *xt) {
+    const float2 *t2 = reinterpret_cast<const float2 *>(xr + q.lo_g + q.n8_g);
+    const int n_t = q.n_g - q.n8_g;
+#pragma unroll
+    for (int t = 0; t < ROW8_TAIL; ++t) xt[t] = (2 * t < n_t) ? t2[t] : make_float2(0.f, 0.f);
+}
 
 // exact score of ONE component for the row held in xv (result on all 8 lanes of the group)
 template <int MAXS>
 __device__ __forceinline__ float km_exact_one8(const float *means, int D, const float *xr, const float2 *xv, int k,
-                                               const Row8Geom &q) {
+                                               const Row8Geom &q, const float2 *xt = nullptr) {
     const float *mu = means + (size_t)k * D;
     const float2 *mu2 = reinterpret_cast<const float2 *>(mu + q.lo_g + 2 * q.c);
+    float2 mt[ROW8_TAIL];
+    if (xt) {                                                        // the mean row's trailing elements, with its other loads
+        const float2 *t2 = reinterpret_cast<const float2 *>(mu + q.lo_g + q.n8_g);
+        const int n_t = q.n_g - q.n8_g;
+#pragma unroll
+        for (int t = 0; t < ROW8_TAIL; ++t) mt[t] = (2 * t < n_t) ? t2[t] : make_float2(0.f, 0.f);
+    }
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXS; ++i) {
@@ -75,9 +92,20 @@ __device__ __forceinline__ float km_exact_one8(const float *means, int D, const 
     acc = __fadd_rn(acc, __shfl_xor_sync(q.gmask, acc, 1));
     acc = __fadd_rn(acc, __shfl_xor_sync(q.gmask, acc, 2));
     if (q.n8_g == 0) acc = 0.f;
-    for (int d = q.lo_g + q.n8_g; d < q.lo_g + q.n_g; ++d) {         // the block's n % 8 trailing terms
-        const float dl = __fsub_rn(mu[d], xr[d]);
-        acc = __fadd_rn(acc, __fmul_rn(dl, dl));
+    if (xt) {                                                        // the block's n % 8 trailing terms, in order
+        const int n_t = q.n_g - q.n8_g;
+#pragma unroll
+        for (int t = 0; t < ROW8_TAIL; ++t)
+            if (2 * t < n_t) {
+                const float d0 = __fsub_rn(mt[t].x, xt[t].x), d1 = __fsub_rn(mt[t].y, xt[t].y);
+                acc = __fadd_rn(acc, __fmul_rn(d0, d0));
+                acc = __fadd_rn(acc, __fmul_rn(d1, d1));
+            }
+    } else {
+        for (int d = q.lo_g + q.n8_g; d < q.lo_g + q.n_g; ++d) {
+            const float dl = __fsub_rn(mu[d], xr[d]);
+            acc = __fadd_rn(acc, __fmul_rn(dl, dl));
+        }
     }
     float tot = __shfl_sync(q.gmask, acc, q.gbase);
     if (q.two_blocks) tot = __fadd_rn(tot, __shfl_sync(q.gmask, acc, q.gbase + 4));
@@ -87,7 +115,7 @@ __device__ __forceinline__ float km_exact_one8(const float *means, int D, const 
 template <int MAXS>
 __device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D, const float *xr, const float2 *xv,
                                               int i1, int i2, uint32_t masks, int code, const Row8Geom &q, float &bv,
-                                              int &bk) {
+                                              int &bk, const float2 *xt = nullptr) {
     bv = -CUDART_INF_F;
     bk = 0x7fffffff;
 #pragma unroll 1
@@ -99,7 +127,7 @@ __device__ __forceinline__ void km_exact_row8(const float *means, int KM, int D,
             mk &= mk - 1;
             const int k = chunk * CHUNK + bit;
             if (k >= KM) continue;
-            const float v = km_exact_one8<MAXS>(means, D, xr, xv, k, q);
+            const float v = km_exact_one8<MAXS>(means, D, xr, xv, k, q, xt);
             if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; }
         }
     }
