@@ -426,7 +426,10 @@ __global__ void __launch_bounds__(REFINE_THREADS) fv_refine_kernel(
         const Cand cd = cd_next;
         const float2 xe = xe_next;
         const int64_t row_n = row + grp_total;
-        if (row_n < n_emb) { cd_next = cand[row_n]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * row_n); }
+        if (row_n < n_emb) {
+            cd_next = cand[row_n]; xe_next = *reinterpret_cast<const float2 *>(x_err + 2 * row_n);
+            prefetch_row_l2(X + row_n * D, D, j);           // the next row's embedding -> L2 (no registers)
+        }
         const float tau = fp8 ? lse_tau8(xe.x, xe.y, W8{w_max[0], w_max[1], w_max[2], w_max[3], w_max[4], w_max[5], w_max[6], w_max[7]},
                                          sx, alpha, D, T)
                               : lse_tau(xe.x, xe.y, w4, KP, T);
