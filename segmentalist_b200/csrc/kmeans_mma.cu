@@ -778,12 +778,14 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
     fb_list += first;
     const int64_t grp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int64_t grp_total = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    int64_t row_next = grp_global < n ? fb_list[grp_global] : 0;
     for (int64_t i = grp_global; i < n; i += grp_total) {
-        const int64_t row = fb_list[i];
+        const int64_t row = row_next;
         float2 xv[MAXS];
         km_load_x8<MAXS>(X + row * D, geo, xv);
         float2 xt[ROW8_TAIL];
         km_load_xtail8(X + row * D, geo, xt);
+        if (i + grp_total < n) row_next = fb_list[i + grp_total];      // consumed (and its row prefetched) at the end of this iteration
         const uint32_t *bm = bitmap + i * n_words;
         float bv = -CUDART_INF_F;
         int bk = 0x7fffffff;
@@ -806,6 +808,8 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_bitmap_kernel(
             if (bk == 0x7fffffff) unres_list[atomicAdd(n_unres, 1ull)] = (int32_t)row;
             else { best_val[row] = bv; best_k[row] = bk; }
         }
+        // the list sends the groups to scattered rows: the next one's embedding is pulled into L2 ahead of its loads
+        if (i + grp_total < n) prefetch_row_l2(X + row_next * D, D, j);
     }
 }
 
