@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(256) km_update_utt_kernel(segb_kmeans m, segb_
 
 // ---- frozen-state sweep pieces: one warp per utterance
 
+// The walk over an utterance's boundaries used to be one position at a time with a chain of four dependent loads per
+// token (boundary flag -> segment id -> winner -> embedding row; ncu: ~29 warps stalled on loads per issue).  Now a
+// lane owns a position: flags, segment ids and winners of 32 positions are fetched side by side, the token rows are
+// pulled into L2 as soon as their ids are known, and the warp then adds them one token at a time.
 template <typename T>
 __global__ void __launch_bounds__(128) km_collect_kernel(segb_kmeans m, segb_corpus c, int utt_first, int n_utt,
                                                          const int32_t *best_k, double *sum_x,
@@ -292,21 +296,34 @@ __global__ void __launch_bounds__(128) km_collect_kernel(segb_kmeans m, segb_cor
     const int u = utt_first + w;
     const int64_t off = c.pos_off[u];
     const int N = (int)(c.pos_off[u + 1] - off);
-    int j_prev = 0;
-    for (int j = 0; j < N; ++j) {
-        const bool b = c.bounds[off + j];
-        int id = -1;
+    const unsigned FULLM = 0xffffffffu;
+    int j_prev = 0;                                   // start of the open segment, carried across 32-position pieces
+    for (int base = 0; base < N; base += 32) {
+        const int j = base + lane;
+        const bool b = j < N && c.bounds[off + j];
+        const unsigned bm = __ballot_sync(FULLM, b);
+        int id = -1, k = -1;
         if (b) {
-            const int t = j + 1, l = t - j_prev;
-            j_prev = j + 1;
-            if (l <= c.S) id = c.seg_id[(off + t - 1) * c.S + (l - 1)];
+            const unsigned below = bm & ((1u << lane) - 1u);
+            const int start = below ? base + (31 - __clz(below)) + 1 : j_prev;
+            const int l = j + 1 - start;
+            if (l <= c.S) id = c.seg_id[(off + j) * c.S + (l - 1)];
+            if (id >= 0) {
+                const char *row = reinterpret_cast<const char *>(KM<T>::X(m) + (size_t)id * m.D);
+                for (int o = 0; o < (int)sizeof(T) * m.D; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+                k = best_k[id];
+            }
         }
-        if (lane == 0) c.tok_id[off + j] = id;
-        if (id >= 0) {
-            const int k = best_k[id];
-            if (lane == 0) { m.assignments[id] = k; atomicAdd(&cnt[k], 1ull); }
+        if (j < N) c.tok_id[off + j] = id;
+        if (id >= 0) { m.assignments[id] = k; atomicAdd(&cnt[k], 1ull); }
+        if (bm) j_prev = base + (31 - __clz(bm)) + 1;
+        unsigned tm = __ballot_sync(FULLM, id >= 0);
+        while (tm) {                                  // one token at a time, the whole warp on its row
+            const int src = __ffs(tm) - 1;
+            tm &= tm - 1;
+            const int tid = __shfl_sync(FULLM, id, src), tk = __shfl_sync(FULLM, k, src);
             for (int d = lane; d < m.D; d += 32)
-                atomicAdd(&sum_x[(size_t)k * m.D + d], (double)KM<T>::X(m)[(size_t)id * m.D + d]);
+                atomicAdd(&sum_x[(size_t)tk * m.D + d], (double)KM<T>::X(m)[(size_t)tid * m.D + d]);
         }
     }
 }
