@@ -163,15 +163,29 @@ __global__ void clamp_apply_kernel(const int32_t *list_id, const int32_t *out_k,
 __global__ void __launch_bounds__(256) fv_collect_kernel(const float *X, int D, segb_corpus c, int64_t pos_first,
                                                          int64_t n_positions, const int32_t *choice, double *sum_x,
                                                          unsigned long long *cnt) {
+    // a lane per position: token ids and choices of 32 positions are fetched side by side and the token rows pulled
+    // into L2 as soon as their ids are known (a warp per position walked the chain id -> choice -> row serially);
+    // then the warp adds the rows one token at a time
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = w; p < n_positions; p += nw) {
-        const int id = c.tok_id[pos_first + p];
-        if (id < 0) continue;
-        const int k = choice[id];
-        if (lane == 0) atomicAdd(&cnt[k], 1ull);
-        for (int d = lane; d < D; d += 32) atomicAdd(&sum_x[(size_t)k * D + d], (double)X[(size_t)id * D + d]);
+    for (int64_t base = w * 32; base < n_positions; base += nw * 32) {
+        const int64_t p = base + lane;
+        const int id = p < n_positions ? c.tok_id[pos_first + p] : -1;
+        int k = -1;
+        if (id >= 0) {
+            const char *row = reinterpret_cast<const char *>(X + (size_t)id * D);
+            for (int o = 0; o < 4 * D; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+            k = choice[id];
+            atomicAdd(&cnt[k], 1ull);
+        }
+        unsigned tm = __ballot_sync(0xffffffffu, id >= 0);
+        while (tm) {
+            const int src = __ffs(tm) - 1;
+            tm &= tm - 1;
+            const int tid = __shfl_sync(0xffffffffu, id, src), tk = __shfl_sync(0xffffffffu, k, src);
+            for (int d = lane; d < D; d += 32) atomicAdd(&sum_x[(size_t)tk * D + d], (double)X[(size_t)tid * D + d]);
+        }
     }
 }
 
@@ -400,7 +414,7 @@ extern "C" int segb_fixedvar_frozen_collect(const segb_fixedvar *m, const segb_c
     SEGB_CHECK_ARG(!m->x_is_f64, "frozen FBGMM sweep: float32 embeddings");
     SEGB_CHECK_ARG(pos_first >= 0 && n_positions >= 0 && pos_first + n_positions <= c->n_pos, "position range");
     if (n_positions == 0) return 0;
-    int64_t blocks = (n_positions * 32 + 255) / 256;
+    int64_t blocks = (n_positions + 255) / 256;         // a lane per position
     if (blocks > 148 * 16) blocks = 148 * 16;
     fv_collect_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float *)m->X, m->D, *c, pos_first,
                                                                           n_positions, choice, sum_x,
