@@ -439,6 +439,32 @@ def test_unigram_diag_golden(sb):
     npt.assert_allclose(rec["log_prob_z"], z["rec_log_prob_z"], rtol=1e-10)
 
 
+def test_frozen_sweeps_long_utterances_vs_oracle(sb):
+    """Utterances longer than a warp (40-70 landmarks): the token collection walks them in 32-position pieces with the
+    open segment's start carried across pieces (km_collect_kernel).  Three frozen k-means sweeps against the oracle's
+    pure functions: objective, boundaries, assignments, counts, means."""
+    from oracle import seg_oracle as so
+    from segmentalist_b200 import kmeans_acoustic_wordseg as kaw, synth
+    mats, vids, durs, lms = synth.make_corpus_dicts(24, D=130, K_true=10, n_min=40, n_max=70, n_slices_max=6, seed=17)
+    assert max(len(v) for v in lms.values()) > 40
+
+    def seeded():
+        random.seed(3)
+        np.random.seed(3)
+    seeded()
+    seg = kaw.KMeansAcousticWordseg(10, mats, vids, durs, lms, n_slices_max=6, init_am_assignments="spread")
+    seeded()
+    ora = so.SegmentalKMeansWordseg(10, mats, vids, durs, lms, n_slices_max=6, init_am_assignments="spread")
+    for _ in range(3):
+        rec = seg.segment_frozen(1, scorer="mma")
+        total, _ = so.frozen_kmeans_sweep(ora)
+        assert rec["sum_neg_len_sqrd_norm"][0] == total
+        npt.assert_array_equal(seg.utterances.boundaries, ora.utterances.boundaries)
+        npt.assert_array_equal(seg.acoustic_model.components.assignments, ora.acoustic_model.components.assignments)
+        npt.assert_array_equal(seg.acoustic_model.components.means, ora.acoustic_model.components.means)
+        npt.assert_array_equal(seg.acoustic_model.components.counts, ora.acoustic_model.components.counts)
+
+
 @pytest.mark.parametrize("init", ["spread", "rand"])
 def test_kmeans_wordseg_golden(sb, init):
     """BASELINE config 1: sequential segment() and the frozen sweep vs the reference."""
